@@ -1,0 +1,122 @@
+"""ctypes binding of libao_pointops.so (C ABI declared in include/ao_pointops.h).
+
+This is the ONLY compute path of the package: there is no CPU or torch fallback.  If the shared
+library is missing or does not export a symbol, importing/using the ops fails loudly.
+
+The reference binds its kernels through a pybind11 torch extension `pointops._C`
+(/root/reference/libs/pointops/src/pointops_api.cpp:15-32) whose functions take at::Tensor and
+forward `data_ptr()` to `extern "C"` launchers; here the same raw-pointer launch boundary is the
+public C ABI and Python forwards `tensor.data_ptr()` + the current CUDA stream.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_void_p
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.environ.get("AO_POINTOPS_LIB", os.path.join(_HERE, "lib", "libao_pointops.so"))
+
+P = c_void_p  # device pointer / stream
+
+# name -> (restype, argtypes); must list every function of include/ao_pointops.h
+SIGNATURES = {
+    "aopt_version": (c_char_p, []),
+    "aopt_status_string": (c_char_p, [c_int]),
+    "aopt_last_cuda_error": (c_char_p, []),
+    "aopt_offset2batch": (c_int, [c_int, c_int, P, P, P]),
+    "aopt_knn_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
+    "aopt_knn_query": (c_int, [c_int, c_int, c_int, c_int, P, P, P, P, P, P, c_int, P, c_size_t, P]),
+    "aopt_csr_workspace_bytes": (c_size_t, [c_int, c_int64]),
+    "aopt_csr_build": (c_int, [c_int, c_int64, P, c_int, P, P, P, c_size_t, P]),
+    "aopt_grouping_forward": (c_int, [c_int, c_int, c_int, P, P, P, c_int, P]),
+    "aopt_grouping_backward": (c_int, [c_int, c_int, P, c_int, P, P, c_float, P, P]),
+    "aopt_group_xyz": (c_int, [c_int, c_int, P, P, P, P, c_int, P]),
+    "aopt_gather_sub_forward": (c_int, [c_int, c_int, c_int, P, P, P, P, P]),
+    "aopt_sum_over_k": (c_int, [c_int, c_int, c_int, P, c_float, P, P]),
+    "aopt_gva_forward": (c_int, [c_int, c_int, c_int, c_int, P, P, P, P, P, P, P]),
+    "aopt_gva_backward_query": (c_int, [c_int, c_int, c_int, c_int, P, P, P, P, P, P, P, P]),
+    "aopt_gva_backward_value": (c_int, [c_int, c_int, c_int, c_int, P, P, P, P, P, P]),
+    "aopt_segment_min3": (c_int, [c_int, c_int, P, P, P, P]),
+    "aopt_voxel_keys": (c_int, [c_int, c_int, P, P, P, c_float, P, P, P]),
+    "aopt_pool_forward": (c_int, [c_int, c_int, P, P, P, P, P, P, P, P]),
+    "aopt_pool_backward": (c_int, [c_int, c_int, P, P, P, P, P]),
+    "aopt_interp_weights": (c_int, [c_int, c_int, P, P, P]),
+    "aopt_interpolation_forward": (c_int, [c_int, c_int, c_int, c_int, P, P, P, P, P]),
+    "aopt_interpolation_backward": (c_int, [c_int, c_int, c_int, P, P, P, P, P, P]),
+    "aopt_aggregation_forward": (c_int, [c_int, c_int, c_int, c_int, P, P, P, P, P, P]),
+    "aopt_aggregation_backward": (c_int, [c_int, c_int, c_int, c_int, P, P, P, P, P, P, P, P, P, P, P]),
+    "aopt_subtraction_forward": (c_int, [c_int, c_int, c_int, P, P, P, P, P]),
+}
+
+KNN_AUTO, KNN_TILE, KNN_GRID = 0, 1, 2
+
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    """Loads the shared library (once) and declares every signature.  Raises if anything is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"ao_b200: {LIB_PATH} not found. Build it with `make -C ao_b200/csrc` "
+            "(or `python -c 'import __graft_entry__ as g; g.build()'`). There is no fallback path."
+        )
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (restype, argtypes) in SIGNATURES.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError as e:  # pragma: no cover - build/ABI mismatch
+            raise ImportError(f"ao_b200: {LIB_PATH} does not export {name}") from e
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def version() -> str:
+    return load().aopt_version().decode()
+
+
+def check(status: int, what: str) -> None:
+    if status != 0:
+        lib = load()
+        msg = lib.aopt_status_string(status).decode()
+        if status == 3:
+            msg += f" ({lib.aopt_last_cuda_error().decode()})"
+        raise RuntimeError(f"ao_b200.{what} failed: {msg}")
+
+
+def stream() -> int:
+    """The caller's current CUDA stream (the reference launches on the legacy default stream)."""
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t) -> int:
+    return 0 if t is None else t.data_ptr()
+
+
+def require_cuda(*tensors) -> torch.device:
+    """All tensors must live on one CUDA device — the product path has no CPU implementation."""
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise ValueError("ao_b200.pointops: expected CUDA tensors (there is no CPU path)")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise ValueError("ao_b200.pointops: tensors are on different devices")
+    if dev is None:
+        raise ValueError("ao_b200.pointops: no tensor arguments")
+    return dev
+
+
+def workspace(nbytes: int, device) -> torch.Tensor:
+    """Scratch from torch's caching allocator (the library itself never allocates)."""
+    return torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=device)

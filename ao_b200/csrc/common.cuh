@@ -1,0 +1,106 @@
+// common.cuh — shared device helpers for libao_pointops (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/ao_pointops.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libao_pointops is written for sm_100a (B200); no other architecture is supported"
+#endif
+
+namespace aopt {
+
+constexpr int kNumSM = 148;  // B200: 2 dies x 74 SMs; grids are sized in multiples of this
+
+// Records the launch error for aopt_last_cuda_error() and maps it to a status.
+int check_launch();
+
+inline cudaStream_t as_stream(aopt_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+inline int div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// Grid for a grid-stride loop over `work` items: enough CTAs to cover the work once, capped at
+// `ctas_per_sm` resident CTAs on each of the 148 SMs (so big problems run as full waves).
+inline int stride_grid(long long work, int block, int ctas_per_sm) {
+    long long need = (work + block - 1) / block;
+    long long cap = (long long)kNumSM * ctas_per_sm;
+    if (need < 1) need = 1;
+    return (int)(need < cap ? need : cap);
+}
+
+inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// ---- 128-bit global memory access with cache hints -------------------------------------------
+// Streaming (touched once) data bypasses L1 so that the gathered rows keep the cache.
+__device__ __forceinline__ float4 ldg_stream4(const float *p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void stg_stream4(float *p, const float4 &v) {
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x),
+                 "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+__device__ __forceinline__ float ldg_stream1(const float *p) {
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void stg_stream1(float *p, float v) {
+    asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+// Gathered rows: read-only path, default caching (re-used across neighbouring queries).
+__device__ __forceinline__ float4 ldg_gather4(const float *p) {
+    return __ldg(reinterpret_cast<const float4 *>(p));
+}
+
+// A VEC-wide channel chunk (VEC = 4: one 128-bit access; VEC = 1: scalar fallback for widths that
+// are not a multiple of 4 or for mis-aligned strides such as the (m,k,3+c) concatenated layout).
+template <int VEC>
+struct Chunk;
+template <>
+struct Chunk<4> {
+    float4 v;
+    __device__ __forceinline__ static Chunk zero() { return {make_float4(0.f, 0.f, 0.f, 0.f)}; }
+    __device__ __forceinline__ static Chunk gather(const float *p) { return {ldg_gather4(p)}; }
+    __device__ __forceinline__ static Chunk stream(const float *p) { return {ldg_stream4(p)}; }
+    __device__ __forceinline__ void store_stream(float *p) const { stg_stream4(p, v); }
+    __device__ __forceinline__ void store(float *p) const { *reinterpret_cast<float4 *>(p) = v; }
+    __device__ __forceinline__ void add(const Chunk &o) { v.x += o.v.x; v.y += o.v.y; v.z += o.v.z; v.w += o.v.w; }
+    __device__ __forceinline__ void sub(const Chunk &o) { v.x -= o.v.x; v.y -= o.v.y; v.z -= o.v.z; v.w -= o.v.w; }
+    __device__ __forceinline__ void scale(float s) { v.x *= s; v.y *= s; v.z *= s; v.w *= s; }
+    __device__ __forceinline__ void fma(const Chunk &a, float s) {
+        v.x = fmaf(a.v.x, s, v.x); v.y = fmaf(a.v.y, s, v.y); v.z = fmaf(a.v.z, s, v.z); v.w = fmaf(a.v.w, s, v.w);
+    }
+};
+template <>
+struct Chunk<1> {
+    float v;
+    __device__ __forceinline__ static Chunk zero() { return {0.f}; }
+    __device__ __forceinline__ static Chunk gather(const float *p) { return {__ldg(p)}; }
+    __device__ __forceinline__ static Chunk stream(const float *p) { return {ldg_stream1(p)}; }
+    __device__ __forceinline__ void store_stream(float *p) const { stg_stream1(p, v); }
+    __device__ __forceinline__ void store(float *p) const { *p = v; }
+    __device__ __forceinline__ void add(const Chunk &o) { v += o.v; }
+    __device__ __forceinline__ void sub(const Chunk &o) { v -= o.v; }
+    __device__ __forceinline__ void scale(float s) { v *= s; }
+    __device__ __forceinline__ void fma(const Chunk &a, float s) { v = fmaf(a.v, s, v); }
+};
+
+// Fast division of a 64-bit work index by a small runtime constant (channel chunks per row):
+// done once per item; the kernels are HBM-bound so a hardware divide is far below the issue budget.
+struct RowCol {
+    long long row;
+    int col;
+};
+__device__ __forceinline__ RowCol split(long long t, int cols) {
+    RowCol rc;
+    rc.row = t / cols;
+    rc.col = (int)(t - rc.row * cols);
+    return rc;
+}
+
+}  // namespace aopt

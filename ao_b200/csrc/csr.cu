@@ -1,0 +1,111 @@
+// csr.cu — transpose of the neighbour graph: for every source point j the list of flat
+// (query, slot) positions p = m*k+s that reference it, in ascending p.
+//
+// This is what makes every backward of the path atomic-free and run-to-run deterministic.  The
+// reference scatters gradients with float atomicAdd
+// (libs/pointops/src/grouping/grouping_cuda_kernel.cu:24, interpolation_cuda_kernel.cu:31,
+// aggregation_cuda_kernel.cu:35-37), which is contended on hub points and non-deterministic.
+// One CSR is built per kNN result and shared by all blocks of a BlockSequence
+// (pointcept/models/point_transformer_v2/point_transformer_v2m2_base.py:223-225 reuses one
+// reference_index for every block).
+//
+// Steps (all on the caller's stream, integer work only):
+//   1. count[j]   += 1 per entry            (int atomics: the counts are order-independent)
+//   2. rowptr      = exclusive scan(count)  (scan.cu)
+//   3. tmp[cursor++] = p                    (int atomic cursor: order inside a row is arbitrary)
+//   4. rank every entry inside its row by the value of p (all-pairs count inside the row, rows are
+//      ~k long) and write perm[rowptr[j] + rank] = p   → ascending p, deterministic.
+// Workspace: count/cursor (n_src+1 ints) + tmp (n_entries ints) + scan partials.
+#include "common.cuh"
+#include "scan.cuh"
+
+namespace aopt {
+
+constexpr int kBlock = 256;
+
+__device__ __forceinline__ int wrap_index(int j, int n_src, int negative_mode) {
+    return (j < 0 && negative_mode == 1) ? j + n_src : j;
+}
+
+__global__ void __launch_bounds__(kBlock)
+csr_count_kernel(long long n_entries, int n_src, int negative_mode, const int *__restrict__ idx,
+                 int *__restrict__ count) {
+    const long long step = (long long)gridDim.x * kBlock;
+    for (long long p = (long long)blockIdx.x * kBlock + threadIdx.x; p < n_entries; p += step) {
+        int j = wrap_index(__ldg(idx + p), n_src, negative_mode);
+        if (j >= 0 && j < n_src) atomicAdd(count + j, 1);
+    }
+}
+
+__global__ void __launch_bounds__(kBlock)
+csr_fill_kernel(long long n_entries, int n_src, int negative_mode, const int *__restrict__ idx,
+                int *__restrict__ cursor, int *__restrict__ tmp) {
+    const long long step = (long long)gridDim.x * kBlock;
+    for (long long p = (long long)blockIdx.x * kBlock + threadIdx.x; p < n_entries; p += step) {
+        int j = wrap_index(__ldg(idx + p), n_src, negative_mode);
+        if (j >= 0 && j < n_src) {
+            int slot = atomicAdd(cursor + j, 1);
+            tmp[slot] = (int)p;
+        }
+    }
+}
+
+// One thread per filled entry e: rank of tmp[e] among the entries of its row.
+__global__ void __launch_bounds__(kBlock)
+csr_rank_kernel(int n_src, int negative_mode, const int *__restrict__ idx,
+                const int *__restrict__ rowptr, const int *__restrict__ tmp, int *__restrict__ perm) {
+    const int total = __ldg(rowptr + n_src);
+    const int step = gridDim.x * kBlock;
+    for (int e = blockIdx.x * kBlock + threadIdx.x; e < total; e += step) {
+        int p = tmp[e];
+        int j = wrap_index(__ldg(idx + p), n_src, negative_mode);
+        int b = __ldg(rowptr + j), end = __ldg(rowptr + j + 1);
+        int rank = 0;
+        for (int q = b; q < end; ++q) rank += (tmp[q] < p) ? 1 : 0;
+        perm[b + rank] = p;
+    }
+}
+
+}  // namespace aopt
+
+using namespace aopt;
+
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+extern "C" size_t aopt_csr_workspace_bytes(int n_src, int64_t n_entries) {
+    if (n_src < 0 || n_entries < 0) return 0;
+    return align256(((size_t)n_src + 1) * 4) + align256((size_t)n_entries * 4) +
+           align256(scan_partial_ints(n_src) * 4);
+}
+
+extern "C" int aopt_csr_build(int n_src, int64_t n_entries, const int *idx, int negative_mode,
+                              int *rowptr, int *perm, void *workspace, size_t workspace_bytes,
+                              aopt_stream_t stream) {
+    if (n_src < 0 || n_entries < 0 || n_entries > 0x7fffffffLL || (negative_mode != 0 && negative_mode != 1))
+        return AOPT_ERR_INVALID_ARGUMENT;
+    if (!rowptr) return AOPT_ERR_INVALID_ARGUMENT;
+    cudaStream_t st = as_stream(stream);
+    if (n_src == 0) {
+        cudaMemsetAsync(rowptr, 0, sizeof(int), st);
+        return check_launch();
+    }
+    if (n_entries > 0 && (!idx || !perm)) return AOPT_ERR_INVALID_ARGUMENT;
+    if (!workspace || workspace_bytes < aopt_csr_workspace_bytes(n_src, n_entries)) return AOPT_ERR_WORKSPACE;
+    char *ws = static_cast<char *>(workspace);
+    int *count = reinterpret_cast<int *>(ws);  // later reused as the fill cursor
+    ws += align256(((size_t)n_src + 1) * 4);
+    int *tmp = reinterpret_cast<int *>(ws);
+    ws += align256((size_t)n_entries * 4);
+    int *partial = reinterpret_cast<int *>(ws);
+
+    cudaMemsetAsync(count, 0, ((size_t)n_src + 1) * 4, st);
+    if (n_entries > 0)
+        csr_count_kernel<<<stride_grid(n_entries, kBlock, 8), kBlock, 0, st>>>(n_entries, n_src, negative_mode, idx, count);
+    launch_exclusive_scan(count, rowptr, n_src, partial, st);   // rowptr[n_src] = number of kept entries
+    cudaMemcpyAsync(count, rowptr, (size_t)n_src * 4, cudaMemcpyDeviceToDevice, st);  // fill cursors
+    if (n_entries > 0) {
+        csr_fill_kernel<<<stride_grid(n_entries, kBlock, 8), kBlock, 0, st>>>(n_entries, n_src, negative_mode, idx, count, tmp);
+        csr_rank_kernel<<<stride_grid(n_entries, kBlock, 8), kBlock, 0, st>>>(n_src, negative_mode, idx, rowptr, tmp, perm);
+    }
+    return check_launch();
+}

@@ -1,0 +1,226 @@
+// grouping.cu — neighbour gather and its atomic-free segmented scatter-add backward.
+//
+// Replaces (paths relative to /root/reference):
+//   libs/pointops/src/grouping/grouping_cuda_kernel.cu:5-25  (1 thread / element, 3 div-mods per
+//       element, 4-byte accesses, float atomicAdd backward)
+//   libs/pointops/functions/grouping.py:36-60                (cat zero row + index + sub + einsum + cat)
+//   pointcept/models/point_transformer_v2/point_transformer_v2m2_base.py:109,112  (key[idx] - q)
+//
+// HBM layout: features are (rows, c) row-major fp32; one thread moves one 128-bit chunk of one
+// (query, neighbour) row, so a warp covers 512 contiguous output bytes.  The gathered source rows
+// go through the read-only path with default caching (each source row is re-read ~k times by
+// nearby queries and stays in L1/L2); the streamed (m,k,c) side uses L1::no_allocate.
+//
+// Algorithmic bytes: forward 4·M·k + 4·N·C + 4·M·k·C;
+// backward 4·M·k·C + 4·M·k + 4·(N+1) + 4·N·C.
+#include "common.cuh"
+
+namespace aopt {
+
+constexpr int kBlock = 256;
+
+// out[p, :] = in[idx[p], :]  (zeros for idx < 0)
+template <int VEC>
+__global__ void __launch_bounds__(kBlock)
+gather_rows_kernel(long long rows, int chunks, int c, const float *__restrict__ in,
+                   const int *__restrict__ idx, float *__restrict__ out, int out_stride) {
+    const long long total = rows * chunks;
+    const long long step = (long long)gridDim.x * kBlock;
+    for (long long t = (long long)blockIdx.x * kBlock + threadIdx.x; t < total; t += step) {
+        RowCol rc = split(t, chunks);
+        int j = __ldg(idx + rc.row);
+        Chunk<VEC> v = Chunk<VEC>::zero();
+        if (j >= 0) v = Chunk<VEC>::gather(in + (size_t)j * c + rc.col * VEC);
+        v.store_stream(out + (size_t)rc.row * out_stride + rc.col * VEC);
+    }
+}
+
+// out[m, s, :] = key[idx[m,s], :] - query[m, :]
+template <int VEC>
+__global__ void __launch_bounds__(kBlock)
+gather_sub_kernel(long long rows, int nsample, int chunks, int c, const float *__restrict__ key,
+                  const float *__restrict__ query, const int *__restrict__ idx,
+                  float *__restrict__ out) {
+    const long long total = rows * chunks;
+    const long long step = (long long)gridDim.x * kBlock;
+    for (long long t = (long long)blockIdx.x * kBlock + threadIdx.x; t < total; t += step) {
+        RowCol rc = split(t, chunks);
+        int j = __ldg(idx + rc.row);
+        long long m = rc.row / nsample;
+        Chunk<VEC> v = Chunk<VEC>::zero();
+        if (j >= 0) v = Chunk<VEC>::gather(key + (size_t)j * c + rc.col * VEC);
+        v.sub(Chunk<VEC>::gather(query + (size_t)m * c + rc.col * VEC));
+        v.store_stream(out + (size_t)rc.row * c + rc.col * VEC);
+    }
+}
+
+// grad_in[j, :] = scale * sum_{e in row j} grad_out[perm[e], :]   — one thread per (source row,
+// chunk); entries are visited in ascending flat position, so the sum order is fixed.
+template <int VEC>
+__global__ void __launch_bounds__(kBlock)
+segmented_sum_kernel(long long n, int chunks, int c, const float *__restrict__ grad_out,
+                     int go_stride, const int *__restrict__ rowptr, const int *__restrict__ perm,
+                     float scale, float *__restrict__ grad_in) {
+    const long long total = n * chunks;
+    const long long step = (long long)gridDim.x * kBlock;
+    for (long long t = (long long)blockIdx.x * kBlock + threadIdx.x; t < total; t += step) {
+        RowCol rc = split(t, chunks);
+        int e = __ldg(rowptr + rc.row);
+        const int e_end = __ldg(rowptr + rc.row + 1);
+        const float *base = grad_out + rc.col * VEC;
+        Chunk<VEC> acc = Chunk<VEC>::zero();
+        // 4 independent 128-bit loads in flight per thread
+        for (; e + 4 <= e_end; e += 4) {
+            int p0 = __ldg(perm + e), p1 = __ldg(perm + e + 1), p2 = __ldg(perm + e + 2),
+                p3 = __ldg(perm + e + 3);
+            Chunk<VEC> a0 = Chunk<VEC>::stream(base + (size_t)p0 * go_stride);
+            Chunk<VEC> a1 = Chunk<VEC>::stream(base + (size_t)p1 * go_stride);
+            Chunk<VEC> a2 = Chunk<VEC>::stream(base + (size_t)p2 * go_stride);
+            Chunk<VEC> a3 = Chunk<VEC>::stream(base + (size_t)p3 * go_stride);
+            acc.add(a0); acc.add(a1); acc.add(a2); acc.add(a3);
+        }
+        for (; e < e_end; ++e) {
+            int p = __ldg(perm + e);
+            acc.add(Chunk<VEC>::stream(base + (size_t)p * go_stride));
+        }
+        acc.scale(scale);
+        acc.store(grad_in + (size_t)rc.row * c + rc.col * VEC);
+    }
+}
+
+// out[m, :] = scale * sum_s grad[m, s, :]
+template <int VEC>
+__global__ void __launch_bounds__(kBlock)
+sum_over_k_kernel(long long m, int nsample, int chunks, int c, const float *__restrict__ grad,
+                  float scale, float *__restrict__ out) {
+    const long long total = m * chunks;
+    const long long step = (long long)gridDim.x * kBlock;
+    for (long long t = (long long)blockIdx.x * kBlock + threadIdx.x; t < total; t += step) {
+        RowCol rc = split(t, chunks);
+        const float *base = grad + (size_t)rc.row * nsample * c + rc.col * VEC;
+        Chunk<VEC> acc = Chunk<VEC>::zero();
+        int s = 0;
+        for (; s + 4 <= nsample; s += 4) {
+            Chunk<VEC> a0 = Chunk<VEC>::stream(base + (size_t)(s + 0) * c);
+            Chunk<VEC> a1 = Chunk<VEC>::stream(base + (size_t)(s + 1) * c);
+            Chunk<VEC> a2 = Chunk<VEC>::stream(base + (size_t)(s + 2) * c);
+            Chunk<VEC> a3 = Chunk<VEC>::stream(base + (size_t)(s + 3) * c);
+            acc.add(a0); acc.add(a1); acc.add(a2); acc.add(a3);
+        }
+        for (; s < nsample; ++s) acc.add(Chunk<VEC>::stream(base + (size_t)s * c));
+        acc.scale(scale);
+        acc.store(out + (size_t)rc.row * c + rc.col * VEC);
+    }
+}
+
+// out[p, 0..2] = (xyz[idx[p]] - new_xyz[p / nsample]) * sign(idx[p] + 1)
+__global__ void __launch_bounds__(kBlock)
+group_xyz_kernel(long long rows, int nsample, const float *__restrict__ xyz,
+                 const float *__restrict__ new_xyz, const int *__restrict__ idx,
+                 float *__restrict__ out, int out_stride) {
+    const long long step = (long long)gridDim.x * kBlock;
+    for (long long p = (long long)blockIdx.x * kBlock + threadIdx.x; p < rows; p += step) {
+        int j = __ldg(idx + p);
+        long long m = p / nsample;
+        float rx = 0.f, ry = 0.f, rz = 0.f;
+        float qx = __ldg(new_xyz + m * 3 + 0), qy = __ldg(new_xyz + m * 3 + 1),
+              qz = __ldg(new_xyz + m * 3 + 2);
+        if (j >= 0) {
+            rx = __ldg(xyz + (size_t)j * 3 + 0) - qx;
+            ry = __ldg(xyz + (size_t)j * 3 + 1) - qy;
+            rz = __ldg(xyz + (size_t)j * 3 + 2) - qz;
+        } else {
+            // grouping.py:41-57: the padded zero row gives (0 - q) * 0 = -0.0 or +0.0 by sign of q
+            rx = (0.f - qx) * 0.f; ry = (0.f - qy) * 0.f; rz = (0.f - qz) * 0.f;
+        }
+        float *o = out + (size_t)p * out_stride;
+        o[0] = rx; o[1] = ry; o[2] = rz;
+    }
+}
+
+}  // namespace aopt
+
+using namespace aopt;
+
+extern "C" int aopt_grouping_forward(int m, int nsample, int c, const float *input, const int *idx,
+                                     float *output, int out_stride, aopt_stream_t stream) {
+    if (m < 0 || nsample < 1 || c < 1 || out_stride < c) return AOPT_ERR_INVALID_ARGUMENT;
+    long long rows = (long long)m * nsample;
+    if (rows == 0) return AOPT_OK;
+    if (!input || !idx || !output) return AOPT_ERR_INVALID_ARGUMENT;
+    bool vec = (c % 4 == 0) && (out_stride % 4 == 0) && aligned16(input) && aligned16(output);
+    if (vec) {
+        int chunks = c / 4;
+        gather_rows_kernel<4><<<stride_grid(rows * chunks, kBlock, 8), kBlock, 0, as_stream(stream)>>>(
+            rows, chunks, c, input, idx, output, out_stride);
+    } else {
+        gather_rows_kernel<1><<<stride_grid(rows * c, kBlock, 8), kBlock, 0, as_stream(stream)>>>(
+            rows, c, c, input, idx, output, out_stride);
+    }
+    return check_launch();
+}
+
+extern "C" int aopt_grouping_backward(int n, int c, const float *grad_output, int go_stride,
+                                      const int *rowptr, const int *perm, float scale,
+                                      float *grad_input, aopt_stream_t stream) {
+    if (n < 0 || c < 1 || go_stride < c) return AOPT_ERR_INVALID_ARGUMENT;
+    if (n == 0) return AOPT_OK;
+    if (!grad_output || !rowptr || !perm || !grad_input) return AOPT_ERR_INVALID_ARGUMENT;
+    bool vec = (c % 4 == 0) && (go_stride % 4 == 0) && aligned16(grad_output) && aligned16(grad_input);
+    if (vec) {
+        int chunks = c / 4;
+        segmented_sum_kernel<4><<<stride_grid((long long)n * chunks, kBlock, 8), kBlock, 0, as_stream(stream)>>>(
+            n, chunks, c, grad_output, go_stride, rowptr, perm, scale, grad_input);
+    } else {
+        segmented_sum_kernel<1><<<stride_grid((long long)n * c, kBlock, 8), kBlock, 0, as_stream(stream)>>>(
+            n, c, c, grad_output, go_stride, rowptr, perm, scale, grad_input);
+    }
+    return check_launch();
+}
+
+extern "C" int aopt_group_xyz(int m, int nsample, const float *xyz, const float *new_xyz,
+                              const int *idx, float *out, int out_stride, aopt_stream_t stream) {
+    if (m < 0 || nsample < 1 || out_stride < 3) return AOPT_ERR_INVALID_ARGUMENT;
+    long long rows = (long long)m * nsample;
+    if (rows == 0) return AOPT_OK;
+    if (!xyz || !new_xyz || !idx || !out) return AOPT_ERR_INVALID_ARGUMENT;
+    group_xyz_kernel<<<stride_grid(rows, kBlock, 8), kBlock, 0, as_stream(stream)>>>(
+        rows, nsample, xyz, new_xyz, idx, out, out_stride);
+    return check_launch();
+}
+
+extern "C" int aopt_gather_sub_forward(int m, int nsample, int c, const float *key,
+                                       const float *query, const int *idx, float *out,
+                                       aopt_stream_t stream) {
+    if (m < 0 || nsample < 1 || c < 1) return AOPT_ERR_INVALID_ARGUMENT;
+    long long rows = (long long)m * nsample;
+    if (rows == 0) return AOPT_OK;
+    if (!key || !query || !idx || !out) return AOPT_ERR_INVALID_ARGUMENT;
+    bool vec = (c % 4 == 0) && aligned16(key) && aligned16(query) && aligned16(out);
+    if (vec) {
+        int chunks = c / 4;
+        gather_sub_kernel<4><<<stride_grid(rows * chunks, kBlock, 8), kBlock, 0, as_stream(stream)>>>(
+            rows, nsample, chunks, c, key, query, idx, out);
+    } else {
+        gather_sub_kernel<1><<<stride_grid(rows * c, kBlock, 8), kBlock, 0, as_stream(stream)>>>(
+            rows, nsample, c, c, key, query, idx, out);
+    }
+    return check_launch();
+}
+
+extern "C" int aopt_sum_over_k(int m, int nsample, int c, const float *grad, float scale,
+                               float *out, aopt_stream_t stream) {
+    if (m < 0 || nsample < 1 || c < 1) return AOPT_ERR_INVALID_ARGUMENT;
+    if (m == 0) return AOPT_OK;
+    if (!grad || !out) return AOPT_ERR_INVALID_ARGUMENT;
+    bool vec = (c % 4 == 0) && aligned16(grad) && aligned16(out);
+    if (vec) {
+        int chunks = c / 4;
+        sum_over_k_kernel<4><<<stride_grid((long long)m * chunks, kBlock, 8), kBlock, 0, as_stream(stream)>>>(
+            m, nsample, chunks, c, grad, scale, out);
+    } else {
+        sum_over_k_kernel<1><<<stride_grid((long long)m * c, kBlock, 8), kBlock, 0, as_stream(stream)>>>(
+            m, nsample, c, c, grad, scale, out);
+    }
+    return check_launch();
+}

@@ -1,0 +1,123 @@
+// interp.cu — three-NN inverse-distance interpolation, forward and backward.
+//
+// Replaces /root/reference/libs/pointops/functions/interpolation.py:8-22 (k separate
+// gather+mul+add passes over (n,c), backward = k index_put_(accumulate)) and the CUDA variant
+// libs/pointops/src/interpolation/interpolation_cuda_kernel.cu:5-33 (1 thread per (n,c), float
+// atomicAdd backward).  The neighbour search itself is aopt_knn_query with nsample = k.
+//
+// Bytes: forward 24·Nf + 4·Nc·C + 4·Nf·C; backward 4·Nf·C + 36·Nf + 4(Nc+1) + 4·Nc·C.
+#include "common.cuh"
+
+namespace aopt {
+
+constexpr int kInterpBlock = 256;
+
+// weight[n,i] = r_i / sum_j r_j with r = 1/(sqrt(d2)+1e-8): every operation IEEE-rounded fp32
+// (sqrt, add, reciprocal, sequential sum, divide) like the torch ops of interpolation.py:15-17.
+__global__ void __launch_bounds__(kInterpBlock)
+interp_weights_kernel(int n, int k, const float *__restrict__ dist2, float *__restrict__ weight) {
+    const int row = blockIdx.x * kInterpBlock + threadIdx.x;
+    if (row >= n) return;
+    const float *d = dist2 + (size_t)row * k;
+    float sum = 0.f;
+    for (int i = 0; i < k; ++i) {
+        float r = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(__ldg(d + i)), 1e-8f));
+        sum = __fadd_rn(sum, r);
+    }
+    for (int i = 0; i < k; ++i) {
+        float r = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(__ldg(d + i)), 1e-8f));
+        weight[(size_t)row * k + i] = __fdiv_rn(r, sum);
+    }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(kInterpBlock)
+interp_forward_kernel(long long n, int chunks, int c, int k, int m, const float *__restrict__ input,
+                      const int *__restrict__ idx, const float *__restrict__ weight,
+                      float *__restrict__ output) {
+    const long long total = n * chunks;
+    const long long step = (long long)gridDim.x * kInterpBlock;
+    for (long long t = (long long)blockIdx.x * kInterpBlock + threadIdx.x; t < total; t += step) {
+        RowCol rc = split(t, chunks);
+        Chunk<VEC> acc = Chunk<VEC>::zero();
+#pragma unroll 3
+        for (int i = 0; i < k; ++i) {
+            int j = __ldg(idx + rc.row * k + i);
+            if (j < 0) j += m;  // python negative index (interpolation.py:21): no -1 masking
+            const float w = __ldg(weight + rc.row * k + i);
+            Chunk<VEC> v = Chunk<VEC>::gather(input + (size_t)j * c + rc.col * VEC);
+            v.scale(w);   // separate multiply and add, as `new_feat += feat[idx] * weight` does
+            acc.add(v);
+        }
+        acc.store_stream(output + (size_t)rc.row * c + rc.col * VEC);
+    }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(kInterpBlock)
+interp_backward_kernel(long long m, int chunks, int c, int k, const float *__restrict__ grad_output,
+                       const float *__restrict__ weight, const int *__restrict__ rowptr,
+                       const int *__restrict__ perm, float *__restrict__ grad_input) {
+    const long long total = m * chunks;
+    const long long step = (long long)gridDim.x * kInterpBlock;
+    for (long long t = (long long)blockIdx.x * kInterpBlock + threadIdx.x; t < total; t += step) {
+        RowCol rc = split(t, chunks);
+        Chunk<VEC> acc = Chunk<VEC>::zero();
+        const int e_end = __ldg(rowptr + rc.row + 1);
+#pragma unroll 4
+        for (int e = __ldg(rowptr + rc.row); e < e_end; ++e) {
+            const int p = __ldg(perm + e);
+            const int q = p / k;
+            const float w = __ldg(weight + p);
+            acc.fma(Chunk<VEC>::gather(grad_output + (size_t)q * c + rc.col * VEC), w);
+        }
+        acc.store(grad_input + (size_t)rc.row * c + rc.col * VEC);
+    }
+}
+
+}  // namespace aopt
+
+using namespace aopt;
+
+extern "C" int aopt_interp_weights(int n, int k, const float *dist2, float *weight, aopt_stream_t stream) {
+    if (n < 0 || k < 1 || k > AOPT_MAX_NSAMPLE) return AOPT_ERR_INVALID_ARGUMENT;
+    if (n == 0) return AOPT_OK;
+    if (!dist2 || !weight) return AOPT_ERR_INVALID_ARGUMENT;
+    interp_weights_kernel<<<div_up(n, kInterpBlock), kInterpBlock, 0, as_stream(stream)>>>(n, k, dist2, weight);
+    return check_launch();
+}
+
+extern "C" int aopt_interpolation_forward(int n, int c, int k, int m, const float *input, const int *idx,
+                                          const float *weight, float *output, aopt_stream_t stream) {
+    if (n < 0 || c < 1 || k < 1 || m < 1) return AOPT_ERR_INVALID_ARGUMENT;
+    if (n == 0) return AOPT_OK;
+    if (!input || !idx || !weight || !output) return AOPT_ERR_INVALID_ARGUMENT;
+    const bool vec = (c % 4 == 0) && aligned16(input) && aligned16(output);
+    if (vec) {
+        const int chunks = c / 4;
+        interp_forward_kernel<4><<<stride_grid((long long)n * chunks, kInterpBlock, 8), kInterpBlock, 0, as_stream(stream)>>>(
+            n, chunks, c, k, m, input, idx, weight, output);
+    } else {
+        interp_forward_kernel<1><<<stride_grid((long long)n * c, kInterpBlock, 8), kInterpBlock, 0, as_stream(stream)>>>(
+            n, c, c, k, m, input, idx, weight, output);
+    }
+    return check_launch();
+}
+
+extern "C" int aopt_interpolation_backward(int m, int c, int k, const float *grad_output, const float *weight,
+                                           const int *rowptr, const int *perm, float *grad_input,
+                                           aopt_stream_t stream) {
+    if (m < 0 || c < 1 || k < 1) return AOPT_ERR_INVALID_ARGUMENT;
+    if (m == 0) return AOPT_OK;
+    if (!grad_output || !weight || !rowptr || !perm || !grad_input) return AOPT_ERR_INVALID_ARGUMENT;
+    const bool vec = (c % 4 == 0) && aligned16(grad_output) && aligned16(grad_input);
+    if (vec) {
+        const int chunks = c / 4;
+        interp_backward_kernel<4><<<stride_grid((long long)m * chunks, kInterpBlock, 8), kInterpBlock, 0, as_stream(stream)>>>(
+            m, chunks, c, k, grad_output, weight, rowptr, perm, grad_input);
+    } else {
+        interp_backward_kernel<1><<<stride_grid((long long)m * c, kInterpBlock, 8), kInterpBlock, 0, as_stream(stream)>>>(
+            m, c, c, k, grad_output, weight, rowptr, perm, grad_input);
+    }
+    return check_launch();
+}

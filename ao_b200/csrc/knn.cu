@@ -1,0 +1,206 @@
+// knn.cu — exact batched-offset k nearest neighbours.
+//
+// Replaces /root/reference/libs/pointops/src/knn_query/knn_query_cuda_kernel.cu:60-104 (one thread
+// per query scanning its whole scene from global memory, k-entry heap in a 1 KB local-memory
+// stack frame) behind the launcher signature of knn_query_cuda_kernel.h:15.
+//
+// Contract (bit-exact with the reference build on every tie-free row, see oracle/knn_oracle.c):
+//   d2 = fma(dz,dz, fma(dx,dx, dy*dy)),  d = query - candidate        (fp32, IEEE, no fast-math)
+//   accept iff d2 < current k-th distance (strict); rows ascending by (d2, idx);
+//   unused slots: idx = -1, dist2 = 1e10.
+//
+// TILE method (this file, part 1): candidates of the query's scene are staged through shared
+// memory in tiles of 1024 points (float4 x,y,z,-), every thread owns one query and keeps its k best
+// in REGISTERS as a sorted list (template K); a candidate is compared against the k-th distance
+// first, four at a time, so the sorted insert (K compare-exchanges) only runs ~k·ln(n/k) times per
+// query.  All lanes of a warp read the same shared-memory word (broadcast, conflict-free).
+// FP32-ALU bound: ~9 issue slots per (query, candidate) pair.
+//
+// GRID method (part 2, knn_grid.cu) prunes the candidate set with a uniform grid and is what the
+// AUTO policy picks for large scenes; both return identical results.
+#include "common.cuh"
+#include "knn_common.cuh"
+
+namespace aopt {
+
+constexpr int kKnnBlock = 256;
+constexpr int kKnnTile = 1024;
+
+template <int K>
+__global__ void __launch_bounds__(kKnnBlock)
+knn_tile_kernel(int m, int n, int b, int nsample, const float *__restrict__ xyz,
+                const float *__restrict__ new_xyz, const int *__restrict__ offset,
+                const int *__restrict__ new_offset, int *__restrict__ idx_out,
+                float *__restrict__ dist2_out) {
+    __shared__ float4 tile[kKnnTile];
+    __shared__ int range_s[2];
+
+    const int q = blockIdx.x * kKnnBlock + threadIdx.x;
+    const bool valid = q < m;
+    int start = 0, end = 0;
+    float qx = 0.f, qy = 0.f, qz = 0.f;
+    if (valid) {
+        int seg = find_segment(q, new_offset, b);
+        if (seg < b) {
+            start = seg == 0 ? 0 : __ldg(offset + seg - 1);
+            end = __ldg(offset + seg);
+            if (end > n) end = n;
+            if (start < 0) start = 0;
+        }
+        qx = __ldg(new_xyz + (size_t)q * 3 + 0);
+        qy = __ldg(new_xyz + (size_t)q * 3 + 1);
+        qz = __ldg(new_xyz + (size_t)q * 3 + 2);
+    }
+    // Candidate range of the block = union of its queries' scene ranges (consecutive queries →
+    // consecutive scenes); warp-reduce, then one shared atomic per warp.
+    if (threadIdx.x == 0) { range_s[0] = 0x7fffffff; range_s[1] = 0; }
+    __syncthreads();
+    {
+        const bool has = end > start;
+        int wlo = __reduce_min_sync(0xffffffffu, has ? start : 0x7fffffff);
+        int whi = __reduce_max_sync(0xffffffffu, has ? end : 0);
+        if ((threadIdx.x & 31) == 0) { atomicMin(&range_s[0], wlo); atomicMax(&range_s[1], whi); }
+    }
+    __syncthreads();
+    const int lo = range_s[0], hi = range_s[1];
+
+    TopK<K, false> top;
+    top.init();
+
+    for (int base = lo; base < hi; base += kKnnTile) {
+        const int cnt = min(kKnnTile, hi - base);
+        __syncthreads();  // previous tile fully consumed
+        for (int t = threadIdx.x; t < cnt; t += kKnnBlock) {
+            const float *p = xyz + (size_t)(base + t) * 3;
+            tile[t] = make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), 0.f);
+        }
+        __syncthreads();
+        int j = max(start, base) - base;
+        const int jhi = min(end, base + cnt) - base;
+        for (; j + 4 <= jhi; j += 4) {
+            float4 c0 = tile[j], c1 = tile[j + 1], c2 = tile[j + 2], c3 = tile[j + 3];
+            float d0 = dist2_ref(qx, qy, qz, c0.x, c0.y, c0.z);
+            float d1 = dist2_ref(qx, qy, qz, c1.x, c1.y, c1.z);
+            float d2 = dist2_ref(qx, qy, qz, c2.x, c2.y, c2.z);
+            float d3 = dist2_ref(qx, qy, qz, c3.x, c3.y, c3.z);
+            float mn = fminf(fminf(d0, d1), fminf(d2, d3));
+            if (mn < top.worst()) {
+                top.offer(d0, base + j);
+                top.offer(d1, base + j + 1);
+                top.offer(d2, base + j + 2);
+                top.offer(d3, base + j + 3);
+            }
+        }
+        for (; j < jhi; ++j) {
+            float4 c0 = tile[j];
+            top.offer(dist2_ref(qx, qy, qz, c0.x, c0.y, c0.z), base + j);
+        }
+    }
+    if (valid) top.store(idx_out + (size_t)q * nsample, dist2_out + (size_t)q * nsample, nsample);
+}
+
+// nsample in (32, 128]: same scan, k best kept in a local-memory sorted list (rare path; the
+// PTv2m2 configs use k <= 32).
+__global__ void __launch_bounds__(kKnnBlock)
+knn_tile_bigk_kernel(int m, int n, int b, int nsample, const float *__restrict__ xyz,
+                     const float *__restrict__ new_xyz, const int *__restrict__ offset,
+                     const int *__restrict__ new_offset, int *__restrict__ idx_out,
+                     float *__restrict__ dist2_out) {
+    const int q = blockIdx.x * kKnnBlock + threadIdx.x;
+    if (q >= m) return;
+    int start = 0, end = 0;
+    int seg = find_segment(q, new_offset, b);
+    if (seg < b) {
+        start = seg == 0 ? 0 : __ldg(offset + seg - 1);
+        end = min(__ldg(offset + seg), n);
+        if (start < 0) start = 0;
+    }
+    const float qx = __ldg(new_xyz + (size_t)q * 3 + 0), qy = __ldg(new_xyz + (size_t)q * 3 + 1),
+                qz = __ldg(new_xyz + (size_t)q * 3 + 2);
+    float bd[AOPT_MAX_NSAMPLE];
+    int bi[AOPT_MAX_NSAMPLE];
+    for (int i = 0; i < nsample; ++i) { bd[i] = 1e10f; bi[i] = -1; }
+    for (int i = start; i < end; ++i) {
+        const float *p = xyz + (size_t)i * 3;
+        float d2 = dist2_ref(qx, qy, qz, __ldg(p), __ldg(p + 1), __ldg(p + 2));
+        if (d2 < bd[nsample - 1]) {
+            int j = nsample - 1;
+            while (j > 0 && bd[j - 1] > d2) { bd[j] = bd[j - 1]; bi[j] = bi[j - 1]; --j; }
+            bd[j] = d2;
+            bi[j] = i;
+        }
+    }
+    for (int i = 0; i < nsample; ++i) {
+        idx_out[(size_t)q * nsample + i] = bi[i];
+        dist2_out[(size_t)q * nsample + i] = bd[i];
+    }
+}
+
+template <int K>
+static void launch_tile(int m, int n, int b, int nsample, const float *xyz, const float *new_xyz,
+                        const int *offset, const int *new_offset, int *idx, float *dist2,
+                        cudaStream_t st) {
+    knn_tile_kernel<K><<<div_up(m, kKnnBlock), kKnnBlock, 0, st>>>(m, n, b, nsample, xyz, new_xyz, offset,
+                                                                   new_offset, idx, dist2);
+}
+
+int knn_tile_launch(int m, int nsample, int n, int b, const float *xyz, const float *new_xyz,
+                    const int *offset, const int *new_offset, int *idx, float *dist2,
+                    cudaStream_t st) {
+    if (nsample <= 1) launch_tile<1>(m, n, b, nsample, xyz, new_xyz, offset, new_offset, idx, dist2, st);
+    else if (nsample <= 4) launch_tile<4>(m, n, b, nsample, xyz, new_xyz, offset, new_offset, idx, dist2, st);
+    else if (nsample <= 8) launch_tile<8>(m, n, b, nsample, xyz, new_xyz, offset, new_offset, idx, dist2, st);
+    else if (nsample <= 16) launch_tile<16>(m, n, b, nsample, xyz, new_xyz, offset, new_offset, idx, dist2, st);
+    else if (nsample <= 32) launch_tile<32>(m, n, b, nsample, xyz, new_xyz, offset, new_offset, idx, dist2, st);
+    else
+        knn_tile_bigk_kernel<<<div_up(m, kKnnBlock), kKnnBlock, 0, st>>>(m, n, b, nsample, xyz, new_xyz, offset,
+                                                                        new_offset, idx, dist2);
+    return check_launch();
+}
+
+// part 2 (knn_grid.cu)
+size_t knn_grid_workspace_bytes(int n, int m, int b);
+int knn_grid_launch(int m, int nsample, int n, int b, const float *xyz, const float *new_xyz,
+                    const int *offset, const int *new_offset, int *idx, float *dist2, void *ws,
+                    size_t ws_bytes, cudaStream_t st);
+
+}  // namespace aopt
+
+using namespace aopt;
+
+// Scenes smaller than this are cheaper to scan than to bin.
+static const int kGridMinPoints = 4096;
+
+static int pick_method(int n, int m, int b, int nsample, int method) {
+    if (method == AOPT_KNN_TILE || method == AOPT_KNN_GRID) return method;
+    if (nsample > 32) return AOPT_KNN_TILE;
+    long long avg = b > 0 ? (long long)n / b : n;
+    return avg >= kGridMinPoints ? AOPT_KNN_GRID : AOPT_KNN_TILE;
+}
+
+extern "C" size_t aopt_knn_workspace_bytes(int n, int m, int b, int nsample, int method) {
+    if (n < 0 || m < 0 || b < 0) return 0;
+    if (pick_method(n, m, b, nsample, method) != AOPT_KNN_GRID) return 0;
+    return knn_grid_workspace_bytes(n, m, b);
+}
+
+extern "C" int aopt_knn_query(int m, int nsample, int n, int b, const float *xyz,
+                              const float *new_xyz, const int *offset, const int *new_offset,
+                              int *idx, float *dist2, int method, void *workspace,
+                              size_t workspace_bytes, aopt_stream_t stream) {
+    if (m < 0 || n < 0 || b < 0 || nsample < 1 || nsample > AOPT_MAX_NSAMPLE) return AOPT_ERR_INVALID_ARGUMENT;
+    if (method < AOPT_KNN_AUTO || method > AOPT_KNN_GRID) return AOPT_ERR_INVALID_ARGUMENT;
+    if (m == 0) return AOPT_OK;
+    if (!new_xyz || !idx || !dist2 || (n > 0 && !xyz) || (b > 0 && (!offset || !new_offset)))
+        return AOPT_ERR_INVALID_ARGUMENT;
+    cudaStream_t st = as_stream(stream);
+    int use = pick_method(n, m, b, nsample, method);
+    if (use == AOPT_KNN_GRID) {
+        if (nsample > 32) return AOPT_ERR_UNSUPPORTED;
+        size_t need = knn_grid_workspace_bytes(n, m, b);
+        if (!workspace || workspace_bytes < need) return AOPT_ERR_WORKSPACE;
+        return knn_grid_launch(m, nsample, n, b, xyz, new_xyz, offset, new_offset, idx, dist2, workspace,
+                               workspace_bytes, st);
+    }
+    return knn_tile_launch(m, nsample, n, b, xyz, new_xyz, offset, new_offset, idx, dist2, st);
+}

@@ -1,0 +1,372 @@
+// knn_grid.cu — exact kNN with spatial pruning (the GRID method of aopt_knn_query).
+//
+// The reference (and the TILE method) scan every candidate of the scene for every query:
+// 80k x 80k pairs per S3DIS room, ALU-bound.  Here each scene gets a uniform grid
+// sized from the data (cell edge ~ the k-th neighbour distance measured on a sample), candidates
+// are counting-sorted by cell, and each query visits the 3x3x3 block around its cell, then
+// successive shells, until the k-th best distance is provably smaller than the distance to
+// anything outside the visited block.  The result is the same set, in the same (d2, idx) order,
+// as the exhaustive scan: distances use the same dist2_ref() and candidates are ranked
+// lexicographically, so the traversal order does not matter.
+//
+// Pipeline (all on the caller's stream, no host synchronisation, no allocation):
+//   1 knn_sample_kernel   r_k^2 of 64 sample points per scene (one warp per sample, register top-k)
+//   2 grid_setup_kernel   per-scene bounding box, cell edge h, grid dims  → GridDesc
+//   3 grid_count_kernel   cell of every candidate + its slot inside the cell (int atomics)
+//   4 exclusive scan      cell counts → cell starts                         (scan.cu)
+//   5 grid_fill_kernel    candidates → cell order as float4 (x, y, z, original index)
+//   6 knn_grid_kernel<K>  one thread per query (self-queries run in cell order so that a warp
+//                         shares its candidate runs through L1), register top-k, LEX ranking
+//
+// Exactness of the stopping rule.  After visiting the block of cells [c-r, c+r]^3 (clipped to the
+// grid) every unvisited candidate lies beyond one of the block's inner faces.  bound = the smallest
+// distance from the query to such a face.  Cell indices are computed in fp32, so a candidate may
+// sit up to ~1e-6·dim cells on the wrong side of a face; the rule therefore stops only when
+// kth_d2 < (bound - margin)^2 with margin = h·(1e-3 + 1e-6·max_dim) — three orders of magnitude
+// more than the rounding it has to absorb.  Being conservative costs an extra shell, never
+// correctness.  The strict '<' also rules out an unvisited candidate tying with the k-th best.
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "knn_common.cuh"
+#include "scan.cuh"
+
+namespace aopt {
+
+constexpr int kSamples = 64;        // sample points per scene for the density estimate
+constexpr int kCellsPerPoint = 8;   // grid capacity: 8 cells per candidate + 64 per scene
+constexpr int kCellsPerScene = 64;
+constexpr int kMaxRing = 8;         // beyond this shell radius a query falls back to a full scan
+constexpr int kQueryBlock = 128;
+
+struct GridDesc {
+    float ox, oy, oz;  // bbox minimum of the scene's candidates
+    float h, inv_h;    // cell edge
+    int nx, ny, nz;
+    int cell_base;     // first cell of the scene in the global cell array
+    int start, end;    // candidate range of the scene
+    float margin;
+    int pad[4];
+};
+static_assert(sizeof(GridDesc) == 64, "GridDesc is 64 bytes");
+
+__device__ __forceinline__ int cell_coord(float p, float o, float inv_h, int dim) {
+    int c = (int)floorf((p - o) * inv_h);
+    return min(max(c, 0), dim - 1);
+}
+
+// ---- 1. density sample ---------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(128)
+knn_sample_kernel(int b, int nsample, const float *__restrict__ xyz, const int *__restrict__ offset,
+                  float *__restrict__ samples) {
+    const int warp = (blockIdx.x * 128 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= b * kSamples) return;
+    const int sc = warp / kSamples, s = warp - sc * kSamples;
+    const int start = sc == 0 ? 0 : __ldg(offset + sc - 1), end = __ldg(offset + sc);
+    const int ns = end - start;
+    float result = 1e10f;
+    if (ns > 0) {
+        const int qi = start + (int)(((long long)(2 * s + 1) * ns) / (2 * kSamples));
+        const float qx = __ldg(xyz + (size_t)qi * 3), qy = __ldg(xyz + (size_t)qi * 3 + 1),
+                    qz = __ldg(xyz + (size_t)qi * 3 + 2);
+        TopK<K, false> top;
+        top.init();
+        for (int i = start + lane; i < end; i += 32) {
+            const float *p = xyz + (size_t)i * 3;
+            top.offer(dist2_ref(qx, qy, qz, __ldg(p), __ldg(p + 1), __ldg(p + 2)), i);
+        }
+        // merge the 32 sorted lists: pop the warp-wide minimum nsample times
+        for (int r = 0; r < nsample; ++r) {
+            float head = top.d[0];
+            float mn = head;
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, d));
+            unsigned who = __ballot_sync(0xffffffffu, head == mn);
+            if (lane == __ffs(who) - 1) {
+#pragma unroll
+                for (int i = 0; i + 1 < K; ++i) top.d[i] = top.d[i + 1];
+                top.d[K - 1] = 1e10f;
+            }
+            result = mn;
+        }
+    }
+    if (lane == 0) samples[warp] = result;
+}
+
+// ---- 2. per-scene grid descriptor ------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+grid_setup_kernel(int b, int n, const float *__restrict__ xyz, const int *__restrict__ offset,
+                  const float *__restrict__ samples, float cell_scale, GridDesc *__restrict__ desc) {
+    __shared__ float red[6][8];
+    const int sc = blockIdx.x;
+    int start = sc == 0 ? 0 : __ldg(offset + sc - 1), end = __ldg(offset + sc);
+    start = max(start, 0);
+    end = min(end, n);
+    float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+    for (int i = start + threadIdx.x; i < end; i += 256) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            float v = __ldg(xyz + (size_t)i * 3 + a);
+            lo[a] = fminf(lo[a], v);
+            hi[a] = fmaxf(hi[a], v);
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], d));
+            hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], d));
+        }
+        if ((threadIdx.x & 31) == 0) {
+            red[a][threadIdx.x >> 5] = lo[a];
+            red[3 + a][threadIdx.x >> 5] = hi[a];
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int a = 0; a < 3; ++a)
+            for (int w = 0; w < 8; ++w) {
+                lo[a] = fminf(lo[a], red[a][w]);
+                hi[a] = fmaxf(hi[a], red[3 + a][w]);
+            }
+        GridDesc g;
+        const int ns = max(end - start, 0);
+        if (ns == 0) { lo[0] = lo[1] = lo[2] = 0.f; hi[0] = hi[1] = hi[2] = 0.f; }
+        float ext[3] = {hi[0] - lo[0], hi[1] - lo[1], hi[2] - lo[2]};
+        float max_ext = fmaxf(ext[0], fmaxf(ext[1], ext[2]));
+        float sum = 0.f;
+        int cnt = 0;
+        for (int s = 0; s < kSamples; ++s) {
+            float v = samples[sc * kSamples + s];
+            if (v < 1e9f) { sum += sqrtf(v); ++cnt; }
+        }
+        float h = cnt > 0 ? cell_scale * sum / (float)cnt : 0.f;
+        if (!(h > max_ext * (1.f / 2048.f))) h = max_ext * (1.f / 2048.f);  // also catches NaN / 0
+        if (!(h > 1e-12f)) h = 1.f;                                         // all points coincide
+        const long long cap = (long long)kCellsPerPoint * ns + kCellsPerScene;
+        int nx, ny, nz;
+        for (int it = 0; it < 200; ++it) {
+            nx = (int)(ext[0] / h) + 1; ny = (int)(ext[1] / h) + 1; nz = (int)(ext[2] / h) + 1;
+            if ((long long)nx * ny * nz <= cap) break;
+            h *= 1.25f;
+        }
+        g.ox = lo[0]; g.oy = lo[1]; g.oz = lo[2];
+        g.h = h; g.inv_h = 1.f / h;
+        g.nx = nx; g.ny = ny; g.nz = nz;
+        g.cell_base = kCellsPerPoint * start + kCellsPerScene * sc;
+        g.start = start; g.end = end;
+        g.margin = h * (1e-3f + 1e-6f * (float)max(nx, max(ny, nz)));
+        g.pad[0] = g.pad[1] = g.pad[2] = g.pad[3] = 0;
+        desc[sc] = g;
+    }
+}
+
+// ---- 3. count ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+grid_count_kernel(int n, int b, const float *__restrict__ xyz, const int *__restrict__ offset,
+                  const GridDesc *__restrict__ desc, int *__restrict__ cells,
+                  int *__restrict__ point_cell, int *__restrict__ point_slot) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const int sc = find_segment(i, offset, b);
+    if (sc >= b) { point_cell[i] = -1; return; }
+    const GridDesc g = desc[sc];
+    const int cx = cell_coord(__ldg(xyz + (size_t)i * 3 + 0), g.ox, g.inv_h, g.nx);
+    const int cy = cell_coord(__ldg(xyz + (size_t)i * 3 + 1), g.oy, g.inv_h, g.ny);
+    const int cz = cell_coord(__ldg(xyz + (size_t)i * 3 + 2), g.oz, g.inv_h, g.nz);
+    const int cell = g.cell_base + (cz * g.ny + cy) * g.nx + cx;
+    point_cell[i] = cell;
+    point_slot[i] = atomicAdd(cells + cell, 1);
+}
+
+// ---- 5. fill ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+grid_fill_kernel(int n, const float *__restrict__ xyz, const int *__restrict__ cells,
+                 const int *__restrict__ point_cell, const int *__restrict__ point_slot,
+                 float4 *__restrict__ sorted) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const int cell = point_cell[i];
+    if (cell < 0) return;
+    const int pos = cells[cell] + point_slot[i];
+    sorted[pos] = make_float4(__ldg(xyz + (size_t)i * 3), __ldg(xyz + (size_t)i * 3 + 1),
+                              __ldg(xyz + (size_t)i * 3 + 2), __int_as_float(i));
+}
+
+// ---- 6. query ------------------------------------------------------------------------------------
+template <int K>
+__device__ __forceinline__ void scan_run(TopK<K, true> &top, const float4 *__restrict__ sorted, int a,
+                                         int e, float qx, float qy, float qz) {
+    for (int i = a; i < e; ++i) {
+        const float4 c = __ldg(sorted + i);
+        top.offer(dist2_ref(qx, qy, qz, c.x, c.y, c.z), __float_as_int(c.w));
+    }
+}
+
+template <int K, bool SELF>
+__global__ void __launch_bounds__(kQueryBlock)
+knn_grid_kernel(int m, int b, int nsample, const float *__restrict__ new_xyz,
+                const int *__restrict__ new_offset, const GridDesc *__restrict__ desc,
+                const int *__restrict__ cells, const float4 *__restrict__ sorted,
+                int *__restrict__ idx_out, float *__restrict__ dist2_out) {
+    const int t = blockIdx.x * kQueryBlock + threadIdx.x;
+    if (t >= m) return;
+    const int sc = find_segment(t, new_offset, b);
+    float qx = 0.f, qy = 0.f, qz = 0.f;
+    int row = t;  // output row = original query index
+    if (SELF) {
+        // thread t takes the t-th candidate in cell order (scene ranges are the same before and
+        // after the counting sort); points past the last offset belong to no scene and were not sorted
+        if (sc < b) {
+            const float4 me = __ldg(sorted + t);
+            qx = me.x; qy = me.y; qz = me.z;
+            row = __float_as_int(me.w);
+        }
+    } else {
+        qx = __ldg(new_xyz + (size_t)t * 3); qy = __ldg(new_xyz + (size_t)t * 3 + 1);
+        qz = __ldg(new_xyz + (size_t)t * 3 + 2);
+    }
+    TopK<K, true> top;
+    top.init();
+    if (sc < b) {
+        const GridDesc g = desc[sc];
+        if (g.end > g.start) {
+            const int cx = cell_coord(qx, g.ox, g.inv_h, g.nx);
+            const int cy = cell_coord(qy, g.oy, g.inv_h, g.ny);
+            const int cz = cell_coord(qz, g.oz, g.inv_h, g.nz);
+            const int *cs = cells + g.cell_base;
+            bool done = false;
+            for (int r = 1; r <= kMaxRing && !done; ++r) {
+                for (int dz = -r; dz <= r; ++dz) {
+                    const int z = cz + dz;
+                    if (z < 0 || z >= g.nz) continue;
+                    for (int dy = -r; dy <= r; ++dy) {
+                        const int y = cy + dy;
+                        if (y < 0 || y >= g.ny) continue;
+                        const int rowbase = (z * g.ny + y) * g.nx;
+                        const bool full = (r == 1) || max(abs(dz), abs(dy)) == r;
+                        if (full) {
+                            const int x0 = max(cx - r, 0), x1 = min(cx + r, g.nx - 1);
+                            scan_run<K>(top, sorted, __ldg(cs + rowbase + x0), __ldg(cs + rowbase + x1 + 1), qx, qy, qz);
+                        } else {
+                            if (cx - r >= 0)
+                                scan_run<K>(top, sorted, __ldg(cs + rowbase + cx - r), __ldg(cs + rowbase + cx - r + 1), qx, qy, qz);
+                            if (cx + r <= g.nx - 1)
+                                scan_run<K>(top, sorted, __ldg(cs + rowbase + cx + r), __ldg(cs + rowbase + cx + r + 1), qx, qy, qz);
+                        }
+                    }
+                }
+                // distance to the nearest inner face of the visited block
+                float bound = 3.0e38f;
+                if (cx - r > 0) bound = fminf(bound, qx - (g.ox + (float)(cx - r) * g.h));
+                if (cx + r < g.nx - 1) bound = fminf(bound, (g.ox + (float)(cx + r + 1) * g.h) - qx);
+                if (cy - r > 0) bound = fminf(bound, qy - (g.oy + (float)(cy - r) * g.h));
+                if (cy + r < g.ny - 1) bound = fminf(bound, (g.oy + (float)(cy + r + 1) * g.h) - qy);
+                if (cz - r > 0) bound = fminf(bound, qz - (g.oz + (float)(cz - r) * g.h));
+                if (cz + r < g.nz - 1) bound = fminf(bound, (g.oz + (float)(cz + r + 1) * g.h) - qz);
+                if (bound > 1.0e38f) {
+                    done = true;  // the block covers the whole grid
+                } else {
+                    const float bs = bound - g.margin;
+                    if (bs > 0.f && top.worst() < bs * bs) done = true;
+                }
+            }
+            if (!done) {  // sparse neighbourhood: exhaustive scan of the scene
+                top.init();
+                scan_run<K>(top, sorted, g.start, g.end, qx, qy, qz);
+            }
+        }
+    }
+    top.store(idx_out + (size_t)row * nsample, dist2_out + (size_t)row * nsample, nsample);
+}
+
+// ---- host side -------------------------------------------------------------------------------------
+static size_t a256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+struct GridWs {
+    GridDesc *desc;
+    float *samples;
+    int *cells;
+    int *point_cell, *point_slot;
+    float4 *sorted;
+    int *partial;
+    size_t total_cells;
+    size_t bytes;
+};
+
+static GridWs carve(void *ws, int n, int b) {
+    GridWs w;
+    char *p = static_cast<char *>(ws);
+    size_t off = 0;
+    w.total_cells = (size_t)kCellsPerPoint * n + (size_t)kCellsPerScene * b;
+    w.desc = reinterpret_cast<GridDesc *>(p + off); off += a256(sizeof(GridDesc) * (size_t)(b > 0 ? b : 1));
+    w.samples = reinterpret_cast<float *>(p + off); off += a256(4 * (size_t)kSamples * (b > 0 ? b : 1));
+    w.cells = reinterpret_cast<int *>(p + off); off += a256(4 * (w.total_cells + 1));
+    w.point_cell = reinterpret_cast<int *>(p + off); off += a256(4 * (size_t)n);
+    w.point_slot = reinterpret_cast<int *>(p + off); off += a256(4 * (size_t)n);
+    w.sorted = reinterpret_cast<float4 *>(p + off); off += a256(16 * (size_t)n);
+    w.partial = reinterpret_cast<int *>(p + off); off += a256(4 * scan_partial_ints((long long)w.total_cells));
+    w.bytes = off;
+    return w;
+}
+
+size_t knn_grid_workspace_bytes(int n, int m, int b) {
+    (void)m;
+    return carve(nullptr, n, b).bytes;
+}
+
+template <int K>
+static void launch_query(bool self, int m, int b, int nsample, const float *new_xyz, const int *new_offset,
+                         const GridWs &w, int *idx, float *dist2, cudaStream_t st) {
+    const int grid = div_up(m, kQueryBlock);
+    if (self)
+        knn_grid_kernel<K, true><<<grid, kQueryBlock, 0, st>>>(m, b, nsample, new_xyz, new_offset, w.desc, w.cells,
+                                                               w.sorted, idx, dist2);
+    else
+        knn_grid_kernel<K, false><<<grid, kQueryBlock, 0, st>>>(m, b, nsample, new_xyz, new_offset, w.desc, w.cells,
+                                                                w.sorted, idx, dist2);
+}
+
+template <int K>
+static void launch_sample(int b, int nsample, const float *xyz, const int *offset, float *samples, cudaStream_t st) {
+    knn_sample_kernel<K><<<div_up((long long)b * kSamples * 32, 128), 128, 0, st>>>(b, nsample, xyz, offset, samples);
+}
+
+int knn_grid_launch(int m, int nsample, int n, int b, const float *xyz, const float *new_xyz,
+                    const int *offset, const int *new_offset, int *idx, float *dist2, void *ws,
+                    size_t ws_bytes, cudaStream_t st) {
+    if (b <= 0 || n <= 0) {  // no candidates: everything is padding
+        return AOPT_ERR_INVALID_ARGUMENT;
+    }
+    GridWs w = carve(ws, n, b);
+    if (ws_bytes < w.bytes) return AOPT_ERR_WORKSPACE;
+    float scale = 1.25f;
+    if (const char *e = getenv("AOPT_KNN_CELL_SCALE")) {
+        float v = (float)atof(e);
+        if (v > 0.01f && v < 100.f) scale = v;
+    }
+    const bool self = (new_xyz == xyz) && (new_offset == offset) && (m == n);
+
+    cudaMemsetAsync(w.cells, 0, 4 * (w.total_cells + 1), st);
+    if (nsample <= 1) launch_sample<1>(b, nsample, xyz, offset, w.samples, st);
+    else if (nsample <= 3) launch_sample<3>(b, nsample, xyz, offset, w.samples, st);
+    else if (nsample <= 4) launch_sample<4>(b, nsample, xyz, offset, w.samples, st);
+    else if (nsample <= 8) launch_sample<8>(b, nsample, xyz, offset, w.samples, st);
+    else if (nsample <= 16) launch_sample<16>(b, nsample, xyz, offset, w.samples, st);
+    else launch_sample<32>(b, nsample, xyz, offset, w.samples, st);
+    grid_setup_kernel<<<b, 256, 0, st>>>(b, n, xyz, offset, w.samples, scale, w.desc);
+    grid_count_kernel<<<div_up(n, 256), 256, 0, st>>>(n, b, xyz, offset, w.desc, w.cells, w.point_cell, w.point_slot);
+    launch_exclusive_scan(w.cells, w.cells, (int)w.total_cells, w.partial, st);
+    grid_fill_kernel<<<div_up(n, 256), 256, 0, st>>>(n, xyz, w.cells, w.point_cell, w.point_slot, w.sorted);
+    if (nsample <= 1) launch_query<1>(self, m, b, nsample, new_xyz, new_offset, w, idx, dist2, st);
+    else if (nsample <= 3) launch_query<3>(self, m, b, nsample, new_xyz, new_offset, w, idx, dist2, st);
+    else if (nsample <= 4) launch_query<4>(self, m, b, nsample, new_xyz, new_offset, w, idx, dist2, st);
+    else if (nsample <= 8) launch_query<8>(self, m, b, nsample, new_xyz, new_offset, w, idx, dist2, st);
+    else if (nsample <= 16) launch_query<16>(self, m, b, nsample, new_xyz, new_offset, w, idx, dist2, st);
+    else launch_query<32>(self, m, b, nsample, new_xyz, new_offset, w, idx, dist2, st);
+    return check_launch();
+}
+
+}  // namespace aopt

@@ -1,0 +1,229 @@
+// pool.cu — GridPool: voxel keys and the per-voxel segment reduction (mean coord, max feature).
+//
+// Replaces, from /root/reference/pointcept/models/point_transformer_v2/point_transformer_v2m2_base.py:
+//   :249-253  segment_csr(coord, ptr, "min")            → aopt_segment_min3
+//   :257-259  voxel_grid(coord - start[batch], size, batch, start=0)   → aopt_voxel_keys
+//   :265-266  segment_csr(coord[sorted], idx_ptr, "mean"), segment_csr(feat[sorted], idx_ptr, "max")
+//                                                        → aopt_pool_forward (no permuted copies)
+//   autograd of :266 (scatter of the gradient to the arg-max rows)     → aopt_pool_backward
+// torch_scatter / torch_cluster are not vendored by the reference; their semantics are restated
+// in oracle/torch_ref.py (segment_csr, voxel_grid_keys) and these kernels follow that restatement.
+//
+// Bytes: forward reads 4NC + 12N + 4N (order) + 4(N'+1), writes 8N'C + 12N';
+// backward reads 8N'C + 4N, writes 4NC.
+#include <float.h>
+
+#include "common.cuh"
+#include "knn_common.cuh"  // find_segment
+
+namespace aopt {
+
+constexpr int kPoolBlock = 256;
+
+// One block per scene: component-wise minimum of its coordinates.
+__global__ void __launch_bounds__(256)
+segment_min3_kernel(int n, int b, const float *__restrict__ coord, const int *__restrict__ offset,
+                    float *__restrict__ start_out) {
+    __shared__ float red[3][8];
+    const int sc = blockIdx.x;
+    const int s = max(sc == 0 ? 0 : __ldg(offset + sc - 1), 0), e = min(__ldg(offset + sc), n);
+    float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX};  // torch_scatter "min" starts from the dtype maximum
+    for (int i = s + threadIdx.x; i < e; i += 256) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) lo[a] = fminf(lo[a], __ldg(coord + (size_t)i * 3 + a));
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], d));
+        if ((threadIdx.x & 31) == 0) red[a][threadIdx.x >> 5] = lo[a];
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        float v = red[threadIdx.x][0];
+        for (int w = 1; w < 8; ++w) v = fminf(v, red[threadIdx.x][w]);
+        start_out[sc * 3 + threadIdx.x] = (e > s) ? v : 0.f;  // empty segment → 0 (segment_csr fill)
+    }
+}
+
+constexpr int kCellBits = 18, kSceneBits = 10;
+
+__global__ void __launch_bounds__(kPoolBlock)
+voxel_keys_kernel(int n, int b, const float *__restrict__ coord, const int *__restrict__ offset,
+                  const float *__restrict__ start, float grid_size, int64_t *__restrict__ keys,
+                  int *__restrict__ status_flag) {
+    const int i = blockIdx.x * kPoolBlock + threadIdx.x;
+    if (i >= n) return;
+    int sc = find_segment(i, offset, b);
+    if (sc >= b) sc = b - 1;
+    int64_t cell[3];
+    bool bad = sc >= (1 << kSceneBits);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        // fp32 subtract then IEEE fp32 divide then truncate — the arithmetic of
+        // (coord - start[batch]) / size → .long() in torch_cluster.grid_cluster
+        float rel = __fsub_rn(__ldg(coord + (size_t)i * 3 + a), __ldg(start + sc * 3 + a));
+        float q = __fdiv_rn(rel, grid_size);
+        int64_t cq = (int64_t)q;
+        if (cq < 0 || cq >= (1LL << kCellBits)) { bad = true; cq = cq < 0 ? 0 : (1LL << kCellBits) - 1; }
+        cell[a] = cq;
+    }
+    keys[i] = ((int64_t)sc << (3 * kCellBits)) | (cell[2] << (2 * kCellBits)) | (cell[1] << kCellBits) | cell[0];
+    if (bad && status_flag) *status_flag = 1;
+}
+
+// One thread per (voxel, 4-channel chunk): running max + the original id of the first maximal point.
+template <int VEC>
+__global__ void __launch_bounds__(kPoolBlock)
+pool_forward_kernel(long long n_vox, int chunks, int c, const float *__restrict__ feat,
+                    const float *__restrict__ coord, const int *__restrict__ order,
+                    const int *__restrict__ idx_ptr, float *__restrict__ out_feat,
+                    int *__restrict__ argmax, float *__restrict__ out_coord) {
+    const long long total = n_vox * chunks;
+    const long long step = (long long)gridDim.x * kPoolBlock;
+    for (long long t = (long long)blockIdx.x * kPoolBlock + threadIdx.x; t < total; t += step) {
+        const long long v = t / chunks;
+        const int col = (int)(t - v * chunks);
+        const int e0 = __ldg(idx_ptr + v), e1 = __ldg(idx_ptr + v + 1);
+        float best[VEC];
+        int arg[VEC];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) { best[i] = -FLT_MAX; arg[i] = -1; }
+        float sx = 0.f, sy = 0.f, sz = 0.f;
+        for (int e = e0; e < e1; ++e) {
+            const int pt = __ldg(order + e);
+            float x[VEC];
+            if constexpr (VEC == 4) {
+                float4 q = ldg_stream4(feat + (size_t)pt * c + col * 4);
+                x[0] = q.x; x[1] = q.y; x[2] = q.z; x[3] = q.w;
+            } else {
+                x[0] = __ldg(feat + (size_t)pt * c + col);
+            }
+#pragma unroll
+            for (int i = 0; i < VEC; ++i)
+                if (x[i] > best[i]) { best[i] = x[i]; arg[i] = pt; }
+            if (col == 0 && out_coord) {  // sequential sum in `order`, like segment_csr
+                sx += __ldg(coord + (size_t)pt * 3 + 0);
+                sy += __ldg(coord + (size_t)pt * 3 + 1);
+                sz += __ldg(coord + (size_t)pt * 3 + 2);
+            }
+        }
+        const size_t o = (size_t)v * c + col * VEC;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            if (arg[i] < 0) best[i] = 0.f;  // nothing compared greater (empty / all NaN): segment_csr writes 0
+        }
+        if constexpr (VEC == 4) {
+            *reinterpret_cast<float4 *>(out_feat + o) = make_float4(best[0], best[1], best[2], best[3]);
+            *reinterpret_cast<int4 *>(argmax + o) = make_int4(arg[0], arg[1], arg[2], arg[3]);
+        } else {
+            out_feat[o] = best[0];
+            argmax[o] = arg[0];
+        }
+        if (col == 0 && out_coord) {
+            const float cnt = (float)max(e1 - e0, 1);
+            out_coord[v * 3 + 0] = sx / cnt;
+            out_coord[v * 3 + 1] = sy / cnt;
+            out_coord[v * 3 + 2] = sz / cnt;
+        }
+    }
+}
+
+// Gather form of the max-pool backward: every (point, channel) looks up its own voxel, so the
+// whole (N,C) gradient is written once, coalesced, with no memset and no atomics.
+template <int VEC>
+__global__ void __launch_bounds__(kPoolBlock)
+pool_backward_kernel(long long n, int chunks, int c, const float *__restrict__ grad_out,
+                     const int *__restrict__ argmax, const int *__restrict__ cluster,
+                     float *__restrict__ grad_feat) {
+    const long long total = n * chunks;
+    const long long step = (long long)gridDim.x * kPoolBlock;
+    for (long long t = (long long)blockIdx.x * kPoolBlock + threadIdx.x; t < total; t += step) {
+        const long long pt = t / chunks;
+        const int col = (int)(t - pt * chunks);
+        const int v = __ldg(cluster + pt);
+        const size_t src = (size_t)v * c + col * VEC, dst = (size_t)pt * c + col * VEC;
+        if constexpr (VEC == 4) {
+            const int4 a = __ldg(reinterpret_cast<const int4 *>(argmax + src));
+            const float4 gq = ldg_gather4(grad_out + src);
+            float4 r;
+            r.x = a.x == (int)pt ? gq.x : 0.f; r.y = a.y == (int)pt ? gq.y : 0.f;
+            r.z = a.z == (int)pt ? gq.z : 0.f; r.w = a.w == (int)pt ? gq.w : 0.f;
+            stg_stream4(grad_feat + dst, r);
+        } else {
+            grad_feat[dst] = __ldg(argmax + src) == (int)pt ? __ldg(grad_out + src) : 0.f;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+offset2batch_kernel(int n, int b, const int *__restrict__ offset, int64_t *__restrict__ batch) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i < n) batch[i] = find_segment(i, offset, b);
+}
+
+}  // namespace aopt
+
+using namespace aopt;
+
+extern "C" int aopt_offset2batch(int n, int b, const int *offset, int64_t *batch, aopt_stream_t stream) {
+    if (n < 0 || b < 0) return AOPT_ERR_INVALID_ARGUMENT;
+    if (n == 0) return AOPT_OK;
+    if (!offset || !batch) return AOPT_ERR_INVALID_ARGUMENT;
+    offset2batch_kernel<<<div_up(n, 256), 256, 0, as_stream(stream)>>>(n, b, offset, batch);
+    return check_launch();
+}
+
+extern "C" int aopt_segment_min3(int n, int b, const float *coord, const int *offset, float *start,
+                                 aopt_stream_t stream) {
+    if (n < 0 || b < 0) return AOPT_ERR_INVALID_ARGUMENT;
+    if (b == 0) return AOPT_OK;
+    if (!coord || !offset || !start) return AOPT_ERR_INVALID_ARGUMENT;
+    segment_min3_kernel<<<b, 256, 0, as_stream(stream)>>>(n, b, coord, offset, start);
+    return check_launch();
+}
+
+extern "C" int aopt_voxel_keys(int n, int b, const float *coord, const int *offset, const float *start,
+                               float grid_size, int64_t *keys, int *status_flag, aopt_stream_t stream) {
+    if (n < 0 || b < 1 || !(grid_size > 0.f)) return AOPT_ERR_INVALID_ARGUMENT;
+    if (n == 0) return AOPT_OK;
+    if (!coord || !offset || !start || !keys) return AOPT_ERR_INVALID_ARGUMENT;
+    voxel_keys_kernel<<<div_up(n, kPoolBlock), kPoolBlock, 0, as_stream(stream)>>>(n, b, coord, offset, start,
+                                                                               grid_size, keys, status_flag);
+    return check_launch();
+}
+
+extern "C" int aopt_pool_forward(int n_vox, int c, const float *feat, const float *coord, const int *order,
+                                 const int *idx_ptr, float *out_feat, int *argmax, float *out_coord,
+                                 aopt_stream_t stream) {
+    if (n_vox < 0 || c < 1) return AOPT_ERR_INVALID_ARGUMENT;
+    if (n_vox == 0) return AOPT_OK;
+    if (!feat || !order || !idx_ptr || !out_feat || !argmax || (out_coord && !coord)) return AOPT_ERR_INVALID_ARGUMENT;
+    const bool vec = (c % 4 == 0) && aligned16(feat) && aligned16(out_feat) && aligned16(argmax);
+    if (vec) {
+        const int chunks = c / 4;
+        pool_forward_kernel<4><<<stride_grid((long long)n_vox * chunks, kPoolBlock, 8), kPoolBlock, 0, as_stream(stream)>>>(
+            n_vox, chunks, c, feat, coord, order, idx_ptr, out_feat, argmax, out_coord);
+    } else {
+        pool_forward_kernel<1><<<stride_grid((long long)n_vox * c, kPoolBlock, 8), kPoolBlock, 0, as_stream(stream)>>>(
+            n_vox, c, c, feat, coord, order, idx_ptr, out_feat, argmax, out_coord);
+    }
+    return check_launch();
+}
+
+extern "C" int aopt_pool_backward(int n, int c, const float *grad_out, const int *argmax, const int *cluster,
+                                  float *grad_feat, aopt_stream_t stream) {
+    if (n < 0 || c < 1) return AOPT_ERR_INVALID_ARGUMENT;
+    if (n == 0) return AOPT_OK;
+    if (!grad_out || !argmax || !cluster || !grad_feat) return AOPT_ERR_INVALID_ARGUMENT;
+    const bool vec = (c % 4 == 0) && aligned16(grad_out) && aligned16(argmax) && aligned16(grad_feat);
+    if (vec) {
+        const int chunks = c / 4;
+        pool_backward_kernel<4><<<stride_grid((long long)n * chunks, kPoolBlock, 8), kPoolBlock, 0, as_stream(stream)>>>(
+            n, chunks, c, grad_out, argmax, cluster, grad_feat);
+    } else {
+        pool_backward_kernel<1><<<stride_grid((long long)n * c, kPoolBlock, 8), kPoolBlock, 0, as_stream(stream)>>>(
+            n, c, c, grad_out, argmax, cluster, grad_feat);
+    }
+    return check_launch();
+}

@@ -1,0 +1,177 @@
+"""GridPool operators (new names): voxel partition + per-voxel segment reduction, and the "map"
+unpooling gather.  Successors of the third-party op chain in
+/root/reference/pointcept/models/point_transformer_v2/point_transformer_v2m2_base.py:244-269
+(offset2batch loop + segment_csr(min) + voxel_grid + torch.unique + torch.sort + two permuted
+copies + segment_csr(mean) + segment_csr(max)) and :308-309 (`proj(feat)[cluster]`).
+
+Kernels: aopt_segment_min3, aopt_voxel_keys, aopt_pool_forward/backward, aopt_grouping_forward/
+backward (map unpool).  The key sort itself is torch.sort (library radix sort) in this round; a
+hand-written sort is listed under SURVEY.md §8f-1 "next".
+"""
+from __future__ import annotations
+
+from typing import NamedTuple
+
+import torch
+from torch.autograd import Function
+
+from .. import _lib
+from ._csr import NeighbourCSR, get_csr
+
+_SCENE_SHIFT = 54  # 3 x 18 bits of cell coordinates below the scene id (pool.cu)
+
+
+class VoxelPartition(NamedTuple):
+    order: torch.Tensor      # (n,) int32 point ids sorted by voxel (stable: ascending id inside a voxel)
+    idx_ptr: torch.Tensor    # (n_vox+1,) int32
+    cluster: torch.Tensor    # (n,) int64 voxel id of every point (the reference's `cluster`)
+    cluster32: torch.Tensor  # (n,) int32 copy used by the kernels
+    offset: torch.Tensor     # (b,) int64 cumulative voxel counts per scene (batch2offset)
+    n_vox: int
+
+
+def voxel_partition(coord, offset, grid_size, start=None) -> VoxelPartition:
+    """Voxel id of every point, voxels numbered in ascending (scene, z, y, x) order — the order
+    torch.unique(sorted=True) gives the keys of torch_cluster.grid_cluster (…v2m2_base.py:257-264)."""
+    dev = _lib.require_cuda(coord, offset)
+    lib = _lib.load()
+    assert coord.is_contiguous() and coord.dtype == torch.float32
+    n, b = coord.shape[0], offset.numel()
+    off32 = offset.int().contiguous()
+    keys = torch.empty(n, dtype=torch.int64, device=dev)
+    flag = torch.zeros(1, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        if start is None:
+            start = torch.empty((b, 3), dtype=torch.float32, device=dev)
+            _lib.check(lib.aopt_segment_min3(n, b, _lib.ptr(coord), _lib.ptr(off32), _lib.ptr(start), _lib.stream()),
+                       "segment_min3")
+        else:
+            start = start.float().contiguous()
+        _lib.check(
+            lib.aopt_voxel_keys(n, b, _lib.ptr(coord), _lib.ptr(off32), _lib.ptr(start), float(grid_size),
+                                _lib.ptr(keys), _lib.ptr(flag), _lib.stream()),
+            "voxel_keys",
+        )
+    sorted_keys, order = torch.sort(keys, stable=True)
+    is_new = torch.ones(n, dtype=torch.bool, device=dev)
+    if n > 1:
+        is_new[1:] = sorted_keys[1:] != sorted_keys[:-1]
+    voxel_of_sorted = torch.cumsum(is_new, 0) - 1                     # int64
+    first = torch.nonzero(is_new).flatten()                           # host sync (like torch.unique)
+    n_vox = first.numel()
+    if int(flag.item()) != 0:
+        raise ValueError("voxel_partition: a voxel coordinate exceeds 2^18 cells per axis or 1024 scenes")
+    idx_ptr = torch.empty(n_vox + 1, dtype=torch.int32, device=dev)
+    idx_ptr[:n_vox] = first
+    idx_ptr[n_vox] = n
+    cluster = torch.empty(n, dtype=torch.int64, device=dev)
+    cluster[order] = voxel_of_sorted
+    scene = (sorted_keys[first] >> _SCENE_SHIFT)
+    new_offset = torch.cumsum(torch.bincount(scene, minlength=b), 0)   # batch2offset (…v2m2_base.py:268)
+    order32 = order.int()
+    cluster32 = cluster.int()
+    # the partition IS the CSR of `cluster` (rows = voxels, entries ascending) → free backward map
+    cluster32._aopt_csr = {(n_vox, 0): NeighbourCSR(idx_ptr, order32, n_vox, 0, cluster32._version)}
+    return VoxelPartition(order32, idx_ptr, cluster, cluster32, new_offset, n_vox)
+
+
+class _PoolFn(Function):
+    @staticmethod
+    def forward(ctx, feat, coord, order, idx_ptr, cluster32, n_vox):
+        lib = _lib.load()
+        n, c = feat.shape
+        dev = feat.device
+        out_feat = torch.empty((n_vox, c), dtype=torch.float32, device=dev)
+        argmax = torch.empty((n_vox, c), dtype=torch.int32, device=dev)
+        out_coord = torch.empty((n_vox, 3), dtype=torch.float32, device=dev)
+        if n_vox > 0:
+            with torch.cuda.device(dev):
+                _lib.check(
+                    lib.aopt_pool_forward(n_vox, c, _lib.ptr(feat), _lib.ptr(coord), _lib.ptr(order),
+                                          _lib.ptr(idx_ptr), _lib.ptr(out_feat), _lib.ptr(argmax),
+                                          _lib.ptr(out_coord), _lib.stream()),
+                    "pool_forward",
+                )
+        ctx.save_for_backward(argmax, cluster32)
+        ctx.shape = (n, c)
+        ctx.mark_non_differentiable(out_coord, argmax)
+        return out_feat, out_coord, argmax
+
+    @staticmethod
+    def backward(ctx, grad_feat, _gc, _ga):
+        lib = _lib.load()
+        argmax, cluster32 = ctx.saved_tensors
+        n, c = ctx.shape
+        grad_feat = grad_feat.contiguous().float()
+        grad_in = torch.empty((n, c), dtype=torch.float32, device=grad_feat.device)
+        if n > 0:
+            with torch.cuda.device(grad_feat.device):
+                _lib.check(
+                    lib.aopt_pool_backward(n, c, _lib.ptr(grad_feat), _lib.ptr(argmax), _lib.ptr(cluster32),
+                                           _lib.ptr(grad_in), _lib.stream()),
+                    "pool_backward",
+                )
+        return grad_in, None, None, None, None, None
+
+
+def grid_pool(coord, feat, offset, grid_size, start=None, return_partition=False):
+    """GridPool after its fc/norm/act: returns ([coord', feat', offset'], cluster) like
+    GridPool.forward (…v2m2_base.py:244-269); feat' = per-voxel max (gradient to the arg-max row),
+    coord' = per-voxel mean, offset' int64, cluster (n,) int64."""
+    assert coord.is_contiguous() and feat.is_contiguous()
+    part = voxel_partition(coord.float(), offset, grid_size, start)
+    out_feat, out_coord, _ = _PoolFn.apply(feat.float(), coord.float(), part.order, part.idx_ptr, part.cluster32,
+                                           part.n_vox)
+    if return_partition:
+        return [out_coord, out_feat, part.offset], part.cluster, part
+    return [out_coord, out_feat, part.offset], part.cluster
+
+
+class _UnpoolMapFn(Function):
+    @staticmethod
+    def forward(ctx, feat, cluster32):
+        lib = _lib.load()
+        n_vox, c = feat.shape
+        n = cluster32.numel()
+        out = torch.empty((n, c), dtype=torch.float32, device=feat.device)
+        if n > 0:
+            with torch.cuda.device(feat.device):
+                _lib.check(
+                    lib.aopt_grouping_forward(n, 1, c, _lib.ptr(feat), _lib.ptr(cluster32), _lib.ptr(out), c,
+                                              _lib.stream()),
+                    "unpool_map_forward",
+                )
+        ctx.cluster32, ctx.shape = cluster32, (n_vox, c)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad):
+        lib = _lib.load()
+        n_vox, c = ctx.shape
+        grad = grad.contiguous().float()
+        csr = get_csr(ctx.cluster32, n_vox, 0)
+        grad_in = torch.empty((n_vox, c), dtype=torch.float32, device=grad.device)
+        with torch.cuda.device(grad.device):
+            _lib.check(
+                lib.aopt_grouping_backward(n_vox, c, _lib.ptr(grad), c, _lib.ptr(csr.rowptr), _lib.ptr(csr.perm),
+                                           1.0, _lib.ptr(grad_in), _lib.stream()),
+                "unpool_map_backward",
+            )
+        return grad_in, None
+
+
+def unpool_map(feat, cluster):
+    """`feat[cluster]` (…v2m2_base.py:308-309) with an atomic-free segmented-sum backward.
+    `cluster` may be the int64 tensor returned by grid_pool or a VoxelPartition."""
+    if isinstance(cluster, VoxelPartition):
+        c32 = cluster.cluster32
+    else:
+        c32 = getattr(cluster, "_aopt_c32", None)
+        if c32 is None:
+            c32 = cluster.int().contiguous()
+            try:
+                cluster._aopt_c32 = c32
+            except Exception:  # pragma: no cover
+                pass
+    _lib.require_cuda(feat, c32)
+    return _UnpoolMapFn.apply(feat.float().contiguous(), c32)

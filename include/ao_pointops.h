@@ -1,0 +1,169 @@
+/*
+ * ao_pointops.h — C ABI of libao_pointops.so, the B200 (sm_100a) point-operator library that
+ * replaces the native side of the reference's `pointops._C` for the PTv2m2 hot path.
+ *
+ * Boundary conventions (mirror the reference launchers):
+ *   - every entry point takes raw DEVICE pointers and sizes, borrows them for the call only,
+ *     allocates nothing and keeps no state (re-entrant; safe from the autograd thread);
+ *   - outputs and scratch ("workspace") are caller-allocated; ask *_workspace_bytes() first;
+ *   - kernels are launched on the caller's stream (`stream` is a cudaStream_t passed as void*;
+ *     NULL = legacy default stream, which is what the reference launchers use implicitly);
+ *   - the return value is an aopt status (0 = AOPT_OK).  The reference launchers return void and
+ *     never check errors; here argument errors and launch errors are reported.
+ *   - offsets are cumulative END indices (`offset[b]` = one past the last point of scene b), int32,
+ *     exactly the reference's offset-encoded batch layout (libs/pointops/functions/query.py:22).
+ *
+ * Reference interfaces replaced (paths relative to /root/reference/libs/pointops/src):
+ *   aopt_knn_query               knn_query/knn_query_cuda_kernel.h:15   knn_query_cuda_launcher
+ *   aopt_grouping_forward        grouping/grouping_cuda_kernel.h:14     grouping_forward_cuda_launcher
+ *   aopt_grouping_backward       grouping/grouping_cuda_kernel.h:15     grouping_backward_cuda_launcher
+ *   aopt_interpolation_forward   interpolation/interpolation_cuda_kernel.h  interpolation_forward_cuda_launcher
+ *   aopt_interpolation_backward  interpolation/interpolation_cuda_kernel.h  interpolation_backward_cuda_launcher
+ *   aopt_aggregation_forward/backward   aggregation/aggregation_cuda_kernel.h   (PTv1 "share-planes" layout)
+ *   aopt_subtraction_forward/backward   subtraction/subtraction_cuda_kernel.h
+ * and the torch / third-party op chains of the PTv2m2 caller
+ * (pointcept/models/point_transformer_v2/point_transformer_v2m2_base.py):
+ *   aopt_group_xyz, aopt_gather_sub_*     :109,:112 + libs/pointops/functions/grouping.py:36-60
+ *   aopt_gva_*                            :119-128   (softmax over k, mask, grouped weighted sum)
+ *   aopt_voxel_*, aopt_pool_*             :244-269   (voxel_grid + segment_csr mean/max)
+ *   aopt_interp_weights                   libs/pointops/functions/interpolation.py:15-17
+ *   aopt_csr_build                        (new) transpose of the neighbour graph → atomic-free backward
+ */
+#ifndef AO_POINTOPS_H_
+#define AO_POINTOPS_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void *aopt_stream_t; /* cudaStream_t */
+
+enum {
+    AOPT_OK = 0,
+    AOPT_ERR_INVALID_ARGUMENT = 1, /* bad size / NULL pointer / k out of range */
+    AOPT_ERR_WORKSPACE = 2,        /* workspace missing or too small */
+    AOPT_ERR_LAUNCH = 3,           /* cudaGetLastError() != cudaSuccess after a launch */
+    AOPT_ERR_UNSUPPORTED = 4
+};
+
+#define AOPT_MAX_NSAMPLE 128 /* reference limit: knn_query_cuda_kernel.cu:82-83 */
+
+/* kNN search strategy (all three are exact and return identical results). */
+enum { AOPT_KNN_AUTO = 0, AOPT_KNN_TILE = 1, AOPT_KNN_GRID = 2 };
+
+const char *aopt_version(void);
+const char *aopt_status_string(int status);
+/* cudaGetErrorString of the last launch error seen by this thread (for AOPT_ERR_LAUNCH). */
+const char *aopt_last_cuda_error(void);
+
+/* ---- offset-encoded batch layout ---------------------------------------------------------- */
+/* batch[i] = scene of point i (int64, like pointcept/models/utils.py:11-24). */
+int aopt_offset2batch(int n, int b, const int *offset, int64_t *batch, aopt_stream_t stream);
+
+/* ---- kNN ---------------------------------------------------------------------------------- */
+/* xyz (n,3), new_xyz (m,3) row-major fp32; offset/new_offset (b,) int32.
+ * idx (m,nsample) int32, -1 padded; dist2 (m,nsample) fp32 SQUARED distances, 1e10 padded, rows
+ * ascending by (dist2, idx).  dist2 = fma(dz,dz,fma(dx,dx,dy*dy)), d = query - candidate: the
+ * bit pattern the reference kernel produces when built for sm_100a. */
+size_t aopt_knn_workspace_bytes(int n, int m, int b, int nsample, int method);
+int aopt_knn_query(int m, int nsample, int n, int b, const float *xyz, const float *new_xyz,
+                   const int *offset, const int *new_offset, int *idx, float *dist2, int method,
+                   void *workspace, size_t workspace_bytes, aopt_stream_t stream);
+
+/* ---- transposed neighbour graph (CSR) ------------------------------------------------------ */
+/* idx: n_entries int32 values in [-1, n_src) (flattened (m,nsample)).  Produces rowptr (n_src+1)
+ * and perm (n_entries): perm[rowptr[j] .. rowptr[j+1]) = flat positions p with idx[p] == j in
+ * ASCENDING p (deterministic summation order).  negative_mode 0: idx<0 entries are dropped;
+ * 1: idx<0 is wrapped to idx+n_src (python negative indexing, interpolation.py:21). */
+size_t aopt_csr_workspace_bytes(int n_src, int64_t n_entries);
+int aopt_csr_build(int n_src, int64_t n_entries, const int *idx, int negative_mode, int *rowptr,
+                   int *perm, void *workspace, size_t workspace_bytes, aopt_stream_t stream);
+
+/* ---- grouping (neighbour gather) ----------------------------------------------------------- */
+/* output[(p)*out_stride + ch] = input[idx[p]*c + ch], zeros when idx[p] < 0; p in [0, m*nsample). */
+int aopt_grouping_forward(int m, int nsample, int c, const float *input, const int *idx,
+                          float *output, int out_stride, aopt_stream_t stream);
+/* grad_input[j,:] = scale * sum over CSR row j of grad_output[perm[e]*go_stride + :]  (no atomics). */
+int aopt_grouping_backward(int n, int c, const float *grad_output, int go_stride, const int *rowptr,
+                           const int *perm, float scale, float *grad_input, aopt_stream_t stream);
+/* out[p*out_stride + 0..2] = (xyz[idx[p]] - new_xyz[p / nsample]) * sign(idx[p]+1). */
+int aopt_group_xyz(int m, int nsample, const float *xyz, const float *new_xyz, const int *idx,
+                   float *out, int out_stride, aopt_stream_t stream);
+/* out[m,s,:] = key[idx[m,s],:] - query[m,:]   (key row = 0 when idx < 0). */
+int aopt_gather_sub_forward(int m, int nsample, int c, const float *key, const float *query,
+                            const int *idx, float *out, aopt_stream_t stream);
+/* out[m,:] = scale * sum_s grad[m,s,:]   (grad_query of gather_sub uses scale = -1). */
+int aopt_sum_over_k(int m, int nsample, int c, const float *grad, float scale, float *out,
+                    aopt_stream_t stream);
+
+/* ---- GroupedVectorAttention softmax-over-k weighted aggregation ---------------------------- */
+/* value (n_src,c) un-gathered; peb (n,nsample,c) or NULL; logits (n,nsample,g); idx (n,nsample).
+ * out[n, gi*I+i] = sum_s (value[idx[n,s], gi*I+i] + peb[n,s,gi*I+i]) * softmax_s(logits[n,:,gi])[s]
+ *                  * sign(idx[n,s]+1),   I = c/g.     prob (n,nsample,g) receives the UNMASKED
+ * softmax (saved for backward) when not NULL. */
+int aopt_gva_forward(int n, int nsample, int c, int g, const float *value, const float *peb,
+                     const float *logits, const int *idx, float *out, float *prob,
+                     aopt_stream_t stream);
+/* grad_peb (n,nsample,c) (may be NULL) and grad_logits (n,nsample,g). */
+int aopt_gva_backward_query(int n, int nsample, int c, int g, const float *grad_out,
+                            const float *value, const float *peb, const float *prob, const int *idx,
+                            float *grad_peb, float *grad_logits, aopt_stream_t stream);
+/* grad_value (n_src,c) through the CSR of idx (no atomics). */
+int aopt_gva_backward_value(int n_src, int nsample, int c, int g, const float *grad_out,
+                            const float *prob, const int *rowptr, const int *perm,
+                            float *grad_value, aopt_stream_t stream);
+
+/* ---- GridPool ----------------------------------------------------------------------------- */
+/* start (b,3) = per-scene minimum corner (segment_csr(coord, ptr, "min")). */
+int aopt_segment_min3(int n, int b, const float *coord, const int *offset, float *start,
+                      aopt_stream_t stream);
+/* keys[i] = order-preserving packing of (scene, z, y, x) voxel coordinates with
+ * cell_d = (int)((coord_d - start_d) / grid_size) in fp32 — same cells and same sort order as
+ * torch_cluster.grid_cluster's Σ cell_d·stride_d.  status_flag (device int, may be NULL) is set
+ * to 1 if a cell coordinate does not fit the packing (18 bits per axis, 10 bits scene). */
+int aopt_voxel_keys(int n, int b, const float *coord, const int *offset, const float *start,
+                    float grid_size, int64_t *keys, int *status_flag, aopt_stream_t stream);
+/* Points sorted by voxel: order (n) = point ids, idx_ptr (n_vox+1).  out_feat/argmax (n_vox,c):
+ * max over the voxel and the ORIGINAL id of the first maximal point; out_coord (n_vox,3) = mean
+ * (sequential sum in `order`, divided by the count). */
+int aopt_pool_forward(int n_vox, int c, const float *feat, const float *coord, const int *order,
+                      const int *idx_ptr, float *out_feat, int *argmax, float *out_coord,
+                      aopt_stream_t stream);
+/* grad_feat[i,ch] = grad_out[cluster[i],ch] if argmax[cluster[i],ch] == i else 0. */
+int aopt_pool_backward(int n, int c, const float *grad_out, const int *argmax, const int *cluster,
+                       float *grad_feat, aopt_stream_t stream);
+
+/* ---- three-NN inverse-distance interpolation ---------------------------------------------- */
+/* weight[n,i] = r_i / sum_j r_j,  r = 1/(sqrt(dist2)+1e-8)  (interpolation.py:15-17). */
+int aopt_interp_weights(int n, int k, const float *dist2, float *weight, aopt_stream_t stream);
+/* output[n,:] = sum_i input[wrap(idx[n,i]),:] * weight[n,i];  wrap(j) = j<0 ? j+m : j. */
+int aopt_interpolation_forward(int n, int c, int k, int m, const float *input, const int *idx,
+                               const float *weight, float *output, aopt_stream_t stream);
+/* grad_input[j,:] = sum over CSR row j of grad_output[perm[e]/k,:] * weight[perm[e]]. */
+int aopt_interpolation_backward(int m, int c, int k, const float *grad_output, const float *weight,
+                                const int *rowptr, const int *perm, float *grad_input,
+                                aopt_stream_t stream);
+
+/* ---- PTv1-layout fused ops kept for API parity --------------------------------------------- */
+/* output[n,ch] = sum_s (input[idx[n,s],ch] + position[n,s,ch]) * weight[n,s,ch % w_c]. */
+int aopt_aggregation_forward(int n, int nsample, int c, int w_c, const float *input,
+                             const float *position, const float *weight, const int *idx,
+                             float *output, aopt_stream_t stream);
+/* grad_position (n,nsample,c), grad_weight (n,nsample,w_c) per query; grad_input through the CSR. */
+int aopt_aggregation_backward(int n, int nsample, int c, int w_c, const float *input,
+                              const float *position, const float *weight, const int *idx,
+                              const int *rowptr, const int *perm, const float *grad_output,
+                              float *grad_input, float *grad_position, float *grad_weight,
+                              aopt_stream_t stream);
+/* output[n,s,:] = input1[n,:] - input2[idx[n,s],:].  Backward: grad_input1 = aopt_sum_over_k(+1),
+ * grad_input2 = aopt_grouping_backward(scale = -1). */
+int aopt_subtraction_forward(int n, int nsample, int c, const float *input1, const float *input2,
+                             const int *idx, float *output, aopt_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AO_POINTOPS_H_ */

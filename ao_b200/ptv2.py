@@ -1,0 +1,373 @@
+"""PointTransformer V2 (mode 2) backbone routed through the ao_b200 point operators.
+
+Mirror of /root/reference/pointcept/models/point_transformer_v2/point_transformer_v2m2_base.py: same
+module tree, constructor arguments and parameter names, so a reference `state_dict` loads with
+`strict=True` and the golden fixtures produced by the reference modules (tests/golden/) can be
+replayed.  What changes is the op schedule underneath:
+
+  reference (per block, :103-129)                         here
+  -------------------------------------------------       ---------------------------------------
+  grouping(idx, key, coord, with_xyz=True)  (N,k,3+C)     pointops.group_xyz            (N,k,3)
+  key[...,3:] - query.unsqueeze(1)                        pointops.gva_relation         (N,k,C)
+  grouping(idx, value); value + peb; softmax; mask;       pointops.gva_aggregate        (N,C)
+  einsum                                                   (value never gathered to (N,k,C))
+  PointBatchNorm 3-D: transpose+contiguous x2 (:36-41)    BatchNorm1d on the (N·k, C) view
+  one kNN per BlockSequence (:223), 7 per forward          4: decoder stages reuse the encoder's
+                                                           neighbour lists (same coords, same k)
+  GridPool: offset2batch loop, voxel_grid, unique, sort,   pointops.grid_pool
+  2 permuted copies, 2 segment_csr (:244-269)
+  interpolation: 3 gather+mul+add passes (:311)            pointops.interpolation (fused fwd, CSR bwd)
+
+Dense per-point Linear layers stay torch.nn.Linear (cuBLAS tensor cores; bf16 under autocast).
+"""
+from __future__ import annotations
+
+from copy import deepcopy
+
+import torch
+import torch.nn as nn
+
+from . import pointops
+
+
+class DropPath(nn.Module):
+    """Stochastic depth per row (timm.models.layers.DropPath semantics for a (N,C) input)."""
+
+    def __init__(self, drop_prob: float = 0.0):
+        super().__init__()
+        self.drop_prob = float(drop_prob)
+
+    def forward(self, x):
+        if self.drop_prob == 0.0 or not self.training:
+            return x
+        keep = 1.0 - self.drop_prob
+        mask = x.new_empty((x.shape[0],) + (1,) * (x.dim() - 1)).bernoulli_(keep)
+        return x * mask.div_(keep)
+
+
+class PointBatchNorm(nn.Module):
+    """Batch Normalization for point features [N, C] or [N, L, C] (…v2m2_base.py:25-45)."""
+
+    def __init__(self, embed_channels):
+        super().__init__()
+        self.norm = nn.BatchNorm1d(embed_channels)
+
+    def forward(self, input: torch.Tensor) -> torch.Tensor:
+        if input.dim() == 3:
+            # same per-channel statistics as BatchNorm1d over (N, C, L), without the two transposes
+            n, l, c = input.shape
+            return self.norm(input.reshape(n * l, c)).view(n, l, c)
+        elif input.dim() == 2:
+            return self.norm(input)
+        raise NotImplementedError
+
+
+class GroupedVectorAttention(nn.Module):
+    def __init__(self, embed_channels, groups, attn_drop_rate=0.0, qkv_bias=True, pe_multiplier=False,
+                 pe_bias=True):
+        super().__init__()
+        self.embed_channels = embed_channels
+        self.groups = groups
+        assert embed_channels % groups == 0
+        self.attn_drop_rate = attn_drop_rate
+        self.qkv_bias = qkv_bias
+        self.pe_multiplier = pe_multiplier
+        self.pe_bias = pe_bias
+        self.linear_q = nn.Sequential(nn.Linear(embed_channels, embed_channels, bias=qkv_bias),
+                                      PointBatchNorm(embed_channels), nn.ReLU(inplace=True))
+        self.linear_k = nn.Sequential(nn.Linear(embed_channels, embed_channels, bias=qkv_bias),
+                                      PointBatchNorm(embed_channels), nn.ReLU(inplace=True))
+        self.linear_v = nn.Linear(embed_channels, embed_channels, bias=qkv_bias)
+        if self.pe_multiplier:
+            self.linear_p_multiplier = nn.Sequential(nn.Linear(3, embed_channels), PointBatchNorm(embed_channels),
+                                                     nn.ReLU(inplace=True), nn.Linear(embed_channels, embed_channels))
+        if self.pe_bias:
+            self.linear_p_bias = nn.Sequential(nn.Linear(3, embed_channels), PointBatchNorm(embed_channels),
+                                               nn.ReLU(inplace=True), nn.Linear(embed_channels, embed_channels))
+        self.weight_encoding = nn.Sequential(nn.Linear(embed_channels, groups), PointBatchNorm(groups),
+                                             nn.ReLU(inplace=True), nn.Linear(groups, groups))
+        self.softmax = nn.Softmax(dim=1)
+        self.attn_drop = nn.Dropout(attn_drop_rate)
+
+    def forward(self, feat, coord, reference_index):
+        query, key, value = self.linear_q(feat), self.linear_k(feat), self.linear_v(feat)
+        pos = pointops.group_xyz(reference_index, coord)                      # :109,:111
+        relation_qk = pointops.gva_relation(key, query, reference_index)      # :109,:112
+        peb = None
+        if self.pe_multiplier:
+            relation_qk = relation_qk * self.linear_p_multiplier(pos)
+        if self.pe_bias:
+            peb = self.linear_p_bias(pos).float()
+            relation_qk = relation_qk + peb
+        weight = self.weight_encoding(relation_qk)                            # (N,k,G) logits
+        if self.attn_drop_rate > 0.0 and self.training:
+            # dropout sits between softmax and mask (:122-125): un-fused tail for this rare setting
+            value_g = pointops.grouping(reference_index, value, coord, with_xyz=False)
+            if peb is not None:
+                value_g = value_g + peb
+            weight = self.attn_drop(self.softmax(weight.float()))
+            mask = torch.sign(reference_index + 1)
+            weight = weight * mask.unsqueeze(-1)
+            n, k, c = value_g.shape
+            out = torch.einsum("nsgi,nsg->ngi", value_g.view(n, k, self.groups, c // self.groups), weight)
+            return out.reshape(n, c)
+        return pointops.gva_aggregate(value, peb, weight, reference_index, self.groups)   # :110,:119-128
+
+
+class Block(nn.Module):
+    def __init__(self, embed_channels, groups, qkv_bias=True, pe_multiplier=False, pe_bias=True,
+                 attn_drop_rate=0.0, drop_path_rate=0.0, enable_checkpoint=False):
+        super().__init__()
+        self.attn = GroupedVectorAttention(embed_channels=embed_channels, groups=groups, qkv_bias=qkv_bias,
+                                           attn_drop_rate=attn_drop_rate, pe_multiplier=pe_multiplier,
+                                           pe_bias=pe_bias)
+        self.fc1 = nn.Linear(embed_channels, embed_channels, bias=False)
+        self.fc3 = nn.Linear(embed_channels, embed_channels, bias=False)
+        self.norm1 = PointBatchNorm(embed_channels)
+        self.norm2 = PointBatchNorm(embed_channels)
+        self.norm3 = PointBatchNorm(embed_channels)
+        self.act = nn.ReLU(inplace=True)
+        self.enable_checkpoint = enable_checkpoint
+        self.drop_path = DropPath(drop_path_rate) if drop_path_rate > 0.0 else nn.Identity()
+
+    def forward(self, points, reference_index):
+        coord, feat, offset = points
+        identity = feat
+        feat = self.act(self.norm1(self.fc1(feat)))
+        if self.enable_checkpoint:
+            from torch.utils.checkpoint import checkpoint
+
+            feat = checkpoint(self.attn, feat, coord, reference_index, use_reentrant=False)
+        else:
+            feat = self.attn(feat, coord, reference_index)
+        feat = self.act(self.norm2(feat))
+        feat = self.norm3(self.fc3(feat))
+        feat = identity + self.drop_path(feat)
+        feat = self.act(feat)
+        return [coord, feat, offset]
+
+
+class BlockSequence(nn.Module):
+    def __init__(self, depth, embed_channels, groups, neighbours=16, qkv_bias=True, pe_multiplier=False,
+                 pe_bias=True, attn_drop_rate=0.0, drop_path_rate=0.0, enable_checkpoint=False):
+        super().__init__()
+        if isinstance(drop_path_rate, list):
+            drop_path_rates = drop_path_rate
+            assert len(drop_path_rates) == depth
+        elif isinstance(drop_path_rate, float):
+            drop_path_rates = [deepcopy(drop_path_rate) for _ in range(depth)]
+        else:
+            drop_path_rates = [0.0 for _ in range(depth)]
+        self.neighbours = neighbours
+        self.blocks = nn.ModuleList()
+        for i in range(depth):
+            self.blocks.append(Block(embed_channels=embed_channels, groups=groups, qkv_bias=qkv_bias,
+                                     pe_multiplier=pe_multiplier, pe_bias=pe_bias, attn_drop_rate=attn_drop_rate,
+                                     drop_path_rate=drop_path_rates[i], enable_checkpoint=enable_checkpoint))
+        self.knn_cache = None  # set by PointTransformerV2: {(coord ptr, n, offset ptr, k): idx}
+
+    def forward(self, points):
+        coord, feat, offset = points
+        key = (coord.data_ptr(), coord.shape[0], offset.data_ptr(), self.neighbours)
+        reference_index = None if self.knn_cache is None else self.knn_cache.get(key)
+        if reference_index is None:
+            reference_index, _ = pointops.knn_query(self.neighbours, coord, offset)     # :223
+            if self.knn_cache is not None:
+                self.knn_cache[key] = reference_index
+        for block in self.blocks:
+            points = block(points, reference_index)
+        return points
+
+
+class GridPool(nn.Module):
+    """Partition-based Pooling (Grid Pooling) (…v2m2_base.py:229-269)."""
+
+    def __init__(self, in_channels, out_channels, grid_size, bias=False):
+        super().__init__()
+        self.in_channels = in_channels
+        self.out_channels = out_channels
+        self.grid_size = grid_size
+        self.fc = nn.Linear(in_channels, out_channels, bias=bias)
+        self.norm = PointBatchNorm(out_channels)
+        self.act = nn.ReLU(inplace=True)
+
+    def forward(self, points, start=None):
+        coord, feat, offset = points
+        feat = self.act(self.norm(self.fc(feat)))
+        (coord, feat, offset), cluster, part = pointops.grid_pool(coord, feat.float().contiguous(), offset,
+                                                                  self.grid_size, start, return_partition=True)
+        cluster._aopt_c32 = part.cluster32      # lets UnpoolWithSkip("map") reuse the partition as its CSR
+        return [coord, feat, offset], cluster
+
+
+class UnpoolWithSkip(nn.Module):
+    """Map / interpolation unpooling with skip connection (…v2m2_base.py:272-316)."""
+
+    def __init__(self, in_channels, skip_channels, out_channels, bias=True, skip=True, backend="map"):
+        super().__init__()
+        self.in_channels = in_channels
+        self.skip_channels = skip_channels
+        self.out_channels = out_channels
+        self.skip = skip
+        self.backend = backend
+        assert self.backend in ["map", "interp"]
+        self.proj = nn.Sequential(nn.Linear(in_channels, out_channels, bias=bias), PointBatchNorm(out_channels),
+                                  nn.ReLU(inplace=True))
+        self.proj_skip = nn.Sequential(nn.Linear(skip_channels, out_channels, bias=bias),
+                                       PointBatchNorm(out_channels), nn.ReLU(inplace=True))
+
+    def forward(self, points, skip_points, cluster=None):
+        coord, feat, offset = points
+        skip_coord, skip_feat, skip_offset = skip_points
+        if self.backend == "map" and cluster is not None:
+            feat = pointops.unpool_map(self.proj(feat), cluster)
+        else:
+            feat = pointops.interpolation(coord, skip_coord, self.proj(feat).float().contiguous(), offset, skip_offset)
+        if self.skip:
+            feat = feat + self.proj_skip(skip_feat)
+        return [skip_coord, feat, skip_offset]
+
+
+class Encoder(nn.Module):
+    def __init__(self, depth, in_channels, embed_channels, groups, grid_size=None, neighbours=16, qkv_bias=True,
+                 pe_multiplier=False, pe_bias=True, attn_drop_rate=None, drop_path_rate=None,
+                 enable_checkpoint=False):
+        super().__init__()
+        self.down = GridPool(in_channels=in_channels, out_channels=embed_channels, grid_size=grid_size)
+        self.blocks = BlockSequence(depth=depth, embed_channels=embed_channels, groups=groups, neighbours=neighbours,
+                                    qkv_bias=qkv_bias, pe_multiplier=pe_multiplier, pe_bias=pe_bias,
+                                    attn_drop_rate=attn_drop_rate if attn_drop_rate is not None else 0.0,
+                                    drop_path_rate=drop_path_rate if drop_path_rate is not None else 0.0,
+                                    enable_checkpoint=enable_checkpoint)
+
+    def forward(self, points):
+        points, cluster = self.down(points)
+        return self.blocks(points), cluster
+
+
+class Decoder(nn.Module):
+    def __init__(self, in_channels, skip_channels, embed_channels, groups, depth, neighbours=16, qkv_bias=True,
+                 pe_multiplier=False, pe_bias=True, attn_drop_rate=None, drop_path_rate=None,
+                 enable_checkpoint=False, unpool_backend="map"):
+        super().__init__()
+        self.up = UnpoolWithSkip(in_channels=in_channels, out_channels=embed_channels, skip_channels=skip_channels,
+                                 backend=unpool_backend)
+        self.blocks = BlockSequence(depth=depth, embed_channels=embed_channels, groups=groups, neighbours=neighbours,
+                                    qkv_bias=qkv_bias, pe_multiplier=pe_multiplier, pe_bias=pe_bias,
+                                    attn_drop_rate=attn_drop_rate if attn_drop_rate is not None else 0.0,
+                                    drop_path_rate=drop_path_rate if drop_path_rate is not None else 0.0,
+                                    enable_checkpoint=enable_checkpoint)
+
+    def forward(self, points, skip_points, cluster):
+        points = self.up(points, skip_points, cluster)
+        return self.blocks(points)
+
+
+class GVAPatchEmbed(nn.Module):
+    def __init__(self, depth, in_channels, embed_channels, groups, neighbours=16, qkv_bias=True,
+                 pe_multiplier=False, pe_bias=True, attn_drop_rate=0.0, drop_path_rate=0.0,
+                 enable_checkpoint=False):
+        super().__init__()
+        self.in_channels = in_channels
+        self.embed_channels = embed_channels
+        self.proj = nn.Sequential(nn.Linear(in_channels, embed_channels, bias=False), PointBatchNorm(embed_channels),
+                                  nn.ReLU(inplace=True))
+        self.blocks = BlockSequence(depth=depth, embed_channels=embed_channels, groups=groups, neighbours=neighbours,
+                                    qkv_bias=qkv_bias, pe_multiplier=pe_multiplier, pe_bias=pe_bias,
+                                    attn_drop_rate=attn_drop_rate, drop_path_rate=drop_path_rate,
+                                    enable_checkpoint=enable_checkpoint)
+
+    def forward(self, points):
+        coord, feat, offset = points
+        feat = self.proj(feat)
+        return self.blocks([coord, feat, offset])
+
+
+class PointTransformerV2(nn.Module):
+    """PT-v2m2 (…v2m2_base.py:447-576).  Defaults equal the reference's; S3DIS_CFG below is
+    configs/s3dis/semseg-pt-v2m2-0-base.py:10-36."""
+
+    def __init__(self, in_channels, num_classes, patch_embed_depth=1, patch_embed_channels=48,
+                 patch_embed_groups=6, patch_embed_neighbours=8, enc_depths=(2, 2, 6, 2),
+                 enc_channels=(96, 192, 384, 512), enc_groups=(12, 24, 48, 64), enc_neighbours=(16, 16, 16, 16),
+                 dec_depths=(1, 1, 1, 1), dec_channels=(48, 96, 192, 384), dec_groups=(6, 12, 24, 48),
+                 dec_neighbours=(16, 16, 16, 16), grid_sizes=(0.06, 0.12, 0.24, 0.48), attn_qkv_bias=True,
+                 pe_multiplier=False, pe_bias=True, attn_drop_rate=0.0, drop_path_rate=0, enable_checkpoint=False,
+                 unpool_backend="map"):
+        super().__init__()
+        self.in_channels = in_channels
+        self.num_classes = num_classes
+        self.num_stages = len(enc_depths)
+        for t in (dec_depths, enc_channels, dec_channels, enc_groups, dec_groups, enc_neighbours, dec_neighbours,
+                  grid_sizes):
+            assert self.num_stages == len(t)
+        self.patch_embed = GVAPatchEmbed(in_channels=in_channels, embed_channels=patch_embed_channels,
+                                         groups=patch_embed_groups, depth=patch_embed_depth,
+                                         neighbours=patch_embed_neighbours, qkv_bias=attn_qkv_bias,
+                                         pe_multiplier=pe_multiplier, pe_bias=pe_bias, attn_drop_rate=attn_drop_rate,
+                                         enable_checkpoint=enable_checkpoint)
+        enc_dp_rates = [x.item() for x in torch.linspace(0, drop_path_rate, sum(enc_depths))]
+        dec_dp_rates = [x.item() for x in torch.linspace(0, drop_path_rate, sum(dec_depths))]
+        enc_channels = [patch_embed_channels] + list(enc_channels)
+        dec_channels = list(dec_channels) + [enc_channels[-1]]
+        self.enc_stages = nn.ModuleList()
+        self.dec_stages = nn.ModuleList()
+        for i in range(self.num_stages):
+            self.enc_stages.append(Encoder(
+                depth=enc_depths[i], in_channels=enc_channels[i], embed_channels=enc_channels[i + 1],
+                groups=enc_groups[i], grid_size=grid_sizes[i], neighbours=enc_neighbours[i], qkv_bias=attn_qkv_bias,
+                pe_multiplier=pe_multiplier, pe_bias=pe_bias, attn_drop_rate=attn_drop_rate,
+                drop_path_rate=enc_dp_rates[sum(enc_depths[:i]): sum(enc_depths[: i + 1])],
+                enable_checkpoint=enable_checkpoint))
+            self.dec_stages.append(Decoder(
+                depth=dec_depths[i], in_channels=dec_channels[i + 1], skip_channels=enc_channels[i],
+                embed_channels=dec_channels[i], groups=dec_groups[i], neighbours=dec_neighbours[i],
+                qkv_bias=attn_qkv_bias, pe_multiplier=pe_multiplier, pe_bias=pe_bias, attn_drop_rate=attn_drop_rate,
+                drop_path_rate=dec_dp_rates[sum(dec_depths[:i]): sum(dec_depths[: i + 1])],
+                enable_checkpoint=enable_checkpoint, unpool_backend=unpool_backend))
+        self.seg_head = (nn.Sequential(nn.Linear(dec_channels[0], dec_channels[0]), PointBatchNorm(dec_channels[0]),
+                                       nn.ReLU(inplace=True), nn.Linear(dec_channels[0], num_classes))
+                         if num_classes > 0 else nn.Identity())
+        # neighbour lists are shared between every BlockSequence that sees the same (coords, k)
+        self._knn_cache = {}
+        for m in self.modules():
+            if isinstance(m, BlockSequence):
+                m.knn_cache = self._knn_cache
+
+    def forward(self, data_dict):
+        coord = data_dict["coord"]
+        feat = data_dict["feat"]
+        offset = data_dict["offset"].int()
+        self._knn_cache.clear()
+        try:
+            points = [coord, feat, offset]
+            points = self.patch_embed(points)
+            skips = [[points]]
+            for i in range(self.num_stages):
+                points, cluster = self.enc_stages[i](points)
+                skips[-1].append(cluster)
+                skips.append([points])
+            points = skips.pop(-1)[0]
+            for i in reversed(range(self.num_stages)):
+                skip_points, cluster = skips.pop(-1)
+                points = self.dec_stages[i](points, skip_points, cluster)
+            coord, feat, offset = points
+            return self.seg_head(feat)
+        finally:
+            self._knn_cache.clear()   # the idx tensors stay alive through autograd; do not pin them here
+
+
+S3DIS_CFG = dict(  # configs/s3dis/semseg-pt-v2m2-0-base.py:10-36
+    in_channels=6, num_classes=13, patch_embed_depth=2, patch_embed_channels=48, patch_embed_groups=6,
+    patch_embed_neighbours=16, enc_depths=(2, 6, 2), enc_channels=(96, 192, 384), enc_groups=(12, 24, 48),
+    enc_neighbours=(16, 16, 16), dec_depths=(1, 1, 1), dec_channels=(48, 96, 192), dec_groups=(6, 12, 24),
+    dec_neighbours=(16, 16, 16), grid_sizes=(0.1, 0.2, 0.4), attn_qkv_bias=True, pe_multiplier=False,
+    pe_bias=True, attn_drop_rate=0.0, drop_path_rate=0.3, enable_checkpoint=False, unpool_backend="interp")
+
+SCANNET_CFG = dict(  # configs/scannet/semseg-pt-v2m2-0-base.py
+    in_channels=9, num_classes=20, patch_embed_depth=1, patch_embed_channels=48, patch_embed_groups=6,
+    patch_embed_neighbours=8, enc_depths=(2, 2, 6, 2), enc_channels=(96, 192, 384, 512),
+    enc_groups=(12, 24, 48, 64), enc_neighbours=(16, 16, 16, 16), dec_depths=(1, 1, 1, 1),
+    dec_channels=(48, 96, 192, 384), dec_groups=(6, 12, 24, 48), dec_neighbours=(16, 16, 16, 16),
+    grid_sizes=(0.06, 0.15, 0.375, 0.9375), attn_qkv_bias=True, pe_multiplier=False, pe_bias=True,
+    attn_drop_rate=0.0, drop_path_rate=0.3, enable_checkpoint=False, unpool_backend="map")

@@ -1,0 +1,257 @@
+"""The point-operator schedule of one PTv2m2 forward+backward — the benchmark
+workload ("PTv2 pointops fwd+bwd").
+
+For a batch in the offset layout it issues exactly the point-operator calls the backbone makes
+(…/point_transformer_v2m2_base.py:556-576), in order, with the shapes of the configured model, and
+then their backward passes:
+
+    level 0:   kNN(k)            patch_embed_depth blocks
+    stage i:   GridPool L_i→L_{i+1} (feature width C_{i+1}), kNN, enc_depths[i] blocks
+    decoder i: interpolation L_{i+1}→L_i (kNN k=3, width C_i), dec_depths[i] blocks
+               (neighbour lists of level i are the encoder's — same coordinates, same k)
+    block:     group_xyz, gva_relation (key[idx]-q), gva_aggregate;   backward: CSR build (once per
+               neighbour list), segmented scatter for key/value, per-query sums, softmax backward
+
+The dense per-point MLPs between the point operators are NOT part of this schedule (they are
+cuBLAS GEMMs / BatchNorm in ao_b200.ptv2); their outputs are stood in for by resident synthetic
+tensors of the right shape (q/k/v (N,C), peb (N,k,C), logits (N,k,G), upstream gradients).
+Everything data-dependent — neighbour search, voxel partition, CSR — is recomputed every step.
+"""
+from __future__ import annotations
+
+import contextlib
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional
+
+import torch
+
+from . import pointops
+
+
+@dataclass
+class ScheduleConfig:
+    k: int = 16
+    patch_depth: int = 2
+    channels: tuple = (48, 96, 192, 384)       # level widths (patch embed, enc stages)
+    groups: tuple = (6, 12, 24, 48)
+    enc_depths: tuple = (2, 6, 2)
+    dec_depths: tuple = (1, 1, 1)
+    grid_sizes: tuple = (0.1, 0.2, 0.4)
+    unpool: str = "interp"
+    interp_k: int = 3
+
+    @staticmethod
+    def s3dis():
+        """configs/s3dis/semseg-pt-v2m2-0-base.py:10-36"""
+        return ScheduleConfig()
+
+
+class Profiler:
+    """CUDA-event timing per kernel family on the launching stream (bench.py roofline)."""
+
+    def __init__(self):
+        self.records: Dict[str, list] = {}
+        self.enabled = False
+
+    @contextlib.contextmanager
+    def span(self, name: str, nbytes: float):
+        if not self.enabled:
+            yield
+            return
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        yield
+        e.record()
+        self.records.setdefault(name, []).append((s, e, nbytes))
+
+    def summary(self):
+        out = {}
+        for name, recs in self.records.items():
+            ms = sum(s.elapsed_time(e) for s, e, _ in recs)
+            nbytes = sum(b for _, _, b in recs)
+            out[name] = dict(ms=ms, calls=len(recs), bytes=nbytes, gbs=(nbytes / (ms * 1e-3) / 1e9) if ms > 0 else 0.0)
+        return out
+
+
+@dataclass
+class Level:
+    n: int = 0
+    c: int = 0
+    g: int = 0
+    coord: Optional[torch.Tensor] = None
+    offset: Optional[torch.Tensor] = None
+    tensors: dict = field(default_factory=dict)
+
+
+class PointOpsSchedule:
+    """Holds the resident synthetic activations; `step(coord, feat, offset)` runs one fwd+bwd."""
+
+    def __init__(self, cfg: ScheduleConfig, device="cuda", seed: int = 0):
+        self.cfg = cfg
+        self.device = torch.device(device)
+        self.gen = torch.Generator(device=self.device)
+        self.gen.manual_seed(seed)
+        self.levels: List[Level] = []
+        self.prof = Profiler()
+        self.last_sizes = None
+
+    # ---- synthetic stand-ins for the dense layers' outputs (allocated once per level size) -------------
+    def _rand(self, *shape, grad=False):
+        t = torch.randn(*shape, device=self.device, generator=self.gen, dtype=torch.float32)
+        return t.requires_grad_(grad)
+
+    def _level_tensors(self, li: int, n: int):
+        cfg = self.cfg
+        while len(self.levels) <= li:
+            self.levels.append(Level())
+        lv = self.levels[li]
+        if lv.n == n and lv.tensors:
+            return lv
+        c, g, k = cfg.channels[li], cfg.groups[li], cfg.k
+        lv.n, lv.c, lv.g = n, c, g
+        t = dict(
+            key=self._rand(n, c, grad=True), query=self._rand(n, c, grad=True), value=self._rand(n, c, grad=True),
+            peb=self._rand(n, k, c, grad=True), logits=self._rand(n, k, g, grad=True),
+            g_out=self._rand(n, c), g_rel=self._rand(n, k, c),
+        )
+        if li + 1 < len(cfg.channels):
+            t["pool_in"] = torch.relu(self._rand(n, cfg.channels[li + 1])).requires_grad_(True)   # post-ReLU (…:247)
+            t["g_interp"] = self._rand(n, c)                                                       # grad of interp output
+        lv.tensors = t
+        return lv
+
+    def _coarse_tensors(self, li: int, n: int):
+        """Tensors living on level li that feed level li-1: grad of the pooled feature, interp input."""
+        lv = self.levels[li]
+        t = lv.tensors
+        c_here, c_fine = self.cfg.channels[li], self.cfg.channels[li - 1]
+        if t.get("_coarse_n") != n:
+            t["g_pool"] = self._rand(n, c_here)
+            t["interp_in"] = self._rand(n, c_fine, grad=True)
+            t["_coarse_n"] = n
+        return t
+
+    # ---- algorithmic bytes (SURVEY.md §8d formulas) ----------------------------------------------------
+    @staticmethod
+    def bytes_relation_fwd(n, k, c): return 4.0 * n * k + 8.0 * n * c + 4.0 * n * k * c
+    @staticmethod
+    def bytes_aggregate_fwd(n, k, c, g): return 4.0 * n * c + 4.0 * n * k * c + 8.0 * n * k * g + 4.0 * n * k + 4.0 * n * c
+    @staticmethod
+    def bytes_group_xyz(n, k): return 12.0 * n + 12.0 * n + 4.0 * n * k + 12.0 * n * k
+
+    # ---- one block ---------------------------------------------------------------------------------------
+    def _block_forward(self, lv: Level, idx):
+        t, k = lv.tensors, self.cfg.k
+        with self.prof.span("group_xyz", self.bytes_group_xyz(lv.n, k)):
+            pos = pointops.group_xyz(idx, lv.coord)
+        with self.prof.span("gva_relation_fwd", self.bytes_relation_fwd(lv.n, k, lv.c)):
+            rel = pointops.gva_relation(t["key"], t["query"], idx)
+        with self.prof.span("gva_aggregate_fwd", self.bytes_aggregate_fwd(lv.n, k, lv.c, lv.g)):
+            out = pointops.gva_aggregate(t["value"], t["peb"], t["logits"], idx, lv.g)
+        return pos, rel, out
+
+    def _block_backward(self, lv: Level, rel, out):
+        t, k, n, c, g = lv.tensors, self.cfg.k, lv.n, lv.c, lv.g
+        # relation backward: grad_key through the CSR (reads (N,k,C) once, writes (N,C)) + grad_query
+        nbytes = 2 * (4.0 * n * k * c) + 4.0 * n * k + 4.0 * (n + 1) + 8.0 * n * c
+        with self.prof.span("gva_relation_bwd", nbytes):
+            gk, gq = torch.autograd.grad(rel, [t["key"], t["query"]], t["g_rel"])
+        nbytes = (8.0 * n * c + 4.0 * n * k * c + 4.0 * n * k * g + 8.0 * n * k + 4.0 * (n + 1)) + \
+                 (4.0 * n * k * c + 4.0 * n * k * g + 4.0 * n * c)
+        with self.prof.span("gva_aggregate_bwd", nbytes):
+            gv, gp, gl = torch.autograd.grad(out, [t["value"], t["peb"], t["logits"]], t["g_out"])
+        return gk, gq, gv, gp, gl
+
+    # ---- one training-step worth of point operators -------------------------------------------------
+    def step(self, coord: torch.Tensor, offset: torch.Tensor):
+        cfg = self.cfg
+        k = cfg.k
+        n_stage = len(cfg.grid_sizes)
+        lv0 = self._level_tensors(0, coord.shape[0])
+        lv0.coord, lv0.offset = coord, offset
+        fwd = []      # (level, rel, out) per block in forward order
+        idxs = []
+        parts = []
+        pooled = []
+        # ---------------- forward ----------------
+        with self.prof.span("knn", 0.0):
+            idx0, _ = pointops.knn_query(k, coord, offset)
+        idxs.append(idx0)
+        for _ in range(cfg.patch_depth):
+            fwd.append((lv0,) + self._block_forward(lv0, idx0)[1:])
+        for i in range(n_stage):
+            fine = self.levels[i]
+            c_next = cfg.channels[i + 1]
+            nb = 4.0 * fine.n * c_next + 16.0 * fine.n
+            with self.prof.span("grid_pool_fwd", nb):
+                (nc, nf, noff), cluster, part = pointops.grid_pool(fine.coord, fine.tensors["pool_in"], fine.offset,
+                                                                   cfg.grid_sizes[i], return_partition=True)
+            lv = self._level_tensors(i + 1, nc.shape[0])
+            lv.coord, lv.offset = nc, noff.int()
+            self._coarse_tensors(i + 1, nc.shape[0])
+            parts.append(part)
+            pooled.append(nf)
+            with self.prof.span("knn", 0.0):
+                idx, _ = pointops.knn_query(k, lv.coord, lv.offset)
+            idxs.append(idx)
+            for _ in range(cfg.enc_depths[i]):
+                fwd.append((lv,) + self._block_forward(lv, idx)[1:])
+        ups = []
+        for i in reversed(range(n_stage)):
+            coarse, fine = self.levels[i + 1], self.levels[i]
+            src = coarse.tensors["interp_in"]
+            nb = 24.0 * fine.n + 4.0 * coarse.n * fine.c + 4.0 * fine.n * fine.c
+            with self.prof.span("unpool_fwd", nb):
+                if cfg.unpool == "interp":
+                    up = pointops.interpolation(coarse.coord, fine.coord, src, coarse.offset, fine.offset, k=cfg.interp_k)
+                else:
+                    up = pointops.unpool_map(src, parts[i])
+            ups.append((i, up))
+            for _ in range(cfg.dec_depths[i]):
+                fwd.append((fine,) + self._block_forward(fine, idxs[i])[1:])   # encoder's neighbour list reused
+        # ---------------- backward (reverse order) ----------------
+        acc = None
+        n_dec_blocks = sum(cfg.dec_depths)
+        pos = len(fwd)
+        for (i, up) in ups[::-1][::-1]:
+            pass
+        # decoder blocks + unpool, from the last decoder stage back
+        dec_iter = list(ups)[::-1]          # finest level first
+        for (i, up) in dec_iter:
+            fine, coarse = self.levels[i], self.levels[i + 1]
+            for _ in range(cfg.dec_depths[i]):
+                pos -= 1
+                lv, rel, out = fwd[pos]
+                g = self._block_backward(lv, rel, out)
+                acc = g[2]
+            nb = 4.0 * fine.n * fine.c + 36.0 * fine.n + 4.0 * (coarse.n + 1) + 4.0 * coarse.n * fine.c
+            with self.prof.span("unpool_bwd", nb):
+                (gsrc,) = torch.autograd.grad(up, [coarse.tensors["interp_in"]], fine.tensors["g_interp"])
+            acc = gsrc
+        for i in reversed(range(n_stage)):
+            lv, fine = self.levels[i + 1], self.levels[i]
+            for _ in range(cfg.enc_depths[i]):
+                pos -= 1
+                l2, rel, out = fwd[pos]
+                g = self._block_backward(l2, rel, out)
+            c_next = cfg.channels[i + 1]
+            nb = 8.0 * lv.n * c_next + 4.0 * fine.n * c_next + 4.0 * fine.n
+            with self.prof.span("grid_pool_bwd", nb):
+                (gin,) = torch.autograd.grad(pooled[i], [fine.tensors["pool_in"]], lv.tensors["g_pool"])
+            acc = gin
+        for _ in range(cfg.patch_depth):
+            pos -= 1
+            lv, rel, out = fwd[pos]
+            g = self._block_backward(lv, rel, out)
+            acc = g[0]
+        assert pos == 0
+        self.last_sizes = [l.n for l in self.levels[: n_stage + 1]]
+        return acc
+
+    # ---- totals for reporting -------------------------------------------------------------------------
+    def blocks_per_level(self):
+        cfg = self.cfg
+        per = [cfg.patch_depth] + list(cfg.enc_depths)
+        for i, d in enumerate(cfg.dec_depths):
+            per[i] += d
+        return per

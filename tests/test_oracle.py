@@ -1,0 +1,163 @@
+"""CPU tests: the oracle (oracle/) against the golden vectors produced by the reference's own Python
+(tests/golden/make_golden.py) and against itself (C vs numpy restatement, heap vs lex rule)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import ROOT
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def gold(name):
+    return {k: v for k, v in np.load(os.path.join(GOLD, name + ".npz")).items()}
+
+
+def T(a):
+    return torch.from_numpy(np.ascontiguousarray(a))
+
+
+# ------------------------------------------------------------------ kNN oracle self-consistency
+@pytest.mark.parametrize("k", [1, 3, 8, 16, 32, 100])
+def test_knn_c_oracle_matches_numpy_restatement(oracle, k):
+    rng = np.random.default_rng(k)
+    sizes = [300, 7, 411, 1]
+    x = rng.standard_normal((sum(sizes), 3)).astype(np.float32)
+    off = np.cumsum(sizes).astype(np.int32)
+    i_c, d_c = oracle.knn_query(k, x, off, rule="lex")
+    i_n, d_n = oracle.knn_query_numpy(k, x, off)
+    assert np.array_equal(i_c, i_n)
+    assert np.array_equal(d_c.view(np.uint32), d_n.view(np.uint32))
+
+
+def test_knn_heap_equals_lex_on_tie_free_rows(oracle):
+    rng = np.random.default_rng(5)
+    sizes = [500, 20, 333]
+    x = rng.standard_normal((sum(sizes), 3)).astype(np.float32)
+    q = rng.standard_normal((400, 3)).astype(np.float32)
+    off = np.cumsum(sizes).astype(np.int32)
+    qoff = np.array([150, 160, 400], np.int32)
+    for k in (1, 3, 16, 24):
+        ih, dh = oracle.knn_query(k, x, off, q, qoff, rule="heap")
+        il, dl = oracle.knn_query(k, x, off, q, qoff, rule="lex")
+        assert np.array_equal(dh.view(np.uint32), dl.view(np.uint32))
+        assert np.array_equal(ih, il)
+    # scene 1 has 20 candidates: with k=24 the last 4 slots are padding
+    assert (il[150:160, 20:] == -1).all() and (dl[150:160, 20:] == np.float32(1e10)).all()
+
+
+def test_knn_tie_behaviour_documented_in_survey(oracle):
+    """d2=[1,1,1,1,0.5], k=3 → reference heap returns [4,1,2]; lex contract [4,0,1]."""
+    xs = np.zeros((5, 3), np.float32)
+    xs[:, 0] = np.sqrt(np.array([1, 1, 1, 1, 0.5], np.float32))
+    q = np.zeros((1, 3), np.float32)
+    off, qoff = np.array([5], np.int32), np.array([1], np.int32)
+    ih, dh = oracle.knn_query(3, xs, off, q, qoff, rule="heap")
+    il, dl = oracle.knn_query(3, xs, off, q, qoff, rule="lex")
+    assert ih.tolist() == [[4, 1, 2]] and il.tolist() == [[4, 0, 1]]
+    assert np.array_equal(dh, dl)
+    xs = np.zeros((6, 3), np.float32)
+    xs[:, 0] = np.sqrt(np.array([2, 1, 1, 1, 0.5, 1], np.float32))
+    ih, _ = oracle.knn_query(4, xs, np.array([6], np.int32), q, qoff, rule="heap")
+    il, _ = oracle.knn_query(4, xs, np.array([6], np.int32), q, qoff, rule="lex")
+    assert ih.tolist() == [[4, 2, 3, 1]] and il.tolist() == [[4, 1, 2, 3]]
+
+
+def test_knn_distance_formula_is_the_compiled_reference_order(oracle):
+    """d2 = fma(dz,dz,fma(dx,dx,dy*dy)) (SASS of the reference build); differs from the source-order
+    fma(dz,dz,fma(dy,dy,dx*dx)) in the last bit for some inputs — make sure we pin the former."""
+    rng = np.random.default_rng(9)
+    x = rng.standard_normal((2000, 3)).astype(np.float32)
+    q = np.zeros((1, 3), np.float32)
+    _, d2 = oracle.knn_query(128, x, np.array([2000], np.int32), q, np.array([1], np.int32))
+    idx, _ = oracle.knn_query(128, x, np.array([2000], np.int32), q, np.array([1], np.int32))
+    p = x[idx[0]].astype(np.float64)
+    dx, dy, dz = (0 - p[:, 0]), (0 - p[:, 1]), (0 - p[:, 2])
+    t = np.float32(dy * dy)
+    t = np.float32(dx * dx + np.float64(t))
+    expect = np.float32(dz * dz + np.float64(t))
+    assert np.array_equal(d2[0].view(np.uint32), expect.view(np.uint32))
+
+
+# ------------------------------------------------------------------ torch restatements vs reference python
+def test_offsets_against_reference(oracle):
+    g = gold("offsets")
+    off = T(g["offset"])
+    assert torch.equal(oracle.offset2batch(off), T(g["batch"]))
+    assert torch.equal(oracle.batch2offset(T(g["batch"])), T(g["back"]))
+
+
+def test_grouping_against_reference(oracle):
+    g = gold("grouping")
+    feat = T(g["feat"]).requires_grad_(True)
+    out = oracle.grouping(T(g["idx"]), feat, T(g["xyz"]), T(g["new_xyz"]), with_xyz=True)
+    assert torch.equal(out, T(g["out_xyz"]))          # includes the -0.0 / +0.0 pattern under ==
+    (gf,) = torch.autograd.grad(out, feat, T(g["grad_out"]))
+    assert torch.allclose(gf, T(g["grad_feat"]), rtol=0, atol=1e-6)
+    assert torch.equal(oracle.grouping(T(g["idx"]), feat, T(g["xyz"]), T(g["new_xyz"])), T(g["out_plain"]))
+
+
+def test_interpolation_against_reference(oracle):
+    g = gold("interpolation")
+    feat = T(g["feat"]).requires_grad_(True)
+    out = oracle.interpolation(T(g["xyz"]), T(g["new_xyz"]), feat, T(g["offset"]), T(g["new_offset"]))
+    assert torch.allclose(out, T(g["out"]), rtol=1e-6, atol=1e-6)
+    (gf,) = torch.autograd.grad(out, feat, T(g["grad_out"]))
+    assert torch.allclose(gf, T(g["grad_feat"]), rtol=1e-5, atol=1e-6)
+    # scene 1 has 2 coarse points < k=3: the reference wraps idx=-1 to the LAST row of the whole batch
+    assert (g["knn_idx"][70:79, 2] == -1).all()
+
+
+def _bn_train(x, w, b):
+    shp = x.shape
+    y = F.batch_norm(x.reshape(-1, shp[-1]), None, None, w, b, training=True, eps=1e-5)
+    return y.view(shp)
+
+
+def test_gva_tail_against_reference_module(oracle):
+    """oracle.gva_relation / gva_aggregate composed with the module's own Linear/BN parameters must
+    reproduce the reference GroupedVectorAttention forward AND input gradient."""
+    g = gold("gva_module")
+    P = {k[len("param."):]: T(v) for k, v in g.items() if k.startswith("param.")}
+    x = T(g["x"]).requires_grad_(True)
+    coord, idx = T(g["coord"]), T(g["idx"])
+    G = P["weight_encoding.3.weight"].shape[0]
+    q = F.relu(_bn_train(F.linear(x, P["linear_q.0.weight"], P["linear_q.0.bias"]), P["linear_q.1.norm.weight"], P["linear_q.1.norm.bias"]))
+    k = F.relu(_bn_train(F.linear(x, P["linear_k.0.weight"], P["linear_k.0.bias"]), P["linear_k.1.norm.weight"], P["linear_k.1.norm.bias"]))
+    v = F.linear(x, P["linear_v.weight"], P["linear_v.bias"])
+    pos = oracle.grouping(idx, k, coord, with_xyz=True)[:, :, :3]
+    rel = oracle.gva_relation(k, q, idx)
+    h = F.relu(_bn_train(F.linear(pos, P["linear_p_bias.0.weight"], P["linear_p_bias.0.bias"]), P["linear_p_bias.1.norm.weight"], P["linear_p_bias.1.norm.bias"]))
+    peb = F.linear(h, P["linear_p_bias.3.weight"], P["linear_p_bias.3.bias"])
+    rel = rel + peb
+    w = F.relu(_bn_train(F.linear(rel, P["weight_encoding.0.weight"], P["weight_encoding.0.bias"]), P["weight_encoding.1.norm.weight"], P["weight_encoding.1.norm.bias"]))
+    logits = F.linear(w, P["weight_encoding.3.weight"], P["weight_encoding.3.bias"])
+    y = oracle.gva_aggregate(v, peb, logits, idx, G)
+    assert torch.allclose(y, T(g["y"]), rtol=1e-4, atol=1e-5)
+    (gx,) = torch.autograd.grad(y, x, T(g["grad_y"]))
+    assert torch.allclose(gx, T(g["grad_x"]), rtol=1e-3, atol=1e-4)
+
+
+# ------------------------------------------------------------------ third-party restatements (unpinned): internal consistency
+def test_grid_pool_restatement_properties(oracle):
+    rng = np.random.default_rng(3)
+    sizes = [400, 37, 250]
+    coord = T(rng.uniform(0, 2, (sum(sizes), 3)).astype(np.float32))
+    feat = T(rng.standard_normal((sum(sizes), 8)).astype(np.float32))
+    off = T(np.cumsum(sizes).astype(np.int32))
+    nc, nf, noff, cluster, argmax = oracle.grid_pool(coord, feat, off, 0.25)
+    nv = nc.shape[0]
+    assert noff[-1].item() == nv and cluster.max().item() == nv - 1
+    batch = oracle.offset2batch(off)
+    # every voxel holds points of ONE scene and voxel ids ascend with the scene (batch-major keys)
+    vb = torch.zeros(nv, dtype=torch.long).scatter_(0, cluster, batch)
+    assert (vb[cluster] == batch).all() and (vb[1:] >= vb[:-1]).all()
+    # max/mean agree with a direct per-voxel computation
+    for v in rng.integers(0, nv, 20):
+        m = cluster == int(v)
+        assert torch.equal(nf[v], feat[m].max(0).values)
+        assert torch.allclose(nc[v], coord[m].mean(0), atol=1e-6)
+        assert (feat[argmax[v], torch.arange(8)] == nf[v]).all()

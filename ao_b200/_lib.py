@@ -12,7 +12,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_void_p
+from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_ulonglong, c_void_p
 
 import torch
 
@@ -26,6 +26,7 @@ SIGNATURES = {
     "aopt_version": (c_char_p, []),
     "aopt_status_string": (c_char_p, [c_int]),
     "aopt_last_cuda_error": (c_char_p, []),
+    "aopt_kernel_launches": (c_ulonglong, []),
     "aopt_offset2batch": (c_int, [c_int, c_int, P, P, P]),
     "aopt_knn_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "aopt_knn_query": (c_int, [c_int, c_int, c_int, c_int, P, P, P, P, P, P, c_int, P, c_size_t, P]),
@@ -54,9 +55,56 @@ SIGNATURES = {
 KNN_AUTO, KNN_TILE, KNN_GRID = 0, 1, 2
 
 _lib = None
+_trace = None  # list of (entry point, args, start event, end event) while bench.py's profiler is on
+_UNTRACED = {"aopt_version", "aopt_status_string", "aopt_last_cuda_error", "aopt_kernel_launches",
+             "aopt_knn_workspace_bytes", "aopt_csr_workspace_bytes"}
 
 
-def load() -> ctypes.CDLL:
+class _Entry:
+    """One C entry point; when tracing, brackets the call with CUDA events on the launching stream."""
+
+    __slots__ = ("name", "fn", "traced")
+
+    def __init__(self, name, fn):
+        self.name, self.fn, self.traced = name, fn, name not in _UNTRACED
+
+    def __call__(self, *args):
+        if _trace is None or not self.traced:
+            return self.fn(*args)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        status = self.fn(*args)
+        e.record()
+        _trace.append((self.name, args, s, e))
+        return status
+
+
+class _Library:
+    """Attribute access to the declared entry points of libao_pointops.so."""
+
+    def __init__(self, cdll):
+        self._cdll = cdll
+
+
+def trace_start() -> list:
+    """Starts recording every kernel-launching C-ABI call (name, args, CUDA events); returns the list."""
+    global _trace
+    _trace = []
+    return _trace
+
+
+def trace_stop() -> list:
+    global _trace
+    t, _trace = _trace, None
+    return t or []
+
+
+def kernel_launches() -> int:
+    """Kernels enqueued by the library so far in this process."""
+    return int(load().aopt_kernel_launches())
+
+
+def load() -> "_Library":
     """Loads the shared library (once) and declares every signature.  Raises if anything is missing."""
     global _lib
     if _lib is not None:
@@ -66,14 +114,16 @@ def load() -> ctypes.CDLL:
             f"ao_b200: {LIB_PATH} not found. Build it with `make -C ao_b200/csrc` "
             "(or `python -c 'import __graft_entry__ as g; g.build()'`). There is no fallback path."
         )
-    lib = ctypes.CDLL(LIB_PATH)
+    cdll = ctypes.CDLL(LIB_PATH)
+    lib = _Library(cdll)
     for name, (restype, argtypes) in SIGNATURES.items():
         try:
-            fn = getattr(lib, name)
+            fn = getattr(cdll, name)
         except AttributeError as e:  # pragma: no cover - build/ABI mismatch
             raise ImportError(f"ao_b200: {LIB_PATH} does not export {name}") from e
         fn.restype = restype
         fn.argtypes = argtypes
+        setattr(lib, name, _Entry(name, fn))
     _lib = lib
     return lib
 

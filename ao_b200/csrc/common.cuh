@@ -12,8 +12,9 @@ namespace aopt {
 
 constexpr int kNumSM = 148;  // B200: 2 dies x 74 SMs; grids are sized in multiples of this
 
-// Records the launch error for aopt_last_cuda_error() and maps it to a status.
-int check_launch();
+// Records the launch error for aopt_last_cuda_error() and maps it to a status; `kernels` = how many
+// kernels the entry point just enqueued (summed into aopt_kernel_launches()).
+int check_launch(int kernels = 1);
 
 inline cudaStream_t as_stream(aopt_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 

@@ -87,7 +87,7 @@ extern "C" int aopt_csr_build(int n_src, int64_t n_entries, const int *idx, int 
     cudaStream_t st = as_stream(stream);
     if (n_src == 0) {
         cudaMemsetAsync(rowptr, 0, sizeof(int), st);
-        return check_launch();
+        return check_launch(0);
     }
     if (n_entries > 0 && (!idx || !perm)) return AOPT_ERR_INVALID_ARGUMENT;
     if (!workspace || workspace_bytes < aopt_csr_workspace_bytes(n_src, n_entries)) return AOPT_ERR_WORKSPACE;
@@ -107,5 +107,5 @@ extern "C" int aopt_csr_build(int n_src, int64_t n_entries, const int *idx, int 
         csr_fill_kernel<<<stride_grid(n_entries, kBlock, 8), kBlock, 0, st>>>(n_entries, n_src, negative_mode, idx, count, tmp);
         csr_rank_kernel<<<stride_grid(n_entries, kBlock, 8), kBlock, 0, st>>>(n_src, negative_mode, idx, rowptr, tmp, perm);
     }
-    return check_launch();
+    return check_launch(n_entries > 0 ? 6 : 3);  // count, 3 x scan, fill, rank
 }

@@ -366,7 +366,7 @@ int knn_grid_launch(int m, int nsample, int n, int b, const float *xyz, const fl
     else if (nsample <= 8) launch_query<8>(self, m, b, nsample, new_xyz, new_offset, w, idx, dist2, st);
     else if (nsample <= 16) launch_query<16>(self, m, b, nsample, new_xyz, new_offset, w, idx, dist2, st);
     else launch_query<32>(self, m, b, nsample, new_xyz, new_offset, w, idx, dist2, st);
-    return check_launch();
+    return check_launch(8);  // sample, setup, count, 3 x scan, fill, query
 }
 
 }  // namespace aopt

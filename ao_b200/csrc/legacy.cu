@@ -141,7 +141,7 @@ extern "C" int aopt_aggregation_backward(int n, int nsample, int c, int w_c, con
         n, nsample, c, w_c, input, position, idx, grad_output, grad_weight);
     aggregation_grad_input_kernel<<<stride_grid((long long)n * c, kLegacyBlock, 8), kLegacyBlock, 0, st>>>(
         n, nsample, c, w_c, weight, grad_output, rowptr, perm, grad_input);
-    return check_launch();
+    return check_launch(3);
 }
 
 extern "C" int aopt_subtraction_forward(int n, int nsample, int c, const float *input1, const float *input2,

@@ -1,0 +1,466 @@
+#!/usr/bin/env python
+"""bench.py — PTv2 pointops fwd+bwd throughput (Mpoints/s) on B200, the metric of BASELINE.json.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            the sm_100a kernels (this repo)
+  python bench.py --impl reference [--gpus N] [--steps K] ...    the reference's pure-torch CPU path
+  torchrun --nproc-per-node N bench.py --gpus N ...              one rank per GPU (weak scaling)
+
+A "step" is one pass of the PTv2m2 point-operator schedule (ao_b200.schedule: every kNN / gather /
+GVA aggregate / GridPool / interpolation call of one forward of semseg-pt-v2m2-0-base and all their
+backward passes) over one S3DIS-shaped batch of 4 rooms x 80k points per GPU (BASELINE.json
+configs[1]).  `value` = level-0 points of all ranks / device time, inputs resident in HBM;
+`e2e` = the same schedule driven from pinned HOST buffers (H2D of coord/feat/offset and a D2H read of
+the result scalar inside the timed region, wall clock).  Rank 0 prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "ptv2_pointops_fwd_bwd_throughput"
+UNIT = "Mpoints/s"
+ROOMS_PER_GPU = 4
+POINTS_PER_ROOM = 80000
+DDP_GRAD_BYTES = 3908641 * 4   # S3DIS-cfg PTv2m2 parameters, fp32
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------------------
+# clocks sampled DURING the timed region
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.rows, self.proc, self.thread = gpu_index, [], None, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        def pump():
+            for line in self.proc.stdout:
+                self.rows.append(line.strip())
+        self.thread = threading.Thread(target=pump, daemon=True)
+        self.thread.start()
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# algorithmic bytes per C-ABI call (SURVEY.md §8d formulas; DESIGN.md §4 lists them per kernel)
+# ---------------------------------------------------------------------------------------------------
+def call_bytes(name, a, sizes, k):
+    """a = the ctypes argument tuple of the call; sizes = level point counts of this step."""
+    def finer(n_coarse):      # level size one above a coarse size
+        for i in range(1, len(sizes)):
+            if sizes[i] == n_coarse:
+                return sizes[i - 1]
+        return n_coarse
+    if name == "aopt_knn_query":
+        m, ns, n = a[0], a[1], a[2]
+        return 12.0 * n + 12.0 * m + 8.0 * m * ns
+    if name == "aopt_csr_build":
+        n_src, e = a[0], a[1]
+        return 4.0 * e + 4.0 * (n_src + 1) + 4.0 * e
+    if name == "aopt_group_xyz":
+        m, ns = a[0], a[1]
+        return 24.0 * m + 4.0 * m * ns + 12.0 * m * ns
+    if name == "aopt_gather_sub_forward":
+        m, ns, c = a[0], a[1], a[2]
+        return 4.0 * m * ns + 8.0 * m * c + 4.0 * m * ns * c
+    if name == "aopt_grouping_forward":
+        m, ns, c = a[0], a[1], a[2]
+        return 4.0 * m * ns + 4.0 * m * c + 4.0 * m * ns * c
+    if name == "aopt_grouping_backward":          # relation backward: E = n*k entries
+        n, c = a[0], a[1]
+        return 4.0 * n * k * c + 4.0 * n * k + 4.0 * (n + 1) + 4.0 * n * c
+    if name == "aopt_sum_over_k":
+        m, ns, c = a[0], a[1], a[2]
+        return 4.0 * m * ns * c + 4.0 * m * c
+    if name == "aopt_gva_forward":
+        n, ns, c, g = a[0], a[1], a[2], a[3]
+        return 4.0 * n * c + 4.0 * n * ns * c + 8.0 * n * ns * g + 4.0 * n * ns + 4.0 * n * c
+    if name == "aopt_gva_backward_query":
+        n, ns, c, g = a[0], a[1], a[2], a[3]
+        return 8.0 * n * c + 4.0 * n * ns * c + 4.0 * n * ns * g + 4.0 * n * ns + 4.0 * n * ns * c + 4.0 * n * ns * g
+    if name == "aopt_gva_backward_value":
+        n, ns, c, g = a[0], a[1], a[2], a[3]
+        return 4.0 * n * ns * g + 4.0 * n * c + 4.0 * (n + 1) + 4.0 * n * ns + 4.0 * n * c
+    if name == "aopt_pool_forward":
+        nv, c = a[0], a[1]
+        n = finer(nv)
+        return 4.0 * n * c + 12.0 * n + 4.0 * n + 4.0 * (nv + 1) + 8.0 * nv * c + 12.0 * nv
+    if name == "aopt_pool_backward":
+        n, c = a[0], a[1]
+        nv = sizes[sizes.index(n) + 1] if n in sizes and sizes.index(n) + 1 < len(sizes) else n
+        return 8.0 * nv * c + 4.0 * n + 4.0 * n * c
+    if name == "aopt_interp_weights":
+        n, kk = a[0], a[1]
+        return 8.0 * n * kk
+    if name == "aopt_interpolation_forward":
+        n, c, kk, m = a[0], a[1], a[2], a[3]
+        return 8.0 * n * kk + 4.0 * m * c + 4.0 * n * c
+    if name == "aopt_interpolation_backward":
+        m, c, kk = a[0], a[1], a[2]
+        n = finer(m)
+        return 4.0 * n * c + 8.0 * n * kk + 4.0 * (m + 1) + 4.0 * m * c
+    if name in ("aopt_segment_min3", "aopt_voxel_keys"):
+        n = a[0]
+        return 12.0 * n + (8.0 * n if name == "aopt_voxel_keys" else 0.0)
+    return 0.0
+
+
+HBM_KERNELS = {"aopt_group_xyz", "aopt_gather_sub_forward", "aopt_grouping_forward", "aopt_grouping_backward",
+               "aopt_sum_over_k", "aopt_gva_forward", "aopt_gva_backward_query", "aopt_gva_backward_value",
+               "aopt_pool_forward", "aopt_pool_backward", "aopt_interpolation_forward",
+               "aopt_interpolation_backward"}
+
+
+def summarise_trace(trace, sizes, k, step_ms_total, peak):
+    per = {}
+    for name, args, s, e in trace:
+        ms = s.elapsed_time(e)
+        d = per.setdefault(name, dict(ms=0.0, calls=0, bytes=0.0))
+        d["ms"] += ms
+        d["calls"] += 1
+        d["bytes"] += call_bytes(name, args, sizes, k)
+    out = []
+    for name, d in sorted(per.items(), key=lambda kv: -kv[1]["ms"]):
+        gbs = d["bytes"] / (d["ms"] * 1e-3) / 1e9 if d["ms"] > 0 else 0.0
+        out.append(dict(kernel=name, calls=d["calls"], ms=round(d["ms"], 4), share=round(d["ms"] / step_ms_total, 4),
+                        alg_gb=round(d["bytes"] / 1e9, 4), gbs=round(gbs, 1),
+                        frac=round(gbs / peak, 4) if name in HBM_KERNELS else None))
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU reference path (oracle/cpu_path.py) — cpu_baseline leg and the --impl reference arm
+# ---------------------------------------------------------------------------------------------------
+def cpu_reference(steps, warmup, budget_s, room_id=0):
+    import torch
+
+    from ao_b200 import scenes          # numpy scene generator only (no kernels)
+    from oracle import cpu_path
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    coord, _ = scenes.indoor_room(room_id, POINTS_PER_ROOM)
+    room = cpu_path.CpuRoom(coord)
+    per_step = max(1.0, budget_s / max(1, steps + warmup + 1))
+    f = max(0.02, cpu_path.calibrate_fraction(room, per_step, f0=0.02))
+    for _ in range(warmup):
+        room.step(f)
+    tot_s, tot_pts, fam = 0.0, 0.0, {}
+    for _ in range(steps):
+        r = room.step(f)
+        tot_s += r["total"]
+        tot_pts += r["points"]
+        for key in ("knn", "block", "pool", "interp"):
+            fam[key] = fam.get(key, 0.0) + r[key]
+    value = tot_pts / tot_s / 1e6
+    sample = (f"one synthetic S3DIS room (80000 pts, k=16), reference op schedule fwd+bwd on the first "
+              f"{f:.4f} of every level's query rows against the full level ({int(tot_pts / max(steps, 1))} "
+              f"level-0 points per step); cdist+topk kNN, torch gather/index_put scatter")
+    return dict(value=value, ms_per_step=tot_s / max(steps, 1) * 1e3, cores=cores, sample=sample,
+                fraction=f, family_seconds={k2: round(v, 3) for k2, v in fam.items()})
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_reference(args.steps, args.warmup, budget_s=float(os.environ.get("AOPT_BENCH_CPU_BUDGET", "150")))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+                         "sample": r["sample"], "family_seconds": r["family_seconds"]},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n_gpus):
+    return {
+        "workload": "PTv2m2 semseg-pt-v2m2-0-base point-operator schedule fwd+bwd, S3DIS-shaped batch of "
+                    f"{ROOMS_PER_GPU} rooms x {POINTS_PER_ROOM} pts per GPU (BASELINE.json configs[1])",
+        "rooms_per_gpu": ROOMS_PER_GPU, "points_per_room": POINTS_PER_ROOM, "k": 16,
+        "channels": [48, 96, 192, 384], "groups": [6, 12, 24, 48], "blocks_per_level": [3, 3, 7, 2],
+        "parallelism": f"scene-sharded x{n_gpus}" + (", fp32 grad all-reduce 14.9 MB/step (NCCL)" if n_gpus > 1 else ""),
+        "l2": "per-step working set (>20 GB) exceeds the 126 MB L2; no explicit flush",
+    }
+
+
+# ---------------------------------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------------------------------
+def run_b200_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    from ao_b200 import _lib, scenes
+    from ao_b200.schedule import PointOpsSchedule, ScheduleConfig
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback "
+                         "(use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+
+    # ---- synthetic batch: rooms [rank*R, rank*R+R) --------------------------------------------------
+    coord_np, feat_np, off_np = scenes.s3dis_batch(ROOMS_PER_GPU, POINTS_PER_ROOM, first_room=rank * ROOMS_PER_GPU)
+    coord_h = torch.from_numpy(coord_np).pin_memory()
+    feat_h = torch.from_numpy(feat_np).pin_memory()
+    off_h = torch.from_numpy(off_np).pin_memory()
+    coord, feat, offset = coord_h.to(dev), feat_h.to(dev), off_h.to(dev)
+    n0 = coord.shape[0]
+    cfg = ScheduleConfig.s3dis()
+    sched = PointOpsSchedule(cfg, device=dev, seed=rank)
+    grads = torch.zeros(DDP_GRAD_BYTES // 4, device=dev) if world > 1 else None
+
+    def one_step(c, o):
+        acc = sched.step(c, o)
+        if grads is not None:
+            dist.all_reduce(grads)          # the DDP gradient all-reduce: the only collective
+        return acc
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, args.min_warmup)):
+        one_step(coord, offset)
+    barrier()
+
+    # ---- timed region: resident inputs, CUDA events on the launching stream ----------------------------
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.3)
+    barrier()
+    launches0 = _lib.kernel_launches()
+    trace = _lib.trace_start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    wall0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        one_step(coord, offset)
+    e1.record()
+    barrier()
+    wall = time.perf_counter() - wall0
+    _lib.trace_stop()
+    launches = _lib.kernel_launches() - launches0
+    clocks = sampler.stop() if sampler else None
+    ms_total = e0.elapsed_time(e1)
+    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = world * n0 / (ms_step * 1e-3) / 1e6
+    sizes = list(sched.last_sizes)
+
+    # ---- e2e: host buffers → H2D → schedule → D2H of the result scalar, wall clock ---------------------
+    def e2e_step():
+        c = coord_h.to(dev, non_blocking=True)
+        f = feat_h.to(dev, non_blocking=True)
+        o = off_h.to(dev, non_blocking=True)
+        acc = one_step(c, o)
+        del f
+        return float(acc.sum().item())      # D2H read of the step result (the loss stand-in)
+
+    e2e_steps = 0 if args.skip_e2e else args.steps
+    if e2e_steps:
+        e2e_step()
+    barrier()
+    w0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = max(time.perf_counter() - w0, 1e-9)
+    t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    e2e_value = world * n0 * e2e_steps / e2e_s / 1e6
+    h2d = coord_h.numel() * 4 + feat_h.numel() * 4 + off_h.numel() * 4
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant HBM-bound kernel, measured live over the timed region ---------------
+    peak, peak_src = hbm_peak()
+    kernels = summarise_trace(trace, sizes, cfg.k, ms_total, peak)
+    for kr in kernels:
+        kr["ms_per_step"] = round(kr.pop("ms") / args.steps, 4)
+        kr["calls_per_step"] = kr.pop("calls") // args.steps
+        kr["alg_gb_per_step"] = round(kr.pop("alg_gb") / args.steps, 4)
+    hbm_rows = [kr for kr in kernels if kr["kernel"] in HBM_KERNELS]
+    dom = hbm_rows[0] if hbm_rows else None
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if dom and os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get(dom["kernel"])
+        except Exception:
+            traffic = None
+    roofline = None
+    if dom:
+        per_launch_bytes = dom["alg_gb_per_step"] * 1e9 / max(dom["calls_per_step"], 1)
+        roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["gbs"], "peak": peak, "unit": "GB/s",
+                    "frac": dom["frac"], "traffic": traffic, "peak_source": peak_src,
+                    "alg_bytes_per_launch": per_launch_bytes, "launches_per_step": dom["calls_per_step"],
+                    "share_of_step": dom["share"]}
+    hbm_ms = sum(kr["ms_per_step"] for kr in hbm_rows)
+    hbm_gb = sum(kr["alg_gb_per_step"] for kr in hbm_rows)
+    knn_row = next((kr for kr in kernels if kr["kernel"] == "aopt_knn_query"), None)
+    # brute-force-equivalent pair count of the searches (scenes of a level are near-equal in size)
+    pairs = sum(float(a[0]) * float(a[2]) / max(a[3], 1) for nm, a, _, _ in trace if nm == "aopt_knn_query") / args.steps
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, args.min_warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(world),
+        "level_sizes": sizes,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                "timing": "wall clock incl. python launch overhead"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roofline,
+        "hbm_kernels_total": {"ms_per_step": round(hbm_ms, 4), "alg_gb_per_step": round(hbm_gb, 3),
+                              "gbs": round(hbm_gb / (hbm_ms * 1e-3), 1) if hbm_ms > 0 else None,
+                              "frac": round(hbm_gb / (hbm_ms * 1e-3) / peak, 4) if hbm_ms > 0 else None},
+        "knn": None if knn_row is None else {"ms_per_step": knn_row["ms_per_step"], "calls_per_step": knn_row["calls_per_step"],
+                                             "brute_force_pairs_per_step": pairs,
+                                             "equiv_pairs_per_s": pairs / (knn_row["ms_per_step"] * 1e-3)},
+        "kernels": kernels,
+        "host_wall_ms_per_step": wall / args.steps * 1e3,
+    }
+
+    # ---- full PTv2m2 model step (information; the dense MLPs are cuBLAS, not part of the metric) -------
+    if not args.no_model and world == 1:
+        try:
+            line["model_step"] = model_step(dev, coord, feat, offset)
+        except Exception as ex:  # pragma: no cover
+            line["model_step"] = {"error": repr(ex)[:200]}
+    # ---- CPU baseline on the box's host cores (bounded sample) -----------------------------------------
+    if not args.no_cpu_baseline and world == 1:
+        r = cpu_reference(steps=1, warmup=0, budget_s=24.0)
+        line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+                                "sample": r["sample"], "family_seconds": r["family_seconds"]}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def model_step(dev, coord, feat, offset, steps=3):
+    import torch
+
+    from ao_b200 import ptv2
+
+    torch.manual_seed(0)
+    model = ptv2.PointTransformerV2(**ptv2.S3DIS_CFG).to(dev).train()
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-3)
+    target = torch.randint(0, 13, (coord.shape[0],), device=dev)
+    def step():
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            logits = model(dict(coord=coord, feat=feat, offset=offset))
+        loss = torch.nn.functional.cross_entropy(logits.float(), target)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        return loss
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {"what": "full PTv2m2 (S3DIS cfg) training step: bf16 autocast GEMMs (cuBLAS) + these point ops + AdamW",
+            "ms_per_step": ms, "mpoints_per_s": coord.shape[0] / (ms * 1e-3) / 1e6, "loss": float(loss.item()),
+            "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 1e9}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-model", action="store_true")
+    ap.add_argument("--skip-e2e", action="store_true", help="(profiling runs only) skip the host-buffer leg")
+    ap.add_argument("--min-warmup", type=int, default=3, help="(profiling runs only) lower bound on warm-up steps")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_b200_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -58,6 +58,9 @@ const char *aopt_version(void);
 const char *aopt_status_string(int status);
 /* cudaGetErrorString of the last launch error seen by this thread (for AOPT_ERR_LAUNCH). */
 const char *aopt_last_cuda_error(void);
+/* Cumulative number of kernels this library has enqueued in the process (all threads); bench.py
+ * reports the difference over its timed region as "gpu_launches". */
+unsigned long long aopt_kernel_launches(void);
 
 /* ---- offset-encoded batch layout ---------------------------------------------------------- */
 /* batch[i] = scene of point i (int64, like pointcept/models/utils.py:11-24). */

@@ -18,6 +18,18 @@ __version__ = "0.1.0"
 def install_as_pointops():
     """Makes `import pointops` resolve to ao_b200.pointops (drop-in for libs/pointops)."""
     from . import pointops as _p
+    from .pointops import _C
 
     sys.modules["pointops"] = _p
+    sys.modules["pointops._C"] = _C
     return _p
+
+
+def install_native_only():
+    """Registers only the native module `pointops._C`: the reference's own Python package
+    (libs/pointops/functions/*.py, imported as `pointops`) keeps running unmodified and its
+    `from pointops._C import knn_query_cuda, …` lines resolve to the B200 kernels."""
+    from .pointops import _C
+
+    sys.modules["pointops._C"] = _C
+    return _C

@@ -42,6 +42,8 @@ SIGNATURES = {
     "aopt_gva_backward_value": (c_int, [c_int, c_int, c_int, c_int, P, P, P, P, P, P]),
     "aopt_segment_min3": (c_int, [c_int, c_int, P, P, P, P]),
     "aopt_voxel_keys": (c_int, [c_int, c_int, P, P, P, c_float, P, P, P]),
+    "aopt_voxel_partition_workspace_bytes": (c_size_t, [c_int]),
+    "aopt_voxel_partition": (c_int, [c_int, c_int, P, P, P, P, P, P, P, P, P, P, c_size_t, P]),
     "aopt_pool_forward": (c_int, [c_int, c_int, P, P, P, P, P, P, P, P]),
     "aopt_pool_backward": (c_int, [c_int, c_int, P, P, P, P, P]),
     "aopt_interp_weights": (c_int, [c_int, c_int, P, P, P]),
@@ -57,7 +59,7 @@ KNN_AUTO, KNN_TILE, KNN_GRID = 0, 1, 2
 _lib = None
 _trace = None  # list of (entry point, args, start event, end event) while bench.py's profiler is on
 _UNTRACED = {"aopt_version", "aopt_status_string", "aopt_last_cuda_error", "aopt_kernel_launches",
-             "aopt_knn_workspace_bytes", "aopt_csr_workspace_bytes"}
+             "aopt_knn_workspace_bytes", "aopt_csr_workspace_bytes", "aopt_voxel_partition_workspace_bytes"}
 
 
 class _Entry:

@@ -1,0 +1,81 @@
+// bbox.cu — see bbox.cuh.
+#include "bbox.cuh"
+
+namespace aopt {
+
+constexpr int kBboxBlock = 256;
+constexpr int kBboxPerThread = 8;
+constexpr int kBboxChunk = kBboxBlock * kBboxPerThread;
+
+template <bool WITH_MAX>
+__global__ void __launch_bounds__(kBboxBlock)
+scene_bbox_kernel(int n, int b, const float *__restrict__ xyz, const int *__restrict__ offset,
+                  unsigned *__restrict__ lo, unsigned *__restrict__ hi) {
+    __shared__ float red[6][kBboxBlock / 32];
+    const int base = blockIdx.x * kBboxChunk;
+    const int last = min(base + kBboxChunk, n) - 1;
+    const int sc_first = find_segment(base, offset, b), sc_last = find_segment(last, offset, b);
+    if (sc_first == sc_last) {
+        // the whole chunk lies in one scene: block reduction, then six atomics
+        if (sc_first >= b) return;  // past the last offset: belongs to no scene
+        float mn[3] = {3.0e38f, 3.0e38f, 3.0e38f}, mx[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+#pragma unroll
+        for (int u = 0; u < kBboxPerThread; ++u) {
+            const int i = base + u * kBboxBlock + threadIdx.x;
+            if (i <= last) {
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+                    const float v = __ldg(xyz + (size_t)i * 3 + a);
+                    mn[a] = fminf(mn[a], v);
+                    if (WITH_MAX) mx[a] = fmaxf(mx[a], v);
+                }
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) {
+                mn[a] = fminf(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], d));
+                if (WITH_MAX) mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], d));
+            }
+            if ((threadIdx.x & 31) == 0) {
+                red[a][threadIdx.x >> 5] = mn[a];
+                if (WITH_MAX) red[3 + a][threadIdx.x >> 5] = mx[a];
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < (WITH_MAX ? 6 : 3)) {
+            const int a = threadIdx.x;
+            float v = red[a][0];
+            for (int w = 1; w < kBboxBlock / 32; ++w) v = a < 3 ? fminf(v, red[a][w]) : fmaxf(v, red[a][w]);
+            if (a < 3) atomicMin(lo + sc_first * 3 + a, bbox_encode(v));
+            else atomicMax(hi + sc_first * 3 + (a - 3), bbox_encode(v));
+        }
+    } else {
+        // chunk straddles a scene boundary (at most b-1 chunks): per-point atomics
+        for (int u = 0; u < kBboxPerThread; ++u) {
+            const int i = base + u * kBboxBlock + threadIdx.x;
+            if (i > last) continue;
+            const int sc = find_segment(i, offset, b);
+            if (sc >= b) continue;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const unsigned e = bbox_encode(__ldg(xyz + (size_t)i * 3 + a));
+                atomicMin(lo + sc * 3 + a, e);
+                if (WITH_MAX) atomicMax(hi + sc * 3 + a, e);
+            }
+        }
+    }
+}
+
+void launch_scene_bbox(int n, int b, const float *xyz, const int *offset, unsigned *lo, unsigned *hi,
+                       cudaStream_t st) {
+    cudaMemsetAsync(lo, 0xff, sizeof(unsigned) * 3 * (size_t)b, st);
+    if (hi) cudaMemsetAsync(hi, 0x00, sizeof(unsigned) * 3 * (size_t)b, st);
+    if (n <= 0) return;
+    const int grid = div_up(n, kBboxChunk);
+    if (hi) scene_bbox_kernel<true><<<grid, kBboxBlock, 0, st>>>(n, b, xyz, offset, lo, hi);
+    else scene_bbox_kernel<false><<<grid, kBboxBlock, 0, st>>>(n, b, xyz, offset, lo, hi);
+}
+
+}  // namespace aopt

@@ -14,11 +14,15 @@
 // (the reference's own CUDA `aggregation` kernel uses the PTv1 layout ch % w_c and is kept
 // separately in legacy.cu).
 //
-// Thread mapping: one thread per (point n, group gi); it owns the I = C/G contiguous channels of
-// that group (I = 8 in every PTv2 config → two 128-bit accesses per neighbour row).  Lanes of a warp
-// hold consecutive groups, so for a fixed neighbour slot a warp reads whole contiguous (n,s) rows of
-// peb (32·I·4 bytes).  peb / grad_peb stream with L1::no_allocate; value / grad_out rows are
-// re-used by neighbouring points and go through the read-only path.
+// Thread mapping (128-bit path, I = C/G a multiple of 4): one thread per (point n, 4-channel chunk).
+// Consecutive lanes hold consecutive 16-byte chunks of the same (n, s) row, so every warp-level
+// load/store of peb / grad_peb covers contiguous memory; the I/4 lanes of one group sit next to each
+// other (dot products over a group are finished with 1-2 shuffles).  The neighbour loop is unrolled by
+// four with unconditional loads (masked slots read row 0 and are discarded by a select), which keeps
+// 8+ independent 128-bit requests in flight per thread — these kernels are latency-bound, not
+// issue-bound.  peb / grad_peb stream with L1::no_allocate; value / grad_out rows are re-used by
+// neighbouring points and go through the read-only path.  Other widths take the scalar
+// one-thread-per-(point, group) kernels (GroupVec<0>).
 //
 // Algorithmic bytes: forward 4NC + 4NkC + 4NkG(+4NkG prob) + 4Nk + 4NC;
 // backward reads 8NC + 4NkC + 4NkG + 8Nk + 4(N+1), writes 4NkC + 4NkG + 4NC.
@@ -30,218 +34,327 @@
 namespace aopt {
 
 constexpr int kGvaBlock = 256;
+constexpr int kMaxScalarI = 64;  // scalar fallback: channels of one group held in registers
 
-// Channels of one group held in registers.  I4 > 0: I = 4·I4 channels, 128-bit accesses.
-// I4 == 0: runtime I (<= kMaxScalarI), scalar accesses — fallback for unusual widths/alignment.
-constexpr int kMaxScalarI = 64;
+__device__ __forceinline__ float4 f4_zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ float4 f4_add(const float4 &a, const float4 &b) {
+    return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+}
+__device__ __forceinline__ float dot4(const float4 &a, const float4 &b) {
+    return fmaf(a.w, b.w, fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x)));
+}
+// acc += x * w when keep, else unchanged (select, no branch: masked slots never touch acc)
+__device__ __forceinline__ void fma_keep(float4 &acc, const float4 &x, float w, bool keep) {
+    acc.x = keep ? fmaf(x.x, w, acc.x) : acc.x;
+    acc.y = keep ? fmaf(x.y, w, acc.y) : acc.y;
+    acc.z = keep ? fmaf(x.z, w, acc.z) : acc.z;
+    acc.w = keep ? fmaf(x.w, w, acc.w) : acc.w;
+}
 
-template <int I4>
-struct GroupVec {
-    float4 v[I4];
-    __device__ __forceinline__ void zero(int) {
-#pragma unroll
-        for (int i = 0; i < I4; ++i) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    __device__ __forceinline__ void load_gather(const float *p, int) {
-#pragma unroll
-        for (int i = 0; i < I4; ++i) v[i] = ldg_gather4(p + 4 * i);
-    }
-    __device__ __forceinline__ void load_stream(const float *p, int) {
-#pragma unroll
-        for (int i = 0; i < I4; ++i) v[i] = ldg_stream4(p + 4 * i);
-    }
-    __device__ __forceinline__ void add(const GroupVec &o, int) {
-#pragma unroll
-        for (int i = 0; i < I4; ++i) { v[i].x += o.v[i].x; v[i].y += o.v[i].y; v[i].z += o.v[i].z; v[i].w += o.v[i].w; }
-    }
-    __device__ __forceinline__ void fma(const GroupVec &a, float s, int) {
-#pragma unroll
-        for (int i = 0; i < I4; ++i) {
-            v[i].x = fmaf(a.v[i].x, s, v[i].x); v[i].y = fmaf(a.v[i].y, s, v[i].y);
-            v[i].z = fmaf(a.v[i].z, s, v[i].z); v[i].w = fmaf(a.v[i].w, s, v[i].w);
-        }
-    }
-    __device__ __forceinline__ float dot(const GroupVec &a, int) const {
-        float d = 0.f;
-#pragma unroll
-        for (int i = 0; i < I4; ++i) {
-            d = fmaf(v[i].x, a.v[i].x, d); d = fmaf(v[i].y, a.v[i].y, d);
-            d = fmaf(v[i].z, a.v[i].z, d); d = fmaf(v[i].w, a.v[i].w, d);
-        }
-        return d;
-    }
-    __device__ __forceinline__ void store_scaled_stream(float *p, float s, int) const {
-#pragma unroll
-        for (int i = 0; i < I4; ++i)
-            stg_stream4(p + 4 * i, make_float4(v[i].x * s, v[i].y * s, v[i].z * s, v[i].w * s));
-    }
-    __device__ __forceinline__ void store(float *p, int) const {
-#pragma unroll
-        for (int i = 0; i < I4; ++i) *reinterpret_cast<float4 *>(p + 4 * i) = v[i];
-    }
-};
+// Sum over the GL adjacent lanes that share one group (GL = I/4 in {1,2,4}); all 32 lanes take part.
+template <int GL>
+__device__ __forceinline__ float group_sum(float v) {
+    if (GL >= 2) v += __shfl_xor_sync(0xffffffffu, v, 1);
+    if (GL >= 4) v += __shfl_xor_sync(0xffffffffu, v, 2);
+    return v;
+}
 
-template <>
-struct GroupVec<0> {
-    float v[kMaxScalarI];
-    __device__ __forceinline__ void zero(int I) { for (int i = 0; i < I; ++i) v[i] = 0.f; }
-    __device__ __forceinline__ void load_gather(const float *p, int I) { for (int i = 0; i < I; ++i) v[i] = __ldg(p + i); }
-    __device__ __forceinline__ void load_stream(const float *p, int I) { for (int i = 0; i < I; ++i) v[i] = __ldg(p + i); }
-    __device__ __forceinline__ void add(const GroupVec &o, int I) { for (int i = 0; i < I; ++i) v[i] += o.v[i]; }
-    __device__ __forceinline__ void fma(const GroupVec &a, float s, int I) { for (int i = 0; i < I; ++i) v[i] = fmaf(a.v[i], s, v[i]); }
-    __device__ __forceinline__ float dot(const GroupVec &a, int I) const {
-        float d = 0.f;
-        for (int i = 0; i < I; ++i) d = fmaf(v[i], a.v[i], d);
-        return d;
-    }
-    __device__ __forceinline__ void store_scaled_stream(float *p, float s, int I) const { for (int i = 0; i < I; ++i) p[i] = v[i] * s; }
-    __device__ __forceinline__ void store(float *p, int I) const { for (int i = 0; i < I; ++i) p[i] = v[i]; }
-};
-
-// ---- forward -------------------------------------------------------------------------------------
-template <int I4>
+// ---- forward: one thread per (point, 4-channel chunk) ------------------------------------------------
+template <int GL>
 __global__ void __launch_bounds__(kGvaBlock)
-gva_forward_kernel(long long n, int k, int c, int g, int I, const float *__restrict__ value,
+gva_forward_kernel(long long n, int k, int c, int g, const float *__restrict__ value,
                    const float *__restrict__ peb, const float *__restrict__ logits,
                    const int *__restrict__ idx, float *__restrict__ out, float *__restrict__ prob) {
+    const int chunks = c >> 2;
+    const long long total = n * chunks;
+    const long long step = (long long)gridDim.x * kGvaBlock;
+    for (long long t = (long long)blockIdx.x * kGvaBlock + threadIdx.x; t < total; t += step) {
+        const long long pt = t / chunks;
+        const int ch = (int)(t - pt * chunks);
+        const int gi = ch / GL;
+        const bool writer = (ch % GL) == 0;  // one lane per group stores the probabilities
+        const float *lg = logits + (size_t)pt * k * g + gi;
+        // softmax over the k neighbour slots of (point, group): exp(x - max) / sum, torch.softmax(dim=1)
+        float mx = -INFINITY;
+        for (int s = 0; s < k; ++s) mx = fmaxf(mx, __ldg(lg + (size_t)s * g));
+        float sum = 0.f;
+        for (int s = 0; s < k; ++s) sum += expf(__ldg(lg + (size_t)s * g) - mx);
+        const int *ix = idx + (size_t)pt * k;
+        const float *vbase = value + ch * 4;
+        const float *pe = peb ? peb + (size_t)pt * k * c + ch * 4 : nullptr;
+        float *pr = prob ? prob + (size_t)pt * k * g + gi : nullptr;
+        float4 acc = f4_zero();
+        int s = 0;
+        for (; s + 4 <= k; s += 4) {
+            int j[4];
+            float4 v[4], q[4];
+            float p[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) j[u] = __ldg(ix + s + u);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = ldg_gather4(vbase + (size_t)max(j[u], 0) * c);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) q[u] = pe ? ldg_stream4(pe + (size_t)(s + u) * c) : f4_zero();
+#pragma unroll
+            for (int u = 0; u < 4; ++u) p[u] = expf(__ldg(lg + (size_t)(s + u) * g) - mx) / sum;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (pr && writer) pr[(size_t)(s + u) * g] = p[u];
+                fma_keep(acc, f4_add(v[u], q[u]), p[u], j[u] >= 0);  // sign(idx+1) mask
+            }
+        }
+        for (; s < k; ++s) {
+            const int j = __ldg(ix + s);
+            const float4 v = ldg_gather4(vbase + (size_t)max(j, 0) * c);
+            const float4 q = pe ? ldg_stream4(pe + (size_t)s * c) : f4_zero();
+            const float p = expf(__ldg(lg + (size_t)s * g) - mx) / sum;
+            if (pr && writer) pr[(size_t)s * g] = p;
+            fma_keep(acc, f4_add(v, q), p, j >= 0);
+        }
+        *reinterpret_cast<float4 *>(out + (size_t)pt * c + ch * 4) = acc;
+    }
+}
+
+// ---- backward, per query: grad_peb and grad_logits ---------------------------------------------------
+// grad_logits[n,s,g] = p_s (gw_s - Σ_s' p_s' gw_s'),  gw_s = mask_s <grad_out[n, group g], value[idx]+peb>.
+template <int GL>
+__global__ void __launch_bounds__(kGvaBlock)
+gva_backward_query_kernel(long long n, int k, int c, int g, const float *__restrict__ grad_out,
+                          const float *__restrict__ value, const float *__restrict__ peb,
+                          const float *__restrict__ prob, const int *__restrict__ idx,
+                          float *__restrict__ grad_peb, float *grad_logits) {
+    const int chunks = c >> 2;
+    const long long total = n * chunks;  // a multiple of GL, so the lanes of a group are in or out together
+    const long long step = (long long)gridDim.x * kGvaBlock;
+    // warp-uniform trip count: lanes past the end run on a clamped index and store nothing, so the
+    // group shuffles below always see all 32 lanes
+    for (long long base = (long long)blockIdx.x * kGvaBlock + (threadIdx.x & ~31); base < total; base += step) {
+        const long long t_raw = base + (threadIdx.x & 31);
+        const bool live = t_raw < total;
+        const long long t = live ? t_raw : total - 1;
+        const long long pt = t / chunks;
+        const int ch = (int)(t - pt * chunks);
+        const int gi = ch / GL;
+        const bool writer = live && (ch % GL) == 0;
+        const float4 go = ldg_gather4(grad_out + (size_t)pt * c + ch * 4);
+        const int *ix = idx + (size_t)pt * k;
+        const float *vbase = value + ch * 4;
+        const float *pe = peb ? peb + (size_t)pt * k * c + ch * 4 : nullptr;
+        float *gp = (grad_peb && live) ? grad_peb + (size_t)pt * k * c + ch * 4 : nullptr;
+        const float *pr = prob + (size_t)pt * k * g + gi;
+        float *gl = grad_logits + (size_t)pt * k * g + gi;
+        float dot = 0.f;  // Σ_s p_s · dL/dp_s
+        int s = 0;
+        for (; s + 4 <= k; s += 4) {
+            int j[4];
+            float4 v[4], q[4];
+            float p[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) j[u] = __ldg(ix + s + u);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = ldg_gather4(vbase + (size_t)max(j[u], 0) * c);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) q[u] = pe ? ldg_stream4(pe + (size_t)(s + u) * c) : f4_zero();
+#pragma unroll
+            for (int u = 0; u < 4; ++u) p[u] = __ldg(pr + (size_t)(s + u) * g);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const bool keep = j[u] >= 0;
+                float gw = group_sum<GL>(dot4(go, f4_add(v[u], q[u])));
+                gw = keep ? gw : 0.f;
+                const float w = keep ? p[u] : 0.f;
+                if (gp) stg_stream4(gp + (size_t)(s + u) * c, make_float4(go.x * w, go.y * w, go.z * w, go.w * w));
+                dot = fmaf(p[u], gw, dot);
+                if (writer) gl[(size_t)(s + u) * g] = gw;  // parked; finalised below by the same thread
+            }
+        }
+        for (; s < k; ++s) {
+            const int j = __ldg(ix + s);
+            const bool keep = j >= 0;
+            const float4 v = ldg_gather4(vbase + (size_t)max(j, 0) * c);
+            const float4 q = pe ? ldg_stream4(pe + (size_t)s * c) : f4_zero();
+            const float p = __ldg(pr + (size_t)s * g);
+            float gw = group_sum<GL>(dot4(go, f4_add(v, q)));
+            gw = keep ? gw : 0.f;
+            const float w = keep ? p : 0.f;
+            if (gp) stg_stream4(gp + (size_t)s * c, make_float4(go.x * w, go.y * w, go.z * w, go.w * w));
+            dot = fmaf(p, gw, dot);
+            if (writer) gl[(size_t)s * g] = gw;
+        }
+        if (writer) {
+            for (s = 0; s < k; ++s) {
+                const float p = __ldg(pr + (size_t)s * g);
+                gl[(size_t)s * g] = p * (gl[(size_t)s * g] - dot);  // softmax backward
+            }
+        }
+    }
+}
+
+// ---- backward, per source: grad_value through the CSR ------------------------------------------------
+// kshift >= 0: k is a power of two and q = p >> kshift; otherwise q = p / k.
+template <int GL>
+__global__ void __launch_bounds__(kGvaBlock)
+gva_backward_value_kernel(long long n_src, int k, int kshift, int c, int g, const float *__restrict__ grad_out,
+                          const float *__restrict__ prob, const int *__restrict__ rowptr,
+                          const int *__restrict__ perm, float *__restrict__ grad_value) {
+    const int chunks = c >> 2;
+    const long long total = n_src * chunks;
+    const long long step = (long long)gridDim.x * kGvaBlock;
+    for (long long t = (long long)blockIdx.x * kGvaBlock + threadIdx.x; t < total; t += step) {
+        const long long j = t / chunks;
+        const int ch = (int)(t - j * chunks);
+        const int gi = ch / GL;
+        const float *gbase = grad_out + ch * 4;
+        float4 acc = f4_zero();
+        int e = __ldg(rowptr + j);
+        const int e_end = __ldg(rowptr + j + 1);
+        for (; e + 4 <= e_end; e += 4) {
+            int p[4];
+            float w[4];
+            float4 go[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) p[u] = __ldg(perm + e + u);  // flat (query, slot); idx[p] == j >= 0, mask = 1
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int q = kshift >= 0 ? (p[u] >> kshift) : (p[u] / k);
+                go[u] = ldg_gather4(gbase + (size_t)q * c);
+                w[u] = __ldg(prob + (size_t)p[u] * g + gi);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) fma_keep(acc, go[u], w[u], true);
+        }
+        for (; e < e_end; ++e) {
+            const int p = __ldg(perm + e);
+            const int q = kshift >= 0 ? (p >> kshift) : (p / k);
+            fma_keep(acc, ldg_gather4(gbase + (size_t)q * c), __ldg(prob + (size_t)p * g + gi), true);
+        }
+        *reinterpret_cast<float4 *>(grad_value + (size_t)j * c + ch * 4) = acc;
+    }
+}
+
+// ---- scalar fallback (I not a multiple of 4, I not in {4,8,16}, or unaligned pointers) ----------------
+// One thread per (point, group) holding the I channels of the group in registers.
+__global__ void __launch_bounds__(kGvaBlock)
+gva_forward_scalar_kernel(long long n, int k, int c, int g, int I, const float *__restrict__ value,
+                          const float *__restrict__ peb, const float *__restrict__ logits,
+                          const int *__restrict__ idx, float *__restrict__ out, float *__restrict__ prob) {
     const long long total = n * g;
     const long long step = (long long)gridDim.x * kGvaBlock;
     for (long long t = (long long)blockIdx.x * kGvaBlock + threadIdx.x; t < total; t += step) {
         const long long pt = t / g;
         const int gi = (int)(t - pt * g);
         const float *lg = logits + (size_t)pt * k * g + gi;
-        // softmax over the k neighbour slots of this (point, group): torch.softmax(dim=1) semantics,
-        // exp(x - max) / sum
         float mx = -INFINITY;
         for (int s = 0; s < k; ++s) mx = fmaxf(mx, __ldg(lg + (size_t)s * g));
         float sum = 0.f;
         for (int s = 0; s < k; ++s) sum += expf(__ldg(lg + (size_t)s * g) - mx);
-        GroupVec<I4> acc;
-        acc.zero(I);
-        const int *ix = idx + (size_t)pt * k;
+        float acc[kMaxScalarI];
+        for (int i = 0; i < I; ++i) acc[i] = 0.f;
         const size_t ch0 = (size_t)gi * I;
-#pragma unroll 4
         for (int s = 0; s < k; ++s) {
             const float p = expf(__ldg(lg + (size_t)s * g) - mx) / sum;
             if (prob) prob[((size_t)pt * k + s) * g + gi] = p;
-            const int j = __ldg(ix + s);
-            if (j >= 0) {  // sign(idx+1) mask: padded slots contribute nothing
-                GroupVec<I4> v;
-                v.load_gather(value + (size_t)j * c + ch0, I);
-                if (peb) {
-                    GroupVec<I4> pe;
-                    pe.load_stream(peb + ((size_t)pt * k + s) * c + ch0, I);
-                    v.add(pe, I);
-                }
-                acc.fma(v, p, I);
+            const int j = __ldg(idx + (size_t)pt * k + s);
+            if (j < 0) continue;
+            for (int i = 0; i < I; ++i) {
+                float v = __ldg(value + (size_t)j * c + ch0 + i);
+                if (peb) v += __ldg(peb + ((size_t)pt * k + s) * c + ch0 + i);
+                acc[i] = fmaf(v, p, acc[i]);
             }
         }
-        acc.store(out + (size_t)pt * c + ch0, I);
+        for (int i = 0; i < I; ++i) out[(size_t)pt * c + ch0 + i] = acc[i];
     }
 }
 
-// ---- backward, per query: grad_peb and grad_logits ---------------------------------------------
-template <int I4>
 __global__ void __launch_bounds__(kGvaBlock)
-gva_backward_query_kernel(long long n, int k, int c, int g, int I, const float *__restrict__ grad_out,
-                          const float *__restrict__ value, const float *__restrict__ peb,
-                          const float *__restrict__ prob, const int *__restrict__ idx,
-                          float *__restrict__ grad_peb, float *grad_logits) {
+gva_backward_query_scalar_kernel(long long n, int k, int c, int g, int I, const float *__restrict__ grad_out,
+                                 const float *__restrict__ value, const float *__restrict__ peb,
+                                 const float *__restrict__ prob, const int *__restrict__ idx,
+                                 float *__restrict__ grad_peb, float *grad_logits) {
     const long long total = n * g;
     const long long step = (long long)gridDim.x * kGvaBlock;
     for (long long t = (long long)blockIdx.x * kGvaBlock + threadIdx.x; t < total; t += step) {
         const long long pt = t / g;
         const int gi = (int)(t - pt * g);
         const size_t ch0 = (size_t)gi * I;
-        GroupVec<I4> go;
-        go.load_gather(grad_out + (size_t)pt * c + ch0, I);
-        const int *ix = idx + (size_t)pt * k;
+        const float *go = grad_out + (size_t)pt * c + ch0;
         const float *pr = prob + (size_t)pt * k * g + gi;
         float *gl = grad_logits + (size_t)pt * k * g + gi;
-        float dot = 0.f;  // sum_s p_s * dL/dp_s
-#pragma unroll 4
+        float dot = 0.f;
         for (int s = 0; s < k; ++s) {
             const float p = __ldg(pr + (size_t)s * g);
-            const int j = __ldg(ix + s);
-            float gw = 0.f;  // dL/dp_s = mask_s * <grad_out, value[idx]+peb>
-            if (j >= 0) {
-                GroupVec<I4> v;
-                v.load_gather(value + (size_t)j * c + ch0, I);
-                if (peb) {
-                    GroupVec<I4> pe;
-                    pe.load_stream(peb + ((size_t)pt * k + s) * c + ch0, I);
-                    v.add(pe, I);
+            const int j = __ldg(idx + (size_t)pt * k + s);
+            float gw = 0.f;
+            for (int i = 0; i < I; ++i) {
+                const float gv = __ldg(go + i);
+                if (j >= 0) {
+                    float v = __ldg(value + (size_t)j * c + ch0 + i);
+                    if (peb) v += __ldg(peb + ((size_t)pt * k + s) * c + ch0 + i);
+                    gw = fmaf(gv, v, gw);
                 }
-                gw = go.dot(v, I);
+                if (grad_peb) grad_peb[((size_t)pt * k + s) * c + ch0 + i] = gv * (j >= 0 ? p : 0.f);
             }
-            if (grad_peb) go.store_scaled_stream(grad_peb + ((size_t)pt * k + s) * c + ch0, j >= 0 ? p : 0.f, I);
             dot = fmaf(p, gw, dot);
-            gl[(size_t)s * g] = gw;  // parked; finalised below by the same thread
+            gl[(size_t)s * g] = gw;
         }
         for (int s = 0; s < k; ++s) {
             const float p = __ldg(pr + (size_t)s * g);
-            const float gw = gl[(size_t)s * g];
-            gl[(size_t)s * g] = p * (gw - dot);  // softmax backward
+            gl[(size_t)s * g] = p * (gl[(size_t)s * g] - dot);
         }
     }
 }
 
-// ---- backward, per source: grad_value through the CSR -------------------------------------------
-template <int I4>
 __global__ void __launch_bounds__(kGvaBlock)
-gva_backward_value_kernel(long long n_src, int k, int c, int g, int I, const float *__restrict__ grad_out,
-                          const float *__restrict__ prob, const int *__restrict__ rowptr,
-                          const int *__restrict__ perm, float *__restrict__ grad_value) {
+gva_backward_value_scalar_kernel(long long n_src, int k, int c, int g, int I, const float *__restrict__ grad_out,
+                                 const float *__restrict__ prob, const int *__restrict__ rowptr,
+                                 const int *__restrict__ perm, float *__restrict__ grad_value) {
     const long long total = n_src * g;
     const long long step = (long long)gridDim.x * kGvaBlock;
     for (long long t = (long long)blockIdx.x * kGvaBlock + threadIdx.x; t < total; t += step) {
         const long long j = t / g;
         const int gi = (int)(t - j * g);
         const size_t ch0 = (size_t)gi * I;
-        GroupVec<I4> acc;
-        acc.zero(I);
+        float acc[kMaxScalarI];
+        for (int i = 0; i < I; ++i) acc[i] = 0.f;
         const int e_end = __ldg(rowptr + j + 1);
-#pragma unroll 4
         for (int e = __ldg(rowptr + j); e < e_end; ++e) {
-            const int p = __ldg(perm + e);  // flat (query, slot) position; idx[p] == j >= 0 so mask = 1
+            const int p = __ldg(perm + e);
             const int q = p / k;
             const float w = __ldg(prob + (size_t)p * g + gi);
-            GroupVec<I4> go;
-            go.load_gather(grad_out + (size_t)q * c + ch0, I);
-            acc.fma(go, w, I);
+            for (int i = 0; i < I; ++i) acc[i] = fmaf(__ldg(grad_out + (size_t)q * c + ch0 + i), w, acc[i]);
         }
-        acc.store(grad_value + (size_t)j * c + ch0, I);
+        for (int i = 0; i < I; ++i) grad_value[(size_t)j * c + ch0 + i] = acc[i];
     }
 }
 
-// I4 to use: 128-bit path needs I % 4 == 0, I4 in {1,2,4} and 16-byte aligned pointers.
-static int pick_i4(int I, std::initializer_list<const void *> ptrs) {
-    if (I % 4 != 0) return 0;
-    int i4 = I / 4;
-    if (i4 != 1 && i4 != 2 && i4 != 4) return 0;
+// Lanes per group for the 128-bit path: I in {4,8,16} and 16-byte aligned pointers; 0 = scalar path.
+static int pick_gl(int c, int I, std::initializer_list<const void *> ptrs) {
+    if (I != 4 && I != 8 && I != 16) return 0;
+    if (c % 4 != 0) return 0;
     for (const void *p : ptrs)
         if (p && !aligned16(p)) return 0;
-    return i4;
+    return I / 4;
+}
+
+static int log2_exact(int k) {
+    for (int sft = 0; sft < 31; ++sft)
+        if ((1 << sft) == k) return sft;
+    return -1;
 }
 
 }  // namespace aopt
 
 using namespace aopt;
 
-#define GVA_DISPATCH(I4VAR, KERNEL, GRID, ST, ...)                                     \
-    switch (I4VAR) {                                                                   \
+#define GVA_DISPATCH(GLVAR, KERNEL, GRID, ST, ...)                                     \
+    switch (GLVAR) {                                                                   \
         case 1: KERNEL<1><<<GRID, kGvaBlock, 0, ST>>>(__VA_ARGS__); break;             \
         case 2: KERNEL<2><<<GRID, kGvaBlock, 0, ST>>>(__VA_ARGS__); break;             \
-        case 4: KERNEL<4><<<GRID, kGvaBlock, 0, ST>>>(__VA_ARGS__); break;             \
-        default: KERNEL<0><<<GRID, kGvaBlock, 0, ST>>>(__VA_ARGS__); break;            \
+        default: KERNEL<4><<<GRID, kGvaBlock, 0, ST>>>(__VA_ARGS__); break;            \
     }
 
 static int gva_check(int n, int nsample, int c, int g) {
     if (n < 0 || nsample < 1 || c < 1 || g < 1 || c % g != 0) return AOPT_ERR_INVALID_ARGUMENT;
-    int I = c / g;
-    if (I % 4 != 0 || (I != 4 && I != 8 && I != 16)) {
-        if (I > kMaxScalarI) return AOPT_ERR_UNSUPPORTED;
-    }
     return AOPT_OK;
 }
 
@@ -253,10 +366,16 @@ extern "C" int aopt_gva_forward(int n, int nsample, int c, int g, const float *v
     if (n == 0) return AOPT_OK;
     if (!value || !logits || !idx || !out) return AOPT_ERR_INVALID_ARGUMENT;
     const int I = c / g;
-    const int i4 = pick_i4(I, {value, peb, out});
-    const int grid = stride_grid((long long)n * g, kGvaBlock, 8);
-    GVA_DISPATCH(i4, gva_forward_kernel, grid, as_stream(stream), (long long)n, nsample, c, g, I, value, peb,
-                 logits, idx, out, prob);
+    const int gl = pick_gl(c, I, {value, peb, out});
+    if (gl > 0) {
+        const int grid = stride_grid((long long)n * (c / 4), kGvaBlock, 8);
+        GVA_DISPATCH(gl, gva_forward_kernel, grid, as_stream(stream), (long long)n, nsample, c, g, value, peb, logits,
+                     idx, out, prob);
+    } else {
+        if (I > kMaxScalarI) return AOPT_ERR_UNSUPPORTED;
+        gva_forward_scalar_kernel<<<stride_grid((long long)n * g, kGvaBlock, 8), kGvaBlock, 0, as_stream(stream)>>>(
+            n, nsample, c, g, I, value, peb, logits, idx, out, prob);
+    }
     return check_launch();
 }
 
@@ -269,10 +388,16 @@ extern "C" int aopt_gva_backward_query(int n, int nsample, int c, int g, const f
     if (n == 0) return AOPT_OK;
     if (!grad_out || !value || !prob || !idx || !grad_logits) return AOPT_ERR_INVALID_ARGUMENT;
     const int I = c / g;
-    const int i4 = pick_i4(I, {grad_out, value, peb, grad_peb});
-    const int grid = stride_grid((long long)n * g, kGvaBlock, 8);
-    GVA_DISPATCH(i4, gva_backward_query_kernel, grid, as_stream(stream), (long long)n, nsample, c, g, I,
-                 grad_out, value, peb, prob, idx, grad_peb, grad_logits);
+    const int gl = pick_gl(c, I, {grad_out, value, peb, grad_peb});
+    if (gl > 0) {
+        const int grid = stride_grid((long long)n * (c / 4), kGvaBlock, 8);
+        GVA_DISPATCH(gl, gva_backward_query_kernel, grid, as_stream(stream), (long long)n, nsample, c, g, grad_out,
+                     value, peb, prob, idx, grad_peb, grad_logits);
+    } else {
+        if (I > kMaxScalarI) return AOPT_ERR_UNSUPPORTED;
+        gva_backward_query_scalar_kernel<<<stride_grid((long long)n * g, kGvaBlock, 8), kGvaBlock, 0, as_stream(stream)>>>(
+            n, nsample, c, g, I, grad_out, value, peb, prob, idx, grad_peb, grad_logits);
+    }
     return check_launch();
 }
 
@@ -284,9 +409,15 @@ extern "C" int aopt_gva_backward_value(int n_src, int nsample, int c, int g, con
     if (n_src == 0) return AOPT_OK;
     if (!grad_out || !prob || !rowptr || !perm || !grad_value) return AOPT_ERR_INVALID_ARGUMENT;
     const int I = c / g;
-    const int i4 = pick_i4(I, {grad_out, grad_value});
-    const int grid = stride_grid((long long)n_src * g, kGvaBlock, 8);
-    GVA_DISPATCH(i4, gva_backward_value_kernel, grid, as_stream(stream), (long long)n_src, nsample, c, g, I,
-                 grad_out, prob, rowptr, perm, grad_value);
+    const int gl = pick_gl(c, I, {grad_out, grad_value});
+    if (gl > 0) {
+        const int grid = stride_grid((long long)n_src * (c / 4), kGvaBlock, 8);
+        GVA_DISPATCH(gl, gva_backward_value_kernel, grid, as_stream(stream), (long long)n_src, nsample,
+                     log2_exact(nsample), c, g, grad_out, prob, rowptr, perm, grad_value);
+    } else {
+        if (I > kMaxScalarI) return AOPT_ERR_UNSUPPORTED;
+        gva_backward_value_scalar_kernel<<<stride_grid((long long)n_src * g, kGvaBlock, 8), kGvaBlock, 0, as_stream(stream)>>>(
+            n_src, nsample, c, g, I, grad_out, prob, rowptr, perm, grad_value);
+    }
     return check_launch();
 }

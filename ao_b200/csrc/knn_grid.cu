@@ -10,8 +10,9 @@
 // lexicographically, so the traversal order does not matter.
 //
 // Pipeline (all on the caller's stream, no host synchronisation, no allocation):
-//   1 knn_sample_kernel   r_k^2 of 64 sample points per scene (one warp per sample, register top-k)
-//   2 grid_setup_kernel   per-scene bounding box, cell edge h, grid dims  → GridDesc
+//   1 knn_sample_kernel   r_k^2 estimate at 64 sample points per scene (one CTA per sample, thinned
+//                         candidate set, register top-k + block-wide pops)
+//   2 scene_bbox_kernel + grid_setup_kernel   per-scene bounding box (bbox.cu), cell edge h, dims → GridDesc
 //   3 grid_count_kernel   cell of every candidate + its slot inside the cell (int atomics)
 //   4 exclusive scan      cell counts → cell starts                         (scan.cu)
 //   5 grid_fill_kernel    candidates → cell order as float4 (x, y, z, original index)
@@ -30,6 +31,7 @@
 #include "common.cuh"
 #include "knn_common.cuh"
 #include "scan.cuh"
+#include "bbox.cuh"
 
 namespace aopt {
 
@@ -56,111 +58,124 @@ __device__ __forceinline__ int cell_coord(float p, float o, float inv_h, int dim
 }
 
 // ---- 1. density sample ---------------------------------------------------------------------------
+// One CTA per sample point.  Big scenes are thinned by an index stride (the cell edge only steers
+// speed, never correctness): the (k-1)/stride-th nearest neighbour in the thinned set estimates the
+// k-th nearest in the full set.  Every thread keeps a register top-K of its share of the candidates
+// (loads for four candidates are issued together), then the CTA pops the block-wide minimum kp times.
+constexpr int kSampleBlock = 128;
+constexpr int kSampleTarget = 8192;  // candidates scanned per sample after thinning
+
 template <int K>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(kSampleBlock)
 knn_sample_kernel(int b, int nsample, const float *__restrict__ xyz, const int *__restrict__ offset,
                   float *__restrict__ samples) {
-    const int warp = (blockIdx.x * 128 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (warp >= b * kSamples) return;
-    const int sc = warp / kSamples, s = warp - sc * kSamples;
+    __shared__ float wmin[kSampleBlock / 32];
+    const int sc = blockIdx.x / kSamples, s = blockIdx.x - sc * kSamples;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int start = sc == 0 ? 0 : __ldg(offset + sc - 1), end = __ldg(offset + sc);
     const int ns = end - start;
-    float result = 1e10f;
-    if (ns > 0) {
-        const int qi = start + (int)(((long long)(2 * s + 1) * ns) / (2 * kSamples));
-        const float qx = __ldg(xyz + (size_t)qi * 3), qy = __ldg(xyz + (size_t)qi * 3 + 1),
-                    qz = __ldg(xyz + (size_t)qi * 3 + 2);
-        TopK<K, false> top;
-        top.init();
-        for (int i = start + lane; i < end; i += 32) {
-            const float *p = xyz + (size_t)i * 3;
-            top.offer(dist2_ref(qx, qy, qz, __ldg(p), __ldg(p + 1), __ldg(p + 2)), i);
-        }
-        // merge the 32 sorted lists: pop the warp-wide minimum nsample times
-        for (int r = 0; r < nsample; ++r) {
-            float head = top.d[0];
-            float mn = head;
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, d));
-            unsigned who = __ballot_sync(0xffffffffu, head == mn);
-            if (lane == __ffs(who) - 1) {
-#pragma unroll
-                for (int i = 0; i + 1 < K; ++i) top.d[i] = top.d[i + 1];
-                top.d[K - 1] = 1e10f;
-            }
-            result = mn;
-        }
+    if (ns <= 0) {
+        if (threadIdx.x == 0) samples[blockIdx.x] = 1e10f;
+        return;
     }
-    if (lane == 0) samples[warp] = result;
+    const int stride = max(1, min(ns / kSampleTarget, max(1, (nsample - 1) / 2)));
+    const int kp = max(1, min(K, (max(nsample - 1, 1) + stride - 1) / stride));  // neighbours excluding the sample itself
+    const int qi = start + (int)(((long long)(2 * s + 1) * ns) / (2 * kSamples));
+    const float qx = __ldg(xyz + (size_t)qi * 3), qy = __ldg(xyz + (size_t)qi * 3 + 1),
+                qz = __ldg(xyz + (size_t)qi * 3 + 2);
+    TopK<K, false> top;
+    top.init();
+    const int cnt = (ns + stride - 1) / stride;  // thinned candidates: start + stride * t
+    int t = threadIdx.x;
+    for (; t + 3 * kSampleBlock < cnt; t += 4 * kSampleBlock) {
+        float d[4];
+        int id[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            id[u] = start + (t + u * kSampleBlock) * stride;
+            const float *p = xyz + (size_t)id[u] * 3;
+            d[u] = dist2_ref(qx, qy, qz, __ldg(p), __ldg(p + 1), __ldg(p + 2));
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (id[u] != qi) top.offer(d[u], id[u]);
+    }
+    for (; t < cnt; t += kSampleBlock) {
+        const int id = start + t * stride;
+        const float *p = xyz + (size_t)id * 3;
+        if (id != qi) top.offer(dist2_ref(qx, qy, qz, __ldg(p), __ldg(p + 1), __ldg(p + 2)), id);
+    }
+    float result = 1e10f;
+    for (int r = 0; r < kp; ++r) {
+        const float head = top.d[0];
+        float mn = head;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, d));
+        const unsigned who = __ballot_sync(0xffffffffu, head == mn);
+        if (lane == 0) wmin[warp] = mn;
+        __syncthreads();
+        float bm = wmin[0];
+        int bw = 0;
+#pragma unroll
+        for (int w = 1; w < kSampleBlock / 32; ++w)
+            if (wmin[w] < bm) { bm = wmin[w]; bw = w; }
+        if (warp == bw && lane == __ffs(who) - 1) {
+#pragma unroll
+            for (int i = 0; i + 1 < K; ++i) top.d[i] = top.d[i + 1];
+            top.d[K - 1] = 1e10f;
+        }
+        result = bm;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) samples[blockIdx.x] = result;
 }
 
 // ---- 2. per-scene grid descriptor ------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-grid_setup_kernel(int b, int n, const float *__restrict__ xyz, const int *__restrict__ offset,
-                  const float *__restrict__ samples, float cell_scale, GridDesc *__restrict__ desc) {
-    __shared__ float red[6][8];
-    const int sc = blockIdx.x;
+// One thread per scene: bounding box from the encoded min/max (bbox.cu), cell edge from the samples.
+__global__ void __launch_bounds__(128)
+grid_setup_kernel(int b, int n, const int *__restrict__ offset, const unsigned *__restrict__ bb_lo,
+                  const unsigned *__restrict__ bb_hi, const float *__restrict__ samples, float cell_scale,
+                  GridDesc *__restrict__ desc) {
+    const int sc = blockIdx.x * 128 + threadIdx.x;
+    if (sc >= b) return;
     int start = sc == 0 ? 0 : __ldg(offset + sc - 1), end = __ldg(offset + sc);
     start = max(start, 0);
     end = min(end, n);
-    float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
-    for (int i = start + threadIdx.x; i < end; i += 256) {
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-            float v = __ldg(xyz + (size_t)i * 3 + a);
-            lo[a] = fminf(lo[a], v);
-            hi[a] = fmaxf(hi[a], v);
-        }
-    }
-#pragma unroll
+    const int ns = max(end - start, 0);
+    float lo[3], hi[3];
     for (int a = 0; a < 3; ++a) {
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) {
-            lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], d));
-            hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], d));
-        }
-        if ((threadIdx.x & 31) == 0) {
-            red[a][threadIdx.x >> 5] = lo[a];
-            red[3 + a][threadIdx.x >> 5] = hi[a];
-        }
+        const unsigned el = bb_lo[sc * 3 + a], eh = bb_hi[sc * 3 + a];
+        const bool empty = ns == 0 || el == kBboxEmptyLo;
+        lo[a] = empty ? 0.f : bbox_decode(el);
+        hi[a] = empty ? 0.f : bbox_decode(eh);
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int a = 0; a < 3; ++a)
-            for (int w = 0; w < 8; ++w) {
-                lo[a] = fminf(lo[a], red[a][w]);
-                hi[a] = fmaxf(hi[a], red[3 + a][w]);
-            }
-        GridDesc g;
-        const int ns = max(end - start, 0);
-        if (ns == 0) { lo[0] = lo[1] = lo[2] = 0.f; hi[0] = hi[1] = hi[2] = 0.f; }
-        float ext[3] = {hi[0] - lo[0], hi[1] - lo[1], hi[2] - lo[2]};
-        float max_ext = fmaxf(ext[0], fmaxf(ext[1], ext[2]));
-        float sum = 0.f;
-        int cnt = 0;
-        for (int s = 0; s < kSamples; ++s) {
-            float v = samples[sc * kSamples + s];
-            if (v < 1e9f) { sum += sqrtf(v); ++cnt; }
-        }
-        float h = cnt > 0 ? cell_scale * sum / (float)cnt : 0.f;
-        if (!(h > max_ext * (1.f / 2048.f))) h = max_ext * (1.f / 2048.f);  // also catches NaN / 0
-        if (!(h > 1e-12f)) h = 1.f;                                         // all points coincide
-        const long long cap = (long long)kCellsPerPoint * ns + kCellsPerScene;
-        int nx, ny, nz;
-        for (int it = 0; it < 200; ++it) {
-            nx = (int)(ext[0] / h) + 1; ny = (int)(ext[1] / h) + 1; nz = (int)(ext[2] / h) + 1;
-            if ((long long)nx * ny * nz <= cap) break;
-            h *= 1.25f;
-        }
-        g.ox = lo[0]; g.oy = lo[1]; g.oz = lo[2];
-        g.h = h; g.inv_h = 1.f / h;
-        g.nx = nx; g.ny = ny; g.nz = nz;
-        g.cell_base = kCellsPerPoint * start + kCellsPerScene * sc;
-        g.start = start; g.end = end;
-        g.margin = h * (1e-3f + 1e-6f * (float)max(nx, max(ny, nz)));
-        g.pad[0] = g.pad[1] = g.pad[2] = g.pad[3] = 0;
-        desc[sc] = g;
+    GridDesc g;
+    float ext[3] = {hi[0] - lo[0], hi[1] - lo[1], hi[2] - lo[2]};
+    float max_ext = fmaxf(ext[0], fmaxf(ext[1], ext[2]));
+    float sum = 0.f;
+    int cnt = 0;
+    for (int s = 0; s < kSamples; ++s) {
+        float v = samples[sc * kSamples + s];
+        if (v < 1e9f) { sum += sqrtf(v); ++cnt; }
     }
+    float h = cnt > 0 ? cell_scale * sum / (float)cnt : 0.f;
+    if (!(h > max_ext * (1.f / 2048.f))) h = max_ext * (1.f / 2048.f);  // also catches NaN / 0
+    if (!(h > 1e-12f)) h = 1.f;                                         // all points coincide
+    const long long cap = (long long)kCellsPerPoint * ns + kCellsPerScene;
+    int nx = 1, ny = 1, nz = 1;
+    for (int it = 0; it < 200; ++it) {
+        nx = (int)(ext[0] / h) + 1; ny = (int)(ext[1] / h) + 1; nz = (int)(ext[2] / h) + 1;
+        if ((long long)nx * ny * nz <= cap) break;
+        h *= 1.25f;
+    }
+    g.ox = lo[0]; g.oy = lo[1]; g.oz = lo[2];
+    g.h = h; g.inv_h = 1.f / h;
+    g.nx = nx; g.ny = ny; g.nz = nz;
+    g.cell_base = kCellsPerPoint * start + kCellsPerScene * sc;
+    g.start = start; g.end = end;
+    g.margin = h * (1e-3f + 1e-6f * (float)max(nx, max(ny, nz)));
+    g.pad[0] = g.pad[1] = g.pad[2] = g.pad[3] = 0;
+    desc[sc] = g;
 }
 
 // ---- 3. count ------------------------------------------------------------------------------------
@@ -288,6 +303,7 @@ static size_t a256(size_t x) { return (x + 255) & ~(size_t)255; }
 struct GridWs {
     GridDesc *desc;
     float *samples;
+    unsigned *bbox;  // (b,3) encoded minima then (b,3) encoded maxima
     int *cells;
     int *point_cell, *point_slot;
     float4 *sorted;
@@ -303,6 +319,7 @@ static GridWs carve(void *ws, int n, int b) {
     w.total_cells = (size_t)kCellsPerPoint * n + (size_t)kCellsPerScene * b;
     w.desc = reinterpret_cast<GridDesc *>(p + off); off += a256(sizeof(GridDesc) * (size_t)(b > 0 ? b : 1));
     w.samples = reinterpret_cast<float *>(p + off); off += a256(4 * (size_t)kSamples * (b > 0 ? b : 1));
+    w.bbox = reinterpret_cast<unsigned *>(p + off); off += a256(4 * 6 * (size_t)(b > 0 ? b : 1));
     w.cells = reinterpret_cast<int *>(p + off); off += a256(4 * (w.total_cells + 1));
     w.point_cell = reinterpret_cast<int *>(p + off); off += a256(4 * (size_t)n);
     w.point_slot = reinterpret_cast<int *>(p + off); off += a256(4 * (size_t)n);
@@ -331,7 +348,7 @@ static void launch_query(bool self, int m, int b, int nsample, const float *new_
 
 template <int K>
 static void launch_sample(int b, int nsample, const float *xyz, const int *offset, float *samples, cudaStream_t st) {
-    knn_sample_kernel<K><<<div_up((long long)b * kSamples * 32, 128), 128, 0, st>>>(b, nsample, xyz, offset, samples);
+    knn_sample_kernel<K><<<b * kSamples, kSampleBlock, 0, st>>>(b, nsample, xyz, offset, samples);
 }
 
 int knn_grid_launch(int m, int nsample, int n, int b, const float *xyz, const float *new_xyz,
@@ -356,7 +373,8 @@ int knn_grid_launch(int m, int nsample, int n, int b, const float *xyz, const fl
     else if (nsample <= 8) launch_sample<8>(b, nsample, xyz, offset, w.samples, st);
     else if (nsample <= 16) launch_sample<16>(b, nsample, xyz, offset, w.samples, st);
     else launch_sample<32>(b, nsample, xyz, offset, w.samples, st);
-    grid_setup_kernel<<<b, 256, 0, st>>>(b, n, xyz, offset, w.samples, scale, w.desc);
+    launch_scene_bbox(n, b, xyz, offset, w.bbox, w.bbox + 3 * (size_t)b, st);
+    grid_setup_kernel<<<div_up(b, 128), 128, 0, st>>>(b, n, offset, w.bbox, w.bbox + 3 * (size_t)b, w.samples, scale, w.desc);
     grid_count_kernel<<<div_up(n, 256), 256, 0, st>>>(n, b, xyz, offset, w.desc, w.cells, w.point_cell, w.point_slot);
     launch_exclusive_scan(w.cells, w.cells, (int)w.total_cells, w.partial, st);
     grid_fill_kernel<<<div_up(n, 256), 256, 0, st>>>(n, xyz, w.cells, w.point_cell, w.point_slot, w.sorted);
@@ -366,7 +384,7 @@ int knn_grid_launch(int m, int nsample, int n, int b, const float *xyz, const fl
     else if (nsample <= 8) launch_query<8>(self, m, b, nsample, new_xyz, new_offset, w, idx, dist2, st);
     else if (nsample <= 16) launch_query<16>(self, m, b, nsample, new_xyz, new_offset, w, idx, dist2, st);
     else launch_query<32>(self, m, b, nsample, new_xyz, new_offset, w, idx, dist2, st);
-    return check_launch(8);  // sample, setup, count, 3 x scan, fill, query
+    return check_launch(9);  // sample, bbox, setup, count, 3 x scan, fill, query
 }
 
 }  // namespace aopt

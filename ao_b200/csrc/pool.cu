@@ -15,35 +15,21 @@
 
 #include "common.cuh"
 #include "knn_common.cuh"  // find_segment
+#include "scan.cuh"
+#include "bbox.cuh"
 
 namespace aopt {
 
 constexpr int kPoolBlock = 256;
 
-// One block per scene: component-wise minimum of its coordinates.
-__global__ void __launch_bounds__(256)
-segment_min3_kernel(int n, int b, const float *__restrict__ coord, const int *__restrict__ offset,
-                    float *__restrict__ start_out) {
-    __shared__ float red[3][8];
-    const int sc = blockIdx.x;
-    const int s = max(sc == 0 ? 0 : __ldg(offset + sc - 1), 0), e = min(__ldg(offset + sc), n);
-    float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX};  // torch_scatter "min" starts from the dtype maximum
-    for (int i = s + threadIdx.x; i < e; i += 256) {
-#pragma unroll
-        for (int a = 0; a < 3; ++a) lo[a] = fminf(lo[a], __ldg(coord + (size_t)i * 3 + a));
-    }
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], d));
-        if ((threadIdx.x & 31) == 0) red[a][threadIdx.x >> 5] = lo[a];
-    }
-    __syncthreads();
-    if (threadIdx.x < 3) {
-        float v = red[threadIdx.x][0];
-        for (int w = 1; w < 8; ++w) v = fminf(v, red[threadIdx.x][w]);
-        start_out[sc * 3 + threadIdx.x] = (e > s) ? v : 0.f;  // empty segment → 0 (segment_csr fill)
-    }
+// start[sc, a] = minimum coordinate of scene sc (0 for an empty scene, like segment_csr's fill value):
+// decode of the integer-encoded minima accumulated in place by scene_bbox_kernel (bbox.cu).
+__global__ void __launch_bounds__(128)
+decode_min_kernel(int count, float *__restrict__ start) {
+    const int i = blockIdx.x * 128 + threadIdx.x;
+    if (i >= count) return;
+    const unsigned e = reinterpret_cast<unsigned *>(start)[i];
+    start[i] = e == kBboxEmptyLo ? 0.f : bbox_decode(e);
 }
 
 constexpr int kCellBits = 18, kSceneBits = 10;
@@ -156,6 +142,45 @@ pool_backward_kernel(long long n, int chunks, int c, const float *__restrict__ g
     }
 }
 
+// ---- voxel partition from sorted keys (the tail of …v2m2_base.py:260-268 without torch.unique) -------
+// flag[i] = 1 where a new voxel starts in the sorted key sequence.
+__global__ void __launch_bounds__(kPoolBlock)
+voxel_mark_kernel(int n, const int64_t *__restrict__ sorted_keys, int *__restrict__ flag) {
+    const int i = blockIdx.x * kPoolBlock + threadIdx.x;
+    if (i >= n) return;
+    flag[i] = (i == 0 || __ldg(sorted_keys + i) != __ldg(sorted_keys + i - 1)) ? 1 : 0;
+}
+
+// scan[i] = exclusive prefix sum of flag → voxel id of sorted position i is scan[i] + flag[i] - 1.
+// Writes order32, cluster (both widths), idx_ptr, the per-scene voxel offsets and meta = {n_vox}.
+__global__ void __launch_bounds__(kPoolBlock)
+voxel_finalize_kernel(int n, int b, const int64_t *__restrict__ order64, const int *__restrict__ flag,
+                      const int *__restrict__ scan, const int *__restrict__ offset,
+                      int *__restrict__ order32, int *__restrict__ cluster32, int64_t *__restrict__ cluster64,
+                      int *__restrict__ idx_ptr, int64_t *__restrict__ new_offset, int *__restrict__ meta) {
+    const int i = blockIdx.x * kPoolBlock + threadIdx.x;
+    const int n_vox = __ldg(scan + n);  // total number of flags
+    if (i < n) {
+        const int f = __ldg(flag + i);
+        const int vid = __ldg(scan + i) + f - 1;
+        const int pt = (int)__ldg(order64 + i);
+        order32[i] = pt;
+        cluster32[pt] = vid;
+        cluster64[pt] = vid;
+        if (f) idx_ptr[vid] = i;
+    }
+    if (i == 0) {
+        idx_ptr[n_vox] = n;
+        meta[0] = n_vox;
+    }
+    // scene ranges are identical before and after the sort (the scene id is the most significant key
+    // digit), so the voxels of scenes 0..s are those starting before sorted position offset[s]
+    if (i < b) {
+        int e = min(max(__ldg(offset + i), 0), n);
+        new_offset[i] = e > 0 ? (int64_t)(__ldg(scan + e - 1) + __ldg(flag + e - 1)) : 0;
+    }
+}
+
 __global__ void __launch_bounds__(256)
 offset2batch_kernel(int n, int b, const int *__restrict__ offset, int64_t *__restrict__ batch) {
     const int i = blockIdx.x * 256 + threadIdx.x;
@@ -179,8 +204,9 @@ extern "C" int aopt_segment_min3(int n, int b, const float *coord, const int *of
     if (n < 0 || b < 0) return AOPT_ERR_INVALID_ARGUMENT;
     if (b == 0) return AOPT_OK;
     if (!coord || !offset || !start) return AOPT_ERR_INVALID_ARGUMENT;
-    segment_min3_kernel<<<b, 256, 0, as_stream(stream)>>>(n, b, coord, offset, start);
-    return check_launch();
+    launch_scene_bbox(n, b, coord, offset, reinterpret_cast<unsigned *>(start), nullptr, as_stream(stream));
+    decode_min_kernel<<<div_up(3 * b, 128), 128, 0, as_stream(stream)>>>(3 * b, start);
+    return check_launch(2);
 }
 
 extern "C" int aopt_voxel_keys(int n, int b, const float *coord, const int *offset, const float *start,
@@ -191,6 +217,34 @@ extern "C" int aopt_voxel_keys(int n, int b, const float *coord, const int *offs
     voxel_keys_kernel<<<div_up(n, kPoolBlock), kPoolBlock, 0, as_stream(stream)>>>(n, b, coord, offset, start,
                                                                                grid_size, keys, status_flag);
     return check_launch();
+}
+
+extern "C" size_t aopt_voxel_partition_workspace_bytes(int n) {
+    if (n < 0) return 0;
+    auto a256 = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    return a256(4 * ((size_t)n + 1)) * 2 + a256(4 * scan_partial_ints(n));
+}
+
+extern "C" int aopt_voxel_partition(int n, int b, const int64_t *sorted_keys, const int64_t *order64,
+                                    const int *offset, int *order32, int *cluster32, int64_t *cluster64,
+                                    int *idx_ptr, int64_t *new_offset, int *meta, void *workspace,
+                                    size_t workspace_bytes, aopt_stream_t stream) {
+    if (n < 1 || b < 1) return AOPT_ERR_INVALID_ARGUMENT;
+    if (!sorted_keys || !order64 || !offset || !order32 || !cluster32 || !cluster64 || !idx_ptr || !new_offset || !meta)
+        return AOPT_ERR_INVALID_ARGUMENT;
+    if (!workspace || workspace_bytes < aopt_voxel_partition_workspace_bytes(n)) return AOPT_ERR_WORKSPACE;
+    auto a256 = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    char *ws = static_cast<char *>(workspace);
+    int *flag = reinterpret_cast<int *>(ws); ws += a256(4 * ((size_t)n + 1));
+    int *scan = reinterpret_cast<int *>(ws); ws += a256(4 * ((size_t)n + 1));
+    int *partial = reinterpret_cast<int *>(ws);
+    cudaStream_t st = as_stream(stream);
+    const int grid = div_up(n > b ? n : b, kPoolBlock);
+    voxel_mark_kernel<<<div_up(n, kPoolBlock), kPoolBlock, 0, st>>>(n, sorted_keys, flag);
+    launch_exclusive_scan(flag, scan, n, partial, st);
+    voxel_finalize_kernel<<<grid, kPoolBlock, 0, st>>>(n, b, order64, flag, scan, offset, order32, cluster32, cluster64,
+                                                       idx_ptr, new_offset, meta);
+    return check_launch(5);
 }
 
 extern "C" int aopt_pool_forward(int n_vox, int c, const float *feat, const float *coord, const int *order,

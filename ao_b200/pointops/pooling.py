@@ -4,9 +4,9 @@ unpooling gather.  Successors of the third-party op chain in
 (offset2batch loop + segment_csr(min) + voxel_grid + torch.unique + torch.sort + two permuted
 copies + segment_csr(mean) + segment_csr(max)) and :308-309 (`proj(feat)[cluster]`).
 
-Kernels: aopt_segment_min3, aopt_voxel_keys, aopt_pool_forward/backward, aopt_grouping_forward/
-backward (map unpool).  The key sort itself is torch.sort (library radix sort) in this round; a
-hand-written sort is listed under SURVEY.md §8f-1 "next".
+Kernels: aopt_segment_min3, aopt_voxel_keys, aopt_voxel_partition, aopt_pool_forward/backward,
+aopt_grouping_forward/backward (map unpool).  The 64-bit key sort itself is torch.sort (library radix
+sort); everything after it is two kernels + a scan with ONE host synchronisation (the voxel count).
 """
 from __future__ import annotations
 
@@ -38,8 +38,12 @@ def voxel_partition(coord, offset, grid_size, start=None) -> VoxelPartition:
     assert coord.is_contiguous() and coord.dtype == torch.float32
     n, b = coord.shape[0], offset.numel()
     off32 = offset.int().contiguous()
+    if n == 0:
+        z32 = torch.zeros(0, dtype=torch.int32, device=dev)
+        return VoxelPartition(z32, torch.zeros(1, dtype=torch.int32, device=dev), torch.zeros(0, dtype=torch.int64, device=dev),
+                              z32, torch.zeros(b, dtype=torch.int64, device=dev), 0)
     keys = torch.empty(n, dtype=torch.int64, device=dev)
-    flag = torch.zeros(1, dtype=torch.int32, device=dev)
+    meta = torch.zeros(2, dtype=torch.int32, device=dev)            # [n_vox, key-overflow flag]
     with torch.cuda.device(dev):
         if start is None:
             start = torch.empty((b, 3), dtype=torch.float32, device=dev)
@@ -49,27 +53,28 @@ def voxel_partition(coord, offset, grid_size, start=None) -> VoxelPartition:
             start = start.float().contiguous()
         _lib.check(
             lib.aopt_voxel_keys(n, b, _lib.ptr(coord), _lib.ptr(off32), _lib.ptr(start), float(grid_size),
-                                _lib.ptr(keys), _lib.ptr(flag), _lib.stream()),
+                                _lib.ptr(keys), meta.data_ptr() + 4, _lib.stream()),
             "voxel_keys",
         )
-    sorted_keys, order = torch.sort(keys, stable=True)
-    is_new = torch.ones(n, dtype=torch.bool, device=dev)
-    if n > 1:
-        is_new[1:] = sorted_keys[1:] != sorted_keys[:-1]
-    voxel_of_sorted = torch.cumsum(is_new, 0) - 1                     # int64
-    first = torch.nonzero(is_new).flatten()                           # host sync (like torch.unique)
-    n_vox = first.numel()
-    if int(flag.item()) != 0:
+        # library radix sort of the 64-bit keys (stable → ascending point id inside a voxel); the
+        # partition itself (boundaries, voxel ids, idx_ptr, per-scene offsets) is one scan + two kernels
+        sorted_keys, order = torch.sort(keys, stable=True)
+        order32 = torch.empty(n, dtype=torch.int32, device=dev)
+        cluster32 = torch.empty(n, dtype=torch.int32, device=dev)
+        cluster = torch.empty(n, dtype=torch.int64, device=dev)
+        idx_ptr_full = torch.empty(n + 1, dtype=torch.int32, device=dev)
+        new_offset = torch.empty(b, dtype=torch.int64, device=dev)
+        ws = _lib.workspace(lib.aopt_voxel_partition_workspace_bytes(n), dev)
+        _lib.check(
+            lib.aopt_voxel_partition(n, b, _lib.ptr(sorted_keys), _lib.ptr(order), _lib.ptr(off32), _lib.ptr(order32),
+                                     _lib.ptr(cluster32), _lib.ptr(cluster), _lib.ptr(idx_ptr_full),
+                                     _lib.ptr(new_offset), _lib.ptr(meta), _lib.ptr(ws), ws.numel(), _lib.stream()),
+            "voxel_partition",
+        )
+    n_vox, bad = meta.tolist()                                       # the one host sync (torch.unique has one too)
+    if bad:
         raise ValueError("voxel_partition: a voxel coordinate exceeds 2^18 cells per axis or 1024 scenes")
-    idx_ptr = torch.empty(n_vox + 1, dtype=torch.int32, device=dev)
-    idx_ptr[:n_vox] = first
-    idx_ptr[n_vox] = n
-    cluster = torch.empty(n, dtype=torch.int64, device=dev)
-    cluster[order] = voxel_of_sorted
-    scene = (sorted_keys[first] >> _SCENE_SHIFT)
-    new_offset = torch.cumsum(torch.bincount(scene, minlength=b), 0)   # batch2offset (…v2m2_base.py:268)
-    order32 = order.int()
-    cluster32 = cluster.int()
+    idx_ptr = idx_ptr_full[: n_vox + 1]
     # the partition IS the CSR of `cluster` (rows = voxels, entries ascending) → free backward map
     cluster32._aopt_csr = {(n_vox, 0): NeighbourCSR(idx_ptr, order32, n_vox, 0, cluster32._version)}
     return VoxelPartition(order32, idx_ptr, cluster, cluster32, new_offset, n_vox)

@@ -7,7 +7,8 @@ replayed.  What changes is the op schedule underneath:
 
   reference (per block, :103-129)                         here
   -------------------------------------------------       ---------------------------------------
-  grouping(idx, key, coord, with_xyz=True)  (N,k,3+C)     pointops.group_xyz            (N,k,3)
+  grouping(idx, key, coord, with_xyz=True)  (N,k,3+C)     pointops.group_xyz            (N,k,3), once per
+                                                           neighbour list instead of once per block
   key[...,3:] - query.unsqueeze(1)                        pointops.gva_relation         (N,k,C)
   grouping(idx, value); value + peb; softmax; mask;       pointops.gva_aggregate        (N,C)
   einsum                                                   (value never gathered to (N,k,C))
@@ -89,9 +90,10 @@ class GroupedVectorAttention(nn.Module):
         self.softmax = nn.Softmax(dim=1)
         self.attn_drop = nn.Dropout(attn_drop_rate)
 
-    def forward(self, feat, coord, reference_index):
+    def forward(self, feat, coord, reference_index, pos=None):
         query, key, value = self.linear_q(feat), self.linear_k(feat), self.linear_v(feat)
-        pos = pointops.group_xyz(reference_index, coord)                      # :109,:111
+        if pos is None:                                                       # (N,k,3): depends only on (idx, coord)
+            pos = pointops.group_xyz(reference_index, coord)                  # :109,:111
         relation_qk = pointops.gva_relation(key, query, reference_index)      # :109,:112
         peb = None
         if self.pe_multiplier:
@@ -130,16 +132,16 @@ class Block(nn.Module):
         self.enable_checkpoint = enable_checkpoint
         self.drop_path = DropPath(drop_path_rate) if drop_path_rate > 0.0 else nn.Identity()
 
-    def forward(self, points, reference_index):
+    def forward(self, points, reference_index, pos=None):
         coord, feat, offset = points
         identity = feat
         feat = self.act(self.norm1(self.fc1(feat)))
         if self.enable_checkpoint:
             from torch.utils.checkpoint import checkpoint
 
-            feat = checkpoint(self.attn, feat, coord, reference_index, use_reentrant=False)
+            feat = checkpoint(self.attn, feat, coord, reference_index, pos, use_reentrant=False)
         else:
-            feat = self.attn(feat, coord, reference_index)
+            feat = self.attn(feat, coord, reference_index, pos)
         feat = self.act(self.norm2(feat))
         feat = self.norm3(self.fc3(feat))
         feat = identity + self.drop_path(feat)
@@ -164,18 +166,22 @@ class BlockSequence(nn.Module):
             self.blocks.append(Block(embed_channels=embed_channels, groups=groups, qkv_bias=qkv_bias,
                                      pe_multiplier=pe_multiplier, pe_bias=pe_bias, attn_drop_rate=attn_drop_rate,
                                      drop_path_rate=drop_path_rates[i], enable_checkpoint=enable_checkpoint))
-        self.knn_cache = None  # set by PointTransformerV2: {(coord ptr, n, offset ptr, k): idx}
+        self.knn_cache = None  # set by PointTransformerV2: {(coord ptr, n, offset ptr, k): (idx, pos)}
 
     def forward(self, points):
         coord, feat, offset = points
         key = (coord.data_ptr(), coord.shape[0], offset.data_ptr(), self.neighbours)
-        reference_index = None if self.knn_cache is None else self.knn_cache.get(key)
-        if reference_index is None:
+        hit = None if self.knn_cache is None else self.knn_cache.get(key)
+        if hit is None:
             reference_index, _ = pointops.knn_query(self.neighbours, coord, offset)     # :223
+            # relative coordinates of the neighbours (:109,:111) are the same for every block of the sequence
+            pos = pointops.group_xyz(reference_index, coord)
+            hit = (reference_index, pos)
             if self.knn_cache is not None:
-                self.knn_cache[key] = reference_index
+                self.knn_cache[key] = hit
+        reference_index, pos = hit
         for block in self.blocks:
-            points = block(points, reference_index)
+            points = block(points, reference_index, pos)
         return points
 
 

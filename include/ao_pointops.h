@@ -129,6 +129,16 @@ int aopt_segment_min3(int n, int b, const float *coord, const int *offset, float
  * to 1 if a cell coordinate does not fit the packing (18 bits per axis, 10 bits scene). */
 int aopt_voxel_keys(int n, int b, const float *coord, const int *offset, const float *start,
                     float grid_size, int64_t *keys, int *status_flag, aopt_stream_t stream);
+/* Voxel partition from the keys sorted ascending (sorted_keys, order64 = the stable argsort, both
+ * (n) int64): order32 (n) = point ids by voxel, cluster32/cluster64 (n) = voxel id of every point
+ * (voxels numbered in ascending key order = torch.unique(sorted=True), …v2m2_base.py:260-262),
+ * idx_ptr (n+1 allocated, n_vox+1 used), new_offset (b) int64 = cumulative voxel count per scene
+ * (:267-268), meta[0] = n_vox.  No host synchronisation inside. */
+size_t aopt_voxel_partition_workspace_bytes(int n);
+int aopt_voxel_partition(int n, int b, const int64_t *sorted_keys, const int64_t *order64,
+                         const int *offset, int *order32, int *cluster32, int64_t *cluster64,
+                         int *idx_ptr, int64_t *new_offset, int *meta, void *workspace,
+                         size_t workspace_bytes, aopt_stream_t stream);
 /* Points sorted by voxel: order (n) = point ids, idx_ptr (n_vox+1).  out_feat/argmax (n_vox,c):
  * max over the voxel and the ORIGINAL id of the first maximal point; out_coord (n_vox,3) = mean
  * (sequential sum in `order`, divided by the count). */

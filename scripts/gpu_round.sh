@@ -24,5 +24,15 @@ if [ "${SKIP_NCU:-0}" != "1" ]; then
   timeout 1200 ncu --set full --clock-control none --import-source on --profile-from-start off -c 80 \
       -o $O/ops_L0 -f python scripts/profile_ops.py 0 > $O/ncu_full.log 2>&1
   tail -2 $O/ncu_full.log
-  ls -la $O
+  # gpurun_out/ is capped at 64 MiB: export what we read (raw metrics + per-kernel source pages) and drop the report
+  ncu -i $O/ops_L0.ncu-rep --page raw --csv > $O/ops_L0_raw.csv 2> /dev/null
+  for kname in gva_forward_kernel gva_backward_query_kernel gva_backward_value_kernel gather_sub_kernel segmented_sum_kernel sum_over_k_kernel knn_grid_kernel group_xyz_kernel csr_rank_kernel pool_forward_kernel; do
+    ncu -i $O/ops_L0.ncu-rep --page source --csv -k regex:$kname -c 1 > $O/src_$kname.csv 2> /dev/null
+  done
+  rm -f $O/ops_L0.ncu-rep
+  gzip -f $O/src_*.csv $O/launches.csv
+  du -sh $O
+fi
+if [ "${MAKE_GOLDEN:-0}" = "1" ]; then
+  python tests/golden/make_knn_golden_gpu.py $O/knn_ref_cuda.npz
 fi

@@ -124,13 +124,17 @@ def test_grouping2_vs_reference_cuda():
 
 
 # ------------------------------------------------------------------------------------------ GVA
-@pytest.mark.parametrize("c,g", [(48, 6), (96, 12), (384, 48), (64, 4), (30, 5)])
+@pytest.mark.parametrize("c,g,k", [(48, 6, 16), (96, 12, 16), (384, 48, 16), (64, 4, 16), (30, 5, 16),
+                                   (32, 8, 16), (48, 6, 3), (48, 6, 18), (96, 12, 7), (64, 4, 32), (20, 4, 5)])
 @pytest.mark.parametrize("use_peb", [True, False])
-def test_gva_relation_and_aggregate(oracle, c, g, use_peb):
+def test_gva_relation_and_aggregate(oracle, c, g, k, use_peb):
+    """I = c/g in {4, 8, 16} takes the 128-bit chunk kernels (1, 2, 4 lanes per group), other widths the
+    scalar kernels; k not a multiple of 4 exercises the remainder loops; n*c/4 is not a multiple of 32
+    (partial last warp in the backward-query kernel)."""
     from ao_b200 import pointops
 
-    rng = np.random.default_rng(c + g)
-    n, k = 1500, 16
+    rng = np.random.default_rng(c + g + k)
+    n = 1501
     idx = rand_idx(rng, n, k, n, pad_rows=20)
     arrs = dict(key=rng.standard_normal((n, c)), query=rng.standard_normal((n, c)), value=rng.standard_normal((n, c)),
                 peb=rng.standard_normal((n, k, c)), logits=3 * rng.standard_normal((n, k, g)),

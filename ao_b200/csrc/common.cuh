@@ -35,7 +35,7 @@ inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 
 // Streaming (touched once) data bypasses L1 so that the gathered rows keep the cache.
 __device__ __forceinline__ float4 ldg_stream4(const float *p) {
     float4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+    asm("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
                  : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
                  : "l"(p));
     return v;
@@ -47,12 +47,48 @@ __device__ __forceinline__ void stg_stream4(float *p, const float4 &v) {
 }
 __device__ __forceinline__ float ldg_stream1(const float *p) {
     float v;
-    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    asm("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
     return v;
 }
 __device__ __forceinline__ void stg_stream1(float *p, float v) {
     asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
+// Ordered variants for software-batched loads: `asm volatile` statements keep their program order, so a
+// run of these followed by issue_fence() reaches ptxas as "all loads, then the consumers" — the
+// compiler otherwise sinks each load next to its use (fewer live registers, but only ~3 requests in
+// flight per thread, and these kernels are bound by DRAM latency, not by issue slots).
+__device__ __forceinline__ float4 ldg_stream4_ordered(const float *p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float4 ldg_gather4_ordered(const float *p) {
+    float4 v;
+    asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void issue_fence() { asm volatile("" ::: "memory"); }
+
+// ---- per-thread asynchronous staging (cp.async → LDGSTS) ----------------------------------------
+// A thread copies 16-byte pieces straight from global to its OWN shared-memory slots and reads them
+// back after cp.async.wait_group: no registers are tied up while the requests are in flight and no
+// barrier is needed (nobody else touches the slots).  Slot u of thread t lives at stage[u*blockDim+t]
+// (consecutive threads → consecutive 16-byte words: conflict-free for the copy and for the read).
+__device__ __forceinline__ void cp_async16_stream(float4 *smem_dst, const float *gsrc) {  // L2 only
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async16_gather(float4 *smem_dst, const float *gsrc) {  // keep in L1
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 // Gathered rows: read-only path, default caching (re-used across neighbouring queries).
 __device__ __forceinline__ float4 ldg_gather4(const float *p) {
     return __ldg(reinterpret_cast<const float4 *>(p));

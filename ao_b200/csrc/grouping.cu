@@ -97,6 +97,67 @@ gather_sub_rows_kernel(long long m, int k, int chunks, int c, const float *__res
     }
 }
 
+// Compile-time neighbour count (NS in {8,16,32}): the idx row of the next item is prefetched and all NS
+// gathered pieces are requested at once with cp.async into the thread's own shared-memory slots, so the
+// DRAM/L2 latency is exposed once per item (NS·16 bytes of shared memory per thread).
+constexpr int kSubNsBlock = 128;
+
+template <int NS>
+__global__ void __launch_bounds__(kSubNsBlock)
+gather_sub_ns_kernel(long long m, int chunks, int c, const float *__restrict__ key,
+                     const float *__restrict__ query, const int *__restrict__ idx,
+                     float *__restrict__ out) {
+    extern __shared__ float4 stage[];  // [NS][kSubNsBlock]
+    float4 *sv = stage + threadIdx.x;
+    const long long total = m * chunks;
+    const long long step = (long long)gridDim.x * kSubNsBlock;
+    long long t = (long long)blockIdx.x * kSubNsBlock + threadIdx.x;
+    int jn[NS];
+    auto load_row = [&](long long row) {
+        const int4 *r4 = reinterpret_cast<const int4 *>(idx + (size_t)row * NS);
+#pragma unroll
+        for (int u = 0; u < NS / 4; ++u) {
+            const int4 q4 = __ldg(r4 + u);
+            jn[4 * u] = q4.x; jn[4 * u + 1] = q4.y; jn[4 * u + 2] = q4.z; jn[4 * u + 3] = q4.w;
+        }
+    };
+    if (t < total) load_row(t / chunks);
+    for (; t < total; t += step) {
+        const long long row = t / chunks;
+        const int col = (int)(t - row * chunks);
+        int j[NS];
+#pragma unroll
+        for (int s = 0; s < NS; ++s) j[s] = jn[s];
+        const float *kbase = key + col * 4;
+#pragma unroll
+        for (int s = 0; s < NS; ++s) cp_async16_gather(sv + s * kSubNsBlock, kbase + (size_t)max(j[s], 0) * c);
+        cp_async_commit();
+        const float4 q = ldg_gather4(query + (size_t)row * c + col * 4);
+        if (t + step < total) load_row((t + step) / chunks);
+        float *o = out + (size_t)row * NS * c + col * 4;
+        cp_async_wait_all();
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            const float4 v = sv[s * kSubNsBlock];
+            const bool keep = j[s] >= 0;  // idx == -1 selects the zero row (grouping.py:41-42)
+            stg_stream4(o + (size_t)s * c, make_float4((keep ? v.x : 0.f) - q.x, (keep ? v.y : 0.f) - q.y,
+                                                       (keep ? v.z : 0.f) - q.z, (keep ? v.w : 0.f) - q.w));
+        }
+    }
+}
+
+template <int NS>
+static void launch_gather_sub_ns(long long m, int chunks, int c, const float *key, const float *query,
+                                 const int *idx, float *out, cudaStream_t st) {
+    const size_t smem = (size_t)NS * 16 * kSubNsBlock;
+    static bool once = (cudaFuncSetAttribute(gather_sub_ns_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)smem), true);
+    (void)once;
+    const int per_sm = NS <= 8 ? 12 : NS <= 16 ? 6 : 3;
+    gather_sub_ns_kernel<NS><<<stride_grid(m * chunks, kSubNsBlock, per_sm), kSubNsBlock, smem, st>>>(
+        m, chunks, c, key, query, idx, out);
+}
+
 // grad_in[j, :] = scale * sum_{e in row j} grad_out[perm[e], :]   — one thread per (source row,
 // chunk); entries are visited in ascending flat position, so the sum order is fixed.
 template <int VEC>
@@ -181,6 +242,37 @@ group_xyz_kernel(long long rows, int nsample, const float *__restrict__ xyz,
     }
 }
 
+// Packed (m, k, 3) output with k a multiple of 4: one thread per (query, four slots) — one 128-bit idx
+// load, twelve gathered coordinates, three 128-bit stores (the per-slot kernel above writes 12-byte
+// pieces with scalar stores, three store instructions over the same lines).
+__global__ void __launch_bounds__(kBlock)
+group_xyz_packed_kernel(long long m, int k4, const float *__restrict__ xyz, const float *__restrict__ new_xyz,
+                        const int *__restrict__ idx, float *__restrict__ out) {
+    const long long total = m * k4;
+    const long long step = (long long)gridDim.x * kBlock;
+    for (long long t = (long long)blockIdx.x * kBlock + threadIdx.x; t < total; t += step) {
+        const long long row = t / k4;
+        const int4 j4 = __ldg(reinterpret_cast<const int4 *>(idx) + t);
+        const int j[4] = {j4.x, j4.y, j4.z, j4.w};
+        const float qx = __ldg(new_xyz + row * 3 + 0), qy = __ldg(new_xyz + row * 3 + 1),
+                    qz = __ldg(new_xyz + row * 3 + 2);
+        float r[12];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const float *p = xyz + (size_t)max(j[u], 0) * 3;
+            const float x = __ldg(p), y = __ldg(p + 1), z = __ldg(p + 2);
+            // grouping.py:41-57: the padded zero row gives (0 - q) * 0 = -0.0 or +0.0 by the sign of q
+            r[3 * u + 0] = j[u] >= 0 ? x - qx : (0.f - qx) * 0.f;
+            r[3 * u + 1] = j[u] >= 0 ? y - qy : (0.f - qy) * 0.f;
+            r[3 * u + 2] = j[u] >= 0 ? z - qz : (0.f - qz) * 0.f;
+        }
+        float *o = out + (size_t)t * 12;
+        stg_stream4(o, make_float4(r[0], r[1], r[2], r[3]));
+        stg_stream4(o + 4, make_float4(r[4], r[5], r[6], r[7]));
+        stg_stream4(o + 8, make_float4(r[8], r[9], r[10], r[11]));
+    }
+}
+
 }  // namespace aopt
 
 using namespace aopt;
@@ -227,8 +319,14 @@ extern "C" int aopt_group_xyz(int m, int nsample, const float *xyz, const float 
     long long rows = (long long)m * nsample;
     if (rows == 0) return AOPT_OK;
     if (!xyz || !new_xyz || !idx || !out) return AOPT_ERR_INVALID_ARGUMENT;
-    group_xyz_kernel<<<stride_grid(rows, kBlock, 8), kBlock, 0, as_stream(stream)>>>(
-        rows, nsample, xyz, new_xyz, idx, out, out_stride);
+    if (out_stride == 3 && nsample % 4 == 0 && aligned16(idx) && aligned16(out)) {
+        const int k4 = nsample / 4;
+        group_xyz_packed_kernel<<<stride_grid((long long)m * k4, kBlock, 8), kBlock, 0, as_stream(stream)>>>(
+            m, k4, xyz, new_xyz, idx, out);
+    } else {
+        group_xyz_kernel<<<stride_grid(rows, kBlock, 8), kBlock, 0, as_stream(stream)>>>(
+            rows, nsample, xyz, new_xyz, idx, out, out_stride);
+    }
     return check_launch();
 }
 
@@ -242,8 +340,13 @@ extern "C" int aopt_gather_sub_forward(int m, int nsample, int c, const float *k
     bool vec = (c % 4 == 0) && aligned16(key) && aligned16(query) && aligned16(out);
     if (vec) {
         int chunks = c / 4;
-        gather_sub_rows_kernel<<<stride_grid((long long)m * chunks, kBlock, 8), kBlock, 0, as_stream(stream)>>>(
-            m, nsample, chunks, c, key, query, idx, out);
+        const bool ns_ok = aligned16(idx);
+        if (ns_ok && nsample == 16) launch_gather_sub_ns<16>(m, chunks, c, key, query, idx, out, as_stream(stream));
+        else if (ns_ok && nsample == 8) launch_gather_sub_ns<8>(m, chunks, c, key, query, idx, out, as_stream(stream));
+        else if (ns_ok && nsample == 32) launch_gather_sub_ns<32>(m, chunks, c, key, query, idx, out, as_stream(stream));
+        else
+            gather_sub_rows_kernel<<<stride_grid((long long)m * chunks, kBlock, 8), kBlock, 0, as_stream(stream)>>>(
+                m, nsample, chunks, c, key, query, idx, out);
     } else {
         gather_sub_kernel<1><<<stride_grid(rows * c, kBlock, 8), kBlock, 0, as_stream(stream)>>>(
             rows, nsample, c, c, key, query, idx, out);

@@ -115,6 +115,90 @@ gva_forward_kernel(long long n, int k, int c, int g, const float *__restrict__ v
     }
 }
 
+// ---- forward, compile-time neighbour count (NS in {8,16,32}) -----------------------------------------
+// Same mapping as gva_forward_kernel, restructured around the DRAM latency (the generic kernel exposes it
+// ~9 times per point and ptxas sinks register loads next to their uses, leaving ~3 requests in flight):
+//   * the idx row of the NEXT item is prefetched into registers while the current one is processed;
+//   * at the top of an item all NS peb pieces and all NS gathered value pieces are requested at once
+//     with cp.async into the thread's own shared-memory slots (no registers held, no barrier);
+//   * the logits column is loaded and the softmax computed while those copies are in flight.
+// One latency window per item instead of nine; 2·NS·16 bytes of shared memory per thread.
+constexpr int kGvaNsBlock = 128;
+
+__device__ __forceinline__ void load_idx_row16(const int *__restrict__ row, int *j, int count4) {
+    const int4 *r4 = reinterpret_cast<const int4 *>(row);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        if (u < count4) {
+            const int4 q4 = __ldg(r4 + u);
+            j[4 * u] = q4.x; j[4 * u + 1] = q4.y; j[4 * u + 2] = q4.z; j[4 * u + 3] = q4.w;
+        }
+    }
+}
+
+template <int GL, int NS, bool HAS_PEB>
+__global__ void __launch_bounds__(kGvaNsBlock)
+gva_forward_ns_kernel(long long n, int c, int g, const float *__restrict__ value,
+                      const float *__restrict__ peb, const float *__restrict__ logits,
+                      const int *__restrict__ idx, float *__restrict__ out, float *__restrict__ prob) {
+    extern __shared__ float4 stage[];  // [2*NS][kGvaNsBlock]: value pieces, then peb pieces
+    float4 *sv = stage + threadIdx.x;
+    float4 *sq = stage + NS * kGvaNsBlock + threadIdx.x;
+    const int chunks = c >> 2;
+    const long long total = n * chunks;
+    const long long step = (long long)gridDim.x * kGvaNsBlock;
+    long long t = (long long)blockIdx.x * kGvaNsBlock + threadIdx.x;
+    int jn[NS];
+    if (t < total) load_idx_row16(idx + (size_t)(t / chunks) * NS, jn, NS / 4);
+    for (; t < total; t += step) {
+        const long long pt = t / chunks;
+        const int ch = (int)(t - pt * chunks);
+        const int gi = ch / GL;
+        const bool writer = (ch % GL) == 0;
+        int j[NS];
+#pragma unroll
+        for (int s = 0; s < NS; ++s) j[s] = jn[s];
+        const float *vbase = value + ch * 4;
+#pragma unroll
+        for (int s = 0; s < NS; ++s) cp_async16_gather(sv + s * kGvaNsBlock, vbase + (size_t)max(j[s], 0) * c);
+        if (HAS_PEB) {
+            const float *pe = peb + (size_t)pt * NS * c + ch * 4;
+#pragma unroll
+            for (int s = 0; s < NS; ++s) cp_async16_stream(sq + s * kGvaNsBlock, pe + (size_t)s * c);
+        }
+        cp_async_commit();
+        const float *lg = logits + (size_t)pt * NS * g + gi;
+        float e[NS];
+#pragma unroll
+        for (int s = 0; s < NS; ++s) e[s] = __ldg(lg + (size_t)s * g);
+        if (t + step < total) load_idx_row16(idx + (size_t)((t + step) / chunks) * NS, jn, NS / 4);
+        float mx = -INFINITY;
+#pragma unroll
+        for (int s = 0; s < NS; ++s) mx = fmaxf(mx, e[s]);
+        float sum = 0.f;
+#pragma unroll
+        for (int s = 0; s < NS; ++s) { e[s] = expf(e[s] - mx); sum += e[s]; }
+        // softmax probabilities: one IEEE division, then multiplies (within 1 ulp of exp(x-max)/sum)
+        const float inv = 1.0f / sum;
+#pragma unroll
+        for (int s = 0; s < NS; ++s) e[s] *= inv;
+        if (prob && writer) {
+            float *pr = prob + (size_t)pt * NS * g + gi;
+#pragma unroll
+            for (int s = 0; s < NS; ++s) pr[(size_t)s * g] = e[s];
+        }
+        cp_async_wait_all();
+        float4 acc = f4_zero();
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            const float4 v = sv[s * kGvaNsBlock];
+            const float4 q = HAS_PEB ? sq[s * kGvaNsBlock] : f4_zero();
+            fma_keep(acc, f4_add(v, q), e[s], j[s] >= 0);  // sign(idx+1) mask
+        }
+        *reinterpret_cast<float4 *>(out + (size_t)pt * c + ch * 4) = acc;
+    }
+}
+
 // ---- backward, per query: grad_peb and grad_logits ---------------------------------------------------
 // grad_logits[n,s,g] = p_s (gw_s - Σ_s' p_s' gw_s'),  gw_s = mask_s <grad_out[n, group g], value[idx]+peb>.
 template <int GL>
@@ -190,17 +274,95 @@ gva_backward_query_kernel(long long n, int k, int c, int g, const float *__restr
     }
 }
 
+// Compile-time neighbour count: same latency-oriented structure as gva_forward_ns_kernel (idx prefetch,
+// all peb / value pieces requested at once with cp.async into per-thread slots); the probability
+// column is loaded while the copies fly and gw stays in registers (no parking in grad_logits).
+template <int GL, int NS, bool HAS_PEB>
+__global__ void __launch_bounds__(kGvaNsBlock)
+gva_backward_query_ns_kernel(long long n, int c, int g, const float *__restrict__ grad_out,
+                             const float *__restrict__ value, const float *__restrict__ peb,
+                             const float *__restrict__ prob, const int *__restrict__ idx,
+                             float *__restrict__ grad_peb, float *__restrict__ grad_logits) {
+    extern __shared__ float4 stage[];
+    float4 *sv = stage + threadIdx.x;
+    float4 *sq = stage + NS * kGvaNsBlock + threadIdx.x;
+    const int chunks = c >> 2;
+    const long long total = n * chunks;
+    const long long step = (long long)gridDim.x * kGvaNsBlock;
+    // warp-uniform trip count (see gva_backward_query_kernel)
+    long long base = (long long)blockIdx.x * kGvaNsBlock + (threadIdx.x & ~31);
+    const int lane = threadIdx.x & 31;
+    int jn[NS];
+    if (base < total) load_idx_row16(idx + (size_t)(min(base + lane, total - 1) / chunks) * NS, jn, NS / 4);
+    for (; base < total; base += step) {
+        const long long t_raw = base + lane;
+        const bool live = t_raw < total;
+        const long long t = live ? t_raw : total - 1;
+        const long long pt = t / chunks;
+        const int ch = (int)(t - pt * chunks);
+        const int gi = ch / GL;
+        const bool writer = live && (ch % GL) == 0;
+        int j[NS];
+#pragma unroll
+        for (int s = 0; s < NS; ++s) j[s] = jn[s];
+        const float *vbase = value + ch * 4;
+#pragma unroll
+        for (int s = 0; s < NS; ++s) cp_async16_gather(sv + s * kGvaNsBlock, vbase + (size_t)max(j[s], 0) * c);
+        if (HAS_PEB) {
+            const float *pe = peb + (size_t)pt * NS * c + ch * 4;
+#pragma unroll
+            for (int s = 0; s < NS; ++s) cp_async16_stream(sq + s * kGvaNsBlock, pe + (size_t)s * c);
+        }
+        cp_async_commit();
+        const float4 go = ldg_gather4(grad_out + (size_t)pt * c + ch * 4);
+        const float *pr = prob + (size_t)pt * NS * g + gi;
+        float p[NS], gw[NS];
+#pragma unroll
+        for (int s = 0; s < NS; ++s) p[s] = __ldg(pr + (size_t)s * g);
+        if (base + step < total)
+            load_idx_row16(idx + (size_t)(min(base + step + lane, total - 1) / chunks) * NS, jn, NS / 4);
+        float *gp = (HAS_PEB && grad_peb && live) ? grad_peb + (size_t)pt * NS * c + ch * 4 : nullptr;
+        cp_async_wait_all();
+        float dot = 0.f;
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            const bool keep = j[s] >= 0;
+            const float4 v = sv[s * kGvaNsBlock];
+            const float4 q = HAS_PEB ? sq[s * kGvaNsBlock] : f4_zero();
+            const float d = group_sum<GL>(dot4(go, f4_add(v, q)));
+            gw[s] = keep ? d : 0.f;
+            const float w = keep ? p[s] : 0.f;
+            if (gp) stg_stream4(gp + (size_t)s * c, make_float4(go.x * w, go.y * w, go.z * w, go.w * w));
+            dot = fmaf(p[s], gw[s], dot);
+        }
+        if (writer) {
+            float *gl = grad_logits + (size_t)pt * NS * g + gi;
+#pragma unroll
+            for (int s = 0; s < NS; ++s) gl[(size_t)s * g] = p[s] * (gw[s] - dot);  // softmax backward
+        }
+    }
+}
+
 // ---- backward, per source: grad_value through the CSR ------------------------------------------------
 // kshift >= 0: k is a power of two and q = p >> kshift; otherwise q = p / k.
+// The row walk is a dependent chain (rowptr → perm → prob / grad_out), so entries are taken eight at a
+// time: eight perm loads, then eight grad_out pieces requested with cp.async into the thread's own
+// shared-memory slots plus eight probability loads, with the next eight perm values prefetched while
+// those are in flight.
+constexpr int kBvBlock = 256;
+constexpr int kBvBatch = 8;
+
 template <int GL>
-__global__ void __launch_bounds__(kGvaBlock)
+__global__ void __launch_bounds__(kBvBlock)
 gva_backward_value_kernel(long long n_src, int k, int kshift, int c, int g, const float *__restrict__ grad_out,
                           const float *__restrict__ prob, const int *__restrict__ rowptr,
                           const int *__restrict__ perm, float *__restrict__ grad_value) {
+    __shared__ float4 stage[kBvBatch * kBvBlock];
+    float4 *sg = stage + threadIdx.x;
     const int chunks = c >> 2;
     const long long total = n_src * chunks;
-    const long long step = (long long)gridDim.x * kGvaBlock;
-    for (long long t = (long long)blockIdx.x * kGvaBlock + threadIdx.x; t < total; t += step) {
+    const long long step = (long long)gridDim.x * kBvBlock;
+    for (long long t = (long long)blockIdx.x * kBvBlock + threadIdx.x; t < total; t += step) {
         const long long j = t / chunks;
         const int ch = (int)(t - j * chunks);
         const int gi = ch / GL;
@@ -208,25 +370,27 @@ gva_backward_value_kernel(long long n_src, int k, int kshift, int c, int g, cons
         float4 acc = f4_zero();
         int e = __ldg(rowptr + j);
         const int e_end = __ldg(rowptr + j + 1);
-        for (; e + 4 <= e_end; e += 4) {
-            int p[4];
-            float w[4];
-            float4 go[4];
+        int pn[kBvBatch];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) p[u] = __ldg(perm + e + u);  // flat (query, slot); idx[p] == j >= 0, mask = 1
+        for (int u = 0; u < kBvBatch; ++u) pn[u] = (e + u < e_end) ? __ldg(perm + e + u) : 0;
+        for (; e < e_end; e += kBvBatch) {
+            int p[kBvBatch];
+            float w[kBvBatch];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < kBvBatch; ++u) {
+                p[u] = pn[u];  // flat (query, slot) position; idx[p] == j >= 0, so the mask is 1
                 const int q = kshift >= 0 ? (p[u] >> kshift) : (p[u] / k);
-                go[u] = ldg_gather4(gbase + (size_t)q * c);
-                w[u] = __ldg(prob + (size_t)p[u] * g + gi);
+                cp_async16_gather(sg + u * kBvBlock, gbase + (size_t)q * c);
             }
+            cp_async_commit();
 #pragma unroll
-            for (int u = 0; u < 4; ++u) fma_keep(acc, go[u], w[u], true);
-        }
-        for (; e < e_end; ++e) {
-            const int p = __ldg(perm + e);
-            const int q = kshift >= 0 ? (p >> kshift) : (p / k);
-            fma_keep(acc, ldg_gather4(gbase + (size_t)q * c), __ldg(prob + (size_t)p * g + gi), true);
+            for (int u = 0; u < kBvBatch; ++u) w[u] = (e + u < e_end) ? __ldg(prob + (size_t)p[u] * g + gi) : 0.f;
+#pragma unroll
+            for (int u = 0; u < kBvBatch; ++u)
+                pn[u] = (e + kBvBatch + u < e_end) ? __ldg(perm + e + kBvBatch + u) : 0;
+            cp_async_wait_all();
+#pragma unroll
+            for (int u = 0; u < kBvBatch; ++u) fma_keep(acc, sg[u * kBvBlock], w[u], e + u < e_end);
         }
         *reinterpret_cast<float4 *>(grad_value + (size_t)j * c + ch * 4) = acc;
     }
@@ -346,6 +510,32 @@ static int log2_exact(int k) {
 
 using namespace aopt;
 
+// Grid of the NS kernels: GRID here is the work-item count; resident CTAs per SM follow from the
+// 2·NS·16·128 bytes of shared memory each CTA needs (227 KB per SM).
+static int ns_grid(long long items, int ns) { return stride_grid(items, kGvaNsBlock, ns <= 8 ? 6 : ns <= 16 ? 3 : 1); }
+
+// Dynamic shared memory of the NS kernels: 2·NS slots of 16 bytes per thread (64 KB at NS=16 → opt-in).
+#define GVA_DISPATCH_NS2(GLV, NSV, PEB, KERNEL, GRID, ST, ...)                                          \
+    {                                                                                                  \
+        const size_t smem = (size_t)2 * NSV * 16 * kGvaNsBlock;                                        \
+        if (PEB) {                                                                                     \
+            static bool once = (cudaFuncSetAttribute(KERNEL<GLV, NSV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), true); \
+            (void)once;                                                                                \
+            KERNEL<GLV, NSV, true><<<ns_grid(GRID, NSV), kGvaNsBlock, smem, ST>>>(__VA_ARGS__);        \
+        } else {                                                                                       \
+            static bool once = (cudaFuncSetAttribute(KERNEL<GLV, NSV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), true); \
+            (void)once;                                                                                \
+            KERNEL<GLV, NSV, false><<<ns_grid(GRID, NSV), kGvaNsBlock, smem, ST>>>(__VA_ARGS__);       \
+        }                                                                                              \
+    }
+
+#define GVA_DISPATCH_NS(GLVAR, NSV, PEB, KERNEL, GRID, ST, ...)                                         \
+    switch (GLVAR) {                                                                                   \
+        case 1: GVA_DISPATCH_NS2(1, NSV, PEB, KERNEL, GRID, ST, __VA_ARGS__) break;                    \
+        case 2: GVA_DISPATCH_NS2(2, NSV, PEB, KERNEL, GRID, ST, __VA_ARGS__) break;                    \
+        default: GVA_DISPATCH_NS2(4, NSV, PEB, KERNEL, GRID, ST, __VA_ARGS__) break;                   \
+    }
+
 #define GVA_DISPATCH(GLVAR, KERNEL, GRID, ST, ...)                                     \
     switch (GLVAR) {                                                                   \
         case 1: KERNEL<1><<<GRID, kGvaBlock, 0, ST>>>(__VA_ARGS__); break;             \
@@ -368,9 +558,22 @@ extern "C" int aopt_gva_forward(int n, int nsample, int c, int g, const float *v
     const int I = c / g;
     const int gl = pick_gl(c, I, {value, peb, out});
     if (gl > 0) {
-        const int grid = stride_grid((long long)n * (c / 4), kGvaBlock, 8);
-        GVA_DISPATCH(gl, gva_forward_kernel, grid, as_stream(stream), (long long)n, nsample, c, g, value, peb, logits,
-                     idx, out, prob);
+        const long long items = (long long)n * (c / 4);
+        const int grid = stride_grid(items, kGvaBlock, 8);
+        const bool ns_ok = aligned16(idx);  // the specialised kernels read the idx row as int4
+        if (ns_ok && nsample == 16) {
+            GVA_DISPATCH_NS(gl, 16, peb != nullptr, gva_forward_ns_kernel, items, as_stream(stream), (long long)n, c, g, value, peb,
+                            logits, idx, out, prob);
+        } else if (ns_ok && nsample == 8) {
+            GVA_DISPATCH_NS(gl, 8, peb != nullptr, gva_forward_ns_kernel, items, as_stream(stream), (long long)n, c, g, value, peb,
+                            logits, idx, out, prob);
+        } else if (ns_ok && nsample == 32) {
+            GVA_DISPATCH_NS(gl, 32, peb != nullptr, gva_forward_ns_kernel, items, as_stream(stream), (long long)n, c, g, value, peb,
+                            logits, idx, out, prob);
+        } else {
+            GVA_DISPATCH(gl, gva_forward_kernel, grid, as_stream(stream), (long long)n, nsample, c, g, value, peb,
+                         logits, idx, out, prob);
+        }
     } else {
         if (I > kMaxScalarI) return AOPT_ERR_UNSUPPORTED;
         gva_forward_scalar_kernel<<<stride_grid((long long)n * g, kGvaBlock, 8), kGvaBlock, 0, as_stream(stream)>>>(
@@ -390,9 +593,22 @@ extern "C" int aopt_gva_backward_query(int n, int nsample, int c, int g, const f
     const int I = c / g;
     const int gl = pick_gl(c, I, {grad_out, value, peb, grad_peb});
     if (gl > 0) {
-        const int grid = stride_grid((long long)n * (c / 4), kGvaBlock, 8);
-        GVA_DISPATCH(gl, gva_backward_query_kernel, grid, as_stream(stream), (long long)n, nsample, c, g, grad_out,
-                     value, peb, prob, idx, grad_peb, grad_logits);
+        const long long items = (long long)n * (c / 4);
+        const int grid = stride_grid(items, kGvaBlock, 8);
+        const bool ns_ok = aligned16(idx);
+        if (ns_ok && nsample == 16) {
+            GVA_DISPATCH_NS(gl, 16, peb != nullptr, gva_backward_query_ns_kernel, items, as_stream(stream), (long long)n, c, g, grad_out,
+                            value, peb, prob, idx, grad_peb, grad_logits);
+        } else if (ns_ok && nsample == 8) {
+            GVA_DISPATCH_NS(gl, 8, peb != nullptr, gva_backward_query_ns_kernel, items, as_stream(stream), (long long)n, c, g, grad_out,
+                            value, peb, prob, idx, grad_peb, grad_logits);
+        } else if (ns_ok && nsample == 32) {
+            GVA_DISPATCH_NS(gl, 32, peb != nullptr, gva_backward_query_ns_kernel, items, as_stream(stream), (long long)n, c, g, grad_out,
+                            value, peb, prob, idx, grad_peb, grad_logits);
+        } else {
+            GVA_DISPATCH(gl, gva_backward_query_kernel, grid, as_stream(stream), (long long)n, nsample, c, g, grad_out,
+                         value, peb, prob, idx, grad_peb, grad_logits);
+        }
     } else {
         if (I > kMaxScalarI) return AOPT_ERR_UNSUPPORTED;
         gva_backward_query_scalar_kernel<<<stride_grid((long long)n * g, kGvaBlock, 8), kGvaBlock, 0, as_stream(stream)>>>(
@@ -411,7 +627,7 @@ extern "C" int aopt_gva_backward_value(int n_src, int nsample, int c, int g, con
     const int I = c / g;
     const int gl = pick_gl(c, I, {grad_out, grad_value});
     if (gl > 0) {
-        const int grid = stride_grid((long long)n_src * (c / 4), kGvaBlock, 8);
+        const int grid = stride_grid((long long)n_src * (c / 4), kBvBlock, 6);
         GVA_DISPATCH(gl, gva_backward_value_kernel, grid, as_stream(stream), (long long)n_src, nsample,
                      log2_exact(nsample), c, g, grad_out, prob, rowptr, perm, grad_value);
     } else {

@@ -18,6 +18,8 @@
 //
 // GRID method (part 2, knn_grid.cu) prunes the candidate set with a uniform grid and is what the
 // AUTO policy picks for large scenes; both return identical results.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "knn_common.cuh"
 
@@ -168,14 +170,25 @@ int knn_grid_launch(int m, int nsample, int n, int b, const float *xyz, const fl
 
 using namespace aopt;
 
-// Scenes smaller than this are cheaper to scan than to bin.
-static const int kGridMinPoints = 4096;
+// Scenes smaller than this (average points per scene) are cheaper to scan than to bin.
+// AOPT_KNN_GRID_MIN overrides it (tuning runs).
+static int grid_min_points() {
+    static int v = [] {
+        int d = 4096;
+        if (const char *e = getenv("AOPT_KNN_GRID_MIN")) {
+            int x = atoi(e);
+            if (x > 0) d = x;
+        }
+        return d;
+    }();
+    return v;
+}
 
 static int pick_method(int n, int m, int b, int nsample, int method) {
     if (method == AOPT_KNN_TILE || method == AOPT_KNN_GRID) return method;
     if (nsample > 32) return AOPT_KNN_TILE;
     long long avg = b > 0 ? (long long)n / b : n;
-    return avg >= kGridMinPoints ? AOPT_KNN_GRID : AOPT_KNN_TILE;
+    return avg >= grid_min_points() ? AOPT_KNN_GRID : AOPT_KNN_TILE;
 }
 
 extern "C" size_t aopt_knn_workspace_bytes(int n, int m, int b, int nsample, int method) {

@@ -59,12 +59,19 @@ voxel_keys_kernel(int n, int b, const float *__restrict__ coord, const int *__re
 }
 
 // One thread per (voxel, 4-channel chunk): running max + the original id of the first maximal point.
+// The voxel walk is a dependent chain (idx_ptr → order → feat row), so the 128-bit path takes the points
+// of a voxel eight at a time: eight `order` loads, then eight feature pieces requested with cp.async into
+// the thread's own shared-memory slots, the next eight `order` values prefetched meanwhile.
+constexpr int kPoolBatch = 8;
+
 template <int VEC>
 __global__ void __launch_bounds__(kPoolBlock)
 pool_forward_kernel(long long n_vox, int chunks, int c, const float *__restrict__ feat,
                     const float *__restrict__ coord, const int *__restrict__ order,
                     const int *__restrict__ idx_ptr, float *__restrict__ out_feat,
                     int *__restrict__ argmax, float *__restrict__ out_coord) {
+    __shared__ float4 stage[VEC == 4 ? kPoolBatch * kPoolBlock : 1];
+    float4 *sf = stage + threadIdx.x;
     const long long total = n_vox * chunks;
     const long long step = (long long)gridDim.x * kPoolBlock;
     for (long long t = (long long)blockIdx.x * kPoolBlock + threadIdx.x; t < total; t += step) {
@@ -76,22 +83,54 @@ pool_forward_kernel(long long n_vox, int chunks, int c, const float *__restrict_
 #pragma unroll
         for (int i = 0; i < VEC; ++i) { best[i] = -FLT_MAX; arg[i] = -1; }
         float sx = 0.f, sy = 0.f, sz = 0.f;
-        for (int e = e0; e < e1; ++e) {
-            const int pt = __ldg(order + e);
-            float x[VEC];
-            if constexpr (VEC == 4) {
-                float4 q = ldg_stream4(feat + (size_t)pt * c + col * 4);
-                x[0] = q.x; x[1] = q.y; x[2] = q.z; x[3] = q.w;
-            } else {
-                x[0] = __ldg(feat + (size_t)pt * c + col);
-            }
+        const bool do_coord = col == 0 && out_coord;
+        if constexpr (VEC == 4) {
+            int pn[kPoolBatch];
 #pragma unroll
-            for (int i = 0; i < VEC; ++i)
-                if (x[i] > best[i]) { best[i] = x[i]; arg[i] = pt; }
-            if (col == 0 && out_coord) {  // sequential sum in `order`, like segment_csr
-                sx += __ldg(coord + (size_t)pt * 3 + 0);
-                sy += __ldg(coord + (size_t)pt * 3 + 1);
-                sz += __ldg(coord + (size_t)pt * 3 + 2);
+            for (int u = 0; u < kPoolBatch; ++u) pn[u] = (e0 + u < e1) ? __ldg(order + e0 + u) : 0;
+            for (int e = e0; e < e1; e += kPoolBatch) {
+                int pt[kPoolBatch];
+#pragma unroll
+                for (int u = 0; u < kPoolBatch; ++u) {
+                    pt[u] = pn[u];
+                    cp_async16_stream(sf + u * kPoolBlock, feat + (size_t)pt[u] * c + col * 4);
+                }
+                cp_async_commit();
+#pragma unroll
+                for (int u = 0; u < kPoolBatch; ++u)
+                    pn[u] = (e + kPoolBatch + u < e1) ? __ldg(order + e + kPoolBatch + u) : 0;
+                if (do_coord) {  // sequential sum in `order`, like segment_csr
+#pragma unroll
+                    for (int u = 0; u < kPoolBatch; ++u) {
+                        if (e + u < e1) {
+                            sx += __ldg(coord + (size_t)pt[u] * 3 + 0);
+                            sy += __ldg(coord + (size_t)pt[u] * 3 + 1);
+                            sz += __ldg(coord + (size_t)pt[u] * 3 + 2);
+                        }
+                    }
+                }
+                cp_async_wait_all();
+#pragma unroll
+                for (int u = 0; u < kPoolBatch; ++u) {
+                    if (e + u < e1) {
+                        const float4 q = sf[u * kPoolBlock];
+                        const float x[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            if (x[i] > best[i]) { best[i] = x[i]; arg[i] = pt[u]; }
+                    }
+                }
+            }
+        } else {
+            for (int e = e0; e < e1; ++e) {
+                const int pt = __ldg(order + e);
+                const float x = __ldg(feat + (size_t)pt * c + col);
+                if (x > best[0]) { best[0] = x; arg[0] = pt; }
+                if (do_coord) {
+                    sx += __ldg(coord + (size_t)pt * 3 + 0);
+                    sy += __ldg(coord + (size_t)pt * 3 + 1);
+                    sz += __ldg(coord + (size_t)pt * 3 + 2);
+                }
             }
         }
         const size_t o = (size_t)v * c + col * VEC;
@@ -106,7 +145,7 @@ pool_forward_kernel(long long n_vox, int chunks, int c, const float *__restrict_
             out_feat[o] = best[0];
             argmax[o] = arg[0];
         }
-        if (col == 0 && out_coord) {
+        if (do_coord) {
             const float cnt = (float)max(e1 - e0, 1);
             out_coord[v * 3 + 0] = sx / cnt;
             out_coord[v * 3 + 1] = sy / cnt;
@@ -256,7 +295,7 @@ extern "C" int aopt_pool_forward(int n_vox, int c, const float *feat, const floa
     const bool vec = (c % 4 == 0) && aligned16(feat) && aligned16(out_feat) && aligned16(argmax);
     if (vec) {
         const int chunks = c / 4;
-        pool_forward_kernel<4><<<stride_grid((long long)n_vox * chunks, kPoolBlock, 8), kPoolBlock, 0, as_stream(stream)>>>(
+        pool_forward_kernel<4><<<stride_grid((long long)n_vox * chunks, kPoolBlock, 6), kPoolBlock, 0, as_stream(stream)>>>(
             n_vox, chunks, c, feat, coord, order, idx_ptr, out_feat, argmax, out_coord);
     } else {
         pool_forward_kernel<1><<<stride_grid((long long)n_vox * c, kPoolBlock, 8), kPoolBlock, 0, as_stream(stream)>>>(

@@ -33,6 +33,9 @@ if [ "${SKIP_NCU:-0}" != "1" ]; then
   gzip -f $O/src_*.csv $O/launches.csv
   du -sh $O
 fi
+if [ "${KNN_SWEEP:-0}" = "1" ]; then
+  timeout 600 python scripts/knn_sweep.py > $O/knn_sweep.txt 2>&1; cat $O/knn_sweep.txt
+fi
 if [ "${MAKE_GOLDEN:-0}" = "1" ]; then
   python tests/golden/make_knn_golden_gpu.py $O/knn_ref_cuda.npz
 fi

@@ -13,6 +13,8 @@
 //
 // Algorithmic bytes: forward 4·M·k + 4·N·C + 4·M·k·C;
 // backward 4·M·k·C + 4·M·k + 4·(N+1) + 4·N·C.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace aopt {
@@ -340,7 +342,8 @@ extern "C" int aopt_gather_sub_forward(int m, int nsample, int c, const float *k
     bool vec = (c % 4 == 0) && aligned16(key) && aligned16(query) && aligned16(out);
     if (vec) {
         int chunks = c / 4;
-        const bool ns_ok = aligned16(idx);
+        static const bool use_rows = [] { const char *e = getenv("AOPT_GATHER_SUB_IMPL"); return e && e[0] == 'r'; }();
+        const bool ns_ok = aligned16(idx) && !use_rows;
         if (ns_ok && nsample == 16) launch_gather_sub_ns<16>(m, chunks, c, key, query, idx, out, as_stream(stream));
         else if (ns_ok && nsample == 8) launch_gather_sub_ns<8>(m, chunks, c, key, query, idx, out, as_stream(stream));
         else if (ns_ok && nsample == 32) launch_gather_sub_ns<32>(m, chunks, c, key, query, idx, out, as_stream(stream));

@@ -27,6 +27,7 @@
 // Algorithmic bytes: forward 4NC + 4NkC + 4NkG(+4NkG prob) + 4Nk + 4NC;
 // backward reads 8NC + 4NkC + 4NkG + 8Nk + 4(N+1), writes 4NkC + 4NkG + 4NC.
 #include <math.h>
+#include <stdlib.h>
 #include <initializer_list>
 
 #include "common.cuh"
@@ -396,6 +397,47 @@ gva_backward_value_kernel(long long n_src, int k, int kshift, int c, int g, cons
     }
 }
 
+// Four entries at a time with plain loads (tuning alternative, AOPT_BV_IMPL=unroll4).
+template <int GL>
+__global__ void __launch_bounds__(kGvaBlock)
+gva_backward_value_unroll4_kernel(long long n_src, int k, int kshift, int c, int g, const float *__restrict__ grad_out,
+                          const float *__restrict__ prob, const int *__restrict__ rowptr,
+                          const int *__restrict__ perm, float *__restrict__ grad_value) {
+    const int chunks = c >> 2;
+    const long long total = n_src * chunks;
+    const long long step = (long long)gridDim.x * kGvaBlock;
+    for (long long t = (long long)blockIdx.x * kGvaBlock + threadIdx.x; t < total; t += step) {
+        const long long j = t / chunks;
+        const int ch = (int)(t - j * chunks);
+        const int gi = ch / GL;
+        const float *gbase = grad_out + ch * 4;
+        float4 acc = f4_zero();
+        int e = __ldg(rowptr + j);
+        const int e_end = __ldg(rowptr + j + 1);
+        for (; e + 4 <= e_end; e += 4) {
+            int p[4];
+            float w[4];
+            float4 go[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) p[u] = __ldg(perm + e + u);  // flat (query, slot); idx[p] == j >= 0, mask = 1
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int q = kshift >= 0 ? (p[u] >> kshift) : (p[u] / k);
+                go[u] = ldg_gather4(gbase + (size_t)q * c);
+                w[u] = __ldg(prob + (size_t)p[u] * g + gi);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) fma_keep(acc, go[u], w[u], true);
+        }
+        for (; e < e_end; ++e) {
+            const int p = __ldg(perm + e);
+            const int q = kshift >= 0 ? (p >> kshift) : (p / k);
+            fma_keep(acc, ldg_gather4(gbase + (size_t)q * c), __ldg(prob + (size_t)p * g + gi), true);
+        }
+        *reinterpret_cast<float4 *>(grad_value + (size_t)j * c + ch * 4) = acc;
+    }
+}
+
 // ---- scalar fallback (I not a multiple of 4, I not in {4,8,16}, or unaligned pointers) ----------------
 // One thread per (point, group) holding the I channels of the group in registers.
 __global__ void __launch_bounds__(kGvaBlock)
@@ -627,6 +669,13 @@ extern "C" int aopt_gva_backward_value(int n_src, int nsample, int c, int g, con
     const int I = c / g;
     const int gl = pick_gl(c, I, {grad_out, grad_value});
     if (gl > 0) {
+        static const bool use_unroll4 = [] { const char *e = getenv("AOPT_BV_IMPL"); return e && e[0] == 'u'; }();
+        if (use_unroll4) {
+            const int grid4 = stride_grid((long long)n_src * (c / 4), kGvaBlock, 8);
+            GVA_DISPATCH(gl, gva_backward_value_unroll4_kernel, grid4, as_stream(stream), (long long)n_src, nsample,
+                         log2_exact(nsample), c, g, grad_out, prob, rowptr, perm, grad_value);
+            return check_launch();
+        }
         const int grid = stride_grid((long long)n_src * (c / 4), kBvBlock, 6);
         GVA_DISPATCH(gl, gva_backward_value_kernel, grid, as_stream(stream), (long long)n_src, nsample,
                      log2_exact(nsample), c, g, grad_out, prob, rowptr, perm, grad_value);

@@ -103,7 +103,6 @@ def test_gva_aggregate_full_size(batch, oracle):
     assert bool((o1[~full] < 1).all())
     # row subset against the torch restatement, forward and backward
     rows = torch.cat([torch.arange(0, n, 997, device="cuda"), torch.arange(0, n, 1000, device="cuda")]).unique()
-    r_out = oracle.gva_aggregate(value, peb[rows], logits[rows], idx[rows], G) if False else None
     v_c, p_c, l_c = value.detach().clone().requires_grad_(True), peb.detach()[rows].clone().requires_grad_(True), \
         logits.detach()[rows].clone().requires_grad_(True)
     ref = oracle.gva_aggregate(v_c, p_c, l_c, idx[rows], G)      # torch ops on the GPU tensors

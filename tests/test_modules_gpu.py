@@ -25,11 +25,22 @@ def load_params(module, g):
     assert all(("running_" in m) or ("num_batches_tracked" in m) for m in missing), missing
 
 
+# Biases of a Linear that feeds a training-mode BatchNorm have an analytically ZERO gradient (the batch
+# mean removes them); what both the reference and this build compute there is fp32 rounding noise, so
+# the two are compared against zero instead of against each other.
+BIAS_BEFORE_BN = ("linear_p_bias.0.bias", "weight_encoding.0.bias", "linear_q.0.bias", "linear_k.0.bias",
+                  "linear_p_multiplier.0.bias", "proj.0.bias", "proj_skip.0.bias")
+
+
 def check_param_grads(module, g, rtol, atol):
     worst = 0.0
     for name, p in module.named_parameters():
         ref = g["grad." + name]
         got = p.grad.detach().cpu()
+        if name.endswith(BIAS_BEFORE_BN):
+            scale = max(1.0, float(g["grad_y"].abs().max())) if "grad_y" in g else 1.0
+            assert got.abs().max().item() < 2e-3 * scale and ref.abs().max().item() < 2e-3 * scale, name
+            continue
         assert torch.allclose(got, ref, rtol=rtol, atol=atol), (name, (got - ref).abs().max().item())
         worst = max(worst, (got - ref).abs().max().item())
     return worst

@@ -12,23 +12,31 @@ __global__ void __launch_bounds__(kBboxBlock)
 scene_bbox_kernel(int n, int b, const float *__restrict__ xyz, const int *__restrict__ offset,
                   unsigned *__restrict__ lo, unsigned *__restrict__ hi) {
     __shared__ float red[6][kBboxBlock / 32];
+    __shared__ int seg_s[2];
     const int base = blockIdx.x * kBboxChunk;
     const int last = min(base + kBboxChunk, n) - 1;
-    const int sc_first = find_segment(base, offset, b), sc_last = find_segment(last, offset, b);
+    if (threadIdx.x < 2) seg_s[threadIdx.x] = find_segment(threadIdx.x == 0 ? base : last, offset, b);
+    __syncthreads();
+    const int sc_first = seg_s[0], sc_last = seg_s[1];
     if (sc_first == sc_last) {
         // the whole chunk lies in one scene: block reduction, then six atomics
         if (sc_first >= b) return;  // past the last offset: belongs to no scene
         float mn[3] = {3.0e38f, 3.0e38f, 3.0e38f}, mx[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+        // unconditional loads (index clamped to the chunk's last point: duplicates do not change a
+        // min/max), so all 24 requests of a thread are in flight together
+        float v[kBboxPerThread][3];
 #pragma unroll
         for (int u = 0; u < kBboxPerThread; ++u) {
-            const int i = base + u * kBboxBlock + threadIdx.x;
-            if (i <= last) {
+            const int i = min(base + u * kBboxBlock + (int)threadIdx.x, last);
 #pragma unroll
-                for (int a = 0; a < 3; ++a) {
-                    const float v = __ldg(xyz + (size_t)i * 3 + a);
-                    mn[a] = fminf(mn[a], v);
-                    if (WITH_MAX) mx[a] = fmaxf(mx[a], v);
-                }
+            for (int a = 0; a < 3; ++a) v[u][a] = __ldg(xyz + (size_t)i * 3 + a);
+        }
+#pragma unroll
+        for (int u = 0; u < kBboxPerThread; ++u) {
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                mn[a] = fminf(mn[a], v[u][a]);
+                if (WITH_MAX) mx[a] = fmaxf(mx[a], v[u][a]);
             }
         }
 #pragma unroll

@@ -11,7 +11,7 @@
 //
 // Steps (all on the caller's stream, integer work only):
 //   1. count[j]   += 1 per entry            (int atomics: the counts are order-independent)
-//   2. rowptr      = exclusive scan(count)  (scan.cu)
+//   2. rowptr      = exclusive scan(count)  (scan.cu, single pass)
 //   3. tmp[cursor++] = p                    (int atomic cursor: order inside a row is arbitrary)
 //   4. rank every entry inside its row by the value of p (all-pairs count inside the row, rows are
 //      ~k long) and write perm[rowptr[j] + rank] = p   → ascending p, deterministic.
@@ -107,5 +107,5 @@ extern "C" int aopt_csr_build(int n_src, int64_t n_entries, const int *idx, int 
         csr_fill_kernel<<<stride_grid(n_entries, kBlock, 8), kBlock, 0, st>>>(n_entries, n_src, negative_mode, idx, count, tmp);
         csr_rank_kernel<<<stride_grid(n_entries, kBlock, 8), kBlock, 0, st>>>(n_src, negative_mode, idx, rowptr, tmp, perm);
     }
-    return check_launch(n_entries > 0 ? 6 : 3);  // count, 3 x scan, fill, rank
+    return check_launch(n_entries > 0 ? 4 : 1);  // count, scan, fill, rank
 }

@@ -342,8 +342,10 @@ extern "C" int aopt_gather_sub_forward(int m, int nsample, int c, const float *k
     bool vec = (c % 4 == 0) && aligned16(key) && aligned16(query) && aligned16(out);
     if (vec) {
         int chunks = c / 4;
-        static const bool use_rows = [] { const char *e = getenv("AOPT_GATHER_SUB_IMPL"); return e && e[0] == 'r'; }();
-        const bool ns_ok = aligned16(idx) && !use_rows;
+        // Measured at L0 (320k x 16 x 48, unsorted S3DIS order): rows kernel 256 us, cp.async NS kernel 327 us
+        // (234 us when the points are Morton-ordered).  Default = rows; AOPT_GATHER_SUB_IMPL=ns opts in.
+        static const bool use_ns = [] { const char *e = getenv("AOPT_GATHER_SUB_IMPL"); return e && e[0] == 'n'; }();
+        const bool ns_ok = aligned16(idx) && use_ns;
         if (ns_ok && nsample == 16) launch_gather_sub_ns<16>(m, chunks, c, key, query, idx, out, as_stream(stream));
         else if (ns_ok && nsample == 8) launch_gather_sub_ns<8>(m, chunks, c, key, query, idx, out, as_stream(stream));
         else if (ns_ok && nsample == 32) launch_gather_sub_ns<32>(m, chunks, c, key, query, idx, out, as_stream(stream));

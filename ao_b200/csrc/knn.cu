@@ -174,7 +174,7 @@ using namespace aopt;
 // AOPT_KNN_GRID_MIN overrides it (tuning runs).
 static int grid_min_points() {
     static int v = [] {
-        int d = 4096;
+        int d = 2048;
         if (const char *e = getenv("AOPT_KNN_GRID_MIN")) {
             int x = atoi(e);
             if (x > 0) d = x;

@@ -36,7 +36,7 @@
 namespace aopt {
 
 constexpr int kSamples = 64;        // sample points per scene for the density estimate
-constexpr int kCellsPerPoint = 8;   // grid capacity: 8 cells per candidate + 64 per scene
+constexpr int kCellsPerPoint = 4;   // grid capacity: 4 cells per candidate + 64 per scene
 constexpr int kCellsPerScene = 64;
 constexpr int kMaxRing = 8;         // beyond this shell radius a query falls back to a full scan
 constexpr int kQueryBlock = 128;
@@ -384,7 +384,7 @@ int knn_grid_launch(int m, int nsample, int n, int b, const float *xyz, const fl
     else if (nsample <= 8) launch_query<8>(self, m, b, nsample, new_xyz, new_offset, w, idx, dist2, st);
     else if (nsample <= 16) launch_query<16>(self, m, b, nsample, new_xyz, new_offset, w, idx, dist2, st);
     else launch_query<32>(self, m, b, nsample, new_xyz, new_offset, w, idx, dist2, st);
-    return check_launch(9);  // sample, bbox, setup, count, 3 x scan, fill, query
+    return check_launch(7);  // sample, bbox, setup, count, scan, fill, query
 }
 
 }  // namespace aopt

@@ -283,7 +283,7 @@ extern "C" int aopt_voxel_partition(int n, int b, const int64_t *sorted_keys, co
     launch_exclusive_scan(flag, scan, n, partial, st);
     voxel_finalize_kernel<<<grid, kPoolBlock, 0, st>>>(n, b, order64, flag, scan, offset, order32, cluster32, cluster64,
                                                        idx_ptr, new_offset, meta);
-    return check_launch(5);
+    return check_launch(3);  // mark, scan, finalize
 }
 
 extern "C" int aopt_pool_forward(int n_vox, int c, const float *feat, const float *coord, const int *order,

@@ -1,12 +1,20 @@
-// scan.cu — three-kernel exclusive scan (tile scan → scan of tile totals → add back).
+// scan.cu — single-pass exclusive scan with decoupled look-back.
+//
+// Every CTA takes the next tile id from an atomic counter (so a tile's predecessors are always running
+// or done), scans its 2048 elements, publishes its aggregate, then walks back over the published states
+// of the preceding tiles until it meets an inclusive prefix.  A state is one 64-bit word
+// (flag << 32 | value) written with a single store, so flag and value are always consistent.
 #include "scan.cuh"
 
 namespace aopt {
 
-// Inclusive scan of one int per thread across a 1024-thread block; returns the inclusive value
-// and leaves the block total in warp_sums[31].
-__device__ __forceinline__ int block_inclusive_scan(int v, int *warp_sums) {
+constexpr unsigned long long kFlagAggregate = 1ull << 32;
+constexpr unsigned long long kFlagInclusive = 2ull << 32;
+
+// Inclusive scan of one int per thread across the block; returns the inclusive value, block total in *total.
+__device__ __forceinline__ int block_inclusive_scan(int v, int *warp_sums, int *total) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int kWarps = kScanBlock / 32;
     int inc = v;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -16,23 +24,28 @@ __device__ __forceinline__ int block_inclusive_scan(int v, int *warp_sums) {
     if (lane == 31) warp_sums[warp] = inc;
     __syncthreads();
     if (warp == 0) {
-        int w = warp_sums[lane];
+        int w = lane < kWarps ? warp_sums[lane] : 0;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             int t = __shfl_up_sync(0xffffffffu, w, d);
             if (lane >= d) w += t;
         }
-        warp_sums[lane] = w;  // inclusive over warps
+        if (lane < kWarps) warp_sums[lane] = w;  // inclusive over warps
     }
     __syncthreads();
+    *total = warp_sums[kWarps - 1];
     return inc + (warp > 0 ? warp_sums[warp - 1] : 0);
 }
 
-// in/out may alias: every thread reads its own 4 elements before writing them.
+// in/out may alias: every thread reads its own elements before any element of the tile is written.
 __global__ void __launch_bounds__(kScanBlock)
-scan_tiles_kernel(int n, const int *in, int *out, int *__restrict__ partial) {
+scan_onepass_kernel(int n, const int *in, int *out, unsigned long long *state, unsigned *counter) {
     __shared__ int warp_sums[kScanBlock / 32];
-    const long long base = (long long)blockIdx.x * kScanTile + threadIdx.x * kScanItems;
+    __shared__ int tile_s, prefix_s;
+    if (threadIdx.x == 0) tile_s = (int)atomicAdd(counter, 1u);
+    __syncthreads();
+    const int tile = tile_s;
+    const long long base = (long long)tile * kScanTile + (long long)threadIdx.x * kScanItems;
     int v[kScanItems];
     int sum = 0;
 #pragma unroll
@@ -40,47 +53,48 @@ scan_tiles_kernel(int n, const int *in, int *out, int *__restrict__ partial) {
         v[i] = (base + i < n) ? in[base + i] : 0;
         sum += v[i];
     }
-    int excl = block_inclusive_scan(sum, warp_sums) - sum;
+    int total;
+    const int inc = block_inclusive_scan(sum, warp_sums, &total);
+    if (threadIdx.x == 0) {
+        volatile unsigned long long *st = state;
+        int prefix = 0;
+        if (tile == 0) {
+            st[0] = kFlagInclusive | (unsigned)total;
+        } else {
+            st[tile] = kFlagAggregate | (unsigned)total;
+            for (int p = tile - 1; p >= 0; --p) {
+                unsigned long long s;
+                do { s = st[p]; } while ((s >> 32) == 0);  // predecessor not published yet
+                prefix += (int)(unsigned)(s & 0xffffffffull);
+                if ((s >> 32) == 2) break;
+            }
+            st[tile] = kFlagInclusive | (unsigned)(prefix + total);
+        }
+        prefix_s = prefix;
+    }
+    __syncthreads();
+    int excl = prefix_s + inc - sum;
 #pragma unroll
     for (int i = 0; i < kScanItems; ++i) {
         if (base + i < n) out[base + i] = excl;
         excl += v[i];
     }
-    if (threadIdx.x == kScanBlock - 1) partial[blockIdx.x] = warp_sums[kScanBlock / 32 - 1];
+    // the tile that holds element n-1 also writes the grand total
+    if (threadIdx.x == kScanBlock - 1 && (long long)(tile + 1) * kScanTile >= n) out[n] = prefix_s + total;
 }
 
-// Single block: exclusive scan of the tile totals in place; partial[n_tiles] = grand total.
-__global__ void __launch_bounds__(kScanBlock)
-scan_partials_kernel(int n_tiles, int *__restrict__ partial) {
-    __shared__ int warp_sums[kScanBlock / 32];
-    __shared__ int carry_s;
-    if (threadIdx.x == 0) carry_s = 0;
-    __syncthreads();
-    for (int base = 0; base < n_tiles; base += kScanBlock) {
-        const int i = base + threadIdx.x;
-        const int v = i < n_tiles ? partial[i] : 0;
-        const int inc = block_inclusive_scan(v, warp_sums);
-        const int carry = carry_s;
-        if (i < n_tiles) partial[i] = carry + inc - v;
-        __syncthreads();  // everyone has read carry_s and warp_sums
-        if (threadIdx.x == kScanBlock - 1) carry_s = carry + inc;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) partial[n_tiles] = carry_s;
-}
-
-__global__ void __launch_bounds__(256)
-scan_add_kernel(int n, int *__restrict__ out, const int *__restrict__ partial, int n_tiles) {
-    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
-    if (i < n) out[i] += partial[i / kScanTile];
-    if (i == n) out[n] = partial[n_tiles];
-}
+__global__ void scan_empty_kernel(int *out) { out[0] = 0; }
 
 void launch_exclusive_scan(const int *in, int *out, int n, int *partial, cudaStream_t st) {
     const int tiles = div_up(n, kScanTile);
-    if (tiles > 0) scan_tiles_kernel<<<tiles, kScanBlock, 0, st>>>(n, in, out, partial);
-    scan_partials_kernel<<<1, kScanBlock, 0, st>>>(tiles, partial);
-    scan_add_kernel<<<div_up((long long)n + 1, 256), 256, 0, st>>>(n, out, partial, tiles);
+    if (tiles == 0) {
+        scan_empty_kernel<<<1, 1, 0, st>>>(out);
+        return;
+    }
+    unsigned long long *state = reinterpret_cast<unsigned long long *>(partial);
+    unsigned *counter = reinterpret_cast<unsigned *>(state + tiles + 1);
+    cudaMemsetAsync(partial, 0, sizeof(int) * scan_partial_ints(n), st);
+    scan_onepass_kernel<<<tiles, kScanBlock, 0, st>>>(n, in, out, state, counter);
 }
 
 }  // namespace aopt

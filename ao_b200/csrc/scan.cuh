@@ -1,18 +1,20 @@
-// scan.cuh — exclusive prefix sum of int32 counts (used by the CSR builder and the kNN grid).
-// out[i] = sum_{j<i} in[j] for i in [0, n], i.e. out has n+1 entries and out[n] is the total.
-// `in` and `out` may be the same buffer.  `partial` needs div_up(n, kScanTile) + 1 ints.
+// scan.cuh — exclusive prefix sum of int32 counts (used by the CSR builder, the kNN grid and the voxel
+// partition).  out[i] = sum_{j<i} in[j] for i in [0, n], i.e. out has n+1 entries and out[n] is the total.
+// `in` and `out` may be the same buffer.  `partial` is scratch of scan_partial_ints(n) ints.
+// Single pass (decoupled look-back): one memset + one kernel instead of three kernels.
 #pragma once
 #include "common.cuh"
 
 namespace aopt {
 
-constexpr int kScanBlock = 1024;
+constexpr int kScanBlock = 512;
 constexpr int kScanItems = 4;  // consecutive elements per thread
 constexpr int kScanTile = kScanBlock * kScanItems;
 
-inline size_t scan_partial_ints(long long n) { return (size_t)div_up(n, kScanTile) + 1; }
+// tile states (one 64-bit word per tile) + the dynamic tile counter
+inline size_t scan_partial_ints(long long n) { return 2 * ((size_t)div_up(n, kScanTile) + 2); }
 
-// Launches 3 kernels on `st`; defined in scan.cu.
+// Enqueues one memset and one kernel on `st`; defined in scan.cu.
 void launch_exclusive_scan(const int *in, int *out, int n, int *partial, cudaStream_t st);
 
 }  // namespace aopt

@@ -164,19 +164,30 @@ HBM_KERNELS = {"aopt_group_xyz", "aopt_gather_sub_forward", "aopt_grouping_forwa
 
 
 def summarise_trace(trace, sizes, k, step_ms_total, peak):
+    """Per entry point: all launches of the traced steps, and separately its LARGEST launch shape (the
+    level-0 launches) — small levels are launch-latency bound and say little about the kernel."""
     per = {}
     for name, args, s, e in trace:
         ms = s.elapsed_time(e)
-        d = per.setdefault(name, dict(ms=0.0, calls=0, bytes=0.0))
+        nb = call_bytes(name, args, sizes, k)
+        d = per.setdefault(name, dict(ms=0.0, calls=0, bytes=0.0, shapes={}))
         d["ms"] += ms
         d["calls"] += 1
-        d["bytes"] += call_bytes(name, args, sizes, k)
+        d["bytes"] += nb
+        sh = d["shapes"].setdefault(nb, [0.0, 0])
+        sh[0] += ms
+        sh[1] += 1
     out = []
     for name, d in sorted(per.items(), key=lambda kv: -kv[1]["ms"]):
         gbs = d["bytes"] / (d["ms"] * 1e-3) / 1e9 if d["ms"] > 0 else 0.0
+        big = max(d["shapes"])
+        big_ms, big_calls = d["shapes"][big]
+        big_gbs = big * big_calls / (big_ms * 1e-3) / 1e9 if big_ms > 0 else 0.0
+        hbm = name in HBM_KERNELS
         out.append(dict(kernel=name, calls=d["calls"], ms=round(d["ms"], 4), share=round(d["ms"] / step_ms_total, 4),
-                        alg_gb=round(d["bytes"] / 1e9, 4), gbs=round(gbs, 1),
-                        frac=round(gbs / peak, 4) if name in HBM_KERNELS else None))
+                        alg_gb=round(d["bytes"] / 1e9, 4), gbs=round(gbs, 1), frac=round(gbs / peak, 4) if hbm else None,
+                        largest=dict(alg_bytes=big, launches=big_calls, us_per_launch=round(big_ms / big_calls * 1e3, 2),
+                                     gbs=round(big_gbs, 1), frac=round(big_gbs / peak, 4) if hbm else None)))
     return out
 
 
@@ -374,6 +385,7 @@ def run_b200_arm(args):
         kr["ms_per_step"] = round(kr.pop("ms") / trace_steps, 4)
         kr["calls_per_step"] = kr.pop("calls") // trace_steps
         kr["alg_gb_per_step"] = round(kr.pop("alg_gb") / trace_steps, 4)
+        kr["largest"]["launches_per_step"] = kr["largest"].pop("launches") // trace_steps
     hbm_rows = [kr for kr in kernels if kr["kernel"] in HBM_KERNELS]
     dom = hbm_rows[0] if hbm_rows else None
     traffic = None
@@ -385,11 +397,18 @@ def run_b200_arm(args):
             traffic = None
     roofline = None
     if dom:
-        per_launch_bytes = dom["alg_gb_per_step"] * 1e9 / max(dom["calls_per_step"], 1)
-        roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["gbs"], "peak": peak, "unit": "GB/s",
-                    "frac": dom["frac"], "traffic": traffic, "peak_source": peak_src,
-                    "alg_bytes_per_launch": per_launch_bytes, "launches_per_step": dom["calls_per_step"],
-                    "share_of_step": dom["share"]}
+        # the dominant HBM-bound kernel at its level-0 launch shape: algorithmic bytes of one launch / its
+        # CUDA-event duration averaged over the traced launches; `traffic` = dram read+write bytes of the
+        # same launch shape from the committed ncu --set full capture (profiles/traffic.json)
+        big = dom["largest"]
+        info = traffic if isinstance(traffic, dict) else {}
+        roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": big["gbs"], "peak": peak, "unit": "GB/s",
+                    "frac": big["frac"], "traffic": info.get("dram_bytes_per_launch"),
+                    "traffic_source": info.get("source"), "peak_source": peak_src,
+                    "alg_bytes_per_launch": big["alg_bytes"], "us_per_launch": big["us_per_launch"],
+                    "launches_per_step": big["launches_per_step"], "launch_shape": "level 0: N=%d, k=%d, C=%d, G=%d" % (
+                        sizes[0], cfg.k, cfg.channels[0], cfg.groups[0]),
+                    "share_of_step_all_launches": dom["share"], "frac_all_launches": dom["frac"]}
     hbm_ms = sum(kr["ms_per_step"] for kr in hbm_rows)
     hbm_gb = sum(kr["alg_gb_per_step"] for kr in hbm_rows)
     knn_row = next((kr for kr in kernels if kr["kernel"] == "aopt_knn_query"), None)

@@ -262,9 +262,12 @@ def run_b200_arm(args):
     from ao_b200 import _lib, scenes
     from ao_b200.schedule import PointOpsSchedule, ScheduleConfig
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    # torchrun exports RANK / LOCAL_RANK / WORLD_SIZE; a plain `python bench.py` is a single process
+    under_torchrun = all(k in os.environ for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"))
+    world = int(os.environ["WORLD_SIZE"]) if under_torchrun else 1
+    rank = int(os.environ["RANK"]) if under_torchrun else 0
+    local = int(os.environ["LOCAL_RANK"]) if under_torchrun else 0
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback "
                          "(use --impl reference for the CPU baseline)")

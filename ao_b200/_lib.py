@@ -49,6 +49,14 @@ SIGNATURES = {
     "aopt_interp_weights": (c_int, [c_int, c_int, P, P, P]),
     "aopt_interpolation_forward": (c_int, [c_int, c_int, c_int, c_int, P, P, P, P, P]),
     "aopt_interpolation_backward": (c_int, [c_int, c_int, c_int, P, P, P, P, P, P]),
+    "aopt_pe_mlp_supported": (c_int, [c_int]),
+    "aopt_pos_moments_workspace_bytes": (c_size_t, []),
+    "aopt_pos_moments": (c_int, [c_int64, P, P, P, c_size_t, P]),
+    "aopt_pe_mlp_state_bytes": (c_size_t, [c_int]),
+    "aopt_pe_mlp_forward": (c_int, [c_int64, c_int, P, P, P, P, P, P, P, P, c_float, c_int, P, P, P, P, c_size_t, P]),
+    "aopt_pe_mlp_stats": (c_int, [c_int, P, P, P]),
+    "aopt_pe_mlp_backward_workspace_bytes": (c_size_t, [c_int64, c_int]),
+    "aopt_pe_mlp_backward": (c_int, [c_int64, c_int, P, P, P, P, c_int, P, P, P, P, P, P, P, P, P, c_size_t, P]),
     "aopt_aggregation_forward": (c_int, [c_int, c_int, c_int, c_int, P, P, P, P, P, P]),
     "aopt_aggregation_backward": (c_int, [c_int, c_int, c_int, c_int, P, P, P, P, P, P, P, P, P, P, P]),
     "aopt_subtraction_forward": (c_int, [c_int, c_int, c_int, P, P, P, P, P]),
@@ -59,7 +67,9 @@ KNN_AUTO, KNN_TILE, KNN_GRID = 0, 1, 2
 _lib = None
 _trace = None  # list of (entry point, args, start event, end event) while bench.py's profiler is on
 _UNTRACED = {"aopt_version", "aopt_status_string", "aopt_last_cuda_error", "aopt_kernel_launches",
-             "aopt_knn_workspace_bytes", "aopt_csr_workspace_bytes", "aopt_voxel_partition_workspace_bytes"}
+             "aopt_knn_workspace_bytes", "aopt_csr_workspace_bytes", "aopt_voxel_partition_workspace_bytes",
+             "aopt_pe_mlp_supported", "aopt_pos_moments_workspace_bytes", "aopt_pe_mlp_state_bytes",
+             "aopt_pe_mlp_backward_workspace_bytes"}
 
 
 class _Entry:

@@ -1,0 +1,557 @@
+// pe_mlp.cu — fused positional-bias MLP of GroupedVectorAttention (the "next" row).
+//
+// Replaces the torch chain of
+// /root/reference/pointcept/models/point_transformer_v2/point_transformer_v2m2_base.py:88-93,116-118
+//     peb = linear_p_bias(pos)  =  Linear(C,C)( ReLU( PointBatchNorm(C)( Linear(3,C)(pos) ) ) )
+// on all N·k neighbour rows — five passes over (N,k,C) tensors forward (Linear out, BN read+write, ReLU,
+// Linear out, dtype copies) and about ten backward — by
+//   forward : read pos (12 B/row), write peb (4C B/row)
+//   backward: read grad_peb (4C B/row) + pos, write only parameter gradients.
+//
+// What makes the fusion possible with TRAINING-mode BatchNorm: the first layer is affine in pos, so its
+// batch statistics follow from the mean and covariance of pos in closed form,
+//     mean_c = W1[c,:]·m + b1[c],   var_c = W1[c,:] · Cov · W1[c,:]ᵀ        (biased, as BN uses)
+// and pos (hence m, Cov) is shared by every block of a BlockSequence.  With a_c = γ_c·rstd_c the hidden
+// activation is  h[r,c] = relu(a_c·(W1[c,:]·pos[r]) + a_c·(b1[c]-mean_c) + β_c): three FMAs per element
+// recomputed on the fly, never stored.  The C×C layer runs on the tensor cores (mma.sync m16n8k16,
+// bf16 operands, fp32 accumulation — the precision of the reference's autocast path); the work is
+// HBM-bound (2·C flops per output byte), so the legacy MMA path keeps up with the memory system.
+//
+// The backward pass needs only row sums (∂L/∂pos is not needed: coordinates are inputs):
+//     dz = (G·W2) ⊙ [z>0],   S1 = Σ dz⊗pos,  S2 = Σ dz,  S3 = Σ dz⊙x̂,   dW2 = Gᵀ·h,  db2 = Σ G
+//     dγ = S3, dβ = S2, dW1 = rstd ⊙ [γ S1 − (γ S2/R)⊗Σpos − (γ S3/R) ⊙ rstd ⊙ (W1·(Σ pos posᵀ − Σpos Σposᵀ/R))]
+//     db1 = 0 (a bias in front of a training-mode BatchNorm has no gradient)
+// One pass over G: per-CTA partial sums (fixed order, no atomics) + a small finalize kernel.
+// Supported widths: C in {48, 96} (levels 0 and 1 of the PTv2m2 configs: 76 % of the (N,k,C) traffic);
+// other widths keep the torch path (ao_b200/ptv2.py).
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace aopt {
+
+constexpr int kPeBlock = 256;       // 8 warps
+constexpr int kPeTile = 128;        // rows per CTA tile (16 per warp)
+constexpr int kMomBlock = 256;
+
+// ---- 1. moments of pos ------------------------------------------------------------------------------
+// out[0..2] = Σp, out[3..8] = Σ xx, xy, xz, yy, yz, zz (double).  Two stages, fixed summation order.
+__global__ void __launch_bounds__(kMomBlock)
+pos_moments_partial_kernel(long long rows, const float *__restrict__ pos, double *__restrict__ partial) {
+    double acc[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) acc[i] = 0.0;
+    const long long step = (long long)gridDim.x * kMomBlock;
+    for (long long r = (long long)blockIdx.x * kMomBlock + threadIdx.x; r < rows; r += step) {
+        const float x = __ldg(pos + r * 3), y = __ldg(pos + r * 3 + 1), z = __ldg(pos + r * 3 + 2);
+        acc[0] += x; acc[1] += y; acc[2] += z;
+        acc[3] += (double)x * x; acc[4] += (double)x * y; acc[5] += (double)x * z;
+        acc[6] += (double)y * y; acc[7] += (double)y * z; acc[8] += (double)z * z;
+    }
+    __shared__ double red[9][kMomBlock / 32];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+        double v = acc[i];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+        if ((threadIdx.x & 31) == 0) red[i][threadIdx.x >> 5] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 9) {
+        double v = 0.0;
+        for (int w = 0; w < kMomBlock / 32; ++w) v += red[threadIdx.x][w];
+        partial[(size_t)blockIdx.x * 9 + threadIdx.x] = v;
+    }
+}
+
+__global__ void pos_moments_final_kernel(int n_partial, const double *__restrict__ partial, double *__restrict__ out) {
+    if (threadIdx.x < 9) {
+        double v = 0.0;
+        for (int i = 0; i < n_partial; ++i) v += partial[(size_t)i * 9 + threadIdx.x];
+        out[threadIdx.x] = v;
+    }
+}
+
+// ---- 2. fold BatchNorm into per-channel affine maps, convert W2 ---------------------------------------
+// fold[c] = { a·W1[c,0..2], a·(b1-mean)+β,  rstd·W1[c,0..2], rstd·(b1-mean) }   (z = fold[0..3]·(p,1), x̂ = fold[4..7]·(p,1))
+// stats[c] = { mean, biased var, rstd }.  use_batch = 1: statistics from the moments; 0: running stats.
+__global__ void __launch_bounds__(128)
+pe_fold_kernel(int c, double rows, const double *__restrict__ mom, const float *__restrict__ w1,
+               const float *__restrict__ b1, const float *__restrict__ gamma, const float *__restrict__ beta,
+               const float *__restrict__ running_mean, const float *__restrict__ running_var, float eps,
+               int use_batch, const float *__restrict__ w2, float *__restrict__ fold, float *__restrict__ stats,
+               __nv_bfloat16 *__restrict__ w2_bf, __nv_bfloat16 *__restrict__ w2t_bf) {
+    const int ch = blockIdx.x;
+    if (threadIdx.x == 0) {
+        const double wx = w1[ch * 3], wy = w1[ch * 3 + 1], wz = w1[ch * 3 + 2];
+        double mean, var;
+        if (use_batch) {
+            const double mx = mom[0] / rows, my = mom[1] / rows, mz = mom[2] / rows;
+            const double cxx = mom[3] / rows - mx * mx, cxy = mom[4] / rows - mx * my, cxz = mom[5] / rows - mx * mz;
+            const double cyy = mom[6] / rows - my * my, cyz = mom[7] / rows - my * mz, czz = mom[8] / rows - mz * mz;
+            mean = wx * mx + wy * my + wz * mz + (double)b1[ch];
+            var = wx * (cxx * wx + cxy * wy + cxz * wz) + wy * (cxy * wx + cyy * wy + cyz * wz) +
+                  wz * (cxz * wx + cyz * wy + czz * wz);
+            if (var < 0.0) var = 0.0;
+        } else {
+            mean = running_mean[ch];
+            var = running_var[ch];
+        }
+        const double rstd = 1.0 / sqrt(var + (double)eps);
+        const double a = (double)gamma[ch] * rstd;
+        const double shift = (double)b1[ch] - mean;
+        float *f = fold + (size_t)ch * 8;
+        f[0] = (float)(a * wx); f[1] = (float)(a * wy); f[2] = (float)(a * wz); f[3] = (float)(a * shift + (double)beta[ch]);
+        f[4] = (float)(rstd * wx); f[5] = (float)(rstd * wy); f[6] = (float)(rstd * wz); f[7] = (float)(rstd * shift);
+        stats[ch] = (float)mean;
+        stats[c + ch] = (float)var;
+        stats[2 * c + ch] = (float)rstd;
+    }
+    for (int i = threadIdx.x; i < c; i += 128) {  // row ch of W2 [co][ci] and column ch of its transpose
+        const __nv_bfloat16 v = __float2bfloat16_rn(w2[(size_t)ch * c + i]);
+        w2_bf[(size_t)ch * c + i] = v;
+        w2t_bf[(size_t)i * c + ch] = v;
+    }
+}
+
+// ---- tensor-core helpers -------------------------------------------------------------------------------
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__device__ __forceinline__ uint32_t ld_u32(const __nv_bfloat16 *p) { return *reinterpret_cast<const uint32_t *>(p); }
+
+// A fragment (16 rows x 16 k) of a row-major [row][k] bf16 tile with leading dimension ld.
+__device__ __forceinline__ void load_a(uint32_t (&a)[4], const __nv_bfloat16 *tile, int ld, int row0, int k0, int lane) {
+    const int g = lane >> 2, t = lane & 3;
+    const __nv_bfloat16 *p = tile + (size_t)(row0 + g) * ld + k0 + t * 2;
+    a[0] = ld_u32(p);
+    a[1] = ld_u32(p + 8 * ld);
+    a[2] = ld_u32(p + 8);
+    a[3] = ld_u32(p + 8 * ld + 8);
+}
+// B fragment (16 k x 8 n) of a tile stored as [n][k] (k contiguous) with leading dimension ld.
+__device__ __forceinline__ void load_b(uint32_t (&b)[2], const __nv_bfloat16 *tile, int ld, int n0, int k0, int lane) {
+    const int g = lane >> 2, t = lane & 3;
+    const __nv_bfloat16 *p = tile + (size_t)(n0 + g) * ld + k0 + t * 2;
+    b[0] = ld_u32(p);
+    b[1] = ld_u32(p + 8);
+}
+
+// ---- 3. forward ------------------------------------------------------------------------------------------
+template <int C>
+__global__ void __launch_bounds__(kPeBlock)
+pe_mlp_forward_kernel(long long rows, const float *__restrict__ pos, const float *__restrict__ fold,
+                      const __nv_bfloat16 *__restrict__ w2_bf, const float *__restrict__ b2,
+                      float *__restrict__ out) {
+    constexpr int LDH = C + 8;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __nv_bfloat16 *w2s = reinterpret_cast<__nv_bfloat16 *>(smem_raw);             // [C][LDH]   (n = co, k = ci)
+    __nv_bfloat16 *hs = w2s + C * LDH;                                              // [128][LDH] (row, k = ci)
+    float4 *fz = reinterpret_cast<float4 *>(hs + kPeTile * LDH);                    // [C] z-map
+    float *b2s = reinterpret_cast<float *>(fz + C);                                 // [C]
+    for (int i = threadIdx.x; i < C * C; i += kPeBlock) w2s[(i / C) * LDH + (i % C)] = w2_bf[i];
+    for (int i = threadIdx.x; i < C; i += kPeBlock) {
+        fz[i] = make_float4(fold[i * 8], fold[i * 8 + 1], fold[i * 8 + 2], fold[i * 8 + 3]);
+        b2s[i] = b2[i];
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const long long n_tiles = (rows + kPeTile - 1) / kPeTile;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const long long row_base = tile * kPeTile;
+        {   // hidden activations of the tile: thread → (row = tid/2, half of the channels)
+            const int r = threadIdx.x >> 1, half = threadIdx.x & 1;
+            const long long gr = row_base + r;
+            float px = 0.f, py = 0.f, pz = 0.f;
+            if (gr < rows) { px = __ldg(pos + gr * 3); py = __ldg(pos + gr * 3 + 1); pz = __ldg(pos + gr * 3 + 2); }
+            __nv_bfloat16 *hrow = hs + r * LDH + half * (C / 2);
+#pragma unroll 4
+            for (int cc = 0; cc < C / 2; cc += 2) {
+                const float4 f0 = fz[half * (C / 2) + cc], f1 = fz[half * (C / 2) + cc + 1];
+                const float z0 = fmaf(f0.x, px, fmaf(f0.y, py, fmaf(f0.z, pz, f0.w)));
+                const float z1 = fmaf(f1.x, px, fmaf(f1.y, py, fmaf(f1.z, pz, f1.w)));
+                *reinterpret_cast<__nv_bfloat162 *>(hrow + cc) = __floats2bfloat162_rn(fmaxf(z0, 0.f), fmaxf(z1, 0.f));
+            }
+        }
+        __syncthreads();
+        float acc[C / 8][4];
+#pragma unroll
+        for (int nt = 0; nt < C / 8; ++nt) { acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f; }
+#pragma unroll
+        for (int kt = 0; kt < C / 16; ++kt) {
+            uint32_t a[4];
+            load_a(a, hs, LDH, warp * 16, kt * 16, lane);
+#pragma unroll
+            for (int nt = 0; nt < C / 8; ++nt) {
+                uint32_t b[2];
+                load_b(b, w2s, LDH, nt * 8, kt * 16, lane);
+                mma_bf16_16816(acc[nt], a, b);
+            }
+        }
+        const long long r0 = row_base + warp * 16 + g, r1 = r0 + 8;
+#pragma unroll
+        for (int nt = 0; nt < C / 8; ++nt) {
+            const int col = nt * 8 + t * 2;
+            const float bb0 = b2s[col], bb1 = b2s[col + 1];
+            if (r0 < rows) *reinterpret_cast<float2 *>(out + r0 * C + col) = make_float2(acc[nt][0] + bb0, acc[nt][1] + bb1);
+            if (r1 < rows) *reinterpret_cast<float2 *>(out + r1 * C + col) = make_float2(acc[nt][2] + bb0, acc[nt][3] + bb1);
+        }
+        __syncthreads();  // hs is rewritten by the next tile
+    }
+}
+
+// ---- 4. backward -----------------------------------------------------------------------------------------
+// Per-CTA partial layout (floats): dW2 [C*C] | db2 [C] | S2 [C] | S3 [C] | S1 [3C]
+template <int C>
+struct PeBwdLayout {
+    static constexpr int LDG = C + 8;            // Gs  [128][LDG]  row-major (row, co)
+    static constexpr int LDT = kPeTile + 8;      // GsT [C][LDT], HsT [C][LDT]  (channel, row)
+    static constexpr int LDW = C + 8;            // W2Ts [C][LDW]  (n = ci, k = co)
+    static constexpr int LDZ = C + 1;            // DZs [128][LDZ] fp32
+    static constexpr size_t bytes = (size_t)2 * (kPeTile * LDG + 2 * C * LDT + C * LDW) + 4 * (size_t)kPeTile * LDZ +
+                                    16 * (size_t)kPeTile + 32 * (size_t)C;
+    static constexpr int partial_floats = C * C + 6 * C;
+};
+
+template <int C>
+__global__ void __launch_bounds__(kPeBlock)
+pe_mlp_backward_kernel(long long rows, const float *__restrict__ pos, const float *__restrict__ fold,
+                       const __nv_bfloat16 *__restrict__ w2t_bf, const float *__restrict__ grad,
+                       float *__restrict__ partial) {
+    using L = PeBwdLayout<C>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __nv_bfloat16 *gs = reinterpret_cast<__nv_bfloat16 *>(smem_raw);
+    __nv_bfloat16 *gst = gs + kPeTile * L::LDG;
+    __nv_bfloat16 *hst = gst + C * L::LDT;
+    __nv_bfloat16 *w2ts = hst + C * L::LDT;
+    float *dzs = reinterpret_cast<float *>(w2ts + C * L::LDW);
+    float4 *ps = reinterpret_cast<float4 *>(dzs + kPeTile * L::LDZ);               // [128] (x, y, z, valid)
+    float4 *fz = ps + kPeTile;                                                       // [C] z-map
+    float4 *fx = fz + C;                                                             // [C] x̂-map
+    for (int i = threadIdx.x; i < C * C; i += kPeBlock) w2ts[(i / C) * L::LDW + (i % C)] = w2t_bf[i];
+    for (int i = threadIdx.x; i < C; i += kPeBlock) {
+        fz[i] = make_float4(fold[i * 8], fold[i * 8 + 1], fold[i * 8 + 2], fold[i * 8 + 3]);
+        fx[i] = make_float4(fold[i * 8 + 4], fold[i * 8 + 5], fold[i * 8 + 6], fold[i * 8 + 7]);
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    // dW2 tiles (16 co x 8 ci) owned by this warp: tile id = warp + 8*i
+    constexpr int MT = C / 16, NT = C / 8, TILES = MT * NT, OWN = (TILES + 7) / 8;
+    float wacc[OWN][4];
+#pragma unroll
+    for (int i = 0; i < OWN; ++i) { wacc[i][0] = wacc[i][1] = wacc[i][2] = wacc[i][3] = 0.f; }
+    // column sums: thread → (channel = tid % C, row group = tid / C), groups = 256 / C
+    constexpr int NG = kPeBlock / C;
+    const int col_c = threadIdx.x % C, col_g = threadIdx.x / C;
+    const bool col_active = col_g < NG;
+    float s_db2 = 0.f, s2 = 0.f, s3 = 0.f, s1x = 0.f, s1y = 0.f, s1z = 0.f;
+    __syncthreads();
+    const long long n_tiles = (rows + kPeTile - 1) / kPeTile;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const long long row_base = tile * kPeTile;
+        // a. positions and the gradient tile (fp32 → bf16, both orientations)
+        if (threadIdx.x < kPeTile) {
+            const long long gr = row_base + threadIdx.x;
+            float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (gr < rows) p = make_float4(__ldg(pos + gr * 3), __ldg(pos + gr * 3 + 1), __ldg(pos + gr * 3 + 2), 1.f);
+            ps[threadIdx.x] = p;
+        }
+        for (int i = threadIdx.x; i < kPeTile * (C / 4); i += kPeBlock) {
+            const int r = i / (C / 4), c4 = (i % (C / 4)) * 4;
+            const long long gr = row_base + r;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (gr < rows) v = ldg_stream4(grad + gr * C + c4);
+            const __nv_bfloat16 b0 = __float2bfloat16_rn(v.x), b1 = __float2bfloat16_rn(v.y),
+                                b2 = __float2bfloat16_rn(v.z), b3 = __float2bfloat16_rn(v.w);
+            __nv_bfloat16 *d = gs + r * L::LDG + c4;
+            d[0] = b0; d[1] = b1; d[2] = b2; d[3] = b3;
+            gst[(c4 + 0) * L::LDT + r] = b0; gst[(c4 + 1) * L::LDT + r] = b1;
+            gst[(c4 + 2) * L::LDT + r] = b2; gst[(c4 + 3) * L::LDT + r] = b3;
+        }
+        __syncthreads();
+        // b. hidden activations, transposed: thread → (row = tid % 128, channel parity)
+        {
+            const int r = threadIdx.x & (kPeTile - 1), half = threadIdx.x >> 7;
+            const float4 p = ps[r];
+            for (int cc = half; cc < C; cc += 2) {
+                const float4 f = fz[cc];
+                const float z = fmaf(f.x, p.x, fmaf(f.y, p.y, fmaf(f.z, p.z, f.w)));
+                hst[cc * L::LDT + r] = __float2bfloat16_rn(p.w > 0.f ? fmaxf(z, 0.f) : 0.f);
+            }
+        }
+        __syncthreads();
+        // c. dh = G · W2 (rows x ci), masked by h > 0 → dzs
+        {
+            float acc[C / 8][4];
+#pragma unroll
+            for (int nt = 0; nt < C / 8; ++nt) { acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f; }
+#pragma unroll
+            for (int kt = 0; kt < C / 16; ++kt) {
+                uint32_t a[4];
+                load_a(a, gs, L::LDG, warp * 16, kt * 16, lane);
+#pragma unroll
+                for (int nt = 0; nt < C / 8; ++nt) {
+                    uint32_t b[2];
+                    load_b(b, w2ts, L::LDW, nt * 8, kt * 16, lane);
+                    mma_bf16_16816(acc[nt], a, b);
+                }
+            }
+            const int r0 = warp * 16 + g, r1 = r0 + 8;
+#pragma unroll
+            for (int nt = 0; nt < C / 8; ++nt) {
+                const int col = nt * 8 + t * 2;
+                const float zero = 0.f;
+                dzs[r0 * L::LDZ + col] = __bfloat162float(hst[col * L::LDT + r0]) > 0.f ? acc[nt][0] : zero;
+                dzs[r0 * L::LDZ + col + 1] = __bfloat162float(hst[(col + 1) * L::LDT + r0]) > 0.f ? acc[nt][1] : zero;
+                dzs[r1 * L::LDZ + col] = __bfloat162float(hst[col * L::LDT + r1]) > 0.f ? acc[nt][2] : zero;
+                dzs[r1 * L::LDZ + col + 1] = __bfloat162float(hst[(col + 1) * L::LDT + r1]) > 0.f ? acc[nt][3] : zero;
+            }
+        }
+        // d. dW2[co][ci] += Σ_r G[r][co] · h[r][ci]   (A = GsT [m=co][k=r], B = HsT [n=ci][k=r])
+#pragma unroll
+        for (int i = 0; i < OWN; ++i) {
+            const int tid_tile = warp + 8 * i;
+            if (tid_tile < TILES) {
+                const int mt = tid_tile / NT, nt = tid_tile % NT;
+#pragma unroll
+                for (int kt = 0; kt < kPeTile / 16; ++kt) {
+                    uint32_t a[4], b[2];
+                    load_a(a, gst, L::LDT, mt * 16, kt * 16, lane);
+                    load_b(b, hst, L::LDT, nt * 8, kt * 16, lane);
+                    mma_bf16_16816(wacc[i], a, b);
+                }
+            }
+        }
+        __syncthreads();
+        // e. column sums over the rows of the tile
+        if (col_active) {
+            const float4 f = fx[col_c];
+            for (int r = col_g; r < kPeTile; r += NG) {
+                const float4 p = ps[r];
+                const float dz = dzs[r * L::LDZ + col_c];
+                const float xh = fmaf(f.x, p.x, fmaf(f.y, p.y, fmaf(f.z, p.z, f.w)));
+                s2 += dz;
+                s3 = fmaf(dz, xh, s3);
+                s1x = fmaf(dz, p.x, s1x); s1y = fmaf(dz, p.y, s1y); s1z = fmaf(dz, p.z, s1z);
+                s_db2 += __bfloat162float(gs[r * L::LDG + col_c]);
+            }
+        }
+        __syncthreads();  // tile buffers are rewritten by the next iteration
+    }
+    // f. per-CTA partials
+    float *out = partial + (size_t)blockIdx.x * L::partial_floats;
+#pragma unroll
+    for (int i = 0; i < OWN; ++i) {
+        const int tid_tile = warp + 8 * i;
+        if (tid_tile < TILES) {
+            const int mt = tid_tile / NT, nt = tid_tile % NT;
+            const int co = mt * 16 + g, ci = nt * 8 + t * 2;
+            out[(size_t)co * C + ci] = wacc[i][0];
+            out[(size_t)co * C + ci + 1] = wacc[i][1];
+            out[(size_t)(co + 8) * C + ci] = wacc[i][2];
+            out[(size_t)(co + 8) * C + ci + 1] = wacc[i][3];
+        }
+    }
+    // combine the row groups of every channel through shared memory (fixed order)
+    float *red = dzs;  // reuse: [NG][6][C]
+    if (col_active) {
+        float *rp = red + (size_t)col_g * 6 * C;
+        rp[0 * C + col_c] = s_db2; rp[1 * C + col_c] = s2; rp[2 * C + col_c] = s3;
+        rp[3 * C + col_c] = s1x; rp[4 * C + col_c] = s1y; rp[5 * C + col_c] = s1z;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 6 * C; i += kPeBlock) {
+        float v = 0.f;
+        for (int gg = 0; gg < NG; ++gg) v += red[(size_t)gg * 6 * C + i];
+        const int which = i / C, ch = i % C;
+        // layout after dW2: db2 [C] | S2 [C] | S3 [C] | S1 [C][3]
+        if (which < 3) out[(size_t)C * C + which * C + ch] = v;
+        else out[(size_t)C * C + 3 * C + ch * 3 + (which - 3)] = v;
+    }
+}
+
+// Sums the per-CTA partials in CTA order: dW2 directly, the channel sums (db2 | S2 | S3 | S1) into `sums`.
+__global__ void __launch_bounds__(256)
+pe_mlp_backward_finalize_kernel(int c, int n_partial, int partial_floats, const float *__restrict__ partial,
+                                float *__restrict__ grad_w2, float *__restrict__ sums) {
+    const int total = c * c + 6 * c;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < total; i += gridDim.x * 256) {
+        float v = 0.f;
+        for (int p = 0; p < n_partial; ++p) v += partial[(size_t)p * partial_floats + i];
+        if (i < c * c) grad_w2[i] = v;
+        else sums[i - c * c] = v;
+    }
+}
+
+// BatchNorm / Linear1 backward algebra on the channel sums (see the file header).
+__global__ void __launch_bounds__(128)
+pe_mlp_backward_params_kernel(int c, double rows, int use_batch, const float *__restrict__ sums,
+                              const double *__restrict__ mom, const float *__restrict__ w1,
+                              const float *__restrict__ gamma, const float *__restrict__ stats,
+                              float *__restrict__ grad_w1, float *__restrict__ grad_b1,
+                              float *__restrict__ grad_gamma, float *__restrict__ grad_beta,
+                              float *__restrict__ grad_b2) {
+    const int ch = blockIdx.x * 128 + threadIdx.x;
+    if (ch >= c) return;
+    const double db2 = sums[ch], s2 = sums[c + ch], s3 = sums[2 * c + ch];
+    const double s1[3] = {sums[3 * c + ch * 3], sums[3 * c + ch * 3 + 1], sums[3 * c + ch * 3 + 2]};
+    const double gam = gamma[ch], rstd = stats[2 * c + ch];
+    grad_b2[ch] = (float)db2;
+    grad_gamma[ch] = (float)s3;
+    grad_beta[ch] = (float)s2;
+    if (use_batch) {
+        const double wx = w1[ch * 3], wy = w1[ch * 3 + 1], wz = w1[ch * 3 + 2];
+        const double sp[3] = {mom[0], mom[1], mom[2]};
+        // R·Cov = Σ p pᵀ − Σp Σpᵀ / R
+        const double cxx = mom[3] - sp[0] * sp[0] / rows, cxy = mom[4] - sp[0] * sp[1] / rows, cxz = mom[5] - sp[0] * sp[2] / rows;
+        const double cyy = mom[6] - sp[1] * sp[1] / rows, cyz = mom[7] - sp[1] * sp[2] / rows, czz = mom[8] - sp[2] * sp[2] / rows;
+        const double xp[3] = {rstd * (wx * cxx + wy * cxy + wz * cxz), rstd * (wx * cxy + wy * cyy + wz * cyz),
+                              rstd * (wx * cxz + wy * cyz + wz * czz)};  // Σ_r x̂ ⊗ p
+        for (int d = 0; d < 3; ++d)
+            grad_w1[ch * 3 + d] = (float)(rstd * (gam * s1[d] - (gam * s2 / rows) * sp[d] - (gam * s3 / rows) * xp[d]));
+        grad_b1[ch] = 0.f;
+    } else {
+        for (int d = 0; d < 3; ++d) grad_w1[ch * 3 + d] = (float)(rstd * gam * s1[d]);
+        grad_b1[ch] = (float)(rstd * gam * s2);
+    }
+}
+
+static int pe_grid(long long rows) {
+    long long tiles = (rows + kPeTile - 1) / kPeTile;
+    long long cap = kNumSM;  // one persistent CTA per SM (shared-memory bound)
+    return (int)(tiles < cap ? (tiles < 1 ? 1 : tiles) : cap);
+}
+
+template <int C>
+static size_t pe_fwd_smem() { return (size_t)2 * (C * (C + 8) + kPeTile * (C + 8)) + 16 * (size_t)C + 4 * (size_t)C; }
+
+}  // namespace aopt
+
+using namespace aopt;
+
+static size_t a256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+extern "C" int aopt_pe_mlp_supported(int c) { return (c == 48 || c == 96) ? 1 : 0; }
+
+/* moments: 9 doubles (Σp, Σ xx xy xz yy yz zz). */
+extern "C" size_t aopt_pos_moments_workspace_bytes(void) { return a256((size_t)kNumSM * 4 * 9 * sizeof(double)); }
+
+extern "C" int aopt_pos_moments(int64_t rows, const float *pos, double *moments, void *workspace,
+                                size_t workspace_bytes, aopt_stream_t stream) {
+    if (rows < 0 || !moments) return AOPT_ERR_INVALID_ARGUMENT;
+    if (rows > 0 && !pos) return AOPT_ERR_INVALID_ARGUMENT;
+    if (!workspace || workspace_bytes < aopt_pos_moments_workspace_bytes()) return AOPT_ERR_WORKSPACE;
+    cudaStream_t st = as_stream(stream);
+    const int grid = stride_grid(rows > 0 ? rows : 1, kMomBlock, 4);
+    double *partial = static_cast<double *>(workspace);
+    pos_moments_partial_kernel<<<grid, kMomBlock, 0, st>>>(rows, pos, partial);
+    pos_moments_final_kernel<<<1, 32, 0, st>>>(grid, partial, moments);
+    return check_launch(2);
+}
+
+/* Scratch that lives from forward to backward of one call (caller-allocated):
+ * fold (8C floats) | stats (3C floats) | W2 bf16 (C*C) | W2ᵀ bf16 (C*C). */
+extern "C" size_t aopt_pe_mlp_state_bytes(int c) {
+    return a256(4 * (size_t)8 * c) + a256(4 * (size_t)3 * c) + 2 * a256(2 * (size_t)c * c);
+}
+
+namespace {
+struct PeState {
+    float *fold, *stats;
+    __nv_bfloat16 *w2, *w2t;
+};
+PeState carve_state(void *state, int c) {
+    char *p = static_cast<char *>(state);
+    PeState s;
+    s.fold = reinterpret_cast<float *>(p); p += a256(4 * (size_t)8 * c);
+    s.stats = reinterpret_cast<float *>(p); p += a256(4 * (size_t)3 * c);
+    s.w2 = reinterpret_cast<__nv_bfloat16 *>(p); p += a256(2 * (size_t)c * c);
+    s.w2t = reinterpret_cast<__nv_bfloat16 *>(p);
+    return s;
+}
+template <int C>
+void launch_fwd(long long rows, const float *pos, const PeState &s, const float *b2, float *out, cudaStream_t st) {
+    const size_t smem = pe_fwd_smem<C>();
+    static bool once = (cudaFuncSetAttribute(pe_mlp_forward_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), true);
+    (void)once;
+    pe_mlp_forward_kernel<C><<<pe_grid(rows), kPeBlock, smem, st>>>(rows, pos, s.fold, s.w2, b2, out);
+}
+template <int C>
+void launch_bwd(long long rows, const float *pos, const PeState &s, const float *grad, float *partial, int grid,
+                cudaStream_t st) {
+    const size_t smem = PeBwdLayout<C>::bytes;
+    static bool once = (cudaFuncSetAttribute(pe_mlp_backward_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), true);
+    (void)once;
+    pe_mlp_backward_kernel<C><<<grid, kPeBlock, smem, st>>>(rows, pos, s.fold, s.w2t, grad, partial);
+}
+}  // namespace
+
+/* peb (rows,c) = W2·relu(BN(W1·pos + b1)) + b2.  use_batch_stats = 1 (training): BatchNorm statistics from
+ * `moments` (aopt_pos_moments of the same pos); 0: running_mean / running_var.  stats_out (3c floats) receives
+ * the batch mean, biased variance and rstd of the first layer (for the running-statistics update). */
+extern "C" int aopt_pe_mlp_forward(int64_t rows, int c, const float *pos, const double *moments, const float *w1,
+                                   const float *b1, const float *gamma, const float *beta,
+                                   const float *running_mean, const float *running_var, float eps,
+                                   int use_batch_stats, const float *w2, const float *b2, float *out, void *state,
+                                   size_t state_bytes, aopt_stream_t stream) {
+    if (rows < 0 || !aopt_pe_mlp_supported(c)) return rows < 0 ? AOPT_ERR_INVALID_ARGUMENT : AOPT_ERR_UNSUPPORTED;
+    if (!w1 || !b1 || !gamma || !beta || !w2 || !b2 || !state) return AOPT_ERR_INVALID_ARGUMENT;
+    if (use_batch_stats ? !moments : (!running_mean || !running_var)) return AOPT_ERR_INVALID_ARGUMENT;
+    if (state_bytes < aopt_pe_mlp_state_bytes(c)) return AOPT_ERR_WORKSPACE;
+    if (rows > 0 && (!pos || !out)) return AOPT_ERR_INVALID_ARGUMENT;
+    cudaStream_t st = as_stream(stream);
+    PeState s = carve_state(state, c);
+    pe_fold_kernel<<<c, 128, 0, st>>>(c, (double)rows, moments, w1, b1, gamma, beta, running_mean, running_var, eps,
+                                      use_batch_stats, w2, s.fold, s.stats, s.w2, s.w2t);
+    if (rows > 0) {
+        if (c == 48) launch_fwd<48>(rows, pos, s, b2, out, st);
+        else launch_fwd<96>(rows, pos, s, b2, out, st);
+    }
+    return check_launch(rows > 0 ? 2 : 1);
+}
+
+extern "C" size_t aopt_pe_mlp_backward_workspace_bytes(int64_t rows, int c) {
+    if (!aopt_pe_mlp_supported(c) || rows < 0) return 0;
+    const size_t pf = (size_t)c * c + 6 * (size_t)c;
+    return a256(4 * pf * (size_t)pe_grid(rows)) + a256(4 * 6 * (size_t)c);
+}
+
+/* Parameter gradients of aopt_pe_mlp_forward given grad (rows,c) = dL/dpeb; `state` is the forward's. */
+extern "C" int aopt_pe_mlp_backward(int64_t rows, int c, const float *pos, const double *moments, const float *w1,
+                                    const float *gamma, int use_batch_stats, const float *grad, const void *state,
+                                    float *grad_w1, float *grad_b1, float *grad_gamma, float *grad_beta,
+                                    float *grad_w2, float *grad_b2, void *workspace, size_t workspace_bytes,
+                                    aopt_stream_t stream) {
+    if (rows < 1) return AOPT_ERR_INVALID_ARGUMENT;
+    if (!aopt_pe_mlp_supported(c)) return AOPT_ERR_UNSUPPORTED;
+    if (!pos || !w1 || !gamma || !grad || !state || !grad_w1 || !grad_b1 || !grad_gamma || !grad_beta || !grad_w2 || !grad_b2)
+        return AOPT_ERR_INVALID_ARGUMENT;
+    if (use_batch_stats && !moments) return AOPT_ERR_INVALID_ARGUMENT;
+    if (!workspace || workspace_bytes < aopt_pe_mlp_backward_workspace_bytes(rows, c)) return AOPT_ERR_WORKSPACE;
+    cudaStream_t st = as_stream(stream);
+    PeState s = carve_state(const_cast<void *>(state), c);
+    const int grid = pe_grid(rows);
+    const int pf = c * c + 6 * c;
+    float *partial = static_cast<float *>(workspace);
+    float *sums = reinterpret_cast<float *>(static_cast<char *>(workspace) + a256(4 * (size_t)pf * grid));
+    if (c == 48) launch_bwd<48>(rows, pos, s, grad, partial, grid, st);
+    else launch_bwd<96>(rows, pos, s, grad, partial, grid, st);
+    pe_mlp_backward_finalize_kernel<<<div_up(pf, 256), 256, 0, st>>>(c, grid, pf, partial, grad_w2, sums);
+    pe_mlp_backward_params_kernel<<<div_up(c, 128), 128, 0, st>>>(c, (double)rows, use_batch_stats, sums, moments, w1,
+                                                                  gamma, s.stats, grad_w1, grad_b1, grad_gamma,
+                                                                  grad_beta, grad_b2);
+    return check_launch(3);
+}
+
+/* stats (3c floats: mean | biased var | rstd) of the forward that filled `state`. */
+extern "C" int aopt_pe_mlp_stats(int c, const void *state, float *stats_out, aopt_stream_t stream) {
+    if (!aopt_pe_mlp_supported(c)) return AOPT_ERR_UNSUPPORTED;
+    if (!state || !stats_out) return AOPT_ERR_INVALID_ARGUMENT;
+    PeState s = carve_state(const_cast<void *>(state), c);
+    cudaMemcpyAsync(stats_out, s.stats, 4 * (size_t)3 * c, cudaMemcpyDeviceToDevice, as_stream(stream));
+    return check_launch(0);
+}

@@ -5,7 +5,8 @@ the PTv2m2 hot path, backed by hand-written sm_100a kernels behind a C ABI (incl
 Names outside the hot path (ball_query, random_ball_query, farthest_point_sampling,
 attention_*_step, ball_query_and_group) exist but raise NotImplementedError.
 New fused operators for the PTv2 caller: group_xyz, gva_relation, gva_aggregate, grid_pool,
-voxel_partition, unpool_map, interpolation_weights, knn_query_raw.
+voxel_partition, unpool_map, interpolation_weights, knn_query_raw, pe_bias_mlp (fused positional-bias MLP),
+pos_moments.
 """
 from .query import knn_query, knn_query_raw, ball_query, random_ball_query
 from .sampling import farthest_point_sampling
@@ -28,4 +29,5 @@ from .utils import (
     batch2offset,
     offset2batch,
 )
+from .pe_mlp import pe_bias_mlp, pe_mlp_supported, pos_moments
 from ._csr import get_csr, build_csr

@@ -31,6 +31,20 @@ import torch.nn as nn
 from . import pointops
 
 
+def fused_pe_enabled() -> bool:
+    """The fused positional-bias MLP (pointops.pe_bias_mlp) computes its C x C layer in bf16 on the tensor
+    cores; it replaces the torch layers only under autocast (where they run in bf16 too), so fp32 runs keep
+    fp32 parity with the reference modules.  AOPT_FUSED_PE=0 disables it, =1 forces it."""
+    import os
+
+    flag = os.environ.get("AOPT_FUSED_PE", "auto")
+    if flag == "0":
+        return False
+    if flag == "1":
+        return True
+    return torch.is_autocast_enabled()
+
+
 class DropPath(nn.Module):
     """Stochastic depth per row (timm.models.layers.DropPath semantics for a (N,C) input)."""
 
@@ -90,7 +104,7 @@ class GroupedVectorAttention(nn.Module):
         self.softmax = nn.Softmax(dim=1)
         self.attn_drop = nn.Dropout(attn_drop_rate)
 
-    def forward(self, feat, coord, reference_index, pos=None):
+    def forward(self, feat, coord, reference_index, pos=None, pos_moments=None):
         query, key, value = self.linear_q(feat), self.linear_k(feat), self.linear_v(feat)
         if pos is None:                                                       # (N,k,3): depends only on (idx, coord)
             pos = pointops.group_xyz(reference_index, coord)                  # :109,:111
@@ -99,7 +113,11 @@ class GroupedVectorAttention(nn.Module):
         if self.pe_multiplier:
             relation_qk = relation_qk * self.linear_p_multiplier(pos)
         if self.pe_bias:
-            peb = self.linear_p_bias(pos).float()
+            if fused_pe_enabled() and pointops.pe_mlp_supported(self.embed_channels):
+                # bf16 tensor-core fused MLP: used where the torch path would run in bf16 anyway (autocast)
+                peb = pointops.pe_bias_mlp(pos, self.linear_p_bias, pos_moments)
+            else:
+                peb = self.linear_p_bias(pos).float()
             relation_qk = relation_qk + peb
         weight = self.weight_encoding(relation_qk)                            # (N,k,G) logits
         if self.attn_drop_rate > 0.0 and self.training:
@@ -132,16 +150,16 @@ class Block(nn.Module):
         self.enable_checkpoint = enable_checkpoint
         self.drop_path = DropPath(drop_path_rate) if drop_path_rate > 0.0 else nn.Identity()
 
-    def forward(self, points, reference_index, pos=None):
+    def forward(self, points, reference_index, pos=None, pos_moments=None):
         coord, feat, offset = points
         identity = feat
         feat = self.act(self.norm1(self.fc1(feat)))
         if self.enable_checkpoint:
             from torch.utils.checkpoint import checkpoint
 
-            feat = checkpoint(self.attn, feat, coord, reference_index, pos, use_reentrant=False)
+            feat = checkpoint(self.attn, feat, coord, reference_index, pos, pos_moments, use_reentrant=False)
         else:
-            feat = self.attn(feat, coord, reference_index, pos)
+            feat = self.attn(feat, coord, reference_index, pos, pos_moments)
         feat = self.act(self.norm2(feat))
         feat = self.norm3(self.fc3(feat))
         feat = identity + self.drop_path(feat)
@@ -166,7 +184,7 @@ class BlockSequence(nn.Module):
             self.blocks.append(Block(embed_channels=embed_channels, groups=groups, qkv_bias=qkv_bias,
                                      pe_multiplier=pe_multiplier, pe_bias=pe_bias, attn_drop_rate=attn_drop_rate,
                                      drop_path_rate=drop_path_rates[i], enable_checkpoint=enable_checkpoint))
-        self.knn_cache = None  # set by PointTransformerV2: {(coord ptr, n, offset ptr, k): (idx, pos)}
+        self.knn_cache = None  # set by PointTransformerV2: {(coord ptr, n, offset ptr, k): (idx, pos, pos moments)}
 
     def forward(self, points):
         coord, feat, offset = points
@@ -176,12 +194,14 @@ class BlockSequence(nn.Module):
             reference_index, _ = pointops.knn_query(self.neighbours, coord, offset)     # :223
             # relative coordinates of the neighbours (:109,:111) are the same for every block of the sequence
             pos = pointops.group_xyz(reference_index, coord)
-            hit = (reference_index, pos)
+            # Σp, Σppᵀ of pos: the closed-form BatchNorm statistics of every block's fused positional MLP
+            mom = pointops.pos_moments(pos) if (fused_pe_enabled() and self.training) else None
+            hit = (reference_index, pos, mom)
             if self.knn_cache is not None:
                 self.knn_cache[key] = hit
-        reference_index, pos = hit
+        reference_index, pos, mom = hit
         for block in self.blocks:
-            points = block(points, reference_index, pos)
+            points = block(points, reference_index, pos, mom)
         return points
 
 

@@ -160,6 +160,34 @@ int aopt_interpolation_backward(int m, int c, int k, const float *grad_output, c
                                 const int *rowptr, const int *perm, float *grad_input,
                                 aopt_stream_t stream);
 
+/* ---- fused positional-bias MLP ("next" row) ------------------------------------------ */
+/* peb = Linear(C,C)(ReLU(BatchNorm(Linear(3,C)(pos)))) on all rows = N*nsample neighbour rows, the
+ * `linear_p_bias` branch of GroupedVectorAttention (…v2m2_base.py:88-93,116-118), without materialising
+ * the hidden (rows,C) tensors: training-mode BatchNorm statistics follow in closed form from the mean and
+ * covariance of pos (aopt_pos_moments).  Widths: aopt_pe_mlp_supported(c) (48 and 96); bf16 tensor-core
+ * products with fp32 accumulation. */
+int aopt_pe_mlp_supported(int c);
+/* moments: 9 doubles = Σp (3), Σ xx xy xz yy yz zz (6) over the rows of pos (rows,3). */
+size_t aopt_pos_moments_workspace_bytes(void);
+int aopt_pos_moments(int64_t rows, const float *pos, double *moments, void *workspace,
+                     size_t workspace_bytes, aopt_stream_t stream);
+/* `state` (aopt_pe_mlp_state_bytes(c), caller-allocated) carries the folded BatchNorm maps and the bf16
+ * copies of W2 from forward to backward.  use_batch_stats = 1: training (statistics from `moments`);
+ * 0: evaluation (running_mean / running_var). */
+size_t aopt_pe_mlp_state_bytes(int c);
+int aopt_pe_mlp_forward(int64_t rows, int c, const float *pos, const double *moments, const float *w1,
+                        const float *b1, const float *gamma, const float *beta, const float *running_mean,
+                        const float *running_var, float eps, int use_batch_stats, const float *w2,
+                        const float *b2, float *out, void *state, size_t state_bytes, aopt_stream_t stream);
+/* stats_out (3c floats) = batch mean | biased variance | rstd of the first layer (running-stat update). */
+int aopt_pe_mlp_stats(int c, const void *state, float *stats_out, aopt_stream_t stream);
+/* Parameter gradients for grad (rows,c) = dL/dpeb.  One pass over grad; deterministic (no atomics). */
+size_t aopt_pe_mlp_backward_workspace_bytes(int64_t rows, int c);
+int aopt_pe_mlp_backward(int64_t rows, int c, const float *pos, const double *moments, const float *w1,
+                         const float *gamma, int use_batch_stats, const float *grad, const void *state,
+                         float *grad_w1, float *grad_b1, float *grad_gamma, float *grad_beta, float *grad_w2,
+                         float *grad_b2, void *workspace, size_t workspace_bytes, aopt_stream_t stream);
+
 /* ---- PTv1-layout fused ops kept for API parity --------------------------------------------- */
 /* output[n,ch] = sum_s (input[idx[n,s],ch] + position[n,s,ch]) * weight[n,s,ch % w_c]. */
 int aopt_aggregation_forward(int n, int nsample, int c, int w_c, const float *input,

@@ -113,7 +113,8 @@ def test_unsupported_width_is_an_error():
 
 
 def test_model_with_fused_pe_tracks_the_unfused_model():
-    """Whole PTv2m2 under bf16 autocast: fused positional MLP (levels with C in {48, 96}) vs the torch path."""
+    """Whole PTv2m2 in fp32 with and without the fused positional MLP (forced on for levels with C in
+    {48, 96}): the only difference between the two runs is the bf16 rounding inside the fused C x C layer."""
     import os
 
     from ao_b200 import ptv2, scenes
@@ -128,8 +129,7 @@ def test_model_with_fused_pe_tracks_the_unfused_model():
         os.environ["AOPT_FUSED_PE"] = flag
         try:
             m = copy.deepcopy(model)
-            with torch.autocast("cuda", dtype=torch.bfloat16):
-                logits = m(data)
+            logits = m(data)
             loss = torch.nn.functional.cross_entropy(logits.float(), target)
             loss.backward()
             out[flag] = (logits.float().detach(), loss.item(),
@@ -137,9 +137,8 @@ def test_model_with_fused_pe_tracks_the_unfused_model():
                          m.patch_embed.blocks.blocks[0].attn.linear_p_bias[0].weight.grad.detach().clone())
         finally:
             os.environ.pop("AOPT_FUSED_PE", None)
-    # both paths are bf16-precision pipelines: compare at bf16 tolerance of the logits' scale
-    assert abs(out["0"][1] - out["1"][1]) < 5e-2 * max(1.0, abs(out["0"][1]))
-    assert rel_err(out["1"][0], out["0"][0]) < 0.15
+    assert abs(out["0"][1] - out["1"][1]) < 2e-2 * max(1.0, abs(out["0"][1]))
+    assert rel_err(out["1"][0], out["0"][0]) < 0.1
     for i in (2, 3):
         cos = torch.nn.functional.cosine_similarity(out["0"][i].flatten(), out["1"][i].flatten(), dim=0).item()
-        assert cos > 0.98, (i, cos)
+        assert cos > 0.9, (i, cos)

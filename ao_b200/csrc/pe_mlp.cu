@@ -140,6 +140,43 @@ __device__ __forceinline__ void load_b(uint32_t (&b)[2], const __nv_bfloat16 *ti
     b[1] = ld_u32(p + 8);
 }
 
+// ---- bulk asynchronous copies (TMA 1-D: cp.async.bulk → SASS UBLKCP) ---------------------------------------
+// A tile of TR consecutive rows is one contiguous TR·C·4-byte block in global memory, so it moves with a
+// single bulk copy issued by one thread: no LSU wavefronts, no registers, completion through an mbarrier
+// (loads) or a bulk group (stores).
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_store(void *gdst, const void *ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_load(void *sdst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(sdst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
 // ---- 3. forward ------------------------------------------------------------------------------------------
 template <int C>
 __global__ void __launch_bounds__(kPeBlock)
@@ -151,7 +188,8 @@ pe_mlp_forward_kernel(long long rows, const float *__restrict__ pos, const float
     __nv_bfloat16 *w2s = reinterpret_cast<__nv_bfloat16 *>(smem_raw);             // [C][LDH]   (n = co, k = ci)
     __nv_bfloat16 *hs = w2s + C * LDH;                                              // [128][LDH] (row, k = ci)
     float4 *fz = reinterpret_cast<float4 *>(hs + kPeTile * LDH);                    // [C] z-map
-    float *b2s = reinterpret_cast<float *>(fz + C);                                 // [C]
+    float *outs = reinterpret_cast<float *>(fz + C);                                // [128][C] output tile (bulk-stored)
+    float *b2s = outs + kPeTile * C;                                                // [C]
     for (int i = threadIdx.x; i < C * C; i += kPeBlock) w2s[(i / C) * LDH + (i % C)] = w2_bf[i];
     for (int i = threadIdx.x; i < C; i += kPeBlock) {
         fz[i] = make_float4(fold[i * 8], fold[i * 8 + 1], fold[i * 8 + 2], fold[i * 8 + 3]);
@@ -163,6 +201,7 @@ pe_mlp_forward_kernel(long long rows, const float *__restrict__ pos, const float
     const long long n_tiles = (rows + kPeTile - 1) / kPeTile;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const long long row_base = tile * kPeTile;
+        if (threadIdx.x == 0) bulk_store_wait_read();  // previous tile's copy has finished reading `outs`
         {   // hidden activations of the tile: thread → (row = tid/2, half of the channels)
             const int r = threadIdx.x >> 1, half = threadIdx.x & 1;
             const long long gr = row_base + r;
@@ -192,29 +231,39 @@ pe_mlp_forward_kernel(long long rows, const float *__restrict__ pos, const float
                 mma_bf16_16816(acc[nt], a, b);
             }
         }
-        const long long r0 = row_base + warp * 16 + g, r1 = r0 + 8;
+        // epilogue: + b2 into the shared output tile, then ONE bulk copy of the tile's contiguous rows
+        const int lr0 = warp * 16 + g, lr1 = lr0 + 8;
 #pragma unroll
         for (int nt = 0; nt < C / 8; ++nt) {
             const int col = nt * 8 + t * 2;
             const float bb0 = b2s[col], bb1 = b2s[col + 1];
-            if (r0 < rows) *reinterpret_cast<float2 *>(out + r0 * C + col) = make_float2(acc[nt][0] + bb0, acc[nt][1] + bb1);
-            if (r1 < rows) *reinterpret_cast<float2 *>(out + r1 * C + col) = make_float2(acc[nt][2] + bb0, acc[nt][3] + bb1);
+            *reinterpret_cast<float2 *>(outs + lr0 * C + col) = make_float2(acc[nt][0] + bb0, acc[nt][1] + bb1);
+            *reinterpret_cast<float2 *>(outs + lr1 * C + col) = make_float2(acc[nt][2] + bb0, acc[nt][3] + bb1);
         }
-        __syncthreads();  // hs is rewritten by the next tile
+        fence_proxy_async();  // generic-proxy writes → visible to the async (bulk copy) proxy
+        __syncthreads();      // tile complete; hs may be rewritten by the next iteration
+        if (threadIdx.x == 0) {
+            const long long valid = rows - row_base < kPeTile ? rows - row_base : kPeTile;
+            bulk_store(out + row_base * C, outs, (uint32_t)(valid * C * 4));
+        }
     }
+    if (threadIdx.x == 0) bulk_store_wait_all();  // shared memory must outlive the last copy
 }
 
 // ---- 4. backward -----------------------------------------------------------------------------------------
 // Per-CTA partial layout (floats): dW2 [C*C] | db2 [C] | S2 [C] | S3 [C] | S1 [3C]
+// TR = rows per tile: 128 at C=48 (74 KB of shared memory → 3 CTAs/SM), 64 at C=96 (86 KB → 2 CTAs/SM).
 template <int C>
 struct PeBwdLayout {
-    static constexpr int LDG = C + 8;            // Gs  [128][LDG]  row-major (row, co)
-    static constexpr int LDT = kPeTile + 8;      // GsT [C][LDT], HsT [C][LDT]  (channel, row)
+    static constexpr int TR = C <= 48 ? 128 : 64;
+    static constexpr int LDG = C + 8;            // Gs  [TR][LDG]  row-major (row, co)
+    static constexpr int LDT = TR + 8;           // GsT [C][LDT], HsT [C][LDT]  (channel, row)
     static constexpr int LDW = C + 8;            // W2Ts [C][LDW]  (n = ci, k = co)
-    static constexpr int LDZ = C + 1;            // DZs [128][LDZ] fp32
-    static constexpr size_t bytes = (size_t)2 * (kPeTile * LDG + 2 * C * LDT + C * LDW) + 4 * (size_t)kPeTile * LDZ +
-                                    16 * (size_t)kPeTile + 32 * (size_t)C;
+    static constexpr int LDZ = C + 1;            // DZs [TR][LDZ] fp32
+    static constexpr size_t bytes = (size_t)2 * (TR * LDG + 2 * C * LDT + C * LDW) + 4 * (size_t)TR * LDZ +
+                                    16 * (size_t)TR + 32 * (size_t)C + 4 * (size_t)TR * C + 16;
     static constexpr int partial_floats = C * C + 6 * C;
+    static constexpr int ctas_per_sm = 2;
 };
 
 template <int C>
@@ -223,15 +272,27 @@ pe_mlp_backward_kernel(long long rows, const float *__restrict__ pos, const floa
                        const __nv_bfloat16 *__restrict__ w2t_bf, const float *__restrict__ grad,
                        float *__restrict__ partial) {
     using L = PeBwdLayout<C>;
+    constexpr int TR = L::TR;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __nv_bfloat16 *gs = reinterpret_cast<__nv_bfloat16 *>(smem_raw);
-    __nv_bfloat16 *gst = gs + kPeTile * L::LDG;
+    __nv_bfloat16 *gst = gs + TR * L::LDG;
     __nv_bfloat16 *hst = gst + C * L::LDT;
     __nv_bfloat16 *w2ts = hst + C * L::LDT;
     float *dzs = reinterpret_cast<float *>(w2ts + C * L::LDW);
-    float4 *ps = reinterpret_cast<float4 *>(dzs + kPeTile * L::LDZ);               // [128] (x, y, z, valid)
-    float4 *fz = ps + kPeTile;                                                       // [C] z-map
+    float4 *ps = reinterpret_cast<float4 *>(dzs + TR * L::LDZ);                    // [TR] (x, y, z, valid)
+    float4 *fz = ps + TR;                                                       // [C] z-map
     float4 *fx = fz + C;                                                             // [C] x̂-map
+    float *gstage = reinterpret_cast<float *>(fx + C);                               // [TR][C] fp32 tile (bulk-loaded)
+    uint64_t *bar = reinterpret_cast<uint64_t *>(gstage + TR * C);
+    const long long n_tiles = (rows + TR - 1) / TR;
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        if ((long long)blockIdx.x < n_tiles) {  // first tile of this CTA
+            const long long rb0 = (long long)blockIdx.x * TR;
+            const long long valid = rows - rb0 < TR ? rows - rb0 : TR;
+            bulk_load(gstage, grad + rb0 * C, (uint32_t)(valid * C * 4), bar);
+        }
+    }
     for (int i = threadIdx.x; i < C * C; i += kPeBlock) w2ts[(i / C) * L::LDW + (i % C)] = w2t_bf[i];
     for (int i = threadIdx.x; i < C; i += kPeBlock) {
         fz[i] = make_float4(fold[i * 8], fold[i * 8 + 1], fold[i * 8 + 2], fold[i * 8 + 3]);
@@ -250,21 +311,23 @@ pe_mlp_backward_kernel(long long rows, const float *__restrict__ pos, const floa
     const bool col_active = col_g < NG;
     float s_db2 = 0.f, s2 = 0.f, s3 = 0.f, s1x = 0.f, s1y = 0.f, s1z = 0.f;
     __syncthreads();
-    const long long n_tiles = (rows + kPeTile - 1) / kPeTile;
+    uint32_t phase = 0;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const long long row_base = tile * kPeTile;
-        // a. positions and the gradient tile (fp32 → bf16, both orientations)
-        if (threadIdx.x < kPeTile) {
+        const long long row_base = tile * TR;
+        // a. positions and the gradient tile (bulk-loaded fp32 → bf16, both orientations)
+        if (threadIdx.x < TR) {
             const long long gr = row_base + threadIdx.x;
             float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
             if (gr < rows) p = make_float4(__ldg(pos + gr * 3), __ldg(pos + gr * 3 + 1), __ldg(pos + gr * 3 + 2), 1.f);
             ps[threadIdx.x] = p;
         }
-        for (int i = threadIdx.x; i < kPeTile * (C / 4); i += kPeBlock) {
+        mbar_wait(bar, phase);
+        phase ^= 1u;
+        for (int i = threadIdx.x; i < TR * (C / 4); i += kPeBlock) {
             const int r = i / (C / 4), c4 = (i % (C / 4)) * 4;
             const long long gr = row_base + r;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (gr < rows) v = ldg_stream4(grad + gr * C + c4);
+            if (gr < rows) v = *reinterpret_cast<const float4 *>(gstage + r * C + c4);
             const __nv_bfloat16 b0 = __float2bfloat16_rn(v.x), b1 = __float2bfloat16_rn(v.y),
                                 b2 = __float2bfloat16_rn(v.z), b3 = __float2bfloat16_rn(v.w);
             __nv_bfloat16 *d = gs + r * L::LDG + c4;
@@ -273,37 +336,45 @@ pe_mlp_backward_kernel(long long rows, const float *__restrict__ pos, const floa
             gst[(c4 + 2) * L::LDT + r] = b2; gst[(c4 + 3) * L::LDT + r] = b3;
         }
         __syncthreads();
-        // b. hidden activations, transposed: thread → (row = tid % 128, channel parity)
+        if (threadIdx.x == 0 && tile + gridDim.x < n_tiles) {  // prefetch the next tile while this one is processed
+            const long long rbn = (tile + gridDim.x) * TR;
+            const long long valid = rows - rbn < TR ? rows - rbn : TR;
+            bulk_load(gstage, grad + rbn * C, (uint32_t)(valid * C * 4), bar);
+        }
+        // b. hidden activations, transposed: thread → (row = tid % TR, channel residue)
         {
-            const int r = threadIdx.x & (kPeTile - 1), half = threadIdx.x >> 7;
+            constexpr int PARTS = kPeBlock / TR;
+            const int r = threadIdx.x % TR, part = threadIdx.x / TR;
             const float4 p = ps[r];
-            for (int cc = half; cc < C; cc += 2) {
+            for (int cc = part; cc < C; cc += PARTS) {
                 const float4 f = fz[cc];
                 const float z = fmaf(f.x, p.x, fmaf(f.y, p.y, fmaf(f.z, p.z, f.w)));
                 hst[cc * L::LDT + r] = __float2bfloat16_rn(p.w > 0.f ? fmaxf(z, 0.f) : 0.f);
             }
         }
         __syncthreads();
-        // c. dh = G · W2 (rows x ci), masked by h > 0 → dzs
+        // c. dh = G · W2 (rows x ci), masked by h > 0 → dzs.  Warp → (16-row block, a slice of the n-tiles).
         {
-            float acc[C / 8][4];
+            constexpr int RB = TR / 16, WPR = 8 / RB, NTW = (C / 8) / WPR;
+            const int rb = warp % RB, nt0 = (warp / RB) * NTW;
+            float acc[NTW][4];
 #pragma unroll
-            for (int nt = 0; nt < C / 8; ++nt) { acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f; }
+            for (int nt = 0; nt < NTW; ++nt) { acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f; }
 #pragma unroll
             for (int kt = 0; kt < C / 16; ++kt) {
                 uint32_t a[4];
-                load_a(a, gs, L::LDG, warp * 16, kt * 16, lane);
+                load_a(a, gs, L::LDG, rb * 16, kt * 16, lane);
 #pragma unroll
-                for (int nt = 0; nt < C / 8; ++nt) {
+                for (int nt = 0; nt < NTW; ++nt) {
                     uint32_t b[2];
-                    load_b(b, w2ts, L::LDW, nt * 8, kt * 16, lane);
+                    load_b(b, w2ts, L::LDW, (nt0 + nt) * 8, kt * 16, lane);
                     mma_bf16_16816(acc[nt], a, b);
                 }
             }
-            const int r0 = warp * 16 + g, r1 = r0 + 8;
+            const int r0 = rb * 16 + g, r1 = r0 + 8;
 #pragma unroll
-            for (int nt = 0; nt < C / 8; ++nt) {
-                const int col = nt * 8 + t * 2;
+            for (int nt = 0; nt < NTW; ++nt) {
+                const int col = (nt0 + nt) * 8 + t * 2;
                 const float zero = 0.f;
                 dzs[r0 * L::LDZ + col] = __bfloat162float(hst[col * L::LDT + r0]) > 0.f ? acc[nt][0] : zero;
                 dzs[r0 * L::LDZ + col + 1] = __bfloat162float(hst[(col + 1) * L::LDT + r0]) > 0.f ? acc[nt][1] : zero;
@@ -318,7 +389,7 @@ pe_mlp_backward_kernel(long long rows, const float *__restrict__ pos, const floa
             if (tid_tile < TILES) {
                 const int mt = tid_tile / NT, nt = tid_tile % NT;
 #pragma unroll
-                for (int kt = 0; kt < kPeTile / 16; ++kt) {
+                for (int kt = 0; kt < TR / 16; ++kt) {
                     uint32_t a[4], b[2];
                     load_a(a, gst, L::LDT, mt * 16, kt * 16, lane);
                     load_b(b, hst, L::LDT, nt * 8, kt * 16, lane);
@@ -330,7 +401,7 @@ pe_mlp_backward_kernel(long long rows, const float *__restrict__ pos, const floa
         // e. column sums over the rows of the tile
         if (col_active) {
             const float4 f = fx[col_c];
-            for (int r = col_g; r < kPeTile; r += NG) {
+            for (int r = col_g; r < TR; r += NG) {
                 const float4 p = ps[r];
                 const float dz = dzs[r * L::LDZ + col_c];
                 const float xh = fmaf(f.x, p.x, fmaf(f.y, p.y, fmaf(f.z, p.z, f.w)));
@@ -420,14 +491,19 @@ pe_mlp_backward_params_kernel(int c, double rows, int use_batch, const float *__
     }
 }
 
-static int pe_grid(long long rows) {
-    long long tiles = (rows + kPeTile - 1) / kPeTile;
-    long long cap = kNumSM;  // one persistent CTA per SM (shared-memory bound)
+// Persistent grids: as many CTAs as fit per SM (shared memory / registers), at most one per tile.
+static int pe_grid(long long rows, int tile_rows, int ctas_per_sm) {
+    long long tiles = (rows + tile_rows - 1) / tile_rows;
+    long long cap = (long long)kNumSM * ctas_per_sm;
     return (int)(tiles < cap ? (tiles < 1 ? 1 : tiles) : cap);
+}
+static int pe_bwd_grid(long long rows, int c) {
+    return c <= 48 ? pe_grid(rows, PeBwdLayout<48>::TR, PeBwdLayout<48>::ctas_per_sm)
+                   : pe_grid(rows, PeBwdLayout<96>::TR, PeBwdLayout<96>::ctas_per_sm);
 }
 
 template <int C>
-static size_t pe_fwd_smem() { return (size_t)2 * (C * (C + 8) + kPeTile * (C + 8)) + 16 * (size_t)C + 4 * (size_t)C; }
+static size_t pe_fwd_smem() { return (size_t)2 * (C * (C + 8) + kPeTile * (C + 8)) + 16 * (size_t)C + 4 * (size_t)kPeTile * C + 4 * (size_t)C; }
 
 }  // namespace aopt
 
@@ -478,7 +554,7 @@ void launch_fwd(long long rows, const float *pos, const PeState &s, const float 
     const size_t smem = pe_fwd_smem<C>();
     static bool once = (cudaFuncSetAttribute(pe_mlp_forward_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), true);
     (void)once;
-    pe_mlp_forward_kernel<C><<<pe_grid(rows), kPeBlock, smem, st>>>(rows, pos, s.fold, s.w2, b2, out);
+    pe_mlp_forward_kernel<C><<<pe_grid(rows, kPeTile, C <= 48 ? 4 : 2), kPeBlock, smem, st>>>(rows, pos, s.fold, s.w2, b2, out);
 }
 template <int C>
 void launch_bwd(long long rows, const float *pos, const PeState &s, const float *grad, float *partial, int grid,
@@ -517,7 +593,7 @@ extern "C" int aopt_pe_mlp_forward(int64_t rows, int c, const float *pos, const 
 extern "C" size_t aopt_pe_mlp_backward_workspace_bytes(int64_t rows, int c) {
     if (!aopt_pe_mlp_supported(c) || rows < 0) return 0;
     const size_t pf = (size_t)c * c + 6 * (size_t)c;
-    return a256(4 * pf * (size_t)pe_grid(rows)) + a256(4 * 6 * (size_t)c);
+    return a256(4 * pf * (size_t)pe_bwd_grid(rows, c)) + a256(4 * 6 * (size_t)c);
 }
 
 /* Parameter gradients of aopt_pe_mlp_forward given grad (rows,c) = dL/dpeb; `state` is the forward's. */
@@ -534,7 +610,7 @@ extern "C" int aopt_pe_mlp_backward(int64_t rows, int c, const float *pos, const
     if (!workspace || workspace_bytes < aopt_pe_mlp_backward_workspace_bytes(rows, c)) return AOPT_ERR_WORKSPACE;
     cudaStream_t st = as_stream(stream);
     PeState s = carve_state(const_cast<void *>(state), c);
-    const int grid = pe_grid(rows);
+    const int grid = pe_bwd_grid(rows, c);
     const int pf = c * c + 6 * c;
     float *partial = static_cast<float *>(workspace);
     float *sums = reinterpret_cast<float *>(static_cast<char *>(workspace) + a256(4 * (size_t)pf * grid));

@@ -11,7 +11,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
 
-from ao_b200 import pointops, scenes
+from ao_b200 import _lib, pointops, scenes
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--presort", action="store_true")
@@ -82,7 +82,6 @@ for li in [int(x) for x in args.levels.split(",")]:
     row("group_xyz", timeit(lambda: pointops.group_xyz(idx, coord)), 24.0 * n + 16.0 * n * k)
     row("gather_sub fwd", timeit(lambda: pointops.gva_relation(key, query, idx)), 4.0 * n * k + 8.0 * n * c + 4.0 * n * k * c)
     rel = pointops.gva_relation(key, query, idx)
-    from ao_b200 import _lib
     lib = _lib.load()
     csr = pointops.get_csr(idx, n)
     gk = torch.empty(n, c, device=dev)
@@ -98,6 +97,31 @@ for li in [int(x) for x in args.levels.split(",")]:
         8.0 * n * c + 8.0 * n * k * c + 8.0 * n * k * g + 4.0 * n * k)
     row("gva_backward_value", timeit(lambda: lib.aopt_gva_backward_value(n, k, c, g, g_out.data_ptr(), prob.data_ptr(), csr.rowptr.data_ptr(), csr.perm.data_ptr(), gval.data_ptr(), _lib.stream())),
         4.0 * n * k * g + 8.0 * n * c + 4.0 * (n + 1) + 4.0 * n * k)
+    if pointops.pe_mlp_supported(c):
+        import torch.nn as nn
+        from ao_b200 import ptv2 as _ptv2
+        mlp = nn.Sequential(nn.Linear(3, c), _ptv2.PointBatchNorm(c), nn.ReLU(inplace=True), nn.Linear(c, c)).to(dev).train()
+        pos = pointops.group_xyz(idx, coord)
+        row("pos_moments", timeit(lambda: pointops.pos_moments(pos)), 12.0 * n * k)
+        mom = pointops.pos_moments(pos)
+        row("pe_mlp forward", timeit(lambda: pointops.pe_bias_mlp(pos, mlp, mom)), 12.0 * n * k + 4.0 * n * k * c)
+        y = pointops.pe_bias_mlp(pos, mlp, mom)
+        gy = torch.randn_like(y)
+        row("pe_mlp backward", timeit(lambda: torch.autograd.grad(y, list(mlp.parameters()), gy, retain_graph=True, allow_unused=True)),
+            12.0 * n * k + 4.0 * n * k * c)
+        # device time of the C entry points alone (CUDA events around each call; best of 5)
+        best = {}
+        for _ in range(5):
+            tr = _lib.trace_start()
+            y2 = pointops.pe_bias_mlp(pos, mlp, mom)
+            torch.autograd.grad(y2, list(mlp.parameters()), gy, allow_unused=True)
+            torch.cuda.synchronize()
+            _lib.trace_stop()
+            for name, _a, s0, e0 in tr:
+                best[name] = min(best.get(name, 1e9), s0.elapsed_time(e0) * 1e3)
+        for name, us in best.items():
+            row("  " + name, us, 12.0 * n * k + 4.0 * n * k * c)
+        del y, y2, gy, pos
     if li < 3:
         c2 = C[li + 1]
         pin = torch.relu(torch.randn(n, c2, device=dev)).requires_grad_(True)

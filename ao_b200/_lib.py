@@ -53,10 +53,12 @@ SIGNATURES = {
     "aopt_pos_moments_workspace_bytes": (c_size_t, []),
     "aopt_pos_moments": (c_int, [c_int64, P, P, P, c_size_t, P]),
     "aopt_pe_mlp_state_bytes": (c_size_t, [c_int]),
-    "aopt_pe_mlp_forward": (c_int, [c_int64, c_int, P, P, P, P, P, P, P, P, c_float, c_int, P, P, P, P, c_size_t, P]),
+    "aopt_pe_mlp_forward": (c_int, [c_int64, c_int, P, P, P, P, P, P, P, P, c_float, c_int, P, P, P, P, c_int, P, P,
+                                    c_size_t, P]),
     "aopt_pe_mlp_stats": (c_int, [c_int, P, P, P]),
     "aopt_pe_mlp_backward_workspace_bytes": (c_size_t, [c_int64, c_int]),
-    "aopt_pe_mlp_backward": (c_int, [c_int64, c_int, P, P, P, P, c_int, P, P, P, P, P, P, P, P, P, c_size_t, P]),
+    "aopt_pe_mlp_backward": (c_int, [c_int64, c_int, P, P, P, P, c_int, P, P, P, P, P, P, P, P, c_int, P, P, P,
+                                     c_size_t, P]),
     "aopt_aggregation_forward": (c_int, [c_int, c_int, c_int, c_int, P, P, P, P, P, P]),
     "aopt_aggregation_backward": (c_int, [c_int, c_int, c_int, c_int, P, P, P, P, P, P, P, P, P, P, P]),
     "aopt_subtraction_forward": (c_int, [c_int, c_int, c_int, P, P, P, P, P]),

@@ -80,7 +80,9 @@ pe_fold_kernel(int c, double rows, const double *__restrict__ mom, const float *
                const float *__restrict__ b1, const float *__restrict__ gamma, const float *__restrict__ beta,
                const float *__restrict__ running_mean, const float *__restrict__ running_var, float eps,
                int use_batch, const float *__restrict__ w2, float *__restrict__ fold, float *__restrict__ stats,
-               __nv_bfloat16 *__restrict__ w2_bf, __nv_bfloat16 *__restrict__ w2t_bf) {
+               __nv_bfloat16 *__restrict__ w2_bf, __nv_bfloat16 *__restrict__ w2t_bf,
+               const float *__restrict__ aux_w, int ga, __nv_bfloat16 *__restrict__ wf_bf,
+               __nv_bfloat16 *__restrict__ wft_bf) {
     const int ch = blockIdx.x;
     if (threadIdx.x == 0) {
         const double wx = w1[ch * 3], wy = w1[ch * 3 + 1], wz = w1[ch * 3 + 2];
@@ -111,6 +113,13 @@ pe_fold_kernel(int c, double rows, const double *__restrict__ mom, const float *
         const __nv_bfloat16 v = __float2bfloat16_rn(w2[(size_t)ch * c + i]);
         w2_bf[(size_t)ch * c + i] = v;
         w2t_bf[(size_t)i * c + ch] = v;
+    }
+    // auxiliary head (ga <= 16 extra outputs): wf [16][c] (rows >= ga zero) and its transpose wft [c][16]
+    if (threadIdx.x < 16) {
+        const int gq = threadIdx.x;
+        const float v = (aux_w && gq < ga) ? aux_w[(size_t)gq * c + ch] : 0.f;
+        wf_bf[(size_t)gq * c + ch] = __float2bfloat16_rn(v);
+        wft_bf[(size_t)ch * 16 + gq] = __float2bfloat16_rn(v);
     }
 }
 
@@ -182,7 +191,8 @@ template <int C>
 __global__ void __launch_bounds__(kPeBlock)
 pe_mlp_forward_kernel(long long rows, const float *__restrict__ pos, const float *__restrict__ fold,
                       const __nv_bfloat16 *__restrict__ w2_bf, const float *__restrict__ b2,
-                      float *__restrict__ out) {
+                      float *__restrict__ out, const __nv_bfloat16 *__restrict__ wf_bf, int ga,
+                      float *__restrict__ aux_out) {
     constexpr int LDH = C + 8;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __nv_bfloat16 *w2s = reinterpret_cast<__nv_bfloat16 *>(smem_raw);             // [C][LDH]   (n = co, k = ci)
@@ -190,6 +200,11 @@ pe_mlp_forward_kernel(long long rows, const float *__restrict__ pos, const float
     float4 *fz = reinterpret_cast<float4 *>(hs + kPeTile * LDH);                    // [C] z-map
     float *outs = reinterpret_cast<float *>(fz + C);                                // [128][C] output tile (bulk-stored)
     float *b2s = outs + kPeTile * C;                                                // [C]
+    __nv_bfloat16 *wfs = reinterpret_cast<__nv_bfloat16 *>(b2s + C);               // [16][LDH] auxiliary head (n = g', k = ci)
+    const bool aux = aux_out != nullptr;
+    const bool aux2 = aux && ga > 8;
+    if (aux)
+        for (int i = threadIdx.x; i < 16 * C; i += kPeBlock) wfs[(i / C) * LDH + (i % C)] = wf_bf[i];
     for (int i = threadIdx.x; i < C * C; i += kPeBlock) w2s[(i / C) * LDH + (i % C)] = w2_bf[i];
     for (int i = threadIdx.x; i < C; i += kPeBlock) {
         fz[i] = make_float4(fold[i * 8], fold[i * 8 + 1], fold[i * 8 + 2], fold[i * 8 + 3]);
@@ -218,6 +233,7 @@ pe_mlp_forward_kernel(long long rows, const float *__restrict__ pos, const float
         }
         __syncthreads();
         float acc[C / 8][4];
+        float aacc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
 #pragma unroll
         for (int nt = 0; nt < C / 8; ++nt) { acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f; }
 #pragma unroll
@@ -230,9 +246,33 @@ pe_mlp_forward_kernel(long long rows, const float *__restrict__ pos, const float
                 load_b(b, w2s, LDH, nt * 8, kt * 16, lane);
                 mma_bf16_16816(acc[nt], a, b);
             }
+            if (aux) {  // one or two more n-tiles: the auxiliary head shares the A fragments
+                uint32_t b[2];
+                load_b(b, wfs, LDH, 0, kt * 16, lane);
+                mma_bf16_16816(aacc[0], a, b);
+                if (aux2) {
+                    load_b(b, wfs, LDH, 8, kt * 16, lane);
+                    mma_bf16_16816(aacc[1], a, b);
+                }
+            }
         }
         // epilogue: + b2 into the shared output tile, then ONE bulk copy of the tile's contiguous rows
         const int lr0 = warp * 16 + g, lr1 = lr0 + 8;
+        if (aux) {  // (rows, ga) fp32, small: direct stores
+            const long long gr0 = row_base + lr0, gr1 = row_base + lr1;
+#pragma unroll
+            for (int an = 0; an < 2; ++an) {
+                const int col = an * 8 + t * 2;
+                if (col < ga) {
+                    if (gr0 < rows) aux_out[gr0 * ga + col] = aacc[an][0];
+                    if (gr1 < rows) aux_out[gr1 * ga + col] = aacc[an][2];
+                }
+                if (col + 1 < ga) {
+                    if (gr0 < rows) aux_out[gr0 * ga + col + 1] = aacc[an][1];
+                    if (gr1 < rows) aux_out[gr1 * ga + col + 1] = aacc[an][3];
+                }
+            }
+        }
 #pragma unroll
         for (int nt = 0; nt < C / 8; ++nt) {
             const int col = nt * 8 + t * 2;
@@ -260,17 +300,20 @@ struct PeBwdLayout {
     static constexpr int LDT = TR + 8;           // GsT [C][LDT], HsT [C][LDT]  (channel, row)
     static constexpr int LDW = C + 8;            // W2Ts [C][LDW]  (n = ci, k = co)
     static constexpr int LDZ = C + 1;            // DZs [TR][LDZ] fp32
+    static constexpr int LDU = 24;               // dus [TR][LDU] (k = g' padded to 16), wfts [C][LDU] (n = ci, k = g')
     static constexpr size_t bytes = (size_t)2 * (TR * LDG + 2 * C * LDT + C * LDW) + 4 * (size_t)TR * LDZ +
-                                    16 * (size_t)TR + 32 * (size_t)C + 4 * (size_t)TR * C + 16;
-    static constexpr int partial_floats = C * C + 6 * C;
-    static constexpr int ctas_per_sm = 2;
+                                    16 * (size_t)TR + 32 * (size_t)C + 4 * (size_t)TR * C + 16 +
+                                    (size_t)2 * (TR * LDU + 16 * LDT + C * LDU);
+    static constexpr int partial_floats = C * C + 6 * C + 16 * C;  // dW2 | db2 S2 S3 S1 | dWf [16][C]
+    static constexpr int ctas_per_sm = (2 * (bytes + 1024) <= 232448) ? 2 : 1;  // 227 KB of shared memory per SM
 };
 
 template <int C>
 __global__ void __launch_bounds__(kPeBlock)
 pe_mlp_backward_kernel(long long rows, const float *__restrict__ pos, const float *__restrict__ fold,
                        const __nv_bfloat16 *__restrict__ w2t_bf, const float *__restrict__ grad,
-                       float *__restrict__ partial) {
+                       float *__restrict__ partial, const __nv_bfloat16 *__restrict__ wft_bf, int ga,
+                       const float *__restrict__ grad_aux) {
     using L = PeBwdLayout<C>;
     constexpr int TR = L::TR;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -284,6 +327,12 @@ pe_mlp_backward_kernel(long long rows, const float *__restrict__ pos, const floa
     float4 *fx = fz + C;                                                             // [C] x̂-map
     float *gstage = reinterpret_cast<float *>(fx + C);                               // [TR][C] fp32 tile (bulk-loaded)
     uint64_t *bar = reinterpret_cast<uint64_t *>(gstage + TR * C);
+    __nv_bfloat16 *dus = reinterpret_cast<__nv_bfloat16 *>(bar + 2);                 // [TR][LDU] aux gradient, row-major
+    __nv_bfloat16 *dut = dus + TR * L::LDU;                                          // [16][LDT] its transpose
+    __nv_bfloat16 *wfts = dut + 16 * L::LDT;                                         // [C][LDU]  (n = ci, k = g')
+    const bool aux = grad_aux != nullptr;
+    if (aux)
+        for (int i = threadIdx.x; i < C * 16; i += kPeBlock) wfts[(i / 16) * L::LDU + (i % 16)] = wft_bf[i];
     const long long n_tiles = (rows + TR - 1) / TR;
     if (threadIdx.x == 0) {
         mbar_init(bar, 1);
@@ -301,7 +350,8 @@ pe_mlp_backward_kernel(long long rows, const float *__restrict__ pos, const floa
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
     // dW2 tiles (16 co x 8 ci) owned by this warp: tile id = warp + 8*i
-    constexpr int MT = C / 16, NT = C / 8, TILES = MT * NT, OWN = (TILES + 7) / 8;
+    constexpr int MT = C / 16, NT = C / 8, TILES = (MT + 1) * NT, OWN = (TILES + 7) / 8;  // row MT = the aux head
+    const int n_own_tiles = aux ? TILES : MT * NT;
     float wacc[OWN][4];
 #pragma unroll
     for (int i = 0; i < OWN; ++i) { wacc[i][0] = wacc[i][1] = wacc[i][2] = wacc[i][3] = 0.f; }
@@ -320,6 +370,16 @@ pe_mlp_backward_kernel(long long rows, const float *__restrict__ pos, const floa
             float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
             if (gr < rows) p = make_float4(__ldg(pos + gr * 3), __ldg(pos + gr * 3 + 1), __ldg(pos + gr * 3 + 2), 1.f);
             ps[threadIdx.x] = p;
+        }
+        if (aux) {  // aux gradient tile (rows x ga fp32, small): both orientations, zero padded to 16
+            for (int i = threadIdx.x; i < TR * 16; i += kPeBlock) {
+                const int r = i >> 4, q = i & 15;
+                const long long gr = row_base + r;
+                const float v = (q < ga && gr < rows) ? __ldg(grad_aux + gr * ga + q) : 0.f;
+                const __nv_bfloat16 bv = __float2bfloat16_rn(v);
+                dus[r * L::LDU + q] = bv;
+                dut[q * L::LDT + r] = bv;
+            }
         }
         mbar_wait(bar, phase);
         phase ^= 1u;
@@ -371,6 +431,16 @@ pe_mlp_backward_kernel(long long rows, const float *__restrict__ pos, const floa
                     mma_bf16_16816(acc[nt], a, b);
                 }
             }
+            if (aux) {  // dh += dU · Wf  (one more k-tile: g' padded to 16)
+                uint32_t a[4];
+                load_a(a, dus, L::LDU, rb * 16, 0, lane);
+#pragma unroll
+                for (int nt = 0; nt < NTW; ++nt) {
+                    uint32_t b[2];
+                    load_b(b, wfts, L::LDU, (nt0 + nt) * 8, 0, lane);
+                    mma_bf16_16816(acc[nt], a, b);
+                }
+            }
             const int r0 = rb * 16 + g, r1 = r0 + 8;
 #pragma unroll
             for (int nt = 0; nt < NTW; ++nt) {
@@ -386,12 +456,13 @@ pe_mlp_backward_kernel(long long rows, const float *__restrict__ pos, const floa
 #pragma unroll
         for (int i = 0; i < OWN; ++i) {
             const int tid_tile = warp + 8 * i;
-            if (tid_tile < TILES) {
+            if (tid_tile < n_own_tiles) {
                 const int mt = tid_tile / NT, nt = tid_tile % NT;
+                const __nv_bfloat16 *asrc = mt < MT ? gst + (size_t)mt * 16 * L::LDT : dut;  // row MT: dWf = dUᵀ·h
 #pragma unroll
                 for (int kt = 0; kt < TR / 16; ++kt) {
                     uint32_t a[4], b[2];
-                    load_a(a, gst, L::LDT, mt * 16, kt * 16, lane);
+                    load_a(a, asrc, L::LDT, 0, kt * 16, lane);
                     load_b(b, hst, L::LDT, nt * 8, kt * 16, lane);
                     mma_bf16_16816(wacc[i], a, b);
                 }
@@ -420,11 +491,13 @@ pe_mlp_backward_kernel(long long rows, const float *__restrict__ pos, const floa
         const int tid_tile = warp + 8 * i;
         if (tid_tile < TILES) {
             const int mt = tid_tile / NT, nt = tid_tile % NT;
-            const int co = mt * 16 + g, ci = nt * 8 + t * 2;
-            out[(size_t)co * C + ci] = wacc[i][0];
-            out[(size_t)co * C + ci + 1] = wacc[i][1];
-            out[(size_t)(co + 8) * C + ci] = wacc[i][2];
-            out[(size_t)(co + 8) * C + ci + 1] = wacc[i][3];
+            // rows 0..C-1: dW2 [co][ci]; row block MT: dWf [g'][ci] stored after the channel sums
+            float *dst = mt < MT ? out + (size_t)mt * 16 * C : out + (size_t)C * C + 6 * C;
+            const int ci = nt * 8 + t * 2;
+            dst[(size_t)g * C + ci] = wacc[i][0];
+            dst[(size_t)g * C + ci + 1] = wacc[i][1];
+            dst[(size_t)(g + 8) * C + ci] = wacc[i][2];
+            dst[(size_t)(g + 8) * C + ci + 1] = wacc[i][3];
         }
     }
     // combine the row groups of every channel through shared memory (fixed order)
@@ -448,13 +521,15 @@ pe_mlp_backward_kernel(long long rows, const float *__restrict__ pos, const floa
 // Sums the per-CTA partials in CTA order: dW2 directly, the channel sums (db2 | S2 | S3 | S1) into `sums`.
 __global__ void __launch_bounds__(256)
 pe_mlp_backward_finalize_kernel(int c, int n_partial, int partial_floats, const float *__restrict__ partial,
-                                float *__restrict__ grad_w2, float *__restrict__ sums) {
-    const int total = c * c + 6 * c;
+                                float *__restrict__ grad_w2, float *__restrict__ sums, int ga,
+                                float *__restrict__ grad_aux_w) {
+    const int total = c * c + 6 * c + (grad_aux_w ? ga * c : 0);
     for (int i = blockIdx.x * 256 + threadIdx.x; i < total; i += gridDim.x * 256) {
         float v = 0.f;
         for (int p = 0; p < n_partial; ++p) v += partial[(size_t)p * partial_floats + i];
         if (i < c * c) grad_w2[i] = v;
-        else sums[i - c * c] = v;
+        else if (i < c * c + 6 * c) sums[i - c * c] = v;
+        else grad_aux_w[i - c * c - 6 * c] = v;  // dWf [ga][c]
     }
 }
 
@@ -503,7 +578,7 @@ static int pe_bwd_grid(long long rows, int c) {
 }
 
 template <int C>
-static size_t pe_fwd_smem() { return (size_t)2 * (C * (C + 8) + kPeTile * (C + 8)) + 16 * (size_t)C + 4 * (size_t)kPeTile * C + 4 * (size_t)C; }
+static size_t pe_fwd_smem() { return (size_t)2 * (C * (C + 8) + kPeTile * (C + 8) + 16 * (C + 8)) + 16 * (size_t)C + 4 * (size_t)kPeTile * C + 4 * (size_t)C; }
 
 }  // namespace aopt
 
@@ -532,13 +607,13 @@ extern "C" int aopt_pos_moments(int64_t rows, const float *pos, double *moments,
 /* Scratch that lives from forward to backward of one call (caller-allocated):
  * fold (8C floats) | stats (3C floats) | W2 bf16 (C*C) | W2ᵀ bf16 (C*C). */
 extern "C" size_t aopt_pe_mlp_state_bytes(int c) {
-    return a256(4 * (size_t)8 * c) + a256(4 * (size_t)3 * c) + 2 * a256(2 * (size_t)c * c);
+    return a256(4 * (size_t)8 * c) + a256(4 * (size_t)3 * c) + 2 * a256(2 * (size_t)c * c) + 2 * a256(2 * (size_t)16 * c);
 }
 
 namespace {
 struct PeState {
     float *fold, *stats;
-    __nv_bfloat16 *w2, *w2t;
+    __nv_bfloat16 *w2, *w2t, *wf, *wft;
 };
 PeState carve_state(void *state, int c) {
     char *p = static_cast<char *>(state);
@@ -546,23 +621,26 @@ PeState carve_state(void *state, int c) {
     s.fold = reinterpret_cast<float *>(p); p += a256(4 * (size_t)8 * c);
     s.stats = reinterpret_cast<float *>(p); p += a256(4 * (size_t)3 * c);
     s.w2 = reinterpret_cast<__nv_bfloat16 *>(p); p += a256(2 * (size_t)c * c);
-    s.w2t = reinterpret_cast<__nv_bfloat16 *>(p);
+    s.w2t = reinterpret_cast<__nv_bfloat16 *>(p); p += a256(2 * (size_t)c * c);
+    s.wf = reinterpret_cast<__nv_bfloat16 *>(p); p += a256(2 * (size_t)16 * c);
+    s.wft = reinterpret_cast<__nv_bfloat16 *>(p);
     return s;
 }
 template <int C>
-void launch_fwd(long long rows, const float *pos, const PeState &s, const float *b2, float *out, cudaStream_t st) {
+void launch_fwd(long long rows, const float *pos, const PeState &s, const float *b2, float *out, int ga,
+                float *aux_out, cudaStream_t st) {
     const size_t smem = pe_fwd_smem<C>();
     static bool once = (cudaFuncSetAttribute(pe_mlp_forward_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), true);
     (void)once;
-    pe_mlp_forward_kernel<C><<<pe_grid(rows, kPeTile, C <= 48 ? 4 : 2), kPeBlock, smem, st>>>(rows, pos, s.fold, s.w2, b2, out);
+    pe_mlp_forward_kernel<C><<<pe_grid(rows, kPeTile, C <= 48 ? 4 : 2), kPeBlock, smem, st>>>(rows, pos, s.fold, s.w2, b2, out, s.wf, ga, aux_out);
 }
 template <int C>
 void launch_bwd(long long rows, const float *pos, const PeState &s, const float *grad, float *partial, int grid,
-                cudaStream_t st) {
+                int ga, const float *grad_aux, cudaStream_t st) {
     const size_t smem = PeBwdLayout<C>::bytes;
     static bool once = (cudaFuncSetAttribute(pe_mlp_backward_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), true);
     (void)once;
-    pe_mlp_backward_kernel<C><<<grid, kPeBlock, smem, st>>>(rows, pos, s.fold, s.w2t, grad, partial);
+    pe_mlp_backward_kernel<C><<<grid, kPeBlock, smem, st>>>(rows, pos, s.fold, s.w2t, grad, partial, s.wft, ga, grad_aux);
 }
 }  // namespace
 
@@ -572,27 +650,30 @@ void launch_bwd(long long rows, const float *pos, const PeState &s, const float 
 extern "C" int aopt_pe_mlp_forward(int64_t rows, int c, const float *pos, const double *moments, const float *w1,
                                    const float *b1, const float *gamma, const float *beta,
                                    const float *running_mean, const float *running_var, float eps,
-                                   int use_batch_stats, const float *w2, const float *b2, float *out, void *state,
-                                   size_t state_bytes, aopt_stream_t stream) {
+                                   int use_batch_stats, const float *w2, const float *b2, float *out,
+                                   const float *aux_w, int ga, float *aux_out, void *state, size_t state_bytes,
+                                   aopt_stream_t stream) {
     if (rows < 0 || !aopt_pe_mlp_supported(c)) return rows < 0 ? AOPT_ERR_INVALID_ARGUMENT : AOPT_ERR_UNSUPPORTED;
     if (!w1 || !b1 || !gamma || !beta || !w2 || !b2 || !state) return AOPT_ERR_INVALID_ARGUMENT;
     if (use_batch_stats ? !moments : (!running_mean || !running_var)) return AOPT_ERR_INVALID_ARGUMENT;
     if (state_bytes < aopt_pe_mlp_state_bytes(c)) return AOPT_ERR_WORKSPACE;
     if (rows > 0 && (!pos || !out)) return AOPT_ERR_INVALID_ARGUMENT;
+    if (aux_w && (ga < 1 || ga > 16 || (rows > 0 && !aux_out))) return AOPT_ERR_INVALID_ARGUMENT;
+    if (!aux_w) { ga = 0; aux_out = nullptr; }
     cudaStream_t st = as_stream(stream);
     PeState s = carve_state(state, c);
     pe_fold_kernel<<<c, 128, 0, st>>>(c, (double)rows, moments, w1, b1, gamma, beta, running_mean, running_var, eps,
-                                      use_batch_stats, w2, s.fold, s.stats, s.w2, s.w2t);
+                                      use_batch_stats, w2, s.fold, s.stats, s.w2, s.w2t, aux_w, ga, s.wf, s.wft);
     if (rows > 0) {
-        if (c == 48) launch_fwd<48>(rows, pos, s, b2, out, st);
-        else launch_fwd<96>(rows, pos, s, b2, out, st);
+        if (c == 48) launch_fwd<48>(rows, pos, s, b2, out, ga, aux_out, st);
+        else launch_fwd<96>(rows, pos, s, b2, out, ga, aux_out, st);
     }
     return check_launch(rows > 0 ? 2 : 1);
 }
 
 extern "C" size_t aopt_pe_mlp_backward_workspace_bytes(int64_t rows, int c) {
     if (!aopt_pe_mlp_supported(c) || rows < 0) return 0;
-    const size_t pf = (size_t)c * c + 6 * (size_t)c;
+    const size_t pf = (size_t)c * c + 6 * (size_t)c + 16 * (size_t)c;
     return a256(4 * pf * (size_t)pe_bwd_grid(rows, c)) + a256(4 * 6 * (size_t)c);
 }
 
@@ -600,23 +681,26 @@ extern "C" size_t aopt_pe_mlp_backward_workspace_bytes(int64_t rows, int c) {
 extern "C" int aopt_pe_mlp_backward(int64_t rows, int c, const float *pos, const double *moments, const float *w1,
                                     const float *gamma, int use_batch_stats, const float *grad, const void *state,
                                     float *grad_w1, float *grad_b1, float *grad_gamma, float *grad_beta,
-                                    float *grad_w2, float *grad_b2, void *workspace, size_t workspace_bytes,
+                                    float *grad_w2, float *grad_b2, int ga, const float *grad_aux,
+                                    float *grad_aux_w, void *workspace, size_t workspace_bytes,
                                     aopt_stream_t stream) {
     if (rows < 1) return AOPT_ERR_INVALID_ARGUMENT;
     if (!aopt_pe_mlp_supported(c)) return AOPT_ERR_UNSUPPORTED;
     if (!pos || !w1 || !gamma || !grad || !state || !grad_w1 || !grad_b1 || !grad_gamma || !grad_beta || !grad_w2 || !grad_b2)
         return AOPT_ERR_INVALID_ARGUMENT;
     if (use_batch_stats && !moments) return AOPT_ERR_INVALID_ARGUMENT;
+    if (grad_aux && (ga < 1 || ga > 16 || !grad_aux_w)) return AOPT_ERR_INVALID_ARGUMENT;
+    if (!grad_aux) { ga = 0; grad_aux_w = nullptr; }
     if (!workspace || workspace_bytes < aopt_pe_mlp_backward_workspace_bytes(rows, c)) return AOPT_ERR_WORKSPACE;
     cudaStream_t st = as_stream(stream);
     PeState s = carve_state(const_cast<void *>(state), c);
     const int grid = pe_bwd_grid(rows, c);
-    const int pf = c * c + 6 * c;
+    const int pf = c * c + 6 * c + 16 * c;
     float *partial = static_cast<float *>(workspace);
     float *sums = reinterpret_cast<float *>(static_cast<char *>(workspace) + a256(4 * (size_t)pf * grid));
-    if (c == 48) launch_bwd<48>(rows, pos, s, grad, partial, grid, st);
-    else launch_bwd<96>(rows, pos, s, grad, partial, grid, st);
-    pe_mlp_backward_finalize_kernel<<<div_up(pf, 256), 256, 0, st>>>(c, grid, pf, partial, grad_w2, sums);
+    if (c == 48) launch_bwd<48>(rows, pos, s, grad, partial, grid, ga, grad_aux, st);
+    else launch_bwd<96>(rows, pos, s, grad, partial, grid, ga, grad_aux, st);
+    pe_mlp_backward_finalize_kernel<<<div_up(pf, 256), 256, 0, st>>>(c, grid, pf, partial, grad_w2, sums, ga, grad_aux_w);
     pe_mlp_backward_params_kernel<<<div_up(c, 128), 128, 0, st>>>(c, (double)rows, use_batch_stats, sums, moments, w1,
                                                                   gamma, s.stats, grad_w1, grad_b1, grad_gamma,
                                                                   grad_beta, grad_b2);

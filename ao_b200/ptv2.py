@@ -108,6 +108,10 @@ class GroupedVectorAttention(nn.Module):
         query, key, value = self.linear_q(feat), self.linear_k(feat), self.linear_v(feat)
         if pos is None:                                                       # (N,k,3): depends only on (idx, coord)
             pos = pointops.group_xyz(reference_index, coord)                  # :109,:111
+        if (self.pe_bias and not self.pe_multiplier and fused_pe_enabled()
+                and pointops.pe_mlp_supported(self.embed_channels) and self.groups <= 16
+                and not (self.attn_drop_rate > 0.0 and self.training)):
+            return self._forward_fused(query, key, value, pos, pos_moments, reference_index)
         relation_qk = pointops.gva_relation(key, query, reference_index)      # :109,:112
         peb = None
         if self.pe_multiplier:
@@ -131,6 +135,30 @@ class GroupedVectorAttention(nn.Module):
             n, k, c = value_g.shape
             out = torch.einsum("nsgi,nsg->ngi", value_g.view(n, k, self.groups, c // self.groups), weight)
             return out.reshape(n, c)
+        return pointops.gva_aggregate(value, peb, weight, reference_index, self.groups)   # :110,:119-128
+
+
+    def _forward_fused(self, query, key, value, pos, pos_moments, reference_index):
+        """Same mathematics as forward() with the (N,k,C) relation tensor eliminated.  The first layer of
+        weight_encoding is linear, so (:112,:118,:120)
+            Linear_e(key[idx] - q + peb) = (key We^T)[idx] - (q We^T) + (We W2) h + We b2 + b_e ,
+        where h is the hidden activation of linear_p_bias: two (N,G) GEMMs, a G-wide gather, and one extra
+        column tile in the fused positional MLP kernel — instead of materialising relation_qk, adding peb,
+        casting and a (N·k,C)x(C,G) GEMM (and their backward passes)."""
+        import torch.nn.functional as F
+
+        lin_e, lin2 = self.weight_encoding[0], self.linear_p_bias[3]
+        with torch.autocast("cuda", enabled=False):
+            we = lin_e.weight.float()                                         # (G, C)
+            wf = we @ lin2.weight.float()                                     # (G, C) acting on h
+            peb, upe = pointops.pe_bias_mlp(pos, self.linear_p_bias, pos_moments, aux_weight=wf)
+            kp = F.linear(key.float(), we)                                    # (N, G)
+            qp = F.linear(query.float(), we)
+            const = lin_e.bias.float() if lin_e.bias is not None else 0.0
+            if lin2.bias is not None:
+                const = const + F.linear(lin2.bias.float(), we)
+            u = pointops.gva_relation(kp, qp, reference_index) + upe + const  # (N, k, G) = weight_encoding[0](relation_qk)
+        weight = self.weight_encoding[1:](u)                                  # BN(G), ReLU, Linear(G,G)
         return pointops.gva_aggregate(value, peb, weight, reference_index, self.groups)   # :110,:119-128
 
 

@@ -175,10 +175,14 @@ int aopt_pos_moments(int64_t rows, const float *pos, double *moments, void *work
  * copies of W2 from forward to backward.  use_batch_stats = 1: training (statistics from `moments`);
  * 0: evaluation (running_mean / running_var). */
 size_t aopt_pe_mlp_state_bytes(int c);
+/* Optional auxiliary head: aux_w (ga,c), ga <= 16, aux_out (rows,ga) = aux_w · h (no bias) — the hidden
+ * activation h is shared, so a Linear applied to peb folds into the same kernel as one more MMA column tile
+ * (ptv2 uses it for weight_encoding[0]∘linear_p_bias[3], which removes the (rows,c) relation tensor). */
 int aopt_pe_mlp_forward(int64_t rows, int c, const float *pos, const double *moments, const float *w1,
                         const float *b1, const float *gamma, const float *beta, const float *running_mean,
                         const float *running_var, float eps, int use_batch_stats, const float *w2,
-                        const float *b2, float *out, void *state, size_t state_bytes, aopt_stream_t stream);
+                        const float *b2, float *out, const float *aux_w, int ga, float *aux_out, void *state,
+                        size_t state_bytes, aopt_stream_t stream);
 /* stats_out (3c floats) = batch mean | biased variance | rstd of the first layer (running-stat update). */
 int aopt_pe_mlp_stats(int c, const void *state, float *stats_out, aopt_stream_t stream);
 /* Parameter gradients for grad (rows,c) = dL/dpeb.  One pass over grad; deterministic (no atomics). */
@@ -186,7 +190,8 @@ size_t aopt_pe_mlp_backward_workspace_bytes(int64_t rows, int c);
 int aopt_pe_mlp_backward(int64_t rows, int c, const float *pos, const double *moments, const float *w1,
                          const float *gamma, int use_batch_stats, const float *grad, const void *state,
                          float *grad_w1, float *grad_b1, float *grad_gamma, float *grad_beta, float *grad_w2,
-                         float *grad_b2, void *workspace, size_t workspace_bytes, aopt_stream_t stream);
+                         float *grad_b2, int ga, const float *grad_aux, float *grad_aux_w, void *workspace,
+                         size_t workspace_bytes, aopt_stream_t stream);
 
 /* ---- PTv1-layout fused ops kept for API parity --------------------------------------------- */
 /* output[n,ch] = sum_s (input[idx[n,s],ch] + position[n,s,ch]) * weight[n,s,ch % w_c]. */

@@ -91,6 +91,38 @@ def test_pe_mlp_eval_mode_uses_running_statistics(c):
         assert rel_err(p_f.grad, p_r.grad) < 2e-2, name
 
 
+@pytest.mark.parametrize("c,ga", [(48, 6), (96, 12), (48, 16), (96, 1)])
+def test_pe_mlp_aux_head_is_a_linear_on_peb(c, ga):
+    """aux = h @ Wf^T with Wf = L.weight @ W2  ==  L(peb) - L.weight @ b2 - L.bias, forward and backward."""
+    from ao_b200 import pointops
+
+    torch.manual_seed(7 + ga)
+    pos = 0.2 * torch.randn(1203, 16, 3, device="cuda")
+    ref = make_mlp(c, 4).train()
+    lin_ref = nn.Linear(c, ga).cuda()
+    fused, lin_f = copy.deepcopy(ref).train(), copy.deepcopy(lin_ref)
+    peb_ref = ref(pos)
+    u_ref = lin_ref(peb_ref)
+    wf = lin_f.weight @ fused[3].weight
+    peb, aux = pointops.pe_bias_mlp(pos, fused, aux_weight=wf)
+    u = aux + (lin_f.weight @ fused[3].bias + lin_f.bias)
+    assert aux.shape == (1203, 16, ga)
+    assert rel_err(peb, peb_ref) < 2e-2 and rel_err(u, u_ref) < 2e-2
+    g_p, g_u = torch.randn_like(peb_ref), torch.randn_like(u_ref)
+    (peb_ref * g_p).sum().add((u_ref * g_u).sum()).backward()
+    (peb * g_p).sum().add((u * g_u).sum()).backward()
+    for (name, p_r), (_, p_f) in zip(list(ref.named_parameters()) + list(lin_ref.named_parameters()),
+                                     list(fused.named_parameters()) + list(lin_f.named_parameters())):
+        if name == "0.bias":
+            continue
+        assert rel_err(p_f.grad, p_r.grad) < 2e-2, name
+    # only one of the two outputs used downstream
+    fused.zero_grad()
+    peb2, aux2 = pointops.pe_bias_mlp(pos, fused, aux_weight=wf.detach())
+    (aux2 * g_u).sum().backward()
+    assert fused[3].weight.grad is not None and torch.isfinite(fused[3].weight.grad).all()
+
+
 def test_pos_moments_against_float64():
     from ao_b200 import pointops
 

@@ -31,6 +31,7 @@
 #include <initializer_list>
 
 #include "common.cuh"
+#include "csr_walk.cuh"
 
 namespace aopt {
 
@@ -397,6 +398,35 @@ gva_backward_value_kernel(long long n_src, int k, int kshift, int c, int g, cons
     }
 }
 
+// csr_walk.cuh policy: entry p = flat (query, slot); gathers grad_out[query] (re-used by the k sources of a
+// query: read-only path, L1-allocating) and the probability of (query, slot, group of the chunk).
+template <int GL>
+struct BvPolicy {
+    const float *grad_out, *prob;
+    int c, g, k, kshift;
+    static constexpr bool kWeighted = true;
+    __device__ __forceinline__ float4 load(int p, int ch) const {
+        const int q = kshift >= 0 ? (p >> kshift) : (p / k);
+        return ldg_gather4(grad_out + (size_t)q * c + ch * 4);
+    }
+    __device__ __forceinline__ float weight(int p, int ch) const { return __ldg(prob + (size_t)p * g + ch / GL); }
+};
+
+template <int GL>
+static void launch_bv_walk(long long n_src, int k, int c, int g, const float *grad_out, const float *prob,
+                           const int *rowptr, const int *perm, float *grad_value, cudaStream_t st) {
+    const int chunks = c / 4;
+    const BvPolicy<GL> pol{grad_out, prob, c, g, k, 0};
+    BvPolicy<GL> p2 = pol;
+    int sh = -1;
+    for (int b = 0; b < 31; ++b) if ((1 << b) == k) sh = b;
+    p2.kshift = sh;
+    if (walk_batch() == 4)
+        csr_walk_kernel<4, BvPolicy<GL>><<<walk_grid(n_src, chunks, 12), kWalkBlock, 0, st>>>(n_src, chunks, c, rowptr, perm, p2, 1.f, grad_value);
+    else
+        csr_walk_kernel<8, BvPolicy<GL>><<<walk_grid(n_src, chunks, 12), kWalkBlock, 0, st>>>(n_src, chunks, c, rowptr, perm, p2, 1.f, grad_value);
+}
+
 // Four entries at a time with plain loads (tuning alternative, AOPT_BV_IMPL=unroll4).
 template <int GL>
 __global__ void __launch_bounds__(kGvaBlock)
@@ -668,6 +698,12 @@ extern "C" int aopt_gva_backward_value(int n_src, int nsample, int c, int g, con
     if (!grad_out || !prob || !rowptr || !perm || !grad_value) return AOPT_ERR_INVALID_ARGUMENT;
     const int I = c / g;
     const int gl = pick_gl(c, I, {grad_out, grad_value});
+    if (gl > 0 && use_batched_walk()) {
+        if (gl == 1) launch_bv_walk<1>(n_src, nsample, c, g, grad_out, prob, rowptr, perm, grad_value, as_stream(stream));
+        else if (gl == 2) launch_bv_walk<2>(n_src, nsample, c, g, grad_out, prob, rowptr, perm, grad_value, as_stream(stream));
+        else launch_bv_walk<4>(n_src, nsample, c, g, grad_out, prob, rowptr, perm, grad_value, as_stream(stream));
+        return check_launch();
+    }
     if (gl > 0) {
         // Measured at L0: unroll4 166 us, batch8 + cp.async 221 us (the row walk is bound by L2 gather
         // bandwidth — ~1.1 GB of grad_out rows per launch — not by latency).  AOPT_BV_IMPL=batch opts in.

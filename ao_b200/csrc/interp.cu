@@ -7,6 +7,7 @@
 //
 // Bytes: forward 24·Nf + 4·Nc·C + 4·Nf·C; backward 4·Nf·C + 36·Nf + 4(Nc+1) + 4·Nc·C.
 #include "common.cuh"
+#include "csr_walk.cuh"
 
 namespace aopt {
 
@@ -75,6 +76,17 @@ interp_backward_kernel(long long m, int chunks, int c, int k, const float *__res
     }
 }
 
+// csr_walk.cuh policy: entry p = flat (fine row, slot); weight[p] * grad_output[p / k].
+struct InterpBwdPolicy {
+    const float *grad_output, *wgt;
+    int c, k;
+    static constexpr bool kWeighted = true;
+    __device__ __forceinline__ float4 load(int p, int ch) const {
+        return ldg_gather4(grad_output + (size_t)(p / k) * c + ch * 4);
+    }
+    __device__ __forceinline__ float weight(int p, int) const { return __ldg(wgt + p); }
+};
+
 }  // namespace aopt
 
 using namespace aopt;
@@ -111,7 +123,16 @@ extern "C" int aopt_interpolation_backward(int m, int c, int k, const float *gra
     if (m == 0) return AOPT_OK;
     if (!grad_output || !weight || !rowptr || !perm || !grad_input) return AOPT_ERR_INVALID_ARGUMENT;
     const bool vec = (c % 4 == 0) && aligned16(grad_output) && aligned16(grad_input);
-    if (vec) {
+    if (vec && use_batched_walk()) {
+        const int chunks = c / 4;
+        const InterpBwdPolicy pol{grad_output, weight, c, k};
+        if (walk_batch() == 4)
+            csr_walk_kernel<4, InterpBwdPolicy><<<walk_grid(m, chunks, 12), kWalkBlock, 0, as_stream(stream)>>>(
+                m, chunks, c, rowptr, perm, pol, 1.f, grad_input);
+        else
+            csr_walk_kernel<8, InterpBwdPolicy><<<walk_grid(m, chunks, 12), kWalkBlock, 0, as_stream(stream)>>>(
+                m, chunks, c, rowptr, perm, pol, 1.f, grad_input);
+    } else if (vec) {
         const int chunks = c / 4;
         interp_backward_kernel<4><<<stride_grid((long long)m * chunks, kInterpBlock, 8), kInterpBlock, 0, as_stream(stream)>>>(
             m, chunks, c, k, grad_output, weight, rowptr, perm, grad_input);

@@ -30,6 +30,7 @@ SIGNATURES = {
     "aopt_offset2batch": (c_int, [c_int, c_int, P, P, P]),
     "aopt_knn_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "aopt_knn_query": (c_int, [c_int, c_int, c_int, c_int, P, P, P, P, P, P, c_int, P, c_size_t, P]),
+    "aopt_farthest_point_sampling": (c_int, [c_int, c_int, P, P, P, P, P, P]),
     "aopt_csr_workspace_bytes": (c_size_t, [c_int, c_int64]),
     "aopt_csr_build": (c_int, [c_int, c_int64, P, c_int, P, P, P, c_size_t, P]),
     "aopt_grouping_forward": (c_int, [c_int, c_int, c_int, P, P, P, c_int, P]),

@@ -161,6 +161,19 @@ def aggregation_backward_cuda(n, nsample, c, w_c, input, position, weight, idx, 
     grad_weight.add_(gw)
 
 
+def farthest_point_sampling_cuda(b, n, xyz, offset, new_offset, tmp, idx):
+    """sampling/sampling_cuda.cpp: b scenes, n = the largest scene, tmp (total points) pre-filled with 1e10,
+    idx (new_offset[-1]) int32 output."""
+    lib = _lib.load()
+    _f(xyz, "xyz"), _i(offset, "offset"), _i(new_offset, "new_offset"), _f(tmp, "tmp"), _i(idx, "idx")
+    if idx.numel() == 0:
+        return
+    with torch.cuda.device(xyz.device):
+        _lib.check(lib.aopt_farthest_point_sampling(int(b), int(n), _lib.ptr(xyz), _lib.ptr(offset), _lib.ptr(new_offset),
+                                                    _lib.ptr(tmp), _lib.ptr(idx), _lib.stream()),
+                   "farthest_point_sampling_cuda")
+
+
 def _not_built(name):
     def f(*args, **kwargs):
         raise NotImplementedError(f"pointops._C.{name}: outside the PTv2m2 hot path (SURVEY.md §8), not built")
@@ -170,7 +183,6 @@ def _not_built(name):
 
 ball_query_cuda = _not_built("ball_query_cuda")
 random_ball_query_cuda = _not_built("random_ball_query_cuda")
-farthest_point_sampling_cuda = _not_built("farthest_point_sampling_cuda")
 attention_relation_step_forward_cuda = _not_built("attention_relation_step_forward_cuda")
 attention_relation_step_backward_cuda = _not_built("attention_relation_step_backward_cuda")
 attention_fusion_step_forward_cuda = _not_built("attention_fusion_step_forward_cuda")

@@ -19,6 +19,7 @@
  *   aopt_grouping_backward       grouping/grouping_cuda_kernel.h:15     grouping_backward_cuda_launcher
  *   aopt_interpolation_forward   interpolation/interpolation_cuda_kernel.h  interpolation_forward_cuda_launcher
  *   aopt_interpolation_backward  interpolation/interpolation_cuda_kernel.h  interpolation_backward_cuda_launcher
+ *   aopt_farthest_point_sampling sampling/sampling_cuda_kernel.h        farthest_point_sampling_cuda_launcher
  *   aopt_aggregation_forward/backward   aggregation/aggregation_cuda_kernel.h   (PTv1 "share-planes" layout)
  *   aopt_subtraction_forward/backward   subtraction/subtraction_cuda_kernel.h
  * and the torch / third-party op chains of the PTv2m2 caller
@@ -75,6 +76,16 @@ size_t aopt_knn_workspace_bytes(int n, int m, int b, int nsample, int method);
 int aopt_knn_query(int m, int nsample, int n, int b, const float *xyz, const float *new_xyz,
                    const int *offset, const int *new_offset, int *idx, float *dist2, int method,
                    void *workspace, size_t workspace_bytes, aopt_stream_t stream);
+
+/* ---- farthest point sampling (PTv1 caller: point_transformer_seg.py:101) --------------------- */
+/* Arguments of farthest_point_sampling_cuda_launcher (sampling/sampling_cuda_kernel.h): b scenes,
+ * n_max = size of the largest scene, xyz (n,3), offset / new_offset (b) cumulative ends, tmp (n)
+ * running squared distances pre-filled with 1e10 by the caller (functions/sampling.py:19), idx
+ * (new_offset[b-1]) output: idx[new_offset[s-1]] = first point of scene s, then repeatedly the point
+ * farthest from everything chosen so far.  Same results as the reference kernel for every input,
+ * equal-distance ties included (fps.cu header).  One thread-block cluster per scene. */
+int aopt_farthest_point_sampling(int b, int n_max, const float *xyz, const int *offset,
+                                 const int *new_offset, float *tmp, int *idx, aopt_stream_t stream);
 
 /* ---- transposed neighbour graph (CSR) ------------------------------------------------------ */
 /* idx: n_entries int32 values in [-1, n_src) (flattened (m,nsample)).  Produces rowptr (n_src+1)

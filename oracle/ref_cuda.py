@@ -29,7 +29,8 @@ def lib():
         for name in ("knn_query_cuda_launcher", "grouping_forward_cuda_launcher", "grouping_backward_cuda_launcher",
                      "interpolation_forward_cuda_launcher", "interpolation_backward_cuda_launcher",
                      "aggregation_forward_cuda_launcher", "aggregation_backward_cuda_launcher",
-                     "subtraction_forward_cuda_launcher", "subtraction_backward_cuda_launcher"):
+                     "subtraction_forward_cuda_launcher", "subtraction_backward_cuda_launcher",
+                     "farthest_point_sampling_cuda_launcher"):
             getattr(_lib, name).restype = None
     return _lib
 
@@ -138,3 +139,18 @@ def subtraction_backward(idx, grad_out, n2):
                                              _p(g1), _p(g2))
     torch.cuda.synchronize()
     return g1, g2
+
+
+def farthest_point_sampling(xyz, offset, new_offset):
+    """FarthestPointSampling.forward (libs/pointops/functions/sampling.py:9-24) through the reference launcher."""
+    off, noff = offset.int().contiguous(), new_offset.int().contiguous()
+    b = off.numel()
+    sizes = torch.diff(off, prepend=off.new_zeros(1))
+    n_max = int(sizes.max().item())
+    idx = torch.zeros(int(noff[-1].item()), dtype=torch.int32, device=xyz.device)
+    tmp = torch.full((xyz.shape[0],), 1e10, dtype=torch.float32, device=xyz.device)
+    torch.cuda.synchronize()
+    lib().farthest_point_sampling_cuda_launcher(ctypes.c_int(b), ctypes.c_int(n_max), _p(xyz), _p(off), _p(noff),
+                                                _p(tmp), _p(idx))
+    torch.cuda.synchronize()
+    return idx, tmp

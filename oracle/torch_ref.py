@@ -51,6 +51,8 @@ def _oracle_lib() -> ctypes.CDLL:
             fn.restype = i
         lib.knn_oracle_lex_range.argtypes = [i, i, i, p, p, p, p, p, p]
         lib.knn_oracle_lex_range.restype = i
+        lib.fps_oracle.argtypes = [i, i, p, p, p, p, p]
+        lib.fps_oracle.restype = i
         _LIB = lib
     return _LIB
 
@@ -65,6 +67,24 @@ def _npi(t) -> np.ndarray:
     if isinstance(t, torch.Tensor):
         t = t.detach().cpu().numpy()
     return np.ascontiguousarray(t, dtype=np.int32)
+
+
+def farthest_point_sampling(xyz, offset, new_offset) -> np.ndarray:
+    """FarthestPointSampling.forward (libs/pointops/functions/sampling.py:9-24) on the CPU through
+    oracle/fps_oracle.c (thread-by-thread emulation of sampling_cuda_kernel.cu).  Returns idx (m,) int32."""
+    x, off, noff = _np32(xyz), _npi(offset), _npi(new_offset)
+    b = off.shape[0]
+    if b == 0:
+        return np.zeros(0, np.int32)
+    sizes = np.diff(np.concatenate([[0], off]))
+    n_max = int(sizes.max())                                  # sampling.py:15-17
+    idx = np.zeros(int(noff[-1]), np.int32)                   # sampling.py:18
+    tmp = np.full(x.shape[0], 1e10, np.float32)               # sampling.py:19
+    rc = _oracle_lib().fps_oracle(b, n_max, x.ctypes.data, off.ctypes.data, noff.ctypes.data, tmp.ctypes.data,
+                                  idx.ctypes.data)
+    if rc != 0:
+        raise RuntimeError("fps_oracle failed")
+    return idx
 
 
 def knn_query(nsample, xyz, offset, new_xyz=None, new_offset=None, rule: str = "lex",

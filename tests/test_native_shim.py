@@ -13,8 +13,8 @@ from helpers import assert_knn_equal, to_cuda
 REF_FUNCTIONS = "/root/reference/libs/pointops/functions"
 HOT = ["knn_query_cuda", "grouping_forward_cuda", "grouping_backward_cuda", "interpolation_forward_cuda",
        "interpolation_backward_cuda", "subtraction_forward_cuda", "subtraction_backward_cuda",
-       "aggregation_forward_cuda", "aggregation_backward_cuda"]
-COLD = ["ball_query_cuda", "random_ball_query_cuda", "farthest_point_sampling_cuda",
+       "aggregation_forward_cuda", "aggregation_backward_cuda", "farthest_point_sampling_cuda"]
+COLD = ["ball_query_cuda", "random_ball_query_cuda",
         "attention_relation_step_forward_cuda", "attention_relation_step_backward_cuda",
         "attention_fusion_step_forward_cuda", "attention_fusion_step_backward_cuda"]
 

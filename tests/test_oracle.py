@@ -193,3 +193,57 @@ def test_knn_oracle_pinned_by_reference_cuda_outputs(oracle, case):
     il, dl = oracle.knn_query(k, xyz, off, q, qoff, rule="lex")
     n_perm = assert_knn_equal(il, dl, ref_idx, ref_d2, allow_tie_perm=True)
     assert n_perm <= int(tie_rows(ref_d2).sum())
+
+
+def _load_fps_golden_module():
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("make_fps_golden_gpu", os.path.join(GOLD, "make_fps_golden_gpu.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_fps_oracle_matches_bruteforce_on_tie_free_data(oracle):
+    """oracle/fps_oracle.c (thread-by-thread emulation of sampling_cuda_kernel.cu) against the textbook
+    definition: next sample = arg-max of the running minimum distance (continuous data, no ties)."""
+    rng = np.random.default_rng(3)
+    xyz = rng.random((1500, 3)).astype(np.float32)
+    off = np.array([1100, 1500], np.int32)
+    noff = np.array([200, 260], np.int32)
+    idx = oracle.farthest_point_sampling(xyz, off, noff)
+    s = 0
+    for e, (ms, me) in zip(off, [(0, 200), (200, 260)]):
+        pts = xyz[s:e].astype(np.float64)
+        t = np.full(len(pts), np.inf)
+        cur = 0
+        for j in range(ms, me):
+            assert idx[j] == s + cur
+            t = np.minimum(t, ((pts - pts[cur]) ** 2).sum(1))
+            cur = int(t.argmax())
+        s = e
+
+
+def test_fps_oracle_tie_rule(oracle):
+    """Equal maxima: the reference thread layout decides (block = 2^floor(log2 n_max), thread tid scans
+    k = tid, tid + block, ...; the tree merges slot s with s + h, h = block/2 .. 1, keeping the lower slot on
+    equal values): the winner has the smallest (bit-reversed k mod block, k)."""
+    # 6 points, block = 4: point 0 is the seed; points 1..5 are all at distance 1 from it.
+    xyz = np.array([[0, 0, 0], [1, 0, 0], [-1, 0, 0], [0, 1, 0], [0, -1, 0], [0, 0, 1]], np.float32)
+    idx = oracle.farthest_point_sampling(xyz, np.array([6], np.int32), np.array([3], np.int32))
+    # k mod 4: 1->1, 2->2, 3->3, 4->0, 5->1  => point 4 (thread 0) wins the first tie
+    assert idx.tolist()[:2] == [0, 4]
+    # 4 points, block = 4, points 1..3 tied: threads 1, 2, 3 bit-reverse to 2, 1, 3 => point 2 wins, not point 1
+    idx = oracle.farthest_point_sampling(xyz[:4].copy(), np.array([4], np.int32), np.array([2], np.int32))
+    assert idx.tolist() == [0, 2]
+
+
+@pytest.mark.parametrize("case", ["small_s4", "small_dup_s2", "small_all", "room_s4", "room_s16"])
+def test_fps_oracle_pinned_by_reference_cuda_outputs(oracle, case):
+    """tests/golden/fps_ref_cuda.npz: idx / final tmp written by the UNMODIFIED reference launcher on a B200."""
+    path = os.path.join(GOLD, "fps_ref_cuda.npz")
+    if not os.path.exists(path):
+        pytest.skip("golden file not generated yet (tests/golden/make_fps_golden_gpu.py on the GPU box)")
+    g = np.load(path)
+    xyz, off, noff = _load_fps_golden_module().inputs(case)
+    assert np.array_equal(oracle.farthest_point_sampling(xyz, off, noff), g[case + "_idx"])

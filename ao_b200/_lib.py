@@ -12,7 +12,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_ulonglong, c_void_p
+from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_longlong, c_size_t, c_ulonglong, c_void_p
 
 import torch
 
@@ -31,6 +31,10 @@ SIGNATURES = {
     "aopt_knn_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "aopt_knn_query": (c_int, [c_int, c_int, c_int, c_int, P, P, P, P, P, P, c_int, P, c_size_t, P]),
     "aopt_farthest_point_sampling": (c_int, [c_int, c_int, P, P, P, P, P, P]),
+    "aopt_grid_sample_keys": (c_int, [c_int, P, c_double, c_double, c_double, c_int, c_int, P, P, P, P]),
+    "aopt_voxel_pick": (c_int, [c_int, P, P, P, c_longlong, P, P]),
+    "aopt_sphere_dist2": (c_int, [c_int, P, c_float, c_float, c_float, P, P]),
+    "aopt_select_rows": (c_int, [c_longlong, c_int, P, P, P, P]),
     "aopt_csr_workspace_bytes": (c_size_t, [c_int, c_int64]),
     "aopt_csr_build": (c_int, [c_int, c_int64, P, c_int, P, P, P, c_size_t, P]),
     "aopt_grouping_forward": (c_int, [c_int, c_int, c_int, P, P, P, c_int, P]),

@@ -28,6 +28,8 @@
  *   aopt_gva_*                            :119-128   (softmax over k, mask, grouped weighted sum)
  *   aopt_voxel_*, aopt_pool_*             :244-269   (voxel_grid + segment_csr mean/max)
  *   aopt_interp_weights                   libs/pointops/functions/interpolation.py:15-17
+ *   aopt_grid_sample_keys, aopt_voxel_pick, aopt_sphere_dist2, aopt_select_rows
+ *                                         pointcept/datasets/transform.py:792-896,968-979 (GridSample, SphereCrop)
  *   aopt_csr_build                        (new) transpose of the neighbour graph → atomic-free backward
  */
 #ifndef AO_POINTOPS_H_
@@ -86,6 +88,26 @@ int aopt_knn_query(int m, int nsample, int n, int b, const float *xyz, const flo
  * equal-distance ties included (fps.cu header).  One thread-block cluster per scene. */
 int aopt_farthest_point_sampling(int b, int n_max, const float *xyz, const int *offset,
                                  const int *new_offset, float *tmp, int *idx, aopt_stream_t stream);
+
+/* ---- per-sample data transforms (pointcept/datasets/transform.py) ------------- */
+/* GridSample front half (transform.py:806-811): cell = floor(coord / grid) per axis (f64 != 0: fp64
+ * division as NumPy >= 2 evaluates `fp32 array / np.array(float)`; 0: fp32 as NumPy 1.x did), minus the
+ * per-axis minimum; keys = hash(cell) ^ 2^63 (hash_type 0 = FNV64-1A :881-896, 1 = ravel :864-878) so that
+ * an int64 sort orders like the reference's uint64 argsort.  stats[0..2] = per-axis minimum of
+ * floor(coord / grid) (min_coord = stats * grid, :808), stats[3..5] = maximum. */
+int aopt_grid_sample_keys(int n, const float *coord, double grid_x, double grid_y, double grid_z,
+                          int f64, int hash_type, int *cell, int64_t *keys, int *stats,
+                          aopt_stream_t stream);
+/* pick[v] = order[idx_ptr[v] + r[v] % count[v]] (transform.py:813-817; r == NULL: r_const for every
+ * voxel = test mode part number, :841-843).  order / idx_ptr from aopt_voxel_partition. */
+int aopt_voxel_pick(int n_vox, const int *idx_ptr, const int *order, const int64_t *r,
+                    long long r_const, int64_t *pick, aopt_stream_t stream);
+/* SphereCrop (transform.py:973-975): dist2[i] = sum(square(coord[i] - centre)) in fp32, numpy's order. */
+int aopt_sphere_dist2(int n, const float *coord, float cx, float cy, float cz, float *dist2,
+                      aopt_stream_t stream);
+/* out[i, :] = src[index[i], :] for rows of `words_per_row` 4-byte words (data_dict[key][idx], any dtype). */
+int aopt_select_rows(long long rows, int words_per_row, const void *src, const int64_t *index,
+                     void *out, aopt_stream_t stream);
 
 /* ---- transposed neighbour graph (CSR) ------------------------------------------------------ */
 /* idx: n_entries int32 values in [-1, n_src) (flattened (m,nsample)).  Produces rowptr (n_src+1)

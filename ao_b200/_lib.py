@@ -39,6 +39,7 @@ SIGNATURES = {
     "aopt_csr_build": (c_int, [c_int, c_int64, P, c_int, P, P, P, c_size_t, P]),
     "aopt_grouping_forward": (c_int, [c_int, c_int, c_int, P, P, P, c_int, P]),
     "aopt_grouping_backward": (c_int, [c_int, c_int, P, c_int, P, P, c_float, P, P]),
+    "aopt_relation_backward": (c_int, [c_int, c_int, c_int, P, P, P, P, P, P]),
     "aopt_group_xyz": (c_int, [c_int, c_int, P, P, P, P, c_int, P]),
     "aopt_gather_sub_forward": (c_int, [c_int, c_int, c_int, P, P, P, P, P]),
     "aopt_sum_over_k": (c_int, [c_int, c_int, c_int, P, c_float, P, P]),

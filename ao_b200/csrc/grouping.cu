@@ -219,6 +219,113 @@ sum_over_k_kernel(long long m, int nsample, int chunks, int c, const float *__re
     }
 }
 
+// Backward of relation = key[idx] - query[:, None] over ONE point set (queries == sources, the GVA case):
+//   grad_query[j] = -sum_s grad[j, s, :]          (the k rows of query j: 16 x C contiguous floats)
+//   grad_key[j]   =  sum_{e in row j} grad[perm[e]] (the rows that gathered j)
+// segmented_sum_kernel + sum_over_k_kernel read the (N,k,C) gradient twice from HBM (2 x 983 MB at level 0).
+// Fused, every row is still read twice, but the two reads fall close together in time: neighbours are close
+// in index (median |i - j| = 559, 90 % < 1643 in S3DIS order, profiles/r01h_bv_locality.md) and a grid-stride
+// loop moves the whole chip through one compact window of rows, so the second read of a row hits L2.
+// The grid is kept small (ctas_per_sm x 148 CTAs) to keep that window a fraction of the 126 MB L2.
+template <int VEC>
+__global__ void __launch_bounds__(kBlock)
+relation_backward_kernel(long long n, int nsample, int chunks, int c, const float *__restrict__ grad,
+                         const int *__restrict__ rowptr, const int *__restrict__ perm,
+                         float *__restrict__ grad_key, float *__restrict__ grad_query) {
+    const long long total = n * chunks;
+    const long long step = (long long)gridDim.x * kBlock;
+    for (long long t = (long long)blockIdx.x * kBlock + threadIdx.x; t < total; t += step) {
+        RowCol rc = split(t, chunks);
+        int e = __ldg(rowptr + rc.row);
+        const int e_end = __ldg(rowptr + rc.row + 1);
+        // grad_query: the query's own k rows (streamed; brings them into L2 for the row walks nearby)
+        const float *own = grad + (size_t)rc.row * nsample * c + rc.col * VEC;
+        Chunk<VEC> accq = Chunk<VEC>::zero();
+        int s = 0;
+        for (; s + 4 <= nsample; s += 4) {
+            Chunk<VEC> a0 = Chunk<VEC>::stream(own + (size_t)(s + 0) * c);
+            Chunk<VEC> a1 = Chunk<VEC>::stream(own + (size_t)(s + 1) * c);
+            Chunk<VEC> a2 = Chunk<VEC>::stream(own + (size_t)(s + 2) * c);
+            Chunk<VEC> a3 = Chunk<VEC>::stream(own + (size_t)(s + 3) * c);
+            accq.add(a0); accq.add(a1); accq.add(a2); accq.add(a3);
+        }
+        for (; s < nsample; ++s) accq.add(Chunk<VEC>::stream(own + (size_t)s * c));
+        accq.scale(-1.0f);
+        accq.store(grad_query + (size_t)rc.row * c + rc.col * VEC);
+        // grad_key: in-edges in ascending flat position (same order as segmented_sum_kernel)
+        const float *base = grad + rc.col * VEC;
+        Chunk<VEC> acc = Chunk<VEC>::zero();
+        for (; e + 4 <= e_end; e += 4) {
+            int p0 = __ldg(perm + e), p1 = __ldg(perm + e + 1), p2 = __ldg(perm + e + 2), p3 = __ldg(perm + e + 3);
+            Chunk<VEC> a0 = Chunk<VEC>::stream(base + (size_t)p0 * c);
+            Chunk<VEC> a1 = Chunk<VEC>::stream(base + (size_t)p1 * c);
+            Chunk<VEC> a2 = Chunk<VEC>::stream(base + (size_t)p2 * c);
+            Chunk<VEC> a3 = Chunk<VEC>::stream(base + (size_t)p3 * c);
+            acc.add(a0); acc.add(a1); acc.add(a2); acc.add(a3);
+        }
+        for (; e < e_end; ++e) acc.add(Chunk<VEC>::stream(base + (size_t)__ldg(perm + e) * c));
+        acc.store(grad_key + (size_t)rc.row * c + rc.col * VEC);
+    }
+}
+
+// 128-bit path: per iteration a thread requests FOUR of its own rows and FOUR gathered rows at once with
+// cp.async (L2-only) into its own shared-memory slots — eight 16-byte requests in flight per thread without
+// holding registers (ptxas folds register-destination batches of this shape back into ~3 live loads) — and
+// prefetches the next four perm entries while they fly.  Slots past the end of either list re-request one of the
+// thread's own rows (an L2 hit) and are dropped by a select, so the summation orders are exactly those of
+// segmented_sum_kernel / sum_over_k_kernel.
+constexpr int kRelBlock = 256;
+
+__global__ void __launch_bounds__(kRelBlock)
+relation_backward_vec_kernel(long long n, int nsample, int chunks, int c, const float *__restrict__ grad,
+                             const int *__restrict__ rowptr, const int *__restrict__ perm,
+                             float *__restrict__ grad_key, float *__restrict__ grad_query) {
+    __shared__ float4 stage[8 * kRelBlock];
+    float4 *sg = stage + threadIdx.x;
+    const long long total = n * chunks;
+    const long long step = (long long)gridDim.x * kRelBlock;
+    for (long long t = (long long)blockIdx.x * kRelBlock + threadIdx.x; t < total; t += step) {
+        RowCol rc = split(t, chunks);
+        const int e0 = __ldg(rowptr + rc.row), e_end = __ldg(rowptr + rc.row + 1);
+        const long long own0 = rc.row * nsample;          // flat row of (query, slot 0)
+        const float *base = grad + rc.col * 4;
+        const int iters = max((nsample + 3) >> 2, (e_end - e0 + 3) >> 2);
+        long long pn[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) pn[u] = (e0 + u < e_end) ? (long long)__ldg(perm + e0 + u) : own0;
+        float4 accq = make_float4(0.f, 0.f, 0.f, 0.f), acck = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int it = 0; it < iters; ++it) {
+            const int s = it * 4, e = e0 + it * 4;
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                cp_async16_stream(sg + u * kRelBlock, base + (size_t)(own0 + min(s + u, nsample - 1)) * c);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) cp_async16_stream(sg + (4 + u) * kRelBlock, base + (size_t)pn[u] * c);
+            cp_async_commit();
+#pragma unroll
+            for (int u = 0; u < 4; ++u) pn[u] = (e + 4 + u < e_end) ? (long long)__ldg(perm + e + 4 + u) : own0;
+            cp_async_wait_all();
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float4 a = sg[u * kRelBlock];
+                const bool keep = s + u < nsample;
+                accq.x = keep ? accq.x + a.x : accq.x; accq.y = keep ? accq.y + a.y : accq.y;
+                accq.z = keep ? accq.z + a.z : accq.z; accq.w = keep ? accq.w + a.w : accq.w;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float4 g4 = sg[(4 + u) * kRelBlock];
+                const bool keep = e + u < e_end;
+                acck.x = keep ? acck.x + g4.x : acck.x; acck.y = keep ? acck.y + g4.y : acck.y;
+                acck.z = keep ? acck.z + g4.z : acck.z; acck.w = keep ? acck.w + g4.w : acck.w;
+            }
+        }
+        accq.x *= -1.0f; accq.y *= -1.0f; accq.z *= -1.0f; accq.w *= -1.0f;
+        *reinterpret_cast<float4 *>(grad_query + (size_t)rc.row * c + rc.col * 4) = accq;
+        *reinterpret_cast<float4 *>(grad_key + (size_t)rc.row * c + rc.col * 4) = acck;
+    }
+}
+
 // out[p, 0..2] = (xyz[idx[p]] - new_xyz[p / nsample]) * sign(idx[p] + 1)
 __global__ void __launch_bounds__(kBlock)
 group_xyz_kernel(long long rows, int nsample, const float *__restrict__ xyz,
@@ -314,6 +421,27 @@ extern "C" int aopt_grouping_backward(int n, int c, const float *grad_output, in
     } else {
         segmented_sum_kernel<1><<<stride_grid((long long)n * c, kBlock, 8), kBlock, 0, as_stream(stream)>>>(
             n, c, c, grad_output, go_stride, rowptr, perm, scale, grad_input);
+    }
+    return check_launch();
+}
+
+// grad (n,nsample,c) of relation = key[idx] - query[:,None] with queries == sources (n rows each):
+// grad_key (n,c) through the CSR of idx, grad_query (n,c) = -sum over the slots.  One pass (see kernel).
+extern "C" int aopt_relation_backward(int n, int nsample, int c, const float *grad, const int *rowptr,
+                                      const int *perm, float *grad_key, float *grad_query,
+                                      aopt_stream_t stream) {
+    if (n < 0 || nsample < 1 || c < 1) return AOPT_ERR_INVALID_ARGUMENT;
+    if (n == 0) return AOPT_OK;
+    if (!grad || !rowptr || !perm || !grad_key || !grad_query) return AOPT_ERR_INVALID_ARGUMENT;
+    static const int ctas = [] { const char *e = getenv("AOPT_RELBWD_CTAS"); int v = e ? atoi(e) : 0; return v >= 1 && v <= 8 ? v : 4; }();
+    const bool vec = (c % 4 == 0) && aligned16(grad) && aligned16(grad_key) && aligned16(grad_query);
+    if (vec) {
+        const int chunks = c / 4;
+        relation_backward_vec_kernel<<<stride_grid((long long)n * chunks, kRelBlock, ctas), kRelBlock, 0, as_stream(stream)>>>(
+            n, nsample, chunks, c, grad, rowptr, perm, grad_key, grad_query);
+    } else {
+        relation_backward_kernel<1><<<stride_grid((long long)n * c, kBlock, ctas), kBlock, 0, as_stream(stream)>>>(
+            n, nsample, c, c, grad, rowptr, perm, grad_key, grad_query);
     }
     return check_launch();
 }

@@ -19,6 +19,11 @@ from ._csr import get_csr
 from .grouping import _as_idx, _scatter
 
 
+import os
+
+_SPLIT_RELATION_BWD = os.environ.get("AOPT_RELBWD", "fused") == "split"   # A/B switch (measurements only)
+
+
 def group_xyz(idx, xyz, new_xyz=None):
     """(m,k,3) masked relative coordinates.  No gradient (coordinates are inputs)."""
     if new_xyz is None:
@@ -61,6 +66,18 @@ class _RelationFn(Function):
         n, m, k, c = ctx.shape
         grad = grad.contiguous().float()
         grad_key = grad_query = None
+        if ctx.needs_input_grad[0] and ctx.needs_input_grad[1] and m == n and m > 0 and not _SPLIT_RELATION_BWD:
+            # queries == sources: one pass over grad for both gradients (csrc/grouping.cu relation_backward_kernel)
+            csr = get_csr(ctx.idx, n, 0)
+            grad_key = torch.empty((n, c), dtype=torch.float32, device=grad.device)
+            grad_query = torch.empty((m, c), dtype=torch.float32, device=grad.device)
+            with torch.cuda.device(grad.device):
+                _lib.check(
+                    lib.aopt_relation_backward(n, k, c, _lib.ptr(grad), _lib.ptr(csr.rowptr), _lib.ptr(csr.perm),
+                                               _lib.ptr(grad_key), _lib.ptr(grad_query), _lib.stream()),
+                    "relation_backward",
+                )
+            return grad_key, grad_query, None
         if ctx.needs_input_grad[0]:
             grad_key = _scatter(grad, c, 0, get_csr(ctx.idx, n, 0), n, c)
         if ctx.needs_input_grad[1]:

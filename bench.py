@@ -121,6 +121,9 @@ def call_bytes(name, a, sizes, k):
     if name == "aopt_grouping_backward":          # relation backward: E = n*k entries
         n, c = a[0], a[1]
         return 4.0 * n * k * c + 4.0 * n * k + 4.0 * (n + 1) + 4.0 * n * c
+    if name == "aopt_relation_backward":          # one read of the (n,k,c) gradient, two (n,c) outputs
+        n, ns, c = a[0], a[1], a[2]
+        return 4.0 * n * ns * c + 4.0 * n * ns + 4.0 * (n + 1) + 8.0 * n * c
     if name == "aopt_sum_over_k":
         m, ns, c = a[0], a[1], a[2]
         return 4.0 * m * ns * c + 4.0 * m * c
@@ -158,6 +161,7 @@ def call_bytes(name, a, sizes, k):
 
 
 HBM_KERNELS = {"aopt_group_xyz", "aopt_gather_sub_forward", "aopt_grouping_forward", "aopt_grouping_backward",
+               "aopt_relation_backward",
                "aopt_sum_over_k", "aopt_gva_forward", "aopt_gva_backward_query", "aopt_gva_backward_value",
                "aopt_pool_forward", "aopt_pool_backward", "aopt_interpolation_forward",
                "aopt_interpolation_backward"}

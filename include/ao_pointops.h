@@ -125,6 +125,12 @@ int aopt_grouping_forward(int m, int nsample, int c, const float *input, const i
 /* grad_input[j,:] = scale * sum over CSR row j of grad_output[perm[e]*go_stride + :]  (no atomics). */
 int aopt_grouping_backward(int n, int c, const float *grad_output, int go_stride, const int *rowptr,
                            const int *perm, float scale, float *grad_input, aopt_stream_t stream);
+/* Backward of out[j,s,:] = key[idx[j,s],:] - query[j,:] when queries and sources are the same n points
+ * (GroupedVectorAttention, …v2m2_base.py:109,112): grad_key[j] = sum over CSR row j of grad rows,
+ * grad_query[j] = -sum_s grad[j,s,:], in ONE pass over grad (n,nsample,c): the second read of every row
+ * is served by L2.  Same summation orders as aopt_grouping_backward / aopt_sum_over_k. */
+int aopt_relation_backward(int n, int nsample, int c, const float *grad, const int *rowptr,
+                           const int *perm, float *grad_key, float *grad_query, aopt_stream_t stream);
 /* out[p*out_stride + 0..2] = (xyz[idx[p]] - new_xyz[p / nsample]) * sign(idx[p]+1). */
 int aopt_group_xyz(int m, int nsample, const float *xyz, const float *new_xyz, const int *idx,
                    float *out, int out_stride, aopt_stream_t stream);

@@ -88,6 +88,9 @@ for li in [int(x) for x in args.levels.split(",")]:
     row("segmented_sum (grad_key)", timeit(lambda: lib.aopt_grouping_backward(n, c, g_rel.data_ptr(), c, csr.rowptr.data_ptr(), csr.perm.data_ptr(), 1.0, gk.data_ptr(), _lib.stream())),
         4.0 * n * k * c + 4.0 * n * k + 4.0 * (n + 1) + 4.0 * n * c)
     row("sum_over_k (grad_query)", timeit(lambda: lib.aopt_sum_over_k(n, k, c, g_rel.data_ptr(), -1.0, gk.data_ptr(), _lib.stream())), 4.0 * n * k * c + 4.0 * n * c)
+    gq = torch.empty(n, c, device=dev)
+    row("relation_backward (fused pair)", timeit(lambda: lib.aopt_relation_backward(n, k, c, g_rel.data_ptr(), csr.rowptr.data_ptr(), csr.perm.data_ptr(), gk.data_ptr(), gq.data_ptr(), _lib.stream())),
+        4.0 * n * k * c + 4.0 * n * k + 4.0 * (n + 1) + 8.0 * n * c)
     out = torch.empty(n, c, device=dev)
     prob = torch.empty(n, k, g, device=dev)
     row("gva_forward", timeit(lambda: lib.aopt_gva_forward(n, k, c, g, value.data_ptr(), peb.data_ptr(), logits.data_ptr(), idx.data_ptr(), out.data_ptr(), prob.data_ptr(), _lib.stream())),

@@ -340,3 +340,31 @@ def test_non_default_stream_and_device_guard():
         gq = pointops.grouping(a, feat, xyz, with_xyz=True)
     s.synchronize()
     assert torch.equal(a, ref) and gq.shape == (xyz.shape[0], 8, 19)
+
+
+@pytest.mark.parametrize("c", [48, 7])
+def test_relation_backward_fused_equals_the_two_pass_kernels(c):
+    """aopt_relation_backward (one pass over the (n,k,c) gradient) gives bit-identical grad_key / grad_query to
+    aopt_grouping_backward + aopt_sum_over_k (same summation orders), -1 padded rows included."""
+    from ao_b200 import _lib, pointops, scenes
+
+    coord, _, off = scenes.small_batch(77, sizes=(900, 5, 1400))
+    xyz, o = to_cuda(coord, off)
+    n, k = xyz.shape[0], 16
+    idx, _ = pointops.knn_query(k, xyz, o)
+    assert int((idx < 0).sum()) > 0                              # the 5-point scene pads with -1
+    g = torch.Generator(device="cuda").manual_seed(c)
+    grad = torch.randn(n, k, c, device="cuda", generator=g)
+    csr = pointops.get_csr(idx, n)
+    lib = _lib.load()
+    gk1, gq1, gk2, gq2 = (torch.empty(n, c, device="cuda") for _ in range(4))
+    _lib.check(lib.aopt_grouping_backward(n, c, grad.data_ptr(), c, csr.rowptr.data_ptr(), csr.perm.data_ptr(), 1.0, gk1.data_ptr(), _lib.stream()), "a")
+    _lib.check(lib.aopt_sum_over_k(n, k, c, grad.data_ptr(), -1.0, gq1.data_ptr(), _lib.stream()), "b")
+    _lib.check(lib.aopt_relation_backward(n, k, c, grad.data_ptr(), csr.rowptr.data_ptr(), csr.perm.data_ptr(), gk2.data_ptr(), gq2.data_ptr(), _lib.stream()), "c")
+    assert torch.equal(gk1, gk2) and torch.equal(gq1, gq2)
+    ref = torch.zeros(n + 1, c, device="cuda", dtype=torch.float64).index_add_(0, torch.where(idx < 0, n, idx).reshape(-1).long(), grad.reshape(-1, c).double())[:n]
+    assert torch.allclose(gk2.double(), ref, rtol=1e-5, atol=1e-4)
+    # through autograd (pointops.gva_relation uses the fused call when queries == sources)
+    key, query = (torch.randn(n, c, device="cuda", generator=g, requires_grad=True) for _ in range(2))
+    a, b = torch.autograd.grad(pointops.gva_relation(key, query, idx), [key, query], grad)
+    assert torch.equal(a, gk2) and torch.equal(b, gq2)

@@ -16,7 +16,10 @@
 //   * the perm values of the NEXT batch — of this row or, on its last batch, of the thread's next row —
 //     are requested before the current batch is consumed;
 //   * rowptr of the row after next is requested one row ahead.
-// Measured at level 0 (320k x 16, C=48): gva_backward_value 162 -> 130 us with B = 8.
+// Measured at level 0 (320k x 16, C=48): gva_backward_value 162 -> 130 us with B = 8.  A cp.async-staged variant
+// of the same walk measured the same 125-180 us (it is the ~32 instructions per gathered 16 bytes — 48 % issue
+// slots, 67 % L1 — that bound it now), and taught one rule kept below: filler slots must not all read ONE line
+// through L2 (entry 0 for every thread via cp.async.cg: 740 us); here they go through L1-allocating loads.
 // The grid is sized so that gridDim.x * blockDim.x is a multiple of `chunks`: a thread keeps its channel
 // chunk for the whole kernel and only the row advances (no divisions in the loop).
 // Entries are accumulated in ascending e (perm is ascending inside a row): the summation order is the

@@ -104,7 +104,7 @@ gather_sub_rows_kernel(long long m, int k, int chunks, int c, const float *__res
 // DRAM/L2 latency is exposed once per item (NS·16 bytes of shared memory per thread).
 constexpr int kSubNsBlock = 128;
 
-template <int NS>
+template <int NS, bool CG>
 __global__ void __launch_bounds__(kSubNsBlock)
 gather_sub_ns_kernel(long long m, int chunks, int c, const float *__restrict__ key,
                      const float *__restrict__ query, const int *__restrict__ idx,
@@ -132,7 +132,10 @@ gather_sub_ns_kernel(long long m, int chunks, int c, const float *__restrict__ k
         for (int s = 0; s < NS; ++s) j[s] = jn[s];
         const float *kbase = key + col * 4;
 #pragma unroll
-        for (int s = 0; s < NS; ++s) cp_async16_gather(sv + s * kSubNsBlock, kbase + (size_t)max(j[s], 0) * c);
+        for (int s = 0; s < NS; ++s) {
+            if (CG) cp_async16_stream(sv + s * kSubNsBlock, kbase + (size_t)max(j[s], 0) * c);
+            else cp_async16_gather(sv + s * kSubNsBlock, kbase + (size_t)max(j[s], 0) * c);
+        }
         cp_async_commit();
         const float4 q = ldg_gather4(query + (size_t)row * c + col * 4);
         if (t + step < total) load_row((t + step) / chunks);
@@ -152,12 +155,19 @@ template <int NS>
 static void launch_gather_sub_ns(long long m, int chunks, int c, const float *key, const float *query,
                                  const int *idx, float *out, cudaStream_t st) {
     const size_t smem = (size_t)NS * 16 * kSubNsBlock;
-    static bool once = (cudaFuncSetAttribute(gather_sub_ns_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)smem), true);
+    static bool once = (cudaFuncSetAttribute(gather_sub_ns_kernel<NS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                        cudaFuncSetAttribute(gather_sub_ns_kernel<NS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), true);
     (void)once;
-    const int per_sm = NS <= 8 ? 12 : NS <= 16 ? 6 : 3;
-    gather_sub_ns_kernel<NS><<<stride_grid(m * chunks, kSubNsBlock, per_sm), kSubNsBlock, smem, st>>>(
-        m, chunks, c, key, query, idx, out);
+    // Measured at level 0 (NS = 16): L2-only copies (.cg) 204 us at 3 CTAs/SM, 235 at 4, 247 at 8; L1-allocating
+    // copies (.ca) 298-329 us (the 61 MB of key rows thrash L1 in S3DIS point order); rows kernel 253 us.
+    int per_sm = NS <= 8 ? 6 : NS <= 16 ? 3 : 2;
+    static const int env_ctas = [] { const char *e = getenv("AOPT_GATHER_SUB_CTAS"); return e ? atoi(e) : 0; }();
+    static const bool cg = [] { const char *e = getenv("AOPT_GATHER_SUB_CG"); return !(e && e[0] == '0'); }();
+    if (env_ctas >= 1 && env_ctas <= 16) per_sm = env_ctas;
+    if (cg)
+        gather_sub_ns_kernel<NS, true><<<stride_grid(m * chunks, kSubNsBlock, per_sm), kSubNsBlock, smem, st>>>(m, chunks, c, key, query, idx, out);
+    else
+        gather_sub_ns_kernel<NS, false><<<stride_grid(m * chunks, kSubNsBlock, per_sm), kSubNsBlock, smem, st>>>(m, chunks, c, key, query, idx, out);
 }
 
 // grad_in[j, :] = scale * sum_{e in row j} grad_out[perm[e], :]   — one thread per (source row,
@@ -473,9 +483,9 @@ extern "C" int aopt_gather_sub_forward(int m, int nsample, int c, const float *k
     bool vec = (c % 4 == 0) && aligned16(key) && aligned16(query) && aligned16(out);
     if (vec) {
         int chunks = c / 4;
-        // Measured at L0 (320k x 16 x 48, unsorted S3DIS order): rows kernel 256 us, cp.async NS kernel 327 us
-        // (234 us when the points are Morton-ordered).  Default = rows; AOPT_GATHER_SUB_IMPL=ns opts in.
-        static const bool use_ns = [] { const char *e = getenv("AOPT_GATHER_SUB_IMPL"); return e && e[0] == 'n'; }();
+        // Default = the cp.async NS kernel with L2-only copies (see launch_gather_sub_ns for the measurements);
+        // AOPT_GATHER_SUB_IMPL=rows selects the register kernel (also used for other neighbour counts).
+        static const bool use_ns = [] { const char *e = getenv("AOPT_GATHER_SUB_IMPL"); return !(e && e[0] == 'r'); }();
         const bool ns_ok = aligned16(idx) && use_ns;
         if (ns_ok && nsample == 16) launch_gather_sub_ns<16>(m, chunks, c, key, query, idx, out, as_stream(stream));
         else if (ns_ok && nsample == 8) launch_gather_sub_ns<8>(m, chunks, c, key, query, idx, out, as_stream(stream));

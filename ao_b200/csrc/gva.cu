@@ -127,6 +127,16 @@ gva_forward_kernel(long long n, int k, int c, int g, const float *__restrict__ v
 // One latency window per item instead of nine; 2·NS·16 bytes of shared memory per thread.
 constexpr int kGvaNsBlock = 128;
 
+// Gathered value rows.  Measured at level 0 on one box (A/B in the same process): forward 232 us with L2-only
+// copies (.cg) vs 244 us with L1-allocating ones (.ca); backward_query 399 us (.cg) vs 368 us (.ca).  Defaults
+// follow that; AOPT_GVA_GATHER=<fwd><bwd> with letters g / a overrides (e.g. "gg", "aa").
+__constant__ int g_gva_gather_ca = 2;   // bit 0: forward uses .ca, bit 1: backward_query uses .ca
+template <int WHICH>
+__device__ __forceinline__ void cp_async16_row(float4 *dst, const float *src) {
+    if (g_gva_gather_ca & WHICH) cp_async16_gather(dst, src);
+    else cp_async16_stream(dst, src);
+}
+
 __device__ __forceinline__ void load_idx_row16(const int *__restrict__ row, int *j, int count4) {
     const int4 *r4 = reinterpret_cast<const int4 *>(row);
 #pragma unroll
@@ -162,7 +172,7 @@ gva_forward_ns_kernel(long long n, int c, int g, const float *__restrict__ value
         for (int s = 0; s < NS; ++s) j[s] = jn[s];
         const float *vbase = value + ch * 4;
 #pragma unroll
-        for (int s = 0; s < NS; ++s) cp_async16_gather(sv + s * kGvaNsBlock, vbase + (size_t)max(j[s], 0) * c);
+        for (int s = 0; s < NS; ++s) cp_async16_row<1>(sv + s * kGvaNsBlock, vbase + (size_t)max(j[s], 0) * c);
         if (HAS_PEB) {
             const float *pe = peb + (size_t)pt * NS * c + ch * 4;
 #pragma unroll
@@ -309,7 +319,7 @@ gva_backward_query_ns_kernel(long long n, int c, int g, const float *__restrict_
         for (int s = 0; s < NS; ++s) j[s] = jn[s];
         const float *vbase = value + ch * 4;
 #pragma unroll
-        for (int s = 0; s < NS; ++s) cp_async16_gather(sv + s * kGvaNsBlock, vbase + (size_t)max(j[s], 0) * c);
+        for (int s = 0; s < NS; ++s) cp_async16_row<2>(sv + s * kGvaNsBlock, vbase + (size_t)max(j[s], 0) * c);
         if (HAS_PEB) {
             const float *pe = peb + (size_t)pt * NS * c + ch * 4;
 #pragma unroll
@@ -584,7 +594,20 @@ using namespace aopt;
 
 // Grid of the NS kernels: GRID here is the work-item count; resident CTAs per SM follow from the
 // 2·NS·16·128 bytes of shared memory each CTA needs (227 KB per SM).
-static int ns_grid(long long items, int ns) { return stride_grid(items, kGvaNsBlock, ns <= 8 ? 6 : ns <= 16 ? 3 : 1); }
+static void gva_gather_mode_init() {
+    static const bool once = [] {
+        const char *e = getenv("AOPT_GVA_GATHER");
+        if (e && e[0] && e[1]) {
+            const int ca = (e[0] == 'a' ? 1 : 0) | (e[1] == 'a' ? 2 : 0);
+            cudaMemcpyToSymbol(g_gva_gather_ca, &ca, sizeof(int));
+        }
+        return true;
+    }();
+    (void)once;
+}
+
+static int ns_grid(long long items, int ns) {
+    gva_gather_mode_init(); return stride_grid(items, kGvaNsBlock, ns <= 8 ? 6 : ns <= 16 ? 3 : 1); }
 
 // Dynamic shared memory of the NS kernels: 2·NS slots of 16 bytes per thread (64 KB at NS=16 → opt-in).
 #define GVA_DISPATCH_NS2(GLV, NSV, PEB, KERNEL, GRID, ST, ...)                                          \

@@ -60,17 +60,49 @@ scene_bbox_kernel(int n, int b, const float *__restrict__ xyz, const int *__rest
             else atomicMax(hi + sc_first * 3 + (a - 3), bbox_encode(v));
         }
     } else {
-        // chunk straddles a scene boundary (at most b-1 chunks): per-point atomics
+        // chunk straddles scene boundaries (at most b-1 chunks).  Per-point atomics serialise on the
+        // few (scene, axis) words — 2048 x 6 same-address atomics cost ~25 us per launch whatever n is
+        // (profiles/r01i: scene_bbox<1> 27 us at 12k and at 320k points).  Instead: one masked warp
+        // reduction per scene present in the chunk, six atomics per warp and scene.
+        float v[kBboxPerThread][3];
+        int pi[kBboxPerThread];
+#pragma unroll
         for (int u = 0; u < kBboxPerThread; ++u) {
-            const int i = base + u * kBboxBlock + threadIdx.x;
-            if (i > last) continue;
-            const int sc = find_segment(i, offset, b);
-            if (sc >= b) continue;
+            pi[u] = base + u * kBboxBlock + (int)threadIdx.x;
+            const int i = min(pi[u], last);
+#pragma unroll
+            for (int a = 0; a < 3; ++a) v[u][a] = __ldg(xyz + (size_t)i * 3 + a);
+        }
+        const int sc_end = min(sc_last, b - 1);
+        for (int sc = sc_first; sc <= sc_end; ++sc) {
+            const int s0 = sc == 0 ? 0 : __ldg(offset + sc - 1), s1 = __ldg(offset + sc);
+            float mn[3] = {3.0e38f, 3.0e38f, 3.0e38f}, mx[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+            bool any = false;
+#pragma unroll
+            for (int u = 0; u < kBboxPerThread; ++u) {
+                const bool in = pi[u] <= last && pi[u] >= s0 && pi[u] < s1;
+                any |= in;
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+                    mn[a] = in ? fminf(mn[a], v[u][a]) : mn[a];
+                    if (WITH_MAX) mx[a] = in ? fmaxf(mx[a], v[u][a]) : mx[a];
+                }
+            }
+            if (!__any_sync(0xffffffffu, any)) continue;
 #pragma unroll
             for (int a = 0; a < 3; ++a) {
-                const unsigned e = bbox_encode(__ldg(xyz + (size_t)i * 3 + a));
-                atomicMin(lo + sc * 3 + a, e);
-                if (WITH_MAX) atomicMax(hi + sc * 3 + a, e);
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) {
+                    mn[a] = fminf(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], d));
+                    if (WITH_MAX) mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], d));
+                }
+            }
+            if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+                    atomicMin(lo + sc * 3 + a, bbox_encode(mn[a]));
+                    if (WITH_MAX) atomicMax(hi + sc * 3 + a, bbox_encode(mx[a]));
+                }
             }
         }
     }

@@ -140,4 +140,32 @@ __device__ __forceinline__ RowCol split(long long t, int cols) {
     return rc;
 }
 
+// ---- "thread keeps its column" grid-stride walk over (rows x cols) items -----------------------
+// t -> (t / cols, t % cols) costs a 64-bit division per item; for the kernels that do one small gather per item
+// (interpolation forward, pool backward) that is more instructions than the work itself.  When gridDim.x * block is
+// a multiple of cols, a thread's column never changes and only its row advances by a constant:
+//   ColWalk w = col_walk(cols, BLOCK);  for (long long row = w.row; row < n_rows; row += w.row_step) { ... w.col ... }
+inline int gcd_i(int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; }
+inline int col_grid(long long n_rows, int cols, int block, int ctas_per_sm) {
+    const int unit = cols / gcd_i(cols, block);   // CTAs per whole number of rows
+    long long need = (n_rows * cols + block - 1) / block;
+    long long cap = (long long)kNumSM * ctas_per_sm;
+    long long grid = need < cap ? need : cap;
+    grid = ((grid + unit - 1) / unit) * unit;
+    if (grid < unit) grid = unit;
+    return (int)grid;
+}
+struct ColWalk {
+    long long row, row_step;
+    int col;
+};
+__device__ __forceinline__ ColWalk col_walk(int cols, int block) {
+    const long long t0 = (long long)blockIdx.x * block + threadIdx.x;
+    ColWalk w;
+    w.row = t0 / cols;
+    w.col = (int)(t0 - w.row * cols);
+    w.row_step = ((long long)gridDim.x * block) / cols;
+    return w;
+}
+
 }  // namespace aopt

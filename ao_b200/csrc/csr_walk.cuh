@@ -130,4 +130,75 @@ csr_walk_kernel(long long n_rows, int chunks, int c_out, const int *__restrict__
     }
 }
 
+// Two adjacent channel chunks per thread (32 bytes of the gathered row, ONE weight): for policies whose weight
+// is shared by an even number of chunks (GVA: I = C/G = 8 channels per group -> the thread owns a whole group).
+// Per gathered 16 bytes this halves the perm / weight / address instructions of csr_walk_kernel — the r01h study
+// found that walk bound by issue slots (48 %) and the L1 pipe (67 %), not by L2 or DRAM.  Same entry order and
+// the same fmaf sequence per channel as csr_walk_kernel: bitwise-identical results.
+// `pairs` = chunks / 2 (threads per row); the grid is a multiple of pairs / gcd(pairs, kWalkBlock) CTAs.
+template <int B, class P>
+__global__ void __launch_bounds__(kWalkBlock)
+csr_walk2_kernel(long long n_rows, int pairs, int c_out, const int *__restrict__ rowptr,
+                 const int *__restrict__ perm, P pol, float *__restrict__ out) {
+    const long long step_items = (long long)gridDim.x * kWalkBlock;  // multiple of pairs (walk_grid)
+    const long long t0 = (long long)blockIdx.x * kWalkBlock + threadIdx.x;
+    const long long row_step = step_items / pairs;
+    long long j = t0 / pairs;
+    const int ch = 2 * (int)(t0 - j * pairs);  // first of the thread's two chunks
+    if (j >= n_rows) return;
+
+    int e = __ldg(rowptr + j), e_end = __ldg(rowptr + j + 1);
+    int pn[B];
+#pragma unroll
+    for (int u = 0; u < B; ++u) pn[u] = (e + u < e_end) ? __ldg(perm + e + u) : 0;
+    long long jn = j + row_step;
+    int ne = 0, ne_end = 0;
+    if (jn < n_rows) { ne = __ldg(rowptr + jn); ne_end = __ldg(rowptr + jn + 1); }
+
+    for (;;) {
+        const long long jnn = jn + row_step;
+        int nne = 0, nne_end = 0;
+        if (jnn < n_rows) { nne = __ldg(rowptr + jnn); nne_end = __ldg(rowptr + jnn + 1); }
+        float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+        for (;;) {
+            const bool last = e + B >= e_end;
+            int p[B];
+            float4 v0[B], v1[B];
+            float w[B];
+#pragma unroll
+            for (int u = 0; u < B; ++u) {
+                p[u] = pn[u];
+                v0[u] = pol.load(p[u], ch);  // unconditional: slots past the row end hold p = 0 (a valid entry)
+                v1[u] = pol.load(p[u], ch + 1);
+            }
+#pragma unroll
+            for (int u = 0; u < B; ++u) w[u] = pol.weight(p[u], ch);
+            const int pe = last ? ne : e + B, pe_end = last ? ne_end : e_end;
+#pragma unroll
+            for (int u = 0; u < B; ++u) pn[u] = (pe + u < pe_end) ? __ldg(perm + pe + u) : 0;
+            issue_fence();
+#pragma unroll
+            for (int u = 0; u < B; ++u) {
+                const bool keep = e + u < e_end;
+                a0.x = keep ? fmaf(v0[u].x, w[u], a0.x) : a0.x;
+                a0.y = keep ? fmaf(v0[u].y, w[u], a0.y) : a0.y;
+                a0.z = keep ? fmaf(v0[u].z, w[u], a0.z) : a0.z;
+                a0.w = keep ? fmaf(v0[u].w, w[u], a0.w) : a0.w;
+                a1.x = keep ? fmaf(v1[u].x, w[u], a1.x) : a1.x;
+                a1.y = keep ? fmaf(v1[u].y, w[u], a1.y) : a1.y;
+                a1.z = keep ? fmaf(v1[u].z, w[u], a1.z) : a1.z;
+                a1.w = keep ? fmaf(v1[u].w, w[u], a1.w) : a1.w;
+            }
+            if (last) break;
+            e += B;
+        }
+        float *o = out + (size_t)j * c_out + ch * 4;
+        *reinterpret_cast<float4 *>(o) = a0;
+        *reinterpret_cast<float4 *>(o + 4) = a1;
+        if (jn >= n_rows) break;
+        j = jn; e = ne; e_end = ne_end;
+        jn = jnn; ne = nne; ne_end = nne_end;
+    }
+}
+
 }  // namespace aopt

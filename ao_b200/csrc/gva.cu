@@ -437,6 +437,32 @@ static void launch_bv_walk(long long n_src, int k, int c, int g, const float *gr
         csr_walk_kernel<8, BvPolicy<GL>><<<walk_grid(n_src, chunks, 12), kWalkBlock, 0, st>>>(n_src, chunks, c, rowptr, perm, p2, 1.f, grad_value);
 }
 
+// Group-per-thread walk (csr_walk2_kernel): the thread owns both chunks of an 8-channel group, one probability
+// per entry.  AOPT_BV_IMPL=group / chunk selects it or the chunk-per-thread walk (A/B measurements); default below.
+static int bv_group_mode() {  // 1 = group walk where it applies (GL == 2), 0 = chunk walk
+    static const int m = [] {
+        const char *e = getenv("AOPT_BV_IMPL");
+        if (e && e[0] == 'g') return 1;
+        if (e && e[0] == 'c') return 0;
+        return 0;
+    }();
+    return m;
+}
+static int bv_group_batch() {  // entries per batch of the group walk: 4 (default) or 8 (AOPT_BV_GROUP_B=8)
+    static const int b = [] { const char *e = getenv("AOPT_BV_GROUP_B"); return (e && e[0] == '8') ? 8 : 4; }();
+    return b;
+}
+static void launch_bv_group_walk(long long n_src, int k, int c, int g, const float *grad_out, const float *prob,
+                                 const int *rowptr, const int *perm, float *grad_value, cudaStream_t st) {
+    const int pairs = c / 8;  // == g when I == 8
+    BvPolicy<2> pol{grad_out, prob, c, g, k, -1};
+    for (int b = 0; b < 31; ++b) if ((1 << b) == k) pol.kshift = b;
+    if (bv_group_batch() == 8)
+        csr_walk2_kernel<8, BvPolicy<2>><<<walk_grid(n_src, pairs, 8), kWalkBlock, 0, st>>>(n_src, pairs, c, rowptr, perm, pol, grad_value);
+    else
+        csr_walk2_kernel<4, BvPolicy<2>><<<walk_grid(n_src, pairs, 12), kWalkBlock, 0, st>>>(n_src, pairs, c, rowptr, perm, pol, grad_value);
+}
+
 // Four entries at a time with plain loads (tuning alternative, AOPT_BV_IMPL=unroll4).
 template <int GL>
 __global__ void __launch_bounds__(kGvaBlock)
@@ -721,6 +747,10 @@ extern "C" int aopt_gva_backward_value(int n_src, int nsample, int c, int g, con
     if (!grad_out || !prob || !rowptr || !perm || !grad_value) return AOPT_ERR_INVALID_ARGUMENT;
     const int I = c / g;
     const int gl = pick_gl(c, I, {grad_out, grad_value});
+    if (gl == 2 && bv_group_mode() == 1 && use_batched_walk()) {
+        launch_bv_group_walk(n_src, nsample, c, g, grad_out, prob, rowptr, perm, grad_value, as_stream(stream));
+        return check_launch();
+    }
     if (gl > 0 && use_batched_walk()) {
         if (gl == 1) launch_bv_walk<1>(n_src, nsample, c, g, grad_out, prob, rowptr, perm, grad_value, as_stream(stream));
         else if (gl == 2) launch_bv_walk<2>(n_src, nsample, c, g, grad_out, prob, rowptr, perm, grad_value, as_stream(stream));

@@ -31,26 +31,43 @@ interp_weights_kernel(int n, int k, const float *__restrict__ dist2, float *__re
     }
 }
 
+// One thread per (fine row, chunk); the thread keeps its chunk and walks rows (col_walk: no division per item),
+// and the three (idx, weight) pairs of a row are requested before the first gather.
 template <int VEC>
 __global__ void __launch_bounds__(kInterpBlock)
 interp_forward_kernel(long long n, int chunks, int c, int k, int m, const float *__restrict__ input,
                       const int *__restrict__ idx, const float *__restrict__ weight,
                       float *__restrict__ output) {
-    const long long total = n * chunks;
-    const long long step = (long long)gridDim.x * kInterpBlock;
-    for (long long t = (long long)blockIdx.x * kInterpBlock + threadIdx.x; t < total; t += step) {
-        RowCol rc = split(t, chunks);
+    const ColWalk cw = col_walk(chunks, kInterpBlock);
+    for (long long row = cw.row; row < n; row += cw.row_step) {
         Chunk<VEC> acc = Chunk<VEC>::zero();
-#pragma unroll 3
-        for (int i = 0; i < k; ++i) {
-            int j = __ldg(idx + rc.row * k + i);
-            if (j < 0) j += m;  // python negative index (interpolation.py:21): no -1 masking
-            const float w = __ldg(weight + rc.row * k + i);
-            Chunk<VEC> v = Chunk<VEC>::gather(input + (size_t)j * c + rc.col * VEC);
-            v.scale(w);   // separate multiply and add, as `new_feat += feat[idx] * weight` does
-            acc.add(v);
+        if (k == 3) {
+            int j[3];
+            float w[3];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) { j[i] = __ldg(idx + row * 3 + i); w[i] = __ldg(weight + row * 3 + i); }
+            Chunk<VEC> v[3];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                if (j[i] < 0) j[i] += m;  // python negative index (interpolation.py:21): no -1 masking
+                v[i] = Chunk<VEC>::gather(input + (size_t)j[i] * c + cw.col * VEC);
+            }
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                v[i].scale(w[i]);   // separate multiply and add, as `new_feat += feat[idx] * weight` does
+                acc.add(v[i]);
+            }
+        } else {
+            for (int i = 0; i < k; ++i) {
+                int j = __ldg(idx + row * k + i);
+                if (j < 0) j += m;
+                const float w = __ldg(weight + row * k + i);
+                Chunk<VEC> v = Chunk<VEC>::gather(input + (size_t)j * c + cw.col * VEC);
+                v.scale(w);
+                acc.add(v);
+            }
         }
-        acc.store_stream(output + (size_t)rc.row * c + rc.col * VEC);
+        acc.store_stream(output + (size_t)row * c + cw.col * VEC);
     }
 }
 
@@ -77,15 +94,31 @@ interp_backward_kernel(long long m, int chunks, int c, int k, const float *__res
 }
 
 // csr_walk.cuh policy: entry p = flat (fine row, slot); weight[p] * grad_output[p / k].
+// KC = compile-time k (3: the interpolation of the model — p / 3 becomes a multiply-high instead of a runtime
+// integer division per entry), 0 = runtime k.
+template <int KC>
 struct InterpBwdPolicy {
     const float *grad_output, *wgt;
     int c, k;
     static constexpr bool kWeighted = true;
     __device__ __forceinline__ float4 load(int p, int ch) const {
-        return ldg_gather4(grad_output + (size_t)(p / k) * c + ch * 4);
+        const int q = KC > 0 ? p / KC : p / k;
+        return ldg_gather4(grad_output + (size_t)q * c + ch * 4);
     }
     __device__ __forceinline__ float weight(int p, int) const { return __ldg(wgt + p); }
 };
+
+template <int KC>
+static void launch_interp_walk(int m, int chunks, int c, int k, const float *grad_output, const float *weight,
+                               const int *rowptr, const int *perm, float *grad_input, cudaStream_t st) {
+    const InterpBwdPolicy<KC> pol{grad_output, weight, c, k};
+    if (walk_batch() == 4)
+        csr_walk_kernel<4, InterpBwdPolicy<KC>><<<walk_grid(m, chunks, 12), kWalkBlock, 0, st>>>(
+            m, chunks, c, rowptr, perm, pol, 1.f, grad_input);
+    else
+        csr_walk_kernel<8, InterpBwdPolicy<KC>><<<walk_grid(m, chunks, 12), kWalkBlock, 0, st>>>(
+            m, chunks, c, rowptr, perm, pol, 1.f, grad_input);
+}
 
 }  // namespace aopt
 
@@ -107,10 +140,10 @@ extern "C" int aopt_interpolation_forward(int n, int c, int k, int m, const floa
     const bool vec = (c % 4 == 0) && aligned16(input) && aligned16(output);
     if (vec) {
         const int chunks = c / 4;
-        interp_forward_kernel<4><<<stride_grid((long long)n * chunks, kInterpBlock, 8), kInterpBlock, 0, as_stream(stream)>>>(
+        interp_forward_kernel<4><<<col_grid(n, chunks, kInterpBlock, 8), kInterpBlock, 0, as_stream(stream)>>>(
             n, chunks, c, k, m, input, idx, weight, output);
     } else {
-        interp_forward_kernel<1><<<stride_grid((long long)n * c, kInterpBlock, 8), kInterpBlock, 0, as_stream(stream)>>>(
+        interp_forward_kernel<1><<<col_grid(n, c, kInterpBlock, 8), kInterpBlock, 0, as_stream(stream)>>>(
             n, c, c, k, m, input, idx, weight, output);
     }
     return check_launch();
@@ -125,13 +158,8 @@ extern "C" int aopt_interpolation_backward(int m, int c, int k, const float *gra
     const bool vec = (c % 4 == 0) && aligned16(grad_output) && aligned16(grad_input);
     if (vec && use_batched_walk()) {
         const int chunks = c / 4;
-        const InterpBwdPolicy pol{grad_output, weight, c, k};
-        if (walk_batch() == 4)
-            csr_walk_kernel<4, InterpBwdPolicy><<<walk_grid(m, chunks, 12), kWalkBlock, 0, as_stream(stream)>>>(
-                m, chunks, c, rowptr, perm, pol, 1.f, grad_input);
-        else
-            csr_walk_kernel<8, InterpBwdPolicy><<<walk_grid(m, chunks, 12), kWalkBlock, 0, as_stream(stream)>>>(
-                m, chunks, c, rowptr, perm, pol, 1.f, grad_input);
+        if (k == 3) launch_interp_walk<3>(m, chunks, c, k, grad_output, weight, rowptr, perm, grad_input, as_stream(stream));
+        else launch_interp_walk<0>(m, chunks, c, k, grad_output, weight, rowptr, perm, grad_input, as_stream(stream));
     } else if (vec) {
         const int chunks = c / 4;
         interp_backward_kernel<4><<<stride_grid((long long)m * chunks, kInterpBlock, 8), kInterpBlock, 0, as_stream(stream)>>>(

@@ -26,10 +26,11 @@
 namespace aopt {
 
 constexpr int kKnnBlock = 256;
+constexpr int kKnnSmallBlock = 64;   // few queries (the coarse levels): 64-thread CTAs so the scan spreads over the chip
 constexpr int kKnnTile = 1024;
 
-template <int K>
-__global__ void __launch_bounds__(kKnnBlock)
+template <int K, int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
 knn_tile_kernel(int m, int n, int b, int nsample, const float *__restrict__ xyz,
                 const float *__restrict__ new_xyz, const int *__restrict__ offset,
                 const int *__restrict__ new_offset, int *__restrict__ idx_out,
@@ -37,7 +38,7 @@ knn_tile_kernel(int m, int n, int b, int nsample, const float *__restrict__ xyz,
     __shared__ float4 tile[kKnnTile];
     __shared__ int range_s[2];
 
-    const int q = blockIdx.x * kKnnBlock + threadIdx.x;
+    const int q = blockIdx.x * BLOCK + threadIdx.x;
     const bool valid = q < m;
     int start = 0, end = 0;
     float qx = 0.f, qy = 0.f, qz = 0.f;
@@ -72,7 +73,7 @@ knn_tile_kernel(int m, int n, int b, int nsample, const float *__restrict__ xyz,
     for (int base = lo; base < hi; base += kKnnTile) {
         const int cnt = min(kKnnTile, hi - base);
         __syncthreads();  // previous tile fully consumed
-        for (int t = threadIdx.x; t < cnt; t += kKnnBlock) {
+        for (int t = threadIdx.x; t < cnt; t += BLOCK) {
             const float *p = xyz + (size_t)(base + t) * 3;
             tile[t] = make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), 0.f);
         }
@@ -142,8 +143,13 @@ template <int K>
 static void launch_tile(int m, int n, int b, int nsample, const float *xyz, const float *new_xyz,
                         const int *offset, const int *new_offset, int *idx, float *dist2,
                         cudaStream_t st) {
-    knn_tile_kernel<K><<<div_up(m, kKnnBlock), kKnnBlock, 0, st>>>(m, n, b, nsample, xyz, new_xyz, offset,
-                                                                   new_offset, idx, dist2);
+    // a 256-thread CTA per 256 queries leaves most SMs idle below ~38k queries (level 3: 2868 queries = 12 CTAs)
+    if (m <= kKnnSmallBlock * kNumSM * 4)
+        knn_tile_kernel<K, kKnnSmallBlock><<<div_up(m, kKnnSmallBlock), kKnnSmallBlock, 0, st>>>(
+            m, n, b, nsample, xyz, new_xyz, offset, new_offset, idx, dist2);
+    else
+        knn_tile_kernel<K, kKnnBlock><<<div_up(m, kKnnBlock), kKnnBlock, 0, st>>>(m, n, b, nsample, xyz, new_xyz, offset,
+                                                                                  new_offset, idx, dist2);
 }
 
 int knn_tile_launch(int m, int nsample, int n, int b, const float *xyz, const float *new_xyz,

@@ -29,34 +29,53 @@ __device__ __forceinline__ int find_segment(int q, const int *__restrict__ offse
 // k best candidates as a sorted list held in registers (all indices compile-time).
 // LEX = false: candidates are offered in ascending index, so "strictly smaller than the k-th" plus a
 //              stable insert already yields ascending (d2, idx).
-// LEX = true : candidates arrive in arbitrary order (grid traversal); compare (d2, idx) pairs.
+// LEX = true : candidates arrive in arbitrary order (grid traversal); compare (d2, idx) pairs.  d2 >= +0
+//              (a sum of squares, never -0 or negative), so its bit pattern orders like the value and a pair is
+//              one 64-bit key (d2 bits : idx) — two integer compares instead of three float/int ones.
+//
+// Insert = K independent "is the candidate before entry j" tests, then every entry picks its new value from
+// {left neighbour, candidate, itself}.  The previous bubble-from-the-end form made each step wait for the swap
+// before it (a ~60-deep dependent chain for K = 16); whenever ANY lane of a warp accepts a candidate the whole
+// warp walks the insert, so on the small levels (one warp per scheduler) the chain latency was the kernel time
+// (profiles/r01i: knn_grid 120 us for 12.5k and for 50k queries alike).  Same result: the list is sorted and the
+// order is strict, so "shift everything after the insertion point" equals the bubble.
+#ifndef AOPT_TOPK_HD
+#define AOPT_TOPK_HD __device__ __forceinline__
+#define AOPT_F2U(x) __float_as_uint(x)
+#endif
 template <int K, bool LEX>
 struct TopK {
     float d[K];
     int id[K];
 
-    __device__ __forceinline__ void init() {
+    AOPT_TOPK_HD void init() {
 #pragma unroll
         for (int i = 0; i < K; ++i) { d[i] = 1e10f; id[i] = -1; }
     }
-    __device__ __forceinline__ float worst() const { return d[K - 1]; }
+    AOPT_TOPK_HD float worst() const { return d[K - 1]; }
 
-    __device__ __forceinline__ static bool before(float da, int ia, float db, int ib) {
-        if (LEX) return da < db || (da == db && ia < ib);
+    AOPT_TOPK_HD static unsigned long long key(float dv, int iv) {
+        return ((unsigned long long)AOPT_F2U(dv) << 32) | (unsigned)iv;
+    }
+    AOPT_TOPK_HD static bool before(float da, int ia, float db, int ib) {
+        if (LEX) return key(da, ia) < key(db, ib);
         return da < db;
     }
-    __device__ __forceinline__ void offer(float d2, int i) {
-        bool acc = LEX ? (d2 < d[K - 1] || (d2 == d[K - 1] && i < id[K - 1] && d2 < 1e10f)) : (d2 < d[K - 1]);
+    AOPT_TOPK_HD void offer(float d2, int i) {
+        // d2 < 1e10f: the reference never accepts a candidate at or beyond its initial heap value
+        // (knn_query_cuda_kernel.cu:85-93); it also keeps NaN distances and the (1e10, -1) padding apart
+        const bool acc = LEX ? (d2 < 1e10f && before(d2, i, d[K - 1], id[K - 1])) : (d2 < d[K - 1]);
         if (acc) {
-            d[K - 1] = d2;
-            id[K - 1] = i;
+            bool lt[K];
+#pragma unroll
+            for (int j = 0; j < K; ++j) lt[j] = before(d2, i, d[j], id[j]);
 #pragma unroll
             for (int j = K - 1; j > 0; --j) {
-                bool sw = before(d[j], id[j], d[j - 1], id[j - 1]);
-                float td = d[j]; int ti = id[j];
-                d[j] = sw ? d[j - 1] : td;   id[j] = sw ? id[j - 1] : ti;
-                d[j - 1] = sw ? td : d[j - 1]; id[j - 1] = sw ? ti : id[j - 1];
+                d[j] = lt[j - 1] ? d[j - 1] : (lt[j] ? d2 : d[j]);
+                id[j] = lt[j - 1] ? id[j - 1] : (lt[j] ? i : id[j]);
             }
+            d[0] = lt[0] ? d2 : d[0];
+            id[0] = lt[0] ? i : id[0];
         }
     }
     __device__ __forceinline__ void store(int *idx_row, float *d2_row, int nsample) const {

@@ -62,7 +62,7 @@ __device__ __forceinline__ int cell_coord(float p, float o, float inv_h, int dim
 // speed, never correctness): the (k-1)/stride-th nearest neighbour in the thinned set estimates the
 // k-th nearest in the full set.  Every thread keeps a register top-K of its share of the candidates
 // (loads for four candidates are issued together), then the CTA pops the block-wide minimum kp times.
-constexpr int kSampleBlock = 128;
+constexpr int kSampleBlock = 512;   // 128 threads left every sample a ~30 us serial chain (profiles/r01i); same result at any width
 constexpr int kSampleTarget = 8192;  // candidates scanned per sample after thinning
 
 template <int K>
@@ -211,10 +211,28 @@ grid_fill_kernel(int n, const float *__restrict__ xyz, const int *__restrict__ c
 }
 
 // ---- 6. query ------------------------------------------------------------------------------------
+// Candidates of a run are requested four at a time: the offer is a divergent branch, so a load issued next to
+// its use would expose its L1/L2 latency on every candidate — on the small levels, where a scheduler holds a
+// single warp, that latency is the kernel time.  (A cross-iteration prefetch of the next four cost 32 more
+// registers and spills at K = 16; not kept.)
 template <int K>
 __device__ __forceinline__ void scan_run(TopK<K, true> &top, const float4 *__restrict__ sorted, int a,
                                          int e, float qx, float qy, float qz) {
-    for (int i = a; i < e; ++i) {
+    int i = a;
+    for (; i + 4 <= e; i += 4) {
+        const float4 c0 = __ldg(sorted + i), c1 = __ldg(sorted + i + 1), c2 = __ldg(sorted + i + 2),
+                     c3 = __ldg(sorted + i + 3);
+        const float d0 = dist2_ref(qx, qy, qz, c0.x, c0.y, c0.z), d1 = dist2_ref(qx, qy, qz, c1.x, c1.y, c1.z);
+        const float d2 = dist2_ref(qx, qy, qz, c2.x, c2.y, c2.z), d3 = dist2_ref(qx, qy, qz, c3.x, c3.y, c3.z);
+        // '<=': a candidate that ties with the k-th distance can still win on its index (LEX rule)
+        if (fminf(fminf(d0, d1), fminf(d2, d3)) <= top.worst()) {
+            top.offer(d0, __float_as_int(c0.w));
+            top.offer(d1, __float_as_int(c1.w));
+            top.offer(d2, __float_as_int(c2.w));
+            top.offer(d3, __float_as_int(c3.w));
+        }
+    }
+    for (; i < e; ++i) {
         const float4 c = __ldg(sorted + i);
         top.offer(dist2_ref(qx, qy, qz, c.x, c.y, c.z), __float_as_int(c.w));
     }

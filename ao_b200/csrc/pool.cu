@@ -72,11 +72,9 @@ pool_forward_kernel(long long n_vox, int chunks, int c, const float *__restrict_
                     int *__restrict__ argmax, float *__restrict__ out_coord) {
     __shared__ float4 stage[VEC == 4 ? kPoolBatch * kPoolBlock : 1];
     float4 *sf = stage + threadIdx.x;
-    const long long total = n_vox * chunks;
-    const long long step = (long long)gridDim.x * kPoolBlock;
-    for (long long t = (long long)blockIdx.x * kPoolBlock + threadIdx.x; t < total; t += step) {
-        const long long v = t / chunks;
-        const int col = (int)(t - v * chunks);
+    const ColWalk cw = col_walk(chunks, kPoolBlock);  // the thread keeps its chunk: no division per item
+    const int col = cw.col;
+    for (long long v = cw.row; v < n_vox; v += cw.row_step) {
         const int e0 = __ldg(idx_ptr + v), e1 = __ldg(idx_ptr + v + 1);
         float best[VEC];
         int arg[VEC];
@@ -87,18 +85,21 @@ pool_forward_kernel(long long n_vox, int chunks, int c, const float *__restrict_
         if constexpr (VEC == 4) {
             int pn[kPoolBatch];
 #pragma unroll
-            for (int u = 0; u < kPoolBatch; ++u) pn[u] = (e0 + u < e1) ? __ldg(order + e0 + u) : 0;
+            for (int u = 0; u < kPoolBatch; ++u) pn[u] = (e0 + u < e1) ? __ldg(order + e0 + u) : -1;
             for (int e = e0; e < e1; e += kPoolBatch) {
                 int pt[kPoolBatch];
 #pragma unroll
                 for (int u = 0; u < kPoolBatch; ++u) {
-                    pt[u] = pn[u];
+                    // slots past the end of the voxel (most voxels hold fewer than 8 points) re-request the
+                    // batch's first point — a line this thread already asked for.  They used to request point 0:
+                    // every thread of the grid hammering ONE L2 line (the csr_walk.cuh hot-spot rule).
+                    pt[u] = pn[u] >= 0 ? pn[u] : pn[0];
                     cp_async16_stream(sf + u * kPoolBlock, feat + (size_t)pt[u] * c + col * 4);
                 }
                 cp_async_commit();
 #pragma unroll
                 for (int u = 0; u < kPoolBatch; ++u)
-                    pn[u] = (e + kPoolBatch + u < e1) ? __ldg(order + e + kPoolBatch + u) : 0;
+                    pn[u] = (e + kPoolBatch + u < e1) ? __ldg(order + e + kPoolBatch + u) : -1;
                 if (do_coord) {  // sequential sum in `order`, like segment_csr
 #pragma unroll
                     for (int u = 0; u < kPoolBatch; ++u) {
@@ -161,11 +162,9 @@ __global__ void __launch_bounds__(kPoolBlock)
 pool_backward_kernel(long long n, int chunks, int c, const float *__restrict__ grad_out,
                      const int *__restrict__ argmax, const int *__restrict__ cluster,
                      float *__restrict__ grad_feat) {
-    const long long total = n * chunks;
-    const long long step = (long long)gridDim.x * kPoolBlock;
-    for (long long t = (long long)blockIdx.x * kPoolBlock + threadIdx.x; t < total; t += step) {
-        const long long pt = t / chunks;
-        const int col = (int)(t - pt * chunks);
+    const ColWalk cw = col_walk(chunks, kPoolBlock);  // the thread keeps its chunk: no division per item
+    const int col = cw.col;
+    for (long long pt = cw.row; pt < n; pt += cw.row_step) {
         const int v = __ldg(cluster + pt);
         const size_t src = (size_t)v * c + col * VEC, dst = (size_t)pt * c + col * VEC;
         if constexpr (VEC == 4) {
@@ -295,10 +294,10 @@ extern "C" int aopt_pool_forward(int n_vox, int c, const float *feat, const floa
     const bool vec = (c % 4 == 0) && aligned16(feat) && aligned16(out_feat) && aligned16(argmax);
     if (vec) {
         const int chunks = c / 4;
-        pool_forward_kernel<4><<<stride_grid((long long)n_vox * chunks, kPoolBlock, 6), kPoolBlock, 0, as_stream(stream)>>>(
+        pool_forward_kernel<4><<<col_grid(n_vox, chunks, kPoolBlock, 6), kPoolBlock, 0, as_stream(stream)>>>(
             n_vox, chunks, c, feat, coord, order, idx_ptr, out_feat, argmax, out_coord);
     } else {
-        pool_forward_kernel<1><<<stride_grid((long long)n_vox * c, kPoolBlock, 8), kPoolBlock, 0, as_stream(stream)>>>(
+        pool_forward_kernel<1><<<col_grid(n_vox, c, kPoolBlock, 8), kPoolBlock, 0, as_stream(stream)>>>(
             n_vox, c, c, feat, coord, order, idx_ptr, out_feat, argmax, out_coord);
     }
     return check_launch();
@@ -312,10 +311,10 @@ extern "C" int aopt_pool_backward(int n, int c, const float *grad_out, const int
     const bool vec = (c % 4 == 0) && aligned16(grad_out) && aligned16(argmax) && aligned16(grad_feat);
     if (vec) {
         const int chunks = c / 4;
-        pool_backward_kernel<4><<<stride_grid((long long)n * chunks, kPoolBlock, 8), kPoolBlock, 0, as_stream(stream)>>>(
+        pool_backward_kernel<4><<<col_grid(n, chunks, kPoolBlock, 8), kPoolBlock, 0, as_stream(stream)>>>(
             n, chunks, c, grad_out, argmax, cluster, grad_feat);
     } else {
-        pool_backward_kernel<1><<<stride_grid((long long)n * c, kPoolBlock, 8), kPoolBlock, 0, as_stream(stream)>>>(
+        pool_backward_kernel<1><<<col_grid(n, c, kPoolBlock, 8), kPoolBlock, 0, as_stream(stream)>>>(
             n, c, c, grad_out, argmax, cluster, grad_feat);
     }
     return check_launch();

@@ -187,6 +187,33 @@ def require_cuda(*tensors) -> torch.device:
     return dev
 
 
+# ---- side streams --------------------------------------------------------------------------------------------
+# Latency-/ALU-bound kernels (CSR walks, neighbour search, CSR build) leave the HBM pipe idle, the streaming
+# kernels leave the SMs' issue slots idle: independent pairs run on two streams so the hardware co-schedules
+# their CTAs.  One side stream per (device, role); AOPT_OVERLAP=0 (or overlap(False)) serialises everything on
+# the caller's stream — bench.py does that on the steps that carry per-kernel CUDA events, so a kernel's
+# roofline is measured with the kernel running alone.
+_side = {}
+_overlap = os.environ.get("AOPT_OVERLAP", "1") != "0"
+
+
+def overlap(on=None) -> bool:
+    """Query / set whether independent kernels are issued on side streams."""
+    global _overlap
+    if on is not None:
+        _overlap = bool(on)
+    return _overlap
+
+
+def side_stream(device, role: str = "aux") -> "torch.cuda.Stream":
+    key = (torch.device(device).index, role)
+    st = _side.get(key)
+    if st is None:
+        st = torch.cuda.Stream(device=device)
+        _side[key] = st
+    return st
+
+
 def workspace(nbytes: int, device) -> torch.Tensor:
     """Scratch from torch's caching allocator (the library itself never allocates)."""
     return torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=device)

@@ -150,8 +150,10 @@ inline int col_grid(long long n_rows, int cols, int block, int ctas_per_sm) {
     const int unit = cols / gcd_i(cols, block);   // CTAs per whole number of rows
     long long need = (n_rows * cols + block - 1) / block;
     long long cap = (long long)kNumSM * ctas_per_sm;
-    long long grid = need < cap ? need : cap;
-    grid = ((grid + unit - 1) / unit) * unit;
+    // below the cap: round UP (every row covered by the first pass); at the cap: round DOWN — one CTA more than
+    // a full wave runs its whole row walk alone after everybody else has finished (pool_backward: 39 -> 51 us)
+    long long grid = ((need + unit - 1) / unit) * unit;
+    if (grid > cap) grid = (cap / unit) * unit;
     if (grid < unit) grid = unit;
     return (int)grid;
 }

@@ -30,4 +30,4 @@ from .utils import (
     offset2batch,
 )
 from .pe_mlp import pe_bias_mlp, pe_mlp_supported, pos_moments
-from ._csr import get_csr, build_csr
+from ._csr import get_csr, build_csr, prefetch_csr

@@ -10,7 +10,7 @@ import torch
 from torch.autograd import Function
 
 from .. import _lib
-from ._csr import get_csr
+from ._csr import get_csr, prefetch_csr
 from .query import knn_query_raw
 
 
@@ -68,6 +68,8 @@ def interpolation(xyz, new_xyz, feat, offset, new_offset, k=3):
     _lib.require_cuda(xyz, new_xyz, feat)
     idx, dist2 = knn_query_raw(k, xyz, offset, new_xyz, new_offset)
     weight = interpolation_weights(dist2)
+    if feat.requires_grad and torch.is_grad_enabled():
+        prefetch_csr(idx, feat.shape[0], 1)               # the backward's transposed graph, built under the forward
     return _InterpFn.apply(feat.float(), idx, weight)     # interpolation.py:19: fp32 accumulator
 
 

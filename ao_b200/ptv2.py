@@ -222,6 +222,10 @@ class BlockSequence(nn.Module):
             reference_index, _ = pointops.knn_query(self.neighbours, coord, offset)     # :223
             # relative coordinates of the neighbours (:109,:111) are the same for every block of the sequence
             pos = pointops.group_xyz(reference_index, coord)
+            if torch.is_grad_enabled() and feat.requires_grad:
+                # transposed neighbour graph of the atomic-free backward passes: built now, on a side stream,
+                # under the forward kernels instead of at the head of the backward pass
+                pointops.prefetch_csr(reference_index, coord.shape[0], 0)
             # Σp, Σppᵀ of pos: the closed-form BatchNorm statistics of every block's fused positional MLP
             mom = pointops.pos_moments(pos) if (fused_pe_enabled() and self.training) else None
             hit = (reference_index, pos, mom)

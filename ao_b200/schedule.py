@@ -178,6 +178,7 @@ class PointOpsSchedule:
         with self.prof.span("knn", 0.0):
             idx0, _ = pointops.knn_query(k, coord, offset)
         idxs.append(idx0)
+        pointops.prefetch_csr(idx0, coord.shape[0], 0)   # as ptv2.BlockSequence does when training
         poss = [pointops.group_xyz(idx0, coord)]      # (N,k,3), shared by every block on this neighbour list
         for _ in range(cfg.patch_depth):
             fwd.append((lv0,) + self._block_forward(lv0, idx0)[1:])
@@ -196,6 +197,7 @@ class PointOpsSchedule:
             with self.prof.span("knn", 0.0):
                 idx, _ = pointops.knn_query(k, lv.coord, lv.offset)
             idxs.append(idx)
+            pointops.prefetch_csr(idx, lv.coord.shape[0], 0)
             poss.append(pointops.group_xyz(idx, lv.coord))
             for _ in range(cfg.enc_depths[i]):
                 fwd.append((lv,) + self._block_forward(lv, idx)[1:])

@@ -1,0 +1,95 @@
+"""Side-stream overlap (ao_b200._lib.overlap): the CSR prefetch and the overlapped GVA backward must give
+bit-identical results to the single-stream path, repeatedly and under allocator reuse, and the schedule's
+gradients must not depend on the switch."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import to_cuda
+
+pytestmark = pytest.mark.gpu
+
+
+def _case(seed, n=20000, k=16, c=48, g=6):
+    rng = np.random.default_rng(seed)
+    idx = rng.integers(0, n, (n, k)).astype(np.int32)
+    idx[rng.integers(0, n, 50), k // 2:] = -1
+    value = rng.standard_normal((n, c)).astype(np.float32)
+    peb = rng.standard_normal((n, k, c)).astype(np.float32)
+    logits = rng.standard_normal((n, k, g)).astype(np.float32)
+    gout = rng.standard_normal((n, c)).astype(np.float32)
+    return to_cuda(idx, value, peb, logits, gout)
+
+
+def _aggregate_grads(tensors, g, prefetch):
+    from ao_b200 import pointops
+
+    idx, value, peb, logits, gout = tensors
+    idx = idx.clone()                      # fresh tensor object: no cached CSR
+    v, p, l = (t.clone().requires_grad_(True) for t in (value, peb, logits))
+    if prefetch:
+        pointops.prefetch_csr(idx, v.shape[0], 0)
+    out = pointops.gva_aggregate(v, p, l, idx, g)
+    gv, gp, gl = torch.autograd.grad(out, [v, p, l], gout)
+    return out, gv, gp, gl
+
+
+def test_overlapped_gva_backward_is_bit_identical():
+    from ao_b200 import _lib
+
+    t = _case(1)
+    was = _lib.overlap()
+    try:
+        _lib.overlap(False)
+        ref = _aggregate_grads(t, 6, prefetch=False)
+        _lib.overlap(True)
+        for rep in range(6):               # repeated: allocator blocks get recycled across the two streams
+            got = _aggregate_grads(t, 6, prefetch=(rep % 2 == 0))
+            for a, b in zip(ref, got):
+                assert torch.equal(a, b)
+            junk = [torch.randn(1 << 20, device="cuda") for _ in range(4)]   # churn the caching allocator
+            del junk
+        torch.cuda.synchronize()
+    finally:
+        _lib.overlap(was)
+
+
+def test_prefetched_csr_equals_lazy_build():
+    from ao_b200 import _lib, pointops
+
+    (idx,) = to_cuda(np.random.default_rng(3).integers(-1, 5000, (7000, 8)).astype(np.int32))
+    was = _lib.overlap()
+    try:
+        _lib.overlap(True)
+        a = idx.clone()
+        pointops.prefetch_csr(a, 5000, 0)
+        ca = pointops.get_csr(a, 5000, 0)
+        _lib.overlap(False)
+        b = idx.clone()
+        pointops.prefetch_csr(b, 5000, 0)          # no-op when overlap is off
+        assert not getattr(b, "_aopt_csr", None)
+        cb = pointops.get_csr(b, 5000, 0)
+        assert torch.equal(ca.rowptr, cb.rowptr) and torch.equal(ca.perm, cb.perm)
+    finally:
+        _lib.overlap(was)
+
+
+def test_schedule_step_does_not_depend_on_overlap():
+    from ao_b200 import _lib, scenes
+    from ao_b200.schedule import PointOpsSchedule, ScheduleConfig
+
+    coord, _, off = scenes.s3dis_batch(2, n_points=6000)
+    c, o = to_cuda(coord, off)
+    was = _lib.overlap()
+    try:
+        outs = []
+        for on in (False, True, True):
+            _lib.overlap(on)
+            sched = PointOpsSchedule(ScheduleConfig.s3dis(), device="cuda", seed=0)
+            outs.append(sched.step(c, o).clone())
+            outs.append(sched.step(c, o).clone())   # second step: reused level tensors, recycled scratch
+        torch.cuda.synchronize()
+        for x in outs[1:]:
+            assert torch.equal(outs[0], x)
+    finally:
+        _lib.overlap(was)

@@ -166,6 +166,28 @@ def stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+class _NullCtx:
+    __slots__ = ()
+
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NULL = _NullCtx()
+
+
+def on_device(dev):
+    """`with on_device(dev):` — torch.cuda.device(dev) only when dev is not already current (the context
+    manager costs ~10 us of host time per call; the step issues ~250 calls and is host-bound below ~8 ms)."""
+    idx = dev.index if isinstance(dev, torch.device) else int(dev)
+    if idx is None or idx == torch.cuda.current_device():
+        return _NULL
+    return torch.cuda.device(dev)
+
+
 def ptr(t) -> int:
     return 0 if t is None else t.data_ptr()
 
@@ -188,20 +210,27 @@ def require_cuda(*tensors) -> torch.device:
 
 
 # ---- side streams --------------------------------------------------------------------------------------------
-# Latency-/ALU-bound kernels (CSR walks, neighbour search, CSR build) leave the HBM pipe idle, the streaming
-# kernels leave the SMs' issue slots idle: independent pairs run on two streams so the hardware co-schedules
-# their CTAs.  One side stream per (device, role); AOPT_OVERLAP=0 (or overlap(False)) serialises everything on
-# the caller's stream — bench.py does that on the steps that carry per-kernel CUDA events, so a kernel's
-# roofline is measured with the kernel running alone.
+# Experiment kept behind a switch (default OFF): issue the latency-bound kernels (GVA backward-value CSR walk,
+# CSR build) on a side stream next to the HBM-bound streaming kernels.  Measured on B200 at configs[1]
+# (scripts/exp_overlap.py, device ms per step, same box): single stream 8.52; walk overlapped with
+# gva_backward_query 8.48 (no gain: the streaming kernel slows by what the walk saves — both live off memory
+# latency, and the streaming kernel's 3 x 64 KB of shared memory per SM leaves the walk almost no L1);
+# CSR build prefetched under the forward 8.95 (a loss: its atomics and the gathers fight over L2).
+# AOPT_OVERLAP=1 / overlap(True) turns it on; results are bit-identical either way (tests/test_streams_gpu.py).
 _side = {}
-_overlap = os.environ.get("AOPT_OVERLAP", "1") != "0"
+_overlap = os.environ.get("AOPT_OVERLAP", "0") == "1"
 
 
-def overlap(on=None) -> bool:
-    """Query / set whether independent kernels are issued on side streams."""
+_roles_off = {r for r in os.environ.get("AOPT_OVERLAP_OFF", "").split(",") if r}   # e.g. "walk" or "geom" (A/B runs)
+
+
+def overlap(on=None, role: str = None) -> bool:
+    """Query / set whether independent kernels are issued on side streams (optionally: for one role)."""
     global _overlap
     if on is not None:
         _overlap = bool(on)
+    if role is not None and role in _roles_off:
+        return False
     return _overlap
 
 

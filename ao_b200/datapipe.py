@@ -58,7 +58,7 @@ def select_rows(x: torch.Tensor, index: torch.Tensor) -> torch.Tensor:
     w = int(np.prod(x.shape[1:])) if x.dim() > 1 else 1
     out = torch.empty((rows,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
     if rows and w:
-        with torch.cuda.device(x.device):
+        with _lib.on_device(x.device):
             _lib.check(_lib.load().aopt_select_rows(rows, w, _lib.ptr(x), _lib.ptr(index), _lib.ptr(out), _lib.stream()),
                        "select_rows")
     return out
@@ -99,7 +99,7 @@ def voxel_hash(coord: torch.Tensor, grid_size, hash_type: str = "fnv", division:
     if n == 0:
         z = torch.zeros(0, dtype=torch.int32, device=dev)
         return VoxelHash(cell, z, torch.zeros(1, dtype=torch.int32, device=dev), 0, 0, stats, g)
-    with torch.cuda.device(dev):
+    with _lib.on_device(dev):
         _lib.check(lib.aopt_grid_sample_keys(n, _lib.ptr(coord), float(g[0]), float(g[1]), float(g[2]),
                                              1 if division == "float64" else 0, 0 if hash_type == "fnv" else 1,
                                              _lib.ptr(cell), _lib.ptr(keys), _lib.ptr(stats), _lib.stream()),
@@ -132,7 +132,7 @@ def voxel_pick(vh: VoxelHash, r=None, part: int = 0) -> torch.Tensor:
     pick = torch.empty(vh.n_vox, dtype=torch.int64, device=dev)
     if vh.n_vox:
         rt = None if r is None else _t(np.ascontiguousarray(r, dtype=np.int64) if isinstance(r, np.ndarray) else r, dev).long().contiguous()
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             _lib.check(lib.aopt_voxel_pick(vh.n_vox, _lib.ptr(vh.idx_ptr), _lib.ptr(vh.order),
                                            _lib.ptr(rt) if rt is not None else None, int(part), _lib.ptr(pick),
                                            _lib.stream()), "voxel_pick")
@@ -215,7 +215,7 @@ def sphere_crop_index(coord: torch.Tensor, center, point_max: int) -> torch.Tens
     n = coord.shape[0]
     c = [float(np.float32(v)) for v in (center.tolist() if hasattr(center, "tolist") else center)]
     d2 = torch.empty(n, dtype=torch.float32, device=coord.device)
-    with torch.cuda.device(coord.device):
+    with _lib.on_device(coord.device):
         _lib.check(lib.aopt_sphere_dist2(n, _lib.ptr(coord), c[0], c[1], c[2], _lib.ptr(d2), _lib.stream()), "sphere_dist2")
     return torch.sort(d2, stable=True).indices[:point_max]
 

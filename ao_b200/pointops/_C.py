@@ -50,7 +50,7 @@ def knn_query_cuda(m, nsample, xyz, new_xyz, offset, new_offset, idx, dist2):
     n, b = xyz.shape[0], offset.numel()
     if m == 0:
         return
-    with torch.cuda.device(xyz.device):
+    with _lib.on_device(xyz.device):
         ws = _lib.workspace(lib.aopt_knn_workspace_bytes(n, m, b, nsample, _lib.KNN_AUTO), xyz.device)
         _lib.check(lib.aopt_knn_query(m, nsample, n, b, _lib.ptr(xyz), _lib.ptr(new_xyz), _lib.ptr(offset),
                                       _lib.ptr(new_offset), _lib.ptr(idx), _lib.ptr(dist2), _lib.KNN_AUTO,
@@ -61,7 +61,7 @@ def grouping_forward_cuda(m, nsample, c, input, idx, output):
     """grouping/grouping_cuda.cpp:7-13: output[m,s,:] = input[idx[m,s],:]."""
     lib = _lib.load()
     _f(input, "input"), _i(idx, "idx"), _f(output, "output")
-    with torch.cuda.device(input.device):
+    with _lib.on_device(input.device):
         _lib.check(lib.aopt_grouping_forward(m, nsample, c, _lib.ptr(input), _lib.ptr(idx), _lib.ptr(output), c,
                                              _lib.stream()), "grouping_forward_cuda")
 
@@ -73,7 +73,7 @@ def grouping_backward_cuda(m, nsample, c, grad_output, idx, grad_input):
     n = grad_input.shape[0]
     csr = get_csr(idx, n, 0)
     tmp = torch.empty_like(grad_input)
-    with torch.cuda.device(grad_output.device):
+    with _lib.on_device(grad_output.device):
         _lib.check(lib.aopt_grouping_backward(n, c, _lib.ptr(grad_output), c, _lib.ptr(csr.rowptr), _lib.ptr(csr.perm),
                                               1.0, _lib.ptr(tmp), _lib.stream()), "grouping_backward_cuda")
     grad_input.add_(tmp)
@@ -84,7 +84,7 @@ def interpolation_forward_cuda(n, c, k, input, idx, weight, output):
     lib = _lib.load()
     _f(input, "input"), _i(idx, "idx"), _f(weight, "weight"), _f(output, "output")
     tmp = torch.empty_like(output)
-    with torch.cuda.device(input.device):
+    with _lib.on_device(input.device):
         _lib.check(lib.aopt_interpolation_forward(n, c, k, input.shape[0], _lib.ptr(input), _lib.ptr(idx),
                                                   _lib.ptr(weight), _lib.ptr(tmp), _lib.stream()),
                    "interpolation_forward_cuda")
@@ -98,7 +98,7 @@ def interpolation_backward_cuda(n, c, k, grad_output, idx, weight, grad_input):
     m = grad_input.shape[0]
     csr = get_csr(idx, m, 1)
     tmp = torch.empty_like(grad_input)
-    with torch.cuda.device(grad_output.device):
+    with _lib.on_device(grad_output.device):
         _lib.check(lib.aopt_interpolation_backward(m, c, k, _lib.ptr(grad_output), _lib.ptr(weight),
                                                    _lib.ptr(csr.rowptr), _lib.ptr(csr.perm), _lib.ptr(tmp),
                                                    _lib.stream()), "interpolation_backward_cuda")
@@ -109,7 +109,7 @@ def subtraction_forward_cuda(n, nsample, c, input1, input2, idx, output):
     """subtraction/subtraction_cuda.cpp:7-14: output[n,s,:] = input1[n,:] − input2[idx[n,s],:]."""
     lib = _lib.load()
     _f(input1, "input1"), _f(input2, "input2"), _i(idx, "idx"), _f(output, "output")
-    with torch.cuda.device(input1.device):
+    with _lib.on_device(input1.device):
         _lib.check(lib.aopt_subtraction_forward(n, nsample, c, _lib.ptr(input1), _lib.ptr(input2), _lib.ptr(idx),
                                                 _lib.ptr(output), _lib.stream()), "subtraction_forward_cuda")
 
@@ -121,7 +121,7 @@ def subtraction_backward_cuda(n, nsample, c, idx, grad_output, grad_input1, grad
     n2 = grad_input2.shape[0]
     csr = get_csr(idx, n2, 0)
     t1, t2 = torch.empty_like(grad_input1), torch.empty_like(grad_input2)
-    with torch.cuda.device(grad_output.device):
+    with _lib.on_device(grad_output.device):
         _lib.check(lib.aopt_sum_over_k(n, nsample, c, _lib.ptr(grad_output), 1.0, _lib.ptr(t1), _lib.stream()),
                    "subtraction_backward_cuda")
         _lib.check(lib.aopt_grouping_backward(n2, c, _lib.ptr(grad_output), c, _lib.ptr(csr.rowptr), _lib.ptr(csr.perm),
@@ -135,7 +135,7 @@ def aggregation_forward_cuda(n, nsample, c, w_c, input, position, weight, idx, o
     lib = _lib.load()
     _f(input, "input"), _f(position, "position"), _f(weight, "weight"), _i(idx, "idx"), _f(output, "output")
     tmp = torch.empty_like(output)
-    with torch.cuda.device(input.device):
+    with _lib.on_device(input.device):
         _lib.check(lib.aopt_aggregation_forward(n, nsample, c, w_c, _lib.ptr(input), _lib.ptr(position),
                                                 _lib.ptr(weight), _lib.ptr(idx), _lib.ptr(tmp), _lib.stream()),
                    "aggregation_forward_cuda")
@@ -151,7 +151,7 @@ def aggregation_backward_cuda(n, nsample, c, w_c, input, position, weight, idx, 
     _f(grad_weight, "grad_weight")
     csr = get_csr(idx, input.shape[0], 0)
     gi, gp, gw = torch.empty_like(grad_input), torch.empty_like(grad_position), torch.empty_like(grad_weight)
-    with torch.cuda.device(input.device):
+    with _lib.on_device(input.device):
         _lib.check(lib.aopt_aggregation_backward(n, nsample, c, w_c, _lib.ptr(input), _lib.ptr(position),
                                                  _lib.ptr(weight), _lib.ptr(idx), _lib.ptr(csr.rowptr),
                                                  _lib.ptr(csr.perm), _lib.ptr(grad_output), _lib.ptr(gi), _lib.ptr(gp),
@@ -168,7 +168,7 @@ def farthest_point_sampling_cuda(b, n, xyz, offset, new_offset, tmp, idx):
     _f(xyz, "xyz"), _i(offset, "offset"), _i(new_offset, "new_offset"), _f(tmp, "tmp"), _i(idx, "idx")
     if idx.numel() == 0:
         return
-    with torch.cuda.device(xyz.device):
+    with _lib.on_device(xyz.device):
         _lib.check(lib.aopt_farthest_point_sampling(int(b), int(n), _lib.ptr(xyz), _lib.ptr(offset), _lib.ptr(new_offset),
                                                     _lib.ptr(tmp), _lib.ptr(idx), _lib.stream()),
                    "farthest_point_sampling_cuda")

@@ -27,7 +27,7 @@ def build_csr(idx: torch.Tensor, n_src: int, negative_mode: int = 0) -> Neighbou
     n_entries = idx.numel()
     rowptr = torch.empty(n_src + 1, dtype=torch.int32, device=idx.device)
     perm = torch.empty(max(n_entries, 1), dtype=torch.int32, device=idx.device)
-    with torch.cuda.device(idx.device):
+    with _lib.on_device(idx.device):
         ws = _lib.workspace(lib.aopt_csr_workspace_bytes(n_src, n_entries), idx.device)
         _lib.check(
             lib.aopt_csr_build(n_src, n_entries, _lib.ptr(idx), negative_mode, _lib.ptr(rowptr),
@@ -67,7 +67,7 @@ def prefetch_csr(idx: torch.Tensor, n_src: int, negative_mode: int = 0) -> None:
     sitting at the head of the backward pass (count / scan / fill / rank: small latency-bound kernels that use
     3 % of the HBM pipe).  The first backward that needs it waits on the build's event.  With overlap off this
     is a no-op (the CSR is then built lazily by get_csr, as before)."""
-    if not _lib.overlap() or idx.numel() == 0:
+    if not _lib.overlap(role="geom") or idx.numel() == 0:
         return
     assert idx.dtype == torch.int32 and idx.is_contiguous() and idx.is_cuda
     cache = _cache_of(idx)

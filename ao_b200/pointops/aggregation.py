@@ -27,7 +27,7 @@ class Aggregation(Function):
         input, position, weight = input.float(), position.float(), weight.float()
         output = torch.empty((n, c), dtype=torch.float32, device=input.device)
         if n > 0:
-            with torch.cuda.device(input.device):
+            with _lib.on_device(input.device):
                 _lib.check(
                     lib.aopt_aggregation_forward(n, nsample, c, w_c, _lib.ptr(input), _lib.ptr(position),
                                                  _lib.ptr(weight), _lib.ptr(idx), _lib.ptr(output), _lib.stream()),
@@ -55,7 +55,7 @@ class Aggregation(Function):
         grad_weight = torch.empty((n, nsample, w_c), dtype=torch.float32, device=dev)
         csr = get_csr(idx, input.shape[0], 0)
         if n > 0:
-            with torch.cuda.device(dev):
+            with _lib.on_device(dev):
                 _lib.check(
                     lib.aopt_aggregation_backward(n, nsample, c, w_c, _lib.ptr(input), _lib.ptr(position),
                                                   _lib.ptr(weight), _lib.ptr(idx), _lib.ptr(csr.rowptr),

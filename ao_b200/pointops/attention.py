@@ -35,7 +35,7 @@ def group_xyz(idx, xyz, new_xyz=None):
     m, k = idx.shape
     out = torch.empty((m, k, 3), dtype=torch.float32, device=xyz.device)
     if m > 0:
-        with torch.cuda.device(xyz.device):
+        with _lib.on_device(xyz.device):
             _lib.check(
                 lib.aopt_group_xyz(m, k, _lib.ptr(xyz.float().contiguous()), _lib.ptr(new_xyz.float().contiguous()),
                                    _lib.ptr(idx), _lib.ptr(out), 3, _lib.stream()),
@@ -52,7 +52,7 @@ class _RelationFn(Function):
         n, c = key.shape
         out = torch.empty((m, k, c), dtype=torch.float32, device=key.device)
         if m > 0:
-            with torch.cuda.device(key.device):
+            with _lib.on_device(key.device):
                 _lib.check(
                     lib.aopt_gather_sub_forward(m, k, c, _lib.ptr(key), _lib.ptr(query), _lib.ptr(idx),
                                                 _lib.ptr(out), _lib.stream()),
@@ -72,7 +72,7 @@ class _RelationFn(Function):
             csr = get_csr(ctx.idx, n, 0)
             grad_key = torch.empty((n, c), dtype=torch.float32, device=grad.device)
             grad_query = torch.empty((m, c), dtype=torch.float32, device=grad.device)
-            with torch.cuda.device(grad.device):
+            with _lib.on_device(grad.device):
                 _lib.check(
                     lib.aopt_relation_backward(n, k, c, _lib.ptr(grad), _lib.ptr(csr.rowptr), _lib.ptr(csr.perm),
                                                _lib.ptr(grad_key), _lib.ptr(grad_query), _lib.stream()),
@@ -83,7 +83,7 @@ class _RelationFn(Function):
             grad_key = _scatter(grad, c, 0, get_csr(ctx.idx, n, 0), n, c)
         if ctx.needs_input_grad[1]:
             grad_query = torch.empty((m, c), dtype=torch.float32, device=grad.device)
-            with torch.cuda.device(grad.device):
+            with _lib.on_device(grad.device):
                 _lib.check(
                     lib.aopt_sum_over_k(m, k, c, _lib.ptr(grad), -1.0, _lib.ptr(grad_query), _lib.stream()),
                     "sum_over_k",
@@ -109,7 +109,7 @@ class _AggregateFn(Function):
         out = torch.empty((n, c), dtype=torch.float32, device=value.device)
         prob = torch.empty((n, k, groups), dtype=torch.float32, device=value.device)
         if n > 0:
-            with torch.cuda.device(value.device):
+            with _lib.on_device(value.device):
                 _lib.check(
                     lib.aopt_gva_forward(n, k, c, groups, _lib.ptr(value), _lib.ptr(peb), _lib.ptr(logits),
                                          _lib.ptr(idx), _lib.ptr(out), _lib.ptr(prob), _lib.stream()),
@@ -133,12 +133,12 @@ class _AggregateFn(Function):
         grad_logits = torch.empty((n, k, g), dtype=torch.float32, device=dev)
         grad_value = None
         want_value = ctx.needs_input_grad[0]
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             # grad_value (CSR walk: latency / L1 bound, 30 % of the HBM pipe) and grad_peb / grad_logits (streaming,
             # HBM bound) are independent: the walk goes to a side stream and overlaps the streaming kernel.
             # Everything is allocated on the caller's stream; the side stream starts after an event that follows
             # the allocations and inputs, and the caller's stream joins it before returning.
-            side = _lib.side_stream(dev, "walk") if (want_value and n > 0 and _lib.overlap()) else None
+            side = _lib.side_stream(dev, "walk") if (want_value and n > 0 and _lib.overlap(role="walk")) else None
             if want_value:
                 csr = get_csr(idx, n_src, 0)
                 grad_value = torch.empty((n_src, c), dtype=torch.float32, device=dev)

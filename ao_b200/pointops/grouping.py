@@ -17,7 +17,7 @@ def _gather(inp, idx, out, out_stride, col0=0):
     lib = _lib.load()
     m, k = idx.shape
     c = inp.shape[1]
-    with torch.cuda.device(inp.device):
+    with _lib.on_device(inp.device):
         _lib.check(
             lib.aopt_grouping_forward(m, k, c, _lib.ptr(inp), _lib.ptr(idx),
                                       out.data_ptr() + 4 * col0, out_stride, _lib.stream()),
@@ -28,7 +28,7 @@ def _gather(inp, idx, out, out_stride, col0=0):
 def _scatter(grad_out, go_stride, col0, csr, n, c, scale=1.0):
     lib = _lib.load()
     grad_in = torch.empty((n, c), dtype=torch.float32, device=grad_out.device)
-    with torch.cuda.device(grad_out.device):
+    with _lib.on_device(grad_out.device):
         _lib.check(
             lib.aopt_grouping_backward(n, c, grad_out.data_ptr() + 4 * col0, go_stride, _lib.ptr(csr.rowptr),
                                        _lib.ptr(csr.perm), float(scale), _lib.ptr(grad_in), _lib.stream()),
@@ -50,7 +50,7 @@ class _GroupingFn(Function):
         if m > 0:
             _gather(feat, idx, out, width, 3 if with_xyz else 0)
             if with_xyz:
-                with torch.cuda.device(feat.device):
+                with _lib.on_device(feat.device):
                     _lib.check(
                         lib.aopt_group_xyz(m, k, _lib.ptr(xyz), _lib.ptr(new_xyz), _lib.ptr(idx),
                                            _lib.ptr(out), width, _lib.stream()),

@@ -20,7 +20,7 @@ def interpolation_weights(dist2: torch.Tensor) -> torch.Tensor:
     n, k = dist2.shape
     w = torch.empty_like(dist2)
     if n > 0:
-        with torch.cuda.device(dist2.device):
+        with _lib.on_device(dist2.device):
             _lib.check(lib.aopt_interp_weights(n, k, _lib.ptr(dist2), _lib.ptr(w), _lib.stream()), "interp_weights")
     return w
 
@@ -33,7 +33,7 @@ class _InterpFn(Function):
         m, c = feat.shape
         out = torch.empty((n, c), dtype=torch.float32, device=feat.device)
         if n > 0:
-            with torch.cuda.device(feat.device):
+            with _lib.on_device(feat.device):
                 _lib.check(
                     lib.aopt_interpolation_forward(n, c, k, m, _lib.ptr(feat), _lib.ptr(idx), _lib.ptr(weight),
                                                    _lib.ptr(out), _lib.stream()),
@@ -49,7 +49,7 @@ class _InterpFn(Function):
         grad_out = grad_out.contiguous().float()
         csr = get_csr(ctx.idx, m, 1)  # negative indices wrap, as in the forward
         grad_in = torch.empty((m, c), dtype=torch.float32, device=grad_out.device)
-        with torch.cuda.device(grad_out.device):
+        with _lib.on_device(grad_out.device):
             _lib.check(
                 lib.aopt_interpolation_backward(m, c, k, _lib.ptr(grad_out), _lib.ptr(ctx.weight),
                                                 _lib.ptr(csr.rowptr), _lib.ptr(csr.perm), _lib.ptr(grad_in),

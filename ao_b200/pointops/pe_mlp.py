@@ -28,7 +28,7 @@ def pos_moments(pos: torch.Tensor) -> torch.Tensor:
     pos = pos.float().contiguous()
     rows = pos.numel() // 3
     out = torch.empty(9, dtype=torch.float64, device=dev)
-    with torch.cuda.device(dev):
+    with _lib.on_device(dev):
         ws = _lib.workspace(lib.aopt_pos_moments_workspace_bytes(), dev)
         _lib.check(lib.aopt_pos_moments(rows, _lib.ptr(pos), _lib.ptr(out), _lib.ptr(ws), ws.numel(), _lib.stream()),
                    "pos_moments")
@@ -47,7 +47,7 @@ class _PeMlpFn(Function):
         aux_out = None if aux_w is None else torch.empty(pos.shape[:-1] + (ga,), dtype=torch.float32, device=dev)
         state = torch.empty(lib.aopt_pe_mlp_state_bytes(c), dtype=torch.uint8, device=dev)
         stats = torch.empty(3 * c, dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             _lib.check(
                 lib.aopt_pe_mlp_forward(rows, c, _lib.ptr(pos), _lib.ptr(moments), _lib.ptr(w1), _lib.ptr(b1),
                                         _lib.ptr(gamma), _lib.ptr(beta), _lib.ptr(running_mean), _lib.ptr(running_var),
@@ -85,7 +85,7 @@ class _PeMlpFn(Function):
             for t in (gw1, gb1, gg, gbeta, gb2, gw2) + ((gaw,) if gaw is not None else ()):
                 t.zero_()
         else:
-            with torch.cuda.device(dev):
+            with _lib.on_device(dev):
                 ws = _lib.workspace(lib.aopt_pe_mlp_backward_workspace_bytes(rows, c), dev)
                 _lib.check(
                     lib.aopt_pe_mlp_backward(rows, c, _lib.ptr(pos), _lib.ptr(moments), _lib.ptr(w1), _lib.ptr(gamma),

@@ -44,7 +44,7 @@ def voxel_partition(coord, offset, grid_size, start=None) -> VoxelPartition:
                               z32, torch.zeros(b, dtype=torch.int64, device=dev), 0)
     keys = torch.empty(n, dtype=torch.int64, device=dev)
     meta = torch.zeros(2, dtype=torch.int32, device=dev)            # [n_vox, key-overflow flag]
-    with torch.cuda.device(dev):
+    with _lib.on_device(dev):
         if start is None:
             start = torch.empty((b, 3), dtype=torch.float32, device=dev)
             _lib.check(lib.aopt_segment_min3(n, b, _lib.ptr(coord), _lib.ptr(off32), _lib.ptr(start), _lib.stream()),
@@ -90,7 +90,7 @@ class _PoolFn(Function):
         argmax = torch.empty((n_vox, c), dtype=torch.int32, device=dev)
         out_coord = torch.empty((n_vox, 3), dtype=torch.float32, device=dev)
         if n_vox > 0:
-            with torch.cuda.device(dev):
+            with _lib.on_device(dev):
                 _lib.check(
                     lib.aopt_pool_forward(n_vox, c, _lib.ptr(feat), _lib.ptr(coord), _lib.ptr(order),
                                           _lib.ptr(idx_ptr), _lib.ptr(out_feat), _lib.ptr(argmax),
@@ -110,7 +110,7 @@ class _PoolFn(Function):
         grad_feat = grad_feat.contiguous().float()
         grad_in = torch.empty((n, c), dtype=torch.float32, device=grad_feat.device)
         if n > 0:
-            with torch.cuda.device(grad_feat.device):
+            with _lib.on_device(grad_feat.device):
                 _lib.check(
                     lib.aopt_pool_backward(n, c, _lib.ptr(grad_feat), _lib.ptr(argmax), _lib.ptr(cluster32),
                                            _lib.ptr(grad_in), _lib.stream()),
@@ -140,7 +140,7 @@ class _UnpoolMapFn(Function):
         n = cluster32.numel()
         out = torch.empty((n, c), dtype=torch.float32, device=feat.device)
         if n > 0:
-            with torch.cuda.device(feat.device):
+            with _lib.on_device(feat.device):
                 _lib.check(
                     lib.aopt_grouping_forward(n, 1, c, _lib.ptr(feat), _lib.ptr(cluster32), _lib.ptr(out), c,
                                               _lib.stream()),
@@ -156,7 +156,7 @@ class _UnpoolMapFn(Function):
         grad = grad.contiguous().float()
         csr = get_csr(ctx.cluster32, n_vox, 0)
         grad_in = torch.empty((n_vox, c), dtype=torch.float32, device=grad.device)
-        with torch.cuda.device(grad.device):
+        with _lib.on_device(grad.device):
             _lib.check(
                 lib.aopt_grouping_backward(n_vox, c, _lib.ptr(grad), c, _lib.ptr(csr.rowptr), _lib.ptr(csr.perm),
                                            1.0, _lib.ptr(grad_in), _lib.stream()),

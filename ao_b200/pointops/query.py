@@ -42,7 +42,7 @@ def knn_query_raw(nsample, xyz, offset, new_xyz=None, new_offset=None, method=No
     dist2 = torch.empty((m, nsample), dtype=torch.float32, device=dev)
     if m == 0:
         return idx, dist2
-    with torch.cuda.device(dev):
+    with _lib.on_device(dev):
         ws = _lib.workspace(lib.aopt_knn_workspace_bytes(n, m, b, nsample, meth), dev)
         _lib.check(
             lib.aopt_knn_query(m, nsample, n, b, _lib.ptr(xyz), _lib.ptr(new_xyz), _lib.ptr(offset),

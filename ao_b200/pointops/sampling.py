@@ -36,7 +36,7 @@ class FarthestPointSampling(Function):
         idx = torch.zeros(m, dtype=torch.int32, device=dev)
         tmp = torch.full((n,), 1e10, dtype=torch.float32, device=dev)
         if m > 0:
-            with torch.cuda.device(dev):
+            with _lib.on_device(dev):
                 _lib.check(_lib.load().aopt_farthest_point_sampling(b, n_max, _lib.ptr(xyz), _lib.ptr(off), _lib.ptr(noff),
                                                                     _lib.ptr(tmp), _lib.ptr(idx), _lib.stream()),
                            "farthest_point_sampling")

@@ -25,7 +25,7 @@ class Subtraction(Function):
         nsample = idx.shape[-1]
         output = torch.empty((n, nsample, c), dtype=torch.float32, device=input1.device)
         if n > 0:
-            with torch.cuda.device(input1.device):
+            with _lib.on_device(input1.device):
                 _lib.check(
                     lib.aopt_subtraction_forward(n, nsample, c, _lib.ptr(input1.float()), _lib.ptr(input2.float()),
                                                  _lib.ptr(idx), _lib.ptr(output), _lib.stream()),
@@ -45,7 +45,7 @@ class Subtraction(Function):
         n, nsample, c = grad_output.shape
         grad_output = grad_output.contiguous().float()
         grad_input1 = torch.empty((n, c), dtype=torch.float32, device=grad_output.device)
-        with torch.cuda.device(grad_output.device):
+        with _lib.on_device(grad_output.device):
             _lib.check(
                 lib.aopt_sum_over_k(n, nsample, c, _lib.ptr(grad_output), 1.0, _lib.ptr(grad_input1), _lib.stream()),
                 "sum_over_k",

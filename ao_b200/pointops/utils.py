@@ -19,7 +19,7 @@ def offset2batch(offset):
     n = int(off32[-1].item()) if b > 0 else 0
     batch = torch.empty(n, dtype=torch.int64, device=dev)
     if n > 0:
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             _lib.check(lib.aopt_offset2batch(n, b, _lib.ptr(off32), _lib.ptr(batch), _lib.stream()), "offset2batch")
     return batch
 

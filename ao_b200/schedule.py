@@ -142,26 +142,18 @@ class PointOpsSchedule:
     def bytes_group_xyz(n, k): return 12.0 * n + 12.0 * n + 4.0 * n * k + 12.0 * n * k
 
     # ---- one block ---------------------------------------------------------------------------------------
-    def _block_forward(self, lv: Level, idx):
+    def _block_forward(self, lv: Level, idx, tape):
+        """Forward of one block's point operators.  Every block gets its own autograd leaves (views of the level's
+        resident tensors — no copy), so the single backward pass at the end of the step produces one gradient per
+        block instead of accumulating into shared leaves (the accumulation would add (N,k,C) element-wise adds that
+        the model does not have)."""
         t, k = lv.tensors, self.cfg.k
-        pos = None   # relative coordinates depend only on (idx, coord): computed once per neighbour list in step()
+        key, query, value, peb, logits = (t[n].detach().requires_grad_(True) for n in ("key", "query", "value", "peb", "logits"))
         with self.prof.span("gva_relation_fwd", self.bytes_relation_fwd(lv.n, k, lv.c)):
-            rel = pointops.gva_relation(t["key"], t["query"], idx)
+            rel = pointops.gva_relation(key, query, idx)
         with self.prof.span("gva_aggregate_fwd", self.bytes_aggregate_fwd(lv.n, k, lv.c, lv.g)):
-            out = pointops.gva_aggregate(t["value"], t["peb"], t["logits"], idx, lv.g)
-        return pos, rel, out
-
-    def _block_backward(self, lv: Level, rel, out):
-        t, k, n, c, g = lv.tensors, self.cfg.k, lv.n, lv.c, lv.g
-        # relation backward: grad_key through the CSR (reads (N,k,C) once, writes (N,C)) + grad_query
-        nbytes = 2 * (4.0 * n * k * c) + 4.0 * n * k + 4.0 * (n + 1) + 8.0 * n * c
-        with self.prof.span("gva_relation_bwd", nbytes):
-            gk, gq = torch.autograd.grad(rel, [t["key"], t["query"]], t["g_rel"])
-        nbytes = (8.0 * n * c + 4.0 * n * k * c + 4.0 * n * k * g + 8.0 * n * k + 4.0 * (n + 1)) + \
-                 (4.0 * n * k * c + 4.0 * n * k * g + 4.0 * n * c)
-        with self.prof.span("gva_aggregate_bwd", nbytes):
-            gv, gp, gl = torch.autograd.grad(out, [t["value"], t["peb"], t["logits"]], t["g_out"])
-        return gk, gq, gv, gp, gl
+            out = pointops.gva_aggregate(value, peb, logits, idx, lv.g)
+        tape.append(([rel, out], [key, query, value, peb, logits], [t["g_rel"], t["g_out"]]))
 
     # ---- one training-step worth of point operators -------------------------------------------------
     def step(self, coord: torch.Tensor, offset: torch.Tensor):
@@ -170,10 +162,9 @@ class PointOpsSchedule:
         n_stage = len(cfg.grid_sizes)
         lv0 = self._level_tensors(0, coord.shape[0])
         lv0.coord, lv0.offset = coord, offset
-        fwd = []      # (level, rel, out) per block in forward order
+        tape = []     # (outputs, leaves, upstream gradients) in forward order
         idxs = []
         parts = []
-        pooled = []
         # ---------------- forward ----------------
         with self.prof.span("knn", 0.0):
             idx0, _ = pointops.knn_query(k, coord, offset)
@@ -181,27 +172,27 @@ class PointOpsSchedule:
         pointops.prefetch_csr(idx0, coord.shape[0], 0)   # as ptv2.BlockSequence does when training
         poss = [pointops.group_xyz(idx0, coord)]      # (N,k,3), shared by every block on this neighbour list
         for _ in range(cfg.patch_depth):
-            fwd.append((lv0,) + self._block_forward(lv0, idx0)[1:])
+            self._block_forward(lv0, idx0, tape)
         for i in range(n_stage):
             fine = self.levels[i]
             c_next = cfg.channels[i + 1]
             nb = 4.0 * fine.n * c_next + 16.0 * fine.n
+            pool_in = fine.tensors["pool_in"]
             with self.prof.span("grid_pool_fwd", nb):
-                (nc, nf, noff), cluster, part = pointops.grid_pool(fine.coord, fine.tensors["pool_in"], fine.offset,
+                (nc, nf, noff), cluster, part = pointops.grid_pool(fine.coord, pool_in, fine.offset,
                                                                    cfg.grid_sizes[i], return_partition=True)
             lv = self._level_tensors(i + 1, nc.shape[0])
             lv.coord, lv.offset = nc, noff.int()
             self._coarse_tensors(i + 1, nc.shape[0])
             parts.append(part)
-            pooled.append(nf)
+            tape.append(([nf], [pool_in], [lv.tensors["g_pool"]]))
             with self.prof.span("knn", 0.0):
                 idx, _ = pointops.knn_query(k, lv.coord, lv.offset)
             idxs.append(idx)
             pointops.prefetch_csr(idx, lv.coord.shape[0], 0)
             poss.append(pointops.group_xyz(idx, lv.coord))
             for _ in range(cfg.enc_depths[i]):
-                fwd.append((lv,) + self._block_forward(lv, idx)[1:])
-        ups = []
+                self._block_forward(lv, idx, tape)
         for i in reversed(range(n_stage)):
             coarse, fine = self.levels[i + 1], self.levels[i]
             src = coarse.tensors["interp_in"]
@@ -211,47 +202,17 @@ class PointOpsSchedule:
                     up = pointops.interpolation(coarse.coord, fine.coord, src, coarse.offset, fine.offset, k=cfg.interp_k)
                 else:
                     up = pointops.unpool_map(src, parts[i])
-            ups.append((i, up))
+            tape.append(([up], [src], [fine.tensors["g_interp"]]))
             for _ in range(cfg.dec_depths[i]):
-                fwd.append((fine,) + self._block_forward(fine, idxs[i])[1:])   # encoder's neighbour list reused
-        # ---------------- backward (reverse order) ----------------
-        acc = None
-        n_dec_blocks = sum(cfg.dec_depths)
-        pos = len(fwd)
-        for (i, up) in ups[::-1][::-1]:
-            pass
-        # decoder blocks + unpool, from the last decoder stage back
-        dec_iter = list(ups)[::-1]          # finest level first
-        for (i, up) in dec_iter:
-            fine, coarse = self.levels[i], self.levels[i + 1]
-            for _ in range(cfg.dec_depths[i]):
-                pos -= 1
-                lv, rel, out = fwd[pos]
-                g = self._block_backward(lv, rel, out)
-                acc = g[2]
-            nb = 4.0 * fine.n * fine.c + 36.0 * fine.n + 4.0 * (coarse.n + 1) + 4.0 * coarse.n * fine.c
-            with self.prof.span("unpool_bwd", nb):
-                (gsrc,) = torch.autograd.grad(up, [coarse.tensors["interp_in"]], fine.tensors["g_interp"])
-            acc = gsrc
-        for i in reversed(range(n_stage)):
-            lv, fine = self.levels[i + 1], self.levels[i]
-            for _ in range(cfg.enc_depths[i]):
-                pos -= 1
-                l2, rel, out = fwd[pos]
-                g = self._block_backward(l2, rel, out)
-            c_next = cfg.channels[i + 1]
-            nb = 8.0 * lv.n * c_next + 4.0 * fine.n * c_next + 4.0 * fine.n
-            with self.prof.span("grid_pool_bwd", nb):
-                (gin,) = torch.autograd.grad(pooled[i], [fine.tensors["pool_in"]], lv.tensors["g_pool"])
-            acc = gin
-        for _ in range(cfg.patch_depth):
-            pos -= 1
-            lv, rel, out = fwd[pos]
-            g = self._block_backward(lv, rel, out)
-            acc = g[0]
-        assert pos == 0
+                self._block_forward(fine, idxs[i], tape)   # encoder's neighbour list reused
+        # ---------------- backward: ONE pass over the recorded graph, like loss.backward() in training ------
+        # (the engine runs the nodes in reverse creation order: decoder blocks, unpool, encoder blocks, pool, ...)
+        outs = [o for rec in tape for o in rec[0]]
+        leaves = [x for rec in tape for x in rec[1]]
+        ups = [g for rec in tape for g in rec[2]]
+        grads = torch.autograd.grad(outs, leaves, ups)
         self.last_sizes = [l.n for l in self.levels[: n_stage + 1]]
-        return acc
+        return grads[0]      # grad_key of the first patch-embed block: the last gradient the pass produces
 
     # ---- totals for reporting -------------------------------------------------------------------------
     def blocks_per_level(self):

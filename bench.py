@@ -253,8 +253,7 @@ def workload_config(n_gpus):
         "channels": [48, 96, 192, 384], "groups": [6, 12, 24, 48], "blocks_per_level": [3, 3, 7, 2],
         "parallelism": f"scene-sharded x{n_gpus}" + (", fp32 grad all-reduce 14.9 MB/step (NCCL)" if n_gpus > 1 else ""),
         "l2": "per-step working set (>20 GB) exceeds the 126 MB L2; no explicit flush",
-        "streams": "latency-bound kernels (CSR walks / builds, neighbour search) overlap the HBM-bound ones on side "
-                   "streams; the %d traced steps run single-stream so per-kernel times are not inflated" % TRACE_STEPS,
+        "streams": "single stream (side-stream overlap of the latency-bound kernels measured and left off: no gain)",
     }
 
 

@@ -161,8 +161,15 @@ def check(status: int, what: str) -> None:
         raise RuntimeError(f"ao_b200.{what} failed: {msg}")
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def stream() -> int:
-    """The caller's current CUDA stream (the reference launches on the legacy default stream)."""
+    """The caller's current CUDA stream (the reference launches on the legacy default stream).
+    Raw handle of torch's current stream on the current device: torch.cuda.current_stream() builds a Python
+    Stream object per call (~3 us x ~120 calls per step on a host-bound path)."""
+    if _raw_stream is not None:
+        return _raw_stream(torch.cuda.current_device())
     return torch.cuda.current_stream().cuda_stream
 
 

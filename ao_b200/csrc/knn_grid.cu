@@ -272,10 +272,16 @@ knn_grid_kernel(int m, int b, int nsample, const float *__restrict__ new_xyz,
             const int *cs = cells + g.cell_base;
             bool done = false;
             for (int r = 1; r <= kMaxRing && !done; ++r) {
-                for (int dz = -r; dz <= r; ++dz) {
+                // rows of the block are visited centre-first (0, -1, +1, -2, +2, ...): the k-th distance drops
+                // to its final range within the first rows, so the rows further out offer far fewer candidates
+                // that pass the `<= worst` test and trigger the warp-wide insert.  The result does not depend on
+                // the visiting order (LEX ranking).
+                for (int iz = 0; iz <= 2 * r; ++iz) {
+                    const int dz = (iz & 1) ? -((iz + 1) >> 1) : (iz >> 1);
                     const int z = cz + dz;
                     if (z < 0 || z >= g.nz) continue;
-                    for (int dy = -r; dy <= r; ++dy) {
+                    for (int iy = 0; iy <= 2 * r; ++iy) {
+                        const int dy = (iy & 1) ? -((iy + 1) >> 1) : (iy >> 1);
                         const int y = cy + dy;
                         if (y < 0 || y >= g.ny) continue;
                         const int rowbase = (z * g.ny + y) * g.nx;

@@ -21,7 +21,7 @@ from .attention import (
     gva_relation,
     gva_aggregate,
 )
-from .pooling import grid_pool, voxel_partition, unpool_map, VoxelPartition
+from .pooling import grid_pool, voxel_partition, unpool_map, VoxelPartition, prepare_pyramid, pool_coord
 from .utils import (
     query_and_group,
     knn_query_and_group,

@@ -88,7 +88,7 @@ class _PoolFn(Function):
         dev = feat.device
         out_feat = torch.empty((n_vox, c), dtype=torch.float32, device=dev)
         argmax = torch.empty((n_vox, c), dtype=torch.int32, device=dev)
-        out_coord = torch.empty((n_vox, 3), dtype=torch.float32, device=dev)
+        out_coord = torch.empty((n_vox, 3), dtype=torch.float32, device=dev) if coord is not None else None
         if n_vox > 0:
             with _lib.on_device(dev):
                 _lib.check(
@@ -99,7 +99,10 @@ class _PoolFn(Function):
                 )
         ctx.save_for_backward(argmax, cluster32)
         ctx.shape = (n, c)
-        ctx.mark_non_differentiable(out_coord, argmax)
+        if out_coord is None:
+            ctx.mark_non_differentiable(argmax)
+        else:
+            ctx.mark_non_differentiable(out_coord, argmax)
         return out_feat, out_coord, argmax
 
     @staticmethod
@@ -119,14 +122,85 @@ class _PoolFn(Function):
         return grad_in, None, None, None, None, None
 
 
+def pool_coord(coord, part: VoxelPartition):
+    """Per-voxel mean of the coordinates only (the `segment_csr(coord, mean)` of …v2m2_base.py:265), same
+    sequential sum in voxel order as the fused pool kernel.  Used by prepare_pyramid, which needs the coarse
+    coordinates before any feature exists."""
+    dev = _lib.require_cuda(coord)
+    lib = _lib.load()
+    coord = coord.float().contiguous()
+    out_coord = torch.empty((part.n_vox, 3), dtype=torch.float32, device=dev)
+    if part.n_vox > 0:
+        scratch = torch.empty((part.n_vox, 3), dtype=torch.float32, device=dev)      # max / arg-max of the coords:
+        scratch_i = torch.empty((part.n_vox, 3), dtype=torch.int32, device=dev)      # by-products, not used
+        with _lib.on_device(dev):
+            _lib.check(
+                lib.aopt_pool_forward(part.n_vox, 3, _lib.ptr(coord), _lib.ptr(coord), _lib.ptr(part.order),
+                                      _lib.ptr(part.idx_ptr), _lib.ptr(scratch), _lib.ptr(scratch_i),
+                                      _lib.ptr(out_coord), _lib.stream()),
+                "pool_coord",
+            )
+    return out_coord
+
+
+def prepare_pyramid(coord, offset, grid_sizes):
+    """Voxel partitions and coarse coordinates of every GridPool stage, computed up front.
+
+    The partition is the one step of the path that needs a host synchronisation (the voxel count sizes every
+    tensor of the next level; the reference's torch.unique has the same sync).  Inside the model it sits between
+    the stages, so three times per step the host stops, the device queue drains, and the small kernels of the
+    coarse levels then run at the speed of the Python launch loop.  Coordinates do not depend on features
+    (…v2m2_base.py:246-268 uses `coord` and `offset` only), so the whole pyramid can be built first; the feature
+    path then runs without a host sync and the host stays ahead of the device.
+
+    Results are cached on the coordinate tensors: grid_pool(coord_l, feat, offset_l, grid_sizes[l]) picks them up
+    (same values as computing them inline — it is the same code).  Returns [(coord_l, offset_l int64)], l = 0..L;
+    the level-l tensors are the ones grid_pool will return for stage l-1."""
+    _lib.require_cuda(coord, offset)
+    levels = [(coord, offset)]
+    for li, gs in enumerate(grid_sizes):
+        c, o = levels[-1]
+        c32 = c.float().contiguous()
+        part = voxel_partition(c32, o, gs)
+        pooled = pool_coord(c32, part)
+        cache = getattr(c, "_aopt_pyramid", None)
+        if cache is None:
+            cache = {}
+            c._aopt_pyramid = cache
+        # level 0 belongs to the caller: the entry is valid for this offset tensor only.  Coarser coordinates are
+        # created here together with their offsets, so any cast of those offsets (same length) is accepted.
+        cache[(float(gs), int(c._version), int(o.numel()))] = (part, pooled, o.data_ptr() if li == 0 else None)
+        levels.append((pooled, part.offset))
+    return levels
+
+
+def _prepared(coord, offset, grid_size, start):
+    if start is not None:
+        return None
+    cache = getattr(coord, "_aopt_pyramid", None)
+    if not cache:
+        return None
+    hit = cache.get((float(grid_size), int(coord._version), int(offset.numel())))
+    if hit is None or (hit[2] is not None and hit[2] != offset.data_ptr()):
+        return None
+    return hit
+
+
 def grid_pool(coord, feat, offset, grid_size, start=None, return_partition=False):
     """GridPool after its fc/norm/act: returns ([coord', feat', offset'], cluster) like
     GridPool.forward (…v2m2_base.py:244-269); feat' = per-voxel max (gradient to the arg-max row),
-    coord' = per-voxel mean, offset' int64, cluster (n,) int64."""
+    coord' = per-voxel mean, offset' int64, cluster (n,) int64.
+    Uses the partition and coarse coordinates of prepare_pyramid when they were built for this coord tensor."""
     assert coord.is_contiguous() and feat.is_contiguous()
-    part = voxel_partition(coord.float(), offset, grid_size, start)
-    out_feat, out_coord, _ = _PoolFn.apply(feat.float(), coord.float(), part.order, part.idx_ptr, part.cluster32,
-                                           part.n_vox)
+    hit = _prepared(coord, offset, grid_size, start)
+    if hit is not None:
+        part, pooled, _ = hit
+        out_feat, _, _ = _PoolFn.apply(feat.float(), None, part.order, part.idx_ptr, part.cluster32, part.n_vox)
+        out_coord = pooled
+    else:
+        part = voxel_partition(coord.float(), offset, grid_size, start)
+        out_feat, out_coord, _ = _PoolFn.apply(feat.float(), coord.float(), part.order, part.idx_ptr, part.cluster32,
+                                               part.n_vox)
     if return_partition:
         return [out_coord, out_feat, part.offset], part.cluster, part
     return [out_coord, out_feat, part.offset], part.cluster

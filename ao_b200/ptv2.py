@@ -386,6 +386,7 @@ class PointTransformerV2(nn.Module):
         self.seg_head = (nn.Sequential(nn.Linear(dec_channels[0], dec_channels[0]), PointBatchNorm(dec_channels[0]),
                                        nn.ReLU(inplace=True), nn.Linear(dec_channels[0], num_classes))
                          if num_classes > 0 else nn.Identity())
+        self.hoist_pyramid = True
         # neighbour lists are shared between every BlockSequence that sees the same (coords, k)
         self._knn_cache = {}
         for m in self.modules():
@@ -399,6 +400,10 @@ class PointTransformerV2(nn.Module):
         self._knn_cache.clear()
         try:
             points = [coord, feat, offset]
+            if self.hoist_pyramid:
+                # all voxel partitions + coarse coordinates first: they depend on coordinates only, and they hold
+                # the forward pass's host synchronisations (pointops.prepare_pyramid)
+                pointops.prepare_pyramid(coord, offset, [enc.down.grid_size for enc in self.enc_stages])
             points = self.patch_embed(points)
             skips = [[points]]
             for i in range(self.num_stages):

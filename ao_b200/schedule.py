@@ -171,6 +171,9 @@ class PointOpsSchedule:
         idxs.append(idx0)
         pointops.prefetch_csr(idx0, coord.shape[0], 0)   # as ptv2.BlockSequence does when training
         poss = [pointops.group_xyz(idx0, coord)]      # (N,k,3), shared by every block on this neighbour list
+        # the coordinate pyramid (voxel partitions + coarse coordinates: the step's only host syncs) is built while
+        # the level-0 search is still running on the device; grid_pool below finds it cached on the coord tensors
+        pointops.prepare_pyramid(coord, offset, cfg.grid_sizes)
         for _ in range(cfg.patch_depth):
             self._block_forward(lv0, idx0, tape)
         for i in range(n_stage):

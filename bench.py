@@ -32,7 +32,7 @@ UNIT = "Mpoints/s"
 ROOMS_PER_GPU = 4
 POINTS_PER_ROOM = 80000
 DDP_GRAD_BYTES = 3908641 * 4   # S3DIS-cfg PTv2m2 parameters, fp32
-TRACE_STEPS = 2                # timed steps that also carry per-call CUDA events (roofline table)
+TRACE_STEPS = int(os.environ.get("AOPT_BENCH_TRACE_STEPS", "2"))   # timed steps that also carry per-call CUDA events (roofline table)
 
 
 def hbm_peak():
@@ -334,9 +334,12 @@ def run_b200_arm(args):
     trace_steps = min(TRACE_STEPS, args.steps)
     trace = []
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]   # end of every step (diagnostics)
     wall0 = time.perf_counter()
     e0.record()
     for i in range(args.steps):
+        if i > 0:
+            marks[i - 1].record()
         if i == args.steps - trace_steps:
             trace = _lib.trace_start()
             # per-kernel roofline = the kernel running ALONE: the traced steps issue everything on one stream
@@ -353,6 +356,8 @@ def run_b200_arm(args):
     launches = _lib.kernel_launches() - launches0
     clocks = sampler.stop() if sampler else None
     ms_total = e0.elapsed_time(e1)
+    bounds = [e0] + marks[: args.steps - 1] + [e1]
+    step_ms = [round(bounds[i].elapsed_time(bounds[i + 1]), 3) for i in range(args.steps)]
     t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -447,6 +452,7 @@ def run_b200_arm(args):
                                              "equiv_pairs_per_s": pairs / (knn_row["ms_per_step"] * 1e-3)},
         "kernels": kernels,
         "host_wall_ms_per_step": wall / args.steps * 1e3,
+        "step_ms": step_ms, "traced_steps": trace_steps,
     }
 
     # ---- full PTv2m2 model step (information; the dense MLPs are cuBLAS, not part of the metric) -------

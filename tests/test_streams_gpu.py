@@ -94,3 +94,35 @@ def test_schedule_step_does_not_depend_on_overlap():
             assert torch.equal(outs[0], x)
     finally:
         _lib.overlap(was)
+
+
+def test_prepared_pyramid_equals_inline_grid_pool():
+    """pointops.prepare_pyramid hoists the voxel partitions (the host syncs) in front of the feature path; grid_pool
+    must return exactly what it returns without it, level after level, gradients included."""
+    from ao_b200 import pointops, scenes
+
+    coord, _, off = scenes.s3dis_batch(3, n_points=5000)
+    grids = (0.1, 0.2, 0.4)
+    rng = np.random.default_rng(0)
+
+    def run(prepare):
+        c, o = to_cuda(coord, off)
+        if prepare:
+            levels = pointops.prepare_pyramid(c, o, grids)
+            assert len(levels) == len(grids) + 1
+        outs = []
+        for li, gs in enumerate(grids):
+            feat = torch.from_numpy(np.abs(np.random.default_rng(li).standard_normal((c.shape[0], 8))).astype(np.float32)).cuda()
+            feat.requires_grad_(True)
+            (nc, nf, no), cluster = pointops.grid_pool(c, feat, o, gs)
+            (g,) = torch.autograd.grad(nf, [feat], torch.ones_like(nf))
+            outs += [nc.clone(), nf.detach().clone(), no.clone(), cluster.clone(), g.clone()]
+            if prepare:
+                assert nc is levels[li + 1][0]
+            c, o = nc, no.int()          # an int32 cast of the offsets, as the model / schedule pass them on
+        return outs
+
+    a, b = run(False), run(True)
+    assert len(a) == len(b)
+    for x, y in zip(a, b):
+        assert x.shape == y.shape and torch.equal(x, y)

@@ -109,9 +109,11 @@ scene_bbox_kernel(int n, int b, const float *__restrict__ xyz, const int *__rest
 }
 
 void launch_scene_bbox(int n, int b, const float *xyz, const int *offset, unsigned *lo, unsigned *hi,
-                       cudaStream_t st) {
-    cudaMemsetAsync(lo, 0xff, sizeof(unsigned) * 3 * (size_t)b, st);
-    if (hi) cudaMemsetAsync(hi, 0x00, sizeof(unsigned) * 3 * (size_t)b, st);
+                       cudaStream_t st, bool init) {
+    if (init) {
+        cudaMemsetAsync(lo, 0xff, sizeof(unsigned) * 3 * (size_t)b, st);
+        if (hi) cudaMemsetAsync(hi, 0x00, sizeof(unsigned) * 3 * (size_t)b, st);
+    }
     if (n <= 0) return;
     const int grid = div_up(n, kBboxChunk);
     if (hi) scene_bbox_kernel<true><<<grid, kBboxBlock, 0, st>>>(n, b, xyz, offset, lo, hi);

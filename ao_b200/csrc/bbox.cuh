@@ -19,7 +19,9 @@ constexpr unsigned kBboxEmptyLo = 0xffffffffu;  // "no point seen" markers (mems
 constexpr unsigned kBboxEmptyHi = 0u;
 
 // lo / hi: (b,3) unsigned encodings.  hi may be NULL (minimum only).  Enqueues the memsets too.
+// init = false: the caller has already set lo to 0xffffffff and hi to 0 on this stream (the grid kNN folds
+// that into its sample kernel: three fewer memset nodes per search).
 void launch_scene_bbox(int n, int b, const float *xyz, const int *offset, unsigned *lo, unsigned *hi,
-                       cudaStream_t st);
+                       cudaStream_t st, bool init = true);
 
 }  // namespace aopt

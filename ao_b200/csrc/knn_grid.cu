@@ -68,8 +68,15 @@ constexpr int kSampleTarget = 8192;  // candidates scanned per sample after thin
 template <int K>
 __global__ void __launch_bounds__(kSampleBlock)
 knn_sample_kernel(int b, int nsample, const float *__restrict__ xyz, const int *__restrict__ offset,
-                  float *__restrict__ samples) {
+                  float *__restrict__ samples, int *__restrict__ cells, long long n_cells,
+                  unsigned *__restrict__ bb_lo, unsigned *__restrict__ bb_hi) {
     __shared__ float wmin[kSampleBlock / 32];
+    // first kernel of the search on the stream: it also clears the cell counters and resets the bounding boxes
+    // (work the following kernels need done; three memset nodes less per search)
+    for (long long i = (long long)blockIdx.x * kSampleBlock + threadIdx.x; i < n_cells; i += (long long)gridDim.x * kSampleBlock)
+        cells[i] = 0;
+    if (blockIdx.x == 0)
+        for (int i = threadIdx.x; i < 3 * b; i += kSampleBlock) { bb_lo[i] = kBboxEmptyLo; bb_hi[i] = kBboxEmptyHi; }
     const int sc = blockIdx.x / kSamples, s = blockIdx.x - sc * kSamples;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int start = sc == 0 ? 0 : __ldg(offset + sc - 1), end = __ldg(offset + sc);
@@ -381,8 +388,9 @@ static void launch_query(bool self, int m, int b, int nsample, const float *new_
 }
 
 template <int K>
-static void launch_sample(int b, int nsample, const float *xyz, const int *offset, float *samples, cudaStream_t st) {
-    knn_sample_kernel<K><<<b * kSamples, kSampleBlock, 0, st>>>(b, nsample, xyz, offset, samples);
+static void launch_sample(int b, int nsample, const float *xyz, const int *offset, const GridWs &w, cudaStream_t st) {
+    knn_sample_kernel<K><<<b * kSamples, kSampleBlock, 0, st>>>(b, nsample, xyz, offset, w.samples, w.cells,
+                                                                (long long)w.total_cells + 1, w.bbox, w.bbox + 3 * (size_t)b);
 }
 
 int knn_grid_launch(int m, int nsample, int n, int b, const float *xyz, const float *new_xyz,
@@ -400,14 +408,13 @@ int knn_grid_launch(int m, int nsample, int n, int b, const float *xyz, const fl
     }
     const bool self = (new_xyz == xyz) && (new_offset == offset) && (m == n);
 
-    cudaMemsetAsync(w.cells, 0, 4 * (w.total_cells + 1), st);
-    if (nsample <= 1) launch_sample<1>(b, nsample, xyz, offset, w.samples, st);
-    else if (nsample <= 3) launch_sample<3>(b, nsample, xyz, offset, w.samples, st);
-    else if (nsample <= 4) launch_sample<4>(b, nsample, xyz, offset, w.samples, st);
-    else if (nsample <= 8) launch_sample<8>(b, nsample, xyz, offset, w.samples, st);
-    else if (nsample <= 16) launch_sample<16>(b, nsample, xyz, offset, w.samples, st);
-    else launch_sample<32>(b, nsample, xyz, offset, w.samples, st);
-    launch_scene_bbox(n, b, xyz, offset, w.bbox, w.bbox + 3 * (size_t)b, st);
+    if (nsample <= 1) launch_sample<1>(b, nsample, xyz, offset, w, st);
+    else if (nsample <= 3) launch_sample<3>(b, nsample, xyz, offset, w, st);
+    else if (nsample <= 4) launch_sample<4>(b, nsample, xyz, offset, w, st);
+    else if (nsample <= 8) launch_sample<8>(b, nsample, xyz, offset, w, st);
+    else if (nsample <= 16) launch_sample<16>(b, nsample, xyz, offset, w, st);
+    else launch_sample<32>(b, nsample, xyz, offset, w, st);
+    launch_scene_bbox(n, b, xyz, offset, w.bbox, w.bbox + 3 * (size_t)b, st, /*init=*/false);
     grid_setup_kernel<<<div_up(b, 4), 128, 0, st>>>(b, n, offset, w.bbox, w.bbox + 3 * (size_t)b, w.samples, scale, w.desc);
     grid_count_kernel<<<div_up(n, 256), 256, 0, st>>>(n, b, xyz, offset, w.desc, w.cells, w.point_cell, w.point_slot);
     launch_exclusive_scan(w.cells, w.cells, (int)w.total_cells, w.partial, st);

@@ -217,28 +217,40 @@ def require_cuda(*tensors) -> torch.device:
 
 
 # ---- side streams --------------------------------------------------------------------------------------------
-# Experiment kept behind a switch (default OFF): issue the latency-bound kernels (GVA backward-value CSR walk,
-# CSR build) on a side stream next to the HBM-bound streaming kernels.  Measured on B200 at configs[1]
-# (scripts/exp_overlap.py, device ms per step, same box): single stream 8.52; walk overlapped with
-# gva_backward_query 8.48 (no gain: the streaming kernel slows by what the walk saves — both live off memory
-# latency, and the streaming kernel's 3 x 64 KB of shared memory per SM leaves the walk almost no L1);
-# CSR build prefetched under the forward 8.95 (a loss: its atomics and the gathers fight over L2).
-# AOPT_OVERLAP=1 / overlap(True) turns it on; results are bit-identical either way (tests/test_streams_gpu.py).
+# Experiment kept behind switches (default: everything on the caller's stream).  Three kinds of work that leave the
+# HBM pipe idle were issued on a side stream next to the HBM-bound streaming kernels; device ms per step of the
+# configs[1] schedule on one B200 (scripts/exp_overlap.py, same box, single stream first):
+#   walk  GVA backward-value CSR walk beside gva_backward_query            8.52 -> 8.48  (nothing)
+#   geom  CSR build prefetched under the forward                           8.52 -> 8.95  (a loss)
+#   knn   neighbour searches of levels 1..3 + interpolation beside the
+#         level-0 blocks (pointops.prepare_pyramid(..., knn=k))            8.30 -> 8.49  (a loss)
+# The streaming kernels run 12 warps per SM, each with ~32 copies in flight; any co-resident kernel that takes
+# issue slots (kNN), L1 (the walk: the streaming kernel's 3 x 64 KB of shared memory leaves it almost none) or L2
+# atomics (CSR build) slows them by more than it gains.  AOPT_OVERLAP=1 or AOPT_OVERLAP_ROLES=knn,walk,geom turn
+# roles on; results are bit-identical either way (tests/test_streams_gpu.py).
 _side = {}
-_overlap = os.environ.get("AOPT_OVERLAP", "0") == "1"
-
-
-_roles_off = {r for r in os.environ.get("AOPT_OVERLAP_OFF", "").split(",") if r}   # e.g. "walk" or "geom" (A/B runs)
+# mode: None = per-role defaults (_roles_on), True = every role on, False = everything on the caller's stream
+_mode = {"1": True, "0": False}.get(os.environ.get("AOPT_OVERLAP", ""), None)
+_roles_on = {r for r in os.environ.get("AOPT_OVERLAP_ROLES", "").split(",") if r}   # roles: knn, walk, geom
 
 
 def overlap(on=None, role: str = None) -> bool:
-    """Query / set whether independent kernels are issued on side streams (optionally: for one role)."""
-    global _overlap
+    """overlap(role=r): is role r issued on its side stream?  overlap(True / False): force every role on / off
+    (bench.py forces off on the steps that carry per-kernel CUDA events, tests A/B both)."""
+    global _mode
     if on is not None:
-        _overlap = bool(on)
-    if role is not None and role in _roles_off:
-        return False
-    return _overlap
+        _mode = bool(on)
+    if _mode is not None:
+        return _mode
+    return (role in _roles_on) if role is not None else bool(_roles_on)
+
+
+def overlap_mode(*set_to):
+    """Get (no argument) or restore (one argument: None / True / False) the forced mode."""
+    global _mode
+    if set_to:
+        _mode = set_to[0]
+    return _mode
 
 
 def side_stream(device, role: str = "aux") -> "torch.cuda.Stream":

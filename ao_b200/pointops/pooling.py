@@ -143,7 +143,7 @@ def pool_coord(coord, part: VoxelPartition):
     return out_coord
 
 
-def prepare_pyramid(coord, offset, grid_sizes):
+def prepare_pyramid(coord, offset, grid_sizes, knn=None, interp_k=None):
     """Voxel partitions and coarse coordinates of every GridPool stage, computed up front.
 
     The partition is the one step of the path that needs a host synchronisation (the voxel count sizes every
@@ -155,7 +155,12 @@ def prepare_pyramid(coord, offset, grid_sizes):
 
     Results are cached on the coordinate tensors: grid_pool(coord_l, feat, offset_l, grid_sizes[l]) picks them up
     (same values as computing them inline — it is the same code).  Returns [(coord_l, offset_l int64)], l = 0..L;
-    the level-l tensors are the ones grid_pool will return for stage l-1."""
+    the level-l tensors are the ones grid_pool will return for stage l-1.
+
+    knn = k (or one k per coarse level): also start the self neighbour searches of levels 1..L on the geometry
+    side stream; interp_k: and the coarse -> fine searches of the interpolation up path (query.prefetch_knn)."""
+    from .query import prefetch_knn
+
     _lib.require_cuda(coord, offset)
     levels = [(coord, offset)]
     for li, gs in enumerate(grid_sizes):
@@ -171,6 +176,15 @@ def prepare_pyramid(coord, offset, grid_sizes):
         # created here together with their offsets, so any cast of those offsets (same length) is accepted.
         cache[(float(gs), int(c._version), int(o.numel()))] = (part, pooled, o.data_ptr() if li == 0 else None)
         levels.append((pooled, part.offset))
+    if knn is not None or interp_k is not None:
+        offs32 = [levels[0][1].int()] + [o.int() for _, o in levels[1:]]
+        for l in range(1, len(levels)):
+            if knn is not None:
+                k = knn[l - 1] if isinstance(knn, (list, tuple)) else knn
+                prefetch_knn(int(k), levels[l][0], offs32[l])
+        if interp_k is not None:
+            for l in reversed(range(1, len(levels))):        # the decoder walks up from the coarsest level
+                prefetch_knn(int(interp_k), levels[l][0], offs32[l], levels[l - 1][0], offs32[l - 1])
     return levels
 
 

@@ -19,6 +19,10 @@ def knn_query_raw(nsample, xyz, offset, new_xyz=None, new_offset=None, method=No
     """Returns (idx int32 (m,k), dist2 float32 (m,k)) — squared distances, the kernel's own output."""
     if new_xyz is None or new_offset is None:
         new_xyz, new_offset = xyz, offset
+    if method is None:
+        hit = _prefetched(int(nsample), xyz, new_xyz)
+        if hit is not None:
+            return hit
     dev = _lib.require_cuda(xyz, new_xyz, offset, new_offset)
     assert xyz.is_contiguous() and new_xyz.is_contiguous()
     if xyz.dtype != torch.float32 or new_xyz.dtype != torch.float32:
@@ -50,6 +54,54 @@ def knn_query_raw(nsample, xyz, offset, new_xyz=None, new_offset=None, method=No
                                ws.numel(), _lib.stream()),
             "knn_query",
         )
+    return idx, dist2
+
+
+# ---- searches issued ahead of time on the geometry side stream (pointops.prepare_pyramid(..., knn=...)) ----------
+def _knn_key(nsample, xyz, new_xyz):
+    if new_xyz is xyz:
+        return ("self", nsample, xyz.shape[0], xyz._version)
+    return ("cross", nsample, new_xyz.data_ptr(), new_xyz.shape[0], new_xyz._version, xyz._version)
+
+
+def prefetch_knn(nsample, xyz, offset, new_xyz=None, new_offset=None):
+    """Starts the search NOW on the geometry side stream; the next knn_query / knn_query_raw / interpolation call
+    with the same tensors returns its result (after making the caller's stream wait for it).  The neighbour
+    search is ALU-bound and moves almost no memory, the streaming kernels of the feature path leave the ALUs idle:
+    run side by side they overlap (unlike the CSR walk / CSR build, see _lib.py).  No-op with overlap off."""
+    if new_xyz is None or new_offset is None:
+        new_xyz, new_offset = xyz, offset
+    if not _lib.overlap(role="knn") or new_xyz.shape[0] == 0:
+        return
+    dev = _lib.require_cuda(xyz, new_xyz, offset, new_offset)
+    main = torch.cuda.current_stream(dev)
+    side = _lib.side_stream(dev, "knn")
+    side.wait_stream(main)                                   # coordinates / offsets are produced on the caller's stream
+    with torch.cuda.stream(side):
+        idx, dist2 = knn_query_raw(nsample, xyz, offset, new_xyz, new_offset, method="auto")
+        ev = torch.cuda.Event()
+        ev.record(side)
+    for t in (xyz, new_xyz, offset, new_offset):
+        t.record_stream(side)                                # read by the side stream
+    cache = getattr(xyz, "_aopt_knn", None)
+    if cache is None:
+        cache = {}
+        xyz._aopt_knn = cache
+    cache[_knn_key(int(nsample), xyz, new_xyz)] = (idx, dist2, ev)
+
+
+def _prefetched(nsample, xyz, new_xyz):
+    cache = getattr(xyz, "_aopt_knn", None)
+    if not cache:
+        return None
+    hit = cache.pop(_knn_key(nsample, xyz, new_xyz), None)   # one consumer: the result is handed over, not kept
+    if hit is None:
+        return None
+    idx, dist2, ev = hit
+    cur = torch.cuda.current_stream(idx.device)
+    cur.wait_event(ev)
+    idx.record_stream(cur)                                   # allocated in the side stream's pool
+    dist2.record_stream(cur)
     return idx, dist2
 
 

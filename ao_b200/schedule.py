@@ -173,7 +173,8 @@ class PointOpsSchedule:
         poss = [pointops.group_xyz(idx0, coord)]      # (N,k,3), shared by every block on this neighbour list
         # the coordinate pyramid (voxel partitions + coarse coordinates: the step's only host syncs) is built while
         # the level-0 search is still running on the device; grid_pool below finds it cached on the coord tensors
-        pointops.prepare_pyramid(coord, offset, cfg.grid_sizes)
+        pointops.prepare_pyramid(coord, offset, cfg.grid_sizes, knn=k,
+                                 interp_k=cfg.interp_k if cfg.unpool == "interp" else None)
         for _ in range(cfg.patch_depth):
             self._block_forward(lv0, idx0, tape)
         for i in range(n_stage):

@@ -253,7 +253,7 @@ def workload_config(n_gpus):
         "channels": [48, 96, 192, 384], "groups": [6, 12, 24, 48], "blocks_per_level": [3, 3, 7, 2],
         "parallelism": f"scene-sharded x{n_gpus}" + (", fp32 grad all-reduce 14.9 MB/step (NCCL)" if n_gpus > 1 else ""),
         "l2": "per-step working set (>20 GB) exceeds the 126 MB L2; no explicit flush",
-        "streams": "single stream (side-stream overlap of the latency-bound kernels measured and left off: no gain)",
+        "streams": "single stream (side-stream overlap of kNN / CSR walk / CSR build measured: no gain, left off)",
     }
 
 
@@ -344,7 +344,7 @@ def run_b200_arm(args):
             trace = _lib.trace_start()
             # per-kernel roofline = the kernel running ALONE: the traced steps issue everything on one stream
             # (they are still part of the timed region, so `value` is a slight under-estimate)
-            overlap_was = _lib.overlap()
+            overlap_was = _lib.overlap_mode()
             _lib.overlap(False)
         one_step(coord, offset)
     e1.record()
@@ -352,7 +352,7 @@ def run_b200_arm(args):
     wall = time.perf_counter() - wall0
     _lib.trace_stop()
     if trace_steps:
-        _lib.overlap(overlap_was)
+        _lib.overlap_mode(overlap_was)
     launches = _lib.kernel_launches() - launches0
     clocks = sampler.stop() if sampler else None
     ms_total = e0.elapsed_time(e1)

@@ -13,7 +13,7 @@ for _ in range(3):
     sched.step(coord, offset)
 torch.cuda.synchronize()
 for mode in sys.argv[1:] or ["0", "1", "0", "1"]:
-    _lib.overlap(mode == "1")
+    _lib.overlap_mode({"1": True, "0": False}.get(mode, None))   # "d" = per-role defaults (AOPT_OVERLAP_ROLES)
     ts = []
     for i in range(8):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -24,6 +24,6 @@ for mode in sys.argv[1:] or ["0", "1", "0", "1"]:
         host = (time.perf_counter() - w0) * 1e3
         torch.cuda.synchronize()
         ts.append((e0.elapsed_time(e1), host))
-    print("overlap", mode, "roles_off", os.environ.get("AOPT_OVERLAP_OFF", ""), " device ms:", " ".join("%.2f" % a for a, _ in ts),
+    print("overlap", mode, "roles", os.environ.get("AOPT_OVERLAP_ROLES", "knn"), " device ms:", " ".join("%.2f" % a for a, _ in ts),
           " host-enqueue ms:", " ".join("%.2f" % b for _, b in ts), flush=True)
 print("mem GB", torch.cuda.memory_reserved() / 1e9, torch.cuda.memory_stats().get("num_alloc_retries"), "device mallocs", torch.cuda.memory_stats().get("num_device_alloc"))

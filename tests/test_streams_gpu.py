@@ -38,7 +38,7 @@ def test_overlapped_gva_backward_is_bit_identical():
     from ao_b200 import _lib
 
     t = _case(1)
-    was = _lib.overlap()
+    was = _lib.overlap_mode()
     try:
         _lib.overlap(False)
         ref = _aggregate_grads(t, 6, prefetch=False)
@@ -51,14 +51,14 @@ def test_overlapped_gva_backward_is_bit_identical():
             del junk
         torch.cuda.synchronize()
     finally:
-        _lib.overlap(was)
+        _lib.overlap_mode(was)
 
 
 def test_prefetched_csr_equals_lazy_build():
     from ao_b200 import _lib, pointops
 
     (idx,) = to_cuda(np.random.default_rng(3).integers(-1, 5000, (7000, 8)).astype(np.int32))
-    was = _lib.overlap()
+    was = _lib.overlap_mode()
     try:
         _lib.overlap(True)
         a = idx.clone()
@@ -72,7 +72,7 @@ def test_prefetched_csr_equals_lazy_build():
         e = int(ca.rowptr[-1])                     # entries past rowptr[-1] (dropped -1 slots) are never written
         assert torch.equal(ca.rowptr, cb.rowptr) and torch.equal(ca.perm[:e], cb.perm[:e])
     finally:
-        _lib.overlap(was)
+        _lib.overlap_mode(was)
 
 
 def test_schedule_step_does_not_depend_on_overlap():
@@ -81,7 +81,7 @@ def test_schedule_step_does_not_depend_on_overlap():
 
     coord, _, off = scenes.s3dis_batch(2, n_points=6000)
     c, o = to_cuda(coord, off)
-    was = _lib.overlap()
+    was = _lib.overlap_mode()
     try:
         outs = []
         for on in (False, True, True):
@@ -93,7 +93,7 @@ def test_schedule_step_does_not_depend_on_overlap():
         for x in outs[1:]:
             assert torch.equal(outs[0], x)
     finally:
-        _lib.overlap(was)
+        _lib.overlap_mode(was)
 
 
 def test_prepared_pyramid_equals_inline_grid_pool():
@@ -126,3 +126,31 @@ def test_prepared_pyramid_equals_inline_grid_pool():
     assert len(a) == len(b)
     for x, y in zip(a, b):
         assert x.shape == y.shape and torch.equal(x, y)
+
+
+def test_prefetched_knn_equals_direct_search():
+    from ao_b200 import _lib, pointops, scenes
+
+    coord, _, off = scenes.s3dis_batch(2, n_points=7000)
+    c, o = to_cuda(coord, off)
+    fine, foff = c, o
+    (coarse, _, coff), _ = pointops.grid_pool(c, c.clone(), o, 0.2)
+    coff = coff.int()
+    was = _lib.overlap_mode()
+    try:
+        _lib.overlap(False)
+        ref_self = pointops.knn_query_raw(16, coarse, coff)
+        ref_cross = pointops.knn_query_raw(3, coarse, coff, fine, foff)
+        _lib.overlap(True)
+        for _ in range(3):
+            pointops.prefetch_knn(16, coarse, coff)
+            pointops.prefetch_knn(3, coarse, coff, fine, foff)
+            assert len(coarse._aopt_knn) == 2
+            got_cross = pointops.knn_query_raw(3, coarse, coff, fine, foff)
+            got_self = pointops.knn_query_raw(16, coarse, coff)
+            assert len(coarse._aopt_knn) == 0                 # handed over, not kept
+            for a, b in zip(ref_self + ref_cross, got_self + got_cross):
+                assert torch.equal(a, b)
+        torch.cuda.synchronize()
+    finally:
+        _lib.overlap_mode(was)

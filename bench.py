@@ -328,6 +328,13 @@ def run_b200_arm(args):
         sampler.start()
         time.sleep(0.3)
     barrier()
+    # the GPU idled while the clock sampler started: one more untimed step brings clocks / power state back up
+    # (without it the first two or three timed steps run 5-20 % slow), and the Python GC stays off while timing
+    one_step(coord, offset)
+    barrier()
+    import gc
+    gc.collect()
+    gc.disable()
     launches0 = _lib.kernel_launches()
     # per-call CUDA events are recorded on TRACE_STEPS of the timed steps (an event pair per call on all
     # ~200 calls of every step costs ~1 ms/step of host time, which would distort the step time)
@@ -381,10 +388,13 @@ def run_b200_arm(args):
             ev.record(copy_stream)
         return c, f, o, ev
 
+    e2e_step_ms = []
+
     def e2e_loop(steps):
         last = 0.0
         nxt = stage()
         for i in range(steps):
+            t_step = time.perf_counter()
             c, f, o, ev = nxt
             cur = torch.cuda.current_stream(dev)
             cur.wait_event(ev)
@@ -395,12 +405,14 @@ def run_b200_arm(args):
             acc = one_step(c, o)
             del f
             last = float(acc.sum().item())   # D2H read of the step result (the loss stand-in)
+            e2e_step_ms.append(round((time.perf_counter() - t_step) * 1e3, 3))
         return last
 
     e2e_steps = 0 if args.skip_e2e else args.steps
     if e2e_steps:
         e2e_loop(1)
     barrier()
+    del e2e_step_ms[:]
     w0 = time.perf_counter()
     e2e_loop(e2e_steps)
     barrier()
@@ -409,6 +421,7 @@ def run_b200_arm(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t.item())
+    gc.enable()
     e2e_value = world * n0 * e2e_steps / e2e_s / 1e6
     h2d = coord_h.numel() * 4 + feat_h.numel() * 4 + off_h.numel() * 4
 
@@ -473,7 +486,7 @@ def run_b200_arm(args):
                                              "equiv_pairs_per_s": pairs / (knn_row["ms_per_step"] * 1e-3)},
         "kernels": kernels,
         "host_wall_ms_per_step": wall / args.steps * 1e3,
-        "step_ms": step_ms, "traced_steps": trace_steps,
+        "step_ms": step_ms, "traced_steps": trace_steps, "e2e_step_ms": e2e_step_ms,
     }
 
     # ---- full PTv2m2 model step (information; the dense MLPs are cuBLAS, not part of the metric) -------

@@ -36,7 +36,16 @@
 namespace aopt {
 
 constexpr int kSamples = 64;        // sample points per scene for the density estimate
-constexpr int kCellsPerPoint = 4;   // grid capacity: 4 cells per candidate + 64 per scene
+// grid capacity: cells per candidate (+ 64 per scene).  Indoor scans are surfaces: most cells of the volume are empty, so the
+// capacity — not the sampled k-th neighbour distance — usually fixes the cell edge.  AOPT_KNN_CELLS_PER_POINT overrides (sweeps).
+static int cells_per_point() {
+    static const int v = [] {
+        int d = 4;
+        if (const char *e = getenv("AOPT_KNN_CELLS_PER_POINT")) { int x = atoi(e); if (x >= 1 && x <= 64) d = x; }
+        return d;
+    }();
+    return v;
+}
 constexpr int kCellsPerScene = 64;
 constexpr int kMaxRing = 8;         // beyond this shell radius a query falls back to a full scan
 constexpr int kQueryBlock = 128;
@@ -144,7 +153,7 @@ knn_sample_kernel(int b, int nsample, const float *__restrict__ xyz, const int *
 __global__ void __launch_bounds__(128)
 grid_setup_kernel(int b, int n, const int *__restrict__ offset, const unsigned *__restrict__ bb_lo,
                   const unsigned *__restrict__ bb_hi, const float *__restrict__ samples, float cell_scale,
-                  GridDesc *__restrict__ desc) {
+                  int kCellsPerPoint, GridDesc *__restrict__ desc) {
     const int sc = blockIdx.x * 4 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (sc >= b) return;
@@ -357,7 +366,7 @@ static GridWs carve(void *ws, int n, int b) {
     GridWs w;
     char *p = static_cast<char *>(ws);
     size_t off = 0;
-    w.total_cells = (size_t)kCellsPerPoint * n + (size_t)kCellsPerScene * b;
+    w.total_cells = (size_t)cells_per_point() * n + (size_t)kCellsPerScene * b;
     w.desc = reinterpret_cast<GridDesc *>(p + off); off += a256(sizeof(GridDesc) * (size_t)(b > 0 ? b : 1));
     w.samples = reinterpret_cast<float *>(p + off); off += a256(4 * (size_t)kSamples * (b > 0 ? b : 1));
     w.bbox = reinterpret_cast<unsigned *>(p + off); off += a256(4 * 6 * (size_t)(b > 0 ? b : 1));
@@ -415,7 +424,7 @@ int knn_grid_launch(int m, int nsample, int n, int b, const float *xyz, const fl
     else if (nsample <= 16) launch_sample<16>(b, nsample, xyz, offset, w, st);
     else launch_sample<32>(b, nsample, xyz, offset, w, st);
     launch_scene_bbox(n, b, xyz, offset, w.bbox, w.bbox + 3 * (size_t)b, st, /*init=*/false);
-    grid_setup_kernel<<<div_up(b, 4), 128, 0, st>>>(b, n, offset, w.bbox, w.bbox + 3 * (size_t)b, w.samples, scale, w.desc);
+    grid_setup_kernel<<<div_up(b, 4), 128, 0, st>>>(b, n, offset, w.bbox, w.bbox + 3 * (size_t)b, w.samples, scale, cells_per_point(), w.desc);
     grid_count_kernel<<<div_up(n, 256), 256, 0, st>>>(n, b, xyz, offset, w.desc, w.cells, w.point_cell, w.point_slot);
     launch_exclusive_scan(w.cells, w.cells, (int)w.total_cells, w.partial, st);
     grid_fill_kernel<<<div_up(n, 256), 256, 0, st>>>(n, xyz, w.cells, w.point_cell, w.point_slot, w.sorted);

@@ -410,7 +410,9 @@ def run_b200_arm(args):
 
     e2e_steps = 0 if args.skip_e2e else args.steps
     if e2e_steps:
-        e2e_loop(1)
+        # warm-up of this leg too: its copy-stream buffers are new allocations (the first two steps of a cold loop
+        # took 37 and 16 ms in cudaMalloc, against 8.4 ms once the double buffers exist)
+        e2e_loop(max(3, args.warmup))
     barrier()
     del e2e_step_ms[:]
     w0 = time.perf_counter()

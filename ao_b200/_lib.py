@@ -71,6 +71,7 @@ SIGNATURES = {
 }
 
 KNN_AUTO, KNN_TILE, KNN_GRID = 0, 1, 2
+KNN_SQRT_DIST = 0x100   # OR-ed into the method: the kernel writes sqrt(dist2)
 
 _lib = None
 _trace = None  # list of (entry point, args, start event, end event) while bench.py's profiler is on

@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(BLOCK)
 knn_tile_kernel(int m, int n, int b, int nsample, const float *__restrict__ xyz,
                 const float *__restrict__ new_xyz, const int *__restrict__ offset,
                 const int *__restrict__ new_offset, int *__restrict__ idx_out,
-                float *__restrict__ dist2_out) {
+                float *__restrict__ dist2_out, bool root) {
     __shared__ float4 tile[kKnnTile];
     __shared__ int range_s[2];
 
@@ -99,7 +99,7 @@ knn_tile_kernel(int m, int n, int b, int nsample, const float *__restrict__ xyz,
             top.offer(dist2_ref(qx, qy, qz, c0.x, c0.y, c0.z), base + j);
         }
     }
-    if (valid) top.store(idx_out + (size_t)q * nsample, dist2_out + (size_t)q * nsample, nsample);
+    if (valid) top.store(idx_out + (size_t)q * nsample, dist2_out + (size_t)q * nsample, nsample, root);
 }
 
 // nsample in (32, 128]: same scan, k best kept in a local-memory sorted list (rare path; the
@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(kKnnBlock)
 knn_tile_bigk_kernel(int m, int n, int b, int nsample, const float *__restrict__ xyz,
                      const float *__restrict__ new_xyz, const int *__restrict__ offset,
                      const int *__restrict__ new_offset, int *__restrict__ idx_out,
-                     float *__restrict__ dist2_out) {
+                     float *__restrict__ dist2_out, bool root) {
     const int q = blockIdx.x * kKnnBlock + threadIdx.x;
     if (q >= m) return;
     int start = 0, end = 0;
@@ -135,41 +135,41 @@ knn_tile_bigk_kernel(int m, int n, int b, int nsample, const float *__restrict__
     }
     for (int i = 0; i < nsample; ++i) {
         idx_out[(size_t)q * nsample + i] = bi[i];
-        dist2_out[(size_t)q * nsample + i] = bd[i];
+        dist2_out[(size_t)q * nsample + i] = root ? __fsqrt_rn(bd[i]) : bd[i];
     }
 }
 
 template <int K>
 static void launch_tile(int m, int n, int b, int nsample, const float *xyz, const float *new_xyz,
                         const int *offset, const int *new_offset, int *idx, float *dist2,
-                        cudaStream_t st) {
+                        bool root, cudaStream_t st) {
     // a 256-thread CTA per 256 queries leaves most SMs idle below ~38k queries (level 3: 2868 queries = 12 CTAs)
     if (m <= kKnnSmallBlock * kNumSM * 4)
         knn_tile_kernel<K, kKnnSmallBlock><<<div_up(m, kKnnSmallBlock), kKnnSmallBlock, 0, st>>>(
-            m, n, b, nsample, xyz, new_xyz, offset, new_offset, idx, dist2);
+            m, n, b, nsample, xyz, new_xyz, offset, new_offset, idx, dist2, root);
     else
         knn_tile_kernel<K, kKnnBlock><<<div_up(m, kKnnBlock), kKnnBlock, 0, st>>>(m, n, b, nsample, xyz, new_xyz, offset,
-                                                                                  new_offset, idx, dist2);
+                                                                                  new_offset, idx, dist2, root);
 }
 
 int knn_tile_launch(int m, int nsample, int n, int b, const float *xyz, const float *new_xyz,
                     const int *offset, const int *new_offset, int *idx, float *dist2,
-                    cudaStream_t st) {
-    if (nsample <= 1) launch_tile<1>(m, n, b, nsample, xyz, new_xyz, offset, new_offset, idx, dist2, st);
-    else if (nsample <= 4) launch_tile<4>(m, n, b, nsample, xyz, new_xyz, offset, new_offset, idx, dist2, st);
-    else if (nsample <= 8) launch_tile<8>(m, n, b, nsample, xyz, new_xyz, offset, new_offset, idx, dist2, st);
-    else if (nsample <= 16) launch_tile<16>(m, n, b, nsample, xyz, new_xyz, offset, new_offset, idx, dist2, st);
-    else if (nsample <= 32) launch_tile<32>(m, n, b, nsample, xyz, new_xyz, offset, new_offset, idx, dist2, st);
+                    bool root, cudaStream_t st) {
+    if (nsample <= 1) launch_tile<1>(m, n, b, nsample, xyz, new_xyz, offset, new_offset, idx, dist2, root, st);
+    else if (nsample <= 4) launch_tile<4>(m, n, b, nsample, xyz, new_xyz, offset, new_offset, idx, dist2, root, st);
+    else if (nsample <= 8) launch_tile<8>(m, n, b, nsample, xyz, new_xyz, offset, new_offset, idx, dist2, root, st);
+    else if (nsample <= 16) launch_tile<16>(m, n, b, nsample, xyz, new_xyz, offset, new_offset, idx, dist2, root, st);
+    else if (nsample <= 32) launch_tile<32>(m, n, b, nsample, xyz, new_xyz, offset, new_offset, idx, dist2, root, st);
     else
         knn_tile_bigk_kernel<<<div_up(m, kKnnBlock), kKnnBlock, 0, st>>>(m, n, b, nsample, xyz, new_xyz, offset,
-                                                                        new_offset, idx, dist2);
+                                                                        new_offset, idx, dist2, root);
     return check_launch();
 }
 
 // part 2 (knn_grid.cu)
 size_t knn_grid_workspace_bytes(int n, int m, int b);
 int knn_grid_launch(int m, int nsample, int n, int b, const float *xyz, const float *new_xyz,
-                    const int *offset, const int *new_offset, int *idx, float *dist2, void *ws,
+                    const int *offset, const int *new_offset, int *idx, float *dist2, bool root, void *ws,
                     size_t ws_bytes, cudaStream_t st);
 
 }  // namespace aopt
@@ -199,6 +199,7 @@ static int pick_method(int n, int m, int b, int nsample, int method) {
 
 extern "C" size_t aopt_knn_workspace_bytes(int n, int m, int b, int nsample, int method) {
     if (n < 0 || m < 0 || b < 0) return 0;
+    method &= ~AOPT_KNN_SQRT_DIST;
     if (pick_method(n, m, b, nsample, method) != AOPT_KNN_GRID) return 0;
     return knn_grid_workspace_bytes(n, m, b);
 }
@@ -208,6 +209,8 @@ extern "C" int aopt_knn_query(int m, int nsample, int n, int b, const float *xyz
                               int *idx, float *dist2, int method, void *workspace,
                               size_t workspace_bytes, aopt_stream_t stream) {
     if (m < 0 || n < 0 || b < 0 || nsample < 1 || nsample > AOPT_MAX_NSAMPLE) return AOPT_ERR_INVALID_ARGUMENT;
+    const bool root = (method & AOPT_KNN_SQRT_DIST) != 0;   // distances instead of squared distances
+    method &= ~AOPT_KNN_SQRT_DIST;
     if (method < AOPT_KNN_AUTO || method > AOPT_KNN_GRID) return AOPT_ERR_INVALID_ARGUMENT;
     if (m == 0) return AOPT_OK;
     if (!new_xyz || !idx || !dist2 || (n > 0 && !xyz) || (b > 0 && (!offset || !new_offset)))
@@ -218,8 +221,8 @@ extern "C" int aopt_knn_query(int m, int nsample, int n, int b, const float *xyz
         if (nsample > 32) return AOPT_ERR_UNSUPPORTED;
         size_t need = knn_grid_workspace_bytes(n, m, b);
         if (!workspace || workspace_bytes < need) return AOPT_ERR_WORKSPACE;
-        return knn_grid_launch(m, nsample, n, b, xyz, new_xyz, offset, new_offset, idx, dist2, workspace,
+        return knn_grid_launch(m, nsample, n, b, xyz, new_xyz, offset, new_offset, idx, dist2, root, workspace,
                                workspace_bytes, st);
     }
-    return knn_tile_launch(m, nsample, n, b, xyz, new_xyz, offset, new_offset, idx, dist2, st);
+    return knn_tile_launch(m, nsample, n, b, xyz, new_xyz, offset, new_offset, idx, dist2, root, st);
 }

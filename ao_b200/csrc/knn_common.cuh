@@ -78,10 +78,10 @@ struct TopK {
             id[0] = lt[0] ? i : id[0];
         }
     }
-    __device__ __forceinline__ void store(int *idx_row, float *d2_row, int nsample) const {
+    __device__ __forceinline__ void store(int *idx_row, float *d2_row, int nsample, bool root = false) const {
 #pragma unroll
         for (int i = 0; i < K; ++i) {
-            if (i < nsample) { idx_row[i] = id[i]; d2_row[i] = d[i]; }
+            if (i < nsample) { idx_row[i] = id[i]; d2_row[i] = root ? __fsqrt_rn(d[i]) : d[i]; }
         }
     }
 };

@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(kQueryBlock)
 knn_grid_kernel(int m, int b, int nsample, const float *__restrict__ new_xyz,
                 const int *__restrict__ new_offset, const GridDesc *__restrict__ desc,
                 const int *__restrict__ cells, const float4 *__restrict__ sorted,
-                int *__restrict__ idx_out, float *__restrict__ dist2_out) {
+                int *__restrict__ idx_out, float *__restrict__ dist2_out, bool root) {
     const int t = blockIdx.x * kQueryBlock + threadIdx.x;
     if (t >= m) return;
     const int sc = find_segment(t, new_offset, b);
@@ -344,7 +344,7 @@ knn_grid_kernel(int m, int b, int nsample, const float *__restrict__ new_xyz,
             }
         }
     }
-    top.store(idx_out + (size_t)row * nsample, dist2_out + (size_t)row * nsample, nsample);
+    top.store(idx_out + (size_t)row * nsample, dist2_out + (size_t)row * nsample, nsample, root);
 }
 
 // ---- host side -------------------------------------------------------------------------------------
@@ -386,14 +386,14 @@ size_t knn_grid_workspace_bytes(int n, int m, int b) {
 
 template <int K>
 static void launch_query(bool self, int m, int b, int nsample, const float *new_xyz, const int *new_offset,
-                         const GridWs &w, int *idx, float *dist2, cudaStream_t st) {
+                         const GridWs &w, int *idx, float *dist2, bool root, cudaStream_t st) {
     const int grid = div_up(m, kQueryBlock);
     if (self)
         knn_grid_kernel<K, true><<<grid, kQueryBlock, 0, st>>>(m, b, nsample, new_xyz, new_offset, w.desc, w.cells,
-                                                               w.sorted, idx, dist2);
+                                                               w.sorted, idx, dist2, root);
     else
         knn_grid_kernel<K, false><<<grid, kQueryBlock, 0, st>>>(m, b, nsample, new_xyz, new_offset, w.desc, w.cells,
-                                                                w.sorted, idx, dist2);
+                                                                w.sorted, idx, dist2, root);
 }
 
 template <int K>
@@ -403,7 +403,7 @@ static void launch_sample(int b, int nsample, const float *xyz, const int *offse
 }
 
 int knn_grid_launch(int m, int nsample, int n, int b, const float *xyz, const float *new_xyz,
-                    const int *offset, const int *new_offset, int *idx, float *dist2, void *ws,
+                    const int *offset, const int *new_offset, int *idx, float *dist2, bool root, void *ws,
                     size_t ws_bytes, cudaStream_t st) {
     if (b <= 0 || n <= 0) {  // no candidates: everything is padding
         return AOPT_ERR_INVALID_ARGUMENT;
@@ -428,12 +428,12 @@ int knn_grid_launch(int m, int nsample, int n, int b, const float *xyz, const fl
     grid_count_kernel<<<div_up(n, 256), 256, 0, st>>>(n, b, xyz, offset, w.desc, w.cells, w.point_cell, w.point_slot);
     launch_exclusive_scan(w.cells, w.cells, (int)w.total_cells, w.partial, st);
     grid_fill_kernel<<<div_up(n, 256), 256, 0, st>>>(n, xyz, w.cells, w.point_cell, w.point_slot, w.sorted);
-    if (nsample <= 1) launch_query<1>(self, m, b, nsample, new_xyz, new_offset, w, idx, dist2, st);
-    else if (nsample <= 3) launch_query<3>(self, m, b, nsample, new_xyz, new_offset, w, idx, dist2, st);
-    else if (nsample <= 4) launch_query<4>(self, m, b, nsample, new_xyz, new_offset, w, idx, dist2, st);
-    else if (nsample <= 8) launch_query<8>(self, m, b, nsample, new_xyz, new_offset, w, idx, dist2, st);
-    else if (nsample <= 16) launch_query<16>(self, m, b, nsample, new_xyz, new_offset, w, idx, dist2, st);
-    else launch_query<32>(self, m, b, nsample, new_xyz, new_offset, w, idx, dist2, st);
+    if (nsample <= 1) launch_query<1>(self, m, b, nsample, new_xyz, new_offset, w, idx, dist2, root, st);
+    else if (nsample <= 3) launch_query<3>(self, m, b, nsample, new_xyz, new_offset, w, idx, dist2, root, st);
+    else if (nsample <= 4) launch_query<4>(self, m, b, nsample, new_xyz, new_offset, w, idx, dist2, root, st);
+    else if (nsample <= 8) launch_query<8>(self, m, b, nsample, new_xyz, new_offset, w, idx, dist2, root, st);
+    else if (nsample <= 16) launch_query<16>(self, m, b, nsample, new_xyz, new_offset, w, idx, dist2, root, st);
+    else launch_query<32>(self, m, b, nsample, new_xyz, new_offset, w, idx, dist2, root, st);
     return check_launch(7);  // sample, bbox, setup, count, scan, fill, query
 }
 

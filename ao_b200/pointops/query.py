@@ -15,14 +15,15 @@ from .. import _lib
 _METHODS = {"auto": _lib.KNN_AUTO, "tile": _lib.KNN_TILE, "grid": _lib.KNN_GRID}
 
 
-def knn_query_raw(nsample, xyz, offset, new_xyz=None, new_offset=None, method=None):
-    """Returns (idx int32 (m,k), dist2 float32 (m,k)) — squared distances, the kernel's own output."""
+def knn_query_raw(nsample, xyz, offset, new_xyz=None, new_offset=None, method=None, root=False):
+    """Returns (idx int32 (m,k), dist2 float32 (m,k)) — squared distances, the kernel's own output.
+    root=True: the kernel writes sqrt(dist2) instead (AOPT_KNN_SQRT_DIST), the reference's return (query.py:24)."""
     if new_xyz is None or new_offset is None:
         new_xyz, new_offset = xyz, offset
     if method is None:
         hit = _prefetched(int(nsample), xyz, new_xyz)
         if hit is not None:
-            return hit
+            return (hit[0], torch.sqrt(hit[1])) if root else hit
     dev = _lib.require_cuda(xyz, new_xyz, offset, new_offset)
     assert xyz.is_contiguous() and new_xyz.is_contiguous()
     if xyz.dtype != torch.float32 or new_xyz.dtype != torch.float32:
@@ -41,6 +42,8 @@ def knn_query_raw(nsample, xyz, offset, new_xyz=None, new_offset=None, method=No
     if method is None:
         method = os.environ.get("AOPT_KNN_METHOD", "auto")
     meth = _METHODS[method] if isinstance(method, str) else int(method)
+    if root:
+        meth |= _lib.KNN_SQRT_DIST
     lib = _lib.load()
     idx = torch.empty((m, nsample), dtype=torch.int32, device=dev)
     dist2 = torch.empty((m, nsample), dtype=torch.float32, device=dev)
@@ -112,9 +115,8 @@ class KNNQuery(Function):
         input: xyz: (n, 3), new_xyz: (m, 3), offset: (b), new_offset: (b)
         output: idx: (m, nsample) -1 is placeholder, dist: (m, nsample)
         """
-        idx, dist2 = knn_query_raw(nsample, xyz, offset, new_xyz, new_offset)
+        idx, dist = knn_query_raw(nsample, xyz, offset, new_xyz, new_offset, root=True)   # sqrt of query.py:24 in-kernel
         ctx.mark_non_differentiable(idx)
-        dist = torch.sqrt(dist2)                             # query.py:24
         ctx.mark_non_differentiable(dist)
         return idx, dist
 

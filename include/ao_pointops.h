@@ -56,6 +56,9 @@ enum {
 
 /* kNN search strategy (all three are exact and return identical results). */
 enum { AOPT_KNN_AUTO = 0, AOPT_KNN_TILE = 1, AOPT_KNN_GRID = 2 };
+/* OR-ed into `method`: write sqrt(dist2) (IEEE round-to-nearest, == torch.sqrt of the squared output) into the
+ * distance buffer — what the reference's Python returns (functions/query.py:24) without a second kernel. */
+enum { AOPT_KNN_SQRT_DIST = 0x100 };
 
 const char *aopt_version(void);
 const char *aopt_status_string(int status);

@@ -147,6 +147,16 @@ def test_python_api_matches_reference_signature():
     assert idx.dtype == torch.int32 and dist.dtype == torch.float32 and idx.shape == (xyz.shape[0], 16)
     idx64, _ = pointops.knn_query(16, xyz, off.long())          # int64 offsets (models/utils.py:28)
     assert torch.equal(idx, idx64)
+    # the sqrt of query.py:24 is applied inside the kernel (AOPT_KNN_SQRT_DIST): same bits as torch.sqrt(dist2)
+    for method in ("tile", "grid"):
+        i2, d2 = pointops.knn_query_raw(16, xyz, off, method=method)
+        i1, d1 = pointops.knn_query_raw(16, xyz, off, method=method, root=True)
+        assert torch.equal(i1, i2) and torch.equal(d1, torch.sqrt(d2))
+    big = torch.from_numpy(np.random.default_rng(0).random((3000, 3)).astype(np.float32)).cuda()
+    boff = torch.tensor([3000], dtype=torch.int32, device="cuda")
+    i2, d2 = pointops.knn_query_raw(40, big, boff)             # nsample > 32: the local-memory kernel
+    i1, d1 = pointops.knn_query_raw(40, big, boff, root=True)
+    assert torch.equal(i1, i2) and torch.equal(d1, torch.sqrt(d2))
     # padding convention of query.py:24: sqrt(1e10) = 1e5
     assert torch.all(dist[700:705, 5:] == 1e5) and torch.all(idx[700:705, 5:] == -1)
     with pytest.raises(ValueError):

@@ -26,7 +26,7 @@ if [ "${SKIP_NCU:-0}" != "1" ]; then
   tail -2 $O/ncu_full.log
   # gpurun_out/ is capped at 64 MiB: export what we read (raw metrics + per-kernel source pages) and drop the report
   ncu -i $O/ops_L0.ncu-rep --page raw --csv > $O/ops_L0_raw.csv 2> /dev/null
-  for kname in gva_forward_kernel gva_backward_query_kernel gva_backward_value_kernel gather_sub_kernel segmented_sum_kernel sum_over_k_kernel knn_grid_kernel group_xyz_kernel csr_rank_kernel pool_forward_kernel; do
+  for kname in gva_forward_ns_kernel gva_backward_query_ns_kernel csr_walk_kernel gather_sub_ns_kernel relation_backward_vec_kernel knn_grid_kernel group_xyz_packed_kernel csr_rank_kernel pool_forward_kernel interp_forward_kernel; do
     ncu -i $O/ops_L0.ncu-rep --page source --csv -k regex:$kname -c 1 > $O/src_$kname.csv 2> /dev/null
   done
   rm -f $O/ops_L0.ncu-rep

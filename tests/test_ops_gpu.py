@@ -368,3 +368,34 @@ def test_relation_backward_fused_equals_the_two_pass_kernels(c):
     key, query = (torch.randn(n, c, device="cuda", generator=g, requires_grad=True) for _ in range(2))
     a, b = torch.autograd.grad(pointops.gva_relation(key, query, idx), [key, query], grad)
     assert torch.equal(a, gk2) and torch.equal(b, gq2)
+
+
+# ------------------------------------------------------------------------------------------ per-scene bounding box
+@pytest.mark.parametrize("sizes", [
+    [5000, 1, 0, 3000, 2047, 2049, 7],            # empty scene, scenes ending right around the 2048-point chunks
+    [1] * 300,                                    # hundreds of one-point scenes inside one chunk
+    [3, 0, 0, 4100, 0, 2],                        # consecutive empty scenes
+    [10000],                                      # B = 1
+])
+def test_segment_min3_matches_numpy_on_adversarial_layouts(sizes):
+    """aopt_segment_min3 (csrc/bbox.cu): chunks that straddle scene boundaries take the masked warp-reduction path;
+    the result must be the exact per-scene minimum (…v2m2_base.py:249-253 `segment_csr(coord, ptr, reduce="min")`)."""
+    from ao_b200 import _lib
+
+    rng = np.random.default_rng(len(sizes))
+    n = int(sum(sizes))
+    coord = (rng.standard_normal((n + 5, 3)) * 10).astype(np.float32)     # 5 points past the last offset: no scene
+    off = np.cumsum(sizes).astype(np.int32)
+    c, o = to_cuda(coord, off)
+    start = torch.empty((len(sizes), 3), dtype=torch.float32, device="cuda")
+    lib = _lib.load()
+    _lib.check(lib.aopt_segment_min3(n + 5, len(sizes), _lib.ptr(c), _lib.ptr(o), _lib.ptr(start), _lib.stream()),
+               "segment_min3")
+    got = start.cpu().numpy()
+    s = 0
+    for b, e in enumerate(off):
+        if e > s:
+            assert np.array_equal(got[b], coord[s:e].min(axis=0)), b
+        else:
+            assert np.array_equal(got[b], np.zeros(3, np.float32)), b       # segment_csr's fill value for an empty segment
+        s = e

@@ -43,18 +43,10 @@ inline int walk_batch() {  // entries per batch: 8 (default) or 4 (AOPT_WALK_B=4
     return b;
 }
 
-inline int gcd_int(int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; }
-
 // CTAs for a walk over n_rows x chunks items: a multiple of chunks / gcd(chunks, kWalkBlock), at most
-// ctas_per_sm x 148, at least one multiple.
+// ctas_per_sm x 148, at least one multiple (common.cuh col_grid).
 inline int walk_grid(long long n_rows, int chunks, int ctas_per_sm) {
-    const int unit = chunks / gcd_int(chunks, kWalkBlock);
-    long long need = (n_rows * chunks + kWalkBlock - 1) / kWalkBlock;
-    long long cap = (long long)kNumSM * ctas_per_sm;
-    long long grid = need < cap ? need : cap;
-    grid = (grid / unit) * unit;
-    if (grid < unit) grid = unit;
-    return (int)grid;
+    return col_grid(n_rows, chunks, kWalkBlock, ctas_per_sm);
 }
 
 // Policy P:

@@ -92,7 +92,8 @@ class _Entry:
     def __call__(self, *args):
         if _trace is None or not self.traced:
             return self.fn(*args)
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s = _event_pool.pop() if _event_pool else torch.cuda.Event(enable_timing=True)
+        e = _event_pool.pop() if _event_pool else torch.cuda.Event(enable_timing=True)
         s.record()
         status = self.fn(*args)
         e.record()
@@ -105,6 +106,16 @@ class _Library:
 
     def __init__(self, cdll):
         self._cdll = cdll
+
+
+_event_pool = []
+
+
+def trace_prepare(n_events: int = 1024) -> None:
+    """Creates the CUDA events of a traced step ahead of time (outside the timed region): creating ~270 events
+    inside the step costs more host time than recording them."""
+    while len(_event_pool) < n_events:
+        _event_pool.append(torch.cuda.Event(enable_timing=True))
 
 
 def trace_start() -> list:

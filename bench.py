@@ -335,6 +335,7 @@ def run_b200_arm(args):
     import gc
     gc.collect()
     gc.disable()
+    _lib.trace_prepare(1024 * max(1, min(TRACE_STEPS, args.steps)))
     launches0 = _lib.kernel_launches()
     # per-call CUDA events are recorded on TRACE_STEPS of the timed steps (an event pair per call on all
     # ~200 calls of every step costs ~1 ms/step of host time, which would distort the step time)

@@ -212,26 +212,55 @@ class BlockSequence(nn.Module):
             self.blocks.append(Block(embed_channels=embed_channels, groups=groups, qkv_bias=qkv_bias,
                                      pe_multiplier=pe_multiplier, pe_bias=pe_bias, attn_drop_rate=attn_drop_rate,
                                      drop_path_rate=drop_path_rates[i], enable_checkpoint=enable_checkpoint))
-        self.knn_cache = None  # set by PointTransformerV2: {(coord ptr, n, offset ptr, k): (idx, pos, pos moments)}
+        self.knn_cache = None  # set by PointTransformerV2: {(coord ptr, n, offset ptr, k): (coord, offset, idx, pos, moments)}
+        self.search_neighbours = neighbours   # PointTransformerV2 raises it to the largest k used on this level
+
+    def _neighbour_list(self, coord, offset, feat):
+        """(idx, pos, pos moments) of this sequence's k, shared by every BlockSequence that sees the same coordinate
+        tensor.  A level that is used with two different k (ScanNet cfg: patch-embed k=8, last decoder k=16 on the
+        level-0 coordinates) is searched ONCE with the larger k: the result is ordered by (dist2, idx), so the smaller
+        list is its first k columns."""
+        k = self.neighbours
+        cache = self.knn_cache
+
+        def lookup(kk):
+            hit = None if cache is None else cache.get((coord.data_ptr(), coord.shape[0], offset.data_ptr(), kk))
+            # the entry pins its tensors: a data_ptr match alone could be a recycled allocation
+            return hit if hit is not None and hit[0] is coord and hit[1] is offset else None
+
+        hit = lookup(k)
+        if hit is not None:
+            return hit[2:]
+        ks = max(self.search_neighbours, k)
+        wide = lookup(ks) if ks != k else None
+        if wide is not None:
+            idx_wide = wide[2]
+        else:
+            idx_wide, _ = pointops.knn_query(ks, coord, offset)                          # :223
+        training = torch.is_grad_enabled() and feat.requires_grad
+        out = None
+        for kk in sorted({k, ks}, reverse=True):
+            if kk == ks and wide is not None:
+                continue
+            idx = idx_wide if kk == ks else idx_wide[:, :kk].contiguous()
+            # relative coordinates of the neighbours (:109,:111) are the same for every block of the sequence
+            pos = pointops.group_xyz(idx, coord)
+            if training:
+                # transposed neighbour graph of the atomic-free backward passes: built now, on a side stream,
+                # under the forward kernels instead of at the head of the backward pass
+                pointops.prefetch_csr(idx, coord.shape[0], 0)
+            # Σp, Σppᵀ of pos: the closed-form BatchNorm statistics of every block's fused positional MLP
+            mom = pointops.pos_moments(pos) if (fused_pe_enabled() and self.training) else None
+            entry = (coord, offset, idx, pos, mom)
+            if cache is not None:
+                cache[(coord.data_ptr(), coord.shape[0], offset.data_ptr(), kk)] = entry
+            if kk == k:
+                out = entry[2:]
+        return out
 
     def forward(self, points):
         coord, feat, offset = points
-        key = (coord.data_ptr(), coord.shape[0], offset.data_ptr(), self.neighbours)
-        hit = None if self.knn_cache is None else self.knn_cache.get(key)
-        if hit is None:
-            reference_index, _ = pointops.knn_query(self.neighbours, coord, offset)     # :223
-            # relative coordinates of the neighbours (:109,:111) are the same for every block of the sequence
-            pos = pointops.group_xyz(reference_index, coord)
-            if torch.is_grad_enabled() and feat.requires_grad:
-                # transposed neighbour graph of the atomic-free backward passes: built now, on a side stream,
-                # under the forward kernels instead of at the head of the backward pass
-                pointops.prefetch_csr(reference_index, coord.shape[0], 0)
-            # Σp, Σppᵀ of pos: the closed-form BatchNorm statistics of every block's fused positional MLP
-            mom = pointops.pos_moments(pos) if (fused_pe_enabled() and self.training) else None
-            hit = (reference_index, pos, mom)
-            if self.knn_cache is not None:
-                self.knn_cache[key] = hit
-        reference_index, pos, mom = hit
+        reference_index, pos, mom = self._neighbour_list(coord, offset, feat)
         for block in self.blocks:
             points = block(points, reference_index, pos, mom)
         return points
@@ -392,6 +421,14 @@ class PointTransformerV2(nn.Module):
         for m in self.modules():
             if isinstance(m, BlockSequence):
                 m.knn_cache = self._knn_cache
+        # largest k per level: level 0 = patch embed + last decoder, level i+1 = encoder i + decoder i+1
+        seqs = [[self.patch_embed.blocks, self.dec_stages[0].blocks]]
+        for i in range(self.num_stages):
+            seqs.append([self.enc_stages[i].blocks] + ([self.dec_stages[i + 1].blocks] if i + 1 < self.num_stages else []))
+        for level in seqs:
+            kmax = max(q.neighbours for q in level)
+            for q in level:
+                q.search_neighbours = kmax
 
     def forward(self, data_dict):
         coord = data_dict["coord"]
@@ -436,3 +473,6 @@ SCANNET_CFG = dict(  # configs/scannet/semseg-pt-v2m2-0-base.py
     dec_channels=(48, 96, 192, 384), dec_groups=(6, 12, 24, 48), dec_neighbours=(16, 16, 16, 16),
     grid_sizes=(0.06, 0.15, 0.375, 0.9375), attn_qkv_bias=True, pe_multiplier=False, pe_bias=True,
     attn_drop_rate=0.0, drop_path_rate=0.3, enable_checkpoint=False, unpool_backend="map")
+
+KITTI_CFG = dict(SCANNET_CFG, in_channels=4, num_classes=19,   # configs/semantic_kitti/semseg-pt-v2m2-0-base.py
+                 grid_sizes=(0.15, 0.375, 0.9375, 2.34375))

@@ -36,15 +36,25 @@ def shard_batch(coord: torch.Tensor, feat: torch.Tensor, offset: torch.Tensor, r
     return coord[p0:p1].contiguous(), feat[p0:p1].contiguous(), offset_r, p0
 
 
-def ddp_wrap(model: torch.nn.Module, device_index: int):
-    """DistributedDataParallel as the reference builds it (engines/defaults.py:38: broadcast_buffers
-    off, no unused parameters), with ONE flat bucket: the S3DIS-cfg gradients are 14.9 MB, so the
-    all-reduce is latency-bound over NVLink and a single launch after backward is cheapest."""
+def ddp_wrap(model: torch.nn.Module, device_index=None, bucket_cap_mb: float = 4.0):
+    """DistributedDataParallel as the reference builds it (create_ddp_model, engines/defaults.py:30-43, called with
+    broadcast_buffers=False, find_unused_parameters=False at engines/train.py:209-213).
+
+    The S3DIS-cfg gradients are 14.9 MB (ScanNet cfg 43.2 MB): over NVLink 5 the all-reduce is latency-bound, so what
+    matters is WHEN it is issued.  One flat bucket would fire only after the last gradient (the patch-embed weights,
+    at the very end of the backward pass) and serialise behind it; small buckets (default 4 MB) let the decoder /
+    deep-encoder gradients — ready while the expensive level-0 backward kernels are still ahead — go out under the
+    backward pass, leaving one small tail bucket.  gradient_as_bucket_view avoids the grad -> bucket copies.
+
+    device_index None: CPU model (gloo) — the host-side plumbing test."""
     from torch.nn.parallel import DistributedDataParallel
 
+    if device_index is None:
+        return DistributedDataParallel(model, broadcast_buffers=False, find_unused_parameters=False,
+                                       bucket_cap_mb=bucket_cap_mb, gradient_as_bucket_view=True)
     return DistributedDataParallel(model, device_ids=[device_index], output_device=device_index,
                                    broadcast_buffers=False, find_unused_parameters=False,
-                                   bucket_cap_mb=64, gradient_as_bucket_view=True)
+                                   bucket_cap_mb=bucket_cap_mb, gradient_as_bucket_view=True)
 
 
 def max_over_ranks(value: float, device) -> float:

@@ -29,9 +29,29 @@ if ROOT not in sys.path:
 
 METRIC = "ptv2_pointops_fwd_bwd_throughput"
 UNIT = "Mpoints/s"
-ROOMS_PER_GPU = 4
-POINTS_PER_ROOM = 80000
-DDP_GRAD_BYTES = 3908641 * 4   # S3DIS-cfg PTv2m2 parameters, fp32
+# BASELINE.json configs[1..4].  rooms = scenes per GPU; params = fp32 parameters of the config's PTv2m2 (SURVEY.md §2.3:
+# the DDP gradient all-reduce payload); variants = extra schedules timed after the headline one (fewer steps).
+CONFIGS = {
+    "s3dis4": dict(baseline=1, sched="s3dis", scenes="s3dis", rooms=4, points=80000, params=3908641, model="S3DIS_CFG",
+                   what="S3DIS-shaped batch of {r} rooms x {p} pts per GPU (BASELINE.json configs[1])",
+                   variants=[("fused", dict(variant="fused"))]),
+    "s3dis8": dict(baseline=2, sched="s3dis", scenes="s3dis", rooms=8, points=80000, params=3908641, model="S3DIS_CFG",
+                   what="S3DIS-shaped batch of {r} rooms x {p} pts per GPU, DDP training-step shape (BASELINE.json configs[2])",
+                   variants=[("fused", dict(variant="fused"))]),
+    "scannet150k": dict(baseline=3, sched="scannet", scenes="scannet", rooms=3, points=150000, params=11323948,
+                        model="SCANNET_CFG",
+                        what="ScanNet-shaped batch of {r} rooms x {p} pts per GPU (12 rooms / 4 GPUs in the reference "
+                             "config), ScanNet cfg: patch k=8, 4 GridPool stages, k=16, `map` unpooling "
+                             "(BASELINE.json configs[3])",
+                        variants=[("interp_up", dict(unpool="interp")), ("k32", dict(k=32)), ("fused", dict(variant="fused"))]),
+    "kitti120k": dict(baseline=4, sched="kitti", scenes="kitti", rooms=2, points=120000, params=11323659, model="KITTI_CFG",
+                      what="SemanticKITTI-shaped batch of {r} scans x {p} pts per GPU (8 scans / 4 GPUs in the reference "
+                           "config), KITTI cfg: patch k=8, 4 GridPool stages, k=16, `map` unpooling (BASELINE.json configs[4])",
+                      variants=[("fused", dict(variant="fused"))]),
+}
+DEFAULT_STEPS = 250    # 250 x ~8 ms: a timed region of >= 2 s (>= 20 clock samples at 100 ms)
+DEFAULT_STEPS_REFERENCE = 10
+VARIANT_STEPS = 30
 TRACE_STEPS = int(os.environ.get("AOPT_BENCH_TRACE_STEPS", "1"))   # timed steps that also carry per-call CUDA events (roofline table)
 
 
@@ -96,7 +116,7 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------
 # algorithmic bytes per C-ABI call (SURVEY.md §8d formulas; DESIGN.md §4 lists them per kernel)
 # ---------------------------------------------------------------------------------------------------
-def call_bytes(name, a, sizes, k):
+def call_bytes(name, a, sizes):
     """a = the ctypes argument tuple of the call; sizes = level point counts of this step."""
     def finer(n_coarse):      # level size one above a coarse size
         for i in range(1, len(sizes)):
@@ -118,9 +138,10 @@ def call_bytes(name, a, sizes, k):
     if name == "aopt_grouping_forward":
         m, ns, c = a[0], a[1], a[2]
         return 4.0 * m * ns + 4.0 * m * c + 4.0 * m * ns * c
-    if name == "aopt_grouping_backward":          # relation backward: E = n*k entries
+    if name == "aopt_grouping_backward":          # in the schedule: `map` unpool backward, E = points of the finer level
         n, c = a[0], a[1]
-        return 4.0 * n * k * c + 4.0 * n * k + 4.0 * (n + 1) + 4.0 * n * c
+        e = finer(n)
+        return 4.0 * e * c + 4.0 * e + 4.0 * (n + 1) + 4.0 * n * c
     if name == "aopt_relation_backward":          # one read of the (n,k,c) gradient, two (n,c) outputs
         n, ns, c = a[0], a[1], a[2]
         return 4.0 * n * ns * c + 4.0 * n * ns + 4.0 * (n + 1) + 8.0 * n * c
@@ -136,6 +157,10 @@ def call_bytes(name, a, sizes, k):
     if name == "aopt_gva_backward_value":
         n, ns, c, g = a[0], a[1], a[2], a[3]
         return 4.0 * n * ns * g + 4.0 * n * c + 4.0 * (n + 1) + 4.0 * n * ns + 4.0 * n * c
+    if name == "aopt_gva_backward":               # fused pair: SURVEY §8d "Fused GVA bwd"
+        n, ns, c, g = a[0], a[1], a[2], a[3]
+        return (8.0 * n * c + 4.0 * n * ns * c + 4.0 * n * ns * g + 8.0 * n * ns + 4.0 * (n + 1)
+                + 4.0 * n * ns * c + 4.0 * n * ns * g + 4.0 * n * c)
     if name == "aopt_pool_forward":
         nv, c = a[0], a[1]
         n = finer(nv)
@@ -157,23 +182,33 @@ def call_bytes(name, a, sizes, k):
     if name in ("aopt_segment_min3", "aopt_voxel_keys"):
         n = a[0]
         return 12.0 * n + (8.0 * n if name == "aopt_voxel_keys" else 0.0)
+    if name == "aopt_pe_mlp_forward":             # rows x (12 B of pos in, 4C out, 4*ga aux out)
+        rows, c, ga = a[0], a[1], a[16]
+        return rows * (12.0 + 4.0 * c + 4.0 * ga)
+    if name == "aopt_pe_mlp_backward":            # rows x (12 B of pos, 4C of grad_out, 4*ga of grad_aux) in
+        rows, c, ga = a[0], a[1], a[15]
+        return rows * (12.0 + 4.0 * c + 4.0 * ga)
+    if name == "aopt_pos_moments":
+        return 12.0 * a[0]
     return 0.0
 
 
 HBM_KERNELS = {"aopt_group_xyz", "aopt_gather_sub_forward", "aopt_grouping_forward", "aopt_grouping_backward",
                "aopt_relation_backward",
                "aopt_sum_over_k", "aopt_gva_forward", "aopt_gva_backward_query", "aopt_gva_backward_value",
+               "aopt_gva_backward",
                "aopt_pool_forward", "aopt_pool_backward", "aopt_interpolation_forward",
                "aopt_interpolation_backward"}
+TENSOR_KERNELS = {"aopt_pe_mlp_forward", "aopt_pe_mlp_backward"}    # contraction kernels: HBM-bound too (2C flop / output byte)
 
 
-def summarise_trace(trace, sizes, k, step_ms_total, peak):
+def summarise_trace(trace, sizes, step_ms_total, peak):
     """Per entry point: all launches of the traced steps, and separately its LARGEST launch shape (the
     level-0 launches) — small levels are launch-latency bound and say little about the kernel."""
     per = {}
     for name, args, s, e in trace:
         ms = s.elapsed_time(e)
-        nb = call_bytes(name, args, sizes, k)
+        nb = call_bytes(name, args, sizes)
         d = per.setdefault(name, dict(ms=0.0, calls=0, bytes=0.0, shapes={}))
         d["ms"] += ms
         d["calls"] += 1
@@ -187,7 +222,7 @@ def summarise_trace(trace, sizes, k, step_ms_total, peak):
         big = max(d["shapes"])
         big_ms, big_calls = d["shapes"][big]
         big_gbs = big * big_calls / (big_ms * 1e-3) / 1e9 if big_ms > 0 else 0.0
-        hbm = name in HBM_KERNELS
+        hbm = name in HBM_KERNELS or name in TENSOR_KERNELS
         out.append(dict(kernel=name, calls=d["calls"], ms=round(d["ms"], 4), share=round(d["ms"] / step_ms_total, 4),
                         alg_gb=round(d["bytes"] / 1e9, 4), gbs=round(gbs, 1), frac=round(gbs / peak, 4) if hbm else None,
                         largest=dict(alg_bytes=big, launches=big_calls, us_per_launch=round(big_ms / big_calls * 1e3, 2),
@@ -195,21 +230,77 @@ def summarise_trace(trace, sizes, k, step_ms_total, peak):
     return out
 
 
+def per_step(kernels, trace_steps):
+    for kr in kernels:
+        kr["ms_per_step"] = round(kr.pop("ms") / trace_steps, 4)
+        kr["calls_per_step"] = kr.pop("calls") // trace_steps
+        kr["alg_gb_per_step"] = round(kr.pop("alg_gb") / trace_steps, 4)
+        kr["largest"]["launches_per_step"] = kr["largest"].pop("launches") // trace_steps
+    return kernels
+
+
+# ---------------------------------------------------------------------------------------------------
+# workloads
+# ---------------------------------------------------------------------------------------------------
+def make_schedule_config(name, **over):
+    from ao_b200.schedule import ScheduleConfig
+
+    return getattr(ScheduleConfig, CONFIGS[name]["sched"])(**over)
+
+
+def make_batch(name, rooms, rank):
+    """Scenes [rank*rooms, rank*rooms+rooms) of the config's synthetic generator (numpy, host)."""
+    from ao_b200 import scenes
+
+    c = CONFIGS[name]
+    if c["scenes"] == "s3dis":
+        return scenes.s3dis_batch(rooms, c["points"], first_room=rank * rooms)
+    if c["scenes"] == "scannet":
+        return scenes.scannet_batch(rooms, c["points"], first_room=100 + rank * rooms)
+    return scenes.kitti_batch(rooms, c["points"], first_scan=rank * rooms)
+
+
+def workload_config(name, rooms, n_gpus, cfg=None):
+    c = CONFIGS[name]
+    if cfg is None:
+        cfg = make_schedule_config(name)
+    per = [cfg.patch_depth] + list(cfg.enc_depths)
+    for i, d in enumerate(cfg.dec_depths):
+        per[i] += d
+    mb = c["params"] * 4 / 1e6
+    return {
+        "workload": "PTv2m2 point-operator schedule fwd+bwd (every kNN / gather / GVA aggregate / GridPool / unpool call of "
+                    "one forward of the config's backbone and their backward passes), " + c["what"].format(r=rooms, p=c["points"])
+                    + "; `value` = the materialised-relation variant (gva_relation at width C, what the model runs in "
+                    "fp32); `variants.fused` = the schedule ptv2 runs under bf16 autocast at C in {48, 96}",
+        "name": name, "rooms_per_gpu": rooms, "points_per_room": c["points"],
+        "k": {"patch": cfg.k_patch(), "enc": [cfg.k_enc(i) for i in range(len(cfg.grid_sizes))],
+              "dec": [cfg.k_dec(i) for i in range(len(cfg.grid_sizes))]},
+        "channels": list(cfg.channels), "groups": list(cfg.groups), "blocks_per_level": per, "grid_sizes": list(cfg.grid_sizes),
+        "unpool": cfg.unpool,
+        "parallelism": f"scene-sharded x{n_gpus}" + (
+            f", fp32 gradient all-reduce {mb:.1f} MB/step (NCCL) issued on its own stream under the backward pass "
+            "(stand-in buffer of the model's gradient size; DDP's own bucketed all-reduce is what `model_step` runs)"
+            if n_gpus > 1 else ""),
+        "l2": "per-step working set (>20 GB) exceeds the 126 MB L2; no explicit flush",
+        "streams": "single compute stream (side-stream overlap of kNN / CSR walk / CSR build measured: no gain, left off)",
+    }
+
+
 # ---------------------------------------------------------------------------------------------------
 # CPU reference path (oracle/cpu_path.py) — cpu_baseline leg and the --impl reference arm
 # ---------------------------------------------------------------------------------------------------
-def cpu_reference(steps, warmup, budget_s, room_id=0):
+def cpu_reference(name, steps, warmup, fraction=None, room_id=0):
     import torch
 
-    from ao_b200 import scenes          # numpy scene generator only (no kernels)
     from oracle import cpu_path
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    coord, _ = scenes.indoor_room(room_id, POINTS_PER_ROOM)
-    room = cpu_path.CpuRoom(coord)
-    per_step = max(1.0, budget_s / max(1, steps + warmup + 1))
-    f = max(0.02, cpu_path.calibrate_fraction(room, per_step, f0=0.02))
+    cfg = make_schedule_config(name)
+    coord, _, _ = make_batch(name, 1, room_id)
+    room = cpu_path.CpuRoom(coord, cfg)
+    f = cpu_path.FIXED_FRACTION if fraction is None else fraction
     for _ in range(warmup):
         room.step(f)
     tot_s, tot_pts, fam = 0.0, 0.0, {}
@@ -220,9 +311,9 @@ def cpu_reference(steps, warmup, budget_s, room_id=0):
         for key in ("knn", "block", "pool", "interp"):
             fam[key] = fam.get(key, 0.0) + r[key]
     value = tot_pts / tot_s / 1e6
-    sample = (f"one synthetic S3DIS room (80000 pts, k=16), reference op schedule fwd+bwd on the first "
-              f"{f:.4f} of every level's query rows against the full level ({int(tot_pts / max(steps, 1))} "
-              f"level-0 points per step); cdist+topk kNN, torch gather/index_put scatter")
+    sample = (f"one synthetic {CONFIGS[name]['scenes']} scene ({coord.shape[0]} pts), reference op schedule fwd+bwd on the "
+              f"first {f:.4f} (fixed) of every level's query rows against the full level "
+              f"({int(tot_pts / max(steps, 1))} level-0 points per step); cdist+topk kNN, torch gather/index_put scatter")
     return dict(value=value, ms_per_step=tot_s / max(steps, 1) * 1e3, cores=cores, sample=sample,
                 fraction=f, family_seconds={k2: round(v, 3) for k2, v in fam.items()})
 
@@ -231,12 +322,17 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    r = cpu_reference(args.steps, args.warmup, budget_s=float(os.environ.get("AOPT_BENCH_CPU_BUDGET", "150")))
+    steps = DEFAULT_STEPS_REFERENCE if args.steps is None else args.steps
+    warmup = 1 if args.warmup is None else args.warmup
+    # a step is a fixed 4 % row sample of one scene (~5 s on 16 cores); long runs shrink the sample, not the contract
+    frac = None if steps + warmup <= 40 else 0.04 * 40.0 / (steps + warmup)
+    r = cpu_reference(args.config, steps, warmup, fraction=frac)
+    rooms = args.rooms_per_gpu or CONFIGS[args.config]["rooms"]
     line = {
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+        "steps": steps, "warmup": warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.gpus),
+        "config": workload_config(args.config, rooms, args.gpus),
         "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
                          "sample": r["sample"], "family_seconds": r["family_seconds"]},
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -245,45 +341,160 @@ def run_reference_arm(args):
     emit(line)
 
 
-def workload_config(n_gpus):
-    return {
-        "workload": "PTv2m2 semseg-pt-v2m2-0-base point-operator schedule fwd+bwd, S3DIS-shaped batch of "
-                    f"{ROOMS_PER_GPU} rooms x {POINTS_PER_ROOM} pts per GPU (BASELINE.json configs[1])",
-        "rooms_per_gpu": ROOMS_PER_GPU, "points_per_room": POINTS_PER_ROOM, "k": 16,
-        "channels": [48, 96, 192, 384], "groups": [6, 12, 24, 48], "blocks_per_level": [3, 3, 7, 2],
-        "parallelism": f"scene-sharded x{n_gpus}" + (", fp32 grad all-reduce 14.9 MB/step (NCCL)" if n_gpus > 1 else ""),
-        "l2": "per-step working set (>20 GB) exceeds the 126 MB L2; no explicit flush",
-        "streams": "single stream (side-stream overlap of kNN / CSR walk / CSR build measured: no gain, left off)",
-    }
-
-
 # ---------------------------------------------------------------------------------------------------
 # B200 arm
 # ---------------------------------------------------------------------------------------------------
+class Ctx:
+    """Process-wide state of one bench run (rank, device, collective helpers)."""
+
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+
+        self.torch, self.dist = torch, dist
+        # torchrun exports RANK / LOCAL_RANK / WORLD_SIZE; a plain `python bench.py` is a single process
+        under_torchrun = all(k in os.environ for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"))
+        self.world = int(os.environ["WORLD_SIZE"]) if under_torchrun else 1
+        self.rank = int(os.environ["RANK"]) if under_torchrun else 0
+        self.local = int(os.environ["LOCAL_RANK"]) if under_torchrun else 0
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback "
+                             "(use --impl reference for the CPU baseline)")
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x: float) -> float:
+        t = self.torch.tensor([x], device=self.dev, dtype=self.torch.float64)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def finish(self):
+        if self.world > 1:
+            self.dist.barrier()
+            self.dist.destroy_process_group()
+
+
+class GradAllReduce:
+    """The DDP gradient all-reduce of the op-schedule step at N > 1 (the only collective).  The schedule
+    has no parameters, so the payload is a resident fp32 buffer of the model's gradient size.  It is issued between
+    the forward and the backward pass on its own stream — DDP overlaps its buckets with the backward pass the same
+    way (engines/defaults.py:38) — and joined at the end of the step."""
+
+    def __init__(self, ctx, n_params):
+        self.ctx = ctx
+        self.buf = ctx.torch.zeros(n_params, device=ctx.dev)
+        self.stream = ctx.torch.cuda.Stream(device=ctx.dev)
+        self.pending = False
+
+    def launch(self):
+        torch = self.ctx.torch
+        self.stream.wait_stream(torch.cuda.current_stream(self.ctx.dev))
+        with torch.cuda.stream(self.stream):
+            self.ctx.dist.all_reduce(self.buf)
+        self.pending = True
+
+    def join(self):
+        if self.pending:
+            self.ctx.torch.cuda.current_stream(self.ctx.dev).wait_stream(self.stream)
+            self.pending = False
+
+
+def time_schedule(ctx, sched, coord, offset, steps, warmup, trace_steps, allreduce=None, sampler=None):
+    """W warm-up steps, then EXACTLY `steps` timed steps between barrier + synchronize, CUDA events on the launching
+    stream, max over ranks.  The last `trace_steps` timed steps carry per-call CUDA events (roofline table)."""
+    import gc
+
+    torch = ctx.torch
+    from ao_b200 import _lib
+
+    def one_step(c, o):
+        acc = sched.step(c, o)
+        if allreduce is not None:
+            allreduce.join()
+        return acc
+
+    sched.between = allreduce.launch if allreduce is not None else None
+    for _ in range(warmup):
+        one_step(coord, offset)
+    ctx.barrier()
+    if sampler is not None:
+        sampler.start()
+        time.sleep(0.3)
+        ctx.barrier()
+        # the GPU idled while the clock sampler started: more untimed steps bring clocks / power state back up
+        # (without them the first two or three timed steps run 5-20 % slow)
+        for _ in range(2):
+            one_step(coord, offset)
+        ctx.barrier()
+    gc.collect()
+    gc.disable()      # the Python GC stays off while timing
+    trace_steps = min(trace_steps, steps)
+    _lib.trace_prepare(1024 * max(1, trace_steps))
+    launches0 = _lib.kernel_launches()
+    trace = []
+    overlap_was = _lib.overlap_mode()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]   # end of every step (diagnostics)
+    wall0 = time.perf_counter()
+    e0.record()
+    for i in range(steps):
+        if i > 0:
+            marks[i - 1].record()
+        if trace_steps and i == steps - trace_steps:
+            # per-call CUDA events are recorded on the LAST trace_steps timed steps only (an event pair per call on
+            # all ~250 calls of a step costs ~1 ms of host time).  Per-kernel roofline = the kernel running ALONE:
+            # these steps issue everything on one stream; they are part of the timed region.
+            trace = _lib.trace_start()
+            _lib.overlap(False)
+        one_step(coord, offset)
+    e1.record()
+    ctx.barrier()
+    wall = time.perf_counter() - wall0
+    _lib.trace_stop()
+    _lib.overlap_mode(overlap_was)
+    gc.enable()
+    launches = _lib.kernel_launches() - launches0
+    clocks = sampler.stop() if sampler is not None else None
+    ms_total = e0.elapsed_time(e1)
+    bounds = [e0] + marks[: steps - 1] + [e1]
+    step_ms = [round(bounds[i].elapsed_time(bounds[i + 1]), 3) for i in range(steps)]
+    ms_step = ctx.max_over_ranks(ms_total) / steps
+    return dict(ms_step=ms_step, step_ms=step_ms, trace=trace, trace_steps=trace_steps, launches=int(launches),
+                clocks=clocks, wall_ms_per_step=wall / steps * 1e3, sizes=list(sched.last_sizes), one_step=one_step)
+
+
+def brief(values):
+    """min / median / max of a list of per-step times."""
+    v = sorted(values)
+    return {"min": v[0], "median": v[len(v) // 2], "max": v[-1]} if v else None
+
+
 def run_b200_arm(args):
-    import torch
-    import torch.distributed as dist
+    ctx = Ctx()
+    torch, dist = ctx.torch, ctx.dist
+    dev, world, rank = ctx.dev, ctx.world, ctx.rank
 
-    from ao_b200 import _lib, scenes
-    from ao_b200.schedule import PointOpsSchedule, ScheduleConfig
+    from ao_b200 import _lib
+    from ao_b200.schedule import PointOpsSchedule
 
-    # torchrun exports RANK / LOCAL_RANK / WORLD_SIZE; a plain `python bench.py` is a single process
-    under_torchrun = all(k in os.environ for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"))
-    world = int(os.environ["WORLD_SIZE"]) if under_torchrun else 1
-    rank = int(os.environ["RANK"]) if under_torchrun else 0
-    local = int(os.environ["LOCAL_RANK"]) if under_torchrun else 0
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback "
-                         "(use --impl reference for the CPU baseline)")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
     _lib.load()
+    name = args.config
+    conf = CONFIGS[name]
+    rooms = args.rooms_per_gpu or conf["rooms"]
+    steps = DEFAULT_STEPS if args.steps is None else args.steps
+    warmup = max(5 if args.warmup is None else args.warmup, args.min_warmup)
 
-    # ---- synthetic batch: rooms [rank*R, rank*R+R) --------------------------------------------------
-    coord_np, feat_np, off_np = scenes.s3dis_batch(ROOMS_PER_GPU, POINTS_PER_ROOM, first_room=rank * ROOMS_PER_GPU)
+    # ---- synthetic batch: scenes [rank*R, rank*R+R) -------------------------------------------------
+    coord_np, feat_np, off_np = make_batch(name, rooms, rank)
     if args.presort:   # experiment: spatially coherent point order inside every room (Morton order of 0.1 m cells)
         import numpy as np
         order, s0 = [], 0
@@ -303,81 +514,22 @@ def run_b200_arm(args):
     off_h = torch.from_numpy(off_np).pin_memory()
     coord, feat, offset = coord_h.to(dev), feat_h.to(dev), off_h.to(dev)
     n0 = coord.shape[0]
-    cfg = ScheduleConfig.s3dis()
+    cfg = make_schedule_config(name)
     sched = PointOpsSchedule(cfg, device=dev, seed=rank)
-    grads = torch.zeros(DDP_GRAD_BYTES // 4, device=dev) if world > 1 else None
-
-    def one_step(c, o):
-        acc = sched.step(c, o)
-        if grads is not None:
-            dist.all_reduce(grads)          # the DDP gradient all-reduce: the only collective
-        return acc
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(max(args.warmup, args.min_warmup)):
-        one_step(coord, offset)
-    barrier()
+    allreduce = GradAllReduce(ctx, conf["params"]) if world > 1 else None
 
     # ---- timed region: resident inputs, CUDA events on the launching stream ----------------------------
-    sampler = ClockSampler(local) if rank == 0 else None
-    if sampler:
-        sampler.start()
-        time.sleep(0.3)
-    barrier()
-    # the GPU idled while the clock sampler started: one more untimed step brings clocks / power state back up
-    # (without it the first two or three timed steps run 5-20 % slow), and the Python GC stays off while timing
-    one_step(coord, offset)
-    barrier()
-    import gc
-    gc.collect()
-    gc.disable()
-    _lib.trace_prepare(1024 * max(1, min(TRACE_STEPS, args.steps)))
-    launches0 = _lib.kernel_launches()
-    # per-call CUDA events are recorded on TRACE_STEPS of the timed steps (an event pair per call on all
-    # ~200 calls of every step costs ~1 ms/step of host time, which would distort the step time)
-    trace_steps = min(TRACE_STEPS, args.steps)
-    trace = []
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]   # end of every step (diagnostics)
-    wall0 = time.perf_counter()
-    e0.record()
-    for i in range(args.steps):
-        if i > 0:
-            marks[i - 1].record()
-        if i == args.steps - trace_steps:
-            trace = _lib.trace_start()
-            # per-kernel roofline = the kernel running ALONE: the traced steps issue everything on one stream
-            # (they are still part of the timed region, so `value` is a slight under-estimate)
-            overlap_was = _lib.overlap_mode()
-            _lib.overlap(False)
-        one_step(coord, offset)
-    e1.record()
-    barrier()
-    wall = time.perf_counter() - wall0
-    _lib.trace_stop()
-    if trace_steps:
-        _lib.overlap_mode(overlap_was)
-    launches = _lib.kernel_launches() - launches0
-    clocks = sampler.stop() if sampler else None
-    ms_total = e0.elapsed_time(e1)
-    bounds = [e0] + marks[: args.steps - 1] + [e1]
-    step_ms = [round(bounds[i].elapsed_time(bounds[i + 1]), 3) for i in range(args.steps)]
-    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
-    ms_step = ms_total / args.steps
+    sampler = ClockSampler(ctx.local) if rank == 0 else None
+    r = time_schedule(ctx, sched, coord, offset, steps, warmup, TRACE_STEPS, allreduce, sampler)
+    ms_step, sizes, trace, trace_steps, one_step = r["ms_step"], r["sizes"], r["trace"], r["trace_steps"], r["one_step"]
     value = world * n0 / (ms_step * 1e-3) / 1e6
-    sizes = list(sched.last_sizes)
 
     # ---- e2e: host buffers → H2D → schedule → D2H of the result scalar, wall clock ---------------------
     # Every step copies its own inputs from pinned host memory and reads the result scalar back (a sync per
     # step, like a training loop that logs its loss).  As a data loader with pin_memory / non_blocking would, the
     # copy of step i+1 is issued on a copy stream while step i computes; all copies lie inside the timed region.
+    import gc
+
     copy_stream = torch.cuda.Stream(device=dev)
 
     def stage():
@@ -391,17 +543,17 @@ def run_b200_arm(args):
 
     e2e_step_ms = []
 
-    def e2e_loop(steps):
+    def e2e_loop(n_steps):
         last = 0.0
         nxt = stage()
-        for i in range(steps):
+        for i in range(n_steps):
             t_step = time.perf_counter()
             c, f, o, ev = nxt
             cur = torch.cuda.current_stream(dev)
             cur.wait_event(ev)
             for t_ in (c, f, o):
                 t_.record_stream(cur)        # allocated on the copy stream, consumed on the compute stream
-            if i + 1 < steps:
+            if i + 1 < n_steps:
                 nxt = stage()
             acc = one_step(c, o)
             del f
@@ -409,141 +561,277 @@ def run_b200_arm(args):
             e2e_step_ms.append(round((time.perf_counter() - t_step) * 1e3, 3))
         return last
 
-    e2e_steps = 0 if args.skip_e2e else args.steps
+    e2e_steps = 0 if args.skip_e2e else steps
+    e2e_value = None
     if e2e_steps:
         # warm-up of this leg too: its copy-stream buffers are new allocations (the first two steps of a cold loop
         # took 37 and 16 ms in cudaMalloc, against 8.4 ms once the double buffers exist)
-        e2e_loop(max(3, args.warmup))
-    barrier()
-    del e2e_step_ms[:]
-    w0 = time.perf_counter()
-    e2e_loop(e2e_steps)
-    barrier()
-    e2e_s = max(time.perf_counter() - w0, 1e-9)
-    t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_s = float(t.item())
-    gc.enable()
-    e2e_value = world * n0 * e2e_steps / e2e_s / 1e6
+        e2e_loop(max(3, min(warmup, 5)))
+        ctx.barrier()
+        del e2e_step_ms[:]
+        gc.collect()
+        gc.disable()
+        w0 = time.perf_counter()
+        e2e_loop(e2e_steps)
+        ctx.barrier()
+        e2e_s = ctx.max_over_ranks(max(time.perf_counter() - w0, 1e-9))
+        gc.enable()
+        e2e_value = world * n0 * e2e_steps / e2e_s / 1e6
     h2d = coord_h.numel() * 4 + feat_h.numel() * 4 + off_h.numel() * 4
-
-    if rank != 0:
-        if world > 1:
-            dist.barrier()
-            dist.destroy_process_group()
-        return
 
     # ---- roofline of the dominant HBM-bound kernel, measured live over the timed region ---------------
     peak, peak_src = hbm_peak()
-    kernels = summarise_trace(trace, sizes, cfg.k, ms_step * trace_steps, peak)
-    for kr in kernels:
-        kr["ms_per_step"] = round(kr.pop("ms") / trace_steps, 4)
-        kr["calls_per_step"] = kr.pop("calls") // trace_steps
-        kr["alg_gb_per_step"] = round(kr.pop("alg_gb") / trace_steps, 4)
-        kr["largest"]["launches_per_step"] = kr["largest"].pop("launches") // trace_steps
-    hbm_rows = [kr for kr in kernels if kr["kernel"] in HBM_KERNELS]
-    dom = hbm_rows[0] if hbm_rows else None
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "traffic.json")
-    if dom and os.path.exists(tp):
-        try:
-            traffic = json.load(open(tp)).get(dom["kernel"])
-        except Exception:
-            traffic = None
-    roofline = None
-    if dom:
-        # the dominant HBM-bound kernel at its level-0 launch shape: algorithmic bytes of one launch / its
-        # CUDA-event duration averaged over the traced launches; `traffic` = dram read+write bytes of the
-        # same launch shape from the committed ncu --set full capture (profiles/traffic.json)
-        big = dom["largest"]
-        info = traffic if isinstance(traffic, dict) else {}
-        roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": big["gbs"], "peak": peak, "unit": "GB/s",
-                    "frac": big["frac"], "traffic": info.get("dram_bytes_per_launch"),
-                    "traffic_source": info.get("source"), "peak_source": peak_src,
-                    "alg_bytes_per_launch": big["alg_bytes"], "us_per_launch": big["us_per_launch"],
-                    "launches_per_step": big["launches_per_step"], "launch_shape": "level 0: N=%d, k=%d, C=%d, G=%d" % (
-                        sizes[0], cfg.k, cfg.channels[0], cfg.groups[0]),
-                    "share_of_step_all_launches": dom["share"], "frac_all_launches": dom["frac"]}
-    hbm_ms = sum(kr["ms_per_step"] for kr in hbm_rows)
-    hbm_gb = sum(kr["alg_gb_per_step"] for kr in hbm_rows)
-    knn_row = next((kr for kr in kernels if kr["kernel"] == "aopt_knn_query"), None)
-    # brute-force-equivalent pair count of the searches (scenes of a level are near-equal in size)
-    pairs = sum(float(a[0]) * float(a[2]) / max(a[3], 1) for nm, a, _, _ in trace if nm == "aopt_knn_query") / trace_steps
-
-    line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, args.min_warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(world),
-        "level_sizes": sizes,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+    line = None
+    if rank == 0:
+        kernels = per_step(summarise_trace(trace, sizes, ms_step * max(trace_steps, 1), peak), max(trace_steps, 1))
+        hbm_rows = [kr for kr in kernels if kr["kernel"] in HBM_KERNELS]
+        dom = hbm_rows[0] if hbm_rows else None
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if dom and os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get(dom["kernel"])
+            except Exception:
+                traffic = None
+        roofline = None
+        if dom:
+            # the dominant HBM-bound kernel at its level-0 launch shape: algorithmic bytes of one launch / its
+            # CUDA-event duration averaged over the traced launches; `traffic` = dram read+write bytes of the
+            # same launch shape from the committed ncu --set full capture (profiles/traffic.json: s3dis4 shapes)
+            big = dom["largest"]
+            info = traffic if isinstance(traffic, dict) and name == "s3dis4" else {}
+            roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": big["gbs"], "peak": peak, "unit": "GB/s",
+                        "frac": big["frac"], "traffic": info.get("dram_bytes_per_launch"),
+                        "traffic_source": info.get("source"), "peak_source": peak_src,
+                        "alg_bytes_per_launch": big["alg_bytes"], "us_per_launch": big["us_per_launch"],
+                        "launches_per_step": big["launches_per_step"],
+                        "launch_shape": "level 0: N=%d, C=%d, G=%d, k per config.k" % (sizes[0], cfg.channels[0], cfg.groups[0]),
+                        "share_of_step_all_launches": dom["share"], "frac_all_launches": dom["frac"]}
+        hbm_ms = sum(kr["ms_per_step"] for kr in hbm_rows)
+        hbm_gb = sum(kr["alg_gb_per_step"] for kr in hbm_rows)
+        knn_row = next((kr for kr in kernels if kr["kernel"] == "aopt_knn_query"), None)
+        # brute-force-equivalent pair count of the searches (scenes of a level are near-equal in size)
+        pairs = sum(float(a[0]) * float(a[2]) / max(a[3], 1) for nm, a, _, _ in trace if nm == "aopt_knn_query") / max(trace_steps, 1)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps,
+            "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(name, rooms, world, cfg),
+            "level_sizes": sizes,
+            "e2e": None if e2e_value is None else {
+                "value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "timing": "wall clock incl. python launch overhead; H2D of step i+1 overlaps step i on a copy stream"},
-        "gpu_launches": int(launches),
-        "clocks": clocks,
-        "roofline": roofline,
-        "hbm_kernels_total": {"ms_per_step": round(hbm_ms, 4), "alg_gb_per_step": round(hbm_gb, 3),
-                              "gbs": round(hbm_gb / (hbm_ms * 1e-3), 1) if hbm_ms > 0 else None,
-                              "frac": round(hbm_gb / (hbm_ms * 1e-3) / peak, 4) if hbm_ms > 0 else None},
-        "knn": None if knn_row is None else {"ms_per_step": knn_row["ms_per_step"], "calls_per_step": knn_row["calls_per_step"],
-                                             "brute_force_pairs_per_step": pairs,
-                                             "equiv_pairs_per_s": pairs / (knn_row["ms_per_step"] * 1e-3)},
-        "kernels": kernels,
-        "host_wall_ms_per_step": wall / args.steps * 1e3,
-        "step_ms": step_ms, "traced_steps": trace_steps, "e2e_step_ms": e2e_step_ms,
-    }
+            "gpu_launches": r["launches"],
+            "clocks": r["clocks"],
+            "roofline": roofline,
+            "hbm_kernels_total": {"ms_per_step": round(hbm_ms, 4), "alg_gb_per_step": round(hbm_gb, 3),
+                                  "gbs": round(hbm_gb / (hbm_ms * 1e-3), 1) if hbm_ms > 0 else None,
+                                  "frac": round(hbm_gb / (hbm_ms * 1e-3) / peak, 4) if hbm_ms > 0 else None,
+                                  "whole_step_frac": round(hbm_gb / (ms_step * 1e-3) / peak, 4)},
+            "knn": None if knn_row is None else {"ms_per_step": knn_row["ms_per_step"], "calls_per_step": knn_row["calls_per_step"],
+                                                 "brute_force_pairs_per_step": pairs,
+                                                 "equiv_pairs_per_s": pairs / (knn_row["ms_per_step"] * 1e-3)},
+            "kernels": kernels,
+            "host_wall_ms_per_step": r["wall_ms_per_step"],
+            "step_ms": brief(r["step_ms"]) if steps > 40 else r["step_ms"], "traced_steps": trace_steps,
+            "e2e_step_ms": brief(e2e_step_ms) if len(e2e_step_ms) > 40 else e2e_step_ms,
+        }
 
-    # ---- full PTv2m2 model step (information; the dense MLPs are cuBLAS, not part of the metric) -------
-    if not args.no_model and world == 1:
-        try:
-            # the schedule's cached (N,k,C) blocks would make the model's different allocation pattern fall
-            # back to synchronous cudaFree/cudaMalloc retries inside its first steps (measured 155 vs 69 ms)
-            del sched
-            trace = None
+    # ---- other schedule variants (fewer steps; same timing rules) ---------------------------------------
+    del sched, trace, one_step
+    r = None
+    torch.cuda.empty_cache()
+    variants = {}
+    if not args.no_variants:
+        for label, over in conf["variants"]:
+            vcfg = make_schedule_config(name, **over)
+            vs = PointOpsSchedule(vcfg, device=dev, seed=rank)
+            vr = time_schedule(ctx, vs, coord, offset, min(steps, VARIANT_STEPS), 3, 1, allreduce)
+            if rank == 0:
+                vk = per_step(summarise_trace(vr["trace"], vr["sizes"], vr["ms_step"], peak), 1)
+                variants[label] = {"value": world * n0 / (vr["ms_step"] * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": vr["ms_step"],
+                                   "steps": min(steps, VARIANT_STEPS), "overrides": over, "gpu_launches_per_step": vr["launches"] // min(steps, VARIANT_STEPS),
+                                   "kernels": [{k2: kr[k2] for k2 in ("kernel", "calls_per_step", "ms_per_step", "frac")} |
+                                               {"largest_us": kr["largest"]["us_per_launch"], "largest_frac": kr["largest"]["frac"]}
+                                               for kr in vk[:8]]}
+            del vs, vr
             torch.cuda.empty_cache()
-            line["model_step"] = model_step(dev, coord, feat, offset)
+    if line is not None and variants:
+        line["variants"] = variants
+
+    # ---- full PTv2m2 training step: bf16 autocast + AdamW, DDP-wrapped at N > 1 --------------------------
+    if not args.no_model:
+        try:
+            ms_model = model_step(ctx, name, coord, feat, offset, args.bucket_cap_mb)
+            if line is not None:
+                line["model_step"] = ms_model
         except Exception as ex:  # pragma: no cover
-            line["model_step"] = {"error": repr(ex)[:200]}
-    # ---- CPU baseline on the box's host cores (bounded sample) -----------------------------------------
-    if not args.no_cpu_baseline and world == 1:
-        r = cpu_reference(steps=1, warmup=0, budget_s=24.0)
-        line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
-                                "sample": r["sample"], "family_seconds": r["family_seconds"]}
-    emit(line)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+            if line is not None:
+                line["model_step"] = {"error": repr(ex)[:300]}
+        torch.cuda.empty_cache()
+    if rank == 0:
+        # ---- the reference's own op schedule on this GPU (oracle/_ref kNN kernel + torch op chains) ----------
+        if not args.no_gpu_reference and world == 1:
+            try:
+                line["gpu_reference"] = gpu_reference(ctx, name, cfg, coord, offset, ms_step)
+            except Exception as ex:  # pragma: no cover
+                line["gpu_reference"] = {"error": repr(ex)[:300]}
+            torch.cuda.empty_cache()
+        if name == "kitti120k" and not args.no_variants and world == 1:
+            try:
+                line["sweep"] = kitti_sweep(ctx, coord, offset, peak)
+            except Exception as ex:  # pragma: no cover
+                line["sweep"] = {"error": repr(ex)[:300]}
+        # ---- CPU baseline on the box's host cores (bounded sample) -----------------------------------------
+        if not args.no_cpu_baseline and world == 1:
+            rc = cpu_reference(name, steps=3, warmup=1)
+            line["cpu_baseline"] = {"value": rc["value"], "unit": UNIT, "cores": rc["cores"], "kind": "port",
+                                    "sample": rc["sample"], "family_seconds": rc["family_seconds"]}
+        emit(line)
+    ctx.finish()
 
 
-def model_step(dev, coord, feat, offset, steps=5):
-    import torch
+def model_step(ctx, name, coord, feat, offset, bucket_cap_mb, steps=8):
+    """Full training step of the config's PTv2m2 (ao_b200.ptv2): bf16 autocast forward, cross-entropy, backward,
+    AdamW — the reference's Trainer.run_step (pointcept/engines/train.py:173-200).  At N > 1 the model is wrapped by
+    ao_b200.sharding.ddp_wrap (engines/defaults.py:30-43), so the gradient all-reduce is DDP's own, bucketed and
+    overlapped with the backward pass."""
+    torch = ctx.torch
+    from ao_b200 import ptv2, sharding
 
-    from ao_b200 import ptv2
-
+    dev = ctx.dev
     torch.manual_seed(0)
-    model = ptv2.PointTransformerV2(**ptv2.S3DIS_CFG).to(dev).train()
-    opt = torch.optim.AdamW(model.parameters(), lr=1e-3)
-    target = torch.randint(0, 13, (coord.shape[0],), device=dev)
+    mcfg = getattr(ptv2, CONFIGS[name]["model"])
+    model = ptv2.PointTransformerV2(**mcfg).to(dev).train()
+    n_params = sum(p.numel() for p in model.parameters())
+    net = sharding.ddp_wrap(model, ctx.local, bucket_cap_mb=bucket_cap_mb) if ctx.world > 1 else model
+    opt = torch.optim.AdamW(net.parameters(), lr=1e-3)
+    target = torch.randint(0, mcfg["num_classes"], (coord.shape[0],), device=dev)
+
     def step():
         with torch.autocast("cuda", dtype=torch.bfloat16):
-            logits = model(dict(coord=coord, feat=feat, offset=offset))
+            logits = net(dict(coord=coord, feat=feat, offset=offset))
         loss = torch.nn.functional.cross_entropy(logits.float(), target)
         opt.zero_grad(set_to_none=True)
         loss.backward()
         opt.step()
         return loss
+
     for _ in range(3):
         step()
-    torch.cuda.synchronize()
+    ctx.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
         loss = step()
     e1.record()
+    ctx.barrier()
+    ms = ctx.max_over_ranks(e0.elapsed_time(e1)) / steps
+    out = {"what": f"full PTv2m2 ({CONFIGS[name]['model']}) training step: bf16 autocast GEMMs (cuBLAS) + these point ops + "
+                   "cross-entropy + AdamW" + (f"; DistributedDataParallel over {ctx.world} ranks (broadcast_buffers=False, "
+                   f"bucket_cap_mb={bucket_cap_mb}, gradient_as_bucket_view), NCCL all-reduce overlapped with backward"
+                   if ctx.world > 1 else ""),
+           "ms_per_step": ms, "mpoints_per_s": ctx.world * coord.shape[0] / (ms * 1e-3) / 1e6, "loss": float(loss.item()),
+           "parameters": n_params, "grad_mb": round(n_params * 4 / 1e6, 2), "steps": steps,
+           "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 1e9}
+    del net, model, opt
+    return out
+
+
+def gpu_reference(ctx, name, cfg, coord, offset, ours_ms_step, steps=2):
+    """The reference's op schedule with the reference's implementations on this B200 (oracle/gpu_path.py: unmodified
+    reference kNN kernel from oracle/_ref + the reference's torch op chains on CUDA tensors).  Checker-side code,
+    timed only here; never on the product path."""
+    torch = ctx.torch
+    from oracle import gpu_path, ref_cuda
+
+    if not ref_cuda.available():
+        return {"unavailable": "oracle/_ref/libpointops_ref.so not built"}
+    n0 = coord.shape[0]
+    out = {}
+    # (1) the reference kNN kernel alone (knn_query_cuda_kernel.cu:60-104): k=16 self search on level 0
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    ref_cuda.knn_query(16, coord, offset)
+    a, b = ev(), ev()
+    a.record()
+    ref_cuda.knn_query(16, coord, offset)
+    b.record()
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / steps
-    return {"what": "full PTv2m2 (S3DIS cfg) training step: bf16 autocast GEMMs (cuBLAS) + these point ops + AdamW",
-            "ms_per_step": ms, "mpoints_per_s": coord.shape[0] / (ms * 1e-3) / 1e6, "loss": float(loss.item()),
-            "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 1e9}
+    out["knn_k16_self_level0_ms"] = round(a.elapsed_time(b), 3)
+    from ao_b200 import pointops
+    pointops.knn_query_raw(16, coord, offset)
+    a, b = ev(), ev()
+    a.record()
+    for _ in range(5):
+        pointops.knn_query_raw(16, coord, offset)
+    b.record()
+    torch.cuda.synchronize()
+    out["knn_k16_self_level0_ms_this_repo"] = round(a.elapsed_time(b) / 5, 3)
+    # (2) the whole reference op schedule
+    sched = gpu_path.GpuReferenceSchedule(cfg, ctx.dev, seed=0)
+    sched.step(coord, offset)
+    torch.cuda.synchronize()
+    a, b = ev(), ev()
+    a.record()
+    for _ in range(steps):
+        sched.step(coord, offset)
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / steps
+    out.update({"what": "reference op schedule on the same B200: unmodified reference kNN kernel (oracle/_ref; 7 self + "
+                        "3 cross searches per step at S3DIS cfg, no neighbour-list sharing) + the reference's pure-torch "
+                        "grouping / GVA tail / GridPool / interpolation on CUDA tensors, autograd backward; same "
+                        "synthetic stand-ins for the dense layers", "ms_per_step": ms, "steps": steps,
+                "value": n0 / (ms * 1e-3) / 1e6, "unit": UNIT, "speedup_of_this_repo": ms / ours_ms_step,
+                "peak_mem_gb": torch.cuda.max_memory_allocated(ctx.dev) / 1e9})
+    del sched
+    return out
+
+
+def kitti_sweep(ctx, coord, offset, peak):
+    """BASELINE.json configs[4]: kNN over k in {8,16,32} and the fused GVA pair (gva_relation + gva_aggregate,
+    forward + backward) over C in {48,96,192,384} on the level-0 scans."""
+    torch = ctx.torch
+    from ao_b200 import pointops
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    n = coord.shape[0]
+    out = {"n": n, "knn": [], "gva": []}
+
+    def timed(fn, reps=5):
+        fn()
+        a, b = ev(), ev()
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    for k in (8, 16, 32):
+        ms = timed(lambda: pointops.knn_query_raw(k, coord, offset))
+        out["knn"].append({"k": k, "ms": round(ms, 4), "mpoints_per_s": round(n / ms / 1e3, 1)})
+    idx, _ = pointops.knn_query(16, coord, offset)
+    k = 16
+    for c in (48, 96, 192, 384):
+        g = c // 8
+        key, query, value = (torch.randn(n, c, device=ctx.dev, requires_grad=True) for _ in range(3))
+        peb = torch.randn(n, k, c, device=ctx.dev, requires_grad=True)
+        logits = torch.randn(n, k, g, device=ctx.dev, requires_grad=True)
+        g_rel, g_out = torch.randn(n, k, c, device=ctx.dev), torch.randn(n, c, device=ctx.dev)
+
+        def fb():
+            rel = pointops.gva_relation(key, query, idx)
+            o = pointops.gva_aggregate(value, peb, logits, idx, g)
+            torch.autograd.grad([rel, o], [key, query, value, peb, logits], [g_rel, g_out])
+
+        ms = timed(fb, 3)
+        nb = (4.0 * n * k + 8.0 * n * c + 4.0 * n * k * c) + (8.0 * n * c + 4.0 * n * k * c + 8.0 * n * k * g + 4.0 * n * k) \
+            + (4.0 * n * k * c + 4.0 * n * k + 4.0 * (n + 1) + 8.0 * n * c) \
+            + (8.0 * n * c + 8.0 * n * k * c + 8.0 * n * k * g + 4.0 * n * k) + (4.0 * n * k * g + 8.0 * n * c + 4.0 * (n + 1) + 4.0 * n * k)
+        out["gva"].append({"c": c, "g": g, "k": k, "fwd_bwd_ms": round(ms, 4), "alg_gb": round(nb / 1e9, 3),
+                           "gbs": round(nb / ms / 1e6, 1), "frac": round(nb / ms / 1e6 / peak, 4)})
+        del key, query, value, peb, logits, g_rel, g_out
+    return out
 
 
 _REAL_STDOUT = None
@@ -572,11 +860,17 @@ def main():
     quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=None, help=f"timed steps (default {DEFAULT_STEPS}: a timed region >= 2 s; "
+                    f"reference arm: {DEFAULT_STEPS_REFERENCE})")
+    ap.add_argument("--warmup", type=int, default=None, help="untimed warm-up steps (default 5)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="s3dis4", choices=sorted(CONFIGS), help="BASELINE.json configs[1..4]")
+    ap.add_argument("--rooms-per-gpu", type=int, default=None, help="override the config's scenes per GPU")
+    ap.add_argument("--bucket-cap-mb", type=float, default=4.0, help="DDP bucket size of the N>1 model step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-reference", action="store_true")
     ap.add_argument("--no-model", action="store_true")
+    ap.add_argument("--no-variants", action="store_true")
     ap.add_argument("--presort", action="store_true", help="(experiment) Morton-order the points of every room on the host")
     ap.add_argument("--skip-e2e", action="store_true", help="(profiling runs only) skip the host-buffer leg")
     ap.add_argument("--min-warmup", type=int, default=3, help="(profiling runs only) lower bound on warm-up steps")

@@ -31,8 +31,30 @@ import torch
 
 from . import torch_ref
 
-S3DIS = dict(k=16, patch_depth=2, channels=(48, 96, 192, 384), groups=(6, 12, 24, 48), enc_depths=(2, 6, 2),
-             dec_depths=(1, 1, 1), grid_sizes=(0.1, 0.2, 0.4), interp_k=3)
+class Cfg:
+    """Op-schedule description with the accessor names of ao_b200.schedule.ScheduleConfig (bench.py passes that
+    dataclass in; this class keeps the oracle importable on its own).  Default = the S3DIS config
+    (configs/s3dis/semseg-pt-v2m2-0-base.py:10-36)."""
+
+    def __init__(self, k=16, patch_k=None, patch_depth=2, channels=(48, 96, 192, 384), groups=(6, 12, 24, 48),
+                 enc_depths=(2, 6, 2), dec_depths=(1, 1, 1), grid_sizes=(0.1, 0.2, 0.4), interp_k=3, unpool="interp"):
+        self.k, self.patch_k, self.patch_depth, self.channels, self.groups = k, patch_k, patch_depth, channels, groups
+        self.enc_depths, self.dec_depths, self.grid_sizes, self.interp_k, self.unpool = (
+            enc_depths, dec_depths, grid_sizes, interp_k, unpool)
+
+    def k_patch(self):
+        return self.patch_k or self.k
+
+    def k_enc(self, i):
+        return self.k
+
+    def k_dec(self, i):
+        return self.k
+
+
+S3DIS = Cfg()
+FIXED_FRACTION = 0.04    # query-row fraction of a reference-arm step (fixed: a per-run calibration made the arm's
+#                          value move by +-40 % between runs of the same code)
 
 
 def knn_cdist_topk(k, xyz, new_xyz, chunk=2048):
@@ -70,10 +92,12 @@ class CpuRoom:
         self.cfg = cfg
         g = torch.Generator().manual_seed(seed)
         self.coords: List[torch.Tensor] = [torch.from_numpy(np.ascontiguousarray(coord))]
-        for gs in cfg["grid_sizes"]:
+        self.clusters = []
+        for gs in cfg.grid_sizes:
             c = self.coords[-1]
-            nc, _, _ = grid_pool_fast(c, c, gs)
+            nc, _, cl = grid_pool_fast(c, c, gs)
             self.coords.append(nc.contiguous())
+            self.clusters.append(cl)
         self.sizes = [c.shape[0] for c in self.coords]
         self.gen = g
 
@@ -82,7 +106,7 @@ class CpuRoom:
 
     def _block(self, li, rows, idx):
         cfg = self.cfg
-        n, c, g, k = self.sizes[li], cfg["channels"][li], cfg["groups"][li], cfg["k"]
+        n, c, g, k = self.sizes[li], cfg.channels[li], cfg.groups[li], idx.shape[1]
         coord = self.coords[li]
         key, value = self._rand(n, c, grad=True), self._rand(n, c, grad=True)
         query, peb = self._rand(rows, c, grad=True), self._rand(rows, k, c, grad=True)
@@ -105,10 +129,9 @@ class CpuRoom:
         Returns seconds per operator family (only operator time is counted, not the synthetic
         tensor generation)."""
         cfg = self.cfg
-        k = cfg["k"]
         rows = [max(1, min(n, math.ceil(f * n))) for n in self.sizes]
         t = dict(knn=0.0, block=0.0, pool=0.0, interp=0.0)
-        n_stage = len(cfg["grid_sizes"])
+        n_stage = len(cfg.grid_sizes)
 
         def knn(li, kk, q):
             t0 = time.perf_counter()
@@ -116,33 +139,37 @@ class CpuRoom:
             t["knn"] += time.perf_counter() - t0
             return idx, dist
 
-        idx, _ = knn(0, k, self.coords[0][:rows[0]])
-        for _ in range(cfg["patch_depth"]):
+        idx, _ = knn(0, cfg.k_patch(), self.coords[0][:rows[0]])
+        for _ in range(cfg.patch_depth):
             t["block"] += self._block(0, rows[0], idx)
         for i in range(n_stage):
-            c_next = cfg["channels"][i + 1]
+            c_next = cfg.channels[i + 1]
             feat = torch.relu(self._rand(rows[i], c_next)).requires_grad_(True)
             t0 = time.perf_counter()
-            _, nf, _ = grid_pool_fast(self.coords[i][:rows[i]], feat, cfg["grid_sizes"][i])
+            _, nf, _ = grid_pool_fast(self.coords[i][:rows[i]], feat, cfg.grid_sizes[i])
             torch.autograd.grad(nf, feat, torch.ones_like(nf))
             t["pool"] += time.perf_counter() - t0
-            idx, _ = knn(i + 1, k, self.coords[i + 1][:rows[i + 1]])
-            for _ in range(cfg["enc_depths"][i]):
+            idx, _ = knn(i + 1, cfg.k_enc(i), self.coords[i + 1][:rows[i + 1]])
+            for _ in range(cfg.enc_depths[i]):
                 t["block"] += self._block(i + 1, rows[i + 1], idx)
         for i in reversed(range(n_stage)):
-            c = cfg["channels"][i]
+            c = cfg.channels[i]
             src = self._rand(self.sizes[i + 1], c, grad=True)
             q = self.coords[i][:rows[i]]
-            idx3, dist3 = knn(i + 1, cfg["interp_k"], q)                                # interpolation.py:14
-            t0 = time.perf_counter()
-            w = torch_ref.interpolation_weights(dist3)
-            up = torch.zeros(rows[i], c)
-            for j in range(cfg["interp_k"]):
-                up = up + src[idx3[:, j].long(), :] * w[:, j].unsqueeze(-1)            # :20-21
+            if cfg.unpool == "interp":
+                idx3, dist3 = knn(i + 1, cfg.interp_k, q)                               # interpolation.py:14
+                t0 = time.perf_counter()
+                w = torch_ref.interpolation_weights(dist3)
+                up = torch.zeros(rows[i], c)
+                for j in range(cfg.interp_k):
+                    up = up + src[idx3[:, j].long(), :] * w[:, j].unsqueeze(-1)        # :20-21
+            else:
+                t0 = time.perf_counter()
+                up = src[self.clusters[i][:rows[i]]]                                    # …v2m2_base.py:309 ("map")
             torch.autograd.grad(up, src, torch.ones_like(up))
             t["interp"] += time.perf_counter() - t0
-            idx, _ = knn(i, k, q)                                                        # …v2m2_base.py:223 (not shared)
-            for _ in range(cfg["dec_depths"][i]):
+            idx, _ = knn(i, cfg.k_dec(i), q)                                             # …v2m2_base.py:223 (not shared)
+            for _ in range(cfg.dec_depths[i]):
                 t["block"] += self._block(i, rows[i], idx)
         t["total"] = sum(t.values())
         t["points"] = f * self.sizes[0] if rows[0] < self.sizes[0] else float(self.sizes[0])

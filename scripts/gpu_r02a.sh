@@ -1,0 +1,20 @@
+#!/bin/bash
+# round 2, call A: GPU parity tests + the four bench configs (first measurement of configs[2..4]) + reference arm
+TAG=${1:-r02a}
+O=gpurun_out/$TAG
+mkdir -p $O
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --format=csv > $O/gpu_info.csv 2>&1
+nproc > $O/nproc.txt
+if [ "${SKIP_TESTS:-0}" != "1" ]; then
+  timeout 1500 python -m pytest tests -m gpu -q -x --timeout 900 -p no:cacheprovider > $O/pytest_gpu.log 2>&1
+  echo "pytest exit: $?" >> $O/pytest_gpu.log
+  tail -8 $O/pytest_gpu.log
+fi
+for cfg in ${CONFIGS:-s3dis4 scannet150k kitti120k s3dis8}; do
+  st=${STEPS:-60}
+  timeout 900 python bench.py --config $cfg --steps $st --warmup 3 > $O/bench_$cfg.json 2> $O/bench_$cfg.err
+  echo "bench $cfg exit: $?"; head -c 700 $O/bench_$cfg.json; echo; tail -3 $O/bench_$cfg.err
+done
+if [ "${SKIP_REF:-0}" != "1" ]; then
+  timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > $O/bench_ref.json 2> $O/bench_ref.err; head -c 400 $O/bench_ref.json
+fi

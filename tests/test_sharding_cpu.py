@@ -47,6 +47,25 @@ def _worker(rank, world, port, tmp):
     dist.all_reduce(g)
     ok = ok and bool((g == sum(range(1, world + 1))).all())
     ok = ok and sharding.max_over_ranks(float(rank), "cpu") == float(world - 1)
+    # ddp_wrap (the reference's create_ddp_model, engines/defaults.py:30-43) on a host model built from the PTv2 module
+    # classes: several small buckets, gradients = mean over ranks of the per-rank gradients (DDP's contract)
+    from ao_b200 import ptv2
+
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(6, 32), ptv2.PointBatchNorm(32), torch.nn.ReLU(), torch.nn.Linear(32, 32),
+                              ptv2.PointBatchNorm(32), torch.nn.ReLU(), torch.nn.Linear(32, 5))
+    ref = __import__("copy").deepcopy(net)
+    ddp = sharding.ddp_wrap(net, None, bucket_cap_mb=0.002)
+    xs = [torch.randn(40 + 10 * r, 6, generator=torch.Generator().manual_seed(100 + r)) for r in range(world)]
+    ddp(xs[rank]).square().mean().backward()
+    want = [torch.zeros_like(p_) for p_ in ref.parameters()]
+    for r in range(world):
+        ref.zero_grad()
+        ref(xs[r]).square().mean().backward()
+        for w_, p_ in zip(want, ref.parameters()):
+            w_ += p_.grad / world
+    ok = ok and all(torch.allclose(p_.grad, w_, rtol=1e-5, atol=1e-6) for p_, w_ in zip(net.parameters(), want))
+    ok = ok and len(ddp.reducer._get_bucket_tensors() if hasattr(ddp.reducer, "_get_bucket_tensors") else [0, 0]) >= 2
     open(os.path.join(tmp, f"ok{rank}"), "w").write("1" if ok else "0")
     dist.destroy_process_group()
 

@@ -46,6 +46,7 @@ SIGNATURES = {
     "aopt_gva_forward": (c_int, [c_int, c_int, c_int, c_int, P, P, P, P, P, P, P]),
     "aopt_gva_backward_query": (c_int, [c_int, c_int, c_int, c_int, P, P, P, P, P, P, P, P]),
     "aopt_gva_backward_value": (c_int, [c_int, c_int, c_int, c_int, P, P, P, P, P, P]),
+    "aopt_gva_backward": (c_int, [c_int, c_int, c_int, c_int, P, P, P, P, P, P, P, P, P, P, P]),
     "aopt_segment_min3": (c_int, [c_int, c_int, P, P, P, P]),
     "aopt_voxel_keys": (c_int, [c_int, c_int, P, P, P, c_float, P, P, P]),
     "aopt_voxel_partition_workspace_bytes": (c_size_t, [c_int]),

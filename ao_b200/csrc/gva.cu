@@ -355,6 +355,137 @@ gva_backward_query_ns_kernel(long long n, int c, int g, const float *__restrict_
     }
 }
 
+// ---- backward, fused: grad_peb + grad_logits (per query) AND grad_value (per source) in one kernel -------
+// In self-attention the queries ARE the sources (n_src == n), so the thread that owns (point, chunk) in the
+// query pass above also owns the same (source row, chunk) of the CSR walk of gva_backward_value.  The two
+// halves bound each other's idle resource: the query half waits on DRAM (HBM-bound: 32 streamed / gathered
+// 16-byte pieces per item, cp.async), the walk half is a dependent chain of L2 hits (rowptr -> perm ->
+// grad_out row + probability, latency-bound at ~30 % of the HBM pipe when it runs alone).  Here the walk of a
+// thread's row runs BETWEEN issuing the item's cp.async copies and waiting for them, i.e. in the shadow of
+// the DRAM latency of the same thread.  DRAM traffic = SURVEY §8d's "fused GVA bwd": the second read of prob /
+// grad_out (by the walk) is an L2 hit because the grid sweeps one compact window of rows.
+// Same per-row entry order (ascending p) and the same fmaf sequence as csr_walk_kernel<8, BvPolicy>: grad_value
+// is bitwise identical to the two-kernel path; grad_peb / grad_logits are the code of the kernel above.
+constexpr int kFusedBatch = 8;
+
+template <int GL, int NS, bool HAS_PEB>
+__global__ void __launch_bounds__(kGvaNsBlock)
+gva_backward_fused_ns_kernel(long long n, int c, int g, const float *__restrict__ grad_out,
+                             const float *__restrict__ value, const float *__restrict__ peb,
+                             const float *__restrict__ prob, const int *__restrict__ idx,
+                             const int *__restrict__ rowptr, const int *__restrict__ perm,
+                             float *__restrict__ grad_peb, float *__restrict__ grad_logits,
+                             float *__restrict__ grad_value) {
+    extern __shared__ float4 stage[];
+    constexpr int B = kFusedBatch;
+    constexpr int KSHIFT = NS == 8 ? 3 : NS == 16 ? 4 : 5;
+    float4 *sv = stage + threadIdx.x;
+    float4 *sq = stage + NS * kGvaNsBlock + threadIdx.x;
+    const int chunks = c >> 2;
+    const long long total = n * chunks;
+    const long long step = (long long)gridDim.x * kGvaNsBlock;
+    long long base = (long long)blockIdx.x * kGvaNsBlock + (threadIdx.x & ~31);
+    const int lane = threadIdx.x & 31;
+    int jn[NS];
+    // walk state: [e, e_end) = CSR row of the current item, pn = its first B perm values, (ne, ne_end) = next item's row
+    int e = 0, e_end = 0, ne = 0, ne_end = 0;
+    int pn[B];
+    if (base < total) {
+        const long long pt0 = min(base + lane, total - 1) / chunks;
+        load_idx_row16(idx + (size_t)pt0 * NS, jn, NS / 4);
+        e = __ldg(rowptr + pt0); e_end = __ldg(rowptr + pt0 + 1);
+#pragma unroll
+        for (int u = 0; u < B; ++u) pn[u] = (e + u < e_end) ? __ldg(perm + e + u) : 0;
+        if (base + step < total) {
+            const long long pt1 = min(base + step + lane, total - 1) / chunks;
+            ne = __ldg(rowptr + pt1); ne_end = __ldg(rowptr + pt1 + 1);
+        }
+    }
+    for (; base < total; base += step) {
+        const long long t_raw = base + lane;
+        const bool live = t_raw < total;
+        const long long t = live ? t_raw : total - 1;
+        const long long pt = t / chunks;
+        const int ch = (int)(t - pt * chunks);
+        const int gi = ch / GL;
+        const bool writer = live && (ch % GL) == 0;
+        int j[NS];
+#pragma unroll
+        for (int s = 0; s < NS; ++s) j[s] = jn[s];
+        const float *vbase = value + ch * 4;
+#pragma unroll
+        for (int s = 0; s < NS; ++s) cp_async16_row<2>(sv + s * kGvaNsBlock, vbase + (size_t)max(j[s], 0) * c);
+        if (HAS_PEB) {
+            const float *pe = peb + (size_t)pt * NS * c + ch * 4;
+#pragma unroll
+            for (int s = 0; s < NS; ++s) cp_async16_stream(sq + s * kGvaNsBlock, pe + (size_t)s * c);
+        }
+        cp_async_commit();
+        const float4 go = ldg_gather4(grad_out + (size_t)pt * c + ch * 4);
+        const float *pr = prob + (size_t)pt * NS * g + gi;
+        float p[NS], gw[NS];
+#pragma unroll
+        for (int s = 0; s < NS; ++s) p[s] = __ldg(pr + (size_t)s * g);
+        const bool more = base + step < total;
+        if (more) load_idx_row16(idx + (size_t)(min(base + step + lane, total - 1) / chunks) * NS, jn, NS / 4);
+        // rowptr of the item after next (two rows ahead, like csr_walk_kernel)
+        int nne = 0, nne_end = 0;
+        if (base + 2 * step < total) {
+            const long long pt2 = min(base + 2 * step + lane, total - 1) / chunks;
+            nne = __ldg(rowptr + pt2); nne_end = __ldg(rowptr + pt2 + 1);
+        }
+        // ---- CSR walk of source row `pt`, chunk `ch` (grad_value), under the copies issued above ----
+        {
+            float4 acc = f4_zero();
+            const float *gbase = grad_out + ch * 4;
+            const float *wbase = prob + gi;
+            for (;;) {
+                const bool last = e + B >= e_end;
+                int q[B];
+                float4 v[B];
+                float w[B];
+#pragma unroll
+                for (int u = 0; u < B; ++u) {
+                    q[u] = pn[u];   // flat (query, slot) position; slots past the row end hold 0 (a valid entry)
+                    v[u] = ldg_gather4(gbase + (size_t)(q[u] >> KSHIFT) * c);
+                }
+#pragma unroll
+                for (int u = 0; u < B; ++u) w[u] = __ldg(wbase + (size_t)q[u] * g);
+                const int pe0 = last ? ne : e + B, pe1 = last ? ne_end : e_end;
+#pragma unroll
+                for (int u = 0; u < B; ++u) pn[u] = (pe0 + u < pe1) ? __ldg(perm + pe0 + u) : 0;
+                issue_fence();
+#pragma unroll
+                for (int u = 0; u < B; ++u) fma_keep(acc, v[u], w[u], e + u < e_end);
+                if (last) break;
+                e += B;
+            }
+            if (live) *reinterpret_cast<float4 *>(grad_value + (size_t)pt * c + ch * 4) = acc;
+            e = ne; e_end = ne_end; ne = nne; ne_end = nne_end;
+        }
+        // ---- query half (identical to gva_backward_query_ns_kernel) ----
+        float *gp = (HAS_PEB && grad_peb && live) ? grad_peb + (size_t)pt * NS * c + ch * 4 : nullptr;
+        cp_async_wait_all();
+        float dot = 0.f;
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            const bool keep = j[s] >= 0;
+            const float4 v = sv[s * kGvaNsBlock];
+            const float4 q = HAS_PEB ? sq[s * kGvaNsBlock] : f4_zero();
+            const float d = group_sum<GL>(dot4(go, f4_add(v, q)));
+            gw[s] = keep ? d : 0.f;
+            const float w = keep ? p[s] : 0.f;
+            if (gp) stg_stream4(gp + (size_t)s * c, make_float4(go.x * w, go.y * w, go.z * w, go.w * w));
+            dot = fmaf(p[s], gw[s], dot);
+        }
+        if (writer) {
+            float *gl = grad_logits + (size_t)pt * NS * g + gi;
+#pragma unroll
+            for (int s = 0; s < NS; ++s) gl[(size_t)s * g] = p[s] * (gw[s] - dot);  // softmax backward
+        }
+    }
+}
+
 // ---- backward, per source: grad_value through the CSR ------------------------------------------------
 // kshift >= 0: k is a power of two and q = p >> kshift; otherwise q = p / k.
 // The row walk is a dependent chain (rowptr → perm → prob / grad_out), so entries are taken eight at a
@@ -774,6 +905,41 @@ extern "C" int aopt_gva_backward_value(int n_src, int nsample, int c, int g, con
         if (I > kMaxScalarI) return AOPT_ERR_UNSUPPORTED;
         gva_backward_value_scalar_kernel<<<stride_grid((long long)n_src * g, kGvaBlock, 8), kGvaBlock, 0, as_stream(stream)>>>(
             n_src, nsample, c, g, I, grad_out, prob, rowptr, perm, grad_value);
+    }
+    return check_launch();
+}
+
+// Fused backward for self-attention (n_src == n): grad_peb, grad_logits and grad_value in ONE kernel when the
+// specialised path applies (128-bit layout, nsample in {8,16,32}); otherwise the two kernels above back to back.
+// AOPT_GVA_BWD=split forces the two-kernel path (A/B measurements).
+extern "C" int aopt_gva_backward(int n, int nsample, int c, int g, const float *grad_out, const float *value,
+                                 const float *peb, const float *prob, const int *idx, const int *rowptr,
+                                 const int *perm, float *grad_peb, float *grad_logits, float *grad_value,
+                                 aopt_stream_t stream) {
+    int rc = gva_check(n, nsample, c, g);
+    if (rc != AOPT_OK) return rc;
+    if (n == 0) return AOPT_OK;
+    if (!grad_out || !value || !prob || !idx || !grad_logits || !rowptr || !perm || !grad_value)
+        return AOPT_ERR_INVALID_ARGUMENT;
+    static const bool split = [] { const char *e = getenv("AOPT_GVA_BWD"); return e && e[0] == 's'; }();
+    const int I = c / g;
+    const int gl = pick_gl(c, I, {grad_out, value, peb, grad_peb, grad_value});
+    const bool ns = nsample == 8 || nsample == 16 || nsample == 32;
+    if (split || gl == 0 || !ns || !aligned16(idx)) {
+        rc = aopt_gva_backward_query(n, nsample, c, g, grad_out, value, peb, prob, idx, grad_peb, grad_logits, stream);
+        if (rc != AOPT_OK) return rc;
+        return aopt_gva_backward_value(n, nsample, c, g, grad_out, prob, rowptr, perm, grad_value, stream);
+    }
+    const long long items = (long long)n * (c / 4);
+    if (nsample == 16) {
+        GVA_DISPATCH_NS(gl, 16, peb != nullptr, gva_backward_fused_ns_kernel, items, as_stream(stream), (long long)n, c, g,
+                        grad_out, value, peb, prob, idx, rowptr, perm, grad_peb, grad_logits, grad_value);
+    } else if (nsample == 8) {
+        GVA_DISPATCH_NS(gl, 8, peb != nullptr, gva_backward_fused_ns_kernel, items, as_stream(stream), (long long)n, c, g,
+                        grad_out, value, peb, prob, idx, rowptr, perm, grad_peb, grad_logits, grad_value);
+    } else {
+        GVA_DISPATCH_NS(gl, 32, peb != nullptr, gva_backward_fused_ns_kernel, items, as_stream(stream), (long long)n, c, g,
+                        grad_out, value, peb, prob, idx, rowptr, perm, grad_peb, grad_logits, grad_value);
     }
     return check_launch();
 }

@@ -134,14 +134,23 @@ class _AggregateFn(Function):
         grad_value = None
         want_value = ctx.needs_input_grad[0]
         with _lib.on_device(dev):
-            # grad_value (CSR walk: latency / L1 bound, 30 % of the HBM pipe) and grad_peb / grad_logits (streaming,
-            # HBM bound) are independent: the walk goes to a side stream and overlaps the streaming kernel.
-            # Everything is allocated on the caller's stream; the side stream starts after an event that follows
-            # the allocations and inputs, and the caller's stream joins it before returning.
             side = _lib.side_stream(dev, "walk") if (want_value and n > 0 and _lib.overlap(role="walk")) else None
             if want_value:
                 csr = get_csr(idx, n_src, 0)
                 grad_value = torch.empty((n_src, c), dtype=torch.float32, device=dev)
+            if want_value and n_src == n and n > 0 and side is None:
+                # self-attention (queries == sources): ONE kernel — the latency-bound CSR walk of grad_value runs in
+                # the shadow of the HBM-bound per-query pass (csrc/gva.cu gva_backward_fused_ns_kernel)
+                _lib.check(
+                    lib.aopt_gva_backward(n, k, c, g, _lib.ptr(grad_out), _lib.ptr(value), _lib.ptr(peb), _lib.ptr(prob),
+                                          _lib.ptr(idx), _lib.ptr(csr.rowptr), _lib.ptr(csr.perm), _lib.ptr(grad_peb),
+                                          _lib.ptr(grad_logits), _lib.ptr(grad_value), _lib.stream()),
+                    "gva_backward",
+                )
+                return grad_value, grad_peb, grad_logits, None, None
+            # cross attention, or the side-stream experiment: grad_value (CSR walk) and grad_peb / grad_logits
+            # (streaming) as two kernels.  Everything is allocated on the caller's stream; the side stream starts
+            # after an event that follows the allocations and inputs, and the caller's stream joins it before returning.
             if side is not None:
                 main = torch.cuda.current_stream(dev)
                 side.wait_stream(main)

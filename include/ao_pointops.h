@@ -160,6 +160,14 @@ int aopt_gva_backward_query(int n, int nsample, int c, int g, const float *grad_
 int aopt_gva_backward_value(int n_src, int nsample, int c, int g, const float *grad_out,
                             const float *prob, const int *rowptr, const int *perm,
                             float *grad_value, aopt_stream_t stream);
+/* Both of the above in ONE kernel for self-attention (queries == sources, n_src == n): the CSR walk of
+ * a thread's source row runs in the shadow of the DRAM latency of its query item.  Same results bit for
+ * bit; falls back to the two kernels for layouts outside the specialised path.  Autograd of
+ * ...v2m2_base.py:110,119-128 in one pass (SURVEY.md 8d "Fused GVA bwd"). */
+int aopt_gva_backward(int n, int nsample, int c, int g, const float *grad_out, const float *value,
+                      const float *peb, const float *prob, const int *idx, const int *rowptr,
+                      const int *perm, float *grad_peb, float *grad_logits, float *grad_value,
+                      aopt_stream_t stream);
 
 /* ---- GridPool ----------------------------------------------------------------------------- */
 /* start (b,3) = per-scene minimum corner (segment_csr(coord, ptr, "min")). */

@@ -10,6 +10,7 @@ if [ "${SKIP_TESTS:-0}" != "1" ]; then
   echo "pytest exit: $?" >> $O/pytest_gpu.log
   tail -8 $O/pytest_gpu.log
 fi
+timeout 600 python scripts/kernel_bench.py --levels 0,1,2 > $O/kernel_bench.txt 2>&1; grep -i "gva_backward\|level" $O/kernel_bench.txt
 for cfg in ${CONFIGS:-s3dis4 scannet150k kitti120k s3dis8}; do
   st=${STEPS:-60}
   timeout 900 python bench.py --config $cfg --steps $st --warmup 3 > $O/bench_$cfg.json 2> $O/bench_$cfg.err

@@ -100,6 +100,8 @@ for li in [int(x) for x in args.levels.split(",")]:
         8.0 * n * c + 8.0 * n * k * c + 8.0 * n * k * g + 4.0 * n * k)
     row("gva_backward_value", timeit(lambda: lib.aopt_gva_backward_value(n, k, c, g, g_out.data_ptr(), prob.data_ptr(), csr.rowptr.data_ptr(), csr.perm.data_ptr(), gval.data_ptr(), _lib.stream())),
         4.0 * n * k * g + 8.0 * n * c + 4.0 * (n + 1) + 4.0 * n * k)
+    row("gva_backward (fused q+v)", timeit(lambda: lib.aopt_gva_backward(n, k, c, g, g_out.data_ptr(), value.data_ptr(), peb.data_ptr(), prob.data_ptr(), idx.data_ptr(), csr.rowptr.data_ptr(), csr.perm.data_ptr(), gpeb.data_ptr(), glog.data_ptr(), gval.data_ptr(), _lib.stream())),
+        8.0 * n * c + 8.0 * n * k * c + 8.0 * n * k * g + 8.0 * n * k + 4.0 * (n + 1) + 4.0 * n * c)
     if pointops.pe_mlp_supported(c):
         import torch.nn as nn
         from ao_b200 import ptv2 as _ptv2

@@ -370,6 +370,45 @@ def test_relation_backward_fused_equals_the_two_pass_kernels(c):
     assert torch.equal(a, gk2) and torch.equal(b, gq2)
 
 
+@pytest.mark.parametrize("c,g,k,use_peb", [(48, 6, 16, True), (96, 12, 16, True), (384, 48, 16, False), (64, 4, 8, True),
+                                           (64, 16, 32, True), (48, 6, 12, True)])
+def test_gva_backward_fused_equals_the_two_kernels(c, g, k, use_peb):
+    """aopt_gva_backward (query pass + CSR walk in one kernel, self-attention) gives bit-identical grad_peb /
+    grad_logits / grad_value to aopt_gva_backward_query + aopt_gva_backward_value: real neighbour lists with -1
+    padded rows, hub rows far longer than one batch of the walk, a partial last warp; k = 12 takes the fallback."""
+    from ao_b200 import _lib, pointops, scenes
+
+    coord, _, off = scenes.small_batch(31, sizes=(1100, 5, 1700, 3))
+    coord[:40] = coord[0] + 1e-3 * np.arange(40, dtype=np.float32)[:, None]   # a tight clump: its members are hubs
+    xyz, o = to_cuda(coord, off)
+    n = xyz.shape[0]
+    idx, _ = pointops.knn_query(k, xyz, o)
+    assert int((idx < 0).sum()) > 0
+    gen = torch.Generator(device="cuda").manual_seed(c + k)
+    rnd = lambda *s: torch.randn(*s, device="cuda", generator=gen)
+    value, peb, logits, grad_out = rnd(n, c), (rnd(n, k, c) if use_peb else None), rnd(n, k, g), rnd(n, c)
+    prob = torch.softmax(logits, dim=1).contiguous()
+    csr = pointops.get_csr(idx, n)
+    assert int(torch.diff(csr.rowptr).max()) > 2 * 8
+    lib = _lib.load()
+    P = _lib.ptr
+    gp1, gp2 = ((torch.empty(n, k, c, device="cuda"), torch.empty(n, k, c, device="cuda")) if use_peb else (None, None))
+    gl1, gl2, gv1, gv2 = (torch.empty(n, k, g, device="cuda"), torch.empty(n, k, g, device="cuda"),
+                          torch.empty(n, c, device="cuda"), torch.empty(n, c, device="cuda"))
+    _lib.check(lib.aopt_gva_backward_query(n, k, c, g, P(grad_out), P(value), P(peb), P(prob), P(idx), P(gp1), P(gl1), _lib.stream()), "q")
+    _lib.check(lib.aopt_gva_backward_value(n, k, c, g, P(grad_out), P(prob), P(csr.rowptr), P(csr.perm), P(gv1), _lib.stream()), "v")
+    _lib.check(lib.aopt_gva_backward(n, k, c, g, P(grad_out), P(value), P(peb), P(prob), P(idx), P(csr.rowptr), P(csr.perm),
+                                     P(gp2), P(gl2), P(gv2), _lib.stream()), "fused")
+    assert torch.equal(gl1, gl2) and torch.equal(gv1, gv2)
+    if use_peb:
+        assert torch.equal(gp1, gp2)
+    # grad_value against an fp64 scatter
+    w = prob.double() * (idx >= 0).unsqueeze(-1)
+    contrib = (w.unsqueeze(-1) * grad_out.double().view(n, 1, g, c // g)).reshape(n * k, c)
+    ref = torch.zeros(n + 1, c, device="cuda", dtype=torch.float64).index_add_(0, torch.where(idx < 0, n, idx).reshape(-1).long(), contrib)[:n]
+    assert torch.allclose(gv2.double(), ref, rtol=1e-5, atol=1e-4)
+
+
 # ------------------------------------------------------------------------------------------ per-scene bounding box
 @pytest.mark.parametrize("sizes", [
     [5000, 1, 0, 3000, 2047, 2049, 7],            # empty scene, scenes ending right around the 2048-point chunks

@@ -27,6 +27,7 @@ SIGNATURES = {
     "aopt_status_string": (c_char_p, [c_int]),
     "aopt_last_cuda_error": (c_char_p, []),
     "aopt_kernel_launches": (c_ulonglong, []),
+    "aopt_set_tuning": (c_int, [c_char_p, c_int]),
     "aopt_offset2batch": (c_int, [c_int, c_int, P, P, P]),
     "aopt_knn_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "aopt_knn_query": (c_int, [c_int, c_int, c_int, c_int, P, P, P, P, P, P, c_int, P, c_size_t, P]),
@@ -51,6 +52,8 @@ SIGNATURES = {
     "aopt_voxel_keys": (c_int, [c_int, c_int, P, P, P, c_float, P, P, P]),
     "aopt_voxel_partition_workspace_bytes": (c_size_t, [c_int]),
     "aopt_voxel_partition": (c_int, [c_int, c_int, P, P, P, P, P, P, P, P, P, P, c_size_t, P]),
+    "aopt_voxel_grid_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "aopt_voxel_grid": (c_int, [c_int, c_int, P, P, P, c_float, c_int, P, P, P, P, P, P, P, c_size_t, P]),
     "aopt_pool_forward": (c_int, [c_int, c_int, P, P, P, P, P, P, P, P]),
     "aopt_pool_backward": (c_int, [c_int, c_int, P, P, P, P, P]),
     "aopt_interp_weights": (c_int, [c_int, c_int, P, P, P]),
@@ -76,8 +79,8 @@ KNN_SQRT_DIST = 0x100   # OR-ed into the method: the kernel writes sqrt(dist2)
 
 _lib = None
 _trace = None  # list of (entry point, args, start event, end event) while bench.py's profiler is on
-_UNTRACED = {"aopt_version", "aopt_status_string", "aopt_last_cuda_error", "aopt_kernel_launches",
-             "aopt_knn_workspace_bytes", "aopt_csr_workspace_bytes", "aopt_voxel_partition_workspace_bytes",
+_UNTRACED = {"aopt_set_tuning", "aopt_version", "aopt_status_string", "aopt_last_cuda_error", "aopt_kernel_launches",
+             "aopt_knn_workspace_bytes", "aopt_csr_workspace_bytes", "aopt_voxel_partition_workspace_bytes", "aopt_voxel_grid_workspace_bytes",
              "aopt_pe_mlp_supported", "aopt_pos_moments_workspace_bytes", "aopt_pe_mlp_state_bytes",
              "aopt_pe_mlp_backward_workspace_bytes"}
 
@@ -159,6 +162,11 @@ def load() -> "_Library":
         setattr(lib, name, _Entry(name, fn))
     _lib = lib
     return lib
+
+
+def set_tuning(name: str, value: int) -> None:
+    """A/B switch of the library (include/ao_pointops.h aopt_set_tuning); results never depend on it."""
+    check(load().aopt_set_tuning(name.encode(), int(value)), "set_tuning")
 
 
 def version() -> str:

@@ -1,5 +1,7 @@
 // api.cu — status plumbing of the C ABI (include/ao_pointops.h).
 #include <atomic>
+#include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -18,7 +20,40 @@ int check_launch(int kernels) {
     return AOPT_OK;
 }
 
+static std::atomic<int> g_tuning[kTuneCount];
+static std::atomic<bool> g_tuning_init{false};
+static const char *const kTuneNames[kTuneCount] = {"csr_impl", "gva_bwd", "voxel_sort", nullptr, nullptr, nullptr, nullptr, nullptr};
+
+static void tuning_init() {
+    if (g_tuning_init.exchange(true)) return;
+    auto env = [](const char *name, const char *one, const char *two) {
+        const char *e = getenv(name);
+        if (!e || !e[0]) return 0;
+        return e[0] == one[0] ? 1 : e[0] == two[0] ? 2 : 0;
+    };
+    g_tuning[kTuneCsrImpl] = env("AOPT_CSR_IMPL", "sort", "count");
+    g_tuning[kTuneGvaBwd] = env("AOPT_GVA_BWD", "fused", "split");
+    g_tuning[kTuneVoxelSort] = env("AOPT_VOXEL_SORT", "radix", "wide");
+}
+
+int tuning(int which) {
+    tuning_init();
+    return (which >= 0 && which < kTuneCount) ? g_tuning[which].load(std::memory_order_relaxed) : 0;
+}
+
 }  // namespace aopt
+
+extern "C" int aopt_set_tuning(const char *name, int value) {
+    aopt::tuning_init();
+    if (!name) return AOPT_ERR_INVALID_ARGUMENT;
+    for (int i = 0; i < aopt::kTuneCount; ++i) {
+        if (aopt::kTuneNames[i] && strcmp(aopt::kTuneNames[i], name) == 0) {
+            aopt::g_tuning[i].store(value, std::memory_order_relaxed);
+            return AOPT_OK;
+        }
+    }
+    return AOPT_ERR_INVALID_ARGUMENT;
+}
 
 extern "C" unsigned long long aopt_kernel_launches(void) {
     return aopt::g_kernel_launches.load(std::memory_order_relaxed);

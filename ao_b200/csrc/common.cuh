@@ -16,6 +16,14 @@ constexpr int kNumSM = 148;  // B200: 2 dies x 74 SMs; grids are sized in multip
 // kernels the entry point just enqueued (summed into aopt_kernel_launches()).
 int check_launch(int kernels = 1);
 
+// Tuning switches (A/B measurements and tests): initialised from the environment variable of the same meaning on
+// first use, changeable at run time through aopt_set_tuning (api.cu).  0 always means "library default".
+enum Tuning { kTuneCsrImpl = 0,   // AOPT_CSR_IMPL:   1 = radix sort, 2 = count / fill / rank
+              kTuneGvaBwd = 1,    // AOPT_GVA_BWD:    1 = fused kernel, 2 = two kernels
+              kTuneVoxelSort = 2, // AOPT_VOXEL_SORT: 1 = own radix sort (3 passes), 2 = wide keys (6 passes)
+              kTuneCount = 8 };
+int tuning(int which);
+
 inline cudaStream_t as_stream(aopt_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
 inline int div_up(long long a, long long b) { return (int)((a + b - 1) / b); }

@@ -16,12 +16,46 @@
 //   4. rank every entry inside its row by the value of p (all-pairs count inside the row, rows are
 //      ~k long) and write perm[rowptr[j] + rank] = p   → ascending p, deterministic.
 // Workspace: count (n_src+1 ints) + tmp and slot (n_entries ints each) + scan partials.
+//
+// Large graphs take a different route to the same arrays (build_sorted below): a stable radix sort of the flat
+// positions by source index (radix.cuh).  Stability IS the ascending-p order inside a row, there are no atomics, and a
+// hub row costs what any other entries cost (the rank of step 4 is quadratic in the in-degree).
+#include <stdlib.h>
+
 #include "common.cuh"
+#include "radix.cuh"
 #include "scan.cuh"
 
 namespace aopt {
 
 constexpr int kBlock = 256;
+
+// Sort key of entry p: its source row, or n_src for entries that reference nothing (-1 padding, out of range):
+// those sort to the end and rowptr[n_src] = number of kept entries.
+struct IdxKeys {
+    const int *idx;
+    int n_src, negative_mode;
+    __device__ __forceinline__ unsigned operator()(int p) const {
+        int j = __ldg(idx + p);
+        if (j < 0 && negative_mode == 1) j += n_src;
+        return (j >= 0 && j < n_src) ? (unsigned)j : (unsigned)n_src;
+    }
+};
+
+// rowptr[j] = first sorted position whose key is >= j (j = 0..n_src): a binary search per row, so empty rows —
+// however many in a run — cost nothing extra.
+__global__ void __launch_bounds__(kBlock)
+csr_rowptr_kernel(int n_src, int n_entries, const unsigned *__restrict__ sorted_keys, int *__restrict__ rowptr) {
+    const int j = blockIdx.x * kBlock + threadIdx.x;
+    if (j > n_src) return;
+    int lo = 0, hi = n_entries;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(sorted_keys + mid) < (unsigned)j) lo = mid + 1;
+        else hi = mid;
+    }
+    rowptr[j] = lo;
+}
 
 __device__ __forceinline__ int wrap_index(int j, int n_src, int negative_mode) {
     return (j < 0 && negative_mode == 1) ? j + n_src : j;
@@ -71,10 +105,53 @@ using namespace aopt;
 
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
-extern "C" size_t aopt_csr_workspace_bytes(int n_src, int64_t n_entries) {
-    if (n_src < 0 || n_entries < 0) return 0;
+// AOPT_CSR_IMPL=sort / count forces one builder; default: the sort for graphs of >= kSortMinEntries entries (below
+// that both are launch-latency bound and the counting build has fewer launches).
+constexpr long long kSortMinEntries = 1 << 18;
+static int csr_impl() { return tuning(kTuneCsrImpl); }
+static bool use_sort(long long n_entries) {
+    const int m = csr_impl();
+    return m == 1 || (m == 0 && n_entries >= kSortMinEntries);
+}
+
+static size_t count_workspace(int n_src, int64_t n_entries) {
     return align256(((size_t)n_src + 1) * 4) + 2 * align256((size_t)n_entries * 4) +
            align256(scan_partial_ints(n_src) * 4);
+}
+static size_t sort_workspace(int64_t n_entries) {   // two key buffers, two value buffers, the pass scratch
+    return 4 * align256((size_t)n_entries * 4) + align256(radix_scratch_ints(n_entries) * 4 + 16);
+}
+
+extern "C" size_t aopt_csr_workspace_bytes(int n_src, int64_t n_entries) {
+    if (n_src < 0 || n_entries < 0) return 0;
+    const size_t a = count_workspace(n_src, n_entries), b = sort_workspace(n_entries);
+    return a > b ? a : b;
+}
+
+// Stable radix sort of the entries by source row; 1-3 passes of 11 bits cover n_src (the padding key).
+static int build_sorted(int n_src, int n_entries, const int *idx, int negative_mode, int *rowptr, int *perm,
+                        char *ws, cudaStream_t st) {
+    unsigned *k0 = reinterpret_cast<unsigned *>(ws); ws += align256((size_t)n_entries * 4);
+    unsigned *k1 = reinterpret_cast<unsigned *>(ws); ws += align256((size_t)n_entries * 4);
+    int *v0 = reinterpret_cast<int *>(ws); ws += align256((size_t)n_entries * 4);
+    int *v1 = reinterpret_cast<int *>(ws); ws += align256((size_t)n_entries * 4);
+    int *scratch = reinterpret_cast<int *>(ws);
+    int bits = 1;
+    while (bits < 32 && (((unsigned)n_src) >> bits) != 0) ++bits;
+    const int npass = (bits + kRadixBits - 1) / kRadixBits;
+    const IdxKeys first{idx, n_src, negative_mode};
+    unsigned *kin = nullptr, *kbuf[2] = {k0, k1};
+    int *vin = nullptr, *vbuf[2] = {v0, v1};
+    for (int pass = 0; pass < npass; ++pass) {
+        const bool last = pass == npass - 1;
+        unsigned *kout = kbuf[pass & 1];
+        int *vout = last ? perm : vbuf[pass & 1];
+        if (pass == 0) launch_radix_pass<unsigned>(first, nullptr, kout, vout, n_entries, pass, nullptr, scratch, st);
+        else launch_radix_pass<unsigned>(PtrKeys<unsigned>{kin}, vin, kout, vout, n_entries, pass, nullptr, scratch, st);
+        kin = kout; vin = vout;
+    }
+    csr_rowptr_kernel<<<div_up((long long)n_src + 1, kBlock), kBlock, 0, st>>>(n_src, n_entries, kin, rowptr);
+    return check_launch(npass * kRadixLaunchesPerPass + 1);
 }
 
 extern "C" int aopt_csr_build(int n_src, int64_t n_entries, const int *idx, int negative_mode,
@@ -91,6 +168,8 @@ extern "C" int aopt_csr_build(int n_src, int64_t n_entries, const int *idx, int 
     if (n_entries > 0 && (!idx || !perm)) return AOPT_ERR_INVALID_ARGUMENT;
     if (!workspace || workspace_bytes < aopt_csr_workspace_bytes(n_src, n_entries)) return AOPT_ERR_WORKSPACE;
     char *ws = static_cast<char *>(workspace);
+    if (n_entries > 0 && use_sort(n_entries))
+        return build_sorted(n_src, (int)n_entries, idx, negative_mode, rowptr, perm, ws, st);
     int *count = reinterpret_cast<int *>(ws);
     ws += align256(((size_t)n_src + 1) * 4);
     int *tmp = reinterpret_cast<int *>(ws);

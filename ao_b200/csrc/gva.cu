@@ -921,7 +921,7 @@ extern "C" int aopt_gva_backward(int n, int nsample, int c, int g, const float *
     if (n == 0) return AOPT_OK;
     if (!grad_out || !value || !prob || !idx || !grad_logits || !rowptr || !perm || !grad_value)
         return AOPT_ERR_INVALID_ARGUMENT;
-    static const bool split = [] { const char *e = getenv("AOPT_GVA_BWD"); return e && e[0] == 's'; }();
+    const bool split = tuning(kTuneGvaBwd) == 2;
     const int I = c / g;
     const int gl = pick_gl(c, I, {grad_out, value, peb, grad_peb, grad_value});
     const bool ns = nsample == 8 || nsample == 16 || nsample == 32;

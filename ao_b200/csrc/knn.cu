@@ -191,6 +191,9 @@ static int grid_min_points() {
 }
 
 static int pick_method(int n, int m, int b, int nsample, int method) {
+    // nothing to search in (no scenes / no candidates): every output row is padding — the tile kernel writes it;
+    // the grid needs at least one scene and one point to build (an explicit GRID request is served the same way)
+    if (b <= 0 || n <= 0) return AOPT_KNN_TILE;
     if (method == AOPT_KNN_TILE || method == AOPT_KNN_GRID) return method;
     if (nsample > 32) return AOPT_KNN_TILE;
     long long avg = b > 0 ? (long long)n / b : n;

@@ -17,6 +17,7 @@
 #include "knn_common.cuh"  // find_segment
 #include "scan.cuh"
 #include "bbox.cuh"
+#include "radix.cuh"
 
 namespace aopt {
 
@@ -32,7 +33,10 @@ decode_min_kernel(int count, float *__restrict__ start) {
     start[i] = e == kBboxEmptyLo ? 0.f : bbox_decode(e);
 }
 
-constexpr int kCellBits = 18, kSceneBits = 10;
+// fixed layout of the stand-alone key (aopt_voxel_keys): 3 x 18 cell bits + 9 scene bits = 63: the key stays
+// non-negative, so a signed 64-bit sort keeps the scene as the most significant digit (a 10th scene bit would be the
+// sign bit).  aopt_voxel_grid below packs its own, compact layout and has no such limit.
+constexpr int kCellBits = 18, kSceneBits = 9;
 
 __global__ void __launch_bounds__(kPoolBlock)
 voxel_keys_kernel(int n, int b, const float *__restrict__ coord, const int *__restrict__ offset,
@@ -219,6 +223,121 @@ voxel_finalize_kernel(int n, int b, const int64_t *__restrict__ order64, const i
     }
 }
 
+// ---- voxel partition, all on the device: bbox -> compact keys -> own radix sort -> partition ------------------------
+// (…v2m2_base.py:246-268: offset2batch, segment_csr(min), voxel_grid, torch.unique, torch.sort in one entry point.)
+// The fixed 3 x 18 + 10 bit key above needs a 64-bit sort (eight library passes).  The cell extents of the batch are
+// known once the per-scene bounding boxes are: the key is packed into the FEWEST bits that hold (scene, z, y, x) —
+// 22 bits for four S3DIS rooms at 0.1 m, 25 for two KITTI scans at 0.15 m — and sorted by radix.cuh in
+// ceil(bits / 11) passes.  The widths live in a device word (meta[2] = passes needed); the host always enqueues
+// `max_passes` passes and the unneeded ones return at once, so there is no extra host synchronisation.
+// Order of the keys = (scene, z, y, x) ascending = the order torch.unique(sorted=True) gives grid_cluster's keys.
+// meta: [0] number of voxels, [1] flags (1: a cell index is negative or the key needs more than 64 bits,
+//       2: more passes needed than were enqueued), [2] passes needed, [3] key bits, [4..6] shifts of y, z, scene.
+constexpr int kMetaInts = 8;
+
+__global__ void __launch_bounds__(128)
+voxel_layout_kernel(int b, const unsigned *__restrict__ lo, const unsigned *__restrict__ hi,
+                    const float *__restrict__ start_in, float grid_size, int max_passes,
+                    float *__restrict__ start, int *__restrict__ meta) {
+    __shared__ long long cell_max[3];
+    if (threadIdx.x < 3) cell_max[threadIdx.x] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < 3 * b; i += 128) {
+        const unsigned elo = lo[i], ehi = hi[i];
+        // an empty scene has no minimum: 0, like segment_csr's fill value
+        const float st = start_in ? start_in[i] : (elo == kBboxEmptyLo ? 0.f : bbox_decode(elo));
+        start[i] = st;
+        if (ehi != kBboxEmptyHi || elo != kBboxEmptyLo) {
+            // fsub / fdiv are monotone in the coordinate, so the scene's largest coordinate has its largest cell
+            const float q = __fdiv_rn(__fsub_rn(bbox_decode(ehi), st), grid_size);
+            long long cq = (long long)q;
+            if (!(q < 9.0e18f)) cq = 0x7fffffffffffffffLL;
+            if (cq > 0) atomicMax(reinterpret_cast<unsigned long long *>(&cell_max[i % 3]), (unsigned long long)cq);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        auto bits_of = [](unsigned long long v) { int n = 0; while (v) { ++n; v >>= 1; } return n; };
+        const int bx = bits_of((unsigned long long)cell_max[0]), by = bits_of((unsigned long long)cell_max[1]),
+                  bz = bits_of((unsigned long long)cell_max[2]), bs = bits_of((unsigned long long)(b - 1));
+        const int total = bx + by + bz + bs;
+        int npass = (total + kRadixBits - 1) / kRadixBits;
+        if (npass < 1) npass = 1;
+        int flags = 0;
+        if (total > 64) flags |= 1;
+        if (npass > max_passes) flags |= 2;
+        meta[0] = 0; meta[1] = flags; meta[2] = npass; meta[3] = total;
+        meta[4] = bx; meta[5] = bx + by; meta[6] = bx + by + bz; meta[7] = 0;
+    }
+}
+
+__global__ void __launch_bounds__(kPoolBlock)
+voxel_ckeys_kernel(int n, int b, const float *__restrict__ coord, const int *__restrict__ offset,
+                   const float *__restrict__ start, float grid_size, unsigned long long *__restrict__ keys,
+                   int *__restrict__ meta) {
+    const int i = blockIdx.x * kPoolBlock + threadIdx.x;
+    if (i >= n) return;
+    int sc = find_segment(i, offset, b);
+    if (sc >= b) sc = b - 1;
+    const int sy = meta[4], sz = meta[5], ss = meta[6];
+    unsigned long long cell[3];
+    bool bad = false;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        // fp32 subtract then IEEE fp32 divide then truncate — the arithmetic of
+        // (coord - start[batch]) / size -> .long() in torch_cluster.grid_cluster
+        const float rel = __fsub_rn(__ldg(coord + (size_t)i * 3 + a), __ldg(start + sc * 3 + a));
+        const long long cq = (long long)__fdiv_rn(rel, grid_size);
+        if (cq < 0) bad = true;   // only with a caller-provided start above the scene minimum
+        cell[a] = cq < 0 ? 0ull : (unsigned long long)cq;
+    }
+    // a cell beyond the widths (possible only next to a `bad` one) must not spill into the next field
+    const unsigned long long mx = sy >= 64 ? ~0ull : ((1ull << sy) - 1), my = (sz - sy) >= 64 ? ~0ull : ((1ull << (sz - sy)) - 1),
+                             mz = (ss - sz) >= 64 ? ~0ull : ((1ull << (ss - sz)) - 1);
+    if (cell[0] > mx || cell[1] > my || cell[2] > mz) bad = true;
+    keys[i] = (ss < 64 ? ((unsigned long long)sc << ss) : 0ull) | (sz < 64 ? ((cell[2] & mz) << sz) : 0ull) |
+              (sy < 64 ? ((cell[1] & my) << sy) : 0ull) | (cell[0] & mx);
+    if (bad) atomicOr(meta + 1, 1);
+}
+
+// result of the sort: buffer P after an odd number of passes, Q after an even number
+__global__ void __launch_bounds__(kPoolBlock)
+voxel_mark2_kernel(int n, const unsigned long long *__restrict__ kp, const unsigned long long *__restrict__ kq,
+                   const int *__restrict__ meta, int *__restrict__ flag) {
+    const int i = blockIdx.x * kPoolBlock + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long *sorted_keys = (meta[2] & 1) ? kp : kq;
+    flag[i] = (i == 0 || sorted_keys[i] != sorted_keys[i - 1]) ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(kPoolBlock)
+voxel_finalize2_kernel(int n, int b, const int *__restrict__ vp, const int *__restrict__ vq,
+                       const int *__restrict__ flag, const int *__restrict__ scan, const int *__restrict__ offset,
+                       int *__restrict__ order32, int *__restrict__ cluster32, int64_t *__restrict__ cluster64,
+                       int *__restrict__ idx_ptr, int64_t *__restrict__ new_offset, int *__restrict__ meta) {
+    const int i = blockIdx.x * kPoolBlock + threadIdx.x;
+    const int n_vox = __ldg(scan + n);
+    const int *order = (meta[2] & 1) ? vp : vq;
+    if (i < n) {
+        const int f = __ldg(flag + i);
+        const int vid = __ldg(scan + i) + f - 1;
+        const int pt = order[i];
+        order32[i] = pt;
+        cluster32[pt] = vid;
+        cluster64[pt] = vid;
+        if (f) idx_ptr[vid] = i;
+    }
+    if (i == 0) {
+        idx_ptr[n_vox] = n;
+        meta[0] = n_vox;
+    }
+    // scene ranges are identical before and after the sort (the scene id is the most significant key field)
+    if (i < b) {
+        int e = min(max(__ldg(offset + i), 0), n);
+        new_offset[i] = e > 0 ? (int64_t)(__ldg(scan + e - 1) + __ldg(flag + e - 1)) : 0;
+    }
+}
+
 __global__ void __launch_bounds__(256)
 offset2batch_kernel(int n, int b, const int *__restrict__ offset, int64_t *__restrict__ batch) {
     const int i = blockIdx.x * 256 + threadIdx.x;
@@ -283,6 +402,58 @@ extern "C" int aopt_voxel_partition(int n, int b, const int64_t *sorted_keys, co
     voxel_finalize_kernel<<<grid, kPoolBlock, 0, st>>>(n, b, order64, flag, scan, offset, order32, cluster32, cluster64,
                                                        idx_ptr, new_offset, meta);
     return check_launch(3);  // mark, scan, finalize
+}
+
+static size_t a256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+extern "C" size_t aopt_voxel_grid_workspace_bytes(int n, int b) {
+    if (n < 0 || b < 0) return 0;
+    return 3 * a256(12 * (size_t)b) + 3 * a256(8 * (size_t)n) + 2 * a256(4 * (size_t)n) + 2 * a256(4 * ((size_t)n + 1)) +
+           a256(4 * radix_scratch_ints(n) + 16) + a256(4 * scan_partial_ints(n));
+}
+
+extern "C" int aopt_voxel_grid(int n, int b, const float *coord, const int *offset, const float *start,
+                               float grid_size, int max_passes, int *order32, int *cluster32, int64_t *cluster64,
+                               int *idx_ptr, int64_t *new_offset, int *meta, void *workspace,
+                               size_t workspace_bytes, aopt_stream_t stream) {
+    if (n < 1 || b < 1 || !(grid_size > 0.f) || max_passes < 1 || max_passes > 6) return AOPT_ERR_INVALID_ARGUMENT;
+    if (!coord || !offset || !order32 || !cluster32 || !cluster64 || !idx_ptr || !new_offset || !meta)
+        return AOPT_ERR_INVALID_ARGUMENT;
+    if (!workspace || workspace_bytes < aopt_voxel_grid_workspace_bytes(n, b)) return AOPT_ERR_WORKSPACE;
+    cudaStream_t st = as_stream(stream);
+    char *ws = static_cast<char *>(workspace);
+    unsigned *lo = reinterpret_cast<unsigned *>(ws); ws += a256(12 * (size_t)b);
+    unsigned *hi = reinterpret_cast<unsigned *>(ws); ws += a256(12 * (size_t)b);
+    float *start_f = reinterpret_cast<float *>(ws); ws += a256(12 * (size_t)b);
+    unsigned long long *k0 = reinterpret_cast<unsigned long long *>(ws); ws += a256(8 * (size_t)n);
+    unsigned long long *kp = reinterpret_cast<unsigned long long *>(ws); ws += a256(8 * (size_t)n);
+    unsigned long long *kq = reinterpret_cast<unsigned long long *>(ws); ws += a256(8 * (size_t)n);
+    int *vp = reinterpret_cast<int *>(ws); ws += a256(4 * (size_t)n);
+    int *vq = reinterpret_cast<int *>(ws); ws += a256(4 * (size_t)n);
+    int *flag = reinterpret_cast<int *>(ws); ws += a256(4 * ((size_t)n + 1));
+    int *scan = reinterpret_cast<int *>(ws); ws += a256(4 * ((size_t)n + 1));
+    int *scratch = reinterpret_cast<int *>(ws); ws += a256(4 * radix_scratch_ints(n) + 16);
+    int *partial = reinterpret_cast<int *>(ws);
+
+    launch_scene_bbox(n, b, coord, offset, lo, hi, st);
+    voxel_layout_kernel<<<1, 128, 0, st>>>(b, lo, hi, start, grid_size, max_passes, start_f, meta);
+    voxel_ckeys_kernel<<<div_up(n, kPoolBlock), kPoolBlock, 0, st>>>(n, b, coord, offset, start_f, grid_size, k0, meta);
+    const int *npass_dev = meta + 2;
+    for (int pass = 0; pass < max_passes; ++pass) {
+        unsigned long long *kout = (pass & 1) ? kq : kp;
+        int *vout = (pass & 1) ? vq : vp;
+        if (pass == 0)
+            launch_radix_pass<unsigned long long>(PtrKeys<unsigned long long>{k0}, nullptr, kout, vout, n, pass, npass_dev, scratch, st);
+        else
+            launch_radix_pass<unsigned long long>(PtrKeys<unsigned long long>{(pass & 1) ? kp : kq}, (pass & 1) ? vp : vq, kout, vout,
+                                                  n, pass, npass_dev, scratch, st);
+    }
+    const int grid = div_up(n > b ? n : b, kPoolBlock);
+    voxel_mark2_kernel<<<div_up(n, kPoolBlock), kPoolBlock, 0, st>>>(n, kp, kq, meta, flag);
+    launch_exclusive_scan(flag, scan, n, partial, st);
+    voxel_finalize2_kernel<<<grid, kPoolBlock, 0, st>>>(n, b, vp, vq, flag, scan, offset, order32, cluster32, cluster64,
+                                                        idx_ptr, new_offset, meta);
+    return check_launch(6 + max_passes * kRadixLaunchesPerPass);
 }
 
 extern "C" int aopt_pool_forward(int n_vox, int c, const float *feat, const float *coord, const int *order,

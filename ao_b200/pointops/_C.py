@@ -48,6 +48,10 @@ def knn_query_cuda(m, nsample, xyz, new_xyz, offset, new_offset, idx, dist2):
     _f(xyz, "xyz"), _f(new_xyz, "new_xyz"), _i(offset, "offset"), _i(new_offset, "new_offset")
     _i(idx, "idx"), _f(dist2, "dist2")
     n, b = xyz.shape[0], offset.numel()
+    # the library writes idx through its raw pointer, which does not bump the tensor's version counter: a transposed
+    # graph cached on a re-used idx buffer (pointops._csr) would be stale
+    if getattr(idx, "_aopt_csr", None):
+        idx._aopt_csr.clear()
     if m == 0:
         return
     with _lib.on_device(xyz.device):

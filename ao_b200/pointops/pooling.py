@@ -4,9 +4,9 @@ unpooling gather.  Successors of the third-party op chain in
 (offset2batch loop + segment_csr(min) + voxel_grid + torch.unique + torch.sort + two permuted
 copies + segment_csr(mean) + segment_csr(max)) and :308-309 (`proj(feat)[cluster]`).
 
-Kernels: aopt_segment_min3, aopt_voxel_keys, aopt_voxel_partition, aopt_pool_forward/backward,
-aopt_grouping_forward/backward (map unpool).  The 64-bit key sort itself is torch.sort (library radix
-sort); everything after it is two kernels + a scan with ONE host synchronisation (the voxel count).
+Kernels: aopt_voxel_grid (per-scene bounding boxes, compact voxel keys, own stable radix sort, partition: all on
+the device, ONE host synchronisation — the voxel count), aopt_pool_forward/backward, aopt_grouping_forward/backward
+(map unpool).
 """
 from __future__ import annotations
 
@@ -18,7 +18,7 @@ from torch.autograd import Function
 from .. import _lib
 from ._csr import NeighbourCSR, get_csr
 
-_SCENE_SHIFT = 54  # 3 x 18 bits of cell coordinates below the scene id (pool.cu)
+_VOXEL_PASSES = 3   # 11-bit radix passes enqueued up front: covers 33 key bits (pool.cu aopt_voxel_grid)
 
 
 class VoxelPartition(NamedTuple):
@@ -42,38 +42,36 @@ def voxel_partition(coord, offset, grid_size, start=None) -> VoxelPartition:
         z32 = torch.zeros(0, dtype=torch.int32, device=dev)
         return VoxelPartition(z32, torch.zeros(1, dtype=torch.int32, device=dev), torch.zeros(0, dtype=torch.int64, device=dev),
                               z32, torch.zeros(b, dtype=torch.int64, device=dev), 0)
-    keys = torch.empty(n, dtype=torch.int64, device=dev)
-    meta = torch.zeros(2, dtype=torch.int32, device=dev)            # [n_vox, key-overflow flag]
-    with _lib.on_device(dev):
-        if start is None:
-            start = torch.empty((b, 3), dtype=torch.float32, device=dev)
-            _lib.check(lib.aopt_segment_min3(n, b, _lib.ptr(coord), _lib.ptr(off32), _lib.ptr(start), _lib.stream()),
-                       "segment_min3")
-        else:
-            start = start.float().contiguous()
-        _lib.check(
-            lib.aopt_voxel_keys(n, b, _lib.ptr(coord), _lib.ptr(off32), _lib.ptr(start), float(grid_size),
-                                _lib.ptr(keys), meta.data_ptr() + 4, _lib.stream()),
-            "voxel_keys",
-        )
-        # library radix sort of the 64-bit keys (stable → ascending point id inside a voxel); the
-        # partition itself (boundaries, voxel ids, idx_ptr, per-scene offsets) is one scan + two kernels
-        sorted_keys, order = torch.sort(keys, stable=True)
-        order32 = torch.empty(n, dtype=torch.int32, device=dev)
-        cluster32 = torch.empty(n, dtype=torch.int32, device=dev)
-        cluster = torch.empty(n, dtype=torch.int64, device=dev)
-        idx_ptr_full = torch.empty(n + 1, dtype=torch.int32, device=dev)
-        new_offset = torch.empty(b, dtype=torch.int64, device=dev)
-        ws = _lib.workspace(lib.aopt_voxel_partition_workspace_bytes(n), dev)
-        _lib.check(
-            lib.aopt_voxel_partition(n, b, _lib.ptr(sorted_keys), _lib.ptr(order), _lib.ptr(off32), _lib.ptr(order32),
-                                     _lib.ptr(cluster32), _lib.ptr(cluster), _lib.ptr(idx_ptr_full),
-                                     _lib.ptr(new_offset), _lib.ptr(meta), _lib.ptr(ws), ws.numel(), _lib.stream()),
-            "voxel_partition",
-        )
-    n_vox, bad = meta.tolist()                                       # the one host sync (torch.unique has one too)
-    if bad:
-        raise ValueError("voxel_partition: a voxel coordinate exceeds 2^18 cells per axis or 1024 scenes")
+    order32 = torch.empty(n, dtype=torch.int32, device=dev)
+    cluster32 = torch.empty(n, dtype=torch.int32, device=dev)
+    cluster = torch.empty(n, dtype=torch.int64, device=dev)
+    idx_ptr_full = torch.empty(n + 1, dtype=torch.int32, device=dev)
+    new_offset = torch.empty(b, dtype=torch.int64, device=dev)
+    meta = torch.empty(8, dtype=torch.int32, device=dev)            # [n_vox, flags, passes needed, key bits, shifts]
+    start32 = None if start is None else start.float().contiguous()
+    if start32 is not None and start32.numel() != 3 * b:
+        raise ValueError("voxel_partition: start must be (b, 3)")
+
+    def run(passes):
+        with _lib.on_device(dev):
+            ws = _lib.workspace(lib.aopt_voxel_grid_workspace_bytes(n, b), dev)
+            # bounding boxes -> compact (scene, z, y, x) keys -> own stable radix sort -> boundaries / voxel ids /
+            # idx_ptr / per-scene offsets: one entry point, no library sort, ONE host synchronisation (the voxel count)
+            _lib.check(
+                lib.aopt_voxel_grid(n, b, _lib.ptr(coord), _lib.ptr(off32), _lib.ptr(start32), float(grid_size), passes,
+                                    _lib.ptr(order32), _lib.ptr(cluster32), _lib.ptr(cluster), _lib.ptr(idx_ptr_full),
+                                    _lib.ptr(new_offset), _lib.ptr(meta), _lib.ptr(ws), ws.numel(), _lib.stream()),
+                "voxel_grid",
+            )
+        return meta.tolist()                                         # the one host sync (torch.unique has one too)
+
+    m = run(_VOXEL_PASSES)
+    if m[1] & 2 and not m[1] & 1:
+        m = run(6)          # key wider than 33 bits (> 8.6e9 cells x scenes): the six-pass sort covers 64 bits
+    n_vox, flags = m[0], m[1]
+    if flags & 1:
+        raise ValueError("voxel_partition: a point lies below its scene's `start`, or the voxel grid needs more than "
+                         "64 key bits (extent / grid_size too large)")
     idx_ptr = idx_ptr_full[: n_vox + 1]
     # the partition IS the CSR of `cluster` (rows = voxels, entries ascending) → free backward map
     cluster32._aopt_csr = {(n_vox, 0): NeighbourCSR(idx_ptr, order32, n_vox, 0, cluster32._version)}
@@ -174,7 +172,8 @@ def prepare_pyramid(coord, offset, grid_sizes, knn=None, interp_k=None):
             c._aopt_pyramid = cache
         # level 0 belongs to the caller: the entry is valid for this offset tensor only.  Coarser coordinates are
         # created here together with their offsets, so any cast of those offsets (same length) is accepted.
-        cache[(float(gs), int(c._version), int(o.numel()))] = (part, pooled, o.data_ptr() if li == 0 else None)
+        # (the entry keeps the offset tensor alive, so its data_ptr cannot be recycled by another tensor)
+        cache[(float(gs), int(c._version), int(o.numel()))] = (part, pooled, o if li == 0 else None)
         levels.append((pooled, part.offset))
     if knn is not None or interp_k is not None:
         offs32 = [levels[0][1].int()] + [o.int() for _, o in levels[1:]]
@@ -195,7 +194,10 @@ def _prepared(coord, offset, grid_size, start):
     if not cache:
         return None
     hit = cache.get((float(grid_size), int(coord._version), int(offset.numel())))
-    if hit is None or (hit[2] is not None and hit[2] != offset.data_ptr()):
+    if hit is None:
+        return None
+    if hit[2] is not None and hit[2] is not offset and (
+            hit[2].data_ptr() != offset.data_ptr() or hit[2].dtype != offset.dtype):
         return None
     return hit
 

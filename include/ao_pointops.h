@@ -67,6 +67,11 @@ const char *aopt_last_cuda_error(void);
 /* Cumulative number of kernels this library has enqueued in the process (all threads); bench.py
  * reports the difference over its timed region as "gpu_launches". */
 unsigned long long aopt_kernel_launches(void);
+/* Tuning switches for A/B measurements and tests (never needed for correctness; every setting gives the same
+ * results bit for bit): "csr_impl" 1 = radix sort / 2 = count-fill-rank, "gva_bwd" 1 = fused / 2 = two kernels,
+ * "voxel_sort" 1 = compact keys, 3 passes / 2 = wide keys, 6 passes; 0 = library default.  Initial values come
+ * from AOPT_CSR_IMPL / AOPT_GVA_BWD / AOPT_VOXEL_SORT. */
+int aopt_set_tuning(const char *name, int value);
 
 /* ---- offset-encoded batch layout ---------------------------------------------------------- */
 /* batch[i] = scene of point i (int64, like pointcept/models/utils.py:11-24). */
@@ -189,6 +194,18 @@ int aopt_voxel_partition(int n, int b, const int64_t *sorted_keys, const int64_t
                          const int *offset, int *order32, int *cluster32, int64_t *cluster64,
                          int *idx_ptr, int64_t *new_offset, int *meta, void *workspace,
                          size_t workspace_bytes, aopt_stream_t stream);
+/* The whole front half of GridPool (...v2m2_base.py:246-264) in one call, all on the device: per-scene
+ * bounding boxes, voxel keys packed into the fewest bits that hold (scene, z, y, x), a stable radix sort of
+ * the points by key (ceil(bits / 11) passes; `max_passes` in [1,6] are enqueued and the unneeded ones return
+ * at once), voxel boundaries, ids, idx_ptr and per-scene voxel offsets.  start (b,3) may be NULL = per-scene
+ * minimum (segment_csr(coord, ptr, "min")).  Outputs as aopt_voxel_partition.  meta (8 ints): [0] number of
+ * voxels, [1] flags (1: a point below `start` or a key wider than 64 bits; 2: more than max_passes passes
+ * needed - call again with 6), [2] passes needed, [3] key bits. */
+size_t aopt_voxel_grid_workspace_bytes(int n, int b);
+int aopt_voxel_grid(int n, int b, const float *coord, const int *offset, const float *start,
+                    float grid_size, int max_passes, int *order32, int *cluster32, int64_t *cluster64,
+                    int *idx_ptr, int64_t *new_offset, int *meta, void *workspace,
+                    size_t workspace_bytes, aopt_stream_t stream);
 /* Points sorted by voxel: order (n) = point ids, idx_ptr (n_vox+1).  out_feat/argmax (n_vox,c):
  * max over the voxel and the ORIGINAL id of the first maximal point; out_coord (n_vox,3) = mean
  * (sequential sum in `order`, divided by the count). */

@@ -36,6 +36,19 @@ def test_small_adversarial_batch_bit_exact(oracle, method, k):
     assert_knn_equal(idx, d2, hi, hd)
 
 
+@pytest.mark.parametrize("method", ["tile", "grid", "auto"])
+def test_no_candidates_gives_padding(method):
+    """Queries against an EMPTY candidate set (n = 0): every row is padding (idx -1, dist2 1e10), whichever method is
+    asked for — the grid has nothing to build and hands over to the scan kernel."""
+    from ao_b200 import pointops
+
+    q = torch.rand(3000, 3, device="cuda")
+    xyz = torch.zeros(0, 3, device="cuda")
+    off, qoff = (torch.tensor([v], dtype=torch.int32, device="cuda") for v in (0, 3000))
+    idx, d2 = pointops.knn_query_raw(4, xyz, off, q, qoff, method=method)
+    assert bool((idx == -1).all()) and bool((d2 == 1e10).all())
+
+
 @pytest.mark.parametrize("method", ["tile", "grid"])
 def test_bigk_and_many_scenes(oracle, method):
     rng = np.random.default_rng(1)

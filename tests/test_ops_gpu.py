@@ -30,12 +30,25 @@ def rand_idx(rng, m, k, n, pad_rows=5):
 
 
 # ------------------------------------------------------------------------------------------ CSR
-@pytest.mark.parametrize("n,m,k", [(1000, 1000, 16), (50, 4000, 3), (5000, 77, 1), (4097 * 3, 9000, 8)])
-def test_csr_build(n, m, k):
+@pytest.fixture(params=["sort", "count"])
+def csr_impl(request):
+    """Both CSR builders (csrc/csr.cu): stable radix sort of the entries, and count / fill / rank."""
+    from ao_b200 import _lib
+
+    _lib.set_tuning("csr_impl", 1 if request.param == "sort" else 2)
+    yield request.param
+    _lib.set_tuning("csr_impl", 0)
+
+
+@pytest.mark.parametrize("n,m,k", [(1000, 1000, 16), (50, 4000, 3), (5000, 77, 1), (4097 * 3, 9000, 8), (2047, 2049, 2),
+                                   (2048, 1, 1), (70000, 40000, 16), (5_000_000, 3000, 4)])
+def test_csr_build(n, m, k, csr_impl):
+    """n = 2047 / 2048: one and two 11-bit digits; 70000 x 16 entries: several tiles per CTA of the sort;
+    n = 5M: three digits."""
     from ao_b200 import pointops
 
     rng = np.random.default_rng(n + k)
-    idx = rand_idx(rng, m, k, n)
+    idx = rand_idx(rng, m, k, n, pad_rows=min(5, m))
     (d_idx,) = to_cuda(idx)
     for mode in (0, 1):
         csr = pointops.build_csr(d_idx, n, mode)
@@ -51,7 +64,7 @@ def test_csr_build(n, m, k):
         assert np.array_equal(perm[: rowptr[-1]], expect_perm)      # ascending positions inside each row
 
 
-def test_csr_hub_row():
+def test_csr_hub_row(csr_impl):
     """All queries reference the same source: one row holds every entry (rank kernel worst case)."""
     from ao_b200 import pointops
 
@@ -207,6 +220,88 @@ def test_grid_pool_vs_restatement(oracle, c):
     assert torch.equal(gf.cpu(), expect)
     # the reference path through its own ops: segment_csr(feat[sorted], idx_ptr) == direct reduction
     assert part.n_vox == rc.shape[0]
+
+
+def test_grid_pool_hand_computed_fixture():
+    """Known-answer test written out by hand (tests/golden/gridpool_hand.json; …v2m2_base.py:249-268): points exactly on
+    cell faces, negative coordinates, single-point voxels, duplicated points, two scenes — and the same batch with an
+    EMPTY scene in the middle."""
+    import json
+
+    from ao_b200 import pointops
+
+    fx = json.load(open(os.path.join(GOLD, "gridpool_hand.json")))
+    coord = torch.tensor(fx["coord"], dtype=torch.float32).cuda()
+    feat = torch.tensor(fx["feat"], dtype=torch.float32).cuda().requires_grad_(True)
+    counts = np.diff(np.array(fx["idx_ptr"]))
+    mean = (np.array(fx["coord_sum"], np.float32) / counts[:, None].astype(np.float32)).astype(np.float32)
+    for offset, new_offset in ((fx["offset"], fx["new_offset"]),
+                               (fx["with_empty_scene"]["offset"], fx["with_empty_scene"]["new_offset"])):
+        off = torch.tensor(offset, dtype=torch.int32).cuda()
+        (nc, nf, noff), cluster, part = pointops.grid_pool(coord, feat, off, fx["grid_size"], return_partition=True)
+        assert cluster.tolist() == fx["cluster"] and cluster.dtype == torch.int64
+        assert part.idx_ptr.tolist() == fx["idx_ptr"]
+        assert [sorted(part.order[a:b].tolist()) for a, b in zip(fx["idx_ptr"], fx["idx_ptr"][1:])] == fx["voxel_points"]
+        assert part.order.tolist() == [p for mem in fx["voxel_points"] for p in mem]    # stable: ascending id in a voxel
+        assert noff.tolist() == new_offset
+        assert np.array_equal(nc.cpu().numpy(), mean)
+        assert nf.tolist() == fx["feat_max"]
+        go = torch.arange(1, nf.numel() + 1, dtype=torch.float32, device="cuda").view_as(nf)
+        (gf,) = torch.autograd.grad(nf, feat, go)
+        expect = torch.zeros_like(gf)
+        for v, row in enumerate(fx["argmax"]):
+            for c, p in enumerate(row):
+                expect[p, c] = go[v, c]
+        assert torch.equal(gf, expect)
+
+
+@pytest.mark.parametrize("case", ["many_scenes", "wide_keys", "one_voxel"])
+def test_voxel_partition_key_layouts(oracle, case):
+    """The compact-key radix sort of aopt_voxel_grid: 700 scenes (10 scene bits; the old fixed layout stopped at
+    512), extents that need more than 33 key bits (second call with six passes), every point in one voxel."""
+    from ao_b200 import pointops
+
+    rng = np.random.default_rng(11)
+    if case == "many_scenes":
+        sizes = rng.integers(1, 9, 700)
+        coord = rng.uniform(-1, 1, (int(sizes.sum()), 3)).astype(np.float32)
+        grid = 0.25
+    elif case == "wide_keys":
+        sizes = np.array([1500, 900])
+        coord = rng.uniform(-4000, 4000, (2400, 3)).astype(np.float32)      # 8000 / 0.25 = 2^15 cells per axis: 46 bits
+        grid = 0.25
+    else:
+        sizes = np.array([300])
+        coord = rng.uniform(0, 0.01, (300, 3)).astype(np.float32)
+        grid = 1.0
+    offset = np.cumsum(sizes).astype(np.int32)
+    d_coord, d_off = to_cuda(coord, offset)
+    part = pointops.voxel_partition(d_coord, d_off, grid)
+    feat = torch.from_numpy(coord.copy())
+    rc, rf, roff, rcluster, rarg = oracle.grid_pool(torch.from_numpy(coord), feat, torch.from_numpy(offset), grid)
+    assert torch.equal(part.cluster.cpu(), rcluster)
+    assert torch.equal(part.offset.cpu(), roff)
+    assert part.n_vox == rc.shape[0]
+    order = part.order.cpu().numpy()
+    ptr = part.idx_ptr.cpu().numpy()
+    assert ptr[0] == 0 and ptr[-1] == coord.shape[0]
+    cl = rcluster.numpy()
+    assert np.array_equal(cl[order], np.repeat(np.arange(part.n_vox), np.diff(ptr)))
+    assert all(np.all(np.diff(order[a:b]) > 0) for a, b in zip(ptr[:-1], ptr[1:]))     # ascending id inside a voxel
+
+
+def test_voxel_partition_rejects_points_below_start():
+    from ao_b200 import pointops
+
+    coord = torch.rand(100, 3, device="cuda")
+    off = torch.tensor([100], dtype=torch.int32, device="cuda")
+    start = torch.full((1, 3), 0.5, device="cuda")
+    with pytest.raises(ValueError):
+        pointops.voxel_partition(coord, off, 0.1, start)
+    part = pointops.voxel_partition(coord, off, 0.1, torch.full((1, 3), -0.25, device="cuda"))   # start below the minimum
+    cells = torch.floor((coord + 0.25) / 0.1).long()
+    key = (cells[:, 2] * 100 + cells[:, 1]) * 100 + cells[:, 0]
+    assert torch.equal(part.cluster, torch.unique(key, return_inverse=True)[1])
 
 
 def test_unpool_map(oracle):

@@ -247,3 +247,24 @@ def test_fps_oracle_pinned_by_reference_cuda_outputs(oracle, case):
     g = np.load(path)
     xyz, off, noff = _load_fps_golden_module().inputs(case)
     assert np.array_equal(oracle.farthest_point_sampling(xyz, off, noff), g[case + "_idx"])
+
+
+def test_grid_pool_restatement_on_hand_computed_fixture(oracle):
+    """The GridPool restatement (third-party torch_scatter / torch_cluster semantics, un-vendored: the one operator
+    whose oracle cannot be pinned on reference outputs) against a known-answer fixture derived BY HAND from
+    …v2m2_base.py:249-268: points exactly on cell faces, negative coordinates, single-point voxels, duplicated
+    points, two scenes (tests/golden/gridpool_hand.json lists the derivation)."""
+    import json
+
+    fx = json.load(open(os.path.join(GOLD, "gridpool_hand.json")))
+    coord = torch.tensor(fx["coord"], dtype=torch.float32)
+    feat = torch.tensor(fx["feat"], dtype=torch.float32)
+    offset = torch.tensor(fx["offset"], dtype=torch.int32)
+    nc, nf, noff, cluster, arg = oracle.grid_pool(coord, feat, offset, fx["grid_size"])
+    assert cluster.tolist() == fx["cluster"]
+    assert noff.tolist() == fx["new_offset"]
+    counts = np.diff(np.array(fx["idx_ptr"]))
+    mean = (np.array(fx["coord_sum"], np.float32) / counts[:, None].astype(np.float32)).astype(np.float32)
+    assert np.array_equal(nc.numpy(), mean)            # the sums are exact in fp32, one IEEE division
+    assert nf.tolist() == fx["feat_max"]
+    assert arg.tolist() == fx["argmax"]

@@ -22,7 +22,7 @@ int check_launch(int kernels) {
 
 static std::atomic<int> g_tuning[kTuneCount];
 static std::atomic<bool> g_tuning_init{false};
-static const char *const kTuneNames[kTuneCount] = {"csr_impl", "gva_bwd", "voxel_sort", nullptr, nullptr, nullptr, nullptr, nullptr};
+static const char *const kTuneNames[kTuneCount] = {"csr_impl", "gva_bwd", "voxel_sort", "pe_fwd", nullptr, nullptr, nullptr, nullptr};
 
 static void tuning_init() {
     if (g_tuning_init.exchange(true)) return;
@@ -34,6 +34,7 @@ static void tuning_init() {
     g_tuning[kTuneCsrImpl] = env("AOPT_CSR_IMPL", "sort", "count");
     g_tuning[kTuneGvaBwd] = env("AOPT_GVA_BWD", "fused", "split");
     g_tuning[kTuneVoxelSort] = env("AOPT_VOXEL_SORT", "radix", "wide");
+    g_tuning[kTunePeFwd] = env("AOPT_PE_FWD", "tcgen05", "mma");
 }
 
 int tuning(int which) {

@@ -290,6 +290,182 @@ pe_mlp_forward_kernel(long long rows, const float *__restrict__ pos, const float
     if (threadIdx.x == 0) bulk_store_wait_all();  // shared memory must outlive the last copy
 }
 
+// ---- 3b. forward on the 5th-generation tensor cores (tcgen05.mma, accumulator in Tensor Memory) -----------
+// One CTA = 128 threads = one 128-row tile at a time (UMMA M = 128: accumulator row i lives in TMEM lane i).
+//   A = h tile (128 x C bf16), written by the threads themselves: thread r recomputes the hidden activations of row
+//       r from pos (three FMAs + ReLU per element) and stores them as 16-byte pieces in the canonical K-major,
+//       no-swizzle operand layout  byte(row, k) = (k/8)·2048 + row·16 + (k%8)·2  (8x8 "core matrices": SBO = 128 B
+//       between 8-row groups, LBO = 2048 B between the two 8-wide K halves of one K=16 step).  Consecutive threads
+//       write consecutive 16-byte words: conflict-free, and no ldmatrix / LSU traffic to feed the MMA afterwards —
+//       the mma.sync kernel above spent its time in exactly that (shared-memory pipe bound).
+//   B = [W2 ; W_aux] (NPAD x C bf16, K-major, same layout with LBO = NPAD·16), resident in shared memory.
+//   D = 128 x NPAD fp32 in TMEM (NPAD columns), C/16 MMAs of K = 16 issued by ONE thread, completion through
+//       tcgen05.commit -> mbarrier.  Epilogue: every warp reads its 32 lanes with tcgen05.ld.32x32b (thread = row),
+//       adds b2 and streams the row to HBM with 128-bit stores.
+// Phases of a tile are serial inside a CTA (produce A | MMA | epilogue); several CTAs per SM (TMEM columns and
+// shared memory allow 8 at C=48, 4 at C=96, 1-2 at C=192) overlap them.  The work is HBM-bound: 4·(C+ga)+12 B/row.
+__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    // cute::UMMA::SmemDescriptor: start address [0,14) >>4 | LBO [16,30) >>4 | SBO [32,46) >>4 | version = 1 at [46,48)
+    // | base offset 0 | layout type [61,64) = 0 (SWIZZLE_NONE)
+    return (uint64_t)((smem_addr >> 4) & 0x3fffu) | ((uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
+    // cute::UMMA::InstrDescriptor (kind::f16): D = f32 (bits [4,6) = 1), A = B = bf16 ([7,10) = [10,13) = 1), both
+    // K-major (bits 15, 16 = 0), N >> 3 at [17,23), M >> 4 at [24,29)
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+constexpr int kTcBlock = 128;   // threads = rows of a tile = TMEM lanes
+
+template <int C>
+struct PeTcLayout {
+    static constexpr int NPAD = C + 16;                         // [W2 ; 16 auxiliary rows]: a multiple of 16 (UMMA M=128)
+    static constexpr int TMEM_COLS = NPAD <= 64 ? 64 : NPAD <= 128 ? 128 : NPAD <= 256 ? 256 : 512;
+    static constexpr uint32_t A_LBO = kTcBlock * 16, B_LBO = NPAD * 16, SBO = 128;
+    static constexpr size_t a_bytes = (size_t)kTcBlock * C * 2, b_bytes = (size_t)NPAD * C * 2;
+    static constexpr size_t bytes = a_bytes + b_bytes + 16 * (size_t)C + 4 * (size_t)C + 64;
+    static constexpr int ctas_per_sm = (512 / TMEM_COLS) < (int)(232448 / (bytes + 1024)) ? (512 / TMEM_COLS) : (int)(232448 / (bytes + 1024));
+};
+
+template <int C>
+__global__ void __launch_bounds__(kTcBlock)
+pe_mlp_forward_tc_kernel(long long rows, const float *__restrict__ pos, const float *__restrict__ fold,
+                         const __nv_bfloat16 *__restrict__ w2_bf, const float *__restrict__ b2,
+                         float *__restrict__ out, const __nv_bfloat16 *__restrict__ wf_bf, int ga,
+                         float *__restrict__ aux_out) {
+    using L = PeTcLayout<C>;
+    constexpr int NPAD = L::NPAD;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned char *a_s = smem_raw;                                             // A: [C/8][128][8] bf16
+    unsigned char *b_s = a_s + L::a_bytes;                                     // B: [C/8][NPAD][8] bf16
+    float4 *fz = reinterpret_cast<float4 *>(b_s + L::b_bytes);                 // [C] folded z-map
+    float *b2s = reinterpret_cast<float *>(fz + C);                            // [C]
+    uint64_t *bar = reinterpret_cast<uint64_t *>(b2s + C);                     // MMA-complete barrier
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar + 1);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const bool aux = aux_out != nullptr;
+
+    // B operand: rows 0..C-1 = W2[co][:], rows C..C+15 = the auxiliary head (rows >= ga are zero), 16 bytes a piece
+    for (int i = tid; i < NPAD * (C / 8); i += kTcBlock) {
+        const int n = i % NPAD, k8 = i / NPAD;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (n < C) v = *reinterpret_cast<const uint4 *>(w2_bf + (size_t)n * C + k8 * 8);
+        else if (aux) v = *reinterpret_cast<const uint4 *>(wf_bf + (size_t)(n - C) * C + k8 * 8);
+        *reinterpret_cast<uint4 *>(b_s + (size_t)k8 * L::B_LBO + n * 16) = v;
+    }
+    for (int i = tid; i < C; i += kTcBlock) {
+        fz[i] = make_float4(fold[i * 8], fold[i * 8 + 1], fold[i * 8 + 2], fold[i * 8 + 3]);
+        b2s[i] = b2[i];
+    }
+    if (tid == 0) mbar_init(bar, 1);
+    if (warp == 0) {  // one warp allocates the accumulator columns and gives the permit back
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(L::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t a_addr = smem_u32(a_s), b_addr = smem_u32(b_s);
+    constexpr uint32_t idesc = umma_idesc_bf16(128, NPAD);
+    const uint32_t tmem_row = tmem_base + ((uint32_t)(warp * 32) << 16);      // this warp's 32 lanes
+
+    const long long n_tiles = (rows + kTcBlock - 1) / kTcBlock;
+    uint32_t phase = 0;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const long long gr = tile * kTcBlock + tid;
+        const bool live = gr < rows;
+        // ---- A: hidden activations of this thread's row, 8 channels (16 bytes) at a time ----
+        float px = 0.f, py = 0.f, pz = 0.f;
+        if (live) { px = __ldg(pos + gr * 3); py = __ldg(pos + gr * 3 + 1); pz = __ldg(pos + gr * 3 + 2); }
+#pragma unroll
+        for (int k8 = 0; k8 < C / 8; ++k8) {
+            uint32_t w[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float4 f0 = fz[k8 * 8 + 2 * q], f1 = fz[k8 * 8 + 2 * q + 1];
+                const float z0 = fmaf(f0.x, px, fmaf(f0.y, py, fmaf(f0.z, pz, f0.w)));
+                const float z1 = fmaf(f1.x, px, fmaf(f1.y, py, fmaf(f1.z, pz, f1.w)));
+                const __nv_bfloat162 h2 = __floats2bfloat162_rn(live ? fmaxf(z0, 0.f) : 0.f, live ? fmaxf(z1, 0.f) : 0.f);
+                w[q] = *reinterpret_cast<const uint32_t *>(&h2);
+            }
+            *reinterpret_cast<uint4 *>(a_s + (size_t)k8 * L::A_LBO + tid * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        fence_proxy_async();   // generic-proxy writes of A -> visible to the tensor core (async proxy)
+        tc_fence_before();     // orders this thread's tcgen05.ld of the previous tile before the barrier
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+#pragma unroll
+            for (int kk = 0; kk < C / 16; ++kk) {
+                const uint64_t da = umma_smem_desc(a_addr + kk * 2 * L::A_LBO, L::A_LBO, L::SBO);
+                const uint64_t db = umma_smem_desc(b_addr + kk * 2 * L::B_LBO, L::B_LBO, L::SBO);
+                umma_bf16(tmem_base, da, db, idesc, kk > 0 ? 1u : 0u);
+            }
+            umma_commit(bar);  // arrives when the MMAs above have completed (implies fence::before_thread_sync)
+        }
+        mbar_wait(bar, phase);
+        phase ^= 1u;
+        tc_fence_after();
+        // ---- epilogue: TMEM lane = row; 16 columns per load ----
+        float *orow = out + gr * C;
+#pragma unroll
+        for (int j = 0; j < C / 16; ++j) {
+            float v[16];
+            tmem_ld16(tmem_row + j * 16, v);
+            tmem_ld_wait();
+            if (live) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int col = j * 16 + q * 4;
+                    stg_stream4(orow + col, make_float4(v[q * 4] + b2s[col], v[q * 4 + 1] + b2s[col + 1],
+                                                        v[q * 4 + 2] + b2s[col + 2], v[q * 4 + 3] + b2s[col + 3]));
+                }
+            }
+        }
+        if (aux) {
+            float v[16];
+            tmem_ld16(tmem_row + C, v);
+            tmem_ld_wait();
+            if (live) {
+#pragma unroll
+                for (int q = 0; q < 16; ++q)
+                    if (q < ga) aux_out[gr * ga + q] = v[q];
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(L::TMEM_COLS) : "memory");
+}
+
 // ---- 4. backward -----------------------------------------------------------------------------------------
 // Per-CTA partial layout (floats): dW2 [C*C] | db2 [C] | S2 [C] | S3 [C] | S1 [3C]
 // TR = rows per tile: 128 at C=48 (74 KB of shared memory → 3 CTAs/SM), 64 at C=96 (86 KB → 2 CTAs/SM).
@@ -629,6 +805,14 @@ PeState carve_state(void *state, int c) {
 template <int C>
 void launch_fwd(long long rows, const float *pos, const PeState &s, const float *b2, float *out, int ga,
                 float *aux_out, cudaStream_t st) {
+    if (tuning(kTunePeFwd) != 2) {   // tcgen05 / TMEM kernel (default)
+        using L = PeTcLayout<C>;
+        static bool once = (cudaFuncSetAttribute(pe_mlp_forward_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::bytes), true);
+        (void)once;
+        pe_mlp_forward_tc_kernel<C><<<pe_grid(rows, kTcBlock, L::ctas_per_sm), kTcBlock, L::bytes, st>>>(
+            rows, pos, s.fold, s.w2, b2, out, s.wf, ga, aux_out);
+        return;
+    }
     const size_t smem = pe_fwd_smem<C>();
     static bool once = (cudaFuncSetAttribute(pe_mlp_forward_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), true);
     (void)once;

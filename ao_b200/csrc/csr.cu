@@ -17,7 +17,7 @@
 //      ~k long) and write perm[rowptr[j] + rank] = p   → ascending p, deterministic.
 // Workspace: count (n_src+1 ints) + tmp and slot (n_entries ints each) + scan partials.
 //
-// Large graphs take a different route to the same arrays (build_sorted below): a stable radix sort of the flat
+// Hub-heavy graphs take a different route to the same arrays (build_sorted below): a stable radix sort of the flat
 // positions by source index (radix.cuh).  Stability IS the ascending-p order inside a row, there are no atomics, and a
 // hub row costs what any other entries cost (the rank of step 4 is quadratic in the in-degree).
 #include <stdlib.h>
@@ -105,13 +105,15 @@ using namespace aopt;
 
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
-// AOPT_CSR_IMPL=sort / count forces one builder; default: the sort for graphs of >= kSortMinEntries entries (below
-// that both are launch-latency bound and the counting build has fewer launches).
-constexpr long long kSortMinEntries = 1 << 18;
-static int csr_impl() { return tuning(kTuneCsrImpl); }
-static bool use_sort(long long n_entries) {
-    const int m = csr_impl();
-    return m == 1 || (m == 0 && n_entries >= kSortMinEntries);
+// Which builder (tuning "csr_impl" / AOPT_CSR_IMPL: 1 = sort, 2 = count).  Measured on a B200 (profiles/r02a_kernel_bench.txt,
+// kNN graphs, in-degree ~16): count / fill / rank 184 us vs 283 us for the two-pass sort at 5.1 M entries, 54 vs 113 us at
+// 0.8 M — with rows this short the all-pairs rank is cheap and the sort pays two full passes over the entries.  The rank
+// is quadratic in the row length, though, so graphs whose AVERAGE in-degree is large (a coarse level interpolated to a
+// fine one, a generic `cluster` map) take the sort, whose cost does not depend on the degree distribution.
+constexpr long long kSortMinAvgDegree = 64;
+static bool use_sort(int n_src, long long n_entries) {
+    const int m = tuning(kTuneCsrImpl);
+    return m == 1 || (m == 0 && n_entries >= kSortMinAvgDegree * (long long)(n_src > 0 ? n_src : 1) && n_entries >= 4096);
 }
 
 static size_t count_workspace(int n_src, int64_t n_entries) {
@@ -168,7 +170,7 @@ extern "C" int aopt_csr_build(int n_src, int64_t n_entries, const int *idx, int 
     if (n_entries > 0 && (!idx || !perm)) return AOPT_ERR_INVALID_ARGUMENT;
     if (!workspace || workspace_bytes < aopt_csr_workspace_bytes(n_src, n_entries)) return AOPT_ERR_WORKSPACE;
     char *ws = static_cast<char *>(workspace);
-    if (n_entries > 0 && use_sort(n_entries))
+    if (n_entries > 0 && use_sort(n_src, n_entries))
         return build_sorted(n_src, (int)n_entries, idx, negative_mode, rowptr, perm, ws, st);
     int *count = reinterpret_cast<int *>(ws);
     ws += align256(((size_t)n_src + 1) * 4);

@@ -126,6 +126,10 @@ gva_forward_kernel(long long n, int k, int c, int g, const float *__restrict__ v
 //   * the logits column is loaded and the softmax computed while those copies are in flight.
 // One latency window per item instead of nine; 2·NS·16 bytes of shared memory per thread.
 constexpr int kGvaNsBlock = 128;
+// threads per CTA of the NS kernels: 2·NS 16-byte slots per thread — 128 threads at NS <= 16 (64 KB at NS = 16: three
+// CTAs per SM); 64 threads at NS = 32, where 128 would need 128 KB and leave ONE CTA (4 warps) per SM: the k = 32
+// schedule ran these kernels at 49-57 % of the HBM peak (profiles/r02a, scannet150k k32 variant).
+template <int NS> __host__ __device__ constexpr int ns_block() { return NS >= 32 ? 64 : kGvaNsBlock; }
 
 // Gathered value rows.  Measured at level 0 on one box (A/B in the same process): forward 232 us with L2-only
 // copies (.cg) vs 244 us with L1-allocating ones (.ca); backward_query 399 us (.cg) vs 368 us (.ca).  Defaults
@@ -149,17 +153,18 @@ __device__ __forceinline__ void load_idx_row16(const int *__restrict__ row, int 
 }
 
 template <int GL, int NS, bool HAS_PEB>
-__global__ void __launch_bounds__(kGvaNsBlock)
+__global__ void __launch_bounds__(ns_block<NS>())
 gva_forward_ns_kernel(long long n, int c, int g, const float *__restrict__ value,
                       const float *__restrict__ peb, const float *__restrict__ logits,
                       const int *__restrict__ idx, float *__restrict__ out, float *__restrict__ prob) {
-    extern __shared__ float4 stage[];  // [2*NS][kGvaNsBlock]: value pieces, then peb pieces
+    constexpr int BLK = ns_block<NS>();
+    extern __shared__ float4 stage[];  // [2*NS][BLK]: value pieces, then peb pieces
     float4 *sv = stage + threadIdx.x;
-    float4 *sq = stage + NS * kGvaNsBlock + threadIdx.x;
+    float4 *sq = stage + NS * BLK + threadIdx.x;
     const int chunks = c >> 2;
     const long long total = n * chunks;
-    const long long step = (long long)gridDim.x * kGvaNsBlock;
-    long long t = (long long)blockIdx.x * kGvaNsBlock + threadIdx.x;
+    const long long step = (long long)gridDim.x * BLK;
+    long long t = (long long)blockIdx.x * BLK + threadIdx.x;
     int jn[NS];
     if (t < total) load_idx_row16(idx + (size_t)(t / chunks) * NS, jn, NS / 4);
     for (; t < total; t += step) {
@@ -172,11 +177,11 @@ gva_forward_ns_kernel(long long n, int c, int g, const float *__restrict__ value
         for (int s = 0; s < NS; ++s) j[s] = jn[s];
         const float *vbase = value + ch * 4;
 #pragma unroll
-        for (int s = 0; s < NS; ++s) cp_async16_row<1>(sv + s * kGvaNsBlock, vbase + (size_t)max(j[s], 0) * c);
+        for (int s = 0; s < NS; ++s) cp_async16_row<1>(sv + s * BLK, vbase + (size_t)max(j[s], 0) * c);
         if (HAS_PEB) {
             const float *pe = peb + (size_t)pt * NS * c + ch * 4;
 #pragma unroll
-            for (int s = 0; s < NS; ++s) cp_async16_stream(sq + s * kGvaNsBlock, pe + (size_t)s * c);
+            for (int s = 0; s < NS; ++s) cp_async16_stream(sq + s * BLK, pe + (size_t)s * c);
         }
         cp_async_commit();
         const float *lg = logits + (size_t)pt * NS * g + gi;
@@ -203,8 +208,8 @@ gva_forward_ns_kernel(long long n, int c, int g, const float *__restrict__ value
         float4 acc = f4_zero();
 #pragma unroll
         for (int s = 0; s < NS; ++s) {
-            const float4 v = sv[s * kGvaNsBlock];
-            const float4 q = HAS_PEB ? sq[s * kGvaNsBlock] : f4_zero();
+            const float4 v = sv[s * BLK];
+            const float4 q = HAS_PEB ? sq[s * BLK] : f4_zero();
             fma_keep(acc, f4_add(v, q), e[s], j[s] >= 0);  // sign(idx+1) mask
         }
         *reinterpret_cast<float4 *>(out + (size_t)pt * c + ch * 4) = acc;
@@ -290,19 +295,20 @@ gva_backward_query_kernel(long long n, int k, int c, int g, const float *__restr
 // all peb / value pieces requested at once with cp.async into per-thread slots); the probability
 // column is loaded while the copies fly and gw stays in registers (no parking in grad_logits).
 template <int GL, int NS, bool HAS_PEB>
-__global__ void __launch_bounds__(kGvaNsBlock)
+__global__ void __launch_bounds__(ns_block<NS>())
 gva_backward_query_ns_kernel(long long n, int c, int g, const float *__restrict__ grad_out,
                              const float *__restrict__ value, const float *__restrict__ peb,
                              const float *__restrict__ prob, const int *__restrict__ idx,
                              float *__restrict__ grad_peb, float *__restrict__ grad_logits) {
+    constexpr int BLK = ns_block<NS>();
     extern __shared__ float4 stage[];
     float4 *sv = stage + threadIdx.x;
-    float4 *sq = stage + NS * kGvaNsBlock + threadIdx.x;
+    float4 *sq = stage + NS * BLK + threadIdx.x;
     const int chunks = c >> 2;
     const long long total = n * chunks;
-    const long long step = (long long)gridDim.x * kGvaNsBlock;
+    const long long step = (long long)gridDim.x * BLK;
     // warp-uniform trip count (see gva_backward_query_kernel)
-    long long base = (long long)blockIdx.x * kGvaNsBlock + (threadIdx.x & ~31);
+    long long base = (long long)blockIdx.x * BLK + (threadIdx.x & ~31);
     const int lane = threadIdx.x & 31;
     int jn[NS];
     if (base < total) load_idx_row16(idx + (size_t)(min(base + lane, total - 1) / chunks) * NS, jn, NS / 4);
@@ -319,11 +325,11 @@ gva_backward_query_ns_kernel(long long n, int c, int g, const float *__restrict_
         for (int s = 0; s < NS; ++s) j[s] = jn[s];
         const float *vbase = value + ch * 4;
 #pragma unroll
-        for (int s = 0; s < NS; ++s) cp_async16_row<2>(sv + s * kGvaNsBlock, vbase + (size_t)max(j[s], 0) * c);
+        for (int s = 0; s < NS; ++s) cp_async16_row<2>(sv + s * BLK, vbase + (size_t)max(j[s], 0) * c);
         if (HAS_PEB) {
             const float *pe = peb + (size_t)pt * NS * c + ch * 4;
 #pragma unroll
-            for (int s = 0; s < NS; ++s) cp_async16_stream(sq + s * kGvaNsBlock, pe + (size_t)s * c);
+            for (int s = 0; s < NS; ++s) cp_async16_stream(sq + s * BLK, pe + (size_t)s * c);
         }
         cp_async_commit();
         const float4 go = ldg_gather4(grad_out + (size_t)pt * c + ch * 4);
@@ -339,8 +345,8 @@ gva_backward_query_ns_kernel(long long n, int c, int g, const float *__restrict_
 #pragma unroll
         for (int s = 0; s < NS; ++s) {
             const bool keep = j[s] >= 0;
-            const float4 v = sv[s * kGvaNsBlock];
-            const float4 q = HAS_PEB ? sq[s * kGvaNsBlock] : f4_zero();
+            const float4 v = sv[s * BLK];
+            const float4 q = HAS_PEB ? sq[s * BLK] : f4_zero();
             const float d = group_sum<GL>(dot4(go, f4_add(v, q)));
             gw[s] = keep ? d : 0.f;
             const float w = keep ? p[s] : 0.f;
@@ -369,22 +375,23 @@ gva_backward_query_ns_kernel(long long n, int c, int g, const float *__restrict_
 constexpr int kFusedBatch = 8;
 
 template <int GL, int NS, bool HAS_PEB>
-__global__ void __launch_bounds__(kGvaNsBlock)
+__global__ void __launch_bounds__(ns_block<NS>())
 gva_backward_fused_ns_kernel(long long n, int c, int g, const float *__restrict__ grad_out,
                              const float *__restrict__ value, const float *__restrict__ peb,
                              const float *__restrict__ prob, const int *__restrict__ idx,
                              const int *__restrict__ rowptr, const int *__restrict__ perm,
                              float *__restrict__ grad_peb, float *__restrict__ grad_logits,
                              float *__restrict__ grad_value) {
+    constexpr int BLK = ns_block<NS>();
     extern __shared__ float4 stage[];
     constexpr int B = kFusedBatch;
     constexpr int KSHIFT = NS == 8 ? 3 : NS == 16 ? 4 : 5;
     float4 *sv = stage + threadIdx.x;
-    float4 *sq = stage + NS * kGvaNsBlock + threadIdx.x;
+    float4 *sq = stage + NS * BLK + threadIdx.x;
     const int chunks = c >> 2;
     const long long total = n * chunks;
-    const long long step = (long long)gridDim.x * kGvaNsBlock;
-    long long base = (long long)blockIdx.x * kGvaNsBlock + (threadIdx.x & ~31);
+    const long long step = (long long)gridDim.x * BLK;
+    long long base = (long long)blockIdx.x * BLK + (threadIdx.x & ~31);
     const int lane = threadIdx.x & 31;
     int jn[NS];
     // walk state: [e, e_end) = CSR row of the current item, pn = its first B perm values, (ne, ne_end) = next item's row
@@ -414,11 +421,11 @@ gva_backward_fused_ns_kernel(long long n, int c, int g, const float *__restrict_
         for (int s = 0; s < NS; ++s) j[s] = jn[s];
         const float *vbase = value + ch * 4;
 #pragma unroll
-        for (int s = 0; s < NS; ++s) cp_async16_row<2>(sv + s * kGvaNsBlock, vbase + (size_t)max(j[s], 0) * c);
+        for (int s = 0; s < NS; ++s) cp_async16_row<2>(sv + s * BLK, vbase + (size_t)max(j[s], 0) * c);
         if (HAS_PEB) {
             const float *pe = peb + (size_t)pt * NS * c + ch * 4;
 #pragma unroll
-            for (int s = 0; s < NS; ++s) cp_async16_stream(sq + s * kGvaNsBlock, pe + (size_t)s * c);
+            for (int s = 0; s < NS; ++s) cp_async16_stream(sq + s * BLK, pe + (size_t)s * c);
         }
         cp_async_commit();
         const float4 go = ldg_gather4(grad_out + (size_t)pt * c + ch * 4);
@@ -470,8 +477,8 @@ gva_backward_fused_ns_kernel(long long n, int c, int g, const float *__restrict_
 #pragma unroll
         for (int s = 0; s < NS; ++s) {
             const bool keep = j[s] >= 0;
-            const float4 v = sv[s * kGvaNsBlock];
-            const float4 q = HAS_PEB ? sq[s * kGvaNsBlock] : f4_zero();
+            const float4 v = sv[s * BLK];
+            const float4 q = HAS_PEB ? sq[s * BLK] : f4_zero();
             const float d = group_sum<GL>(dot4(go, f4_add(v, q)));
             gw[s] = keep ? d : 0.f;
             const float w = keep ? p[s] : 0.f;
@@ -763,21 +770,22 @@ static void gva_gather_mode_init() {
     (void)once;
 }
 
-static int ns_grid(long long items, int ns) {
-    gva_gather_mode_init(); return stride_grid(items, kGvaNsBlock, ns <= 8 ? 6 : ns <= 16 ? 3 : 1); }
+static int ns_grid(long long items, int ns, int block) {
+    gva_gather_mode_init(); return stride_grid(items, block, ns <= 8 ? 6 : 3); }
 
 // Dynamic shared memory of the NS kernels: 2·NS slots of 16 bytes per thread (64 KB at NS=16 → opt-in).
 #define GVA_DISPATCH_NS2(GLV, NSV, PEB, KERNEL, GRID, ST, ...)                                          \
     {                                                                                                  \
-        const size_t smem = (size_t)2 * NSV * 16 * kGvaNsBlock;                                        \
+        constexpr int BLKV = ns_block<NSV>();                                                          \
+        const size_t smem = (size_t)2 * NSV * 16 * BLKV;                                               \
         if (PEB) {                                                                                     \
             static bool once = (cudaFuncSetAttribute(KERNEL<GLV, NSV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), true); \
             (void)once;                                                                                \
-            KERNEL<GLV, NSV, true><<<ns_grid(GRID, NSV), kGvaNsBlock, smem, ST>>>(__VA_ARGS__);        \
+            KERNEL<GLV, NSV, true><<<ns_grid(GRID, NSV, BLKV), BLKV, smem, ST>>>(__VA_ARGS__);        \
         } else {                                                                                       \
             static bool once = (cudaFuncSetAttribute(KERNEL<GLV, NSV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), true); \
             (void)once;                                                                                \
-            KERNEL<GLV, NSV, false><<<ns_grid(GRID, NSV), kGvaNsBlock, smem, ST>>>(__VA_ARGS__);       \
+            KERNEL<GLV, NSV, false><<<ns_grid(GRID, NSV, BLKV), BLKV, smem, ST>>>(__VA_ARGS__);       \
         }                                                                                              \
     }
 

@@ -349,7 +349,9 @@ struct PeTcLayout {
     static constexpr int TMEM_COLS = NPAD <= 64 ? 64 : NPAD <= 128 ? 128 : NPAD <= 256 ? 256 : 512;
     static constexpr uint32_t A_LBO = kTcBlock * 16, B_LBO = NPAD * 16, SBO = 128;
     static constexpr size_t a_bytes = (size_t)kTcBlock * C * 2, b_bytes = (size_t)NPAD * C * 2;
-    static constexpr size_t bytes = a_bytes + b_bytes + 16 * (size_t)C + 4 * (size_t)C + 64;
+    static constexpr int OUT_LD = C + 4;                         // floats per staged output row: 16 bytes of padding
+    static constexpr size_t out_bytes = (size_t)kTcBlock * OUT_LD * 4;
+    static constexpr size_t bytes = a_bytes + b_bytes + out_bytes + 16 * (size_t)C + 4 * (size_t)C + 64;
     static constexpr int ctas_per_sm = (512 / TMEM_COLS) < (int)(232448 / (bytes + 1024)) ? (512 / TMEM_COLS) : (int)(232448 / (bytes + 1024));
 };
 
@@ -364,7 +366,8 @@ pe_mlp_forward_tc_kernel(long long rows, const float *__restrict__ pos, const fl
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char *a_s = smem_raw;                                             // A: [C/8][128][8] bf16
     unsigned char *b_s = a_s + L::a_bytes;                                     // B: [C/8][NPAD][8] bf16
-    float4 *fz = reinterpret_cast<float4 *>(b_s + L::b_bytes);                 // [C] folded z-map
+    float *out_s = reinterpret_cast<float *>(b_s + L::b_bytes);               // [128][C+4] staged output rows
+    float4 *fz = reinterpret_cast<float4 *>(out_s + kTcBlock * L::OUT_LD);     // [C] folded z-map
     float *b2s = reinterpret_cast<float *>(fz + C);                            // [C]
     uint64_t *bar = reinterpret_cast<uint64_t *>(b2s + C);                     // MMA-complete barrier
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar + 1);
@@ -433,22 +436,28 @@ pe_mlp_forward_tc_kernel(long long rows, const float *__restrict__ pos, const fl
         mbar_wait(bar, phase);
         phase ^= 1u;
         tc_fence_after();
-        // ---- epilogue: TMEM lane = row; 16 columns per load ----
-        float *orow = out + gr * C;
+        // ---- epilogue: TMEM lane = row; 16 columns per load.  The row goes to this thread's OWN padded slot in shared
+        // memory (row stride C+4 floats: the 16-byte stores of a quarter warp hit distinct banks) and from there to HBM
+        // with one bulk copy per row (cp.async.bulk, 4C contiguous bytes).  Storing straight from registers made every
+        // warp-wide store touch 32 different 128-byte lines (row stride 4C): 453 us at level 0 against 371 us for the
+        // mma.sync kernel, whose tile left through a bulk copy too (profiles/r02a_kernel_bench.txt).  No barrier: the slot
+        // is private to the thread, which waits for its previous copy to have READ the slot before rewriting it. ----
+        float *srow = out_s + tid * L::OUT_LD;
+        bulk_store_wait_read();
 #pragma unroll
         for (int j = 0; j < C / 16; ++j) {
             float v[16];
             tmem_ld16(tmem_row + j * 16, v);
             tmem_ld_wait();
-            if (live) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int col = j * 16 + q * 4;
-                    stg_stream4(orow + col, make_float4(v[q * 4] + b2s[col], v[q * 4 + 1] + b2s[col + 1],
-                                                        v[q * 4 + 2] + b2s[col + 2], v[q * 4 + 3] + b2s[col + 3]));
-                }
+            for (int q = 0; q < 4; ++q) {
+                const int col = j * 16 + q * 4;
+                *reinterpret_cast<float4 *>(srow + col) = make_float4(v[q * 4] + b2s[col], v[q * 4 + 1] + b2s[col + 1],
+                                                                       v[q * 4 + 2] + b2s[col + 2], v[q * 4 + 3] + b2s[col + 3]);
             }
         }
+        fence_proxy_async();   // this thread's generic-proxy writes -> visible to the bulk-copy (async) proxy
+        if (live) bulk_store(out + gr * C, srow, (uint32_t)(C * 4));
         if (aux) {
             float v[16];
             tmem_ld16(tmem_row + C, v);
@@ -460,6 +469,7 @@ pe_mlp_forward_tc_kernel(long long rows, const float *__restrict__ pos, const fl
             }
         }
     }
+    bulk_store_wait_all();   // shared memory must outlive this thread's last copy
     tc_fence_before();
     __syncthreads();
     if (warp == 0)

@@ -57,8 +57,8 @@ class GpuReferenceSchedule:
         self.gen = torch.Generator(device=self.device).manual_seed(seed)
         self.cache = {}
 
-    def _rand(self, name, *shape, grad=False):
-        key = (name,) + tuple(shape)
+    def _rand(self, name, level, *shape, grad=False):
+        key = (name, level) + tuple(shape)
         t = self.cache.get(key)
         if t is None:
             t = torch.randn(*shape, device=self.device, generator=self.gen)

@@ -704,6 +704,264 @@ pe_mlp_backward_kernel(long long rows, const float *__restrict__ pos, const floa
     }
 }
 
+// ---- 4b. backward on tcgen05: three UMMA products per 128-row tile, parameter-gradient accumulators resident in TMEM ----
+// Operand tiles live in shared memory as 16-byte pieces  byte(chunk, row) = chunk·2048 + row·16  (chunk = 8 consecutive
+// channels, row = 0..127).  ONE such buffer is two canonical no-swizzle UMMA layouts at once:
+//   K-major  (M/N = row,     K = channel): SBO = 128 (8-row groups),     LBO = 2048 (8-channel groups)
+//   MN-major (M/N = channel, K = row)    : SBO = 2048 (8-channel groups), LBO = 128  (8-row groups)
+// so the gradient tile GU = [G | dU] feeds  dh = GU · [W2 ; Wf]  as a K-major A operand and, untouched, the transposed
+// product  P = GUᵀ · [h | 1]  (= dW2, db2, dWf) as an MN-major A operand — no transposed copy (the mma.sync kernel kept
+// G and h in both orientations and was bound by the shared-memory pipe: 17 % of the HBM roofline).
+//   (1) D1 (128 x C)        = GU (128 x C+16, K-major)  · W2T ((C+16) x C, K-major B)        fresh every tile
+//   (2) dz = D1 ⊙ [h > 0] -> bf16 into the GU buffer (free once (1) and (3) have completed)
+//   (3) P  ((C+16) x (C+16)) += GUᵀ (MN-major A, K = 128 rows) · [h | 1 | 0] (MN-major B)       accumulates over tiles
+//   (4) Q  (C x 16)          += dzᵀ (MN-major A)              · [p_hi | 1 | p_lo | 0] (MN-major B)   accumulates over tiles
+// P and Q stay in Tensor Memory for the whole life of the CTA; they are read once at the end into the per-CTA partial
+// sums the finalize kernels already consume.  S3 = Σ dz ⊙ x̂ is linear in (S1, S2): x̂ = fx·(p, 1), so it needs no sum of
+// its own.  pos enters (4) as bf16 hi + lo parts (16 significant bits: dW1 subtracts Σ dz ⊗ mean(p) from S1).
+// UMMA M = 64 accumulators (C = 48: 64 channel rows) sit in lanes 0-15 of each 32-lane quarter: row m <-> lane
+// (m % 16) + 32 (m / 16)  (cute::UMMA::tmem_frg, 1-SM, M = 64); M = 128: row m <-> lane m.
+__device__ __forceinline__ constexpr uint32_t umma_idesc_bf16_mn(int m, int n) {   // both operands MN-major
+    return umma_idesc_bf16(m, n) | (1u << 15) | (1u << 16);
+}
+
+template <int C>
+struct PeTcBwd {
+    static constexpr int CA = C + 16;                          // channels of [G | dU]  (aux gradient padded to 16)
+    static constexpr int NP = C + 16;                          // columns of P: [h | 1 | 0 ...]
+    static constexpr int MP = CA <= 64 ? 64 : 128;             // UMMA M of P (rows = channels of GU)
+    static constexpr int MQ = C <= 64 ? 64 : 128;              // UMMA M of Q (rows = channels of dz)
+    static constexpr int GU_CHUNKS = (MP > MQ ? MP : MQ) / 8;  // the GU buffer is re-used for dz
+    static constexpr int H_CHUNKS = NP / 8;
+    static constexpr uint32_t CHUNK = kTcBlock * 16;           // bytes of one chunk (8 channels x 128 rows)
+    static constexpr uint32_t W_LBO = C * 16;                  // W2T: [(C+16)/8][C][8], K-major B of product (1)
+    static constexpr size_t gu_bytes = (size_t)GU_CHUNKS * CHUNK, h_bytes = (size_t)H_CHUNKS * CHUNK, pp_bytes = 2 * (size_t)CHUNK,
+                            w_bytes = (size_t)(CA / 8) * W_LBO;
+    static constexpr size_t bytes = gu_bytes + h_bytes + pp_bytes + w_bytes + 16 * (size_t)C + 64;
+    static constexpr int COL_D1 = 0, COL_P = C, COL_Q = C + NP;
+    static constexpr int TMEM_COLS = (2 * C + 32) <= 128 ? 128 : 256;
+    static constexpr int ctas_per_sm = (512 / TMEM_COLS) < (int)(232448 / (bytes + 1024)) ? (512 / TMEM_COLS) : (int)(232448 / (bytes + 1024));
+    static constexpr int partial_floats = C * C + 6 * C + 16 * C;   // same per-CTA layout as PeBwdLayout
+};
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+    const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<const uint32_t *>(&v);
+}
+
+template <int C>
+__global__ void __launch_bounds__(kTcBlock)
+pe_mlp_backward_tc_kernel(long long rows, const float *__restrict__ pos, const float *__restrict__ fold,
+                          const __nv_bfloat16 *__restrict__ w2t_bf, const float *__restrict__ grad,
+                          float *__restrict__ partial, const __nv_bfloat16 *__restrict__ wft_bf, int ga,
+                          const float *__restrict__ grad_aux) {
+    using L = PeTcBwd<C>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned char *gu_s = smem_raw;                                   // [G | dU] tile, later the dz tile
+    unsigned char *h_s = gu_s + L::gu_bytes;                          // [h | 1 | 0] tile
+    unsigned char *pp_s = h_s + L::h_bytes;                           // [p_hi, 1, p_lo, 0 | 0] tile
+    unsigned char *w_s = pp_s + L::pp_bytes;                          // W2T: n = ci, k = co then the 16 aux rows
+    float4 *fz = reinterpret_cast<float4 *>(w_s + L::w_bytes);        // [C] folded z-map
+    uint64_t *bar = reinterpret_cast<uint64_t *>(fz + C);             // bar[0]: products (1)+(3) done, bar[1]: (4) done
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar + 2);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const bool aux = grad_aux != nullptr;
+
+    // ---- one-time setup: W2T, the constant chunks of the h / pos tiles, barriers, TMEM ----
+    for (int i = tid; i < C * (L::CA / 8); i += kTcBlock) {
+        const int n = i % C, k8 = i / C;     // B(n = ci, k = 8 k8 ..): W2[co][ci] for co < C, Wf[g'][ci] for the last 16
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (k8 < C / 8) v = *reinterpret_cast<const uint4 *>(w2t_bf + (size_t)n * C + k8 * 8);
+        else if (aux) v = *reinterpret_cast<const uint4 *>(wft_bf + (size_t)n * 16 + (k8 - C / 8) * 8);
+        *reinterpret_cast<uint4 *>(w_s + (size_t)k8 * L::W_LBO + n * 16) = v;
+    }
+    for (int i = tid; i < C; i += kTcBlock) fz[i] = make_float4(fold[i * 8], fold[i * 8 + 1], fold[i * 8 + 2], fold[i * 8 + 3]);
+    {   // column C of [h | 1 | 0] is the constant 1 (db2 = Σ G), the rest of the last two chunks is 0; second pos chunk 0
+        const uint32_t one = pack_bf16x2(1.f, 0.f);
+        *reinterpret_cast<uint4 *>(h_s + (size_t)(C / 8) * L::CHUNK + tid * 16) = make_uint4(one, 0u, 0u, 0u);
+        *reinterpret_cast<uint4 *>(h_s + (size_t)(C / 8 + 1) * L::CHUNK + tid * 16) = make_uint4(0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4 *>(pp_s + L::CHUNK + tid * 16) = make_uint4(0u, 0u, 0u, 0u);
+        // chunks of the GU buffer beyond the real channels are only ever read as M-padding (ignored output rows)
+        for (int ch = L::CA / 8; ch < L::GU_CHUNKS; ++ch)
+            *reinterpret_cast<uint4 *>(gu_s + (size_t)ch * L::CHUNK + tid * 16) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    if (tid == 0) { mbar_init(bar, 1); mbar_init(bar + 1, 1); }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(L::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t gu_addr = smem_u32(gu_s), h_addr = smem_u32(h_s), pp_addr = smem_u32(pp_s), w_addr = smem_u32(w_s);
+    constexpr uint32_t idesc1 = umma_idesc_bf16(128, C);
+    constexpr uint32_t idescP = umma_idesc_bf16_mn(L::MP, L::NP);
+    constexpr uint32_t idescQ = umma_idesc_bf16_mn(L::MQ, 16);
+    const uint32_t tmem_row = tmem_base + ((uint32_t)(warp * 32) << 16);
+
+    const long long n_tiles = (rows + kTcBlock - 1) / kTcBlock;
+    uint32_t phase = 0;
+    bool first = true;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const long long row_base = tile * kTcBlock;
+        // ---- a. gradient tile: the warp's 32 rows are 32·C contiguous floats — coalesced 128-bit loads, two lanes
+        //         assemble one 16-byte bf16 piece (8 channels) ----
+        {
+            constexpr int F4 = C / 4;                                 // float4 per row (even)
+            const long long wrow0 = row_base + warp * 32;
+            const float4 *src = reinterpret_cast<const float4 *>(grad + wrow0 * C);
+#pragma unroll
+            for (int i = 0; i < F4; ++i) {
+                const int q = i * 32 + lane;
+                const int rl = q / F4, c4 = q - rl * F4;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (wrow0 + rl < rows) v = ldg_stream4(reinterpret_cast<const float *>(src + q));
+                const uint32_t u0 = pack_bf16x2(v.x, v.y), u1 = pack_bf16x2(v.z, v.w);
+                const uint32_t n0 = __shfl_down_sync(0xffffffffu, u0, 1), n1 = __shfl_down_sync(0xffffffffu, u1, 1);
+                if ((lane & 1) == 0)
+                    *reinterpret_cast<uint4 *>(gu_s + (size_t)(c4 >> 1) * L::CHUNK + (warp * 32 + rl) * 16) = make_uint4(u0, u1, n0, n1);
+            }
+        }
+        const long long gr = row_base + tid;
+        const bool live = gr < rows;
+        {   // aux gradient of this thread's row: 16 channels (two chunks), zero beyond ga
+            float du[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) du[q] = (aux && live && q < ga) ? __ldg(grad_aux + gr * ga + q) : 0.f;
+#pragma unroll
+            for (int hlf = 0; hlf < 2; ++hlf)
+                *reinterpret_cast<uint4 *>(gu_s + (size_t)(C / 8 + hlf) * L::CHUNK + tid * 16) =
+                    make_uint4(pack_bf16x2(du[hlf * 8], du[hlf * 8 + 1]), pack_bf16x2(du[hlf * 8 + 2], du[hlf * 8 + 3]),
+                               pack_bf16x2(du[hlf * 8 + 4], du[hlf * 8 + 5]), pack_bf16x2(du[hlf * 8 + 6], du[hlf * 8 + 7]));
+        }
+        // ---- b. hidden activations of this thread's row (as in the forward kernel) and its position ----
+        float px = 0.f, py = 0.f, pz = 0.f;
+        if (live) { px = __ldg(pos + gr * 3); py = __ldg(pos + gr * 3 + 1); pz = __ldg(pos + gr * 3 + 2); }
+#pragma unroll
+        for (int k8 = 0; k8 < C / 8; ++k8) {
+            uint32_t w[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float4 f0 = fz[k8 * 8 + 2 * q], f1 = fz[k8 * 8 + 2 * q + 1];
+                const float z0 = fmaf(f0.x, px, fmaf(f0.y, py, fmaf(f0.z, pz, f0.w)));
+                const float z1 = fmaf(f1.x, px, fmaf(f1.y, py, fmaf(f1.z, pz, f1.w)));
+                w[q] = pack_bf16x2(live ? fmaxf(z0, 0.f) : 0.f, live ? fmaxf(z1, 0.f) : 0.f);
+            }
+            *reinterpret_cast<uint4 *>(h_s + (size_t)k8 * L::CHUNK + tid * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        {
+            const float hx = __bfloat162float(__float2bfloat16_rn(px)), hy = __bfloat162float(__float2bfloat16_rn(py)),
+                        hz = __bfloat162float(__float2bfloat16_rn(pz));
+            *reinterpret_cast<uint4 *>(pp_s + tid * 16) =
+                make_uint4(pack_bf16x2(hx, hy), pack_bf16x2(hz, live ? 1.f : 0.f), pack_bf16x2(px - hx, py - hy), pack_bf16x2(pz - hz, 0.f));
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            // (1) dh = GU · W2T                                   M = 128 rows, N = C, K = C + 16
+#pragma unroll
+            for (int kk = 0; kk < L::CA / 16; ++kk)
+                umma_bf16(tmem_base + L::COL_D1, umma_smem_desc(gu_addr + kk * 2 * L::CHUNK, L::CHUNK, 128),
+                          umma_smem_desc(w_addr + kk * 2 * L::W_LBO, L::W_LBO, 128), idesc1, kk > 0 ? 1u : 0u);
+            // (3) P += GUᵀ · [h | 1 | 0]                           M = channels of GU, N = C + 16, K = 128 rows
+#pragma unroll
+            for (int kk = 0; kk < kTcBlock / 16; ++kk)
+                umma_bf16(tmem_base + L::COL_P, umma_smem_desc(gu_addr + kk * 256, 128, L::CHUNK),
+                          umma_smem_desc(h_addr + kk * 256, 128, L::CHUNK), idescP, (!first || kk > 0) ? 1u : 0u);
+            umma_commit(bar);
+        }
+        mbar_wait(bar, phase);
+        tc_fence_after();
+        // ---- c. dz = dh ⊙ [h > 0] of this thread's row -> bf16 pieces into the (now free) GU buffer ----
+#pragma unroll
+        for (int j = 0; j < C / 16; ++j) {
+            float v[16];
+            tmem_ld16(tmem_row + L::COL_D1 + j * 16, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int hlf = 0; hlf < 2; ++hlf) {
+                const uint4 hb = *reinterpret_cast<const uint4 *>(h_s + (size_t)(2 * j + hlf) * L::CHUNK + tid * 16);
+                const uint32_t hw[4] = {hb.x, hb.y, hb.z, hb.w};
+                uint32_t w[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float d0 = (hw[q] & 0x7fffu) ? v[hlf * 8 + 2 * q] : 0.f;
+                    const float d1 = (hw[q] & 0x7fff0000u) ? v[hlf * 8 + 2 * q + 1] : 0.f;
+                    w[q] = pack_bf16x2(d0, d1);
+                }
+                *reinterpret_cast<uint4 *>(gu_s + (size_t)(2 * j + hlf) * L::CHUNK + tid * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            // (4) Q += dzᵀ · [p_hi, 1, p_lo, 0]                    M = channels, N = 16, K = 128 rows
+#pragma unroll
+            for (int kk = 0; kk < kTcBlock / 16; ++kk)
+                umma_bf16(tmem_base + L::COL_Q, umma_smem_desc(gu_addr + kk * 256, 128, L::CHUNK),
+                          umma_smem_desc(pp_addr + kk * 256, 128, L::CHUNK), idescQ, (!first || kk > 0) ? 1u : 0u);
+            umma_commit(bar + 1);
+        }
+        mbar_wait(bar + 1, phase);   // the tiles are rewritten by the next iteration
+        tc_fence_after();
+        phase ^= 1u;
+        first = false;
+    }
+    // ---- d. per-CTA partial sums out of Tensor Memory (layout of PeBwdLayout: dW2 | db2 | S2 | S3 | S1 | dWf) ----
+    float *out = partial + (size_t)blockIdx.x * L::partial_floats;
+    if (first) {   // a CTA that owned no tile (cannot happen with pe_grid, kept for safety): zeros
+        for (int i = tid; i < L::partial_floats; i += kTcBlock) out[i] = 0.f;
+    } else {
+        {   // P: row m = channel of GU
+            const int m = L::MP == 64 ? warp * 16 + lane : warp * 32 + lane;
+            const bool owner = (L::MP == 64 ? lane < 16 : true) && m < L::CA;
+#pragma unroll
+            for (int j = 0; j < L::NP / 16; ++j) {
+                float v[16];
+                tmem_ld16(tmem_row + L::COL_P + j * 16, v);
+                tmem_ld_wait();
+                if (owner) {
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) {
+                        const int n = j * 16 + q;
+                        if (m < C) {
+                            if (n < C) out[(size_t)m * C + n] = v[q];                     // dW2[co][ci]
+                            else if (n == C) out[(size_t)C * C + m] = v[q];               // db2[co]
+                        } else if (n < C) {
+                            out[(size_t)C * C + 6 * C + (size_t)(m - C) * C + n] = v[q];  // dWf[g'][ci]
+                        }
+                    }
+                }
+            }
+        }
+        {   // Q: row m = channel of dz; columns p_hi (0..2), 1 (3), p_lo (4..6)
+            const int m = L::MQ == 64 ? warp * 16 + lane : warp * 32 + lane;
+            const bool owner = (L::MQ == 64 ? lane < 16 : true) && m < C;
+            float v[16];
+            tmem_ld16(tmem_row + L::COL_Q, v);
+            tmem_ld_wait();
+            if (owner) {
+                const float s1x = v[0] + v[4], s1y = v[1] + v[5], s1z = v[2] + v[6], s2 = v[3];
+                const float4 fx = make_float4(fold[m * 8 + 4], fold[m * 8 + 5], fold[m * 8 + 6], fold[m * 8 + 7]);
+                out[(size_t)C * C + C + m] = s2;                                                   // S2
+                out[(size_t)C * C + 2 * C + m] = fmaf(fx.x, s1x, fmaf(fx.y, s1y, fmaf(fx.z, s1z, fx.w * s2)));   // S3 = Σ dz·x̂
+                out[(size_t)C * C + 3 * C + m * 3 + 0] = s1x;
+                out[(size_t)C * C + 3 * C + m * 3 + 1] = s1y;
+                out[(size_t)C * C + 3 * C + m * 3 + 2] = s1z;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(L::TMEM_COLS) : "memory");
+}
+
 // Sums the per-CTA partials in CTA order: dW2 directly, the channel sums (db2 | S2 | S3 | S1) into `sums`.
 __global__ void __launch_bounds__(256)
 pe_mlp_backward_finalize_kernel(int c, int n_partial, int partial_floats, const float *__restrict__ partial,
@@ -759,8 +1017,17 @@ static int pe_grid(long long rows, int tile_rows, int ctas_per_sm) {
     return (int)(tiles < cap ? (tiles < 1 ? 1 : tiles) : cap);
 }
 static int pe_bwd_grid(long long rows, int c) {
+    if (tuning(kTunePeBwd) != 2)   // tcgen05 kernel: 128-row tiles
+        return c <= 48 ? pe_grid(rows, kTcBlock, PeTcBwd<48>::ctas_per_sm) : pe_grid(rows, kTcBlock, PeTcBwd<96>::ctas_per_sm);
     return c <= 48 ? pe_grid(rows, PeBwdLayout<48>::TR, PeBwdLayout<48>::ctas_per_sm)
                    : pe_grid(rows, PeBwdLayout<96>::TR, PeBwdLayout<96>::ctas_per_sm);
+}
+// upper bound over both kernels (the workspace query must not depend on a switch that can change between calls)
+static int pe_bwd_grid_max(long long rows, int c) {
+    const int a = c <= 48 ? pe_grid(rows, kTcBlock, PeTcBwd<48>::ctas_per_sm) : pe_grid(rows, kTcBlock, PeTcBwd<96>::ctas_per_sm);
+    const int b = c <= 48 ? pe_grid(rows, PeBwdLayout<48>::TR, PeBwdLayout<48>::ctas_per_sm)
+                          : pe_grid(rows, PeBwdLayout<96>::TR, PeBwdLayout<96>::ctas_per_sm);
+    return a > b ? a : b;
 }
 
 template <int C>
@@ -831,6 +1098,13 @@ void launch_fwd(long long rows, const float *pos, const PeState &s, const float 
 template <int C>
 void launch_bwd(long long rows, const float *pos, const PeState &s, const float *grad, float *partial, int grid,
                 int ga, const float *grad_aux, cudaStream_t st) {
+    if (tuning(kTunePeBwd) != 2) {   // tcgen05 / TMEM kernel (default)
+        using L = PeTcBwd<C>;
+        static bool once = (cudaFuncSetAttribute(pe_mlp_backward_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::bytes), true);
+        (void)once;
+        pe_mlp_backward_tc_kernel<C><<<grid, kTcBlock, L::bytes, st>>>(rows, pos, s.fold, s.w2t, grad, partial, s.wft, ga, grad_aux);
+        return;
+    }
     const size_t smem = PeBwdLayout<C>::bytes;
     static bool once = (cudaFuncSetAttribute(pe_mlp_backward_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), true);
     (void)once;
@@ -868,7 +1142,7 @@ extern "C" int aopt_pe_mlp_forward(int64_t rows, int c, const float *pos, const 
 extern "C" size_t aopt_pe_mlp_backward_workspace_bytes(int64_t rows, int c) {
     if (!aopt_pe_mlp_supported(c) || rows < 0) return 0;
     const size_t pf = (size_t)c * c + 6 * (size_t)c + 16 * (size_t)c;
-    return a256(4 * pf * (size_t)pe_bwd_grid(rows, c)) + a256(4 * 6 * (size_t)c);
+    return a256(4 * pf * (size_t)pe_bwd_grid_max(rows, c)) + a256(4 * 6 * (size_t)c);
 }
 
 /* Parameter gradients of aopt_pe_mlp_forward given grad (rows,c) = dL/dpeb; `state` is the forward's. */

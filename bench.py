@@ -690,7 +690,7 @@ def run_b200_arm(args):
     ctx.finish()
 
 
-def model_step(ctx, name, coord, feat, offset, bucket_cap_mb, steps=8):
+def model_step(ctx, name, coord, feat, offset, bucket_cap_mb, steps=10):
     """Full training step of the config's PTv2m2 (ao_b200.ptv2): bf16 autocast forward, cross-entropy, backward,
     AdamW — the reference's Trainer.run_step (pointcept/engines/train.py:173-200).  At N > 1 the model is wrapped by
     ao_b200.sharding.ddp_wrap (engines/defaults.py:30-43), so the gradient all-reduce is DDP's own, bucketed and
@@ -719,19 +719,25 @@ def model_step(ctx, name, coord, feat, offset, bucket_cap_mb, steps=8):
     for _ in range(3):
         step()
     ctx.barrier()
+    # the dense layers are compute-heavy: under the board's power cap their clocks (hence this number) depend on how
+    # long the GPU has been loaded before — the SM clock during these steps is reported next to the time
+    sampler = ClockSampler(ctx.local) if ctx.rank == 0 else None
+    if sampler:
+        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
         loss = step()
     e1.record()
     ctx.barrier()
+    clocks = sampler.stop() if sampler else None
     ms = ctx.max_over_ranks(e0.elapsed_time(e1)) / steps
     out = {"what": f"full PTv2m2 ({CONFIGS[name]['model']}) training step: bf16 autocast GEMMs (cuBLAS) + these point ops + "
                    "cross-entropy + AdamW" + (f"; DistributedDataParallel over {ctx.world} ranks (broadcast_buffers=False, "
                    f"bucket_cap_mb={bucket_cap_mb}, gradient_as_bucket_view), NCCL all-reduce overlapped with backward"
                    if ctx.world > 1 else ""),
            "ms_per_step": ms, "mpoints_per_s": ctx.world * coord.shape[0] / (ms * 1e-3) / 1e6, "loss": float(loss.item()),
-           "parameters": n_params, "grad_mb": round(n_params * 4 / 1e6, 2), "steps": steps,
+           "parameters": n_params, "grad_mb": round(n_params * 4 / 1e6, 2), "steps": steps, "clocks": clocks,
            "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 1e9}
     del net, model, opt
     return out

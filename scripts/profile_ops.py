@@ -30,9 +30,20 @@ c_next = C[min(level + 1, 3)]
 pool_in = torch.relu(torch.randn(n, c_next, device=dev)).requires_grad_(True)
 
 
+mlp = None
+if pointops.pe_mlp_supported(c):
+    mlp = torch.nn.Sequential(torch.nn.Linear(3, c), torch.nn.BatchNorm1d(c), torch.nn.ReLU(inplace=True),
+                              torch.nn.Linear(c, c)).to(dev).train()
+    aux_w = torch.randn(g, c, device=dev, requires_grad=True)
+
+
 def run():
     idx, _ = pointops.knn_query(k, coord, offset)
     pos = pointops.group_xyz(idx, coord)
+    if mlp is not None:      # fused positional-bias MLP (tcgen05 forward) with the auxiliary head, forward + backward
+        mom = pointops.pos_moments(pos)
+        y, u = pointops.pe_bias_mlp(pos, mlp, mom, aux_weight=aux_w)
+        torch.autograd.grad([y, u], list(mlp.parameters()) + [aux_w], [torch.ones_like(y), torch.ones_like(u)])
     rel = pointops.gva_relation(key, query, idx)
     out = pointops.gva_aggregate(value, peb, logits, idx, g)
     torch.autograd.grad(rel, [key, query], g_rel)

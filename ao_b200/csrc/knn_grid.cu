@@ -150,6 +150,18 @@ knn_sample_kernel(int b, int nsample, const float *__restrict__ xyz, const int *
     if (threadIdx.x == 0) samples[blockIdx.x] = result;
 }
 
+// ---- 1b. no density sample: clear only ---------------------------------------------------------------
+// The sampled k-th neighbour distance rarely decides the cell edge: the capacity (cells per point) does for surface
+// scans, and the search is exact for any edge.  With tuning "knn_sample" = 0 (default) the edge comes from the bounding
+// box alone, h = cbrt(volume / capacity) per scene, and this kernel only does the sample kernel's housekeeping
+// (21 us -> 3 us per search, seven searches per step).
+__global__ void __launch_bounds__(256)
+knn_clear_kernel(int b, int *__restrict__ cells, long long n_cells, unsigned *__restrict__ bb_lo, unsigned *__restrict__ bb_hi) {
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n_cells; i += (long long)gridDim.x * 256) cells[i] = 0;
+    if (blockIdx.x == 0)
+        for (int i = threadIdx.x; i < 3 * b; i += 256) { bb_lo[i] = kBboxEmptyLo; bb_hi[i] = kBboxEmptyHi; }
+}
+
 // ---- 2. per-scene grid descriptor ------------------------------------------------------------------
 // One thread per scene: bounding box from the encoded min/max (bbox.cu), cell edge from the samples.
 // One WARP per scene (the 64 sample loads are issued together and reduced with shuffles; one thread per scene
@@ -165,7 +177,7 @@ grid_setup_kernel(int b, int n, const int *__restrict__ offset, const unsigned *
     int cnt = 0;
 #pragma unroll
     for (int s = lane; s < kSamples; s += 32) {
-        const float v = __ldg(samples + sc * kSamples + s);
+        const float v = samples ? __ldg(samples + sc * kSamples + s) : 1e10f;
         if (v < 1e9f) { sum += sqrtf(v); ++cnt; }
     }
 #pragma unroll
@@ -189,6 +201,17 @@ grid_setup_kernel(int b, int n, const int *__restrict__ offset, const unsigned *
     float ext[3] = {hi[0] - lo[0], hi[1] - lo[1], hi[2] - lo[2]};
     float max_ext = fmaxf(ext[0], fmaxf(ext[1], ext[2]));
     float h = cnt > 0 ? cell_scale * sum / (float)cnt : 0.f;
+    if (!samples) {
+        // capacity-driven edge: the cube root of (bounding-box volume / cells allowed); flat boxes (a wall, a ground
+        // plane) use the two or one extents that are not degenerate
+        const long long cap0 = (long long)kCellsPerPoint * ns + kCellsPerScene;
+        float dims[3] = {ext[0], ext[1], ext[2]};
+        const float tiny = max_ext * 1e-3f;
+        float vol = 1.f;
+        int nd = 0;
+        for (int a = 0; a < 3; ++a) if (dims[a] > tiny) { vol *= dims[a]; ++nd; }
+        h = nd == 3 ? cbrtf(vol / (float)cap0) : nd == 2 ? sqrtf(vol / (float)cap0) : nd == 1 ? vol / (float)cap0 : 0.f;
+    }
     if (!(h > max_ext * (1.f / 2048.f))) h = max_ext * (1.f / 2048.f);  // also catches NaN / 0
     if (!(h > 1e-12f)) h = 1.f;                                         // all points coincide
     const long long cap = (long long)kCellsPerPoint * ns + kCellsPerScene;
@@ -421,14 +444,20 @@ int knn_grid_launch(int m, int nsample, int n, int b, const float *xyz, const fl
     }
     const bool self = (new_xyz == xyz) && (new_offset == offset) && (m == n);
 
-    if (nsample <= 1) launch_sample<1>(b, nsample, xyz, offset, w, st);
+    const bool sampled = tuning(kTuneKnnSample) == 2;
+    if (!sampled) {
+        const long long nc = (long long)w.total_cells + 1;
+        knn_clear_kernel<<<stride_grid(nc, 256, 8), 256, 0, st>>>(b, w.cells, nc, w.bbox, w.bbox + 3 * (size_t)b);
+    }
+    else if (nsample <= 1) launch_sample<1>(b, nsample, xyz, offset, w, st);
     else if (nsample <= 3) launch_sample<3>(b, nsample, xyz, offset, w, st);
     else if (nsample <= 4) launch_sample<4>(b, nsample, xyz, offset, w, st);
     else if (nsample <= 8) launch_sample<8>(b, nsample, xyz, offset, w, st);
     else if (nsample <= 16) launch_sample<16>(b, nsample, xyz, offset, w, st);
     else launch_sample<32>(b, nsample, xyz, offset, w, st);
     launch_scene_bbox(n, b, xyz, offset, w.bbox, w.bbox + 3 * (size_t)b, st, /*init=*/false);
-    grid_setup_kernel<<<div_up(b, 4), 128, 0, st>>>(b, n, offset, w.bbox, w.bbox + 3 * (size_t)b, w.samples, scale, cells_per_point(), w.desc);
+    grid_setup_kernel<<<div_up(b, 4), 128, 0, st>>>(b, n, offset, w.bbox, w.bbox + 3 * (size_t)b, sampled ? w.samples : nullptr, scale,
+                                                    cells_per_point(), w.desc);
     grid_count_kernel<<<div_up(n, 256), 256, 0, st>>>(n, b, xyz, offset, w.desc, w.cells, w.point_cell, w.point_slot);
     launch_exclusive_scan(w.cells, w.cells, (int)w.total_cells, w.partial, st);
     grid_fill_kernel<<<div_up(n, 256), 256, 0, st>>>(n, xyz, w.cells, w.point_cell, w.point_slot, w.sorted);

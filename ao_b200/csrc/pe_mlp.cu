@@ -64,12 +64,16 @@ pos_moments_partial_kernel(long long rows, const float *__restrict__ pos, double
     }
 }
 
-__global__ void pos_moments_final_kernel(int n_partial, const double *__restrict__ partial, double *__restrict__ out) {
-    if (threadIdx.x < 9) {
-        double v = 0.0;
-        for (int i = 0; i < n_partial; ++i) v += partial[(size_t)i * 9 + threadIdx.x];
-        out[threadIdx.x] = v;
-    }
+// One warp per moment (9 warps): lanes stride over the per-CTA partials, then a shuffle tree — a fixed order (one thread
+// per moment walking all 592 partials took 37 us: profiles/r02c_ops_L0_ncu_summary.md).
+__global__ void __launch_bounds__(288)
+pos_moments_final_kernel(int n_partial, const double *__restrict__ partial, double *__restrict__ out) {
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double v = 0.0;
+    for (int i = lane; i < n_partial; i += 32) v += partial[(size_t)i * 9 + w];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    if (lane == 0) out[w] = v;
 }
 
 // ---- 2. fold BatchNorm into per-channel affine maps, convert W2 ---------------------------------------
@@ -351,7 +355,9 @@ struct PeTcLayout {
     static constexpr size_t a_bytes = (size_t)kTcBlock * C * 2, b_bytes = (size_t)NPAD * C * 2;
     static constexpr int OUT_LD = C + 4;                         // floats per staged output row: 16 bytes of padding
     static constexpr size_t out_bytes = (size_t)kTcBlock * OUT_LD * 4;
-    static constexpr size_t bytes = a_bytes + b_bytes + out_bytes + 16 * (size_t)C + 4 * (size_t)C + 64;
+    // the staged output rows re-use the A tile's memory (A is dead once the tile's MMAs have completed)
+    static constexpr size_t ao_bytes = a_bytes > out_bytes ? a_bytes : out_bytes;
+    static constexpr size_t bytes = ao_bytes + b_bytes + 16 * (size_t)C + 4 * (size_t)C + 64;
     static constexpr int ctas_per_sm = (512 / TMEM_COLS) < (int)(232448 / (bytes + 1024)) ? (512 / TMEM_COLS) : (int)(232448 / (bytes + 1024));
 };
 
@@ -364,10 +370,10 @@ pe_mlp_forward_tc_kernel(long long rows, const float *__restrict__ pos, const fl
     using L = PeTcLayout<C>;
     constexpr int NPAD = L::NPAD;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    unsigned char *a_s = smem_raw;                                             // A: [C/8][128][8] bf16
-    unsigned char *b_s = a_s + L::a_bytes;                                     // B: [C/8][NPAD][8] bf16
-    float *out_s = reinterpret_cast<float *>(b_s + L::b_bytes);               // [128][C+4] staged output rows
-    float4 *fz = reinterpret_cast<float4 *>(out_s + kTcBlock * L::OUT_LD);     // [C] folded z-map
+    unsigned char *a_s = smem_raw;                                             // A: [C/8][128][8] bf16 ...
+    float *out_s = reinterpret_cast<float *>(smem_raw);                       // ... and, after the MMAs, [128][C+4] staged output rows
+    unsigned char *b_s = a_s + L::ao_bytes;                                    // B: [C/8][NPAD][8] bf16
+    float4 *fz = reinterpret_cast<float4 *>(b_s + L::b_bytes);                 // [C] folded z-map
     float *b2s = reinterpret_cast<float *>(fz + C);                            // [C]
     uint64_t *bar = reinterpret_cast<uint64_t *>(b2s + C);                     // MMA-complete barrier
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar + 1);
@@ -407,6 +413,10 @@ pe_mlp_forward_tc_kernel(long long rows, const float *__restrict__ pos, const fl
         // ---- A: hidden activations of this thread's row, 8 channels (16 bytes) at a time ----
         float px = 0.f, py = 0.f, pz = 0.f;
         if (live) { px = __ldg(pos + gr * 3); py = __ldg(pos + gr * 3 + 1); pz = __ldg(pos + gr * 3 + 2); }
+        // the A tile shares its memory with the staged output rows of the previous tile: every thread's bulk copy must
+        // have finished READING before anybody writes A (each thread waits for its own copy, the barrier below joins them)
+        bulk_store_wait_read();
+        __syncthreads();
 #pragma unroll
         for (int k8 = 0; k8 < C / 8; ++k8) {
             uint32_t w[4];
@@ -443,7 +453,6 @@ pe_mlp_forward_tc_kernel(long long rows, const float *__restrict__ pos, const fl
         // mma.sync kernel, whose tile left through a bulk copy too (profiles/r02a_kernel_bench.txt).  No barrier: the slot
         // is private to the thread, which waits for its previous copy to have READ the slot before rewriting it. ----
         float *srow = out_s + tid * L::OUT_LD;
-        bulk_store_wait_read();
 #pragma unroll
         for (int j = 0; j < C / 16; ++j) {
             float v[16];
@@ -733,7 +742,11 @@ struct PeTcBwd {
     static constexpr int MQ = C <= 64 ? 64 : 128;              // UMMA M of Q (rows = channels of dz)
     static constexpr int GU_CHUNKS = (MP > MQ ? MP : MQ) / 8;  // the GU buffer is re-used for dz
     static constexpr int H_CHUNKS = NP / 8;
-    static constexpr uint32_t CHUNK = kTcBlock * 16;           // bytes of one chunk (8 channels x 128 rows)
+    // bytes from one chunk (8 channels x 128 rows) to the next: 2048 + 16.  The 16 bytes of padding rotate the banks of
+    // successive chunks, so that the 16-byte pieces the gradient load writes for ONE row (6 chunks, same row) no longer
+    // fall on the same four banks (19 M conflict wavefronts of 66 M at level 0, LSU pipe 79 %: profiles/r02c); the
+    // UMMA descriptors take the stride as it is (LBO of the K-major view, SBO of the MN-major view).
+    static constexpr uint32_t CHUNK = kTcBlock * 16 + 16;
     static constexpr uint32_t W_LBO = C * 16;                  // W2T: [(C+16)/8][C][8], K-major B of product (1)
     static constexpr size_t gu_bytes = (size_t)GU_CHUNKS * CHUNK, h_bytes = (size_t)H_CHUNKS * CHUNK, pp_bytes = 2 * (size_t)CHUNK,
                             w_bytes = (size_t)(CA / 8) * W_LBO;
@@ -963,17 +976,28 @@ pe_mlp_backward_tc_kernel(long long rows, const float *__restrict__ pos, const f
 }
 
 // Sums the per-CTA partials in CTA order: dW2 directly, the channel sums (db2 | S2 | S3 | S1) into `sums`.
+// 256 threads = 32 output elements x 8 slices of the partials; the slices are combined through shared memory in a
+// fixed order (one thread per element walking all ~592 partials: 57 us per call, profiles/r02c_ops_L0_ncu_summary.md).
 __global__ void __launch_bounds__(256)
 pe_mlp_backward_finalize_kernel(int c, int n_partial, int partial_floats, const float *__restrict__ partial,
                                 float *__restrict__ grad_w2, float *__restrict__ sums, int ga,
                                 float *__restrict__ grad_aux_w) {
+    __shared__ float red[8][32];
     const int total = c * c + 6 * c + (grad_aux_w ? ga * c : 0);
-    for (int i = blockIdx.x * 256 + threadIdx.x; i < total; i += gridDim.x * 256) {
-        float v = 0.f;
-        for (int p = 0; p < n_partial; ++p) v += partial[(size_t)p * partial_floats + i];
-        if (i < c * c) grad_w2[i] = v;
-        else if (i < c * c + 6 * c) sums[i - c * c] = v;
-        else grad_aux_w[i - c * c - 6 * c] = v;  // dWf [ga][c]
+    const int e = threadIdx.x & 31, sl = threadIdx.x >> 5;
+    const int i = blockIdx.x * 32 + e;
+    float v = 0.f;
+    if (i < total)
+        for (int p = sl; p < n_partial; p += 8) v += partial[(size_t)p * partial_floats + i];
+    red[sl][e] = v;
+    __syncthreads();
+    if (sl == 0 && i < total) {
+        float t = red[0][e];
+#pragma unroll
+        for (int q = 1; q < 8; ++q) t += red[q][e];
+        if (i < c * c) grad_w2[i] = t;
+        else if (i < c * c + 6 * c) sums[i - c * c] = t;
+        else grad_aux_w[i - c * c - 6 * c] = t;  // dWf [ga][c]
     }
 }
 
@@ -1053,7 +1077,7 @@ extern "C" int aopt_pos_moments(int64_t rows, const float *pos, double *moments,
     const int grid = stride_grid(rows > 0 ? rows : 1, kMomBlock, 4);
     double *partial = static_cast<double *>(workspace);
     pos_moments_partial_kernel<<<grid, kMomBlock, 0, st>>>(rows, pos, partial);
-    pos_moments_final_kernel<<<1, 32, 0, st>>>(grid, partial, moments);
+    pos_moments_final_kernel<<<1, 288, 0, st>>>(grid, partial, moments);
     return check_launch(2);
 }
 
@@ -1168,7 +1192,7 @@ extern "C" int aopt_pe_mlp_backward(int64_t rows, int c, const float *pos, const
     float *sums = reinterpret_cast<float *>(static_cast<char *>(workspace) + a256(4 * (size_t)pf * grid));
     if (c == 48) launch_bwd<48>(rows, pos, s, grad, partial, grid, ga, grad_aux, st);
     else launch_bwd<96>(rows, pos, s, grad, partial, grid, ga, grad_aux, st);
-    pe_mlp_backward_finalize_kernel<<<div_up(pf, 256), 256, 0, st>>>(c, grid, pf, partial, grad_w2, sums, ga, grad_aux_w);
+    pe_mlp_backward_finalize_kernel<<<div_up(pf, 32), 256, 0, st>>>(c, grid, pf, partial, grad_w2, sums, ga, grad_aux_w);
     pe_mlp_backward_params_kernel<<<div_up(c, 128), 128, 0, st>>>(c, (double)rows, use_batch_stats, sums, moments, w1,
                                                                   gamma, s.stats, grad_w1, grad_b1, grad_gamma,
                                                                   grad_beta, grad_b2);

@@ -52,7 +52,10 @@ struct PtrKeys {
 template <typename K, class Load>
 __global__ void __launch_bounds__(kRadixBlock)
 radix_hist_kernel(Load load, int n, int shift, int pass, const int *__restrict__ npass_dev, int tpb,
-                  int *__restrict__ table) {
+                  int *__restrict__ table, int *__restrict__ scan_state, int scan_state_ints) {
+    // the look-back states / tile counter of this pass's scan (launch_exclusive_scan_prezeroed), also when the pass is
+    // skipped: the scan kernel still runs
+    for (int i = blockIdx.x * kRadixBlock + threadIdx.x; i < scan_state_ints; i += gridDim.x * kRadixBlock) scan_state[i] = 0;
     if (npass_dev && pass >= *npass_dev) return;
     __shared__ int hist[kRadixBins];
     for (int d = threadIdx.x; d < kRadixBins; d += kRadixBlock) hist[d] = 0;
@@ -136,7 +139,7 @@ radix_scatter_kernel(Load load, const int *__restrict__ vin, K *__restrict__ kou
 
 // One pass over digit `pass` (bits [11 pass, 11 pass + 11)).  vin == NULL: the values are 0..n-1 (first pass).
 // kout == NULL: keys are not written (last pass when only the permutation is wanted).
-// scratch: radix_scratch_ints(n) ints.  Enqueues 1 memset + 3 kernels.
+// scratch: radix_scratch_ints(n) ints.  Enqueues 3 kernels (the histogram kernel also zeroes the scan's state).
 template <typename K, class Load>
 inline void launch_radix_pass(Load load, const int *vin, K *kout, int *vout, int n, int pass, const int *npass_dev,
                               int *scratch, cudaStream_t st) {
@@ -147,8 +150,9 @@ inline void launch_radix_pass(Load load, const int *vin, K *kout, int *vout, int
     int *partial = scratch + radix_table_ints(n) + 1;
     if ((reinterpret_cast<uintptr_t>(partial) & 7u) != 0) ++partial;  // the scan's states are 64-bit words
     const int shift = pass * kRadixBits;
-    radix_hist_kernel<K, Load><<<blocks, kRadixBlock, 0, st>>>(load, n, shift, pass, npass_dev, tpb, table);
-    launch_exclusive_scan(table, table, entries, partial, st);
+    radix_hist_kernel<K, Load><<<blocks, kRadixBlock, 0, st>>>(load, n, shift, pass, npass_dev, tpb, table, partial,
+                                                              (int)scan_partial_ints(entries));
+    launch_exclusive_scan_prezeroed(table, table, entries, partial, st);
     radix_scatter_kernel<K, Load><<<blocks, kRadixBlock, 0, st>>>(load, vin, kout, vout, n, shift, pass, npass_dev,
                                                                  tpb, table);
 }

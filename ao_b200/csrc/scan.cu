@@ -55,22 +55,36 @@ scan_onepass_kernel(int n, const int *in, int *out, unsigned long long *state, u
     }
     int total;
     const int inc = block_inclusive_scan(sum, warp_sums, &total);
-    if (threadIdx.x == 0) {
+    // Look-back by warp 0, 32 predecessors at a time (a single thread walking back one tile per L2 round trip made
+    // the scan of 1.3 M cell counters take 23 us and every small scan 8-13 us: profiles/r02c_ops_L0_ncu_summary.md).
+    // Lane l polls tile (base - l) until it is published; the nearest tile that already holds an inclusive prefix
+    // ends the walk, the aggregates in front of it are summed.
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
         volatile unsigned long long *st = state;
         int prefix = 0;
         if (tile == 0) {
-            st[0] = kFlagInclusive | (unsigned)total;
+            if (lane == 0) st[0] = kFlagInclusive | (unsigned)total;
         } else {
-            st[tile] = kFlagAggregate | (unsigned)total;
-            for (int p = tile - 1; p >= 0; --p) {
-                unsigned long long s;
-                do { s = st[p]; } while ((s >> 32) == 0);  // predecessor not published yet
-                prefix += (int)(unsigned)(s & 0xffffffffull);
-                if ((s >> 32) == 2) break;
+            if (lane == 0) st[tile] = kFlagAggregate | (unsigned)total;
+            int base = tile - 1;
+            for (;;) {
+                const int p = base - lane;
+                unsigned long long sv = kFlagInclusive;             // tiles before the first: inclusive prefix 0
+                if (p >= 0) { do { sv = st[p]; } while ((sv >> 32) == 0); }
+                const bool inclusive = (sv >> 32) == 2;
+                const unsigned inc_mask = __ballot_sync(0xffffffffu, inclusive);
+                const int first = inc_mask ? __ffs(inc_mask) - 1 : 31;   // nearest predecessor with an inclusive prefix
+                int v = lane <= first ? (int)(unsigned)(sv & 0xffffffffull) : 0;
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+                prefix += v;
+                if (inc_mask) break;
+                base -= 32;
             }
-            st[tile] = kFlagInclusive | (unsigned)(prefix + total);
+            if (lane == 0) st[tile] = kFlagInclusive | (unsigned)(prefix + total);
         }
-        prefix_s = prefix;
+        if (lane == 0) prefix_s = prefix;
     }
     __syncthreads();
     int excl = prefix_s + inc - sum;
@@ -85,7 +99,7 @@ scan_onepass_kernel(int n, const int *in, int *out, unsigned long long *state, u
 
 __global__ void scan_empty_kernel(int *out) { out[0] = 0; }
 
-void launch_exclusive_scan(const int *in, int *out, int n, int *partial, cudaStream_t st) {
+static void launch_scan(const int *in, int *out, int n, int *partial, cudaStream_t st, bool zero) {
     const int tiles = div_up(n, kScanTile);
     if (tiles == 0) {
         scan_empty_kernel<<<1, 1, 0, st>>>(out);
@@ -93,8 +107,13 @@ void launch_exclusive_scan(const int *in, int *out, int n, int *partial, cudaStr
     }
     unsigned long long *state = reinterpret_cast<unsigned long long *>(partial);
     unsigned *counter = reinterpret_cast<unsigned *>(state + tiles + 1);
-    cudaMemsetAsync(partial, 0, sizeof(int) * scan_partial_ints(n), st);
+    if (zero) cudaMemsetAsync(partial, 0, sizeof(int) * scan_partial_ints(n), st);
     scan_onepass_kernel<<<tiles, kScanBlock, 0, st>>>(n, in, out, state, counter);
+}
+
+void launch_exclusive_scan(const int *in, int *out, int n, int *partial, cudaStream_t st) { launch_scan(in, out, n, partial, st, true); }
+void launch_exclusive_scan_prezeroed(const int *in, int *out, int n, int *partial, cudaStream_t st) {
+    launch_scan(in, out, n, partial, st, false);
 }
 
 }  // namespace aopt

@@ -8,7 +8,7 @@
 namespace aopt {
 
 constexpr int kScanBlock = 512;
-constexpr int kScanItems = 4;  // consecutive elements per thread
+constexpr int kScanItems = 8;  // consecutive elements per thread
 constexpr int kScanTile = kScanBlock * kScanItems;
 
 // tile states (one 64-bit word per tile) + the dynamic tile counter
@@ -16,5 +16,8 @@ inline size_t scan_partial_ints(long long n) { return 2 * ((size_t)div_up(n, kSc
 
 // Enqueues one memset and one kernel on `st`; defined in scan.cu.
 void launch_exclusive_scan(const int *in, int *out, int n, int *partial, cudaStream_t st);
+// Same without the memset: the caller guarantees that the scan_partial_ints(n) ints of `partial` were zeroed by an
+// earlier kernel on the stream (radix.cuh: the histogram kernel of the pass does it — one graph node less per pass).
+void launch_exclusive_scan_prezeroed(const int *in, int *out, int n, int *partial, cudaStream_t st);
 
 }  // namespace aopt

@@ -18,7 +18,8 @@ from torch.autograd import Function
 from .. import _lib
 from ._csr import NeighbourCSR, get_csr
 
-_VOXEL_PASSES = 3   # 11-bit radix passes enqueued up front: covers 33 key bits (pool.cu aopt_voxel_grid)
+_VOXEL_PASSES = 3   # 11-bit radix passes enqueued on first sight: covers 33 key bits (pool.cu aopt_voxel_grid)
+_PASSES_NEEDED = {}  # (grid size, scenes) -> passes the last partition needed
 
 
 class VoxelPartition(NamedTuple):
@@ -65,9 +66,15 @@ def voxel_partition(coord, offset, grid_size, start=None) -> VoxelPartition:
             )
         return meta.tolist()                                         # the one host sync (torch.unique has one too)
 
-    m = run(_VOXEL_PASSES)
+    # Passes enqueued: what the previous partition with this (grid size, scene count) needed — the key width is known
+    # only on the device, but it barely moves from one batch to the next, and an unneeded pass still costs its three
+    # launches.  Too few is detected (flag 2) and repaired by a second call.
+    guess = _PASSES_NEEDED.get((float(grid_size), b), _VOXEL_PASSES)
+    m = run(guess)
     if m[1] & 2 and not m[1] & 1:
-        m = run(6)          # key wider than 33 bits (> 8.6e9 cells x scenes): the six-pass sort covers 64 bits
+        m = run(min(6, max(m[2], guess + 1)))
+    if not m[1] & 1:
+        _PASSES_NEEDED[(float(grid_size), b)] = max(1, min(6, m[2]))
     n_vox, flags = m[0], m[1]
     if flags & 1:
         raise ValueError("voxel_partition: a point lies below its scene's `start`, or the voxel grid needs more than "

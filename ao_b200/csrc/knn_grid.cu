@@ -151,10 +151,10 @@ knn_sample_kernel(int b, int nsample, const float *__restrict__ xyz, const int *
 }
 
 // ---- 1b. no density sample: clear only ---------------------------------------------------------------
-// The sampled k-th neighbour distance rarely decides the cell edge: the capacity (cells per point) does for surface
-// scans, and the search is exact for any edge.  With tuning "knn_sample" = 0 (default) the edge comes from the bounding
-// box alone, h = cbrt(volume / capacity) per scene, and this kernel only does the sample kernel's housekeeping
-// (21 us -> 3 us per search, seven searches per step).
+// Experiment kept behind tuning "knn_sample" = 1 (AOPT_KNN_SAMPLE=bbox): cell edge from the bounding box alone,
+// h = cbrt(volume / capacity) per scene, this kernel doing only the sample kernel's housekeeping (21 us -> 3 us per
+// search).  Measured (profiles/r02d_kernel_bench*.txt): the query pays more than the build saves — level-0 self search
+// 426 us vs 328 us with the sampled edge, level 2 185 vs 130 us, the step 8.06 vs 7.91 ms — so the sample stays.
 __global__ void __launch_bounds__(256)
 knn_clear_kernel(int b, int *__restrict__ cells, long long n_cells, unsigned *__restrict__ bb_lo, unsigned *__restrict__ bb_hi) {
     for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n_cells; i += (long long)gridDim.x * 256) cells[i] = 0;
@@ -444,7 +444,7 @@ int knn_grid_launch(int m, int nsample, int n, int b, const float *xyz, const fl
     }
     const bool self = (new_xyz == xyz) && (new_offset == offset) && (m == n);
 
-    const bool sampled = tuning(kTuneKnnSample) == 2;
+    const bool sampled = tuning(kTuneKnnSample) != 1;
     if (!sampled) {
         const long long nc = (long long)w.total_cells + 1;
         knn_clear_kernel<<<stride_grid(nc, 256, 8), 256, 0, st>>>(b, w.cells, nc, w.bbox, w.bbox + 3 * (size_t)b);

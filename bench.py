@@ -364,7 +364,11 @@ class Ctx:
         torch.cuda.set_device(self.local)
         self.dev = torch.device("cuda", self.local)
         if self.world > 1:
-            dist.init_process_group("nccl", device_id=self.dev)
+            import datetime
+
+            # a collective mismatch should fail in minutes, not in the default 10 (every rank holds a GPU meanwhile)
+            dist.init_process_group("nccl", device_id=self.dev,
+                                    timeout=datetime.timedelta(seconds=int(os.environ.get("AOPT_NCCL_TIMEOUT_S", "180"))))
 
     def barrier(self):
         if self.world > 1:
@@ -408,7 +412,7 @@ class GradAllReduce:
             self.pending = False
 
 
-def time_schedule(ctx, sched, coord, offset, steps, warmup, trace_steps, allreduce=None, sampler=None):
+def time_schedule(ctx, sched, coord, offset, steps, warmup, trace_steps, allreduce=None, sampler=None, with_clocks=False):
     """W warm-up steps, then EXACTLY `steps` timed steps between barrier + synchronize, CUDA events on the launching
     stream, max over ranks.  The last `trace_steps` timed steps carry per-call CUDA events (roofline table)."""
     import gc
@@ -426,9 +430,10 @@ def time_schedule(ctx, sched, coord, offset, steps, warmup, trace_steps, allredu
     for _ in range(warmup):
         one_step(coord, offset)
     ctx.barrier()
-    if sampler is not None:
-        sampler.start()
-        time.sleep(0.3)
+    if with_clocks:     # EVERY rank takes this branch (collectives inside); only rank 0 owns a sampler
+        if sampler is not None:
+            sampler.start()
+            time.sleep(0.3)
         ctx.barrier()
         # the GPU idled while the clock sampler started: more untimed steps bring clocks / power state back up
         # (without them the first two or three timed steps run 5-20 % slow)
@@ -520,7 +525,7 @@ def run_b200_arm(args):
 
     # ---- timed region: resident inputs, CUDA events on the launching stream ----------------------------
     sampler = ClockSampler(ctx.local) if rank == 0 else None
-    r = time_schedule(ctx, sched, coord, offset, steps, warmup, TRACE_STEPS, allreduce, sampler)
+    r = time_schedule(ctx, sched, coord, offset, steps, warmup, TRACE_STEPS, allreduce, sampler, with_clocks=True)
     ms_step, sizes, trace, trace_steps, one_step = r["ms_step"], r["sizes"], r["trace"], r["trace_steps"], r["one_step"]
     value = world * n0 / (ms_step * 1e-3) / 1e6
 

@@ -8,7 +8,10 @@ ALG = {  # level-0 algorithmic MB: N=320000, k=16, C=48, G=6; po
     "aopt_gather_sub_forward": ("gather_sub_ns_kernel", 1126.4),
     "aopt_gva_forward": ("gva_forward_ns_kernel", 1372.2),
     "aopt_relation_backward": ("relation_backward_vec_kernel", 1127.7),
+    "aopt_gva_backward": ("gva_backward_fused_ns_kernel", 2438.4),
     "aopt_gva_backward_query": ("gva_backward_query_ns_kernel", 2355.2),
+    "aopt_pe_mlp_forward": ("pe_mlp_forward_tc_kernel", 1052.2),
+    "aopt_pe_mlp_backward": ("pe_mlp_backward_tc_kernel", 1052.2),
     "aopt_gva_backward_value": ("csr_walk_kernel<8, BvPolicy", 267.5),
     "aopt_pool_forward": ("pool_forward_kernel<4>", 167.3),
     "aopt_pool_backward": ("pool_backward_kernel<4>", 162.7),

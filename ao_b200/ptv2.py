@@ -148,12 +148,15 @@ class GroupedVectorAttention(nn.Module):
         import torch.nn.functional as F
 
         lin_e, lin2 = self.weight_encoding[0], self.linear_p_bias[3]
+        # key / query projected by weight_encoding[0]: (N,C) x (C,G) in the autocast dtype, like the Linear it replaces
+        # (in fp32 these two skinny GEMMs ran as SIMT sgemm kernels, 174 us each at level 0:
+        # profiles/r02e_model_step_torch_profile.txt)
+        kp = F.linear(key, lin_e.weight).float()                              # (N, G)
+        qp = F.linear(query, lin_e.weight).float()
         with torch.autocast("cuda", enabled=False):
             we = lin_e.weight.float()                                         # (G, C)
             wf = we @ lin2.weight.float()                                     # (G, C) acting on h
             peb, upe = pointops.pe_bias_mlp(pos, self.linear_p_bias, pos_moments, aux_weight=wf)
-            kp = F.linear(key.float(), we)                                    # (N, G)
-            qp = F.linear(query.float(), we)
             const = lin_e.bias.float() if lin_e.bias is not None else 0.0
             if lin2.bias is not None:
                 const = const + F.linear(lin2.bias.float(), we)

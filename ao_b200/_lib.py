@@ -31,6 +31,7 @@ SIGNATURES = {
     "aopt_offset2batch": (c_int, [c_int, c_int, P, P, P]),
     "aopt_knn_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "aopt_knn_query": (c_int, [c_int, c_int, c_int, c_int, P, P, P, P, P, P, c_int, P, c_size_t, P]),
+    "aopt_knn_query_multi": (c_int, [c_int, c_int, c_int, c_int, P, P, P, P, P, P, P, c_int, P, c_size_t, P]),
     "aopt_farthest_point_sampling": (c_int, [c_int, c_int, P, P, P, P, P, P]),
     "aopt_grid_sample_keys": (c_int, [c_int, P, c_double, c_double, c_double, c_int, c_int, P, P, P, P]),
     "aopt_voxel_pick": (c_int, [c_int, P, P, P, c_longlong, P, P]),

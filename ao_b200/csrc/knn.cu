@@ -207,10 +207,24 @@ extern "C" size_t aopt_knn_workspace_bytes(int n, int m, int b, int nsample, int
     return knn_grid_workspace_bytes(n, m, b);
 }
 
-extern "C" int aopt_knn_query(int m, int nsample, int n, int b, const float *xyz,
-                              const float *new_xyz, const int *offset, const int *new_offset,
-                              int *idx, float *dist2, int method, void *workspace,
-                              size_t workspace_bytes, aopt_stream_t stream) {
+// idx[row, :] -= index_base[scene of row] for the valid entries (the -1 padding stays): the second half of
+// aopt_knn_query_multi.
+__global__ void __launch_bounds__(256)
+knn_rebase_kernel(long long total, int nsample, int b, const int *__restrict__ new_offset,
+                  const int *__restrict__ index_base, int *__restrict__ idx) {
+    const long long step = (long long)gridDim.x * 256;
+    for (long long p = (long long)blockIdx.x * 256 + threadIdx.x; p < total; p += step) {
+        const int row = (int)(p / nsample);
+        const int sc = aopt::find_segment(row, new_offset, b);
+        const int v = idx[p];
+        if (sc < b && v >= 0) idx[p] = v - __ldg(index_base + sc);
+    }
+}
+
+extern "C" int aopt_knn_query_multi(int m, int nsample, int n, int b, const float *xyz,
+                                    const float *new_xyz, const int *offset, const int *new_offset,
+                                    const int *index_base, int *idx, float *dist2, int method, void *workspace,
+                                    size_t workspace_bytes, aopt_stream_t stream) {
     if (m < 0 || n < 0 || b < 0 || nsample < 1 || nsample > AOPT_MAX_NSAMPLE) return AOPT_ERR_INVALID_ARGUMENT;
     const bool root = (method & AOPT_KNN_SQRT_DIST) != 0;   // distances instead of squared distances
     method &= ~AOPT_KNN_SQRT_DIST;
@@ -220,12 +234,26 @@ extern "C" int aopt_knn_query(int m, int nsample, int n, int b, const float *xyz
         return AOPT_ERR_INVALID_ARGUMENT;
     cudaStream_t st = as_stream(stream);
     int use = pick_method(n, m, b, nsample, method);
+    int rc;
     if (use == AOPT_KNN_GRID) {
         if (nsample > 32) return AOPT_ERR_UNSUPPORTED;
         size_t need = knn_grid_workspace_bytes(n, m, b);
         if (!workspace || workspace_bytes < need) return AOPT_ERR_WORKSPACE;
-        return knn_grid_launch(m, nsample, n, b, xyz, new_xyz, offset, new_offset, idx, dist2, root, workspace,
-                               workspace_bytes, st);
+        rc = knn_grid_launch(m, nsample, n, b, xyz, new_xyz, offset, new_offset, idx, dist2, root, workspace,
+                             workspace_bytes, st);
+    } else {
+        rc = knn_tile_launch(m, nsample, n, b, xyz, new_xyz, offset, new_offset, idx, dist2, root, st);
     }
-    return knn_tile_launch(m, nsample, n, b, xyz, new_xyz, offset, new_offset, idx, dist2, root, st);
+    if (rc != AOPT_OK || !index_base || b == 0) return rc;
+    const long long total = (long long)m * nsample;
+    knn_rebase_kernel<<<stride_grid(total, 256, 8), 256, 0, st>>>(total, nsample, b, new_offset, index_base, idx);
+    return check_launch(1);
+}
+
+extern "C" int aopt_knn_query(int m, int nsample, int n, int b, const float *xyz,
+                              const float *new_xyz, const int *offset, const int *new_offset,
+                              int *idx, float *dist2, int method, void *workspace,
+                              size_t workspace_bytes, aopt_stream_t stream) {
+    return aopt_knn_query_multi(m, nsample, n, b, xyz, new_xyz, offset, new_offset, nullptr, idx, dist2, method,
+                                workspace, workspace_bytes, stream);
 }

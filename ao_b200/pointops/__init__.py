@@ -8,7 +8,7 @@ New fused operators for the PTv2 caller: group_xyz, gva_relation, gva_aggregate,
 voxel_partition, unpool_map, interpolation_weights, knn_query_raw, pe_bias_mlp (fused positional-bias MLP),
 pos_moments.
 """
-from .query import knn_query, knn_query_raw, prefetch_knn, ball_query, random_ball_query
+from .query import knn_query, knn_query_raw, knn_query_sets, prefetch_knn, ball_query, random_ball_query
 from .sampling import farthest_point_sampling
 from .grouping import grouping, grouping2
 from .interpolation import interpolation, interpolation2, interpolation_weights

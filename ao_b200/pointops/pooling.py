@@ -164,7 +164,7 @@ def prepare_pyramid(coord, offset, grid_sizes, knn=None, interp_k=None):
 
     knn = k (or one k per coarse level): also start the self neighbour searches of levels 1..L on the geometry
     side stream; interp_k: and the coarse -> fine searches of the interpolation up path (query.prefetch_knn)."""
-    from .query import prefetch_knn
+    from .query import knn_query_sets, prefetch_knn, stash_knn
 
     _lib.require_cuda(coord, offset)
     levels = [(coord, offset)]
@@ -184,13 +184,37 @@ def prepare_pyramid(coord, offset, grid_sizes, knn=None, interp_k=None):
         levels.append((pooled, part.offset))
     if knn is not None or interp_k is not None:
         offs32 = [levels[0][1].int()] + [o.int() for _, o in levels[1:]]
-        for l in range(1, len(levels)):
-            if knn is not None:
-                k = knn[l - 1] if isinstance(knn, (list, tuple)) else knn
-                prefetch_knn(int(k), levels[l][0], offs32[l])
-        if interp_k is not None:
-            for l in reversed(range(1, len(levels))):        # the decoder walks up from the coarsest level
-                prefetch_knn(int(interp_k), levels[l][0], offs32[l], levels[l - 1][0], offs32[l - 1])
+        n_lv = len(levels)
+        ks = None if knn is None else [int(knn[l - 1] if isinstance(knn, (list, tuple)) else knn) for l in range(1, n_lv)]
+        if _lib.overlap(role="knn"):
+            # experiment: one search per level, on the geometry side stream
+            for l in range(1, n_lv):
+                if ks is not None:
+                    prefetch_knn(ks[l - 1], levels[l][0], offs32[l])
+            if interp_k is not None:
+                for l in reversed(range(1, n_lv)):       # the decoder walks up from the coarsest level
+                    prefetch_knn(int(interp_k), levels[l][0], offs32[l], levels[l - 1][0], offs32[l - 1])
+        else:
+            # The coarse levels' searches are independent of each other once the coordinates exist: ONE batched
+            # search per distinct k for the self lists of levels 1..L, ONE for the coarse -> fine searches of the
+            # interpolation up path (query.knn_query_sets).  The results wait on the coordinate tensors for the
+            # knn_query / interpolation calls of the feature path.
+            if ks is not None and n_lv > 2:
+                for k in sorted(set(ks)):
+                    ls = [l for l in range(1, n_lv) if ks[l - 1] == k and levels[l][0].shape[0] > 0]
+                    if len(ls) < 2:
+                        continue
+                    res = knn_query_sets(k, [(levels[l][0], offs32[l], None, None) for l in ls], root=True)
+                    for l, (idx, dist) in zip(ls, res):
+                        stash_knn(k, levels[l][0], None, idx, dist, True)
+            if interp_k is not None and n_lv > 2:
+                ls = [l for l in range(1, n_lv) if levels[l][0].shape[0] > 0 and levels[l - 1][0].shape[0] > 0]
+                if len(ls) >= 2:
+                    res = knn_query_sets(int(interp_k), [(levels[l][0], offs32[l], levels[l - 1][0].float().contiguous()
+                                                           if levels[l - 1][0].dtype != torch.float32 else levels[l - 1][0],
+                                                           offs32[l - 1]) for l in ls], root=False)
+                    for l, (idx, dist2) in zip(ls, res):
+                        stash_knn(int(interp_k), levels[l][0], levels[l - 1][0], idx, dist2, False)
     return levels
 
 

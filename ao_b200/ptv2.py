@@ -444,7 +444,7 @@ class PointTransformerV2(nn.Module):
                 # all voxel partitions + coarse coordinates first: they depend on coordinates only, and they hold
                 # the forward pass's host synchronisations (pointops.prepare_pyramid)
                 pointops.prepare_pyramid(coord, offset, [enc.down.grid_size for enc in self.enc_stages],
-                                         knn=[enc.blocks.neighbours for enc in self.enc_stages],
+                                         knn=[enc.blocks.search_neighbours for enc in self.enc_stages],
                                          interp_k=3 if self.dec_stages[0].up.backend == "interp" else None)
             points = self.patch_embed(points)
             skips = [[points]]

@@ -274,7 +274,7 @@ class PointOpsSchedule:
         lists.append(self._neighbour_lists(0, lv0))
         # the coordinate pyramid (voxel partitions + coarse coordinates: the step's only host syncs) is built while
         # the level-0 search is still running on the device; grid_pool below finds it cached on the coord tensors
-        pointops.prepare_pyramid(coord, offset, cfg.grid_sizes, knn=[cfg.k_enc(i) for i in range(n_stage)],
+        pointops.prepare_pyramid(coord, offset, cfg.grid_sizes, knn=[cfg.level_ks()[i + 1][-1] for i in range(n_stage)],
                                  interp_k=cfg.interp_k if cfg.unpool == "interp" else None)
         for _ in range(cfg.patch_depth):
             self._block_forward(lv0, lists[0][cfg.k_patch()], tape)

@@ -86,6 +86,15 @@ size_t aopt_knn_workspace_bytes(int n, int m, int b, int nsample, int method);
 int aopt_knn_query(int m, int nsample, int n, int b, const float *xyz, const float *new_xyz,
                    const int *offset, const int *new_offset, int *idx, float *dist2, int method,
                    void *workspace, size_t workspace_bytes, aopt_stream_t stream);
+/* The same search over several INDEPENDENT point sets at once: the sets are concatenated scene by scene into one
+ * offset-encoded batch (the search never crosses a scene), and index_base (b,) int32 — may be NULL — is subtracted
+ * from the valid indices of every scene, so that each set gets indices relative to its own first point.  One call
+ * (one grid build, one query launch) instead of one per set: the pyramid levels 1..L of a PTv2m2 forward
+ * (...v2m2_base.py:223 once per BlockSequence; functions/interpolation.py:14 once per unpooling stage). */
+int aopt_knn_query_multi(int m, int nsample, int n, int b, const float *xyz, const float *new_xyz,
+                         const int *offset, const int *new_offset, const int *index_base, int *idx,
+                         float *dist2, int method, void *workspace, size_t workspace_bytes,
+                         aopt_stream_t stream);
 
 /* ---- farthest point sampling (PTv1 caller: point_transformer_seg.py:101) --------------------- */
 /* Arguments of farthest_point_sampling_cuda_launcher (sampling/sampling_cuda_kernel.h): b scenes,

@@ -12,6 +12,10 @@ run() {  # config steps extra...
 }
 run s3dis4 100 --no-variants
 run s3dis8 60 --no-variants
+if [ "${WITH_N1:-0}" = "1" ]; then   # one-GPU lines of the same box (scaling ratio)
+  timeout 300 python bench.py --config s3dis4 --steps 100 --warmup 3 --no-variants --no-model --no-cpu-baseline --no-gpu-reference > $O/bench_s3dis4_n1.json 2> $O/bench_s3dis4_n1.err; head -c 200 $O/bench_s3dis4_n1.json; echo
+  timeout 300 python bench.py --config s3dis8 --steps 60 --warmup 3 --no-variants --no-model --no-cpu-baseline --no-gpu-reference > $O/bench_s3dis8_n1.json 2> $O/bench_s3dis8_n1.err; head -c 200 $O/bench_s3dis8_n1.json; echo
+fi
 cat $O/nccl_*.log 2>/dev/null | grep -i "AllReduce: [0-9]\|NVLS\|via P2P\|Algo\|nranks" | sed 's/^[^ ]* //' | sed 's/0x[0-9a-f]*/PTR/g' | sort | uniq -c | sort -rn | head -40 > $O/nccl_summary.txt
 rm -f $O/nccl_*.log
 head -12 $O/nccl_summary.txt

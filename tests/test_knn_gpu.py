@@ -49,6 +49,29 @@ def test_no_candidates_gives_padding(method):
     assert bool((idx == -1).all()) and bool((d2 == 1e10).all())
 
 
+@pytest.mark.parametrize("method", ["tile", "grid", "auto"])
+def test_batched_sets_equal_one_search_per_set(method):
+    """pointops.knn_query_sets (aopt_knn_query_multi: several point sets concatenated scene by scene, indices rebased per
+    set) returns, bit for bit, what one search per set returns — self lists (k = 16) and coarse -> fine cross lists
+    (k = 3), scenes shorter than k included."""
+    from ao_b200 import pointops, scenes
+
+    sets = []
+    for seed, sizes in ((1, (3000, 7, 2500)), (2, (900, 400, 5)), (3, (60, 33, 12))):
+        coord, _, off = scenes.small_batch(seed, sizes=sizes)
+        sets.append(to_cuda(coord, off))
+    res = pointops.knn_query_sets(16, [(c, o, None, None) for c, o in sets], root=True, method=method)
+    for (c, o), (idx, dist) in zip(sets, res):
+        ri, rd2 = pointops.knn_query_raw(16, c, o, method=method)
+        assert torch.equal(idx, ri) and torch.equal(dist, torch.sqrt(rd2))
+        assert int(idx.max()) < c.shape[0]
+    cross = [(sets[l][0], sets[l][1], sets[l - 1][0], sets[l - 1][1]) for l in (1, 2)]
+    res = pointops.knn_query_sets(3, cross, root=False, method=method)
+    for (c, o, q, qo), (idx, d2) in zip(cross, res):
+        ri, rd2 = pointops.knn_query_raw(3, c, o, q, qo, method=method)
+        assert torch.equal(idx, ri) and torch.equal(d2, rd2)
+
+
 @pytest.mark.parametrize("method", ["tile", "grid"])
 def test_bigk_and_many_scenes(oracle, method):
     rng = np.random.default_rng(1)

@@ -113,3 +113,26 @@ def test_shim_against_reference_launchers(oracle):
         assert torch.equal(sub, ref_cuda.subtraction_forward(inp, inp2, idx))
         q1, q2 = ref_cuda.subtraction_backward(idx, go, m)
         assert torch.allclose(g1, q1, rtol=1e-5, atol=1e-5) and torch.allclose(g2, q2, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.gpu
+def test_reused_index_buffer_does_not_keep_a_stale_transposed_graph():
+    """A caller that refills ONE preallocated idx buffer (the reference's pattern: query.py:19 allocates, the launcher
+    writes through the raw pointer) must get gradients of the NEW neighbour lists: the library's writes do not bump
+    the tensor version, so `_C.knn_query_cuda` drops the transposed graph cached on the buffer."""
+    from ao_b200 import scenes
+    from ao_b200.pointops import _C
+
+    c, k = 12, 8
+    idx = torch.zeros((1500, k), dtype=torch.int32, device="cuda")
+    d2 = torch.zeros((1500, k), dtype=torch.float32, device="cuda")
+    for seed in (21, 22):
+        coord, _, offset = scenes.small_batch(seed, sizes=(700, 800))
+        xyz, off = to_cuda(coord, offset)
+        m = xyz.shape[0]
+        _C.knn_query_cuda(m, k, xyz, xyz, off, off, idx, d2)
+        go = torch.randn(m, k, c, device="cuda")
+        gi = torch.zeros(m, c, device="cuda")
+        _C.grouping_backward_cuda(m, k, c, go, idx, gi)      # builds (and caches) the CSR of the current idx
+        ref = torch.zeros(m, c, device="cuda").index_add_(0, idx.view(-1).long(), go.view(-1, c))
+        assert torch.allclose(gi, ref, rtol=1e-5, atol=1e-5), f"stale CSR after refill (seed {seed})"

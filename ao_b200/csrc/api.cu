@@ -22,7 +22,7 @@ int check_launch(int kernels) {
 
 static std::atomic<int> g_tuning[kTuneCount];
 static std::atomic<bool> g_tuning_init{false};
-static const char *const kTuneNames[kTuneCount] = {"csr_impl", "gva_bwd", "voxel_sort", "pe_fwd", "pe_bwd", "knn_sample", nullptr, nullptr};
+static const char *const kTuneNames[kTuneCount] = {"csr_impl", "gva_bwd", "voxel_sort", "pe_fwd", "pe_bwd", "knn_sample", "pdl", nullptr};
 
 static void tuning_init() {
     if (g_tuning_init.exchange(true)) return;
@@ -37,6 +37,7 @@ static void tuning_init() {
     g_tuning[kTunePeFwd] = env("AOPT_PE_FWD", "tcgen05", "mma");
     g_tuning[kTunePeBwd] = env("AOPT_PE_BWD", "tcgen05", "mma");
     g_tuning[kTuneKnnSample] = env("AOPT_KNN_SAMPLE", "bbox", "sampled");
+    g_tuning[kTunePdl] = env("AOPT_PDL", "1", "0");
 }
 
 int tuning(int which) {

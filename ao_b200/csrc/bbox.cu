@@ -13,6 +13,8 @@ scene_bbox_kernel(int n, int b, const float *__restrict__ xyz, const int *__rest
                   unsigned *__restrict__ lo, unsigned *__restrict__ hi) {
     __shared__ float red[6][kBboxBlock / 32];
     __shared__ int seg_s[2];
+    pdl_wait();      // chained launch from the kNN grid build (no-op otherwise)
+    pdl_trigger();
     const int base = blockIdx.x * kBboxChunk;
     const int last = min(base + kBboxChunk, n) - 1;
     if (threadIdx.x < 2) seg_s[threadIdx.x] = find_segment(threadIdx.x == 0 ? base : last, offset, b);
@@ -109,15 +111,15 @@ scene_bbox_kernel(int n, int b, const float *__restrict__ xyz, const int *__rest
 }
 
 void launch_scene_bbox(int n, int b, const float *xyz, const int *offset, unsigned *lo, unsigned *hi,
-                       cudaStream_t st, bool init) {
+                       cudaStream_t st, bool init, bool pdl) {
     if (init) {
         cudaMemsetAsync(lo, 0xff, sizeof(unsigned) * 3 * (size_t)b, st);
         if (hi) cudaMemsetAsync(hi, 0x00, sizeof(unsigned) * 3 * (size_t)b, st);
     }
     if (n <= 0) return;
     const int grid = div_up(n, kBboxChunk);
-    if (hi) scene_bbox_kernel<true><<<grid, kBboxBlock, 0, st>>>(n, b, xyz, offset, lo, hi);
-    else scene_bbox_kernel<false><<<grid, kBboxBlock, 0, st>>>(n, b, xyz, offset, lo, hi);
+    if (hi) launch_chain(pdl, scene_bbox_kernel<true>, grid, kBboxBlock, 0, st, n, b, xyz, offset, lo, hi);
+    else launch_chain(pdl, scene_bbox_kernel<false>, grid, kBboxBlock, 0, st, n, b, xyz, offset, lo, hi);
 }
 
 }  // namespace aopt

@@ -22,6 +22,6 @@ constexpr unsigned kBboxEmptyHi = 0u;
 // init = false: the caller has already set lo to 0xffffffff and hi to 0 on this stream (the grid kNN folds
 // that into its sample kernel: three fewer memset nodes per search).
 void launch_scene_bbox(int n, int b, const float *xyz, const int *offset, unsigned *lo, unsigned *hi,
-                       cudaStream_t st, bool init = true);
+                       cudaStream_t st, bool init = true, bool pdl = false);
 
 }  // namespace aopt

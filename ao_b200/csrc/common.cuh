@@ -24,8 +24,37 @@ enum Tuning { kTuneCsrImpl = 0,   // AOPT_CSR_IMPL:   1 = radix sort, 2 = count 
               kTunePeFwd = 3,     // AOPT_PE_FWD:     1 = tcgen05 / TMEM kernel, 2 = mma.sync kernel
               kTunePeBwd = 4,     // AOPT_PE_BWD:     1 = tcgen05 / TMEM kernel, 2 = mma.sync kernel
               kTuneKnnSample = 5, // AOPT_KNN_SAMPLE: 1 = cell edge from the bounding box (no density sample), 0 / 2 = sampled r_k (default)
+              kTunePdl = 6,       // AOPT_PDL:        1 = programmatic dependent launch inside the small-kernel chains, 2 = off
               kTuneCount = 8 };
 int tuning(int which);
+
+// ---- programmatic dependent launch (PDL) for chains of small dependent kernels -----------------------------------
+// A kernel launched with launch_chain(pdl = true, ...) may be scheduled while its predecessor on the stream is still
+// running; it MUST call pdl_wait() before it touches global memory (the wait returns once the predecessor grid has
+// completed and its writes are visible; it is a no-op for a normally launched kernel).  pdl_trigger() in the
+// predecessor lets the dependent grid start launching early.  What overlaps is launch latency and ramp-up, which is most
+// of what a 4-8 us kernel costs.  Tuning "pdl" (AOPT_PDL): 1 = on, 2 = off.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline void launch_chain(bool pdl, void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, Args... args) {
+    if (!pdl) {
+        kernel<<<grid, block, smem, st>>>(static_cast<KArgs>(args)...);
+        return;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid, 1, 1);
+    cfg.blockDim = dim3((unsigned)block, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 inline cudaStream_t as_stream(aopt_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 

@@ -65,7 +65,10 @@ __device__ __forceinline__ int wrap_index(int j, int n_src, int negative_mode) {
 // that the fill needs no second round of atomics (it was 70 us of the 165 us level-0 build).
 __global__ void __launch_bounds__(kBlock)
 csr_count_kernel(long long n_entries, int n_src, int negative_mode, const int *__restrict__ idx,
-                 int *__restrict__ count, int *__restrict__ slot) {
+                 int *__restrict__ count, int *__restrict__ slot, int *__restrict__ scan_state, int scan_state_ints) {
+    pdl_trigger();
+    // the look-back states of the scan that follows (launch_exclusive_scan_chained): zeroed here, one memset node less
+    for (int i = blockIdx.x * kBlock + threadIdx.x; i < scan_state_ints; i += gridDim.x * kBlock) scan_state[i] = 0;
     const long long step = (long long)gridDim.x * kBlock;
     for (long long p = (long long)blockIdx.x * kBlock + threadIdx.x; p < n_entries; p += step) {
         int j = wrap_index(__ldg(idx + p), n_src, negative_mode);
@@ -76,6 +79,8 @@ csr_count_kernel(long long n_entries, int n_src, int negative_mode, const int *_
 __global__ void __launch_bounds__(kBlock)
 csr_fill_kernel(long long n_entries, int n_src, int negative_mode, const int *__restrict__ idx,
                 const int *__restrict__ rowptr, const int *__restrict__ slot, int *__restrict__ tmp) {
+    pdl_wait();
+    pdl_trigger();
     const long long step = (long long)gridDim.x * kBlock;
     for (long long p = (long long)blockIdx.x * kBlock + threadIdx.x; p < n_entries; p += step) {
         int j = wrap_index(__ldg(idx + p), n_src, negative_mode);
@@ -87,6 +92,7 @@ csr_fill_kernel(long long n_entries, int n_src, int negative_mode, const int *__
 __global__ void __launch_bounds__(kBlock)
 csr_rank_kernel(int n_src, int negative_mode, const int *__restrict__ idx,
                 const int *__restrict__ rowptr, const int *__restrict__ tmp, int *__restrict__ perm) {
+    pdl_wait();
     const int total = __ldg(rowptr + n_src);
     const int step = gridDim.x * kBlock;
     for (int e = blockIdx.x * kBlock + threadIdx.x; e < total; e += step) {
@@ -181,12 +187,18 @@ extern "C" int aopt_csr_build(int n_src, int64_t n_entries, const int *idx, int 
     int *partial = reinterpret_cast<int *>(ws);
 
     cudaMemsetAsync(count, 0, ((size_t)n_src + 1) * 4, st);
-    if (n_entries > 0)
-        csr_count_kernel<<<stride_grid(n_entries, kBlock, 8), kBlock, 0, st>>>(n_entries, n_src, negative_mode, idx, count, slot);
-    launch_exclusive_scan(count, rowptr, n_src, partial, st);   // rowptr[n_src] = number of kept entries
-    if (n_entries > 0) {
-        csr_fill_kernel<<<stride_grid(n_entries, kBlock, 8), kBlock, 0, st>>>(n_entries, n_src, negative_mode, idx, rowptr, slot, tmp);
-        csr_rank_kernel<<<stride_grid(n_entries, kBlock, 8), kBlock, 0, st>>>(n_src, negative_mode, idx, rowptr, tmp, perm);
+    if (n_entries == 0) {
+        launch_exclusive_scan(count, rowptr, n_src, partial, st);
+        return check_launch(1);
     }
+    // count -> scan -> fill -> rank as a chain of programmatic dependent launches (tuning "pdl")
+    const bool pdl = tuning(kTunePdl) != 2;
+    const int grid = stride_grid(n_entries, kBlock, 8);
+    csr_count_kernel<<<grid, kBlock, 0, st>>>(n_entries, n_src, negative_mode, idx, count, slot, partial,
+                                              (int)scan_partial_ints(n_src));
+    launch_exclusive_scan_chained(count, rowptr, n_src, partial, st, pdl);   // rowptr[n_src] = number of kept entries
+    launch_chain(pdl, csr_fill_kernel, grid, kBlock, 0, st, n_entries, n_src, negative_mode, idx, (const int *)rowptr,
+                 (const int *)slot, tmp);
+    launch_chain(pdl, csr_rank_kernel, grid, kBlock, 0, st, n_src, negative_mode, idx, (const int *)rowptr, (const int *)tmp, perm);
     return check_launch(n_entries > 0 ? 4 : 1);  // count, scan, fill, rank
 }

@@ -212,6 +212,7 @@ extern "C" size_t aopt_knn_workspace_bytes(int n, int m, int b, int nsample, int
 __global__ void __launch_bounds__(256)
 knn_rebase_kernel(long long total, int nsample, int b, const int *__restrict__ new_offset,
                   const int *__restrict__ index_base, int *__restrict__ idx) {
+    aopt::pdl_wait();
     const long long step = (long long)gridDim.x * 256;
     for (long long p = (long long)blockIdx.x * 256 + threadIdx.x; p < total; p += step) {
         const int row = (int)(p / nsample);

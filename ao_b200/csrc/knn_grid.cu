@@ -84,6 +84,7 @@ knn_sample_kernel(int b, int nsample, const float *__restrict__ xyz, const int *
                   float *__restrict__ samples, int *__restrict__ cells, long long n_cells,
                   unsigned *__restrict__ bb_lo, unsigned *__restrict__ bb_hi) {
     __shared__ float wmin[kSampleBlock / 32];
+    pdl_trigger();
     // first kernel of the search on the stream: it also clears the cell counters and resets the bounding boxes
     // (work the following kernels need done; three memset nodes less per search)
     for (long long i = (long long)blockIdx.x * kSampleBlock + threadIdx.x; i < n_cells; i += (long long)gridDim.x * kSampleBlock)
@@ -170,6 +171,8 @@ __global__ void __launch_bounds__(128)
 grid_setup_kernel(int b, int n, const int *__restrict__ offset, const unsigned *__restrict__ bb_lo,
                   const unsigned *__restrict__ bb_hi, const float *__restrict__ samples, float cell_scale,
                   int kCellsPerPoint, GridDesc *__restrict__ desc) {
+    pdl_wait();
+    pdl_trigger();
     const int sc = blockIdx.x * 4 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (sc >= b) return;
@@ -235,7 +238,10 @@ grid_setup_kernel(int b, int n, const int *__restrict__ offset, const unsigned *
 __global__ void __launch_bounds__(256)
 grid_count_kernel(int n, int b, const float *__restrict__ xyz, const int *__restrict__ offset,
                   const GridDesc *__restrict__ desc, int *__restrict__ cells,
-                  int *__restrict__ point_cell, int *__restrict__ point_slot) {
+                  int *__restrict__ point_cell, int *__restrict__ point_slot, int *__restrict__ scan_state, int scan_state_ints) {
+    pdl_wait();
+    pdl_trigger();
+    for (int t = blockIdx.x * 256 + threadIdx.x; t < scan_state_ints; t += gridDim.x * 256) scan_state[t] = 0;
     const int i = blockIdx.x * 256 + threadIdx.x;
     if (i >= n) return;
     const int sc = find_segment(i, offset, b);
@@ -254,6 +260,8 @@ __global__ void __launch_bounds__(256)
 grid_fill_kernel(int n, const float *__restrict__ xyz, const int *__restrict__ cells,
                  const int *__restrict__ point_cell, const int *__restrict__ point_slot,
                  float4 *__restrict__ sorted) {
+    pdl_wait();
+    pdl_trigger();
     const int i = blockIdx.x * 256 + threadIdx.x;
     if (i >= n) return;
     const int cell = point_cell[i];
@@ -297,6 +305,7 @@ knn_grid_kernel(int m, int b, int nsample, const float *__restrict__ new_xyz,
                 const int *__restrict__ new_offset, const GridDesc *__restrict__ desc,
                 const int *__restrict__ cells, const float4 *__restrict__ sorted,
                 int *__restrict__ idx_out, float *__restrict__ dist2_out, bool root) {
+    pdl_wait();
     const int t = blockIdx.x * kQueryBlock + threadIdx.x;
     if (t >= m) return;
     const int sc = find_segment(t, new_offset, b);
@@ -415,12 +424,13 @@ template <int K>
 static void launch_query(bool self, int m, int b, int nsample, const float *new_xyz, const int *new_offset,
                          const GridWs &w, int *idx, float *dist2, bool root, cudaStream_t st) {
     const int grid = div_up(m, kQueryBlock);
+    const bool pdl = tuning(kTunePdl) != 2;
     if (self)
-        knn_grid_kernel<K, true><<<grid, kQueryBlock, 0, st>>>(m, b, nsample, new_xyz, new_offset, w.desc, w.cells,
-                                                               w.sorted, idx, dist2, root);
+        launch_chain(pdl, knn_grid_kernel<K, true>, grid, kQueryBlock, 0, st, m, b, nsample, new_xyz, new_offset,
+                     (const GridDesc *)w.desc, (const int *)w.cells, (const float4 *)w.sorted, idx, dist2, root);
     else
-        knn_grid_kernel<K, false><<<grid, kQueryBlock, 0, st>>>(m, b, nsample, new_xyz, new_offset, w.desc, w.cells,
-                                                                w.sorted, idx, dist2, root);
+        launch_chain(pdl, knn_grid_kernel<K, false>, grid, kQueryBlock, 0, st, m, b, nsample, new_xyz, new_offset,
+                     (const GridDesc *)w.desc, (const int *)w.cells, (const float4 *)w.sorted, idx, dist2, root);
 }
 
 template <int K>
@@ -455,12 +465,17 @@ int knn_grid_launch(int m, int nsample, int n, int b, const float *xyz, const fl
     else if (nsample <= 8) launch_sample<8>(b, nsample, xyz, offset, w, st);
     else if (nsample <= 16) launch_sample<16>(b, nsample, xyz, offset, w, st);
     else launch_sample<32>(b, nsample, xyz, offset, w, st);
-    launch_scene_bbox(n, b, xyz, offset, w.bbox, w.bbox + 3 * (size_t)b, st, /*init=*/false);
-    grid_setup_kernel<<<div_up(b, 4), 128, 0, st>>>(b, n, offset, w.bbox, w.bbox + 3 * (size_t)b, sampled ? w.samples : nullptr, scale,
-                                                    cells_per_point(), w.desc);
-    grid_count_kernel<<<div_up(n, 256), 256, 0, st>>>(n, b, xyz, offset, w.desc, w.cells, w.point_cell, w.point_slot);
-    launch_exclusive_scan(w.cells, w.cells, (int)w.total_cells, w.partial, st);
-    grid_fill_kernel<<<div_up(n, 256), 256, 0, st>>>(n, xyz, w.cells, w.point_cell, w.point_slot, w.sorted);
+    // sample -> bbox -> setup -> count -> scan -> fill -> query: one chain of programmatic dependent launches
+    const bool pdl = tuning(kTunePdl) != 2;
+    launch_scene_bbox(n, b, xyz, offset, w.bbox, w.bbox + 3 * (size_t)b, st, /*init=*/false, pdl);
+    launch_chain(pdl, grid_setup_kernel, div_up(b, 4), 128, 0, st, b, n, offset, (const unsigned *)w.bbox,
+                 (const unsigned *)(w.bbox + 3 * (size_t)b), (const float *)(sampled ? w.samples : nullptr), scale,
+                 cells_per_point(), w.desc);
+    launch_chain(pdl, grid_count_kernel, div_up(n, 256), 256, 0, st, n, b, xyz, offset, (const GridDesc *)w.desc, w.cells,
+                 w.point_cell, w.point_slot, w.partial, (int)scan_partial_ints((long long)w.total_cells));
+    launch_exclusive_scan_chained(w.cells, w.cells, (int)w.total_cells, w.partial, st, pdl);
+    launch_chain(pdl, grid_fill_kernel, div_up(n, 256), 256, 0, st, n, xyz, (const int *)w.cells, (const int *)w.point_cell,
+                 (const int *)w.point_slot, w.sorted);
     if (nsample <= 1) launch_query<1>(self, m, b, nsample, new_xyz, new_offset, w, idx, dist2, root, st);
     else if (nsample <= 3) launch_query<3>(self, m, b, nsample, new_xyz, new_offset, w, idx, dist2, root, st);
     else if (nsample <= 4) launch_query<4>(self, m, b, nsample, new_xyz, new_offset, w, idx, dist2, root, st);

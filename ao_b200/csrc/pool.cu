@@ -239,6 +239,8 @@ __global__ void __launch_bounds__(128)
 voxel_layout_kernel(int b, const unsigned *__restrict__ lo, const unsigned *__restrict__ hi,
                     const float *__restrict__ start_in, float grid_size, int max_passes,
                     float *__restrict__ start, int *__restrict__ meta) {
+    pdl_wait();
+    pdl_trigger();
     __shared__ long long cell_max[3];
     if (threadIdx.x < 3) cell_max[threadIdx.x] = 0;
     __syncthreads();
@@ -275,6 +277,8 @@ __global__ void __launch_bounds__(kPoolBlock)
 voxel_ckeys_kernel(int n, int b, const float *__restrict__ coord, const int *__restrict__ offset,
                    const float *__restrict__ start, float grid_size, unsigned long long *__restrict__ keys,
                    int *__restrict__ meta) {
+    pdl_wait();
+    pdl_trigger();
     const int i = blockIdx.x * kPoolBlock + threadIdx.x;
     if (i >= n) return;
     int sc = find_segment(i, offset, b);
@@ -303,7 +307,10 @@ voxel_ckeys_kernel(int n, int b, const float *__restrict__ coord, const int *__r
 // result of the sort: buffer P after an odd number of passes, Q after an even number
 __global__ void __launch_bounds__(kPoolBlock)
 voxel_mark2_kernel(int n, const unsigned long long *__restrict__ kp, const unsigned long long *__restrict__ kq,
-                   const int *__restrict__ meta, int *__restrict__ flag) {
+                   const int *__restrict__ meta, int *__restrict__ flag, int *__restrict__ scan_state, int scan_state_ints) {
+    pdl_wait();
+    pdl_trigger();
+    for (int t = blockIdx.x * kPoolBlock + threadIdx.x; t < scan_state_ints; t += gridDim.x * kPoolBlock) scan_state[t] = 0;
     const int i = blockIdx.x * kPoolBlock + threadIdx.x;
     if (i >= n) return;
     const unsigned long long *sorted_keys = (meta[2] & 1) ? kp : kq;
@@ -315,6 +322,7 @@ voxel_finalize2_kernel(int n, int b, const int *__restrict__ vp, const int *__re
                        const int *__restrict__ flag, const int *__restrict__ scan, const int *__restrict__ offset,
                        int *__restrict__ order32, int *__restrict__ cluster32, int64_t *__restrict__ cluster64,
                        int *__restrict__ idx_ptr, int64_t *__restrict__ new_offset, int *__restrict__ meta) {
+    pdl_wait();
     const int i = blockIdx.x * kPoolBlock + threadIdx.x;
     const int n_vox = __ldg(scan + n);
     const int *order = (meta[2] & 1) ? vp : vq;
@@ -435,24 +443,30 @@ extern "C" int aopt_voxel_grid(int n, int b, const float *coord, const int *offs
     int *scratch = reinterpret_cast<int *>(ws); ws += a256(4 * radix_scratch_ints(n) + 16);
     int *partial = reinterpret_cast<int *>(ws);
 
+    // bbox -> layout -> keys -> (histogram, scan, scatter) x passes -> mark -> scan -> finalize: one chain of programmatic
+    // dependent launches (tuning "pdl"; every kernel of the chain starts with pdl_wait())
+    const bool pdl = tuning(kTunePdl) != 2;
     launch_scene_bbox(n, b, coord, offset, lo, hi, st);
-    voxel_layout_kernel<<<1, 128, 0, st>>>(b, lo, hi, start, grid_size, max_passes, start_f, meta);
-    voxel_ckeys_kernel<<<div_up(n, kPoolBlock), kPoolBlock, 0, st>>>(n, b, coord, offset, start_f, grid_size, k0, meta);
+    launch_chain(pdl, voxel_layout_kernel, 1, 128, 0, st, b, (const unsigned *)lo, (const unsigned *)hi, start, grid_size,
+                 max_passes, start_f, meta);
+    launch_chain(pdl, voxel_ckeys_kernel, div_up(n, kPoolBlock), kPoolBlock, 0, st, n, b, coord, offset, (const float *)start_f,
+                 grid_size, k0, meta);
     const int *npass_dev = meta + 2;
     for (int pass = 0; pass < max_passes; ++pass) {
         unsigned long long *kout = (pass & 1) ? kq : kp;
         int *vout = (pass & 1) ? vq : vp;
         if (pass == 0)
-            launch_radix_pass<unsigned long long>(PtrKeys<unsigned long long>{k0}, nullptr, kout, vout, n, pass, npass_dev, scratch, st);
+            launch_radix_pass<unsigned long long>(PtrKeys<unsigned long long>{k0}, nullptr, kout, vout, n, pass, npass_dev, scratch, st, pdl);
         else
             launch_radix_pass<unsigned long long>(PtrKeys<unsigned long long>{(pass & 1) ? kp : kq}, (pass & 1) ? vp : vq, kout, vout,
-                                                  n, pass, npass_dev, scratch, st);
+                                                  n, pass, npass_dev, scratch, st, pdl);
     }
     const int grid = div_up(n > b ? n : b, kPoolBlock);
-    voxel_mark2_kernel<<<div_up(n, kPoolBlock), kPoolBlock, 0, st>>>(n, kp, kq, meta, flag);
-    launch_exclusive_scan(flag, scan, n, partial, st);
-    voxel_finalize2_kernel<<<grid, kPoolBlock, 0, st>>>(n, b, vp, vq, flag, scan, offset, order32, cluster32, cluster64,
-                                                        idx_ptr, new_offset, meta);
+    launch_chain(pdl, voxel_mark2_kernel, div_up(n, kPoolBlock), kPoolBlock, 0, st, n, (const unsigned long long *)kp,
+                 (const unsigned long long *)kq, (const int *)meta, flag, partial, (int)scan_partial_ints(n));
+    launch_exclusive_scan_chained(flag, scan, n, partial, st, pdl);
+    launch_chain(pdl, voxel_finalize2_kernel, grid, kPoolBlock, 0, st, n, b, (const int *)vp, (const int *)vq, (const int *)flag,
+                 (const int *)scan, offset, order32, cluster32, cluster64, idx_ptr, new_offset, meta);
     return check_launch(6 + max_passes * kRadixLaunchesPerPass);
 }
 

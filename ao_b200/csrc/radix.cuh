@@ -53,6 +53,8 @@ template <typename K, class Load>
 __global__ void __launch_bounds__(kRadixBlock)
 radix_hist_kernel(Load load, int n, int shift, int pass, const int *__restrict__ npass_dev, int tpb,
                   int *__restrict__ table, int *__restrict__ scan_state, int scan_state_ints) {
+    pdl_wait();      // chained launches (launch_radix_pass with pdl): no-op otherwise
+    pdl_trigger();
     // the look-back states / tile counter of this pass's scan (launch_exclusive_scan_prezeroed), also when the pass is
     // skipped: the scan kernel still runs
     for (int i = blockIdx.x * kRadixBlock + threadIdx.x; i < scan_state_ints; i += gridDim.x * kRadixBlock) scan_state[i] = 0;
@@ -73,6 +75,8 @@ __global__ void __launch_bounds__(kRadixBlock)
 radix_scatter_kernel(Load load, const int *__restrict__ vin, K *__restrict__ kout, int *__restrict__ vout, int n,
                      int shift, int pass, const int *__restrict__ npass_dev, int tpb,
                      const int *__restrict__ table) {
+    pdl_wait();
+    pdl_trigger();
     if (npass_dev && pass >= *npass_dev) return;
     __shared__ unsigned short whist[kRadixWarps][kRadixBins];  // keys of the digit seen so far by the warp (<= 256)
     __shared__ unsigned short tile_count[kRadixBins];          // keys of the digit in the current tile (<= 2048)
@@ -142,7 +146,7 @@ radix_scatter_kernel(Load load, const int *__restrict__ vin, K *__restrict__ kou
 // scratch: radix_scratch_ints(n) ints.  Enqueues 3 kernels (the histogram kernel also zeroes the scan's state).
 template <typename K, class Load>
 inline void launch_radix_pass(Load load, const int *vin, K *kout, int *vout, int n, int pass, const int *npass_dev,
-                              int *scratch, cudaStream_t st) {
+                              int *scratch, cudaStream_t st, bool pdl = false) {
     if (n <= 0) return;
     const int tpb = radix_tiles_per_block(n), blocks = radix_blocks(n);
     int *table = scratch;
@@ -150,11 +154,11 @@ inline void launch_radix_pass(Load load, const int *vin, K *kout, int *vout, int
     int *partial = scratch + radix_table_ints(n) + 1;
     if ((reinterpret_cast<uintptr_t>(partial) & 7u) != 0) ++partial;  // the scan's states are 64-bit words
     const int shift = pass * kRadixBits;
-    radix_hist_kernel<K, Load><<<blocks, kRadixBlock, 0, st>>>(load, n, shift, pass, npass_dev, tpb, table, partial,
-                                                              (int)scan_partial_ints(entries));
-    launch_exclusive_scan_prezeroed(table, table, entries, partial, st);
-    radix_scatter_kernel<K, Load><<<blocks, kRadixBlock, 0, st>>>(load, vin, kout, vout, n, shift, pass, npass_dev,
-                                                                 tpb, table);
+    launch_chain(pdl, radix_hist_kernel<K, Load>, blocks, kRadixBlock, 0, st, load, n, shift, pass, npass_dev, tpb, table,
+                 partial, (int)scan_partial_ints(entries));
+    launch_exclusive_scan_chained(table, table, entries, partial, st, pdl);
+    launch_chain(pdl, radix_scatter_kernel<K, Load>, blocks, kRadixBlock, 0, st, load, vin, kout, vout, n, shift, pass,
+                 npass_dev, tpb, (const int *)table);
 }
 constexpr int kRadixLaunchesPerPass = 3;
 

@@ -42,6 +42,8 @@ __global__ void __launch_bounds__(kScanBlock)
 scan_onepass_kernel(int n, const int *in, int *out, unsigned long long *state, unsigned *counter) {
     __shared__ int warp_sums[kScanBlock / 32];
     __shared__ int tile_s, prefix_s;
+    pdl_wait();      // no-op unless launched as a programmatic dependent (launch_exclusive_scan_chained)
+    pdl_trigger();
     if (threadIdx.x == 0) tile_s = (int)atomicAdd(counter, 1u);
     __syncthreads();
     const int tile = tile_s;
@@ -112,6 +114,16 @@ static void launch_scan(const int *in, int *out, int n, int *partial, cudaStream
 }
 
 void launch_exclusive_scan(const int *in, int *out, int n, int *partial, cudaStream_t st) { launch_scan(in, out, n, partial, st, true); }
+void launch_exclusive_scan_chained(const int *in, int *out, int n, int *partial, cudaStream_t st, bool pdl) {
+    const int tiles = div_up(n, kScanTile);
+    if (tiles == 0) {
+        scan_empty_kernel<<<1, 1, 0, st>>>(out);
+        return;
+    }
+    unsigned long long *state = reinterpret_cast<unsigned long long *>(partial);
+    unsigned *counter = reinterpret_cast<unsigned *>(state + tiles + 1);
+    launch_chain(pdl, scan_onepass_kernel, tiles, kScanBlock, 0, st, n, in, out, state, counter);
+}
 void launch_exclusive_scan_prezeroed(const int *in, int *out, int n, int *partial, cudaStream_t st) {
     launch_scan(in, out, n, partial, st, false);
 }

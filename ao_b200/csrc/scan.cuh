@@ -19,5 +19,7 @@ void launch_exclusive_scan(const int *in, int *out, int n, int *partial, cudaStr
 // Same without the memset: the caller guarantees that the scan_partial_ints(n) ints of `partial` were zeroed by an
 // earlier kernel on the stream (radix.cuh: the histogram kernel of the pass does it — one graph node less per pass).
 void launch_exclusive_scan_prezeroed(const int *in, int *out, int n, int *partial, cudaStream_t st);
+// Pre-zeroed state as above, launched inside a chain of programmatic dependent launches when pdl is true (common.cuh).
+void launch_exclusive_scan_chained(const int *in, int *out, int n, int *partial, cudaStream_t st, bool pdl);
 
 }  // namespace aopt

@@ -407,12 +407,23 @@ pe_mlp_forward_tc_kernel(long long rows, const float *__restrict__ pos, const fl
 
     const long long n_tiles = (rows + kTcBlock - 1) / kTcBlock;
     uint32_t phase = 0;
+    // position of this thread's row in the NEXT tile, requested one tile ahead (its latency used to sit at the head of
+    // every tile, in front of the whole serial produce -> MMA -> epilogue chain)
+    float nx = 0.f, ny = 0.f, nz = 0.f;
+    {
+        const long long g0 = (long long)blockIdx.x * kTcBlock + tid;
+        if (blockIdx.x < n_tiles && g0 < rows) { nx = __ldg(pos + g0 * 3); ny = __ldg(pos + g0 * 3 + 1); nz = __ldg(pos + g0 * 3 + 2); }
+    }
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const long long gr = tile * kTcBlock + tid;
         const bool live = gr < rows;
         // ---- A: hidden activations of this thread's row, 8 channels (16 bytes) at a time ----
-        float px = 0.f, py = 0.f, pz = 0.f;
-        if (live) { px = __ldg(pos + gr * 3); py = __ldg(pos + gr * 3 + 1); pz = __ldg(pos + gr * 3 + 2); }
+        const float px = nx, py = ny, pz = nz;
+        {
+            const long long gn = (tile + gridDim.x) * kTcBlock + tid;
+            nx = ny = nz = 0.f;
+            if (tile + gridDim.x < n_tiles && gn < rows) { nx = __ldg(pos + gn * 3); ny = __ldg(pos + gn * 3 + 1); nz = __ldg(pos + gn * 3 + 2); }
+        }
         // the A tile shares its memory with the staged output rows of the previous tile: every thread's bulk copy must
         // have finished READING before anybody writes A (each thread waits for its own copy, the barrier below joins them)
         bulk_store_wait_read();
@@ -816,20 +827,33 @@ pe_mlp_backward_tc_kernel(long long rows, const float *__restrict__ pos, const f
     const long long n_tiles = (rows + kTcBlock - 1) / kTcBlock;
     uint32_t phase = 0;
     bool first = true;
+    // The gradient tile of the NEXT iteration, in registers: C/4 coalesced 128-bit loads per lane, issued right after this
+    // tile's MMAs so that their DRAM latency runs under the epilogue instead of at the head of the next tile
+    // (long-scoreboard was the top stall: profiles/r02c_ops_L0_ncu_summary.md row 21).
+    float4 gnext[C / 4];
+    auto load_tile = [&](long long t) {
+        constexpr int F4 = C / 4;
+        const long long wrow0 = t * kTcBlock + warp * 32;
+        const float4 *src = reinterpret_cast<const float4 *>(grad + wrow0 * C);
+#pragma unroll
+        for (int i = 0; i < F4; ++i) {
+            const int q = i * 32 + lane;
+            const int rl = q / F4;
+            gnext[i] = (t < n_tiles && wrow0 + rl < rows) ? ldg_stream4(reinterpret_cast<const float *>(src + q)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    load_tile(blockIdx.x);
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const long long row_base = tile * kTcBlock;
-        // ---- a. gradient tile: the warp's 32 rows are 32·C contiguous floats — coalesced 128-bit loads, two lanes
-        //         assemble one 16-byte bf16 piece (8 channels) ----
+        // ---- a. gradient tile: the warp's 32 rows are 32·C contiguous floats — coalesced 128-bit loads (issued ONE TILE
+        //         AHEAD into registers, see the end of the loop body), two lanes assemble one 16-byte bf16 piece ----
         {
             constexpr int F4 = C / 4;                                 // float4 per row (even)
-            const long long wrow0 = row_base + warp * 32;
-            const float4 *src = reinterpret_cast<const float4 *>(grad + wrow0 * C);
 #pragma unroll
             for (int i = 0; i < F4; ++i) {
                 const int q = i * 32 + lane;
                 const int rl = q / F4, c4 = q - rl * F4;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (wrow0 + rl < rows) v = ldg_stream4(reinterpret_cast<const float *>(src + q));
+                const float4 v = gnext[i];
                 const uint32_t u0 = pack_bf16x2(v.x, v.y), u1 = pack_bf16x2(v.z, v.w);
                 const uint32_t n0 = __shfl_down_sync(0xffffffffu, u0, 1), n1 = __shfl_down_sync(0xffffffffu, u1, 1);
                 if ((lane & 1) == 0)
@@ -886,6 +910,7 @@ pe_mlp_backward_tc_kernel(long long rows, const float *__restrict__ pos, const f
                           umma_smem_desc(h_addr + kk * 256, 128, L::CHUNK), idescP, (!first || kk > 0) ? 1u : 0u);
             umma_commit(bar);
         }
+        load_tile(tile + gridDim.x);   // next tile's gradient rows: in flight during the rest of this tile
         mbar_wait(bar, phase);
         tc_fence_after();
         // ---- c. dz = dh ⊙ [h > 0] of this thread's row -> bf16 pieces into the (now free) GU buffer ----

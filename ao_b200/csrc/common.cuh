@@ -21,8 +21,6 @@ int check_launch(int kernels = 1);
 enum Tuning { kTuneCsrImpl = 0,   // AOPT_CSR_IMPL:   1 = radix sort, 2 = count / fill / rank
               kTuneGvaBwd = 1,    // AOPT_GVA_BWD:    1 = fused kernel, 2 = two kernels
               kTuneVoxelSort = 2, // AOPT_VOXEL_SORT: 1 = own radix sort (3 passes), 2 = wide keys (6 passes)
-              kTunePeFwd = 3,     // AOPT_PE_FWD:     1 = tcgen05 / TMEM kernel, 2 = mma.sync kernel
-              kTunePeBwd = 4,     // AOPT_PE_BWD:     1 = tcgen05 / TMEM kernel, 2 = mma.sync kernel
               kTuneKnnSample = 5, // AOPT_KNN_SAMPLE: 1 = cell edge from the bounding box (no density sample), 0 / 2 = sampled r_k (default)
               kTunePdl = 6,       // AOPT_PDL:        1 = programmatic dependent launch inside the small-kernel chains, 2 = off
               kTuneCount = 8 };

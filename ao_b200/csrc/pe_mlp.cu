@@ -13,9 +13,11 @@
 //     mean_c = W1[c,:]·m + b1[c],   var_c = W1[c,:] · Cov · W1[c,:]ᵀ        (biased, as BN uses)
 // and pos (hence m, Cov) is shared by every block of a BlockSequence.  With a_c = γ_c·rstd_c the hidden
 // activation is  h[r,c] = relu(a_c·(W1[c,:]·pos[r]) + a_c·(b1[c]-mean_c) + β_c): three FMAs per element
-// recomputed on the fly, never stored.  The C×C layer runs on the tensor cores (mma.sync m16n8k16,
-// bf16 operands, fp32 accumulation — the precision of the reference's autocast path); the work is
-// HBM-bound (2·C flops per output byte), so the legacy MMA path keeps up with the memory system.
+// recomputed on the fly, never stored.  The C×C layer runs on the 5th-generation tensor cores (tcgen05.mma,
+// bf16 operands, fp32 accumulation in Tensor Memory — the precision of the reference's autocast path); the work
+// is HBM-bound (2·C flops per output byte).  (Round 1's mma.sync kernels — forward 43 %, backward 17 % of the HBM
+// peak, bound by the shared-memory pipe that fed the MMA — were measured against these and removed:
+// profiles/r02a_kernel_bench_count_csr_mma_pe.txt, r02c_kernel_bench_pe_tc.txt.)
 //
 // The backward pass needs only row sums (∂L/∂pos is not needed: coordinates are inputs):
 //     dz = (G·W2) ⊙ [z>0],   S1 = Σ dz⊗pos,  S2 = Σ dz,  S3 = Σ dz⊙x̂,   dW2 = Gᵀ·h,  db2 = Σ G
@@ -30,8 +32,6 @@
 
 namespace aopt {
 
-constexpr int kPeBlock = 256;       // 8 warps
-constexpr int kPeTile = 128;        // rows per CTA tile (16 per warp)
 constexpr int kMomBlock = 256;
 
 // ---- 1. moments of pos ------------------------------------------------------------------------------
@@ -127,32 +127,6 @@ pe_fold_kernel(int c, double rows, const double *__restrict__ mom, const float *
     }
 }
 
-// ---- tensor-core helpers -------------------------------------------------------------------------------
-__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
-    asm volatile(
-        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
-}
-__device__ __forceinline__ uint32_t ld_u32(const __nv_bfloat16 *p) { return *reinterpret_cast<const uint32_t *>(p); }
-
-// A fragment (16 rows x 16 k) of a row-major [row][k] bf16 tile with leading dimension ld.
-__device__ __forceinline__ void load_a(uint32_t (&a)[4], const __nv_bfloat16 *tile, int ld, int row0, int k0, int lane) {
-    const int g = lane >> 2, t = lane & 3;
-    const __nv_bfloat16 *p = tile + (size_t)(row0 + g) * ld + k0 + t * 2;
-    a[0] = ld_u32(p);
-    a[1] = ld_u32(p + 8 * ld);
-    a[2] = ld_u32(p + 8);
-    a[3] = ld_u32(p + 8 * ld + 8);
-}
-// B fragment (16 k x 8 n) of a tile stored as [n][k] (k contiguous) with leading dimension ld.
-__device__ __forceinline__ void load_b(uint32_t (&b)[2], const __nv_bfloat16 *tile, int ld, int n0, int k0, int lane) {
-    const int g = lane >> 2, t = lane & 3;
-    const __nv_bfloat16 *p = tile + (size_t)(n0 + g) * ld + k0 + t * 2;
-    b[0] = ld_u32(p);
-    b[1] = ld_u32(p + 8);
-}
-
 // ---- bulk asynchronous copies (TMA 1-D: cp.async.bulk → SASS UBLKCP) ---------------------------------------
 // A tile of TR consecutive rows is one contiguous TR·C·4-byte block in global memory, so it moves with a
 // single bulk copy issued by one thread: no LSU wavefronts, no registers, completion through an mbarrier
@@ -170,12 +144,6 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
-__device__ __forceinline__ void bulk_load(void *sdst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(sdst)),
-                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     asm volatile(
         "{\n"
@@ -188,110 +156,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "}\n" ::"r"(smem_u32(bar)),
         "r"(parity)
         : "memory");
-}
-
-// ---- 3. forward ------------------------------------------------------------------------------------------
-template <int C>
-__global__ void __launch_bounds__(kPeBlock)
-pe_mlp_forward_kernel(long long rows, const float *__restrict__ pos, const float *__restrict__ fold,
-                      const __nv_bfloat16 *__restrict__ w2_bf, const float *__restrict__ b2,
-                      float *__restrict__ out, const __nv_bfloat16 *__restrict__ wf_bf, int ga,
-                      float *__restrict__ aux_out) {
-    constexpr int LDH = C + 8;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    __nv_bfloat16 *w2s = reinterpret_cast<__nv_bfloat16 *>(smem_raw);             // [C][LDH]   (n = co, k = ci)
-    __nv_bfloat16 *hs = w2s + C * LDH;                                              // [128][LDH] (row, k = ci)
-    float4 *fz = reinterpret_cast<float4 *>(hs + kPeTile * LDH);                    // [C] z-map
-    float *outs = reinterpret_cast<float *>(fz + C);                                // [128][C] output tile (bulk-stored)
-    float *b2s = outs + kPeTile * C;                                                // [C]
-    __nv_bfloat16 *wfs = reinterpret_cast<__nv_bfloat16 *>(b2s + C);               // [16][LDH] auxiliary head (n = g', k = ci)
-    const bool aux = aux_out != nullptr;
-    const bool aux2 = aux && ga > 8;
-    if (aux)
-        for (int i = threadIdx.x; i < 16 * C; i += kPeBlock) wfs[(i / C) * LDH + (i % C)] = wf_bf[i];
-    for (int i = threadIdx.x; i < C * C; i += kPeBlock) w2s[(i / C) * LDH + (i % C)] = w2_bf[i];
-    for (int i = threadIdx.x; i < C; i += kPeBlock) {
-        fz[i] = make_float4(fold[i * 8], fold[i * 8 + 1], fold[i * 8 + 2], fold[i * 8 + 3]);
-        b2s[i] = b2[i];
-    }
-    __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int g = lane >> 2, t = lane & 3;
-    const long long n_tiles = (rows + kPeTile - 1) / kPeTile;
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const long long row_base = tile * kPeTile;
-        if (threadIdx.x == 0) bulk_store_wait_read();  // previous tile's copy has finished reading `outs`
-        {   // hidden activations of the tile: thread → (row = tid/2, half of the channels)
-            const int r = threadIdx.x >> 1, half = threadIdx.x & 1;
-            const long long gr = row_base + r;
-            float px = 0.f, py = 0.f, pz = 0.f;
-            if (gr < rows) { px = __ldg(pos + gr * 3); py = __ldg(pos + gr * 3 + 1); pz = __ldg(pos + gr * 3 + 2); }
-            __nv_bfloat16 *hrow = hs + r * LDH + half * (C / 2);
-#pragma unroll 4
-            for (int cc = 0; cc < C / 2; cc += 2) {
-                const float4 f0 = fz[half * (C / 2) + cc], f1 = fz[half * (C / 2) + cc + 1];
-                const float z0 = fmaf(f0.x, px, fmaf(f0.y, py, fmaf(f0.z, pz, f0.w)));
-                const float z1 = fmaf(f1.x, px, fmaf(f1.y, py, fmaf(f1.z, pz, f1.w)));
-                *reinterpret_cast<__nv_bfloat162 *>(hrow + cc) = __floats2bfloat162_rn(fmaxf(z0, 0.f), fmaxf(z1, 0.f));
-            }
-        }
-        __syncthreads();
-        float acc[C / 8][4];
-        float aacc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-#pragma unroll
-        for (int nt = 0; nt < C / 8; ++nt) { acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f; }
-#pragma unroll
-        for (int kt = 0; kt < C / 16; ++kt) {
-            uint32_t a[4];
-            load_a(a, hs, LDH, warp * 16, kt * 16, lane);
-#pragma unroll
-            for (int nt = 0; nt < C / 8; ++nt) {
-                uint32_t b[2];
-                load_b(b, w2s, LDH, nt * 8, kt * 16, lane);
-                mma_bf16_16816(acc[nt], a, b);
-            }
-            if (aux) {  // one or two more n-tiles: the auxiliary head shares the A fragments
-                uint32_t b[2];
-                load_b(b, wfs, LDH, 0, kt * 16, lane);
-                mma_bf16_16816(aacc[0], a, b);
-                if (aux2) {
-                    load_b(b, wfs, LDH, 8, kt * 16, lane);
-                    mma_bf16_16816(aacc[1], a, b);
-                }
-            }
-        }
-        // epilogue: + b2 into the shared output tile, then ONE bulk copy of the tile's contiguous rows
-        const int lr0 = warp * 16 + g, lr1 = lr0 + 8;
-        if (aux) {  // (rows, ga) fp32, small: direct stores
-            const long long gr0 = row_base + lr0, gr1 = row_base + lr1;
-#pragma unroll
-            for (int an = 0; an < 2; ++an) {
-                const int col = an * 8 + t * 2;
-                if (col < ga) {
-                    if (gr0 < rows) aux_out[gr0 * ga + col] = aacc[an][0];
-                    if (gr1 < rows) aux_out[gr1 * ga + col] = aacc[an][2];
-                }
-                if (col + 1 < ga) {
-                    if (gr0 < rows) aux_out[gr0 * ga + col + 1] = aacc[an][1];
-                    if (gr1 < rows) aux_out[gr1 * ga + col + 1] = aacc[an][3];
-                }
-            }
-        }
-#pragma unroll
-        for (int nt = 0; nt < C / 8; ++nt) {
-            const int col = nt * 8 + t * 2;
-            const float bb0 = b2s[col], bb1 = b2s[col + 1];
-            *reinterpret_cast<float2 *>(outs + lr0 * C + col) = make_float2(acc[nt][0] + bb0, acc[nt][1] + bb1);
-            *reinterpret_cast<float2 *>(outs + lr1 * C + col) = make_float2(acc[nt][2] + bb0, acc[nt][3] + bb1);
-        }
-        fence_proxy_async();  // generic-proxy writes → visible to the async (bulk copy) proxy
-        __syncthreads();      // tile complete; hs may be rewritten by the next iteration
-        if (threadIdx.x == 0) {
-            const long long valid = rows - row_base < kPeTile ? rows - row_base : kPeTile;
-            bulk_store(out + row_base * C, outs, (uint32_t)(valid * C * 4));
-        }
-    }
-    if (threadIdx.x == 0) bulk_store_wait_all();  // shared memory must outlive the last copy
 }
 
 // ---- 3b. forward on the 5th-generation tensor cores (tcgen05.mma, accumulator in Tensor Memory) -----------
@@ -496,234 +360,6 @@ pe_mlp_forward_tc_kernel(long long rows, const float *__restrict__ pos, const fl
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(L::TMEM_COLS) : "memory");
 }
 
-// ---- 4. backward -----------------------------------------------------------------------------------------
-// Per-CTA partial layout (floats): dW2 [C*C] | db2 [C] | S2 [C] | S3 [C] | S1 [3C]
-// TR = rows per tile: 128 at C=48 (74 KB of shared memory → 3 CTAs/SM), 64 at C=96 (86 KB → 2 CTAs/SM).
-template <int C>
-struct PeBwdLayout {
-    static constexpr int TR = C <= 48 ? 128 : 64;
-    static constexpr int LDG = C + 8;            // Gs  [TR][LDG]  row-major (row, co)
-    static constexpr int LDT = TR + 8;           // GsT [C][LDT], HsT [C][LDT]  (channel, row)
-    static constexpr int LDW = C + 8;            // W2Ts [C][LDW]  (n = ci, k = co)
-    static constexpr int LDZ = C + 1;            // DZs [TR][LDZ] fp32
-    static constexpr int LDU = 24;               // dus [TR][LDU] (k = g' padded to 16), wfts [C][LDU] (n = ci, k = g')
-    static constexpr size_t bytes = (size_t)2 * (TR * LDG + 2 * C * LDT + C * LDW) + 4 * (size_t)TR * LDZ +
-                                    16 * (size_t)TR + 32 * (size_t)C + 4 * (size_t)TR * C + 16 +
-                                    (size_t)2 * (TR * LDU + 16 * LDT + C * LDU);
-    static constexpr int partial_floats = C * C + 6 * C + 16 * C;  // dW2 | db2 S2 S3 S1 | dWf [16][C]
-    static constexpr int ctas_per_sm = (2 * (bytes + 1024) <= 232448) ? 2 : 1;  // 227 KB of shared memory per SM
-};
-
-template <int C>
-__global__ void __launch_bounds__(kPeBlock)
-pe_mlp_backward_kernel(long long rows, const float *__restrict__ pos, const float *__restrict__ fold,
-                       const __nv_bfloat16 *__restrict__ w2t_bf, const float *__restrict__ grad,
-                       float *__restrict__ partial, const __nv_bfloat16 *__restrict__ wft_bf, int ga,
-                       const float *__restrict__ grad_aux) {
-    using L = PeBwdLayout<C>;
-    constexpr int TR = L::TR;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    __nv_bfloat16 *gs = reinterpret_cast<__nv_bfloat16 *>(smem_raw);
-    __nv_bfloat16 *gst = gs + TR * L::LDG;
-    __nv_bfloat16 *hst = gst + C * L::LDT;
-    __nv_bfloat16 *w2ts = hst + C * L::LDT;
-    float *dzs = reinterpret_cast<float *>(w2ts + C * L::LDW);
-    float4 *ps = reinterpret_cast<float4 *>(dzs + TR * L::LDZ);                    // [TR] (x, y, z, valid)
-    float4 *fz = ps + TR;                                                       // [C] z-map
-    float4 *fx = fz + C;                                                             // [C] x̂-map
-    float *gstage = reinterpret_cast<float *>(fx + C);                               // [TR][C] fp32 tile (bulk-loaded)
-    uint64_t *bar = reinterpret_cast<uint64_t *>(gstage + TR * C);
-    __nv_bfloat16 *dus = reinterpret_cast<__nv_bfloat16 *>(bar + 2);                 // [TR][LDU] aux gradient, row-major
-    __nv_bfloat16 *dut = dus + TR * L::LDU;                                          // [16][LDT] its transpose
-    __nv_bfloat16 *wfts = dut + 16 * L::LDT;                                         // [C][LDU]  (n = ci, k = g')
-    const bool aux = grad_aux != nullptr;
-    if (aux)
-        for (int i = threadIdx.x; i < C * 16; i += kPeBlock) wfts[(i / 16) * L::LDU + (i % 16)] = wft_bf[i];
-    const long long n_tiles = (rows + TR - 1) / TR;
-    if (threadIdx.x == 0) {
-        mbar_init(bar, 1);
-        if ((long long)blockIdx.x < n_tiles) {  // first tile of this CTA
-            const long long rb0 = (long long)blockIdx.x * TR;
-            const long long valid = rows - rb0 < TR ? rows - rb0 : TR;
-            bulk_load(gstage, grad + rb0 * C, (uint32_t)(valid * C * 4), bar);
-        }
-    }
-    for (int i = threadIdx.x; i < C * C; i += kPeBlock) w2ts[(i / C) * L::LDW + (i % C)] = w2t_bf[i];
-    for (int i = threadIdx.x; i < C; i += kPeBlock) {
-        fz[i] = make_float4(fold[i * 8], fold[i * 8 + 1], fold[i * 8 + 2], fold[i * 8 + 3]);
-        fx[i] = make_float4(fold[i * 8 + 4], fold[i * 8 + 5], fold[i * 8 + 6], fold[i * 8 + 7]);
-    }
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int g = lane >> 2, t = lane & 3;
-    // dW2 tiles (16 co x 8 ci) owned by this warp: tile id = warp + 8*i
-    constexpr int MT = C / 16, NT = C / 8, TILES = (MT + 1) * NT, OWN = (TILES + 7) / 8;  // row MT = the aux head
-    const int n_own_tiles = aux ? TILES : MT * NT;
-    float wacc[OWN][4];
-#pragma unroll
-    for (int i = 0; i < OWN; ++i) { wacc[i][0] = wacc[i][1] = wacc[i][2] = wacc[i][3] = 0.f; }
-    // column sums: thread → (channel = tid % C, row group = tid / C), groups = 256 / C
-    constexpr int NG = kPeBlock / C;
-    const int col_c = threadIdx.x % C, col_g = threadIdx.x / C;
-    const bool col_active = col_g < NG;
-    float s_db2 = 0.f, s2 = 0.f, s3 = 0.f, s1x = 0.f, s1y = 0.f, s1z = 0.f;
-    __syncthreads();
-    uint32_t phase = 0;
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const long long row_base = tile * TR;
-        // a. positions and the gradient tile (bulk-loaded fp32 → bf16, both orientations)
-        if (threadIdx.x < TR) {
-            const long long gr = row_base + threadIdx.x;
-            float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (gr < rows) p = make_float4(__ldg(pos + gr * 3), __ldg(pos + gr * 3 + 1), __ldg(pos + gr * 3 + 2), 1.f);
-            ps[threadIdx.x] = p;
-        }
-        if (aux) {  // aux gradient tile (rows x ga fp32, small): both orientations, zero padded to 16
-            for (int i = threadIdx.x; i < TR * 16; i += kPeBlock) {
-                const int r = i >> 4, q = i & 15;
-                const long long gr = row_base + r;
-                const float v = (q < ga && gr < rows) ? __ldg(grad_aux + gr * ga + q) : 0.f;
-                const __nv_bfloat16 bv = __float2bfloat16_rn(v);
-                dus[r * L::LDU + q] = bv;
-                dut[q * L::LDT + r] = bv;
-            }
-        }
-        mbar_wait(bar, phase);
-        phase ^= 1u;
-        for (int i = threadIdx.x; i < TR * (C / 4); i += kPeBlock) {
-            const int r = i / (C / 4), c4 = (i % (C / 4)) * 4;
-            const long long gr = row_base + r;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (gr < rows) v = *reinterpret_cast<const float4 *>(gstage + r * C + c4);
-            const __nv_bfloat16 b0 = __float2bfloat16_rn(v.x), b1 = __float2bfloat16_rn(v.y),
-                                b2 = __float2bfloat16_rn(v.z), b3 = __float2bfloat16_rn(v.w);
-            __nv_bfloat16 *d = gs + r * L::LDG + c4;
-            d[0] = b0; d[1] = b1; d[2] = b2; d[3] = b3;
-            gst[(c4 + 0) * L::LDT + r] = b0; gst[(c4 + 1) * L::LDT + r] = b1;
-            gst[(c4 + 2) * L::LDT + r] = b2; gst[(c4 + 3) * L::LDT + r] = b3;
-        }
-        __syncthreads();
-        if (threadIdx.x == 0 && tile + gridDim.x < n_tiles) {  // prefetch the next tile while this one is processed
-            const long long rbn = (tile + gridDim.x) * TR;
-            const long long valid = rows - rbn < TR ? rows - rbn : TR;
-            bulk_load(gstage, grad + rbn * C, (uint32_t)(valid * C * 4), bar);
-        }
-        // b. hidden activations, transposed: thread → (row = tid % TR, channel residue)
-        {
-            constexpr int PARTS = kPeBlock / TR;
-            const int r = threadIdx.x % TR, part = threadIdx.x / TR;
-            const float4 p = ps[r];
-            for (int cc = part; cc < C; cc += PARTS) {
-                const float4 f = fz[cc];
-                const float z = fmaf(f.x, p.x, fmaf(f.y, p.y, fmaf(f.z, p.z, f.w)));
-                hst[cc * L::LDT + r] = __float2bfloat16_rn(p.w > 0.f ? fmaxf(z, 0.f) : 0.f);
-            }
-        }
-        __syncthreads();
-        // c. dh = G · W2 (rows x ci), masked by h > 0 → dzs.  Warp → (16-row block, a slice of the n-tiles).
-        {
-            constexpr int RB = TR / 16, WPR = 8 / RB, NTW = (C / 8) / WPR;
-            const int rb = warp % RB, nt0 = (warp / RB) * NTW;
-            float acc[NTW][4];
-#pragma unroll
-            for (int nt = 0; nt < NTW; ++nt) { acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f; }
-#pragma unroll
-            for (int kt = 0; kt < C / 16; ++kt) {
-                uint32_t a[4];
-                load_a(a, gs, L::LDG, rb * 16, kt * 16, lane);
-#pragma unroll
-                for (int nt = 0; nt < NTW; ++nt) {
-                    uint32_t b[2];
-                    load_b(b, w2ts, L::LDW, (nt0 + nt) * 8, kt * 16, lane);
-                    mma_bf16_16816(acc[nt], a, b);
-                }
-            }
-            if (aux) {  // dh += dU · Wf  (one more k-tile: g' padded to 16)
-                uint32_t a[4];
-                load_a(a, dus, L::LDU, rb * 16, 0, lane);
-#pragma unroll
-                for (int nt = 0; nt < NTW; ++nt) {
-                    uint32_t b[2];
-                    load_b(b, wfts, L::LDU, (nt0 + nt) * 8, 0, lane);
-                    mma_bf16_16816(acc[nt], a, b);
-                }
-            }
-            const int r0 = rb * 16 + g, r1 = r0 + 8;
-#pragma unroll
-            for (int nt = 0; nt < NTW; ++nt) {
-                const int col = (nt0 + nt) * 8 + t * 2;
-                const float zero = 0.f;
-                dzs[r0 * L::LDZ + col] = __bfloat162float(hst[col * L::LDT + r0]) > 0.f ? acc[nt][0] : zero;
-                dzs[r0 * L::LDZ + col + 1] = __bfloat162float(hst[(col + 1) * L::LDT + r0]) > 0.f ? acc[nt][1] : zero;
-                dzs[r1 * L::LDZ + col] = __bfloat162float(hst[col * L::LDT + r1]) > 0.f ? acc[nt][2] : zero;
-                dzs[r1 * L::LDZ + col + 1] = __bfloat162float(hst[(col + 1) * L::LDT + r1]) > 0.f ? acc[nt][3] : zero;
-            }
-        }
-        // d. dW2[co][ci] += Σ_r G[r][co] · h[r][ci]   (A = GsT [m=co][k=r], B = HsT [n=ci][k=r])
-#pragma unroll
-        for (int i = 0; i < OWN; ++i) {
-            const int tid_tile = warp + 8 * i;
-            if (tid_tile < n_own_tiles) {
-                const int mt = tid_tile / NT, nt = tid_tile % NT;
-                const __nv_bfloat16 *asrc = mt < MT ? gst + (size_t)mt * 16 * L::LDT : dut;  // row MT: dWf = dUᵀ·h
-#pragma unroll
-                for (int kt = 0; kt < TR / 16; ++kt) {
-                    uint32_t a[4], b[2];
-                    load_a(a, asrc, L::LDT, 0, kt * 16, lane);
-                    load_b(b, hst, L::LDT, nt * 8, kt * 16, lane);
-                    mma_bf16_16816(wacc[i], a, b);
-                }
-            }
-        }
-        __syncthreads();
-        // e. column sums over the rows of the tile
-        if (col_active) {
-            const float4 f = fx[col_c];
-            for (int r = col_g; r < TR; r += NG) {
-                const float4 p = ps[r];
-                const float dz = dzs[r * L::LDZ + col_c];
-                const float xh = fmaf(f.x, p.x, fmaf(f.y, p.y, fmaf(f.z, p.z, f.w)));
-                s2 += dz;
-                s3 = fmaf(dz, xh, s3);
-                s1x = fmaf(dz, p.x, s1x); s1y = fmaf(dz, p.y, s1y); s1z = fmaf(dz, p.z, s1z);
-                s_db2 += __bfloat162float(gs[r * L::LDG + col_c]);
-            }
-        }
-        __syncthreads();  // tile buffers are rewritten by the next iteration
-    }
-    // f. per-CTA partials
-    float *out = partial + (size_t)blockIdx.x * L::partial_floats;
-#pragma unroll
-    for (int i = 0; i < OWN; ++i) {
-        const int tid_tile = warp + 8 * i;
-        if (tid_tile < TILES) {
-            const int mt = tid_tile / NT, nt = tid_tile % NT;
-            // rows 0..C-1: dW2 [co][ci]; row block MT: dWf [g'][ci] stored after the channel sums
-            float *dst = mt < MT ? out + (size_t)mt * 16 * C : out + (size_t)C * C + 6 * C;
-            const int ci = nt * 8 + t * 2;
-            dst[(size_t)g * C + ci] = wacc[i][0];
-            dst[(size_t)g * C + ci + 1] = wacc[i][1];
-            dst[(size_t)(g + 8) * C + ci] = wacc[i][2];
-            dst[(size_t)(g + 8) * C + ci + 1] = wacc[i][3];
-        }
-    }
-    // combine the row groups of every channel through shared memory (fixed order)
-    float *red = dzs;  // reuse: [NG][6][C]
-    if (col_active) {
-        float *rp = red + (size_t)col_g * 6 * C;
-        rp[0 * C + col_c] = s_db2; rp[1 * C + col_c] = s2; rp[2 * C + col_c] = s3;
-        rp[3 * C + col_c] = s1x; rp[4 * C + col_c] = s1y; rp[5 * C + col_c] = s1z;
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < 6 * C; i += kPeBlock) {
-        float v = 0.f;
-        for (int gg = 0; gg < NG; ++gg) v += red[(size_t)gg * 6 * C + i];
-        const int which = i / C, ch = i % C;
-        // layout after dW2: db2 [C] | S2 [C] | S3 [C] | S1 [C][3]
-        if (which < 3) out[(size_t)C * C + which * C + ch] = v;
-        else out[(size_t)C * C + 3 * C + ch * 3 + (which - 3)] = v;
-    }
-}
-
 // ---- 4b. backward on tcgen05: three UMMA products per 128-row tile, parameter-gradient accumulators resident in TMEM ----
 // Operand tiles live in shared memory as 16-byte pieces  byte(chunk, row) = chunk·2048 + row·16  (chunk = 8 consecutive
 // channels, row = 0..127).  ONE such buffer is two canonical no-swizzle UMMA layouts at once:
@@ -765,7 +401,7 @@ struct PeTcBwd {
     static constexpr int COL_D1 = 0, COL_P = C, COL_Q = C + NP;
     static constexpr int TMEM_COLS = (2 * C + 32) <= 128 ? 128 : 256;
     static constexpr int ctas_per_sm = (512 / TMEM_COLS) < (int)(232448 / (bytes + 1024)) ? (512 / TMEM_COLS) : (int)(232448 / (bytes + 1024));
-    static constexpr int partial_floats = C * C + 6 * C + 16 * C;   // same per-CTA layout as PeBwdLayout
+    static constexpr int partial_floats = C * C + 6 * C + 16 * C;   // per-CTA partial sums: dW2 [C*C] | db2 [C] | S2 [C] | S3 [C] | S1 [C][3] | dWf [16][C]
 };
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
@@ -950,7 +586,7 @@ pe_mlp_backward_tc_kernel(long long rows, const float *__restrict__ pos, const f
         phase ^= 1u;
         first = false;
     }
-    // ---- d. per-CTA partial sums out of Tensor Memory (layout of PeBwdLayout: dW2 | db2 | S2 | S3 | S1 | dWf) ----
+    // ---- d. per-CTA partial sums out of Tensor Memory (dW2 | db2 | S2 | S3 | S1 | dWf) ----
     float *out = partial + (size_t)blockIdx.x * L::partial_floats;
     if (first) {   // a CTA that owned no tile (cannot happen with pe_grid, kept for safety): zeros
         for (int i = tid; i < L::partial_floats; i += kTcBlock) out[i] = 0.f;
@@ -1066,21 +702,9 @@ static int pe_grid(long long rows, int tile_rows, int ctas_per_sm) {
     return (int)(tiles < cap ? (tiles < 1 ? 1 : tiles) : cap);
 }
 static int pe_bwd_grid(long long rows, int c) {
-    if (tuning(kTunePeBwd) != 2)   // tcgen05 kernel: 128-row tiles
-        return c <= 48 ? pe_grid(rows, kTcBlock, PeTcBwd<48>::ctas_per_sm) : pe_grid(rows, kTcBlock, PeTcBwd<96>::ctas_per_sm);
-    return c <= 48 ? pe_grid(rows, PeBwdLayout<48>::TR, PeBwdLayout<48>::ctas_per_sm)
-                   : pe_grid(rows, PeBwdLayout<96>::TR, PeBwdLayout<96>::ctas_per_sm);
-}
-// upper bound over both kernels (the workspace query must not depend on a switch that can change between calls)
-static int pe_bwd_grid_max(long long rows, int c) {
-    const int a = c <= 48 ? pe_grid(rows, kTcBlock, PeTcBwd<48>::ctas_per_sm) : pe_grid(rows, kTcBlock, PeTcBwd<96>::ctas_per_sm);
-    const int b = c <= 48 ? pe_grid(rows, PeBwdLayout<48>::TR, PeBwdLayout<48>::ctas_per_sm)
-                          : pe_grid(rows, PeBwdLayout<96>::TR, PeBwdLayout<96>::ctas_per_sm);
-    return a > b ? a : b;
+    return c <= 48 ? pe_grid(rows, kTcBlock, PeTcBwd<48>::ctas_per_sm) : pe_grid(rows, kTcBlock, PeTcBwd<96>::ctas_per_sm);
 }
 
-template <int C>
-static size_t pe_fwd_smem() { return (size_t)2 * (C * (C + 8) + kPeTile * (C + 8) + 16 * (C + 8)) + 16 * (size_t)C + 4 * (size_t)kPeTile * C + 4 * (size_t)C; }
 
 }  // namespace aopt
 
@@ -1131,33 +755,19 @@ PeState carve_state(void *state, int c) {
 template <int C>
 void launch_fwd(long long rows, const float *pos, const PeState &s, const float *b2, float *out, int ga,
                 float *aux_out, cudaStream_t st) {
-    if (tuning(kTunePeFwd) != 2) {   // tcgen05 / TMEM kernel (default)
-        using L = PeTcLayout<C>;
-        static bool once = (cudaFuncSetAttribute(pe_mlp_forward_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::bytes), true);
-        (void)once;
-        pe_mlp_forward_tc_kernel<C><<<pe_grid(rows, kTcBlock, L::ctas_per_sm), kTcBlock, L::bytes, st>>>(
-            rows, pos, s.fold, s.w2, b2, out, s.wf, ga, aux_out);
-        return;
-    }
-    const size_t smem = pe_fwd_smem<C>();
-    static bool once = (cudaFuncSetAttribute(pe_mlp_forward_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), true);
+    using L = PeTcLayout<C>;
+    static bool once = (cudaFuncSetAttribute(pe_mlp_forward_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::bytes), true);
     (void)once;
-    pe_mlp_forward_kernel<C><<<pe_grid(rows, kPeTile, C <= 48 ? 4 : 2), kPeBlock, smem, st>>>(rows, pos, s.fold, s.w2, b2, out, s.wf, ga, aux_out);
+    pe_mlp_forward_tc_kernel<C><<<pe_grid(rows, kTcBlock, L::ctas_per_sm), kTcBlock, L::bytes, st>>>(
+        rows, pos, s.fold, s.w2, b2, out, s.wf, ga, aux_out);
 }
 template <int C>
 void launch_bwd(long long rows, const float *pos, const PeState &s, const float *grad, float *partial, int grid,
                 int ga, const float *grad_aux, cudaStream_t st) {
-    if (tuning(kTunePeBwd) != 2) {   // tcgen05 / TMEM kernel (default)
-        using L = PeTcBwd<C>;
-        static bool once = (cudaFuncSetAttribute(pe_mlp_backward_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::bytes), true);
-        (void)once;
-        pe_mlp_backward_tc_kernel<C><<<grid, kTcBlock, L::bytes, st>>>(rows, pos, s.fold, s.w2t, grad, partial, s.wft, ga, grad_aux);
-        return;
-    }
-    const size_t smem = PeBwdLayout<C>::bytes;
-    static bool once = (cudaFuncSetAttribute(pe_mlp_backward_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), true);
+    using L = PeTcBwd<C>;
+    static bool once = (cudaFuncSetAttribute(pe_mlp_backward_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::bytes), true);
     (void)once;
-    pe_mlp_backward_kernel<C><<<grid, kPeBlock, smem, st>>>(rows, pos, s.fold, s.w2t, grad, partial, s.wft, ga, grad_aux);
+    pe_mlp_backward_tc_kernel<C><<<grid, kTcBlock, L::bytes, st>>>(rows, pos, s.fold, s.w2t, grad, partial, s.wft, ga, grad_aux);
 }
 }  // namespace
 
@@ -1191,7 +801,7 @@ extern "C" int aopt_pe_mlp_forward(int64_t rows, int c, const float *pos, const 
 extern "C" size_t aopt_pe_mlp_backward_workspace_bytes(int64_t rows, int c) {
     if (!aopt_pe_mlp_supported(c) || rows < 0) return 0;
     const size_t pf = (size_t)c * c + 6 * (size_t)c + 16 * (size_t)c;
-    return a256(4 * pf * (size_t)pe_bwd_grid_max(rows, c)) + a256(4 * 6 * (size_t)c);
+    return a256(4 * pf * (size_t)pe_bwd_grid(rows, c)) + a256(4 * 6 * (size_t)c);
 }
 
 /* Parameter gradients of aopt_pe_mlp_forward given grad (rows,c) = dL/dpeb; `state` is the forward's. */

@@ -69,10 +69,9 @@ const char *aopt_last_cuda_error(void);
 unsigned long long aopt_kernel_launches(void);
 /* Tuning switches for A/B measurements and tests (never needed for correctness; every setting gives the same
  * results bit for bit): "csr_impl" 1 = radix sort / 2 = count-fill-rank, "gva_bwd" 1 = fused / 2 = two kernels,
- * "voxel_sort" 1 = compact keys, 3 passes / 2 = wide keys, 6 passes, "pe_fwd" / "pe_bwd" 1 = tcgen05 / 2 = mma.sync
- * kernels of the positional MLP, "knn_sample" 1 = cell edge from the bounding box / 2 = sampled, "pdl" 1 = programmatic
- * dependent launch inside the small-kernel chains / 2 = off; 0 = library default.  Initial values come from
- * AOPT_CSR_IMPL / AOPT_GVA_BWD / AOPT_VOXEL_SORT / AOPT_PE_FWD / AOPT_PE_BWD / AOPT_KNN_SAMPLE / AOPT_PDL. */
+ * "voxel_sort" 1 = compact keys, 3 passes / 2 = wide keys, 6 passes, "knn_sample" 1 = cell edge from the bounding box /
+ * 2 = sampled, "pdl" 1 = programmatic dependent launch inside the small-kernel chains / 2 = off; 0 = library default.
+ * Initial values come from AOPT_CSR_IMPL / AOPT_GVA_BWD / AOPT_VOXEL_SORT / AOPT_KNN_SAMPLE / AOPT_PDL. */
 int aopt_set_tuning(const char *name, int value);
 
 /* ---- offset-encoded batch layout ---------------------------------------------------------- */

@@ -22,7 +22,7 @@ int check_launch(int kernels) {
 
 static std::atomic<int> g_tuning[kTuneCount];
 static std::atomic<bool> g_tuning_init{false};
-static const char *const kTuneNames[kTuneCount] = {"csr_impl", "gva_bwd", "voxel_sort", nullptr, nullptr, "knn_sample", "pdl", nullptr};
+static const char *const kTuneNames[kTuneCount] = {"csr_impl", "gva_bwd", "voxel_sort", "knn_topk", nullptr, "knn_sample", "pdl", nullptr};
 
 static void tuning_init() {
     if (g_tuning_init.exchange(true)) return;
@@ -34,6 +34,7 @@ static void tuning_init() {
     g_tuning[kTuneCsrImpl] = env("AOPT_CSR_IMPL", "sort", "count");
     g_tuning[kTuneGvaBwd] = env("AOPT_GVA_BWD", "fused", "split");
     g_tuning[kTuneVoxelSort] = env("AOPT_VOXEL_SORT", "radix", "wide");
+    g_tuning[kTuneKnnTopk] = env("AOPT_KNN_TOPK", "heap", "list");
     g_tuning[kTuneKnnSample] = env("AOPT_KNN_SAMPLE", "bbox", "sampled");
     g_tuning[kTunePdl] = env("AOPT_PDL", "1", "0");
 }

@@ -272,12 +272,98 @@ grid_fill_kernel(int n, const float *__restrict__ xyz, const int *__restrict__ c
 }
 
 // ---- 6. query ------------------------------------------------------------------------------------
+// Two interchangeable top-k containers (same results: both rank candidates by the 64-bit (d2 bits : idx) key):
+//   TopK<K, true>  (knn_common.cuh)  sorted list in registers; an insert is K compares + 2K selects on 64-bit keys
+//                                    = 96 ALU-pipe instructions at K = 16, executed by the whole warp whenever ANY of its
+//                                    32 queries accepts a candidate — which is nearly every candidate (an acceptance
+//                                    probability of 0.1-0.3 per lane): ncu r01q: ALU pipe 81 %, 14.5 of 32 lanes active.
+//   HeapK<K>       (below)           binary max-heap, one shared-memory column per thread (slot s of thread t at
+//                                    [s * kQueryBlock + t]: every lane hits its own bank whatever slot it is at), root
+//                                    mirrored in registers.  An insert replaces the root and sifts down: <= log2 K levels
+//                                    of (4 LDS, 4 integer compares, 3 selects, 2 STS) — about a third of the ALU-pipe work,
+//                                    the rest moved to the otherwise idle LSU pipe; no K x 2 registers for the list, so no
+//                                    spills and more warps to hide the chain.  A heap sort at the end writes the ascending
+//                                    list the API promises.  This is the reference's own data structure
+//                                    (knn_query_cuda_kernel.cu:15-43) moved from local memory into conflict-free shared memory.
+template <int K>
+struct HeapK {
+    unsigned *hd;  // column of this thread: element s at hd[s * kQueryBlock]
+    int *hi;
+    unsigned rd;   // root = current k-th best, mirrored
+    int ri;
+
+    static __device__ __forceinline__ unsigned long long key(unsigned dv, int iv) {
+        return ((unsigned long long)dv << 32) | (unsigned)iv;
+    }
+    __device__ __forceinline__ void init(unsigned *sd, int *si) {
+        hd = sd + threadIdx.x;
+        hi = si + threadIdx.x;
+        reset();
+    }
+    __device__ __forceinline__ void reset() {
+#pragma unroll
+        for (int s = 0; s < K; ++s) { hd[s * kQueryBlock] = __float_as_uint(1e10f); hi[s * kQueryBlock] = -1; }
+        rd = __float_as_uint(1e10f);
+        ri = -1;
+    }
+    __device__ __forceinline__ float worst() const { return __uint_as_float(rd); }
+
+    // (nd, ni) enters at the root and sinks below every larger child; `limit` = heap size
+    __device__ __forceinline__ void sift(unsigned nd, int ni, int limit) {
+        const unsigned long long nk = key(nd, ni);
+        int pos = 0;
+        for (;;) {
+            const int l = 2 * pos + 1;
+            if (l >= limit) break;
+            const unsigned dl = hd[l * kQueryBlock];
+            const int il = hi[l * kQueryBlock];
+            unsigned dr = 0u;
+            int ir = 0;
+            if (l + 1 < limit) { dr = hd[(l + 1) * kQueryBlock]; ir = hi[(l + 1) * kQueryBlock]; }
+            const bool rbig = key(dr, ir) > key(dl, il);
+            const unsigned dc = rbig ? dr : dl;
+            const int ic = rbig ? ir : il;
+            if (!(key(dc, ic) > nk)) break;
+            hd[pos * kQueryBlock] = dc;
+            hi[pos * kQueryBlock] = ic;
+            if (pos == 0) { rd = dc; ri = ic; }
+            pos = l + (rbig ? 1 : 0);
+        }
+        hd[pos * kQueryBlock] = nd;
+        hi[pos * kQueryBlock] = ni;
+        if (pos == 0) { rd = nd; ri = ni; }
+    }
+    __device__ __forceinline__ void offer(float d2, int i) {
+        // same acceptance rule as TopK<K, true>::offer
+        const unsigned du = __float_as_uint(d2);
+        if (d2 < 1e10f && key(du, i) < key(rd, ri)) sift(du, i, K);
+    }
+    // heap sort in place (ascending), then the first nsample entries go out
+    __device__ __forceinline__ void store(int *idx_row, float *d2_row, int nsample, bool root) {
+        for (int end = K - 1; end >= 1; --end) {
+            const unsigned nd = hd[end * kQueryBlock];
+            const int ni = hi[end * kQueryBlock];
+            hd[end * kQueryBlock] = rd;
+            hi[end * kQueryBlock] = ri;
+            sift(nd, ni, end);
+        }
+#pragma unroll
+        for (int s = 0; s < K; ++s) {
+            if (s < nsample) {
+                const float dv = __uint_as_float(hd[s * kQueryBlock]);
+                idx_row[s] = hi[s * kQueryBlock];
+                d2_row[s] = root ? __fsqrt_rn(dv) : dv;
+            }
+        }
+    }
+};
+
 // Candidates of a run are requested four at a time: the offer is a divergent branch, so a load issued next to
 // its use would expose its L1/L2 latency on every candidate — on the small levels, where a scheduler holds a
 // single warp, that latency is the kernel time.  (A cross-iteration prefetch of the next four cost 32 more
 // registers and spills at K = 16; not kept.)
-template <int K>
-__device__ __forceinline__ void scan_run(TopK<K, true> &top, const float4 *__restrict__ sorted, int a,
+template <class Top>
+__device__ __forceinline__ void scan_run(Top &top, const float4 *__restrict__ sorted, int a,
                                          int e, float qx, float qy, float qz) {
     int i = a;
     for (; i + 4 <= e; i += 4) {
@@ -299,7 +385,24 @@ __device__ __forceinline__ void scan_run(TopK<K, true> &top, const float4 *__res
     }
 }
 
-template <int K, bool SELF>
+template <int K, bool HEAP>
+struct TopSel {
+    using type = TopK<K, true>;
+    static __device__ __forceinline__ void init(type &t) { t.init(); }
+    static __device__ __forceinline__ void reset(type &t) { t.init(); }
+};
+template <int K>
+struct TopSel<K, true> {
+    using type = HeapK<K>;
+    static __device__ __forceinline__ void init(type &t) {
+        __shared__ unsigned sd[K * kQueryBlock];
+        __shared__ int si[K * kQueryBlock];
+        t.init(sd, si);
+    }
+    static __device__ __forceinline__ void reset(type &t) { t.reset(); }
+};
+
+template <int K, bool SELF, bool HEAP>
 __global__ void __launch_bounds__(kQueryBlock)
 knn_grid_kernel(int m, int b, int nsample, const float *__restrict__ new_xyz,
                 const int *__restrict__ new_offset, const GridDesc *__restrict__ desc,
@@ -323,8 +426,8 @@ knn_grid_kernel(int m, int b, int nsample, const float *__restrict__ new_xyz,
         qx = __ldg(new_xyz + (size_t)t * 3); qy = __ldg(new_xyz + (size_t)t * 3 + 1);
         qz = __ldg(new_xyz + (size_t)t * 3 + 2);
     }
-    TopK<K, true> top;
-    top.init();
+    typename TopSel<K, HEAP>::type top;
+    TopSel<K, HEAP>::init(top);
     if (sc < b) {
         const GridDesc g = desc[sc];
         if (g.end > g.start) {
@@ -350,12 +453,12 @@ knn_grid_kernel(int m, int b, int nsample, const float *__restrict__ new_xyz,
                         const bool full = (r == 1) || max(abs(dz), abs(dy)) == r;
                         if (full) {
                             const int x0 = max(cx - r, 0), x1 = min(cx + r, g.nx - 1);
-                            scan_run<K>(top, sorted, __ldg(cs + rowbase + x0), __ldg(cs + rowbase + x1 + 1), qx, qy, qz);
+                            scan_run(top, sorted, __ldg(cs + rowbase + x0), __ldg(cs + rowbase + x1 + 1), qx, qy, qz);
                         } else {
                             if (cx - r >= 0)
-                                scan_run<K>(top, sorted, __ldg(cs + rowbase + cx - r), __ldg(cs + rowbase + cx - r + 1), qx, qy, qz);
+                                scan_run(top, sorted, __ldg(cs + rowbase + cx - r), __ldg(cs + rowbase + cx - r + 1), qx, qy, qz);
                             if (cx + r <= g.nx - 1)
-                                scan_run<K>(top, sorted, __ldg(cs + rowbase + cx + r), __ldg(cs + rowbase + cx + r + 1), qx, qy, qz);
+                                scan_run(top, sorted, __ldg(cs + rowbase + cx + r), __ldg(cs + rowbase + cx + r + 1), qx, qy, qz);
                         }
                     }
                 }
@@ -375,8 +478,8 @@ knn_grid_kernel(int m, int b, int nsample, const float *__restrict__ new_xyz,
                 }
             }
             if (!done) {  // sparse neighbourhood: exhaustive scan of the scene
-                top.init();
-                scan_run<K>(top, sorted, g.start, g.end, qx, qy, qz);
+                TopSel<K, HEAP>::reset(top);
+                scan_run(top, sorted, g.start, g.end, qx, qy, qz);
             }
         }
     }
@@ -420,17 +523,35 @@ size_t knn_grid_workspace_bytes(int n, int m, int b) {
     return carve(nullptr, n, b).bytes;
 }
 
-template <int K>
-static void launch_query(bool self, int m, int b, int nsample, const float *new_xyz, const int *new_offset,
-                         const GridWs &w, int *idx, float *dist2, bool root, cudaStream_t st) {
+template <int K, bool HEAP>
+static void launch_query_t(bool self, int m, int b, int nsample, const float *new_xyz, const int *new_offset,
+                           const GridWs &w, int *idx, float *dist2, bool root, cudaStream_t st) {
     const int grid = div_up(m, kQueryBlock);
     const bool pdl = tuning(kTunePdl) != 2;
     if (self)
-        launch_chain(pdl, knn_grid_kernel<K, true>, grid, kQueryBlock, 0, st, m, b, nsample, new_xyz, new_offset,
+        launch_chain(pdl, knn_grid_kernel<K, true, HEAP>, grid, kQueryBlock, 0, st, m, b, nsample, new_xyz, new_offset,
                      (const GridDesc *)w.desc, (const int *)w.cells, (const float4 *)w.sorted, idx, dist2, root);
     else
-        launch_chain(pdl, knn_grid_kernel<K, false>, grid, kQueryBlock, 0, st, m, b, nsample, new_xyz, new_offset,
+        launch_chain(pdl, knn_grid_kernel<K, false, HEAP>, grid, kQueryBlock, 0, st, m, b, nsample, new_xyz, new_offset,
                      (const GridDesc *)w.desc, (const int *)w.cells, (const float4 *)w.sorted, idx, dist2, root);
+}
+
+// Container choice (tuning "knn_topk", AOPT_KNN_TOPK=heap|list).  Default: the register list.  Measured on a B200
+// (profiles/r02m_knn_topk_ab.txt, whole search, identical bits): the heap wins only at k = 32 on the dense indoor
+// scans (S3DIS level 0: 515 vs 634 us, ScanNet 3 x 150k: 776 vs 967 us); at k = 16 it is level (317 vs 313 us at
+// level 0) or slower (173 vs 146 us at level 1, 113 vs 84 us at level 3), at k = 8 slower everywhere: a sift is
+// <= 4 dependent shared-memory round trips with the lanes at different depths, which costs the warp as many issue
+// slots as the 96 independent compares / selects of the list insert.
+template <int K>
+static void launch_query(bool self, int m, int b, int nsample, const float *new_xyz, const int *new_offset,
+                         const GridWs &w, int *idx, float *dist2, bool root, cudaStream_t st) {
+    if constexpr (K >= 8) {
+        if (tuning(kTuneKnnTopk) == 1) {
+            launch_query_t<K, true>(self, m, b, nsample, new_xyz, new_offset, w, idx, dist2, root, st);
+            return;
+        }
+    }
+    launch_query_t<K, false>(self, m, b, nsample, new_xyz, new_offset, w, idx, dist2, root, st);
 }
 
 template <int K>

@@ -36,6 +36,26 @@ def test_small_adversarial_batch_bit_exact(oracle, method, k):
     assert_knn_equal(idx, d2, hi, hd)
 
 
+@pytest.mark.parametrize("k", [8, 16, 32])
+def test_heap_container_equals_register_list(oracle, k):
+    """The GRID query kernel's opt-in top-k container (tuning "knn_topk" = 1: binary heap in shared memory + heap sort)
+    returns the bits of the default sorted register list — ties (duplicated points), short scenes and padding included."""
+    from ao_b200 import _lib, scenes
+
+    coord, _, offset = scenes.small_batch(seed=40 + k, sizes=(3000, 5, 4100, 257))
+    coord[100:140] = coord[60:100]                   # duplicates: equal distances, ranked by index
+    try:
+        _lib.set_tuning("knn_topk", 1)
+        hi, hd = run("grid", k, coord, offset)
+        _lib.set_tuning("knn_topk", 2)
+        li, ld = run("grid", k, coord, offset)
+    finally:
+        _lib.set_tuning("knn_topk", 0)
+    assert np.array_equal(hi, li) and np.array_equal(hd, ld)
+    ri, rd = oracle.knn_query(k, coord, offset, rule="lex")
+    assert np.array_equal(hi, ri) and np.array_equal(hd, rd)
+
+
 @pytest.mark.parametrize("method", ["tile", "grid", "auto"])
 def test_no_candidates_gives_padding(method):
     """Queries against an EMPTY candidate set (n = 0): every row is padding (idx -1, dist2 1e10), whichever method is

@@ -70,6 +70,14 @@ SIGNATURES = {
     "aopt_pe_mlp_backward_workspace_bytes": (c_size_t, [c_int64, c_int]),
     "aopt_pe_mlp_backward": (c_int, [c_int64, c_int, P, P, P, P, c_int, P, P, P, P, P, P, P, P, c_int, P, P, P,
                                      c_size_t, P]),
+    "aopt_dense_workspace_bytes": (c_size_t, [c_int]),
+    "aopt_bn_act_supported": (c_int, [c_int]),
+    "aopt_bn_act_forward": (c_int, [c_int64, c_int, P, c_int, P, P, c_float, P, P, c_int, P, c_int, P, P, P, c_float, P, P,
+                                    c_size_t, P]),
+    "aopt_bn_act_backward": (c_int, [c_int64, c_int, P, P, c_int, P, c_int, P, P, P, P, P, P, P, P, c_size_t, P]),
+    "aopt_we_tail_supported": (c_int, [c_int]),
+    "aopt_we_tail_forward": (c_int, [c_int64, c_int, P, P, P, P, P, c_float, P, P, P, P, P, P, c_float, P, c_size_t, P]),
+    "aopt_we_tail_backward": (c_int, [c_int64, c_int, P, P, P, P, P, P, P, P, P, P, P, P, P, P, c_size_t, P]),
     "aopt_aggregation_forward": (c_int, [c_int, c_int, c_int, c_int, P, P, P, P, P, P]),
     "aopt_aggregation_backward": (c_int, [c_int, c_int, c_int, c_int, P, P, P, P, P, P, P, P, P, P, P]),
     "aopt_subtraction_forward": (c_int, [c_int, c_int, c_int, P, P, P, P, P]),
@@ -83,7 +91,8 @@ _trace = None  # list of (entry point, args, start event, end event) while bench
 _UNTRACED = {"aopt_set_tuning", "aopt_version", "aopt_status_string", "aopt_last_cuda_error", "aopt_kernel_launches",
              "aopt_knn_workspace_bytes", "aopt_csr_workspace_bytes", "aopt_voxel_partition_workspace_bytes", "aopt_voxel_grid_workspace_bytes",
              "aopt_pe_mlp_supported", "aopt_pos_moments_workspace_bytes", "aopt_pe_mlp_state_bytes",
-             "aopt_pe_mlp_backward_workspace_bytes"}
+             "aopt_pe_mlp_backward_workspace_bytes", "aopt_dense_workspace_bytes", "aopt_bn_act_supported",
+             "aopt_we_tail_supported"}
 
 
 class _Entry:

@@ -1,0 +1,713 @@
+// dense.cu — the BatchNorm-shaped parts of a PTv2 block that sit between the point operators and the dense
+// per-point Linear layers ("BN + tiny-K Linear fusion"):
+//
+//   aopt_bn_act_*        y = [ReLU]( [residual +] [row_scale ·] BatchNorm_train(x) )  on the rows of an (rows, C) matrix
+//                        = PointBatchNorm (+ nn.ReLU, + DropPath, + the residual add) of
+//                        /root/reference/pointcept/models/point_transformer_v2/point_transformer_v2m2_base.py:25-45,187-197
+//                        and of every Linear → PointBatchNorm → ReLU triple (:86-93,240-242,288-295,363-364).
+//                        fp32 or bf16 in / out, statistics and arithmetic in fp32 (partial sums combined in fp64).
+//   aopt_we_tail_*       logits = Linear(G,G)( ReLU( BatchNorm_train( rel + upe + const ) ) ) on the (rows = N·k, G) tensors:
+//                        weight_encoding[1:] of GroupedVectorAttention (:94-99,120) together with the two additions that
+//                        form its input in the relation-free schedule (ptv2._forward_fused).  The G x G layer is K = 6 / 12:
+//                        CUDA-core FMAs on a row held in registers; its parameter gradients (a (G, rows) x (rows, G) product
+//                        with rows = 5.12 M that cuBLAS runs as ONE CTA: 723 us per call, profiles/r02e) are per-thread
+//                        accumulators reduced in a fixed order.
+//
+// All of it is HBM-/L2-bound element-wise and reduction work: one thread keeps one 4-channel column chunk (BN) or one
+// row (tail), 128-bit accesses, grids sized in multiples of the SM count, no atomics (per-CTA partials are summed in a
+// fixed order by partials_reduce_kernel, so results are bitwise repeatable).  The small kernels of one call are chained
+// with programmatic dependent launch.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace aopt {
+
+constexpr int kDenseBlock = 256;
+constexpr int kDenseCtasPerSm = 4;
+constexpr int kDenseMaxGrid = kNumSM * kDenseCtasPerSm;
+
+// ---- typed 4-channel access -------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ float4 ld4(const T *p);
+template <>
+__device__ __forceinline__ float4 ld4<float>(const float *p) {
+    return __ldg(reinterpret_cast<const float4 *>(p));
+}
+template <>
+__device__ __forceinline__ float4 ld4<__nv_bfloat16>(const __nv_bfloat16 *p) {
+    const uint2 r = __ldg(reinterpret_cast<const uint2 *>(p));
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&r.x));
+    const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&r.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+template <typename T>
+__device__ __forceinline__ void st4(T *p, const float4 &v);
+template <>
+__device__ __forceinline__ void st4<float>(float *p, const float4 &v) {
+    *reinterpret_cast<float4 *>(p) = v;
+}
+template <>
+__device__ __forceinline__ void st4<__nv_bfloat16>(__nv_bfloat16 *p, const float4 &v) {
+    const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 r;
+    r.x = *reinterpret_cast<const unsigned *>(&a);
+    r.y = *reinterpret_cast<const unsigned *>(&b);
+    *reinterpret_cast<uint2 *>(p) = r;
+}
+
+// ---- reductions ---------------------------------------------------------------------------------------------------
+// Threads of a CTA that own the same column chunk (t, t + cols, t + 2 cols, ...) are summed in that order by the
+// first `cols` threads; partial row = [ A (c floats) | B (c floats) ].
+__device__ __forceinline__ void column_reduce_store(const float4 &a, const float4 &b, int cols, int c, int col,
+                                                    float *__restrict__ partial_row) {
+    __shared__ float4 sh[2][kDenseBlock];
+    const int t = threadIdx.x;
+    sh[0][t] = a;
+    sh[1][t] = b;
+    __syncthreads();
+    if (t < cols) {
+        float4 A = sh[0][t], B = sh[1][t];
+        for (int u = t + cols; u < kDenseBlock; u += cols) {
+            const float4 x = sh[0][u], y = sh[1][u];
+            A.x += x.x; A.y += x.y; A.z += x.z; A.w += x.w;
+            B.x += y.x; B.y += y.y; B.z += y.z; B.w += y.w;
+        }
+        *reinterpret_cast<float4 *>(partial_row + 4 * col) = A;
+        *reinterpret_cast<float4 *>(partial_row + c + 4 * col) = B;
+    }
+}
+
+// NV per-thread values -> one row of NV floats per CTA (warp shuffles, then the warps in order).
+template <int NV>
+__device__ __forceinline__ void block_reduce_store(float (&v)[NV], float *__restrict__ partial_row) {
+    __shared__ float sh[kDenseBlock / 32][NV];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        float x = v[j];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(0xffffffffu, x, d);
+        if (lane == 0) sh[warp][j] = x;
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < NV; j += kDenseBlock) {
+        float s = sh[0][j];
+#pragma unroll
+        for (int w = 1; w < kDenseBlock / 32; ++w) s += sh[w][j];
+        partial_row[j] = s;
+    }
+}
+
+// out[v] = Σ_p partials[p][v] in fp64, fixed order.  CTA = 32 values x 8 slices of the partial rows.
+__global__ void __launch_bounds__(256)
+partials_reduce_kernel(int parts, int width, const float *__restrict__ partials, double *__restrict__ out) {
+    __shared__ double sh[8][32];
+    pdl_wait();
+    pdl_trigger();
+    const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+    const int v = blockIdx.x * 32 + lane;
+    double s = 0.0;
+    if (v < width)
+        for (int p = slice; p < parts; p += 8) s += (double)partials[(size_t)p * width + v];
+    sh[slice][lane] = s;
+    __syncthreads();
+    if (slice == 0 && v < width) {
+        double t = sh[0][lane];
+#pragma unroll
+        for (int u = 1; u < 8; ++u) t += sh[u][lane];
+        out[v] = t;
+    }
+}
+
+struct ChanStat {
+    float mean, rstd;
+};
+__device__ __forceinline__ ChanStat stat_from_sums(double s, double q, double inv_rows, float eps, float *var_out = nullptr) {
+    const double m = s * inv_rows;
+    double var = q * inv_rows - m * m;
+    if (var < 0.0) var = 0.0;
+    if (var_out) *var_out = (float)var;
+    ChanStat r;
+    r.mean = (float)m;
+    r.rstd = (float)(1.0 / sqrt(var + (double)eps));
+    return r;
+}
+
+// ---- BatchNorm (+ ReLU, + residual, + per-row scale) on (rows, C), C % 4 == 0 ----------------------------------
+template <typename XT>
+__global__ void __launch_bounds__(kDenseBlock)
+bn_partial_kernel(long long rows, int c, const XT *__restrict__ x, float *__restrict__ partials) {
+    const int cols = c >> 2;
+    const ColWalk w = col_walk(cols, kDenseBlock);
+    pdl_trigger();
+    float4 s[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
+    float4 q[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
+    const XT *p = x + 4 * w.col;
+    long long row = w.row;
+    for (; row + 3 * w.row_step < rows; row += 4 * w.row_step) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = ld4(p + (row + u * w.row_step) * c);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            float4 &S = s[u & 1], &Q = q[u & 1];
+            S.x += v[u].x; S.y += v[u].y; S.z += v[u].z; S.w += v[u].w;
+            Q.x = fmaf(v[u].x, v[u].x, Q.x); Q.y = fmaf(v[u].y, v[u].y, Q.y);
+            Q.z = fmaf(v[u].z, v[u].z, Q.z); Q.w = fmaf(v[u].w, v[u].w, Q.w);
+        }
+    }
+    for (; row < rows; row += w.row_step) {
+        const float4 v = ld4(p + row * c);
+        s[0].x += v.x; s[0].y += v.y; s[0].z += v.z; s[0].w += v.w;
+        q[0].x = fmaf(v.x, v.x, q[0].x); q[0].y = fmaf(v.y, v.y, q[0].y);
+        q[0].z = fmaf(v.z, v.z, q[0].z); q[0].w = fmaf(v.w, v.w, q[0].w);
+    }
+    s[0].x += s[1].x; s[0].y += s[1].y; s[0].z += s[1].z; s[0].w += s[1].w;
+    q[0].x += q[1].x; q[0].y += q[1].y; q[0].z += q[1].z; q[0].w += q[1].w;
+    column_reduce_store(s[0], q[0], cols, c, w.col, partials + (size_t)blockIdx.x * 2 * c);
+}
+
+template <typename XT, typename OT>
+__global__ void __launch_bounds__(kDenseBlock)
+bn_apply_kernel(long long rows, int c, const XT *__restrict__ x, const double *__restrict__ sums, double inv_rows,
+                float eps, const float *__restrict__ gamma, const float *__restrict__ beta,
+                const OT *__restrict__ residual, const float *__restrict__ row_scale, int relu, OT *__restrict__ out,
+                float *__restrict__ stats_out, float *__restrict__ running_mean, float *__restrict__ running_var,
+                float momentum, float unbias, const float *__restrict__ mean_shift) {
+    const int cols = c >> 2;
+    const ColWalk w = col_walk(cols, kDenseBlock);
+    pdl_wait();
+    float mean[4], sc[4], sh[4];
+    const bool writer = (long long)blockIdx.x * kDenseBlock + threadIdx.x < cols;   // one thread per column chunk
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int ch = 4 * w.col + j;
+        float var;
+        const ChanStat st = stat_from_sums(sums[ch], sums[c + ch], inv_rows, eps, &var);
+        mean[j] = st.mean;
+        sc[j] = __ldg(gamma + ch) * st.rstd;
+        sh[j] = __ldg(beta + ch);
+        if (writer) {
+            stats_out[ch] = st.mean;
+            stats_out[c + ch] = st.rstd;
+            // mean_shift: a bias the caller left out of x because the normalisation removes it (Linear bias in front of
+            // a training-mode BatchNorm); only the running mean sees it
+            if (running_mean)
+                running_mean[ch] = (1.f - momentum) * running_mean[ch] + momentum * (st.mean + (mean_shift ? mean_shift[ch] : 0.f));
+            if (running_var) running_var[ch] = (1.f - momentum) * running_var[ch] + momentum * var * unbias;
+        }
+    }
+    const XT *px = x + 4 * w.col;
+    const OT *pr = residual ? residual + 4 * w.col : nullptr;
+    OT *po = out + 4 * w.col;
+    for (long long row = w.row; row < rows; row += w.row_step) {
+        const float4 v = ld4(px + row * c);
+        float4 y;
+        y.x = fmaf(v.x - mean[0], sc[0], sh[0]);
+        y.y = fmaf(v.y - mean[1], sc[1], sh[1]);
+        y.z = fmaf(v.z - mean[2], sc[2], sh[2]);
+        y.w = fmaf(v.w - mean[3], sc[3], sh[3]);
+        if (row_scale) {
+            const float r = __ldg(row_scale + row);
+            y.x *= r; y.y *= r; y.z *= r; y.w *= r;
+        }
+        if (pr) {
+            const float4 e = ld4(pr + row * c);
+            y.x += e.x; y.y += e.y; y.z += e.z; y.w += e.w;
+        }
+        if (relu) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
+        st4(po + row * c, y);
+    }
+}
+
+// dy = grad_out ⊙ [out > 0] (· row_scale);  partial row = [ Σ dy | Σ dy·x̂ ]
+template <typename XT, typename OT>
+__global__ void __launch_bounds__(kDenseBlock)
+bn_bwd_partial_kernel(long long rows, int c, const OT *__restrict__ grad_out, const OT *__restrict__ out,
+                      const XT *__restrict__ x, const float *__restrict__ stats, const float *__restrict__ row_scale,
+                      float *__restrict__ partials) {
+    const int cols = c >> 2;
+    const ColWalk w = col_walk(cols, kDenseBlock);
+    pdl_trigger();
+    const float4 mean = *reinterpret_cast<const float4 *>(stats + 4 * w.col);
+    const float4 rstd = *reinterpret_cast<const float4 *>(stats + c + 4 * w.col);
+    float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const XT *px = x + 4 * w.col;
+    const OT *pg = grad_out + 4 * w.col;
+    const OT *po = out ? out + 4 * w.col : nullptr;
+    for (long long row = w.row; row < rows; row += w.row_step) {
+        float4 g = ld4(pg + row * c);
+        const float4 v = ld4(px + row * c);
+        if (po) {
+            const float4 o = ld4(po + row * c);
+            g.x = o.x > 0.f ? g.x : 0.f; g.y = o.y > 0.f ? g.y : 0.f;
+            g.z = o.z > 0.f ? g.z : 0.f; g.w = o.w > 0.f ? g.w : 0.f;
+        }
+        if (row_scale) {
+            const float r = __ldg(row_scale + row);
+            g.x *= r; g.y *= r; g.z *= r; g.w *= r;
+        }
+        s1.x += g.x; s1.y += g.y; s1.z += g.z; s1.w += g.w;
+        s2.x = fmaf(g.x, (v.x - mean.x) * rstd.x, s2.x);
+        s2.y = fmaf(g.y, (v.y - mean.y) * rstd.y, s2.y);
+        s2.z = fmaf(g.z, (v.z - mean.z) * rstd.z, s2.z);
+        s2.w = fmaf(g.w, (v.w - mean.w) * rstd.w, s2.w);
+    }
+    column_reduce_store(s1, s2, cols, c, w.col, partials + (size_t)blockIdx.x * 2 * c);
+}
+
+// dx = γ·rstd·(dy − mean(dy) − x̂·mean(dy·x̂));  grad_residual = grad_out ⊙ [out > 0];  dγ = Σ dy·x̂, dβ = Σ dy
+template <typename XT, typename OT>
+__global__ void __launch_bounds__(kDenseBlock)
+bn_bwd_apply_kernel(long long rows, int c, const OT *__restrict__ grad_out, const OT *__restrict__ out,
+                    const XT *__restrict__ x, const float *__restrict__ stats, const float *__restrict__ gamma,
+                    const float *__restrict__ row_scale, const double *__restrict__ sums, double inv_rows,
+                    XT *__restrict__ grad_x, OT *__restrict__ grad_residual, float *__restrict__ grad_gamma,
+                    float *__restrict__ grad_beta) {
+    const int cols = c >> 2;
+    const ColWalk w = col_walk(cols, kDenseBlock);
+    pdl_wait();
+    const bool writer = (long long)blockIdx.x * kDenseBlock + threadIdx.x < cols;
+    float mean[4], rstd[4], a[4], m1[4], m2[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int ch = 4 * w.col + j;
+        mean[j] = stats[ch];
+        rstd[j] = stats[c + ch];
+        a[j] = __ldg(gamma + ch) * rstd[j];
+        const double S1 = sums[ch], S2 = sums[c + ch];
+        m1[j] = (float)(S1 * inv_rows);
+        m2[j] = (float)(S2 * inv_rows);
+        if (writer) {
+            grad_beta[ch] = (float)S1;
+            grad_gamma[ch] = (float)S2;
+        }
+    }
+    const XT *px = x + 4 * w.col;
+    const OT *pg = grad_out + 4 * w.col;
+    const OT *po = out ? out + 4 * w.col : nullptr;
+    XT *pdx = grad_x + 4 * w.col;
+    OT *pdr = grad_residual ? grad_residual + 4 * w.col : nullptr;
+    for (long long row = w.row; row < rows; row += w.row_step) {
+        float4 g = ld4(pg + row * c);
+        const float4 v = ld4(px + row * c);
+        if (po) {
+            const float4 o = ld4(po + row * c);
+            g.x = o.x > 0.f ? g.x : 0.f; g.y = o.y > 0.f ? g.y : 0.f;
+            g.z = o.z > 0.f ? g.z : 0.f; g.w = o.w > 0.f ? g.w : 0.f;
+        }
+        if (pdr) st4(pdr + row * c, g);
+        if (row_scale) {
+            const float r = __ldg(row_scale + row);
+            g.x *= r; g.y *= r; g.z *= r; g.w *= r;
+        }
+        float4 d;
+        d.x = a[0] * (g.x - m1[0] - (v.x - mean[0]) * rstd[0] * m2[0]);
+        d.y = a[1] * (g.y - m1[1] - (v.y - mean[1]) * rstd[1] * m2[1]);
+        d.z = a[2] * (g.z - m1[2] - (v.z - mean[2]) * rstd[2] * m2[2]);
+        d.w = a[3] * (g.w - m1[3] - (v.w - mean[3]) * rstd[3] * m2[3]);
+        st4(pdx + row * c, d);
+    }
+}
+
+// ---- weight-encoding tail on (rows, G): u = rel + upe + cst;  logits = W2 · ReLU(BN(u)) + b2 --------------------------
+template <int G>
+struct TailRow {
+    float u[G];
+    __device__ __forceinline__ void load(const float *__restrict__ rel, const float *__restrict__ upe, const float *cst,
+                                         long long row) {
+        const float2 *a = reinterpret_cast<const float2 *>(rel + row * G);
+#pragma unroll
+        for (int j = 0; j < G / 2; ++j) {
+            const float2 v = __ldg(a + j);
+            u[2 * j] = v.x;
+            u[2 * j + 1] = v.y;
+        }
+        if (upe) {
+            const float2 *b = reinterpret_cast<const float2 *>(upe + row * G);
+#pragma unroll
+            for (int j = 0; j < G / 2; ++j) {
+                const float2 v = __ldg(b + j);
+                u[2 * j] += v.x;
+                u[2 * j + 1] += v.y;
+            }
+        }
+        if (cst) {
+#pragma unroll
+            for (int j = 0; j < G; ++j) u[j] += cst[j];
+        }
+    }
+};
+
+template <int G>
+__global__ void __launch_bounds__(kDenseBlock)
+we_partial_kernel(long long rows, const float *__restrict__ rel, const float *__restrict__ upe,
+                  const float *__restrict__ cst, float *__restrict__ partials) {
+    __shared__ float s_c[G];
+    pdl_trigger();
+    if (cst && threadIdx.x < G) s_c[threadIdx.x] = cst[threadIdx.x];
+    __syncthreads();
+    float acc[2 * G];
+#pragma unroll
+    for (int j = 0; j < 2 * G; ++j) acc[j] = 0.f;
+    for (long long row = (long long)blockIdx.x * kDenseBlock + threadIdx.x; row < rows;
+         row += (long long)gridDim.x * kDenseBlock) {
+        TailRow<G> r;
+        r.load(rel, upe, cst ? s_c : nullptr, row);
+#pragma unroll
+        for (int j = 0; j < G; ++j) {
+            acc[j] += r.u[j];
+            acc[G + j] = fmaf(r.u[j], r.u[j], acc[G + j]);
+        }
+    }
+    block_reduce_store<2 * G>(acc, partials + (size_t)blockIdx.x * 2 * G);
+}
+
+template <int G>
+struct TailParams {   // shared-memory copy of the per-channel maps and the G x G layer
+    float cst[G], mean[G], sc[G], beta[G], rstd[G], w[G * G], b[G];
+};
+
+template <int G>
+__global__ void __launch_bounds__(kDenseBlock)
+we_apply_kernel(long long rows, const float *__restrict__ rel, const float *__restrict__ upe,
+                const float *__restrict__ cst, const double *__restrict__ sums, double inv_rows, float eps,
+                const float *__restrict__ gamma, const float *__restrict__ beta, const float *__restrict__ w2,
+                const float *__restrict__ b2, float *__restrict__ logits, float *__restrict__ stats_out,
+                float *__restrict__ running_mean, float *__restrict__ running_var, float momentum, float unbias) {
+    __shared__ TailParams<G> P;
+    pdl_wait();
+    const int t = threadIdx.x;
+    if (t < G) {
+        float var;
+        const ChanStat st = stat_from_sums(sums[t], sums[G + t], inv_rows, eps, &var);
+        P.cst[t] = cst ? cst[t] : 0.f;
+        P.mean[t] = st.mean;
+        P.sc[t] = gamma[t] * st.rstd;
+        P.beta[t] = beta[t];
+        P.b[t] = b2 ? b2[t] : 0.f;
+        if (blockIdx.x == 0) {
+            stats_out[t] = st.mean;
+            stats_out[G + t] = st.rstd;
+            if (running_mean) running_mean[t] = (1.f - momentum) * running_mean[t] + momentum * st.mean;
+            if (running_var) running_var[t] = (1.f - momentum) * running_var[t] + momentum * var * unbias;
+        }
+    }
+    for (int i = t; i < G * G; i += kDenseBlock) P.w[i] = w2[i];
+    __syncthreads();
+    for (long long row = (long long)blockIdx.x * kDenseBlock + t; row < rows; row += (long long)gridDim.x * kDenseBlock) {
+        TailRow<G> r;
+        r.load(rel, upe, cst ? P.cst : nullptr, row);
+        float h[G];
+#pragma unroll
+        for (int j = 0; j < G; ++j) h[j] = fmaxf(fmaf(r.u[j] - P.mean[j], P.sc[j], P.beta[j]), 0.f);
+        float2 *o = reinterpret_cast<float2 *>(logits + row * G);
+#pragma unroll
+        for (int i = 0; i < G; i += 2) {
+            float y0 = P.b[i], y1 = P.b[i + 1];
+#pragma unroll
+            for (int j = 0; j < G; ++j) {
+                y0 = fmaf(P.w[i * G + j], h[j], y0);
+                y1 = fmaf(P.w[(i + 1) * G + j], h[j], y1);
+            }
+            o[i / 2] = make_float2(y0, y1);
+        }
+    }
+}
+
+// Backward, pass 1.  Per row: h (recomputed), dl = grad_logits row, dh = (W2ᵀ dl) ⊙ [h > 0].
+// partial row (width 3G + G·G) = [ Σ dh | Σ dh·x̂ | Σ dl | Σ dl_i·h_j ].  gridDim.y slices of IB rows of the G x G
+// block keep the per-thread accumulators in registers; slice 0 also owns the three G-wide sums.
+template <int G, int IB>
+__global__ void __launch_bounds__(kDenseBlock)
+we_bwd_partial_kernel(long long rows, const float *__restrict__ rel, const float *__restrict__ upe,
+                      const float *__restrict__ cst, const float *__restrict__ grad_logits,
+                      const float *__restrict__ stats, const float *__restrict__ gamma, const float *__restrict__ beta,
+                      const float *__restrict__ w2, float *__restrict__ partials) {
+    __shared__ TailParams<G> P;
+    pdl_trigger();
+    const int t = threadIdx.x;
+    if (t < G) {
+        P.cst[t] = cst ? cst[t] : 0.f;
+        P.mean[t] = stats[t];
+        P.rstd[t] = stats[G + t];
+        P.sc[t] = gamma[t] * stats[G + t];
+        P.beta[t] = beta[t];
+    }
+    for (int i = t; i < G * G; i += kDenseBlock) P.w[i] = w2[i];
+    __syncthreads();
+    const int i0 = blockIdx.y * IB;
+    const bool lead = blockIdx.y == 0;
+    float s[3 * G], wacc[IB * G];
+#pragma unroll
+    for (int j = 0; j < 3 * G; ++j) s[j] = 0.f;
+#pragma unroll
+    for (int j = 0; j < IB * G; ++j) wacc[j] = 0.f;
+    for (long long row = (long long)blockIdx.x * kDenseBlock + t; row < rows; row += (long long)gridDim.x * kDenseBlock) {
+        TailRow<G> r;
+        r.load(rel, upe, cst ? P.cst : nullptr, row);
+        float dl[G], h[G];
+        const float2 *gp = reinterpret_cast<const float2 *>(grad_logits + row * G);
+#pragma unroll
+        for (int j = 0; j < G / 2; ++j) {
+            const float2 v = __ldg(gp + j);
+            dl[2 * j] = v.x;
+            dl[2 * j + 1] = v.y;
+        }
+#pragma unroll
+        for (int j = 0; j < G; ++j) h[j] = fmaxf(fmaf(r.u[j] - P.mean[j], P.sc[j], P.beta[j]), 0.f);
+        // Σ dl_i·h_j for this slice's rows i0 .. i0 + IB - 1 (i0 is CTA-uniform: the select compiles to a shared index)
+#pragma unroll
+        for (int i = 0; i < IB; ++i) {
+            float di = 0.f;
+#pragma unroll
+            for (int q = 0; q < G; ++q) di = (q == i0 + i) ? dl[q] : di;
+#pragma unroll
+            for (int j = 0; j < G; ++j) wacc[i * G + j] = fmaf(di, h[j], wacc[i * G + j]);
+        }
+        if (lead) {
+#pragma unroll
+            for (int j = 0; j < G; ++j) {
+                float dh = 0.f;
+#pragma unroll
+                for (int i = 0; i < G; ++i) dh = fmaf(P.w[i * G + j], dl[i], dh);
+                dh = h[j] > 0.f ? dh : 0.f;
+                s[j] += dh;
+                s[G + j] = fmaf(dh, (r.u[j] - P.mean[j]) * P.rstd[j], s[G + j]);
+                s[2 * G + j] += dl[j];
+            }
+        }
+    }
+    float *prow = partials + (size_t)blockIdx.x * (3 * G + G * G);
+    if (lead) block_reduce_store<3 * G>(s, prow);
+    __syncthreads();
+    block_reduce_store<IB * G>(wacc, prow + 3 * G + i0 * G);
+}
+
+// Backward, pass 2: du = γ·rstd·(dh − mean(dh) − x̂·mean(dh·x̂)); parameter gradients from the reduced sums.
+template <int G>
+__global__ void __launch_bounds__(kDenseBlock)
+we_bwd_apply_kernel(long long rows, const float *__restrict__ rel, const float *__restrict__ upe,
+                    const float *__restrict__ cst, const float *__restrict__ grad_logits,
+                    const float *__restrict__ stats, const float *__restrict__ gamma, const float *__restrict__ beta,
+                    const float *__restrict__ w2, const double *__restrict__ sums, double inv_rows,
+                    float *__restrict__ grad_u, float *__restrict__ grad_gamma, float *__restrict__ grad_beta,
+                    float *__restrict__ grad_b2, float *__restrict__ grad_w2) {
+    __shared__ TailParams<G> P;
+    __shared__ float m1[G], m2[G];
+    pdl_wait();
+    const int t = threadIdx.x;
+    if (t < G) {
+        P.cst[t] = cst ? cst[t] : 0.f;
+        P.mean[t] = stats[t];
+        P.rstd[t] = stats[G + t];
+        P.sc[t] = gamma[t] * stats[G + t];
+        P.beta[t] = beta[t];
+        m1[t] = (float)(sums[t] * inv_rows);
+        m2[t] = (float)(sums[G + t] * inv_rows);
+        if (blockIdx.x == 0) {
+            grad_beta[t] = (float)sums[t];
+            grad_gamma[t] = (float)sums[G + t];
+            grad_b2[t] = (float)sums[2 * G + t];
+        }
+    }
+    for (int i = t; i < G * G; i += kDenseBlock) {
+        P.w[i] = w2[i];
+        if (blockIdx.x == 0) grad_w2[i] = (float)sums[3 * G + i];
+    }
+    __syncthreads();
+    for (long long row = (long long)blockIdx.x * kDenseBlock + t; row < rows; row += (long long)gridDim.x * kDenseBlock) {
+        TailRow<G> r;
+        r.load(rel, upe, cst ? P.cst : nullptr, row);
+        float dl[G];
+        const float2 *gp = reinterpret_cast<const float2 *>(grad_logits + row * G);
+#pragma unroll
+        for (int j = 0; j < G / 2; ++j) {
+            const float2 v = __ldg(gp + j);
+            dl[2 * j] = v.x;
+            dl[2 * j + 1] = v.y;
+        }
+        float2 *o = reinterpret_cast<float2 *>(grad_u + row * G);
+        float du[2];
+#pragma unroll
+        for (int j = 0; j < G; ++j) {
+            const float xc = r.u[j] - P.mean[j];
+            const float hpre = fmaf(xc, P.sc[j], P.beta[j]);
+            float dh = 0.f;
+#pragma unroll
+            for (int i = 0; i < G; ++i) dh = fmaf(P.w[i * G + j], dl[i], dh);
+            dh = hpre > 0.f ? dh : 0.f;
+            du[j & 1] = P.sc[j] * (dh - m1[j] - xc * P.rstd[j] * m2[j]);
+            if (j & 1) o[j / 2] = make_float2(du[0], du[1]);
+        }
+    }
+}
+
+// ---- host side ----------------------------------------------------------------------------------------------------
+static size_t a256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static int bn_grid(long long rows, int c) { return col_grid(rows, c >> 2, kDenseBlock, kDenseCtasPerSm); }
+static int row_grid(long long rows) { return stride_grid(rows, kDenseBlock, kDenseCtasPerSm); }
+static bool bn_width_ok(int c) { return c >= 4 && (c & 3) == 0 && c <= 4 * kDenseBlock; }
+
+template <typename XT, typename OT>
+static int bn_forward_t(long long rows, int c, const void *x, const float *gamma, const float *beta, float eps,
+                        const void *residual, const float *row_scale, int relu, void *out, float *stats_out,
+                        float *running_mean, float *running_var, float momentum, const float *mean_shift, float *partials,
+                        double *sums, cudaStream_t st) {
+    const int grid = bn_grid(rows, c);
+    const bool pdl = tuning(kTunePdl) != 2;
+    bn_partial_kernel<XT><<<grid, kDenseBlock, 0, st>>>(rows, c, static_cast<const XT *>(x), partials);
+    launch_chain(pdl, partials_reduce_kernel, div_up(2 * c, 32), 256, 0, st, grid, 2 * c, (const float *)partials, sums);
+    const float unbias = rows > 1 ? (float)((double)rows / (double)(rows - 1)) : 1.f;
+    launch_chain(pdl, bn_apply_kernel<XT, OT>, grid, kDenseBlock, 0, st, rows, c, static_cast<const XT *>(x),
+                 (const double *)sums, 1.0 / (double)rows, eps, gamma, beta, static_cast<const OT *>(residual), row_scale,
+                 relu, static_cast<OT *>(out), stats_out, running_mean, running_var, momentum, unbias, mean_shift);
+    return check_launch(3);
+}
+
+template <typename XT, typename OT>
+static int bn_backward_t(long long rows, int c, const void *grad_out, const void *out, const void *x, const float *stats,
+                         const float *gamma, const float *row_scale, void *grad_x, void *grad_residual,
+                         float *grad_gamma, float *grad_beta, float *partials, double *sums, cudaStream_t st) {
+    const int grid = bn_grid(rows, c);
+    const bool pdl = tuning(kTunePdl) != 2;
+    bn_bwd_partial_kernel<XT, OT><<<grid, kDenseBlock, 0, st>>>(rows, c, static_cast<const OT *>(grad_out),
+                                                                static_cast<const OT *>(out), static_cast<const XT *>(x),
+                                                                stats, row_scale, partials);
+    launch_chain(pdl, partials_reduce_kernel, div_up(2 * c, 32), 256, 0, st, grid, 2 * c, (const float *)partials, sums);
+    launch_chain(pdl, bn_bwd_apply_kernel<XT, OT>, grid, kDenseBlock, 0, st, rows, c, static_cast<const OT *>(grad_out),
+                 static_cast<const OT *>(out), static_cast<const XT *>(x), stats, gamma, row_scale, (const double *)sums,
+                 1.0 / (double)rows, static_cast<XT *>(grad_x), static_cast<OT *>(grad_residual), grad_gamma, grad_beta);
+    return check_launch(3);
+}
+
+template <int G, int IB>
+static int we_forward_t(long long rows, const float *rel, const float *upe, const float *cst, const float *gamma,
+                        const float *beta, float eps, const float *w2, const float *b2, float *logits, float *stats_out,
+                        float *running_mean, float *running_var, float momentum, float *partials, double *sums,
+                        cudaStream_t st) {
+    const int grid = row_grid(rows);
+    const bool pdl = tuning(kTunePdl) != 2;
+    we_partial_kernel<G><<<grid, kDenseBlock, 0, st>>>(rows, rel, upe, cst, partials);
+    launch_chain(pdl, partials_reduce_kernel, div_up(2 * G, 32), 256, 0, st, grid, 2 * G, (const float *)partials, sums);
+    const float unbias = rows > 1 ? (float)((double)rows / (double)(rows - 1)) : 1.f;
+    launch_chain(pdl, we_apply_kernel<G>, grid, kDenseBlock, 0, st, rows, rel, upe, cst, (const double *)sums,
+                 1.0 / (double)rows, eps, gamma, beta, w2, b2, logits, stats_out, running_mean, running_var, momentum, unbias);
+    return check_launch(3);
+}
+
+template <int G, int IB>
+static int we_backward_t(long long rows, const float *rel, const float *upe, const float *cst, const float *grad_logits,
+                         const float *stats, const float *gamma, const float *beta, const float *w2, float *grad_u,
+                         float *grad_gamma, float *grad_beta, float *grad_b2, float *grad_w2, float *partials, double *sums,
+                         cudaStream_t st) {
+    const int grid = row_grid(rows);
+    const bool pdl = tuning(kTunePdl) != 2;
+    const int width = 3 * G + G * G;
+    we_bwd_partial_kernel<G, IB><<<dim3(grid, G / IB), kDenseBlock, 0, st>>>(rows, rel, upe, cst, grad_logits, stats, gamma,
+                                                                             beta, w2, partials);
+    launch_chain(pdl, partials_reduce_kernel, div_up(width, 32), 256, 0, st, grid, width, (const float *)partials, sums);
+    launch_chain(pdl, we_bwd_apply_kernel<G>, grid, kDenseBlock, 0, st, rows, rel, upe, cst, grad_logits, stats, gamma, beta,
+                 w2, (const double *)sums, 1.0 / (double)rows, grad_u, grad_gamma, grad_beta, grad_b2, grad_w2);
+    return check_launch(3);
+}
+
+}  // namespace aopt
+
+using namespace aopt;
+
+extern "C" int aopt_bn_act_supported(int c) { return bn_width_ok(c) ? 1 : 0; }
+extern "C" int aopt_we_tail_supported(int g) { return (g == 6 || g == 12) ? 1 : 0; }
+
+// partial rows (<= kDenseMaxGrid of them) + the fp64 sums
+extern "C" size_t aopt_dense_workspace_bytes(int width) {
+    if (width < 1) width = 1;
+    return a256(4 * (size_t)kDenseMaxGrid * width) + a256(8 * (size_t)width);
+}
+
+static bool carve_dense(void *ws, size_t ws_bytes, int width, float **partials, double **sums) {
+    if (!ws || ws_bytes < aopt_dense_workspace_bytes(width)) return false;
+    *partials = static_cast<float *>(ws);
+    *sums = reinterpret_cast<double *>(static_cast<char *>(ws) + a256(4 * (size_t)kDenseMaxGrid * width));
+    return true;
+}
+
+extern "C" int aopt_bn_act_forward(int64_t rows, int c, const void *x, int x_dtype, const float *gamma, const float *beta,
+                                   float eps, const void *residual, const float *row_scale, int relu, void *out,
+                                   int out_dtype, float *stats_out, float *running_mean, float *running_var,
+                                   float momentum, const float *mean_shift, void *workspace, size_t workspace_bytes,
+                                   aopt_stream_t stream) {
+    if (rows <= 0 || !bn_width_ok(c) || !x || !gamma || !beta || !out || !stats_out) return AOPT_ERR_INVALID_ARGUMENT;
+    if ((x_dtype | out_dtype) & ~1) return AOPT_ERR_INVALID_ARGUMENT;
+    float *partials;
+    double *sums;
+    if (!carve_dense(workspace, workspace_bytes, 2 * c, &partials, &sums)) return AOPT_ERR_WORKSPACE;
+    cudaStream_t st = as_stream(stream);
+#define AOPT_BN_FWD(XT, OT)                                                                                               \
+    return bn_forward_t<XT, OT>(rows, c, x, gamma, beta, eps, residual, row_scale, relu, out, stats_out, running_mean,   \
+                                running_var, momentum, mean_shift, partials, sums, st)
+    if (x_dtype == AOPT_F32 && out_dtype == AOPT_F32) AOPT_BN_FWD(float, float);
+    if (x_dtype == AOPT_F32 && out_dtype == AOPT_BF16) AOPT_BN_FWD(float, __nv_bfloat16);
+    if (x_dtype == AOPT_BF16 && out_dtype == AOPT_F32) AOPT_BN_FWD(__nv_bfloat16, float);
+    AOPT_BN_FWD(__nv_bfloat16, __nv_bfloat16);
+#undef AOPT_BN_FWD
+}
+
+extern "C" int aopt_bn_act_backward(int64_t rows, int c, const void *grad_out, const void *out, int out_dtype, const void *x,
+                                    int x_dtype, const float *stats, const float *gamma, const float *row_scale,
+                                    void *grad_x, void *grad_residual, float *grad_gamma, float *grad_beta,
+                                    void *workspace, size_t workspace_bytes, aopt_stream_t stream) {
+    if (rows <= 0 || !bn_width_ok(c) || !grad_out || !x || !stats || !gamma || !grad_x || !grad_gamma || !grad_beta)
+        return AOPT_ERR_INVALID_ARGUMENT;
+    if ((x_dtype | out_dtype) & ~1) return AOPT_ERR_INVALID_ARGUMENT;
+    float *partials;
+    double *sums;
+    if (!carve_dense(workspace, workspace_bytes, 2 * c, &partials, &sums)) return AOPT_ERR_WORKSPACE;
+    cudaStream_t st = as_stream(stream);
+#define AOPT_BN_BWD(XT, OT)                                                                                               \
+    return bn_backward_t<XT, OT>(rows, c, grad_out, out, x, stats, gamma, row_scale, grad_x, grad_residual, grad_gamma,  \
+                                 grad_beta, partials, sums, st)
+    if (x_dtype == AOPT_F32 && out_dtype == AOPT_F32) AOPT_BN_BWD(float, float);
+    if (x_dtype == AOPT_F32 && out_dtype == AOPT_BF16) AOPT_BN_BWD(float, __nv_bfloat16);
+    if (x_dtype == AOPT_BF16 && out_dtype == AOPT_F32) AOPT_BN_BWD(__nv_bfloat16, float);
+    AOPT_BN_BWD(__nv_bfloat16, __nv_bfloat16);
+#undef AOPT_BN_BWD
+}
+
+extern "C" int aopt_we_tail_forward(int64_t rows, int g, const float *rel, const float *upe, const float *cst,
+                                    const float *gamma, const float *beta, float eps, const float *w2, const float *b2,
+                                    float *logits, float *stats_out, float *running_mean, float *running_var,
+                                    float momentum, void *workspace, size_t workspace_bytes, aopt_stream_t stream) {
+    if (rows <= 0 || !rel || !gamma || !beta || !w2 || !logits || !stats_out) return AOPT_ERR_INVALID_ARGUMENT;
+    if (!aopt_we_tail_supported(g)) return AOPT_ERR_UNSUPPORTED;
+    float *partials;
+    double *sums;
+    if (!carve_dense(workspace, workspace_bytes, 3 * g + g * g, &partials, &sums)) return AOPT_ERR_WORKSPACE;
+    cudaStream_t st = as_stream(stream);
+    if (g == 6)
+        return we_forward_t<6, 6>(rows, rel, upe, cst, gamma, beta, eps, w2, b2, logits, stats_out, running_mean, running_var,
+                                  momentum, partials, sums, st);
+    return we_forward_t<12, 4>(rows, rel, upe, cst, gamma, beta, eps, w2, b2, logits, stats_out, running_mean, running_var,
+                               momentum, partials, sums, st);
+}
+
+extern "C" int aopt_we_tail_backward(int64_t rows, int g, const float *rel, const float *upe, const float *cst,
+                                     const float *grad_logits, const float *stats, const float *gamma, const float *beta,
+                                     const float *w2, float *grad_u, float *grad_gamma, float *grad_beta, float *grad_b2,
+                                     float *grad_w2, void *workspace, size_t workspace_bytes, aopt_stream_t stream) {
+    if (rows <= 0 || !rel || !grad_logits || !stats || !gamma || !beta || !w2 || !grad_u || !grad_gamma || !grad_beta ||
+        !grad_b2 || !grad_w2)
+        return AOPT_ERR_INVALID_ARGUMENT;
+    if (!aopt_we_tail_supported(g)) return AOPT_ERR_UNSUPPORTED;
+    float *partials;
+    double *sums;
+    if (!carve_dense(workspace, workspace_bytes, 3 * g + g * g, &partials, &sums)) return AOPT_ERR_WORKSPACE;
+    cudaStream_t st = as_stream(stream);
+    if (g == 6)
+        return we_backward_t<6, 6>(rows, rel, upe, cst, grad_logits, stats, gamma, beta, w2, grad_u, grad_gamma, grad_beta,
+                                   grad_b2, grad_w2, partials, sums, st);
+    return we_backward_t<12, 4>(rows, rel, upe, cst, grad_logits, stats, gamma, beta, w2, grad_u, grad_gamma, grad_beta,
+                                grad_b2, grad_w2, partials, sums, st);
+}

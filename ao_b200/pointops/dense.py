@@ -1,0 +1,254 @@
+"""BatchNorm-shaped element-wise work around the dense layers of a PTv2 block (new operators).
+
+    bn_act(x, bn, relu, residual, row_scale)   [ReLU]([residual +] [row_scale ·] BatchNorm_train(x))  on (rows, C)
+        PointBatchNorm (+ nn.ReLU, DropPath, residual add):
+        /root/reference/pointcept/models/point_transformer_v2/point_transformer_v2m2_base.py:25-45,187-197
+    we_tail(rel, upe, cst, bn, lin)            Linear(G,G)(ReLU(BatchNorm_train(rel + upe + cst)))    on (N, k, G)
+        weight_encoding[1:] of GroupedVectorAttention (:94-99,120)
+
+Kernels: ao_b200/csrc/dense.cu (fp32 statistics, fp64 combination, no atomics).  These replace ATen's BatchNorm /
+ReLU / cast / skinny-GEMM kernels in TRAINING mode; in evaluation mode (running statistics) the torch modules run.
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+from torch.autograd import Function
+
+from .. import _lib
+
+_DT = {torch.float32: 0, torch.bfloat16: 1}
+
+
+def fused_dense_enabled() -> bool:
+    """AOPT_FUSED_DENSE=0 routes every BatchNorm site back through torch.nn (A/B measurements, tests)."""
+    return os.environ.get("AOPT_FUSED_DENSE", "1") != "0"
+
+
+def bn_act_supported(channels: int) -> bool:
+    return bool(_lib.load().aopt_bn_act_supported(int(channels)))
+
+
+def we_tail_supported(groups: int) -> bool:
+    return bool(_lib.load().aopt_we_tail_supported(int(groups)))
+
+
+_WS = {}
+
+
+def _dense_ws(width: int, dev: torch.device):
+    """Scratch of the dense kernels (partial rows + fp64 sums), allocated once per (device, stream, width): the
+    calls are stream-ordered, so consecutive operators on one stream can share it; ~100 BatchNorm sites per step would
+    otherwise each pay a size query and an allocator round trip on a host-bound path."""
+    key = (dev.index, _lib.stream(), width)
+    ws = _WS.get(key)
+    if ws is None:
+        ws = _WS[key] = _lib.workspace(_lib.load().aopt_dense_workspace_bytes(width), dev)
+    return ws
+
+
+class _BnActFn(Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, residual, row_scale, running_mean, running_var, momentum, eps, relu, out_dtype,
+                pre_bias):
+        lib = _lib.load()
+        dev = x.device
+        rows, c = x.shape
+        out = torch.empty((rows, c), dtype=out_dtype, device=dev)
+        stats = torch.empty(2 * c, dtype=torch.float32, device=dev)
+        with _lib.on_device(dev):
+            ws = _dense_ws(2 * c, dev)
+            _lib.check(
+                lib.aopt_bn_act_forward(rows, c, x.data_ptr(), _DT[x.dtype], gamma.data_ptr(), beta.data_ptr(), eps,
+                                        _lib.ptr(residual), _lib.ptr(row_scale), int(relu), out.data_ptr(), _DT[out_dtype],
+                                        stats.data_ptr(), _lib.ptr(running_mean), _lib.ptr(running_var), momentum,
+                                        _lib.ptr(pre_bias), ws.data_ptr(), ws.numel(), _lib.stream()),
+                "bn_act_forward")
+        ctx.save_for_backward(x, out if relu else None, gamma, stats, row_scale)
+        ctx.relu = bool(relu)
+        ctx.has_res = residual is not None
+        ctx.bias_like = pre_bias
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        lib = _lib.load()
+        x, out, gamma, stats, row_scale = ctx.saved_tensors
+        dev = x.device
+        rows, c = x.shape
+        odt = out.dtype if out is not None else grad_out.dtype
+        if grad_out.dtype != odt or not grad_out.is_contiguous():
+            grad_out = grad_out.to(odt).contiguous()
+        gx = torch.empty_like(x)
+        want_res = ctx.has_res and ctx.needs_input_grad[3]
+        # without a ReLU the residual's gradient IS grad_out
+        gres = torch.empty_like(grad_out) if (want_res and ctx.relu) else None
+        gg = torch.empty(c, dtype=torch.float32, device=dev)
+        gb = torch.empty(c, dtype=torch.float32, device=dev)
+        with _lib.on_device(dev):
+            ws = _dense_ws(2 * c, dev)
+            _lib.check(
+                lib.aopt_bn_act_backward(rows, c, grad_out.data_ptr(), _lib.ptr(out), _DT[odt], x.data_ptr(), _DT[x.dtype],
+                                         stats.data_ptr(), gamma.data_ptr(), _lib.ptr(row_scale), gx.data_ptr(),
+                                         _lib.ptr(gres), gg.data_ptr(), gb.data_ptr(), ws.data_ptr(), ws.numel(),
+                                         _lib.stream()),
+                "bn_act_backward")
+        if want_res and not ctx.relu:
+            gres = grad_out
+        # a bias in front of a training-mode BatchNorm has an identically zero gradient
+        gpb = torch.zeros_like(ctx.bias_like) if (ctx.bias_like is not None and ctx.needs_input_grad[11]) else None
+        return gx, gg, gb, gres, None, None, None, None, None, None, None, gpb
+
+
+def _torch_bn_act(x, bn, relu, residual, row_scale, out_dtype):
+    y = bn(x)
+    if row_scale is not None:
+        y = y * row_scale.to(y.dtype).unsqueeze(-1)
+    if residual is not None:
+        y = residual + y
+    if relu:
+        y = torch.relu(y)
+    return y if out_dtype is None else y.to(out_dtype)
+
+
+_WIDTH_OK = {}
+
+
+def bn_fusable(bn: torch.nn.Module, c: int, rows: int, is_cuda: bool, dtype: torch.dtype, out_dtype: torch.dtype = None) -> bool:
+    """True when bn_act would run the fused kernels for a (rows, c) input of `dtype` (training-mode statistics, CUDA,
+    fp32 / bf16, supported width)."""
+    bn = getattr(bn, "norm", bn)
+    ok = _WIDTH_OK.get(c)
+    if ok is None:
+        ok = _WIDTH_OK[c] = bn_act_supported(c)
+    return (ok and fused_dense_enabled() and (bn.training or not bn.track_running_stats) and is_cuda and dtype in _DT
+            and rows >= 2 and bn.weight is not None and bn.weight.dtype == torch.float32
+            and (out_dtype is None or out_dtype in _DT))
+
+
+def bn_act_usable(x: torch.Tensor, bn: torch.nn.Module, out_dtype: torch.dtype = None) -> bool:
+    c = x.shape[-1]
+    return bn_fusable(bn, c, x.numel() // max(c, 1), x.is_cuda, x.dtype, out_dtype)
+
+
+def bn_act(x: torch.Tensor, bn: torch.nn.Module, relu: bool = False, residual: torch.Tensor = None,
+           row_scale: torch.Tensor = None, out_dtype: torch.dtype = None, pre_bias: torch.Tensor = None) -> torch.Tensor:
+    """`bn` is a BatchNorm1d (or a module with a `.norm` BatchNorm1d: the reference's PointBatchNorm).  x is (N, C) or
+    (N, L, C); statistics over all leading dimensions, like PointBatchNorm.  Returns
+        [relu]( [residual +] [row_scale[:, None] *] bn(x) )       in out_dtype (default: x.dtype, or the residual's),
+    and updates the running statistics like nn.BatchNorm1d.  row_scale (N,) fp32 carries DropPath (mask / keep_prob).
+    pre_bias (C,): a bias the caller did NOT add to x because training-mode normalisation removes it (the bias of the
+    Linear in front): it only shifts the running mean, and receives a zero gradient.  Only with bn_act_usable()."""
+    bn = getattr(bn, "norm", bn)
+    c = x.shape[-1]
+    rows = x.numel() // max(c, 1)
+    if not bn_act_usable(x, bn, out_dtype):
+        if pre_bias is not None:
+            x = x + pre_bias.to(x.dtype)
+        shape = x.shape
+        y = _torch_bn_act(x.reshape(rows, c), bn, relu, None if residual is None else residual.reshape(rows, c), row_scale,
+                          out_dtype)
+        return y.view(shape)
+    shape = x.shape
+    x2 = x.reshape(rows, c)
+    if not x2.is_contiguous():
+        x2 = x2.contiguous()
+    if out_dtype is None:
+        out_dtype = x.dtype if residual is None else torch.promote_types(x.dtype, residual.dtype)
+    if residual is not None:
+        residual = residual.reshape(rows, c)
+        if residual.dtype != out_dtype or not residual.is_contiguous():
+            residual = residual.to(out_dtype).contiguous()
+    if row_scale is not None:
+        row_scale = row_scale.reshape(rows).float().contiguous()
+    track = bn.training and bn.track_running_stats
+    momentum = 0.0
+    if track:
+        bn.num_batches_tracked.add_(1)
+        momentum = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
+    if pre_bias is not None and (pre_bias.dtype != torch.float32 or not pre_bias.is_contiguous()):
+        pre_bias = pre_bias.float().contiguous()
+    out = _BnActFn.apply(x2, bn.weight, bn.bias, residual, row_scale, bn.running_mean if track else None,
+                         bn.running_var if track else None, float(momentum), float(bn.eps), bool(relu), out_dtype, pre_bias)
+    return out.view(shape)
+
+
+class _WeTailFn(Function):
+    @staticmethod
+    def forward(ctx, rel, upe, cst, gamma, beta, w2, b2, running_mean, running_var, momentum, eps):
+        lib = _lib.load()
+        dev = rel.device
+        g = rel.shape[-1]
+        rows = rel.numel() // g
+        logits = torch.empty_like(rel)
+        stats = torch.empty(2 * g, dtype=torch.float32, device=dev)
+        with _lib.on_device(dev):
+            ws = _dense_ws(3 * g + g * g, dev)
+            _lib.check(
+                lib.aopt_we_tail_forward(rows, g, rel.data_ptr(), _lib.ptr(upe), _lib.ptr(cst), gamma.data_ptr(),
+                                         beta.data_ptr(), eps, w2.data_ptr(), _lib.ptr(b2), logits.data_ptr(),
+                                         stats.data_ptr(), _lib.ptr(running_mean), _lib.ptr(running_var), momentum,
+                                         ws.data_ptr(), ws.numel(), _lib.stream()),
+                "we_tail_forward")
+        ctx.save_for_backward(rel, upe, cst, gamma, beta, w2, stats)
+        ctx.has_b2 = b2 is not None
+        return logits
+
+    @staticmethod
+    def backward(ctx, grad_logits):
+        lib = _lib.load()
+        rel, upe, cst, gamma, beta, w2, stats = ctx.saved_tensors
+        dev = rel.device
+        g = rel.shape[-1]
+        rows = rel.numel() // g
+        grad_logits = grad_logits.float().contiguous()
+        gu = torch.empty_like(rel)
+        gg, gb, gb2 = (torch.empty(g, dtype=torch.float32, device=dev) for _ in range(3))
+        gw2 = torch.empty((g, g), dtype=torch.float32, device=dev)
+        with _lib.on_device(dev):
+            ws = _dense_ws(3 * g + g * g, dev)
+            _lib.check(
+                lib.aopt_we_tail_backward(rows, g, rel.data_ptr(), _lib.ptr(upe), _lib.ptr(cst), grad_logits.data_ptr(),
+                                          stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), w2.data_ptr(), gu.data_ptr(),
+                                          gg.data_ptr(), gb.data_ptr(), gb2.data_ptr(), gw2.data_ptr(), ws.data_ptr(),
+                                          ws.numel(), _lib.stream()),
+                "we_tail_backward")
+        # cst sits in front of a training-mode BatchNorm: its gradient (the column sums of grad_u) is identically zero
+        gcst = torch.zeros_like(cst) if (cst is not None and ctx.needs_input_grad[2]) else None
+        return (gu, gu if upe is not None else None, gcst, gg, gb, gw2, gb2 if ctx.has_b2 else None,
+                None, None, None, None)
+
+
+def we_tail_usable(rel: torch.Tensor, bn: torch.nn.Module) -> bool:
+    bn = getattr(bn, "norm", bn)
+    return (fused_dense_enabled() and rel.is_cuda and rel.dtype == torch.float32 and (bn.training or not bn.track_running_stats)
+            and bn.weight is not None and rel.numel() // rel.shape[-1] >= 2 and we_tail_supported(rel.shape[-1]))
+
+
+def we_tail(rel: torch.Tensor, upe: torch.Tensor, cst: torch.Tensor, bn: torch.nn.Module, lin: torch.nn.Linear) -> torch.Tensor:
+    """logits = lin(ReLU(bn(rel + upe + cst))) with `bn` / `lin` = weight_encoding[1] / weight_encoding[3]; rel, upe
+    (..., G) fp32, cst (G) or None.  Training-mode statistics only (check with we_tail_usable); G in {6, 12}."""
+    bn = getattr(bn, "norm", bn)
+    _lib.require_cuda(rel, lin.weight)
+    if not we_tail_usable(rel, bn):
+        raise ValueError("we_tail: unsupported input (see we_tail_usable)")
+    g = rel.shape[-1]
+    rel = rel.contiguous()
+    if upe is not None:
+        upe = upe.float().contiguous()
+        if upe.shape != rel.shape:
+            raise ValueError("we_tail: upe must have rel's shape")
+    if cst is not None:
+        cst = cst.float().contiguous()
+        if cst.numel() != g:
+            raise ValueError("we_tail: cst must have G entries")
+    track = bn.training and bn.track_running_stats
+    momentum = 0.0
+    if track:
+        bn.num_batches_tracked.add_(1)
+        momentum = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
+    f = lambda t: t if t.dtype == torch.float32 and t.is_contiguous() else t.float().contiguous()
+    return _WeTailFn.apply(rel, upe, cst, f(bn.weight), f(bn.bias), f(lin.weight), None if lin.bias is None else f(lin.bias),
+                           bn.running_mean if track else None, bn.running_var if track else None, float(momentum),
+                           float(bn.eps))

@@ -19,6 +19,11 @@ replayed.  What changes is the op schedule underneath:
   2 permuted copies, 2 segment_csr (:244-269)
   interpolation: 3 gather+mul+add passes (:311)            pointops.interpolation (fused fwd, CSR bwd)
 
+  PointBatchNorm + ReLU (+ DropPath + residual) as 3-6   pointops.bn_act: statistics + apply, two passes, fp32 /
+  ATen kernels per site, dtype casts in between            bf16 in and out (training mode)
+  weight_encoding[1:] on (N,k,G): BN, ReLU, cast,          pointops.we_tail (with the additions that form its input)
+  (N·k,G)x(G,G) GEMM, cast
+
 Dense per-point Linear layers stay torch.nn.Linear (cuBLAS tensor cores; bf16 under autocast).
 """
 from __future__ import annotations
@@ -77,6 +82,39 @@ class PointBatchNorm(nn.Module):
         raise NotImplementedError
 
 
+def _autocast_dtype():
+    return torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled() else None
+
+
+def run_seq(seq, x, out_dtype=None):
+    """nn.Sequential forward with every [PointBatchNorm, ReLU] pair (or lone PointBatchNorm) routed through
+    pointops.bn_act — the Linear -> PointBatchNorm -> ReLU triples of the reference (…v2m2_base.py:86-93,240-242,
+    288-295,363-364,566-571).  out_dtype: element type wanted from a trailing BatchNorm stage (saves a cast kernel)."""
+    mods = list(seq)
+    i = 0
+    pre_bias = None
+    while i < len(mods):
+        m = mods[i]
+        if isinstance(m, PointBatchNorm):
+            relu = i + 1 < len(mods) and isinstance(mods[i + 1], nn.ReLU)
+            last = i + (2 if relu else 1) >= len(mods)
+            x = pointops.bn_act(x, m.norm, relu=relu, out_dtype=out_dtype if last else None, pre_bias=pre_bias)
+            pre_bias = None
+            i += 2 if relu else 1
+        elif (isinstance(m, nn.Linear) and m.bias is not None and i + 1 < len(mods) and isinstance(mods[i + 1], PointBatchNorm)
+              and pointops.bn_fusable(mods[i + 1].norm, m.out_features, x.numel() // max(x.shape[-1], 1), x.is_cuda,
+                                      _autocast_dtype() or x.dtype)):
+            # the bias of a Linear in front of a training-mode BatchNorm cancels in the output: the GEMM runs without it
+            # (no bias-gradient reduction over the rows in the backward pass); bn_act adds it to the running mean
+            x = nn.functional.linear(x, m.weight)
+            pre_bias = m.bias
+            i += 1
+        else:
+            x = m(x)
+            i += 1
+    return x
+
+
 class GroupedVectorAttention(nn.Module):
     def __init__(self, embed_channels, groups, attn_drop_rate=0.0, qkv_bias=True, pe_multiplier=False,
                  pe_bias=True):
@@ -105,7 +143,7 @@ class GroupedVectorAttention(nn.Module):
         self.attn_drop = nn.Dropout(attn_drop_rate)
 
     def forward(self, feat, coord, reference_index, pos=None, pos_moments=None):
-        query, key, value = self.linear_q(feat), self.linear_k(feat), self.linear_v(feat)
+        query, key, value = run_seq(self.linear_q, feat), run_seq(self.linear_k, feat), self.linear_v(feat)
         if pos is None:                                                       # (N,k,3): depends only on (idx, coord)
             pos = pointops.group_xyz(reference_index, coord)                  # :109,:111
         if (self.pe_bias and not self.pe_multiplier and fused_pe_enabled()
@@ -121,9 +159,9 @@ class GroupedVectorAttention(nn.Module):
                 # bf16 tensor-core fused MLP: used where the torch path would run in bf16 anyway (autocast)
                 peb = pointops.pe_bias_mlp(pos, self.linear_p_bias, pos_moments)
             else:
-                peb = self.linear_p_bias(pos).float()
+                peb = run_seq(self.linear_p_bias, pos).float()
             relation_qk = relation_qk + peb
-        weight = self.weight_encoding(relation_qk)                            # (N,k,G) logits
+        weight = run_seq(self.weight_encoding, relation_qk)                   # (N,k,G) logits
         if self.attn_drop_rate > 0.0 and self.training:
             # dropout sits between softmax and mask (:122-125): un-fused tail for this rare setting
             value_g = pointops.grouping(reference_index, value, coord, with_xyz=False)
@@ -157,10 +195,18 @@ class GroupedVectorAttention(nn.Module):
             we = lin_e.weight.float()                                         # (G, C)
             wf = we @ lin2.weight.float()                                     # (G, C) acting on h
             peb, upe = pointops.pe_bias_mlp(pos, self.linear_p_bias, pos_moments, aux_weight=wf)
-            const = lin_e.bias.float() if lin_e.bias is not None else 0.0
+            const = lin_e.bias.float() if lin_e.bias is not None else None
             if lin2.bias is not None:
-                const = const + F.linear(lin2.bias.float(), we)
-            u = pointops.gva_relation(kp, qp, reference_index) + upe + const  # (N, k, G) = weight_encoding[0](relation_qk)
+                cb = F.linear(lin2.bias.float(), we)
+                const = cb if const is None else const + cb
+            rel = pointops.gva_relation(kp, qp, reference_index)              # (N, k, G)
+            if pointops.we_tail_usable(rel, self.weight_encoding[1]):
+                # u = rel + upe + const = weight_encoding[0](relation_qk); BN(G), ReLU, Linear(G,G) in one operator
+                weight = pointops.we_tail(rel, upe, const, self.weight_encoding[1], self.weight_encoding[3])
+                return pointops.gva_aggregate(value, peb, weight, reference_index, self.groups)
+            u = rel + upe
+            if const is not None:
+                u = u + const
         weight = self.weight_encoding[1:](u)                                  # BN(G), ReLU, Linear(G,G)
         return pointops.gva_aggregate(value, peb, weight, reference_index, self.groups)   # :110,:119-128
 
@@ -184,17 +230,21 @@ class Block(nn.Module):
     def forward(self, points, reference_index, pos=None, pos_moments=None):
         coord, feat, offset = points
         identity = feat
-        feat = self.act(self.norm1(self.fc1(feat)))
+        feat = pointops.bn_act(self.fc1(feat), self.norm1.norm, relu=True)
         if self.enable_checkpoint:
             from torch.utils.checkpoint import checkpoint
 
             feat = checkpoint(self.attn, feat, coord, reference_index, pos, pos_moments, use_reentrant=False)
         else:
             feat = self.attn(feat, coord, reference_index, pos, pos_moments)
-        feat = self.act(self.norm2(feat))
-        feat = self.norm3(self.fc3(feat))
-        feat = identity + self.drop_path(feat)
-        feat = self.act(feat)
+        # norm2 + ReLU written in the dtype fc3 consumes; norm3 + DropPath + residual + ReLU in one pass (:194-197)
+        feat = pointops.bn_act(feat, self.norm2.norm, relu=True, out_dtype=_autocast_dtype())
+        feat = self.fc3(feat)
+        row_scale = None
+        if isinstance(self.drop_path, DropPath) and self.drop_path.drop_prob > 0.0 and self.training:
+            keep = 1.0 - self.drop_path.drop_prob
+            row_scale = torch.empty(feat.shape[0], dtype=torch.float32, device=feat.device).bernoulli_(keep).div_(keep)
+        feat = pointops.bn_act(feat, self.norm3.norm, relu=True, residual=identity, row_scale=row_scale)
         return [coord, feat, offset]
 
 
@@ -283,7 +333,7 @@ class GridPool(nn.Module):
 
     def forward(self, points, start=None):
         coord, feat, offset = points
-        feat = self.act(self.norm(self.fc(feat)))
+        feat = pointops.bn_act(self.fc(feat), self.norm.norm, relu=True, out_dtype=torch.float32)
         (coord, feat, offset), cluster, part = pointops.grid_pool(coord, feat.float().contiguous(), offset,
                                                                   self.grid_size, start, return_partition=True)
         cluster._aopt_c32 = part.cluster32      # lets UnpoolWithSkip("map") reuse the partition as its CSR
@@ -310,11 +360,12 @@ class UnpoolWithSkip(nn.Module):
         coord, feat, offset = points
         skip_coord, skip_feat, skip_offset = skip_points
         if self.backend == "map" and cluster is not None:
-            feat = pointops.unpool_map(self.proj(feat), cluster)
+            feat = pointops.unpool_map(run_seq(self.proj, feat), cluster)
         else:
-            feat = pointops.interpolation(coord, skip_coord, self.proj(feat).float().contiguous(), offset, skip_offset)
+            feat = pointops.interpolation(coord, skip_coord, run_seq(self.proj, feat, torch.float32).float().contiguous(),
+                                          offset, skip_offset)
         if self.skip:
-            feat = feat + self.proj_skip(skip_feat)
+            feat = feat + run_seq(self.proj_skip, skip_feat)
         return [skip_coord, feat, skip_offset]
 
 
@@ -369,7 +420,7 @@ class GVAPatchEmbed(nn.Module):
 
     def forward(self, points):
         coord, feat, offset = points
-        feat = self.proj(feat)
+        feat = run_seq(self.proj, feat)
         return self.blocks([coord, feat, offset])
 
 
@@ -457,7 +508,7 @@ class PointTransformerV2(nn.Module):
                 skip_points, cluster = skips.pop(-1)
                 points = self.dec_stages[i](points, skip_points, cluster)
             coord, feat, offset = points
-            return self.seg_head(feat)
+            return run_seq(self.seg_head, feat) if isinstance(self.seg_head, nn.Sequential) else self.seg_head(feat)
         finally:
             self._knn_cache.clear()   # the idx tensors stay alive through autograd; do not pin them here
 

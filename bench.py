@@ -709,7 +709,7 @@ def model_step(ctx, name, coord, feat, offset, bucket_cap_mb, steps=10):
     model = ptv2.PointTransformerV2(**mcfg).to(dev).train()
     n_params = sum(p.numel() for p in model.parameters())
     net = sharding.ddp_wrap(model, ctx.local, bucket_cap_mb=bucket_cap_mb) if ctx.world > 1 else model
-    opt = torch.optim.AdamW(net.parameters(), lr=1e-3)
+    opt = torch.optim.AdamW(net.parameters(), lr=1e-3, fused=True)   # one multi-tensor kernel pair instead of ~12 per step
     target = torch.randint(0, mcfg["num_classes"], (coord.shape[0],), device=dev)
 
     def step():

@@ -271,6 +271,47 @@ int aopt_pe_mlp_backward(int64_t rows, int c, const float *pos, const double *mo
                          float *grad_b2, int ga, const float *grad_aux, float *grad_aux_w, void *workspace,
                          size_t workspace_bytes, aopt_stream_t stream);
 
+/* ---- BatchNorm-shaped element-wise work around the dense layers ("next" row) ----------- */
+/* Element types of the (rows, c) activations below. */
+#define AOPT_F32 0
+#define AOPT_BF16 1
+/* Scratch for the calls below: `width` = 2*c (aopt_bn_act_*) or 3*g + g*g (aopt_we_tail_*). */
+size_t aopt_dense_workspace_bytes(int width);
+/* out = [ReLU]( [residual +] [row_scale[row] *] BatchNorm_train(x) ) over the rows of x (rows, c): PointBatchNorm on
+ * (N, C) / (N*k, C) tensors with the nn.ReLU, DropPath scale and residual add that follow it in a PTv2 block
+ * (point_transformer_v2m2_base.py:25-45,187-197; Linear -> PointBatchNorm -> ReLU triples :86-93,240-242,288-295).
+ * Batch statistics in fp32 with fp64 combination; x and out/residual are fp32 or bf16 (x_dtype / out_dtype; residual has
+ * out's type); c % 4 == 0, c <= 1024 (aopt_bn_act_supported).  stats_out (2c floats) = batch mean | rstd, kept for the
+ * backward pass; running_mean / running_var (optional) are updated like nn.BatchNorm1d does (momentum, unbiased
+ * variance).  mean_shift (optional, c floats) is added to the batch mean in the running-mean update only: a Linear bias
+ * in front of a training-mode BatchNorm cancels in the output, so the caller may leave it out of x.  residual, row_scale
+ * may be NULL; relu = 0 / 1. */
+int aopt_bn_act_supported(int c);
+int aopt_bn_act_forward(int64_t rows, int c, const void *x, int x_dtype, const float *gamma, const float *beta, float eps,
+                        const void *residual, const float *row_scale, int relu, void *out, int out_dtype,
+                        float *stats_out, float *running_mean, float *running_var, float momentum,
+                        const float *mean_shift, void *workspace, size_t workspace_bytes, aopt_stream_t stream);
+/* Backward of the above.  out = the forward result (only read when relu was 1: pass NULL otherwise).  grad_x has x's
+ * type; grad_residual (optional, out's type) = grad_out masked by the ReLU.  Deterministic (no atomics). */
+int aopt_bn_act_backward(int64_t rows, int c, const void *grad_out, const void *out, int out_dtype, const void *x,
+                         int x_dtype, const float *stats, const float *gamma, const float *row_scale, void *grad_x,
+                         void *grad_residual, float *grad_gamma, float *grad_beta, void *workspace,
+                         size_t workspace_bytes, aopt_stream_t stream);
+/* Tail of GroupedVectorAttention.weight_encoding (point_transformer_v2m2_base.py:94-99,120) on the (rows = N*nsample, g)
+ * tensors:  u = rel + upe + cst  (upe (rows, g) and cst (g) optional),  logits = W2 * ReLU(BatchNorm_train(u)) + b2.
+ * g in {6, 12} (aopt_we_tail_supported); w2 (g, g) row-major [out][in]; b2 optional; stats_out (2g) = mean | rstd. */
+int aopt_we_tail_supported(int g);
+int aopt_we_tail_forward(int64_t rows, int g, const float *rel, const float *upe, const float *cst, const float *gamma,
+                         const float *beta, float eps, const float *w2, const float *b2, float *logits, float *stats_out,
+                         float *running_mean, float *running_var, float momentum, void *workspace,
+                         size_t workspace_bytes, aopt_stream_t stream);
+/* grad_u (rows, g) is the gradient of rel and of upe alike (the gradient of cst is identically zero: it sits in
+ * front of a training-mode BatchNorm).  grad_w2 (g, g), grad_b2 / grad_gamma / grad_beta (g).  Deterministic. */
+int aopt_we_tail_backward(int64_t rows, int g, const float *rel, const float *upe, const float *cst,
+                          const float *grad_logits, const float *stats, const float *gamma, const float *beta,
+                          const float *w2, float *grad_u, float *grad_gamma, float *grad_beta, float *grad_b2,
+                          float *grad_w2, void *workspace, size_t workspace_bytes, aopt_stream_t stream);
+
 /* ---- PTv1-layout fused ops kept for API parity --------------------------------------------- */
 /* output[n,ch] = sum_s (input[idx[n,s],ch] + position[n,s,ch]) * weight[n,s,ch % w_c]. */
 int aopt_aggregation_forward(int n, int nsample, int c, int w_c, const float *input,

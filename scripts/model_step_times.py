@@ -15,7 +15,7 @@ coord_np, feat_np, off_np = scenes.s3dis_batch(4, 80000)
 coord, feat, offset = (torch.from_numpy(a).to(dev) for a in (coord_np, feat_np, off_np))
 torch.manual_seed(0)
 model = ptv2.PointTransformerV2(**ptv2.S3DIS_CFG).to(dev).train()
-opt = torch.optim.AdamW(model.parameters(), lr=1e-3)
+opt = torch.optim.AdamW(model.parameters(), lr=1e-3, fused=os.environ.get('ADAMW_FUSED', '1') == '1')
 target = torch.randint(0, 13, (coord.shape[0],), device=dev)
 
 

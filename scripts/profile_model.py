@@ -14,7 +14,7 @@ coord_np, feat_np, off_np = scenes.s3dis_batch(4, 80000)
 coord, feat, offset = (torch.from_numpy(a).to(dev) for a in (coord_np, feat_np, off_np))
 torch.manual_seed(0)
 model = ptv2.PointTransformerV2(**ptv2.S3DIS_CFG).to(dev).train()
-opt = torch.optim.AdamW(model.parameters(), lr=1e-3)
+opt = torch.optim.AdamW(model.parameters(), lr=1e-3, fused=os.environ.get('ADAMW_FUSED', '1') == '1')
 target = torch.randint(0, 13, (coord.shape[0],), device=dev)
 
 
@@ -33,4 +33,5 @@ torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
     step()
     torch.cuda.synchronize()
-print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=45, max_name_column_width=70))
+print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=int(os.environ.get("ROWS", 45)), max_name_column_width=70))
+print(prof.key_averages().table(sort_by="self_cpu_time_total", row_limit=int(os.environ.get("CPU_ROWS", 30)), max_name_column_width=70))

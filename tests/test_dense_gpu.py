@@ -1,0 +1,198 @@
+"""GPU parity of the BatchNorm-shaped operators (ao_b200/csrc/dense.cu, through the C ABI via ao_b200.pointops.bn_act /
+we_tail) against the torch modules they replace in a PTv2 block — PointBatchNorm + ReLU + DropPath + residual
+(/root/reference/pointcept/models/point_transformer_v2/point_transformer_v2m2_base.py:25-45,187-197) and
+weight_encoding[1:] (:94-99,120) — evaluated in fp32 on the same inputs.
+Tolerances: fp32 in / out: rtol 2e-5, atol 2e-5 (the sums are formed in a different order than ATen's);
+bf16 outputs: one bf16 rounding of the fp32 result (rtol 2^-7)."""
+import pytest
+import torch
+import torch.nn as nn
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def _ref_bn_act(x, bn, relu, residual, row_scale):
+    y = bn(x.float())
+    if row_scale is not None:
+        y = y * row_scale[:, None]
+    if residual is not None:
+        y = residual.float() + y
+    return torch.relu(y) if relu else y
+
+
+@pytest.mark.parametrize("c,rows", [(48, 50139), (96, 1000), (192, 12534), (384, 2868), (24, 3001), (8, 7)])
+@pytest.mark.parametrize("xdt,odt", [(torch.float32, torch.float32), (torch.bfloat16, torch.bfloat16),
+                                     (torch.float32, torch.bfloat16), (torch.bfloat16, torch.float32)])
+@pytest.mark.parametrize("relu,res,drop", [(True, False, False), (False, False, False), (True, True, True), (False, True, False)])
+def test_bn_act_matches_torch(c, rows, xdt, odt, relu, res, drop):
+    from ao_b200 import pointops
+
+    torch.manual_seed(c + rows)
+    x = (torch.randn(rows, c, device=DEV) * 1.7 + torch.linspace(-3, 5, c, device=DEV)).to(xdt).requires_grad_(True)
+    residual = torch.randn(rows, c, device=DEV).to(odt).requires_grad_(True) if res else None
+    row_scale = (torch.rand(rows, device=DEV) < 0.7).float() / 0.7 if drop else None
+    bn_a, bn_b = nn.BatchNorm1d(c).to(DEV), nn.BatchNorm1d(c).to(DEV)
+    with torch.no_grad():
+        bn_a.weight.uniform_(0.5, 1.5)
+        bn_a.bias.uniform_(-0.5, 0.5)
+    bn_b.load_state_dict(bn_a.state_dict())
+    out = pointops.bn_act(x, bn_a, relu=relu, residual=residual, row_scale=row_scale, out_dtype=odt)
+    assert out.dtype == odt and out.shape == x.shape
+    xr = x.detach().clone().requires_grad_(True)
+    rr = residual.detach().clone().requires_grad_(True) if res else None
+    ref = _ref_bn_act(xr, bn_b, relu, rr, row_scale)
+    tol = dict(rtol=2e-5, atol=2e-5) if odt == torch.float32 else dict(rtol=2 ** -7, atol=2 ** -7)
+    torch.testing.assert_close(out.float(), ref, **tol)
+    torch.testing.assert_close(bn_a.running_mean, bn_b.running_mean, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(bn_a.running_var, bn_b.running_var, rtol=1e-5, atol=1e-6)
+    assert int(bn_a.num_batches_tracked) == 1
+    # backward: the mask of the reference is taken from the fused output so that a value rounded to / away from 0 in
+    # bf16 does not count as a mismatch
+    g = torch.randn(rows, c, device=DEV).to(odt)
+    out.backward(g)
+    if relu:
+        gm = g.float() * (out.detach().float() > 0)
+        pre = _ref_bn_act(xr, bn_b, False, rr, row_scale)
+        pre.backward(gm)
+    else:
+        ref.backward(g.float())
+    gtol = dict(rtol=2e-4, atol=2e-4) if xdt == torch.float32 else dict(rtol=2 ** -6, atol=2 ** -6)
+    scale = max(1.0, float(xr.grad.abs().max()))
+    torch.testing.assert_close(x.grad.float() / scale, xr.grad.float() / scale, **gtol)
+    ptol = dict(rtol=5e-4, atol=5e-4 * max(1.0, rows ** 0.5))
+    torch.testing.assert_close(bn_a.weight.grad, bn_b.weight.grad, **ptol)
+    torch.testing.assert_close(bn_a.bias.grad, bn_b.bias.grad, **ptol)
+    if res:
+        rtol_ = dict(rtol=1e-6, atol=1e-6) if odt == torch.float32 else dict(rtol=2 ** -7, atol=2 ** -7)
+        torch.testing.assert_close(residual.grad.float(), rr.grad.float(), **rtol_)
+
+
+def test_bn_act_three_dims_eval_mode_and_repeatability():
+    from ao_b200 import pointops
+
+    torch.manual_seed(3)
+    x = torch.randn(4000, 16, 48, device=DEV)
+    bn = nn.BatchNorm1d(48).to(DEV)
+    a = pointops.bn_act(x, bn, relu=True)
+    bn2 = nn.BatchNorm1d(48).to(DEV)
+    b = pointops.bn_act(x, bn2, relu=True)
+    assert torch.equal(a, b)                                     # no atomics: bitwise repeatable
+    ref = torch.relu(nn.BatchNorm1d(48).to(DEV)(x.reshape(-1, 48))).view_as(x)
+    torch.testing.assert_close(a, ref, rtol=2e-5, atol=2e-5)
+    bn.eval()                                                    # running statistics: the torch module runs
+    e = pointops.bn_act(x, bn, relu=True)
+    torch.testing.assert_close(e, torch.relu(bn(x.reshape(-1, 48))).view_as(x))
+    with pytest.raises(ValueError):
+        pointops.we_tail(x[..., :5].contiguous(), None, None, bn, nn.Linear(5, 5).to(DEV))
+
+
+@pytest.mark.parametrize("g,n", [(6, 50139), (12, 12534), (6, 3), (12, 1000)])
+@pytest.mark.parametrize("with_upe", [True, False])
+def test_we_tail_matches_torch(g, n, with_upe):
+    from ao_b200 import pointops
+
+    torch.manual_seed(g + n)
+    k = 16
+    rel = (torch.randn(n, k, g, device=DEV) * 2.0 + 0.3).requires_grad_(True)
+    upe = torch.randn(n, k, g, device=DEV).requires_grad_(True) if with_upe else None
+    cst = torch.randn(g, device=DEV).requires_grad_(True) if with_upe else None
+    bn_a, lin_a = nn.BatchNorm1d(g).to(DEV), nn.Linear(g, g).to(DEV)
+    bn_b, lin_b = nn.BatchNorm1d(g).to(DEV), nn.Linear(g, g).to(DEV)
+    with torch.no_grad():
+        bn_a.weight.uniform_(0.5, 1.5)
+        bn_a.bias.uniform_(-0.5, 0.5)
+    bn_b.load_state_dict(bn_a.state_dict())
+    lin_b.load_state_dict(lin_a.state_dict())
+    assert pointops.we_tail_usable(rel, bn_a)
+    out = pointops.we_tail(rel, upe, cst, bn_a, lin_a)
+    rel_r = rel.detach().clone().requires_grad_(True)
+    upe_r = upe.detach().clone().requires_grad_(True) if with_upe else None
+    cst_r = cst.detach().clone().requires_grad_(True) if with_upe else None
+    u = rel_r if not with_upe else rel_r + upe_r + cst_r
+    ref = lin_b(torch.relu(bn_b(u.reshape(-1, g)))).view(n, k, g)
+    torch.testing.assert_close(out, ref, rtol=2e-5, atol=2e-5)
+    torch.testing.assert_close(bn_a.running_mean, bn_b.running_mean, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(bn_a.running_var, bn_b.running_var, rtol=1e-5, atol=1e-6)
+    gl = torch.randn(n, k, g, device=DEV)
+    out.backward(gl)
+    ref.backward(gl)
+    torch.testing.assert_close(rel.grad, rel_r.grad, rtol=2e-4, atol=2e-5)
+    rows = n * k
+    ptol = dict(rtol=5e-4, atol=5e-4 * max(1.0, rows ** 0.5))
+    for a, b in ((bn_a.weight, bn_b.weight), (bn_a.bias, bn_b.bias), (lin_a.weight, lin_b.weight), (lin_a.bias, lin_b.bias)):
+        torch.testing.assert_close(a.grad, b.grad, **ptol)
+    if with_upe:
+        torch.testing.assert_close(upe.grad, upe_r.grad, rtol=2e-4, atol=2e-5)
+        assert float(cst.grad.abs().max()) == 0.0                 # in front of a training-mode BatchNorm
+        assert float(cst_r.grad.abs().max()) < 1e-2 * max(1.0, rows ** 0.5)
+    # repeatable bit for bit
+    bn_c = nn.BatchNorm1d(g).to(DEV)
+    bn_c.load_state_dict(bn_b.state_dict())
+    bn_c.running_mean.zero_(); bn_c.running_var.fill_(1.0)
+    out2 = pointops.we_tail(rel.detach(), None if upe is None else upe.detach(), None if cst is None else cst.detach(), bn_c, lin_a)
+    assert torch.equal(out2, out.detach())
+
+
+def test_block_with_fused_dense_equals_torch_modules(monkeypatch):
+    """One PTv2 Block + GridPool stage, fp32, training mode: the bn_act / we_tail routing against the same modules
+    with AOPT_FUSED_DENSE=0 (plain torch.nn BatchNorm / ReLU)."""
+    from ao_b200 import ptv2, scenes
+
+    coord_np, feat_np, off_np = scenes.small_batch(seed=5, sizes=(3000, 2500))
+    coord, offset = torch.from_numpy(coord_np).to(DEV), torch.from_numpy(off_np).to(DEV).int()
+    torch.manual_seed(0)
+    feat = torch.randn(coord.shape[0], 48, device=DEV)
+
+    def run(flag):
+        monkeypatch.setenv("AOPT_FUSED_DENSE", flag)
+        monkeypatch.setenv("AOPT_FUSED_PE", "1")                      # the relation-free schedule (uses we_tail)
+        torch.manual_seed(1)
+        seq = ptv2.BlockSequence(depth=2, embed_channels=48, groups=6, neighbours=16, drop_path_rate=0.0).to(DEV).train()
+        pool = ptv2.GridPool(48, 96, 0.2).to(DEV).train()
+        f = feat.clone().requires_grad_(True)
+        pts = seq([coord, f, offset])
+        (c2, f2, o2), _ = pool(pts)
+        loss = (f2 * torch.linspace(-1, 1, 96, device=DEV)).sum() + pts[1].square().mean()
+        loss.backward()
+        grads = {n: p.grad.clone() for n, p in list(seq.named_parameters()) + list(pool.named_parameters())}
+        return pts[1].detach(), f2.detach(), f.grad.clone(), grads
+
+    a, b = run("1"), run("0")
+    torch.testing.assert_close(a[0], b[0], rtol=2e-3, atol=2e-3)
+    torch.testing.assert_close(a[1], b[1], rtol=2e-3, atol=2e-3)
+    torch.testing.assert_close(a[2], b[2], rtol=2e-2, atol=2e-3)
+    gmax = max(float(g.abs().max()) for g in b[3].values())
+    for n in a[3]:
+        # gradients that are zero up to rounding (a bias in front of a BatchNorm) are compared on the scale of the others
+        ga, gb = a[3][n], b[3][n]
+        scale = max(1e-2 * gmax, float(gb.abs().max()))
+        assert float((ga - gb).abs().max()) / scale < 3e-2, n
+
+
+def test_linear_bias_in_front_of_batchnorm_is_folded(monkeypatch):
+    """ptv2.run_seq leaves the bias of a Linear -> PointBatchNorm -> ReLU triple out of the GEMM (training mode): same output,
+    same running statistics (the running mean sees the bias), zero bias gradient."""
+    from ao_b200 import ptv2
+
+    torch.manual_seed(7)
+    seq = nn.Sequential(nn.Linear(48, 96), ptv2.PointBatchNorm(96), nn.ReLU(inplace=True)).to(DEV).train()
+    with torch.no_grad():
+        seq[0].bias.uniform_(-2, 2)
+    ref = nn.Sequential(nn.Linear(48, 96), ptv2.PointBatchNorm(96), nn.ReLU(inplace=True)).to(DEV).train()
+    ref.load_state_dict(seq.state_dict())
+    x = torch.randn(5000, 48, device=DEV)
+    out = ptv2.run_seq(seq, x)
+    want = ref(x)
+    torch.testing.assert_close(out, want, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(seq[1].norm.running_mean, ref[1].norm.running_mean, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(seq[1].norm.running_var, ref[1].norm.running_var, rtol=1e-4, atol=1e-5)
+    out.square().sum().backward()
+    want.square().sum().backward()
+    assert float(seq[0].bias.grad.abs().max()) == 0.0
+    assert float(ref[0].bias.grad.abs().max()) < 1e-1                 # rounding noise around the exact zero
+    torch.testing.assert_close(seq[0].weight.grad, ref[0].weight.grad, rtol=1e-3, atol=1e-2)
+    seq.eval()                                                        # evaluation: the bias is back in the GEMM
+    ref.eval()
+    torch.testing.assert_close(ptv2.run_seq(seq, x), ref(x), rtol=1e-5, atol=1e-5)

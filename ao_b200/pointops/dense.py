@@ -252,3 +252,81 @@ def we_tail(rel: torch.Tensor, upe: torch.Tensor, cst: torch.Tensor, bn: torch.n
     return _WeTailFn.apply(rel, upe, cst, f(bn.weight), f(bn.bias), f(lin.weight), None if lin.bias is None else f(lin.bias),
                            bn.running_mean if track else None, bn.running_var if track else None, float(momentum),
                            float(bn.eps))
+
+
+# ---- autocast Linear with cached low-precision weights ------------------------------------------------------------------
+# torch.autocast casts every fp32 weight to bf16 through autograd: a copy kernel, a ToCopyBackward node and a second copy
+# kernel per weight and step, plus ~40 us of dispatcher / autograd host time per nn.Linear call — on a path whose GEMMs
+# take 10-30 us (profiles/r02o_model_step_torch_profile.txt: `aten::_to_copy` 537 calls, 6.6 ms of host time).  `linear`
+# is the same computation (bf16 operands, fp32 accumulation in cuBLAS, the weight gradient returned in fp32) with the cast
+# weight cached until the optimizer changes the parameter (`_version`) and no autograd node for the casts.
+_MM_OUT_DTYPE = None
+
+
+def _shadow(p: torch.Tensor, dt: torch.dtype) -> torch.Tensor:
+    """Low-precision copy of parameter p, kept on the parameter until an in-place update changes its version."""
+    hit = getattr(p, "_aopt_lo", None)
+    if hit is not None and hit[0] == p._version and hit[1] == dt:
+        return hit[2]
+    lo = p.detach().to(dt)
+    p._aopt_lo = (p._version, dt, lo)
+    return lo
+
+
+def _mm_f32(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """a @ b with low-precision operands and an fp32 result (cuBLAS writes the fp32 accumulator; no cast kernel)."""
+    global _MM_OUT_DTYPE
+    if _MM_OUT_DTYPE is None:
+        try:
+            torch.mm(a, b, out_dtype=torch.float32)
+            _MM_OUT_DTYPE = True
+        except (TypeError, RuntimeError):
+            _MM_OUT_DTYPE = False
+    return torch.mm(a, b, out_dtype=torch.float32) if _MM_OUT_DTYPE else torch.mm(a, b).float()
+
+
+class _LinearFn(Function):
+    @staticmethod
+    def forward(ctx, x, w, b, dt, out_f32):
+        shape = x.shape
+        x2 = x.reshape(-1, shape[-1])
+        xb = x2 if x2.dtype == dt else x2.to(dt)
+        wb = _shadow(w, dt)
+        if out_f32:
+            y = _mm_f32(xb, wb.t())
+            if b is not None:
+                y.add_(b)
+        else:
+            y = torch.mm(xb, wb.t()) if b is None else torch.addmm(_shadow(b, dt), xb, wb.t())
+        ctx.save_for_backward(xb, wb)
+        ctx.x_dtype = x.dtype
+        ctx.has_bias = b is not None
+        return y.view(shape[:-1] + (w.shape[0],))
+
+    @staticmethod
+    def backward(ctx, gy):
+        xb, wb = ctx.saved_tensors
+        g2 = gy.reshape(-1, gy.shape[-1])
+        if g2.dtype != xb.dtype:
+            g2 = g2.to(xb.dtype)
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = torch.mm(g2, wb).view(gy.shape[:-1] + (wb.shape[1],))
+            if gx.dtype != ctx.x_dtype:
+                gx = gx.to(ctx.x_dtype)
+        if ctx.needs_input_grad[1]:
+            gw = _mm_f32(g2.t(), xb)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = g2.sum(0, dtype=torch.float32)
+        return gx, gw, gb, None, None
+
+
+def linear(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor = None, out_f32: bool = False) -> torch.Tensor:
+    """torch.nn.functional.linear; under CUDA autocast the low-precision copy of the fp32 parameters is cached across
+    calls (see above).  Same arithmetic as the autocast Linear it replaces.  out_f32: return fp32 (under autocast the
+    GEMM writes its fp32 accumulator instead of a rounded copy that the caller would cast back)."""
+    if (x.is_cuda and torch.is_autocast_enabled() and fused_dense_enabled() and weight.dtype == torch.float32
+            and x.dtype in (torch.float32, torch.bfloat16, torch.float16) and x.numel() > 0):
+        return _LinearFn.apply(x, weight, bias, torch.get_autocast_dtype("cuda"), bool(out_f32))
+    y = torch.nn.functional.linear(x, weight, bias)
+    return y.float() if out_f32 else y

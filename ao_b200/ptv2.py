@@ -106,8 +106,11 @@ def run_seq(seq, x, out_dtype=None):
                                       _autocast_dtype() or x.dtype)):
             # the bias of a Linear in front of a training-mode BatchNorm cancels in the output: the GEMM runs without it
             # (no bias-gradient reduction over the rows in the backward pass); bn_act adds it to the running mean
-            x = nn.functional.linear(x, m.weight)
+            x = pointops.linear(x, m.weight)
             pre_bias = m.bias
+            i += 1
+        elif isinstance(m, nn.Linear):
+            x = pointops.linear(x, m.weight, m.bias, out_f32=(out_dtype == torch.float32 and i + 1 == len(mods)))
             i += 1
         else:
             x = m(x)
@@ -143,12 +146,17 @@ class GroupedVectorAttention(nn.Module):
         self.attn_drop = nn.Dropout(attn_drop_rate)
 
     def forward(self, feat, coord, reference_index, pos=None, pos_moments=None):
-        query, key, value = run_seq(self.linear_q, feat), run_seq(self.linear_k, feat), self.linear_v(feat)
+        fused = (self.pe_bias and not self.pe_multiplier and fused_pe_enabled()
+                 and pointops.pe_mlp_supported(self.embed_channels) and self.groups <= 16
+                 and not (self.attn_drop_rate > 0.0 and self.training))
+        # the point operators compute in fp32: q / k feed a GEMM in the relation-free schedule (any dtype) and
+        # gva_relation otherwise (fp32); value always feeds gva_aggregate
+        qk_dtype = None if fused else torch.float32
+        query, key = run_seq(self.linear_q, feat, qk_dtype), run_seq(self.linear_k, feat, qk_dtype)
+        value = pointops.linear(feat, self.linear_v.weight, self.linear_v.bias, out_f32=True)
         if pos is None:                                                       # (N,k,3): depends only on (idx, coord)
             pos = pointops.group_xyz(reference_index, coord)                  # :109,:111
-        if (self.pe_bias and not self.pe_multiplier and fused_pe_enabled()
-                and pointops.pe_mlp_supported(self.embed_channels) and self.groups <= 16
-                and not (self.attn_drop_rate > 0.0 and self.training)):
+        if fused:
             return self._forward_fused(query, key, value, pos, pos_moments, reference_index)
         relation_qk = pointops.gva_relation(key, query, reference_index)      # :109,:112
         peb = None
@@ -159,9 +167,9 @@ class GroupedVectorAttention(nn.Module):
                 # bf16 tensor-core fused MLP: used where the torch path would run in bf16 anyway (autocast)
                 peb = pointops.pe_bias_mlp(pos, self.linear_p_bias, pos_moments)
             else:
-                peb = run_seq(self.linear_p_bias, pos).float()
+                peb = run_seq(self.linear_p_bias, pos, torch.float32).float()
             relation_qk = relation_qk + peb
-        weight = run_seq(self.weight_encoding, relation_qk)                   # (N,k,G) logits
+        weight = run_seq(self.weight_encoding, relation_qk, torch.float32)    # (N,k,G) logits
         if self.attn_drop_rate > 0.0 and self.training:
             # dropout sits between softmax and mask (:122-125): un-fused tail for this rare setting
             value_g = pointops.grouping(reference_index, value, coord, with_xyz=False)
@@ -189,8 +197,8 @@ class GroupedVectorAttention(nn.Module):
         # key / query projected by weight_encoding[0]: (N,C) x (C,G) in the autocast dtype, like the Linear it replaces
         # (in fp32 these two skinny GEMMs ran as SIMT sgemm kernels, 174 us each at level 0:
         # profiles/r02e_model_step_torch_profile.txt)
-        kp = F.linear(key, lin_e.weight).float()                              # (N, G)
-        qp = F.linear(query, lin_e.weight).float()
+        kp = pointops.linear(key, lin_e.weight, out_f32=True)                 # (N, G)
+        qp = pointops.linear(query, lin_e.weight, out_f32=True)
         with torch.autocast("cuda", enabled=False):
             we = lin_e.weight.float()                                         # (G, C)
             wf = we @ lin2.weight.float()                                     # (G, C) acting on h
@@ -230,7 +238,7 @@ class Block(nn.Module):
     def forward(self, points, reference_index, pos=None, pos_moments=None):
         coord, feat, offset = points
         identity = feat
-        feat = pointops.bn_act(self.fc1(feat), self.norm1.norm, relu=True)
+        feat = pointops.bn_act(pointops.linear(feat, self.fc1.weight, self.fc1.bias), self.norm1.norm, relu=True)
         if self.enable_checkpoint:
             from torch.utils.checkpoint import checkpoint
 
@@ -239,7 +247,7 @@ class Block(nn.Module):
             feat = self.attn(feat, coord, reference_index, pos, pos_moments)
         # norm2 + ReLU written in the dtype fc3 consumes; norm3 + DropPath + residual + ReLU in one pass (:194-197)
         feat = pointops.bn_act(feat, self.norm2.norm, relu=True, out_dtype=_autocast_dtype())
-        feat = self.fc3(feat)
+        feat = pointops.linear(feat, self.fc3.weight, self.fc3.bias)
         row_scale = None
         if isinstance(self.drop_path, DropPath) and self.drop_path.drop_prob > 0.0 and self.training:
             keep = 1.0 - self.drop_path.drop_prob
@@ -333,7 +341,7 @@ class GridPool(nn.Module):
 
     def forward(self, points, start=None):
         coord, feat, offset = points
-        feat = pointops.bn_act(self.fc(feat), self.norm.norm, relu=True, out_dtype=torch.float32)
+        feat = pointops.bn_act(pointops.linear(feat, self.fc.weight, self.fc.bias), self.norm.norm, relu=True, out_dtype=torch.float32)
         (coord, feat, offset), cluster, part = pointops.grid_pool(coord, feat.float().contiguous(), offset,
                                                                   self.grid_size, start, return_partition=True)
         cluster._aopt_c32 = part.cluster32      # lets UnpoolWithSkip("map") reuse the partition as its CSR

@@ -196,3 +196,38 @@ def test_linear_bias_in_front_of_batchnorm_is_folded(monkeypatch):
     seq.eval()                                                        # evaluation: the bias is back in the GEMM
     ref.eval()
     torch.testing.assert_close(ptv2.run_seq(seq, x), ref(x), rtol=1e-5, atol=1e-5)
+
+
+def test_cached_weight_linear_equals_autocast_linear():
+    """pointops.linear under bf16 autocast = nn.Linear under bf16 autocast (same operand rounding, fp32 accumulation);
+    the cached low-precision weight follows in-place parameter updates."""
+    from ao_b200 import pointops
+
+    torch.manual_seed(11)
+    lin = nn.Linear(96, 48).to(DEV)
+    ref = nn.Linear(96, 48).to(DEV)
+    ref.load_state_dict(lin.state_dict())
+    for shape, f32 in (((7000, 96), False), ((500, 16, 96), True)):
+        x = torch.randn(*shape, device=DEV, requires_grad=True)
+        xr = x.detach().clone().requires_grad_(True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            y = pointops.linear(x, lin.weight, lin.bias, out_f32=f32)
+            yr = ref(xr)
+        assert y.dtype == (torch.float32 if f32 else torch.bfloat16) and y.shape == yr.shape
+        torch.testing.assert_close(y.float(), yr.float(), rtol=2 ** -7, atol=2 ** -7)
+        g = torch.randn_like(yr)
+        y.backward(g.to(y.dtype))
+        yr.backward(g)
+        torch.testing.assert_close(x.grad, xr.grad, rtol=2 ** -6, atol=2 ** -6)
+        torch.testing.assert_close(lin.weight.grad, ref.weight.grad, rtol=2e-2, atol=2e-2 * float(ref.weight.grad.abs().max()))
+        torch.testing.assert_close(lin.bias.grad, ref.bias.grad, rtol=2e-2, atol=2e-2 * float(ref.bias.grad.abs().max()))
+        assert lin.weight.grad.dtype == torch.float32
+        lin.zero_grad(); ref.zero_grad()
+    with torch.no_grad():                                        # an optimizer step: in-place update bumps the version
+        lin.weight.mul_(2.0)
+        ref.weight.mul_(2.0)
+    x = torch.randn(100, 96, device=DEV)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        torch.testing.assert_close(pointops.linear(x, lin.weight, lin.bias).float(), ref(x).float(), rtol=2 ** -7, atol=2 ** -7)
+    # no autocast: plain fp32 F.linear
+    torch.testing.assert_close(pointops.linear(x, lin.weight, lin.bias), ref(x))

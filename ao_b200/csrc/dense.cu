@@ -99,23 +99,37 @@ __device__ __forceinline__ void block_reduce_store(float (&v)[NV], float *__rest
     }
 }
 
-// out[v] = Σ_p partials[p][v] in fp64, fixed order.  CTA = 32 values x 8 slices of the partial rows.
-__global__ void __launch_bounds__(256)
+// out[v] = Σ_p partials[p][v] in fp64, fixed order.  CTA = 32 values x 32 slices of the partial rows: a thread issues
+// its <= 19 loads (592 partial rows) back to back — with 8 slices the 74 dependent-latency loads per thread made this
+// 3-CTA kernel the longest of the chain (15 us per call, 220 calls per training step: profiles/r02p).
+constexpr int kReduceSlices = 32;
+__global__ void __launch_bounds__(32 * kReduceSlices)
 partials_reduce_kernel(int parts, int width, const float *__restrict__ partials, double *__restrict__ out) {
-    __shared__ double sh[8][32];
+    __shared__ double sh[kReduceSlices][33];
     pdl_wait();
     pdl_trigger();
     const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
     const int v = blockIdx.x * 32 + lane;
     double s = 0.0;
-    if (v < width)
-        for (int p = slice; p < parts; p += 8) s += (double)partials[(size_t)p * width + v];
+    if (v < width) {
+        int p = slice;
+        for (; p + 3 * kReduceSlices < parts; p += 4 * kReduceSlices) {
+            const float a = partials[(size_t)p * width + v], b = partials[(size_t)(p + kReduceSlices) * width + v];
+            const float c = partials[(size_t)(p + 2 * kReduceSlices) * width + v];
+            const float d = partials[(size_t)(p + 3 * kReduceSlices) * width + v];
+            s += (double)a;
+            s += (double)b;
+            s += (double)c;
+            s += (double)d;
+        }
+        for (; p < parts; p += kReduceSlices) s += (double)partials[(size_t)p * width + v];
+    }
     sh[slice][lane] = s;
     __syncthreads();
     if (slice == 0 && v < width) {
         double t = sh[0][lane];
 #pragma unroll
-        for (int u = 1; u < 8; ++u) t += sh[u][lane];
+        for (int u = 1; u < kReduceSlices; ++u) t += sh[u][lane];
         out[v] = t;
     }
 }
@@ -174,12 +188,13 @@ bn_apply_kernel(long long rows, int c, const XT *__restrict__ x, const double *_
                 float eps, const float *__restrict__ gamma, const float *__restrict__ beta,
                 const OT *__restrict__ residual, const float *__restrict__ row_scale, int relu, OT *__restrict__ out,
                 float *__restrict__ stats_out, float *__restrict__ running_mean, float *__restrict__ running_var,
-                float momentum, float unbias, const float *__restrict__ mean_shift) {
+                float momentum, float unbias, const float *__restrict__ mean_shift, long long *__restrict__ batches_tracked) {
     const int cols = c >> 2;
     const ColWalk w = col_walk(cols, kDenseBlock);
     pdl_wait();
     float mean[4], sc[4], sh[4];
     const bool writer = (long long)blockIdx.x * kDenseBlock + threadIdx.x < cols;   // one thread per column chunk
+    if (batches_tracked && blockIdx.x == 0 && threadIdx.x == 0) *batches_tracked += 1;   // nn.BatchNorm1d.num_batches_tracked
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const int ch = 4 * w.col + j;
@@ -375,10 +390,12 @@ we_apply_kernel(long long rows, const float *__restrict__ rel, const float *__re
                 const float *__restrict__ cst, const double *__restrict__ sums, double inv_rows, float eps,
                 const float *__restrict__ gamma, const float *__restrict__ beta, const float *__restrict__ w2,
                 const float *__restrict__ b2, float *__restrict__ logits, float *__restrict__ stats_out,
-                float *__restrict__ running_mean, float *__restrict__ running_var, float momentum, float unbias) {
+                float *__restrict__ running_mean, float *__restrict__ running_var, float momentum, float unbias,
+                long long *__restrict__ batches_tracked) {
     __shared__ TailParams<G> P;
     pdl_wait();
     const int t = threadIdx.x;
+    if (batches_tracked && blockIdx.x == 0 && t == 0) *batches_tracked += 1;
     if (t < G) {
         float var;
         const ChanStat st = stat_from_sums(sums[t], sums[G + t], inv_rows, eps, &var);
@@ -554,16 +571,16 @@ static bool bn_width_ok(int c) { return c >= 4 && (c & 3) == 0 && c <= 4 * kDens
 template <typename XT, typename OT>
 static int bn_forward_t(long long rows, int c, const void *x, const float *gamma, const float *beta, float eps,
                         const void *residual, const float *row_scale, int relu, void *out, float *stats_out,
-                        float *running_mean, float *running_var, float momentum, const float *mean_shift, float *partials,
-                        double *sums, cudaStream_t st) {
+                        float *running_mean, float *running_var, float momentum, const float *mean_shift,
+                        long long *batches_tracked, float *partials, double *sums, cudaStream_t st) {
     const int grid = bn_grid(rows, c);
     const bool pdl = tuning(kTunePdl) != 2;
     bn_partial_kernel<XT><<<grid, kDenseBlock, 0, st>>>(rows, c, static_cast<const XT *>(x), partials);
-    launch_chain(pdl, partials_reduce_kernel, div_up(2 * c, 32), 256, 0, st, grid, 2 * c, (const float *)partials, sums);
+    launch_chain(pdl, partials_reduce_kernel, div_up(2 * c, 32), 32 * kReduceSlices, 0, st, grid, 2 * c, (const float *)partials, sums);
     const float unbias = rows > 1 ? (float)((double)rows / (double)(rows - 1)) : 1.f;
     launch_chain(pdl, bn_apply_kernel<XT, OT>, grid, kDenseBlock, 0, st, rows, c, static_cast<const XT *>(x),
                  (const double *)sums, 1.0 / (double)rows, eps, gamma, beta, static_cast<const OT *>(residual), row_scale,
-                 relu, static_cast<OT *>(out), stats_out, running_mean, running_var, momentum, unbias, mean_shift);
+                 relu, static_cast<OT *>(out), stats_out, running_mean, running_var, momentum, unbias, mean_shift, batches_tracked);
     return check_launch(3);
 }
 
@@ -576,7 +593,7 @@ static int bn_backward_t(long long rows, int c, const void *grad_out, const void
     bn_bwd_partial_kernel<XT, OT><<<grid, kDenseBlock, 0, st>>>(rows, c, static_cast<const OT *>(grad_out),
                                                                 static_cast<const OT *>(out), static_cast<const XT *>(x),
                                                                 stats, row_scale, partials);
-    launch_chain(pdl, partials_reduce_kernel, div_up(2 * c, 32), 256, 0, st, grid, 2 * c, (const float *)partials, sums);
+    launch_chain(pdl, partials_reduce_kernel, div_up(2 * c, 32), 32 * kReduceSlices, 0, st, grid, 2 * c, (const float *)partials, sums);
     launch_chain(pdl, bn_bwd_apply_kernel<XT, OT>, grid, kDenseBlock, 0, st, rows, c, static_cast<const OT *>(grad_out),
                  static_cast<const OT *>(out), static_cast<const XT *>(x), stats, gamma, row_scale, (const double *)sums,
                  1.0 / (double)rows, static_cast<XT *>(grad_x), static_cast<OT *>(grad_residual), grad_gamma, grad_beta);
@@ -586,15 +603,16 @@ static int bn_backward_t(long long rows, int c, const void *grad_out, const void
 template <int G, int IB>
 static int we_forward_t(long long rows, const float *rel, const float *upe, const float *cst, const float *gamma,
                         const float *beta, float eps, const float *w2, const float *b2, float *logits, float *stats_out,
-                        float *running_mean, float *running_var, float momentum, float *partials, double *sums,
-                        cudaStream_t st) {
+                        float *running_mean, float *running_var, float momentum, long long *batches_tracked, float *partials,
+                        double *sums, cudaStream_t st) {
     const int grid = row_grid(rows);
     const bool pdl = tuning(kTunePdl) != 2;
     we_partial_kernel<G><<<grid, kDenseBlock, 0, st>>>(rows, rel, upe, cst, partials);
-    launch_chain(pdl, partials_reduce_kernel, div_up(2 * G, 32), 256, 0, st, grid, 2 * G, (const float *)partials, sums);
+    launch_chain(pdl, partials_reduce_kernel, div_up(2 * G, 32), 32 * kReduceSlices, 0, st, grid, 2 * G, (const float *)partials, sums);
     const float unbias = rows > 1 ? (float)((double)rows / (double)(rows - 1)) : 1.f;
     launch_chain(pdl, we_apply_kernel<G>, grid, kDenseBlock, 0, st, rows, rel, upe, cst, (const double *)sums,
-                 1.0 / (double)rows, eps, gamma, beta, w2, b2, logits, stats_out, running_mean, running_var, momentum, unbias);
+                 1.0 / (double)rows, eps, gamma, beta, w2, b2, logits, stats_out, running_mean, running_var, momentum, unbias,
+                 batches_tracked);
     return check_launch(3);
 }
 
@@ -608,7 +626,7 @@ static int we_backward_t(long long rows, const float *rel, const float *upe, con
     const int width = 3 * G + G * G;
     we_bwd_partial_kernel<G, IB><<<dim3(grid, G / IB), kDenseBlock, 0, st>>>(rows, rel, upe, cst, grad_logits, stats, gamma,
                                                                              beta, w2, partials);
-    launch_chain(pdl, partials_reduce_kernel, div_up(width, 32), 256, 0, st, grid, width, (const float *)partials, sums);
+    launch_chain(pdl, partials_reduce_kernel, div_up(width, 32), 32 * kReduceSlices, 0, st, grid, width, (const float *)partials, sums);
     launch_chain(pdl, we_bwd_apply_kernel<G>, grid, kDenseBlock, 0, st, rows, rel, upe, cst, grad_logits, stats, gamma, beta,
                  w2, (const double *)sums, 1.0 / (double)rows, grad_u, grad_gamma, grad_beta, grad_b2, grad_w2);
     return check_launch(3);
@@ -637,8 +655,8 @@ static bool carve_dense(void *ws, size_t ws_bytes, int width, float **partials, 
 extern "C" int aopt_bn_act_forward(int64_t rows, int c, const void *x, int x_dtype, const float *gamma, const float *beta,
                                    float eps, const void *residual, const float *row_scale, int relu, void *out,
                                    int out_dtype, float *stats_out, float *running_mean, float *running_var,
-                                   float momentum, const float *mean_shift, void *workspace, size_t workspace_bytes,
-                                   aopt_stream_t stream) {
+                                   float momentum, const float *mean_shift, long long *batches_tracked, void *workspace,
+                                   size_t workspace_bytes, aopt_stream_t stream) {
     if (rows <= 0 || !bn_width_ok(c) || !x || !gamma || !beta || !out || !stats_out) return AOPT_ERR_INVALID_ARGUMENT;
     if ((x_dtype | out_dtype) & ~1) return AOPT_ERR_INVALID_ARGUMENT;
     float *partials;
@@ -647,7 +665,7 @@ extern "C" int aopt_bn_act_forward(int64_t rows, int c, const void *x, int x_dty
     cudaStream_t st = as_stream(stream);
 #define AOPT_BN_FWD(XT, OT)                                                                                               \
     return bn_forward_t<XT, OT>(rows, c, x, gamma, beta, eps, residual, row_scale, relu, out, stats_out, running_mean,   \
-                                running_var, momentum, mean_shift, partials, sums, st)
+                                running_var, momentum, mean_shift, batches_tracked, partials, sums, st)
     if (x_dtype == AOPT_F32 && out_dtype == AOPT_F32) AOPT_BN_FWD(float, float);
     if (x_dtype == AOPT_F32 && out_dtype == AOPT_BF16) AOPT_BN_FWD(float, __nv_bfloat16);
     if (x_dtype == AOPT_BF16 && out_dtype == AOPT_F32) AOPT_BN_FWD(__nv_bfloat16, float);
@@ -679,7 +697,8 @@ extern "C" int aopt_bn_act_backward(int64_t rows, int c, const void *grad_out, c
 extern "C" int aopt_we_tail_forward(int64_t rows, int g, const float *rel, const float *upe, const float *cst,
                                     const float *gamma, const float *beta, float eps, const float *w2, const float *b2,
                                     float *logits, float *stats_out, float *running_mean, float *running_var,
-                                    float momentum, void *workspace, size_t workspace_bytes, aopt_stream_t stream) {
+                                    float momentum, long long *batches_tracked, void *workspace, size_t workspace_bytes,
+                                    aopt_stream_t stream) {
     if (rows <= 0 || !rel || !gamma || !beta || !w2 || !logits || !stats_out) return AOPT_ERR_INVALID_ARGUMENT;
     if (!aopt_we_tail_supported(g)) return AOPT_ERR_UNSUPPORTED;
     float *partials;
@@ -688,9 +707,9 @@ extern "C" int aopt_we_tail_forward(int64_t rows, int g, const float *rel, const
     cudaStream_t st = as_stream(stream);
     if (g == 6)
         return we_forward_t<6, 6>(rows, rel, upe, cst, gamma, beta, eps, w2, b2, logits, stats_out, running_mean, running_var,
-                                  momentum, partials, sums, st);
+                                  momentum, batches_tracked, partials, sums, st);
     return we_forward_t<12, 4>(rows, rel, upe, cst, gamma, beta, eps, w2, b2, logits, stats_out, running_mean, running_var,
-                               momentum, partials, sums, st);
+                               momentum, batches_tracked, partials, sums, st);
 }
 
 extern "C" int aopt_we_tail_backward(int64_t rows, int g, const float *rel, const float *upe, const float *cst,

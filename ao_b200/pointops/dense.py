@@ -51,7 +51,7 @@ def _dense_ws(width: int, dev: torch.device):
 class _BnActFn(Function):
     @staticmethod
     def forward(ctx, x, gamma, beta, residual, row_scale, running_mean, running_var, momentum, eps, relu, out_dtype,
-                pre_bias):
+                pre_bias, tracked):
         lib = _lib.load()
         dev = x.device
         rows, c = x.shape
@@ -63,7 +63,7 @@ class _BnActFn(Function):
                 lib.aopt_bn_act_forward(rows, c, x.data_ptr(), _DT[x.dtype], gamma.data_ptr(), beta.data_ptr(), eps,
                                         _lib.ptr(residual), _lib.ptr(row_scale), int(relu), out.data_ptr(), _DT[out_dtype],
                                         stats.data_ptr(), _lib.ptr(running_mean), _lib.ptr(running_var), momentum,
-                                        _lib.ptr(pre_bias), ws.data_ptr(), ws.numel(), _lib.stream()),
+                                        _lib.ptr(pre_bias), _lib.ptr(tracked), ws.data_ptr(), ws.numel(), _lib.stream()),
                 "bn_act_forward")
         ctx.save_for_backward(x, out if relu else None, gamma, stats, row_scale)
         ctx.relu = bool(relu)
@@ -98,7 +98,7 @@ class _BnActFn(Function):
             gres = grad_out
         # a bias in front of a training-mode BatchNorm has an identically zero gradient
         gpb = torch.zeros_like(ctx.bias_like) if (ctx.bias_like is not None and ctx.needs_input_grad[11]) else None
-        return gx, gg, gb, gres, None, None, None, None, None, None, None, gpb
+        return gx, gg, gb, gres, None, None, None, None, None, None, None, gpb, None
 
 
 def _torch_bn_act(x, bn, relu, residual, row_scale, out_dtype):
@@ -132,6 +132,20 @@ def bn_act_usable(x: torch.Tensor, bn: torch.nn.Module, out_dtype: torch.dtype =
     return bn_fusable(bn, c, x.numel() // max(c, 1), x.is_cuda, x.dtype, out_dtype)
 
 
+def _momentum(bn, track):
+    """(momentum, counter the kernel increments).  With a fixed momentum the num_batches_tracked increment rides in the
+    apply kernel (one launch and ~8 us of host time less per BatchNorm site); the cumulative average (momentum=None)
+    needs the count on the host, as in nn.BatchNorm1d."""
+    if not track:
+        return 0.0, None
+    nbt = bn.num_batches_tracked
+    if bn.momentum is not None and nbt is not None and nbt.is_cuda and nbt.dtype == torch.int64:
+        return float(bn.momentum), nbt
+    if nbt is not None:
+        nbt.add_(1)
+    return (float(bn.momentum) if bn.momentum is not None else 1.0 / float(nbt)), None
+
+
 def bn_act(x: torch.Tensor, bn: torch.nn.Module, relu: bool = False, residual: torch.Tensor = None,
            row_scale: torch.Tensor = None, out_dtype: torch.dtype = None, pre_bias: torch.Tensor = None) -> torch.Tensor:
     """`bn` is a BatchNorm1d (or a module with a `.norm` BatchNorm1d: the reference's PointBatchNorm).  x is (N, C) or
@@ -163,20 +177,17 @@ def bn_act(x: torch.Tensor, bn: torch.nn.Module, relu: bool = False, residual: t
     if row_scale is not None:
         row_scale = row_scale.reshape(rows).float().contiguous()
     track = bn.training and bn.track_running_stats
-    momentum = 0.0
-    if track:
-        bn.num_batches_tracked.add_(1)
-        momentum = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
+    momentum, tracked = _momentum(bn, track)
     if pre_bias is not None and (pre_bias.dtype != torch.float32 or not pre_bias.is_contiguous()):
         pre_bias = pre_bias.float().contiguous()
     out = _BnActFn.apply(x2, bn.weight, bn.bias, residual, row_scale, bn.running_mean if track else None,
-                         bn.running_var if track else None, float(momentum), float(bn.eps), bool(relu), out_dtype, pre_bias)
+                         bn.running_var if track else None, momentum, float(bn.eps), bool(relu), out_dtype, pre_bias, tracked)
     return out.view(shape)
 
 
 class _WeTailFn(Function):
     @staticmethod
-    def forward(ctx, rel, upe, cst, gamma, beta, w2, b2, running_mean, running_var, momentum, eps):
+    def forward(ctx, rel, upe, cst, gamma, beta, w2, b2, running_mean, running_var, momentum, eps, tracked):
         lib = _lib.load()
         dev = rel.device
         g = rel.shape[-1]
@@ -189,7 +200,7 @@ class _WeTailFn(Function):
                 lib.aopt_we_tail_forward(rows, g, rel.data_ptr(), _lib.ptr(upe), _lib.ptr(cst), gamma.data_ptr(),
                                          beta.data_ptr(), eps, w2.data_ptr(), _lib.ptr(b2), logits.data_ptr(),
                                          stats.data_ptr(), _lib.ptr(running_mean), _lib.ptr(running_var), momentum,
-                                         ws.data_ptr(), ws.numel(), _lib.stream()),
+                                         _lib.ptr(tracked), ws.data_ptr(), ws.numel(), _lib.stream()),
                 "we_tail_forward")
         ctx.save_for_backward(rel, upe, cst, gamma, beta, w2, stats)
         ctx.has_b2 = b2 is not None
@@ -217,7 +228,7 @@ class _WeTailFn(Function):
         # cst sits in front of a training-mode BatchNorm: its gradient (the column sums of grad_u) is identically zero
         gcst = torch.zeros_like(cst) if (cst is not None and ctx.needs_input_grad[2]) else None
         return (gu, gu if upe is not None else None, gcst, gg, gb, gw2, gb2 if ctx.has_b2 else None,
-                None, None, None, None)
+                None, None, None, None, None)
 
 
 def we_tail_usable(rel: torch.Tensor, bn: torch.nn.Module) -> bool:
@@ -244,14 +255,11 @@ def we_tail(rel: torch.Tensor, upe: torch.Tensor, cst: torch.Tensor, bn: torch.n
         if cst.numel() != g:
             raise ValueError("we_tail: cst must have G entries")
     track = bn.training and bn.track_running_stats
-    momentum = 0.0
-    if track:
-        bn.num_batches_tracked.add_(1)
-        momentum = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
+    momentum, tracked = _momentum(bn, track)
     f = lambda t: t if t.dtype == torch.float32 and t.is_contiguous() else t.float().contiguous()
     return _WeTailFn.apply(rel, upe, cst, f(bn.weight), f(bn.bias), f(lin.weight), None if lin.bias is None else f(lin.bias),
-                           bn.running_mean if track else None, bn.running_var if track else None, float(momentum),
-                           float(bn.eps))
+                           bn.running_mean if track else None, bn.running_var if track else None, momentum,
+                           float(bn.eps), tracked)
 
 
 # ---- autocast Linear with cached low-precision weights ------------------------------------------------------------------

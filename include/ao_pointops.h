@@ -285,12 +285,14 @@ size_t aopt_dense_workspace_bytes(int width);
  * backward pass; running_mean / running_var (optional) are updated like nn.BatchNorm1d does (momentum, unbiased
  * variance).  mean_shift (optional, c floats) is added to the batch mean in the running-mean update only: a Linear bias
  * in front of a training-mode BatchNorm cancels in the output, so the caller may leave it out of x.  residual, row_scale
- * may be NULL; relu = 0 / 1. */
+ * may be NULL; relu = 0 / 1.  batches_tracked (optional): device int64 counter incremented by one
+ * (nn.BatchNorm1d.num_batches_tracked). */
 int aopt_bn_act_supported(int c);
 int aopt_bn_act_forward(int64_t rows, int c, const void *x, int x_dtype, const float *gamma, const float *beta, float eps,
                         const void *residual, const float *row_scale, int relu, void *out, int out_dtype,
                         float *stats_out, float *running_mean, float *running_var, float momentum,
-                        const float *mean_shift, void *workspace, size_t workspace_bytes, aopt_stream_t stream);
+                        const float *mean_shift, long long *batches_tracked, void *workspace, size_t workspace_bytes,
+                        aopt_stream_t stream);
 /* Backward of the above.  out = the forward result (only read when relu was 1: pass NULL otherwise).  grad_x has x's
  * type; grad_residual (optional, out's type) = grad_out masked by the ReLU.  Deterministic (no atomics). */
 int aopt_bn_act_backward(int64_t rows, int c, const void *grad_out, const void *out, int out_dtype, const void *x,
@@ -303,8 +305,8 @@ int aopt_bn_act_backward(int64_t rows, int c, const void *grad_out, const void *
 int aopt_we_tail_supported(int g);
 int aopt_we_tail_forward(int64_t rows, int g, const float *rel, const float *upe, const float *cst, const float *gamma,
                          const float *beta, float eps, const float *w2, const float *b2, float *logits, float *stats_out,
-                         float *running_mean, float *running_var, float momentum, void *workspace,
-                         size_t workspace_bytes, aopt_stream_t stream);
+                         float *running_mean, float *running_var, float momentum, long long *batches_tracked,
+                         void *workspace, size_t workspace_bytes, aopt_stream_t stream);
 /* grad_u (rows, g) is the gradient of rel and of upe alike (the gradient of cst is identically zero: it sits in
  * front of a training-mode BatchNorm).  grad_w2 (g, g), grad_b2 / grad_gamma / grad_beta (g).  Deterministic. */
 int aopt_we_tail_backward(int64_t rows, int g, const float *rel, const float *upe, const float *cst,

@@ -151,7 +151,7 @@ __device__ __forceinline__ ChanStat stat_from_sums(double s, double q, double in
 // ---- BatchNorm (+ ReLU, + residual, + per-row scale) on (rows, C), C % 4 == 0 ----------------------------------
 template <typename XT>
 __global__ void __launch_bounds__(kDenseBlock)
-bn_partial_kernel(long long rows, int c, const XT *__restrict__ x, float *__restrict__ partials) {
+bn_partial_kernel(long long rows, int c, const XT *__restrict__ x, long long ldx, float *__restrict__ partials) {
     const int cols = c >> 2;
     const ColWalk w = col_walk(cols, kDenseBlock);
     pdl_trigger();
@@ -162,7 +162,7 @@ bn_partial_kernel(long long rows, int c, const XT *__restrict__ x, float *__rest
     for (; row + 3 * w.row_step < rows; row += 4 * w.row_step) {
         float4 v[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) v[u] = ld4(p + (row + u * w.row_step) * c);
+        for (int u = 0; u < 4; ++u) v[u] = ld4(p + (row + u * w.row_step) * ldx);
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             float4 &S = s[u & 1], &Q = q[u & 1];
@@ -172,7 +172,7 @@ bn_partial_kernel(long long rows, int c, const XT *__restrict__ x, float *__rest
         }
     }
     for (; row < rows; row += w.row_step) {
-        const float4 v = ld4(p + row * c);
+        const float4 v = ld4(p + row * ldx);
         s[0].x += v.x; s[0].y += v.y; s[0].z += v.z; s[0].w += v.w;
         q[0].x = fmaf(v.x, v.x, q[0].x); q[0].y = fmaf(v.y, v.y, q[0].y);
         q[0].z = fmaf(v.z, v.z, q[0].z); q[0].w = fmaf(v.w, v.w, q[0].w);
@@ -184,7 +184,7 @@ bn_partial_kernel(long long rows, int c, const XT *__restrict__ x, float *__rest
 
 template <typename XT, typename OT>
 __global__ void __launch_bounds__(kDenseBlock)
-bn_apply_kernel(long long rows, int c, const XT *__restrict__ x, const double *__restrict__ sums, double inv_rows,
+bn_apply_kernel(long long rows, int c, const XT *__restrict__ x, long long ldx, const double *__restrict__ sums, double inv_rows,
                 float eps, const float *__restrict__ gamma, const float *__restrict__ beta,
                 const OT *__restrict__ residual, const float *__restrict__ row_scale, int relu, OT *__restrict__ out,
                 float *__restrict__ stats_out, float *__restrict__ running_mean, float *__restrict__ running_var,
@@ -217,7 +217,7 @@ bn_apply_kernel(long long rows, int c, const XT *__restrict__ x, const double *_
     const OT *pr = residual ? residual + 4 * w.col : nullptr;
     OT *po = out + 4 * w.col;
     for (long long row = w.row; row < rows; row += w.row_step) {
-        const float4 v = ld4(px + row * c);
+        const float4 v = ld4(px + row * ldx);
         float4 y;
         y.x = fmaf(v.x - mean[0], sc[0], sh[0]);
         y.y = fmaf(v.y - mean[1], sc[1], sh[1]);
@@ -240,8 +240,8 @@ bn_apply_kernel(long long rows, int c, const XT *__restrict__ x, const double *_
 template <typename XT, typename OT>
 __global__ void __launch_bounds__(kDenseBlock)
 bn_bwd_partial_kernel(long long rows, int c, const OT *__restrict__ grad_out, const OT *__restrict__ out,
-                      const XT *__restrict__ x, const float *__restrict__ stats, const float *__restrict__ row_scale,
-                      float *__restrict__ partials) {
+                      const XT *__restrict__ x, long long ldx, const float *__restrict__ stats,
+                      const float *__restrict__ row_scale, float *__restrict__ partials) {
     const int cols = c >> 2;
     const ColWalk w = col_walk(cols, kDenseBlock);
     pdl_trigger();
@@ -253,7 +253,7 @@ bn_bwd_partial_kernel(long long rows, int c, const OT *__restrict__ grad_out, co
     const OT *po = out ? out + 4 * w.col : nullptr;
     for (long long row = w.row; row < rows; row += w.row_step) {
         float4 g = ld4(pg + row * c);
-        const float4 v = ld4(px + row * c);
+        const float4 v = ld4(px + row * ldx);
         if (po) {
             const float4 o = ld4(po + row * c);
             g.x = o.x > 0.f ? g.x : 0.f; g.y = o.y > 0.f ? g.y : 0.f;
@@ -276,9 +276,9 @@ bn_bwd_partial_kernel(long long rows, int c, const OT *__restrict__ grad_out, co
 template <typename XT, typename OT>
 __global__ void __launch_bounds__(kDenseBlock)
 bn_bwd_apply_kernel(long long rows, int c, const OT *__restrict__ grad_out, const OT *__restrict__ out,
-                    const XT *__restrict__ x, const float *__restrict__ stats, const float *__restrict__ gamma,
+                    const XT *__restrict__ x, long long ldx, const float *__restrict__ stats, const float *__restrict__ gamma,
                     const float *__restrict__ row_scale, const double *__restrict__ sums, double inv_rows,
-                    XT *__restrict__ grad_x, OT *__restrict__ grad_residual, float *__restrict__ grad_gamma,
+                    XT *__restrict__ grad_x, long long ldgx, OT *__restrict__ grad_residual, float *__restrict__ grad_gamma,
                     float *__restrict__ grad_beta) {
     const int cols = c >> 2;
     const ColWalk w = col_walk(cols, kDenseBlock);
@@ -306,7 +306,7 @@ bn_bwd_apply_kernel(long long rows, int c, const OT *__restrict__ grad_out, cons
     OT *pdr = grad_residual ? grad_residual + 4 * w.col : nullptr;
     for (long long row = w.row; row < rows; row += w.row_step) {
         float4 g = ld4(pg + row * c);
-        const float4 v = ld4(px + row * c);
+        const float4 v = ld4(px + row * ldx);
         if (po) {
             const float4 o = ld4(po + row * c);
             g.x = o.x > 0.f ? g.x : 0.f; g.y = o.y > 0.f ? g.y : 0.f;
@@ -322,7 +322,7 @@ bn_bwd_apply_kernel(long long rows, int c, const OT *__restrict__ grad_out, cons
         d.y = a[1] * (g.y - m1[1] - (v.y - mean[1]) * rstd[1] * m2[1]);
         d.z = a[2] * (g.z - m1[2] - (v.z - mean[2]) * rstd[2] * m2[2]);
         d.w = a[3] * (g.w - m1[3] - (v.w - mean[3]) * rstd[3] * m2[3]);
-        st4(pdx + row * c, d);
+        st4(pdx + row * ldgx, d);
     }
 }
 
@@ -569,34 +569,35 @@ static int row_grid(long long rows) { return stride_grid(rows, kDenseBlock, kDen
 static bool bn_width_ok(int c) { return c >= 4 && (c & 3) == 0 && c <= 4 * kDenseBlock; }
 
 template <typename XT, typename OT>
-static int bn_forward_t(long long rows, int c, const void *x, const float *gamma, const float *beta, float eps,
+static int bn_forward_t(long long rows, int c, const void *x, long long ldx, const float *gamma, const float *beta, float eps,
                         const void *residual, const float *row_scale, int relu, void *out, float *stats_out,
                         float *running_mean, float *running_var, float momentum, const float *mean_shift,
                         long long *batches_tracked, float *partials, double *sums, cudaStream_t st) {
     const int grid = bn_grid(rows, c);
     const bool pdl = tuning(kTunePdl) != 2;
-    bn_partial_kernel<XT><<<grid, kDenseBlock, 0, st>>>(rows, c, static_cast<const XT *>(x), partials);
+    bn_partial_kernel<XT><<<grid, kDenseBlock, 0, st>>>(rows, c, static_cast<const XT *>(x), ldx, partials);
     launch_chain(pdl, partials_reduce_kernel, div_up(2 * c, 32), 32 * kReduceSlices, 0, st, grid, 2 * c, (const float *)partials, sums);
     const float unbias = rows > 1 ? (float)((double)rows / (double)(rows - 1)) : 1.f;
-    launch_chain(pdl, bn_apply_kernel<XT, OT>, grid, kDenseBlock, 0, st, rows, c, static_cast<const XT *>(x),
+    launch_chain(pdl, bn_apply_kernel<XT, OT>, grid, kDenseBlock, 0, st, rows, c, static_cast<const XT *>(x), ldx,
                  (const double *)sums, 1.0 / (double)rows, eps, gamma, beta, static_cast<const OT *>(residual), row_scale,
                  relu, static_cast<OT *>(out), stats_out, running_mean, running_var, momentum, unbias, mean_shift, batches_tracked);
     return check_launch(3);
 }
 
 template <typename XT, typename OT>
-static int bn_backward_t(long long rows, int c, const void *grad_out, const void *out, const void *x, const float *stats,
-                         const float *gamma, const float *row_scale, void *grad_x, void *grad_residual,
+static int bn_backward_t(long long rows, int c, const void *grad_out, const void *out, const void *x, long long ldx,
+                         const float *stats, const float *gamma, const float *row_scale, void *grad_x, long long ldgx,
+                         void *grad_residual,
                          float *grad_gamma, float *grad_beta, float *partials, double *sums, cudaStream_t st) {
     const int grid = bn_grid(rows, c);
     const bool pdl = tuning(kTunePdl) != 2;
     bn_bwd_partial_kernel<XT, OT><<<grid, kDenseBlock, 0, st>>>(rows, c, static_cast<const OT *>(grad_out),
                                                                 static_cast<const OT *>(out), static_cast<const XT *>(x),
-                                                                stats, row_scale, partials);
+                                                                ldx, stats, row_scale, partials);
     launch_chain(pdl, partials_reduce_kernel, div_up(2 * c, 32), 32 * kReduceSlices, 0, st, grid, 2 * c, (const float *)partials, sums);
     launch_chain(pdl, bn_bwd_apply_kernel<XT, OT>, grid, kDenseBlock, 0, st, rows, c, static_cast<const OT *>(grad_out),
-                 static_cast<const OT *>(out), static_cast<const XT *>(x), stats, gamma, row_scale, (const double *)sums,
-                 1.0 / (double)rows, static_cast<XT *>(grad_x), static_cast<OT *>(grad_residual), grad_gamma, grad_beta);
+                 static_cast<const OT *>(out), static_cast<const XT *>(x), ldx, stats, gamma, row_scale, (const double *)sums,
+                 1.0 / (double)rows, static_cast<XT *>(grad_x), ldgx, static_cast<OT *>(grad_residual), grad_gamma, grad_beta);
     return check_launch(3);
 }
 
@@ -652,19 +653,20 @@ static bool carve_dense(void *ws, size_t ws_bytes, int width, float **partials, 
     return true;
 }
 
-extern "C" int aopt_bn_act_forward(int64_t rows, int c, const void *x, int x_dtype, const float *gamma, const float *beta,
+extern "C" int aopt_bn_act_forward(int64_t rows, int c, const void *x, int64_t ldx, int x_dtype, const float *gamma, const float *beta,
                                    float eps, const void *residual, const float *row_scale, int relu, void *out,
                                    int out_dtype, float *stats_out, float *running_mean, float *running_var,
                                    float momentum, const float *mean_shift, long long *batches_tracked, void *workspace,
                                    size_t workspace_bytes, aopt_stream_t stream) {
     if (rows <= 0 || !bn_width_ok(c) || !x || !gamma || !beta || !out || !stats_out) return AOPT_ERR_INVALID_ARGUMENT;
     if ((x_dtype | out_dtype) & ~1) return AOPT_ERR_INVALID_ARGUMENT;
+    if (ldx < c || (ldx & 3)) return AOPT_ERR_INVALID_ARGUMENT;   // rows of x stay 4-element aligned
     float *partials;
     double *sums;
     if (!carve_dense(workspace, workspace_bytes, 2 * c, &partials, &sums)) return AOPT_ERR_WORKSPACE;
     cudaStream_t st = as_stream(stream);
 #define AOPT_BN_FWD(XT, OT)                                                                                               \
-    return bn_forward_t<XT, OT>(rows, c, x, gamma, beta, eps, residual, row_scale, relu, out, stats_out, running_mean,   \
+    return bn_forward_t<XT, OT>(rows, c, x, ldx, gamma, beta, eps, residual, row_scale, relu, out, stats_out, running_mean,   \
                                 running_var, momentum, mean_shift, batches_tracked, partials, sums, st)
     if (x_dtype == AOPT_F32 && out_dtype == AOPT_F32) AOPT_BN_FWD(float, float);
     if (x_dtype == AOPT_F32 && out_dtype == AOPT_BF16) AOPT_BN_FWD(float, __nv_bfloat16);
@@ -674,18 +676,19 @@ extern "C" int aopt_bn_act_forward(int64_t rows, int c, const void *x, int x_dty
 }
 
 extern "C" int aopt_bn_act_backward(int64_t rows, int c, const void *grad_out, const void *out, int out_dtype, const void *x,
-                                    int x_dtype, const float *stats, const float *gamma, const float *row_scale,
-                                    void *grad_x, void *grad_residual, float *grad_gamma, float *grad_beta,
+                                    int64_t ldx, int x_dtype, const float *stats, const float *gamma, const float *row_scale,
+                                    void *grad_x, int64_t ldgx, void *grad_residual, float *grad_gamma, float *grad_beta,
                                     void *workspace, size_t workspace_bytes, aopt_stream_t stream) {
     if (rows <= 0 || !bn_width_ok(c) || !grad_out || !x || !stats || !gamma || !grad_x || !grad_gamma || !grad_beta)
         return AOPT_ERR_INVALID_ARGUMENT;
     if ((x_dtype | out_dtype) & ~1) return AOPT_ERR_INVALID_ARGUMENT;
+    if (ldx < c || (ldx & 3) || ldgx < c || (ldgx & 3)) return AOPT_ERR_INVALID_ARGUMENT;
     float *partials;
     double *sums;
     if (!carve_dense(workspace, workspace_bytes, 2 * c, &partials, &sums)) return AOPT_ERR_WORKSPACE;
     cudaStream_t st = as_stream(stream);
 #define AOPT_BN_BWD(XT, OT)                                                                                               \
-    return bn_backward_t<XT, OT>(rows, c, grad_out, out, x, stats, gamma, row_scale, grad_x, grad_residual, grad_gamma,  \
+    return bn_backward_t<XT, OT>(rows, c, grad_out, out, x, ldx, stats, gamma, row_scale, grad_x, ldgx, grad_residual, grad_gamma,  \
                                  grad_beta, partials, sums, st)
     if (x_dtype == AOPT_F32 && out_dtype == AOPT_F32) AOPT_BN_BWD(float, float);
     if (x_dtype == AOPT_F32 && out_dtype == AOPT_BF16) AOPT_BN_BWD(float, __nv_bfloat16);

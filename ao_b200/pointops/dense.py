@@ -60,7 +60,7 @@ class _BnActFn(Function):
         with _lib.on_device(dev):
             ws = _dense_ws(2 * c, dev)
             _lib.check(
-                lib.aopt_bn_act_forward(rows, c, x.data_ptr(), _DT[x.dtype], gamma.data_ptr(), beta.data_ptr(), eps,
+                lib.aopt_bn_act_forward(rows, c, x.data_ptr(), c, _DT[x.dtype], gamma.data_ptr(), beta.data_ptr(), eps,
                                         _lib.ptr(residual), _lib.ptr(row_scale), int(relu), out.data_ptr(), _DT[out_dtype],
                                         stats.data_ptr(), _lib.ptr(running_mean), _lib.ptr(running_var), momentum,
                                         _lib.ptr(pre_bias), _lib.ptr(tracked), ws.data_ptr(), ws.numel(), _lib.stream()),
@@ -89,8 +89,8 @@ class _BnActFn(Function):
         with _lib.on_device(dev):
             ws = _dense_ws(2 * c, dev)
             _lib.check(
-                lib.aopt_bn_act_backward(rows, c, grad_out.data_ptr(), _lib.ptr(out), _DT[odt], x.data_ptr(), _DT[x.dtype],
-                                         stats.data_ptr(), gamma.data_ptr(), _lib.ptr(row_scale), gx.data_ptr(),
+                lib.aopt_bn_act_backward(rows, c, grad_out.data_ptr(), _lib.ptr(out), _DT[odt], x.data_ptr(), c, _DT[x.dtype],
+                                         stats.data_ptr(), gamma.data_ptr(), _lib.ptr(row_scale), gx.data_ptr(), c,
                                          _lib.ptr(gres), gg.data_ptr(), gb.data_ptr(), ws.data_ptr(), ws.numel(),
                                          _lib.stream()),
                 "bn_act_backward")
@@ -338,3 +338,130 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor = None, out
         return _LinearFn.apply(x, weight, bias, torch.get_autocast_dtype("cuda"), bool(out_f32))
     y = torch.nn.functional.linear(x, weight, bias)
     return y.float() if out_f32 else y
+
+
+# ---- q | k | v of GroupedVectorAttention as ONE GEMM -----------------------------------------------------------------
+# linear_q / linear_k (Linear -> PointBatchNorm -> ReLU) and linear_v (Linear) read the same input (…v2m2_base.py:104-108):
+# one (N, C) x (C, 3C) product instead of three, the two BatchNorm stages read their column block of the result in
+# place (row stride 3C) and, in the backward pass, write their input gradients into the column blocks of ONE (N, 3C)
+# buffer, so dX and dW are one product each as well: 3 cuBLAS calls per block instead of 9, one autograd node instead of 5.
+def _cat_weights(ws, dt):
+    """[Wq; Wk; Wv] in dtype dt, cached on Wq until one of the three parameters changes."""
+    wq = ws[0]
+    ver = tuple(w._version for w in ws)
+    hit = getattr(wq, "_aopt_cat", None)
+    if hit is not None and hit[0] == ver and hit[1] == dt and hit[3] is ws[1] and hit[4] is ws[2]:
+        return hit[2]
+    cat = torch.cat([w.detach() for w in ws], 0).to(dt)
+    wq._aopt_cat = (ver, dt, cat, ws[1], ws[2])
+    return cat
+
+
+class _QkvFn(Function):
+    @staticmethod
+    def forward(ctx, x, wq, bq, wk, bk, wv, bv, gq, betaq, gk, betak, rmq, rvq, rmk, rvk, momq, momk, epsq, epsk,
+                trq, trk, dt, qk_dtype):
+        lib = _lib.load()
+        dev = x.device
+        rows, c = x.shape
+        xb = x if x.dtype == dt else x.to(dt)
+        wcat = _cat_weights((wq, wk, wv), dt)
+        y = torch.mm(xb, wcat.t())                                           # (rows, 3c): q_pre | k_pre | v_pre
+        q = torch.empty((rows, c), dtype=qk_dtype, device=dev)
+        k = torch.empty((rows, c), dtype=qk_dtype, device=dev)
+        stats = torch.empty(4 * c, dtype=torch.float32, device=dev)
+        esz = y.element_size()
+        with _lib.on_device(dev):
+            ws = _dense_ws(2 * c, dev)
+            for j, (out, g, b, rm, rv, mom, eps, bias, tr) in enumerate(((q, gq, betaq, rmq, rvq, momq, epsq, bq, trq),
+                                                                         (k, gk, betak, rmk, rvk, momk, epsk, bk, trk))):
+                _lib.check(
+                    lib.aopt_bn_act_forward(rows, c, y.data_ptr() + j * c * esz, 3 * c, _DT[dt], g.data_ptr(), b.data_ptr(),
+                                            eps, 0, 0, 1, out.data_ptr(), _DT[qk_dtype], stats.data_ptr() + j * 8 * c,
+                                            _lib.ptr(rm), _lib.ptr(rv), mom, _lib.ptr(bias), _lib.ptr(tr), ws.data_ptr(),
+                                            ws.numel(), _lib.stream()),
+                    "bn_act_forward")
+        v = y[:, 2 * c:].to(torch.float32, copy=True)                        # dense fp32 copy of the column block
+        if bv is not None:
+            v.add_(bv)
+        ctx.save_for_backward(xb, wcat, y, q, k, gq, gk, stats)
+        ctx.x_dtype = x.dtype
+        ctx.biases = (bq, bk, bv)
+        return q, k, v
+
+    @staticmethod
+    def backward(ctx, gq_out, gk_out, gv):
+        lib = _lib.load()
+        xb, wcat, y, q, k, gq, gk, stats = ctx.saved_tensors
+        dev = xb.device
+        rows, c = xb.shape
+        dt = y.dtype
+        gy = torch.empty_like(y)
+        ggq, gbq, ggk, gbk = (torch.empty(c, dtype=torch.float32, device=dev) for _ in range(4))
+        esz = y.element_size()
+        with _lib.on_device(dev):
+            ws = _dense_ws(2 * c, dev)
+            for j, (go, out, g, gg, gb) in enumerate(((gq_out, q, gq, ggq, gbq), (gk_out, k, gk, ggk, gbk))):
+                if go is None:
+                    gy[:, j * c:(j + 1) * c].zero_()
+                    gg.zero_()
+                    gb.zero_()
+                    continue
+                if go.dtype != out.dtype or not go.is_contiguous():
+                    go = go.to(out.dtype).contiguous()
+                _lib.check(
+                    lib.aopt_bn_act_backward(rows, c, go.data_ptr(), out.data_ptr(), _DT[out.dtype], y.data_ptr() + j * c * esz,
+                                             3 * c, _DT[dt], stats.data_ptr() + j * 8 * c, g.data_ptr(), 0,
+                                             gy.data_ptr() + j * c * esz, 3 * c, 0, gg.data_ptr(), gb.data_ptr(),
+                                             ws.data_ptr(), ws.numel(), _lib.stream()),
+                    "bn_act_backward")
+        if gv is None:
+            gy[:, 2 * c:].zero_()
+        else:
+            gy[:, 2 * c:].copy_(gv)
+        gx = None
+        if ctx.needs_input_grad[0]:
+            gx = torch.mm(gy, wcat)
+            if gx.dtype != ctx.x_dtype:
+                gx = gx.to(ctx.x_dtype)
+        gw = _mm_f32(gy.t(), xb) if dt != torch.float32 else torch.mm(gy.t(), xb)
+        bq, bk, bv = ctx.biases
+        zq = torch.zeros_like(bq) if bq is not None else None          # in front of a training-mode BatchNorm
+        zk = torch.zeros_like(bk) if bk is not None else None
+        gbv = gv.sum(0, dtype=torch.float32) if (bv is not None and gv is not None) else (None if bv is None else torch.zeros_like(bv))
+        return (gx, gw[:c], zq, gw[c:2 * c], zk, gw[2 * c:], gbv, ggq, gbq, ggk, gbk) + (None,) * 12
+
+
+def qkv_usable(x: torch.Tensor, seq_q, seq_k, lin_v) -> bool:
+    """linear_q / linear_k are [Linear(C,C), PointBatchNorm(C), ReLU], linear_v is Linear(C,C), all on x (N, C), and the
+    BatchNorm stages run on batch statistics."""
+    try:
+        lq, bq, lk, bk = seq_q[0], getattr(seq_q[1], "norm", seq_q[1]), seq_k[0], getattr(seq_k[1], "norm", seq_k[1])
+    except (TypeError, IndexError):
+        return False
+    c = x.shape[-1]
+    dt = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled() else x.dtype
+    return (x.dim() == 2 and len(seq_q) == 3 and len(seq_k) == 3 and isinstance(seq_q[2], torch.nn.ReLU)
+            and isinstance(seq_k[2], torch.nn.ReLU) and isinstance(bq, torch.nn.BatchNorm1d) and isinstance(bk, torch.nn.BatchNorm1d)
+            and all(isinstance(l, torch.nn.Linear) and l.weight.shape == (c, c) and l.weight.dtype == torch.float32
+                    for l in (lq, lk, lin_v))
+            and bn_fusable(bq, c, x.shape[0], x.is_cuda, dt) and bn_fusable(bk, c, x.shape[0], x.is_cuda, dt))
+
+
+def qkv_bn(x: torch.Tensor, seq_q, seq_k, lin_v, qk_dtype: torch.dtype = None):
+    """(ReLU(BN_q(x Wqᵀ + bq)), ReLU(BN_k(x Wkᵀ + bk)), x Wvᵀ + bv) with one GEMM (see above).  q, k in qk_dtype
+    (default: the GEMM's dtype — the autocast dtype, or x's), v in fp32 (it feeds gva_aggregate).  Check qkv_usable()."""
+    lq, bnq, lk, bnk = seq_q[0], getattr(seq_q[1], "norm", seq_q[1]), seq_k[0], getattr(seq_k[1], "norm", seq_k[1])
+    dt = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled() else x.dtype
+    if qk_dtype is None:
+        qk_dtype = dt
+    if not x.is_contiguous():
+        x = x.contiguous()
+    trackq = bnq.training and bnq.track_running_stats
+    trackk = bnk.training and bnk.track_running_stats
+    momq, trq = _momentum(bnq, trackq)
+    momk, trk = _momentum(bnk, trackk)
+    return _QkvFn.apply(x, lq.weight, lq.bias, lk.weight, lk.bias, lin_v.weight, lin_v.bias, bnq.weight, bnq.bias, bnk.weight,
+                        bnk.bias, bnq.running_mean if trackq else None, bnq.running_var if trackq else None,
+                        bnk.running_mean if trackk else None, bnk.running_var if trackk else None, momq, momk,
+                        float(bnq.eps), float(bnk.eps), trq, trk, dt, qk_dtype)

@@ -152,8 +152,11 @@ class GroupedVectorAttention(nn.Module):
         # the point operators compute in fp32: q / k feed a GEMM in the relation-free schedule (any dtype) and
         # gva_relation otherwise (fp32); value always feeds gva_aggregate
         qk_dtype = None if fused else torch.float32
-        query, key = run_seq(self.linear_q, feat, qk_dtype), run_seq(self.linear_k, feat, qk_dtype)
-        value = pointops.linear(feat, self.linear_v.weight, self.linear_v.bias, out_f32=True)
+        if pointops.qkv_usable(feat, self.linear_q, self.linear_k, self.linear_v):
+            query, key, value = pointops.qkv_bn(feat, self.linear_q, self.linear_k, self.linear_v, qk_dtype)   # one GEMM
+        else:
+            query, key = run_seq(self.linear_q, feat, qk_dtype), run_seq(self.linear_k, feat, qk_dtype)
+            value = pointops.linear(feat, self.linear_v.weight, self.linear_v.bias, out_f32=True)
         if pos is None:                                                       # (N,k,3): depends only on (idx, coord)
             pos = pointops.group_xyz(reference_index, coord)                  # :109,:111
         if fused:

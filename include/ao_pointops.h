@@ -281,23 +281,24 @@ size_t aopt_dense_workspace_bytes(int width);
  * (N, C) / (N*k, C) tensors with the nn.ReLU, DropPath scale and residual add that follow it in a PTv2 block
  * (point_transformer_v2m2_base.py:25-45,187-197; Linear -> PointBatchNorm -> ReLU triples :86-93,240-242,288-295).
  * Batch statistics in fp32 with fp64 combination; x and out/residual are fp32 or bf16 (x_dtype / out_dtype; residual has
- * out's type); c % 4 == 0, c <= 1024 (aopt_bn_act_supported).  stats_out (2c floats) = batch mean | rstd, kept for the
+ * out's type); c % 4 == 0, c <= 1024 (aopt_bn_act_supported).  ldx = row stride of x in elements (>= c, a multiple of 4):
+ * x may be a column block of a wider matrix, e.g. the q or k part of a fused q|k|v GEMM output; out is dense.  stats_out (2c floats) = batch mean | rstd, kept for the
  * backward pass; running_mean / running_var (optional) are updated like nn.BatchNorm1d does (momentum, unbiased
  * variance).  mean_shift (optional, c floats) is added to the batch mean in the running-mean update only: a Linear bias
  * in front of a training-mode BatchNorm cancels in the output, so the caller may leave it out of x.  residual, row_scale
  * may be NULL; relu = 0 / 1.  batches_tracked (optional): device int64 counter incremented by one
  * (nn.BatchNorm1d.num_batches_tracked). */
 int aopt_bn_act_supported(int c);
-int aopt_bn_act_forward(int64_t rows, int c, const void *x, int x_dtype, const float *gamma, const float *beta, float eps,
+int aopt_bn_act_forward(int64_t rows, int c, const void *x, int64_t ldx, int x_dtype, const float *gamma, const float *beta, float eps,
                         const void *residual, const float *row_scale, int relu, void *out, int out_dtype,
                         float *stats_out, float *running_mean, float *running_var, float momentum,
                         const float *mean_shift, long long *batches_tracked, void *workspace, size_t workspace_bytes,
                         aopt_stream_t stream);
 /* Backward of the above.  out = the forward result (only read when relu was 1: pass NULL otherwise).  grad_x has x's
- * type; grad_residual (optional, out's type) = grad_out masked by the ReLU.  Deterministic (no atomics). */
+ * type and row stride ldgx; grad_residual (optional, out's type) = grad_out masked by the ReLU.  Deterministic (no atomics). */
 int aopt_bn_act_backward(int64_t rows, int c, const void *grad_out, const void *out, int out_dtype, const void *x,
-                         int x_dtype, const float *stats, const float *gamma, const float *row_scale, void *grad_x,
-                         void *grad_residual, float *grad_gamma, float *grad_beta, void *workspace,
+                         int64_t ldx, int x_dtype, const float *stats, const float *gamma, const float *row_scale,
+                         void *grad_x, int64_t ldgx, void *grad_residual, float *grad_gamma, float *grad_beta, void *workspace,
                          size_t workspace_bytes, aopt_stream_t stream);
 /* Tail of GroupedVectorAttention.weight_encoding (point_transformer_v2m2_base.py:94-99,120) on the (rows = N*nsample, g)
  * tensors:  u = rel + upe + cst  (upe (rows, g) and cst (g) optional),  logits = W2 * ReLU(BatchNorm_train(u)) + b2.

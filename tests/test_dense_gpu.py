@@ -231,3 +231,48 @@ def test_cached_weight_linear_equals_autocast_linear():
         torch.testing.assert_close(pointops.linear(x, lin.weight, lin.bias).float(), ref(x).float(), rtol=2 ** -7, atol=2 ** -7)
     # no autocast: plain fp32 F.linear
     torch.testing.assert_close(pointops.linear(x, lin.weight, lin.bias), ref(x))
+
+
+@pytest.mark.parametrize("autocast", [False, True])
+def test_qkv_one_gemm_equals_three_layers(autocast):
+    """pointops.qkv_bn (one (N,C)x(C,3C) product, BatchNorm stages on column blocks) against linear_q / linear_k /
+    linear_v evaluated one by one with torch modules."""
+    from ao_b200 import pointops, ptv2
+
+    torch.manual_seed(21)
+    c, n = 96, 6000
+    gva = ptv2.GroupedVectorAttention(c, 12).to(DEV).train()
+    ref = ptv2.GroupedVectorAttention(c, 12).to(DEV).train()
+    ref.load_state_dict(gva.state_dict())
+    x = torch.randn(n, c, device=DEV, requires_grad=True)
+    xr = x.detach().clone().requires_grad_(True)
+    assert pointops.qkv_usable(x, gva.linear_q, gva.linear_k, gva.linear_v)
+    with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+        q, k, v = pointops.qkv_bn(x, gva.linear_q, gva.linear_k, gva.linear_v)
+        qr, kr, vr = ref.linear_q(xr), ref.linear_k(xr), ref.linear_v(xr)
+    assert v.dtype == torch.float32 and v.is_contiguous() and q.dtype == qr.dtype
+    tol = dict(rtol=2 ** -6, atol=2 ** -6) if autocast else dict(rtol=1e-4, atol=1e-4)
+    for a, b in ((q, qr), (k, kr), (v, vr)):
+        torch.testing.assert_close(a.float(), b.float(), **tol)
+    for name in ("running_mean", "running_var"):
+        for s in ("linear_q", "linear_k"):
+            torch.testing.assert_close(getattr(getattr(gva, s)[1].norm, name), getattr(getattr(ref, s)[1].norm, name),
+                                       rtol=1e-2 if autocast else 1e-4, atol=1e-2 if autocast else 1e-5)
+    wts = [torch.randn(n, c, device=DEV) for _ in range(3)]
+    (q.float() * wts[0] + k.float() * wts[1] + v * wts[2]).sum().backward()
+    (qr.float() * wts[0] + kr.float() * wts[1] + vr.float() * wts[2]).sum().backward()
+    if autocast:
+        # bf16: a pre-activation that rounds to the other side of zero flips a ReLU mask in one of the two
+        # implementations — isolated elements differ, so the input gradient is compared in the L2 norm
+        assert float((x.grad - xr.grad).norm() / xr.grad.norm()) < 2e-2
+    else:
+        torch.testing.assert_close(x.grad, xr.grad, rtol=1e-3, atol=1e-3 * float(xr.grad.abs().max()))
+    for s in ("linear_q", "linear_k"):
+        wa, wb = getattr(gva, s)[0].weight.grad, getattr(ref, s)[0].weight.grad
+        torch.testing.assert_close(wa, wb, rtol=5e-2 if autocast else 1e-3, atol=(5e-2 if autocast else 1e-3) * float(wb.abs().max()))
+        ga, gb = getattr(gva, s)[1].norm.weight.grad, getattr(ref, s)[1].norm.weight.grad
+        torch.testing.assert_close(ga, gb, rtol=5e-2 if autocast else 1e-3, atol=(5e-2 if autocast else 1e-3) * float(gb.abs().max()))
+        assert float(getattr(gva, s)[0].bias.grad.abs().max()) == 0.0
+    torch.testing.assert_close(gva.linear_v.weight.grad, ref.linear_v.weight.grad, rtol=5e-2 if autocast else 1e-3,
+                               atol=(5e-2 if autocast else 1e-3) * float(ref.linear_v.weight.grad.abs().max()))
+    torch.testing.assert_close(gva.linear_v.bias.grad, ref.linear_v.bias.grad, rtol=2e-2, atol=2e-2 * float(ref.linear_v.bias.grad.abs().max()))

@@ -22,6 +22,7 @@ enum Tuning { kTuneCsrImpl = 0,   // AOPT_CSR_IMPL:   1 = radix sort, 2 = count 
               kTuneGvaBwd = 1,    // AOPT_GVA_BWD:    1 = fused kernel, 2 = two kernels
               kTuneVoxelSort = 2, // AOPT_VOXEL_SORT: 1 = own radix sort (3 passes), 2 = wide keys (6 passes)
               kTuneKnnTopk = 3,   // AOPT_KNN_TOPK:   1 = shared-memory heap (K >= 8), 0 / 2 = sorted list in registers (default)
+              kTuneKnnPend = 4,   // AOPT_KNN_PEND:   1 = per-lane pending list in the GRID query kernel (K >= 8), 0 / 2 = insert in place (default)
               kTuneKnnSample = 5, // AOPT_KNN_SAMPLE: 1 = cell edge from the bounding box (no density sample), 0 / 2 = sampled r_k (default)
               kTunePdl = 6,       // AOPT_PDL:        1 = programmatic dependent launch inside the small-kernel chains, 2 = off
               kTuneCount = 8 };

@@ -358,20 +358,54 @@ struct HeapK {
     }
 };
 
-// Candidates of a run are requested four at a time: the offer is a divergent branch, so a load issued next to
-// its use would expose its L1/L2 latency on every candidate — on the small levels, where a scheduler holds a
-// single warp, that latency is the kernel time.  (A cross-iteration prefetch of the next four cost 32 more
-// registers and spills at K = 16; not kept.)
+// Candidates of a run are requested eight at a time (the offer is a divergent branch, so a load issued next to its use
+// would expose its L1/L2 latency on every candidate).
+//
+// Pending list (round 2, opt-in: see launch_query for the measurement).  A warp executes the 96-instruction list insert whenever ANY of its 32 queries accepts the
+// candidate at hand — and with a per-lane acceptance probability of 16 / i for the i-th candidate that is nearly every
+// candidate, with 1-4 lanes doing useful work late in the scan (ncu r01q: 14.5 of 32 lanes active over the kernel).
+// Here each lane first tests its eight candidates against its current k-th distance and appends the survivors to a
+// private pending list (one 64-bit (d2 : idx) word per entry in the lane's own shared-memory column), then drains the
+// list: the warp runs max-over-lanes(list length) inserts per eight candidates instead of (almost) eight — ~3 early in
+// the scan, 1-2 once the threshold has settled.  Entries that no longer qualify when their turn comes (the threshold moved
+// inside the batch) fail the offer's own test.  Same result: the candidate set and the (d2, idx) ranking are unchanged.
+constexpr int kPendBatch = 8;
+
 template <class Top>
-__device__ __forceinline__ void scan_run(Top &top, const float4 *__restrict__ sorted, int a,
-                                         int e, float qx, float qy, float qz) {
+__device__ __forceinline__ void scan_run(Top &top, const float4 *__restrict__ sorted, int a, int e, float qx,
+                                         float qy, float qz, unsigned long long *__restrict__ pend) {
+    for (int i = a; i < e; i += kPendBatch) {
+        float4 c[kPendBatch];
+#pragma unroll
+        for (int u = 0; u < kPendBatch; ++u) c[u] = __ldg(sorted + min(i + u, e - 1));
+        const float w = top.worst();
+        int cnt = 0;
+#pragma unroll
+        for (int u = 0; u < kPendBatch; ++u) {
+            const float d = dist2_ref(qx, qy, qz, c[u].x, c[u].y, c[u].z);
+            // '<=': a candidate that ties with the k-th distance can still win on its index (LEX rule)
+            if (i + u < e && d <= w) {
+                pend[cnt * kQueryBlock] = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)__float_as_int(c[u].w);
+                ++cnt;
+            }
+        }
+        for (int r = 0; r < cnt; ++r) {
+            const unsigned long long p = pend[r * kQueryBlock];
+            top.offer(__uint_as_float((unsigned)(p >> 32)), (int)(unsigned)p);
+        }
+    }
+}
+
+// the batch-of-four form of round 1 (tuning "knn_pend" = 2): every accepted candidate is inserted where it is found
+template <class Top>
+__device__ __forceinline__ void scan_run4(Top &top, const float4 *__restrict__ sorted, int a,
+                                          int e, float qx, float qy, float qz) {
     int i = a;
     for (; i + 4 <= e; i += 4) {
         const float4 c0 = __ldg(sorted + i), c1 = __ldg(sorted + i + 1), c2 = __ldg(sorted + i + 2),
                      c3 = __ldg(sorted + i + 3);
         const float d0 = dist2_ref(qx, qy, qz, c0.x, c0.y, c0.z), d1 = dist2_ref(qx, qy, qz, c1.x, c1.y, c1.z);
         const float d2 = dist2_ref(qx, qy, qz, c2.x, c2.y, c2.z), d3 = dist2_ref(qx, qy, qz, c3.x, c3.y, c3.z);
-        // '<=': a candidate that ties with the k-th distance can still win on its index (LEX rule)
         if (fminf(fminf(d0, d1), fminf(d2, d3)) <= top.worst()) {
             top.offer(d0, __float_as_int(c0.w));
             top.offer(d1, __float_as_int(c1.w));
@@ -383,6 +417,13 @@ __device__ __forceinline__ void scan_run(Top &top, const float4 *__restrict__ so
         const float4 c = __ldg(sorted + i);
         top.offer(dist2_ref(qx, qy, qz, c.x, c.y, c.z), __float_as_int(c.w));
     }
+}
+
+template <bool PEND, class Top>
+__device__ __forceinline__ void scan(Top &top, const float4 *__restrict__ sorted, int a, int e, float qx, float qy,
+                                     float qz, unsigned long long *__restrict__ pend) {
+    if (PEND) scan_run(top, sorted, a, e, qx, qy, qz, pend);
+    else scan_run4(top, sorted, a, e, qx, qy, qz);
 }
 
 template <int K, bool HEAP>
@@ -402,7 +443,7 @@ struct TopSel<K, true> {
     static __device__ __forceinline__ void reset(type &t) { t.reset(); }
 };
 
-template <int K, bool SELF, bool HEAP>
+template <int K, bool SELF, bool HEAP, bool PEND>
 __global__ void __launch_bounds__(kQueryBlock)
 knn_grid_kernel(int m, int b, int nsample, const float *__restrict__ new_xyz,
                 const int *__restrict__ new_offset, const GridDesc *__restrict__ desc,
@@ -426,6 +467,8 @@ knn_grid_kernel(int m, int b, int nsample, const float *__restrict__ new_xyz,
         qx = __ldg(new_xyz + (size_t)t * 3); qy = __ldg(new_xyz + (size_t)t * 3 + 1);
         qz = __ldg(new_xyz + (size_t)t * 3 + 2);
     }
+    __shared__ unsigned long long s_pend[PEND ? kPendBatch * kQueryBlock : 1];
+    unsigned long long *pend = s_pend + (PEND ? threadIdx.x : 0);
     typename TopSel<K, HEAP>::type top;
     TopSel<K, HEAP>::init(top);
     if (sc < b) {
@@ -453,12 +496,12 @@ knn_grid_kernel(int m, int b, int nsample, const float *__restrict__ new_xyz,
                         const bool full = (r == 1) || max(abs(dz), abs(dy)) == r;
                         if (full) {
                             const int x0 = max(cx - r, 0), x1 = min(cx + r, g.nx - 1);
-                            scan_run(top, sorted, __ldg(cs + rowbase + x0), __ldg(cs + rowbase + x1 + 1), qx, qy, qz);
+                            scan<PEND>(top, sorted, __ldg(cs + rowbase + x0), __ldg(cs + rowbase + x1 + 1), qx, qy, qz, pend);
                         } else {
                             if (cx - r >= 0)
-                                scan_run(top, sorted, __ldg(cs + rowbase + cx - r), __ldg(cs + rowbase + cx - r + 1), qx, qy, qz);
+                                scan<PEND>(top, sorted, __ldg(cs + rowbase + cx - r), __ldg(cs + rowbase + cx - r + 1), qx, qy, qz, pend);
                             if (cx + r <= g.nx - 1)
-                                scan_run(top, sorted, __ldg(cs + rowbase + cx + r), __ldg(cs + rowbase + cx + r + 1), qx, qy, qz);
+                                scan<PEND>(top, sorted, __ldg(cs + rowbase + cx + r), __ldg(cs + rowbase + cx + r + 1), qx, qy, qz, pend);
                         }
                     }
                 }
@@ -479,7 +522,7 @@ knn_grid_kernel(int m, int b, int nsample, const float *__restrict__ new_xyz,
             }
             if (!done) {  // sparse neighbourhood: exhaustive scan of the scene
                 TopSel<K, HEAP>::reset(top);
-                scan_run(top, sorted, g.start, g.end, qx, qy, qz);
+                scan<PEND>(top, sorted, g.start, g.end, qx, qy, qz, pend);
             }
         }
     }
@@ -523,16 +566,16 @@ size_t knn_grid_workspace_bytes(int n, int m, int b) {
     return carve(nullptr, n, b).bytes;
 }
 
-template <int K, bool HEAP>
+template <int K, bool HEAP, bool PEND>
 static void launch_query_t(bool self, int m, int b, int nsample, const float *new_xyz, const int *new_offset,
                            const GridWs &w, int *idx, float *dist2, bool root, cudaStream_t st) {
     const int grid = div_up(m, kQueryBlock);
     const bool pdl = tuning(kTunePdl) != 2;
     if (self)
-        launch_chain(pdl, knn_grid_kernel<K, true, HEAP>, grid, kQueryBlock, 0, st, m, b, nsample, new_xyz, new_offset,
+        launch_chain(pdl, knn_grid_kernel<K, true, HEAP, PEND>, grid, kQueryBlock, 0, st, m, b, nsample, new_xyz, new_offset,
                      (const GridDesc *)w.desc, (const int *)w.cells, (const float4 *)w.sorted, idx, dist2, root);
     else
-        launch_chain(pdl, knn_grid_kernel<K, false, HEAP>, grid, kQueryBlock, 0, st, m, b, nsample, new_xyz, new_offset,
+        launch_chain(pdl, knn_grid_kernel<K, false, HEAP, PEND>, grid, kQueryBlock, 0, st, m, b, nsample, new_xyz, new_offset,
                      (const GridDesc *)w.desc, (const int *)w.cells, (const float4 *)w.sorted, idx, dist2, root);
 }
 
@@ -542,16 +585,28 @@ static void launch_query_t(bool self, int m, int b, int nsample, const float *ne
 // level 0) or slower (173 vs 146 us at level 1, 113 vs 84 us at level 3), at k = 8 slower everywhere: a sift is
 // <= 4 dependent shared-memory round trips with the lanes at different depths, which costs the warp as many issue
 // slots as the 96 independent compares / selects of the list insert.
+// Pending list (tuning "knn_pend", AOPT_KNN_PEND=1|0), K >= 8.  Default: off.  Measured (profiles/r02s_knn_variants_ab.txt,
+// identical bits): level 0, k = 16: 335 us with the list, 319 us inserting in place; level 1: 180 vs 147 us; ScanNet
+// 3 x 150k: 430 vs 385 us; it gains only at k = 32 (KITTI 811 vs 891 us).  The premise — a warp inserting for 1-4 of its
+// lanes through most of the scan — does not hold at k = 16: a query sees only ~60 candidates in its 27 cells (4 cells per
+// point: most cells of an indoor scan are empty), so the acceptance probability 16 / i stays above 0.25 to the end and
+// the longest pending list of a warp is as long as the batch.
 template <int K>
 static void launch_query(bool self, int m, int b, int nsample, const float *new_xyz, const int *new_offset,
                          const GridWs &w, int *idx, float *dist2, bool root, cudaStream_t st) {
     if constexpr (K >= 8) {
+        const bool pend = tuning(kTuneKnnPend) == 1;
         if (tuning(kTuneKnnTopk) == 1) {
-            launch_query_t<K, true>(self, m, b, nsample, new_xyz, new_offset, w, idx, dist2, root, st);
+            if (pend) launch_query_t<K, true, true>(self, m, b, nsample, new_xyz, new_offset, w, idx, dist2, root, st);
+            else launch_query_t<K, true, false>(self, m, b, nsample, new_xyz, new_offset, w, idx, dist2, root, st);
+            return;
+        }
+        if (pend) {
+            launch_query_t<K, false, true>(self, m, b, nsample, new_xyz, new_offset, w, idx, dist2, root, st);
             return;
         }
     }
-    launch_query_t<K, false>(self, m, b, nsample, new_xyz, new_offset, w, idx, dist2, root, st);
+    launch_query_t<K, false, false>(self, m, b, nsample, new_xyz, new_offset, w, idx, dist2, root, st);
 }
 
 template <int K>

@@ -71,8 +71,10 @@ unsigned long long aopt_kernel_launches(void);
  * results bit for bit): "csr_impl" 1 = radix sort / 2 = count-fill-rank, "gva_bwd" 1 = fused / 2 = two kernels,
  * "voxel_sort" 1 = compact keys, 3 passes / 2 = wide keys, 6 passes, "knn_sample" 1 = cell edge from the bounding box /
  * 2 = sampled, "pdl" 1 = programmatic dependent launch inside the small-kernel chains / 2 = off, "knn_topk" 1 = top-k of the
- * GRID query kernel as a shared-memory heap / 2 = as a sorted list in registers; 0 = library default.
- * Initial values come from AOPT_CSR_IMPL / AOPT_GVA_BWD / AOPT_VOXEL_SORT / AOPT_KNN_SAMPLE / AOPT_PDL / AOPT_KNN_TOPK. */
+ * GRID query kernel as a shared-memory heap / 2 = as a sorted list in registers, "knn_pend" 1 = accepted candidates
+ * go through a per-lane pending list drained every eight candidates / 2 = inserted in place; 0 = library default.
+ * Initial values come from AOPT_CSR_IMPL / AOPT_GVA_BWD / AOPT_VOXEL_SORT / AOPT_KNN_SAMPLE / AOPT_PDL / AOPT_KNN_TOPK /
+ * AOPT_KNN_PEND. */
 int aopt_set_tuning(const char *name, int value);
 
 /* ---- offset-encoded batch layout ---------------------------------------------------------- */

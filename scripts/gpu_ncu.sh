@@ -11,7 +11,7 @@ timeout 1200 ncu --set full --clock-control none --import-source on --profile-fr
     -o $O/ops_L0 -f python scripts/profile_ops.py 0 > $O/ncu_full.log 2>&1
 tail -2 $O/ncu_full.log
 ncu -i $O/ops_L0.ncu-rep --page raw --csv > $O/ops_L0_raw.csv 2> /dev/null
-for kname in gva_backward_fused_ns_kernel gva_forward_ns_kernel pe_mlp_forward_tc_kernel pe_mlp_backward_kernel knn_grid_kernel csr_rank_kernel radix_scatter_kernel; do
+for kname in gva_backward_fused_ns_kernel gva_forward_ns_kernel pe_mlp_forward_tc_kernel pe_mlp_backward_tc_kernel knn_grid_kernel bn_bwd_apply_kernel we_bwd_partial_kernel; do
   ncu -i $O/ops_L0.ncu-rep --page source --csv -k regex:$kname -c 1 > $O/src_$kname.csv 2> /dev/null
 done
 rm -f $O/ops_L0.ncu-rep

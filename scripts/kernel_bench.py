@@ -127,6 +127,43 @@ for li in [int(x) for x in args.levels.split(",")]:
         for name, us in best.items():
             row("  " + name, us, 12.0 * n * k + 4.0 * n * k * c)
         del y, y2, gy, pos
+    # ---- dense.cu: BatchNorm + ReLU on (n, c) and the weight-encoding tail on (n*k, g); device time of the C entry points
+    # (stats pass + partial reduce + apply pass each).  Algorithmic bytes count every tensor ONCE: the second pass over x
+    # (and grad / out in the backward) is expected from the 126 MB L2 when the tensor fits.
+    import torch.nn as nn
+    for xdt, nm, esz in ((torch.bfloat16, "bf16", 2.0), (torch.float32, "f32", 4.0)):
+        bn = nn.BatchNorm1d(c).to(dev).train()
+        xin = torch.randn(n, c, device=dev).to(xdt).requires_grad_(True)
+        best = {}
+        for _ in range(5):
+            tr = _lib.trace_start()
+            yb = pointops.bn_act(xin, bn, relu=True)
+            yb.backward(torch.ones_like(yb))
+            torch.cuda.synchronize()
+            _lib.trace_stop()
+            for name, _a, s0, e0 in tr:
+                best[name] = min(best.get(name, 1e9), s0.elapsed_time(e0) * 1e3)
+        row(f"bn_act forward  ({nm}, relu)", best["aopt_bn_act_forward"], 2.0 * esz * n * c)
+        row(f"bn_act backward ({nm}, relu)", best["aopt_bn_act_backward"], 4.0 * esz * n * c)
+        del xin, yb
+    if pointops.we_tail_supported(g):
+        bn = nn.BatchNorm1d(g).to(dev).train()
+        lin = nn.Linear(g, g).to(dev)
+        relg = torch.randn(n, k, g, device=dev, requires_grad=True)
+        upeg = torch.randn(n, k, g, device=dev, requires_grad=True)
+        cstg = torch.randn(g, device=dev)
+        best = {}
+        for _ in range(5):
+            tr = _lib.trace_start()
+            yl = pointops.we_tail(relg, upeg, cstg, bn, lin)
+            yl.backward(torch.ones_like(yl))
+            torch.cuda.synchronize()
+            _lib.trace_stop()
+            for name, _a, s0, e0 in tr:
+                best[name] = min(best.get(name, 1e9), s0.elapsed_time(e0) * 1e3)
+        row("we_tail forward  (rel+upe -> logits)", best["aopt_we_tail_forward"], 12.0 * n * k * g)
+        row("we_tail backward", best["aopt_we_tail_backward"], 16.0 * n * k * g)
+        del relg, upeg, yl
     if li < 3:
         c2 = C[li + 1]
         pin = torch.relu(torch.randn(n, c2, device=dev)).requires_grad_(True)

@@ -1,5 +1,6 @@
-"""A/B of the two top-k containers of the GRID kNN query kernel (tuning "knn_topk": 1 = shared-memory heap,
-2 = sorted list in registers) on the BASELINE.json shapes: S3DIS levels 0..3 (4 rooms x 80k), one ScanNet room,
+"""A/B of the GRID kNN query kernel variants: top-k container (tuning "knn_topk": 1 = shared-memory heap,
+2 = sorted list in registers) x insert schedule ("knn_pend": 1 = per-lane pending list drained per eight candidates,
+2 = insert in place) on the BASELINE.json shapes: S3DIS levels 0..3 (4 rooms x 80k), one ScanNet room,
 two KITTI scans; k in {8, 16, 32}.  Checks that both containers return identical bits, then prints CUDA-event times
 (best of 7) of the whole search (grid build + query).
   python scripts/knn_ab.py"""
@@ -47,14 +48,18 @@ cases.append(("scannet 3x150k", levels_of(c, o, ())[0]))
 c, _, o = scenes.kitti_batch(2, 120000)
 cases.append(("kitti 2 scans", levels_of(c, o, ())[0]))
 
-print(f"{'case':18s} {'n':>8s} {'k':>3s} {'heap us':>9s} {'list us':>9s}  ratio  identical")
+VARIANTS = (("list+pend", 2, 1), ("list", 2, 2), ("heap+pend", 1, 1), ("heap", 1, 2))   # (label, knn_topk, knn_pend)
+print(f"{'case':18s} {'n':>8s} {'k':>3s} " + " ".join(f"{v[0] + ' us':>12s}" for v in VARIANTS) + "  identical")
 for name, (coord, offset) in cases:
     for k in (8, 16, 32):
         res, t = {}, {}
-        for label, v in (("heap", 1), ("list", 2)):
-            _lib.set_tuning("knn_topk", v)
+        for label, topk, pend in VARIANTS:
+            _lib.set_tuning("knn_topk", topk)
+            _lib.set_tuning("knn_pend", pend)
             res[label] = pointops.knn_query_raw(k, coord, offset, method="grid")
             t[label] = timeit(lambda: pointops.knn_query_raw(k, coord, offset, method="grid"))
-        same = torch.equal(res["heap"][0], res["list"][0]) and torch.equal(res["heap"][1], res["list"][1])
-        print(f"{name:18s} {coord.shape[0]:8d} {k:3d} {t['heap']:9.1f} {t['list']:9.1f}  {t['list'] / t['heap']:5.2f}  {same}")
+        ref = res["list"]
+        same = all(torch.equal(r[0], ref[0]) and torch.equal(r[1], ref[1]) for r in res.values())
+        print(f"{name:18s} {coord.shape[0]:8d} {k:3d} " + " ".join(f"{t[v[0]]:12.1f}" for v in VARIANTS) + f"  {same}")
 _lib.set_tuning("knn_topk", 0)
+_lib.set_tuning("knn_pend", 0)

@@ -1,6 +1,7 @@
 """One call of every hot-path operator at BASELINE.json configs[1] level-0 shapes (4 rooms x 80k, k=16,
 C=48, G=6) plus the level-0→1 pool and level-1→0 interpolation, bracketed by cudaProfilerStart/Stop
-so that `ncu --profile-from-start off` captures exactly these launches (scripts/gpu_round.sh).
+so that `ncu --profile-from-start off` captures exactly these launches (scripts/gpu_ncu.sh).  Round 2 adds the
+dense.cu operators (bn_act, we_tail) in front.
 Optional argv[1] = level (0..3) whose block shapes to use."""
 import os
 import sys
@@ -37,7 +38,21 @@ if pointops.pe_mlp_supported(c):
     aux_w = torch.randn(g, c, device=dev, requires_grad=True)
 
 
+bn_c = torch.nn.BatchNorm1d(c).to(dev).train()
+bn_g = torch.nn.BatchNorm1d(g).to(dev).train()
+lin_g = torch.nn.Linear(g, g).to(dev)
+x_bf = torch.randn(n, c, device=dev).bfloat16().requires_grad_(True)
+rel_g = torch.randn(n, k, g, device=dev, requires_grad=True)
+upe_g = torch.randn(n, k, g, device=dev, requires_grad=True)
+
+
 def run():
+    # dense.cu: BatchNorm + ReLU on (n, c) bf16 and the weight-encoding tail on (n*k, g), forward + backward
+    yb = pointops.bn_act(x_bf, bn_c, relu=True)
+    torch.autograd.grad(yb, [x_bf, bn_c.weight, bn_c.bias], torch.ones_like(yb))
+    if pointops.we_tail_supported(g):
+        yl = pointops.we_tail(rel_g, upe_g, None, bn_g, lin_g)
+        torch.autograd.grad(yl, [rel_g, upe_g, lin_g.weight], torch.ones_like(yl))
     idx, _ = pointops.knn_query(k, coord, offset)
     pos = pointops.group_xyz(idx, coord)
     if mlp is not None:      # fused positional-bias MLP (tcgen05 forward) with the auxiliary head, forward + backward

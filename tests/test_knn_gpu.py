@@ -49,9 +49,16 @@ def test_heap_container_equals_register_list(oracle, k):
         hi, hd = run("grid", k, coord, offset)
         _lib.set_tuning("knn_topk", 2)
         li, ld = run("grid", k, coord, offset)
+        _lib.set_tuning("knn_pend", 1)               # per-lane pending list instead of inserting in place
+        pi, pd = run("grid", k, coord, offset)
+        _lib.set_tuning("knn_topk", 1)               # ... and both together
+        qi, qd = run("grid", k, coord, offset)
+        assert np.array_equal(qi, li) and np.array_equal(qd, ld)
     finally:
         _lib.set_tuning("knn_topk", 0)
+        _lib.set_tuning("knn_pend", 0)
     assert np.array_equal(hi, li) and np.array_equal(hd, ld)
+    assert np.array_equal(pi, li) and np.array_equal(pd, ld)
     ri, rd = oracle.knn_query(k, coord, offset, rule="lex")
     assert np.array_equal(hi, ri) and np.array_equal(hd, rd)
 

@@ -78,6 +78,10 @@ SIGNATURES = {
     "aopt_we_tail_supported": (c_int, [c_int]),
     "aopt_we_tail_forward": (c_int, [c_int64, c_int, P, P, P, P, P, c_float, P, P, P, P, P, P, c_float, P, P, c_size_t, P]),
     "aopt_we_tail_backward": (c_int, [c_int64, c_int, P, P, P, P, P, P, P, P, P, P, P, P, P, P, c_size_t, P]),
+    "aopt_col_sum": (c_int, [c_int64, c_int, P, c_int64, c_int, P, P, c_size_t, P]),
+    "aopt_copy_cols": (c_int, [c_int64, c_int, P, c_int64, c_int, P, P, c_int64, c_int, P]),
+    "aopt_skinny_wgrad_supported": (c_int, [c_int, c_int]),
+    "aopt_skinny_wgrad": (c_int, [c_int64, c_int, c_int, P, c_int, P, c_int64, c_int, P, P, c_size_t, P]),
     "aopt_aggregation_forward": (c_int, [c_int, c_int, c_int, c_int, P, P, P, P, P, P]),
     "aopt_aggregation_backward": (c_int, [c_int, c_int, c_int, c_int, P, P, P, P, P, P, P, P, P, P, P]),
     "aopt_subtraction_forward": (c_int, [c_int, c_int, c_int, P, P, P, P, P]),
@@ -92,7 +96,7 @@ _UNTRACED = {"aopt_set_tuning", "aopt_version", "aopt_status_string", "aopt_last
              "aopt_knn_workspace_bytes", "aopt_csr_workspace_bytes", "aopt_voxel_partition_workspace_bytes", "aopt_voxel_grid_workspace_bytes",
              "aopt_pe_mlp_supported", "aopt_pos_moments_workspace_bytes", "aopt_pe_mlp_state_bytes",
              "aopt_pe_mlp_backward_workspace_bytes", "aopt_dense_workspace_bytes", "aopt_bn_act_supported",
-             "aopt_we_tail_supported"}
+             "aopt_we_tail_supported", "aopt_skinny_wgrad_supported"}
 
 
 class _Entry:

@@ -104,7 +104,8 @@ __device__ __forceinline__ void block_reduce_store(float (&v)[NV], float *__rest
 // 3-CTA kernel the longest of the chain (15 us per call, 220 calls per training step: profiles/r02p).
 constexpr int kReduceSlices = 32;
 __global__ void __launch_bounds__(32 * kReduceSlices)
-partials_reduce_kernel(int parts, int width, const float *__restrict__ partials, double *__restrict__ out) {
+partials_reduce_kernel(int parts, int width, int stride, const float *__restrict__ partials, double *__restrict__ out,
+                       float *__restrict__ out_f32) {
     __shared__ double sh[kReduceSlices][33];
     pdl_wait();
     pdl_trigger();
@@ -114,15 +115,15 @@ partials_reduce_kernel(int parts, int width, const float *__restrict__ partials,
     if (v < width) {
         int p = slice;
         for (; p + 3 * kReduceSlices < parts; p += 4 * kReduceSlices) {
-            const float a = partials[(size_t)p * width + v], b = partials[(size_t)(p + kReduceSlices) * width + v];
-            const float c = partials[(size_t)(p + 2 * kReduceSlices) * width + v];
-            const float d = partials[(size_t)(p + 3 * kReduceSlices) * width + v];
+            const float a = partials[(size_t)p * stride + v], b = partials[(size_t)(p + kReduceSlices) * stride + v];
+            const float c = partials[(size_t)(p + 2 * kReduceSlices) * stride + v];
+            const float d = partials[(size_t)(p + 3 * kReduceSlices) * stride + v];
             s += (double)a;
             s += (double)b;
             s += (double)c;
             s += (double)d;
         }
-        for (; p < parts; p += kReduceSlices) s += (double)partials[(size_t)p * width + v];
+        for (; p < parts; p += kReduceSlices) s += (double)partials[(size_t)p * stride + v];
     }
     sh[slice][lane] = s;
     __syncthreads();
@@ -130,7 +131,8 @@ partials_reduce_kernel(int parts, int width, const float *__restrict__ partials,
         double t = sh[0][lane];
 #pragma unroll
         for (int u = 1; u < kReduceSlices; ++u) t += sh[u][lane];
-        out[v] = t;
+        if (out) out[v] = t;
+        if (out_f32) out_f32[v] = (float)t;
     }
 }
 
@@ -561,6 +563,90 @@ we_bwd_apply_kernel(long long rows, const float *__restrict__ rel, const float *
     }
 }
 
+// ---- small dense helpers of the Linear layers' backward passes ----------------------------------------------------------
+// dst[r, j] = src[r, j] (+ bias[j]) for a c-wide column block of two row-major matrices with their own row strides and
+// element types: the v block of the fused q|k|v product -> dense fp32 (+ linear_v.bias), and its gradient back into the
+// (N, 3C) gradient buffer (one kernel instead of a strided cast + an add).
+template <typename ST, typename DT>
+__global__ void __launch_bounds__(kDenseBlock)
+copy_cols_kernel(long long rows, int c, const ST *__restrict__ src, long long ld_src, const float *__restrict__ bias,
+                 DT *__restrict__ dst, long long ld_dst) {
+    const int cols = c >> 2;
+    const ColWalk w = col_walk(cols, kDenseBlock);
+    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (bias) b = *reinterpret_cast<const float4 *>(bias + 4 * w.col);
+    const ST *ps = src + 4 * w.col;
+    DT *pd = dst + 4 * w.col;
+    for (long long row = w.row; row < rows; row += w.row_step) {
+        float4 v = ld4(ps + row * ld_src);
+        v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+        st4(pd + row * ld_dst, v);
+    }
+}
+
+// Weight gradient of a Linear with a handful of outputs: out[i, :] = Σ_r g[r, i] · x[r, :], g (rows, G), x (rows, c).
+// cuBLAS runs this (G, rows) x (rows, c) product — rows = 320 000, G = 6 — at 170 us (profiles/r02r: a single column of
+// CTAs walks the whole K dimension); here a thread keeps a 4-channel column chunk of x, walks the rows and accumulates
+// its G x 4 block; per-CTA partials are summed in a fixed order (partials_reduce_kernel).
+template <typename GT, typename XT, int G>
+__global__ void __launch_bounds__(kDenseBlock)
+skinny_wgrad_kernel(long long rows, int c, const GT *__restrict__ g, const XT *__restrict__ x, long long ldx,
+                    float *__restrict__ partials) {
+    const int cols = c >> 2;
+    const ColWalk w = col_walk(cols, kDenseBlock);
+    pdl_trigger();
+    float4 acc[G];
+#pragma unroll
+    for (int i = 0; i < G; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const XT *px = x + 4 * w.col;
+    for (long long row = w.row; row < rows; row += w.row_step) {
+        const float4 v = ld4(px + row * ldx);
+        float gr[G];
+        if constexpr (sizeof(GT) == 4) {
+            const float2 *gp = reinterpret_cast<const float2 *>(g + row * G);
+#pragma unroll
+            for (int i = 0; i < G / 2; ++i) {
+                const float2 t = __ldg(gp + i);
+                gr[2 * i] = t.x;
+                gr[2 * i + 1] = t.y;
+            }
+        } else {
+            const __nv_bfloat162 *gp = reinterpret_cast<const __nv_bfloat162 *>(g + row * G);
+#pragma unroll
+            for (int i = 0; i < G / 2; ++i) {
+                const float2 t = __bfloat1622float2(gp[i]);
+                gr[2 * i] = t.x;
+                gr[2 * i + 1] = t.y;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < G; ++i) {
+            acc[i].x = fmaf(gr[i], v.x, acc[i].x);
+            acc[i].y = fmaf(gr[i], v.y, acc[i].y);
+            acc[i].z = fmaf(gr[i], v.z, acc[i].z);
+            acc[i].w = fmaf(gr[i], v.w, acc[i].w);
+        }
+    }
+    // threads of the CTA with the same column chunk, in thread order (as column_reduce_store, G rows at a time)
+    __shared__ float4 sh[kDenseBlock];
+    float *prow = partials + (size_t)blockIdx.x * G * c;
+    const int t = threadIdx.x;
+#pragma unroll
+    for (int i = 0; i < G; ++i) {
+        __syncthreads();
+        sh[t] = acc[i];
+        __syncthreads();
+        if (t < cols) {
+            float4 A = sh[t];
+            for (int u = t + cols; u < kDenseBlock; u += cols) {
+                const float4 y = sh[u];
+                A.x += y.x; A.y += y.y; A.z += y.z; A.w += y.w;
+            }
+            *reinterpret_cast<float4 *>(prow + (size_t)i * c + 4 * w.col) = A;
+        }
+    }
+}
+
 // ---- host side ----------------------------------------------------------------------------------------------------
 static size_t a256(size_t x) { return (x + 255) & ~(size_t)255; }
 
@@ -576,7 +662,8 @@ static int bn_forward_t(long long rows, int c, const void *x, long long ldx, con
     const int grid = bn_grid(rows, c);
     const bool pdl = tuning(kTunePdl) != 2;
     bn_partial_kernel<XT><<<grid, kDenseBlock, 0, st>>>(rows, c, static_cast<const XT *>(x), ldx, partials);
-    launch_chain(pdl, partials_reduce_kernel, div_up(2 * c, 32), 32 * kReduceSlices, 0, st, grid, 2 * c, (const float *)partials, sums);
+    launch_chain(pdl, partials_reduce_kernel, div_up(2 * c, 32), 32 * kReduceSlices, 0, st, grid, 2 * c, 2 * c, (const float *)partials, sums,
+                 (float *)nullptr);
     const float unbias = rows > 1 ? (float)((double)rows / (double)(rows - 1)) : 1.f;
     launch_chain(pdl, bn_apply_kernel<XT, OT>, grid, kDenseBlock, 0, st, rows, c, static_cast<const XT *>(x), ldx,
                  (const double *)sums, 1.0 / (double)rows, eps, gamma, beta, static_cast<const OT *>(residual), row_scale,
@@ -594,7 +681,8 @@ static int bn_backward_t(long long rows, int c, const void *grad_out, const void
     bn_bwd_partial_kernel<XT, OT><<<grid, kDenseBlock, 0, st>>>(rows, c, static_cast<const OT *>(grad_out),
                                                                 static_cast<const OT *>(out), static_cast<const XT *>(x),
                                                                 ldx, stats, row_scale, partials);
-    launch_chain(pdl, partials_reduce_kernel, div_up(2 * c, 32), 32 * kReduceSlices, 0, st, grid, 2 * c, (const float *)partials, sums);
+    launch_chain(pdl, partials_reduce_kernel, div_up(2 * c, 32), 32 * kReduceSlices, 0, st, grid, 2 * c, 2 * c, (const float *)partials, sums,
+                 (float *)nullptr);
     launch_chain(pdl, bn_bwd_apply_kernel<XT, OT>, grid, kDenseBlock, 0, st, rows, c, static_cast<const OT *>(grad_out),
                  static_cast<const OT *>(out), static_cast<const XT *>(x), ldx, stats, gamma, row_scale, (const double *)sums,
                  1.0 / (double)rows, static_cast<XT *>(grad_x), ldgx, static_cast<OT *>(grad_residual), grad_gamma, grad_beta);
@@ -609,7 +697,8 @@ static int we_forward_t(long long rows, const float *rel, const float *upe, cons
     const int grid = row_grid(rows);
     const bool pdl = tuning(kTunePdl) != 2;
     we_partial_kernel<G><<<grid, kDenseBlock, 0, st>>>(rows, rel, upe, cst, partials);
-    launch_chain(pdl, partials_reduce_kernel, div_up(2 * G, 32), 32 * kReduceSlices, 0, st, grid, 2 * G, (const float *)partials, sums);
+    launch_chain(pdl, partials_reduce_kernel, div_up(2 * G, 32), 32 * kReduceSlices, 0, st, grid, 2 * G, 2 * G, (const float *)partials, sums,
+                 (float *)nullptr);
     const float unbias = rows > 1 ? (float)((double)rows / (double)(rows - 1)) : 1.f;
     launch_chain(pdl, we_apply_kernel<G>, grid, kDenseBlock, 0, st, rows, rel, upe, cst, (const double *)sums,
                  1.0 / (double)rows, eps, gamma, beta, w2, b2, logits, stats_out, running_mean, running_var, momentum, unbias,
@@ -627,7 +716,8 @@ static int we_backward_t(long long rows, const float *rel, const float *upe, con
     const int width = 3 * G + G * G;
     we_bwd_partial_kernel<G, IB><<<dim3(grid, G / IB), kDenseBlock, 0, st>>>(rows, rel, upe, cst, grad_logits, stats, gamma,
                                                                              beta, w2, partials);
-    launch_chain(pdl, partials_reduce_kernel, div_up(width, 32), 32 * kReduceSlices, 0, st, grid, width, (const float *)partials, sums);
+    launch_chain(pdl, partials_reduce_kernel, div_up(width, 32), 32 * kReduceSlices, 0, st, grid, width, width, (const float *)partials, sums,
+                 (float *)nullptr);
     launch_chain(pdl, we_bwd_apply_kernel<G>, grid, kDenseBlock, 0, st, rows, rel, upe, cst, grad_logits, stats, gamma, beta,
                  w2, (const double *)sums, 1.0 / (double)rows, grad_u, grad_gamma, grad_beta, grad_b2, grad_w2);
     return check_launch(3);
@@ -732,4 +822,72 @@ extern "C" int aopt_we_tail_backward(int64_t rows, int g, const float *rel, cons
                                    grad_b2, grad_w2, partials, sums, st);
     return we_backward_t<12, 4>(rows, rel, upe, cst, grad_logits, stats, gamma, beta, w2, grad_u, grad_gamma, grad_beta,
                                 grad_b2, grad_w2, partials, sums, st);
+}
+
+// out (c floats) = column sums of x (rows, c) [row stride ldx]: the bias gradient of a Linear layer.
+extern "C" int aopt_col_sum(int64_t rows, int c, const void *x, int64_t ldx, int x_dtype, float *out, void *workspace,
+                            size_t workspace_bytes, aopt_stream_t stream) {
+    if (rows <= 0 || !bn_width_ok(c) || !x || !out || (x_dtype & ~1) || ldx < c || (ldx & 3)) return AOPT_ERR_INVALID_ARGUMENT;
+    float *partials;
+    double *sums;
+    if (!carve_dense(workspace, workspace_bytes, 2 * c, &partials, &sums)) return AOPT_ERR_WORKSPACE;
+    cudaStream_t st = as_stream(stream);
+    const int grid = bn_grid(rows, c);
+    const bool pdl = tuning(kTunePdl) != 2;
+    if (x_dtype == AOPT_F32) bn_partial_kernel<float><<<grid, kDenseBlock, 0, st>>>(rows, c, static_cast<const float *>(x), ldx, partials);
+    else bn_partial_kernel<__nv_bfloat16><<<grid, kDenseBlock, 0, st>>>(rows, c, static_cast<const __nv_bfloat16 *>(x), ldx, partials);
+    launch_chain(pdl, partials_reduce_kernel, div_up(c, 32), 32 * kReduceSlices, 0, st, grid, c, 2 * c, (const float *)partials,
+                 (double *)nullptr, out);
+    return check_launch(2);
+}
+
+extern "C" int aopt_copy_cols(int64_t rows, int c, const void *src, int64_t ld_src, int src_dtype, const float *bias, void *dst,
+                              int64_t ld_dst, int dst_dtype, aopt_stream_t stream) {
+    if (rows <= 0 || !bn_width_ok(c) || !src || !dst || ((src_dtype | dst_dtype) & ~1) || ld_src < c || (ld_src & 3) ||
+        ld_dst < c || (ld_dst & 3))
+        return AOPT_ERR_INVALID_ARGUMENT;
+    cudaStream_t st = as_stream(stream);
+    const int grid = bn_grid(rows, c);
+#define AOPT_COPY(ST, DT)                                                                                          \
+    copy_cols_kernel<ST, DT><<<grid, kDenseBlock, 0, st>>>(rows, c, static_cast<const ST *>(src), ld_src, bias,  \
+                                                           static_cast<DT *>(dst), ld_dst)
+    if (src_dtype == AOPT_F32 && dst_dtype == AOPT_F32) AOPT_COPY(float, float);
+    else if (src_dtype == AOPT_F32) AOPT_COPY(float, __nv_bfloat16);
+    else if (dst_dtype == AOPT_F32) AOPT_COPY(__nv_bfloat16, float);
+    else AOPT_COPY(__nv_bfloat16, __nv_bfloat16);
+#undef AOPT_COPY
+    return check_launch(1);
+}
+
+extern "C" int aopt_skinny_wgrad_supported(int g, int c) { return ((g == 6 || g == 12) && bn_width_ok(c)) ? 1 : 0; }
+
+// out (g, c) fp32 = gradᵀ · x;  grad (rows, g) dense, x (rows, c) with row stride ldx.  workspace: aopt_dense_workspace_bytes(g * c).
+extern "C" int aopt_skinny_wgrad(int64_t rows, int g, int c, const void *grad, int grad_dtype, const void *x, int64_t ldx,
+                                 int x_dtype, float *out, void *workspace, size_t workspace_bytes, aopt_stream_t stream) {
+    if (rows <= 0 || !grad || !x || !out || ((grad_dtype | x_dtype) & ~1) || ldx < c || (ldx & 3)) return AOPT_ERR_INVALID_ARGUMENT;
+    if (!aopt_skinny_wgrad_supported(g, c)) return AOPT_ERR_UNSUPPORTED;
+    float *partials;
+    double *sums;
+    if (!carve_dense(workspace, workspace_bytes, g * c, &partials, &sums)) return AOPT_ERR_WORKSPACE;
+    cudaStream_t st = as_stream(stream);
+    const int grid = bn_grid(rows, c);
+    const bool pdl = tuning(kTunePdl) != 2;
+#define AOPT_SW(GT, XT, GG)                                                                                         \
+    skinny_wgrad_kernel<GT, XT, GG><<<grid, kDenseBlock, 0, st>>>(rows, c, static_cast<const GT *>(grad),        \
+                                                                  static_cast<const XT *>(x), ldx, partials)
+    if (g == 6) {
+        if (grad_dtype == AOPT_F32 && x_dtype == AOPT_F32) AOPT_SW(float, float, 6);
+        else if (grad_dtype == AOPT_F32) AOPT_SW(float, __nv_bfloat16, 6);
+        else if (x_dtype == AOPT_F32) AOPT_SW(__nv_bfloat16, float, 6);
+        else AOPT_SW(__nv_bfloat16, __nv_bfloat16, 6);
+    } else {
+        if (grad_dtype == AOPT_F32 && x_dtype == AOPT_F32) AOPT_SW(float, float, 12);
+        else if (grad_dtype == AOPT_F32) AOPT_SW(float, __nv_bfloat16, 12);
+        else if (x_dtype == AOPT_F32) AOPT_SW(__nv_bfloat16, float, 12);
+        else AOPT_SW(__nv_bfloat16, __nv_bfloat16, 12);
+    }
+#undef AOPT_SW
+    launch_chain(pdl, partials_reduce_kernel, div_up(g * c, 32), 32 * kReduceSlices, 0, st, grid, g * c, g * c,
+                 (const float *)partials, (double *)nullptr, out);
+    return check_launch(2);
 }

@@ -293,6 +293,43 @@ def _mm_f32(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     return torch.mm(a, b, out_dtype=torch.float32) if _MM_OUT_DTYPE else torch.mm(a, b).float()
 
 
+def col_sum(x: torch.Tensor) -> torch.Tensor:
+    """fp32 column sums of a dense (rows, c) fp32 / bf16 matrix (a bias gradient); c % 4 == 0, c <= 1024."""
+    rows, c = x.shape
+    out = torch.empty(c, dtype=torch.float32, device=x.device)
+    ws = _dense_ws(2 * c, x.device)
+    _lib.check(_lib.load().aopt_col_sum(rows, c, x.data_ptr(), c, _DT[x.dtype], out.data_ptr(), ws.data_ptr(), ws.numel(),
+                                        _lib.stream()), "col_sum")
+    return out
+
+
+def _bias_grad(g2: torch.Tensor) -> torch.Tensor:
+    c = g2.shape[1]
+    if g2.dtype in _DT and g2.is_contiguous() and g2.shape[0] >= 1024 and _WIDTH_OK.get(c, bn_act_supported(c)):
+        return col_sum(g2)
+    return g2.sum(0, dtype=torch.float32)
+
+
+_SKINNY_OK = {}
+
+
+def _weight_grad(g2: torch.Tensor, xb: torch.Tensor) -> torch.Tensor:
+    """g2ᵀ @ xb in fp32.  A Linear with 6 / 12 outputs over >= 16k rows goes through aopt_skinny_wgrad."""
+    rows, g = g2.shape
+    c = xb.shape[1]
+    if g <= 16 and rows >= 16384 and g2.dtype in _DT and xb.dtype in _DT and g2.is_contiguous() and xb.is_contiguous():
+        ok = _SKINNY_OK.get((g, c))
+        if ok is None:
+            ok = _SKINNY_OK[(g, c)] = bool(_lib.load().aopt_skinny_wgrad_supported(g, c))
+        if ok:
+            out = torch.empty((g, c), dtype=torch.float32, device=xb.device)
+            ws = _dense_ws(g * c, xb.device)
+            _lib.check(_lib.load().aopt_skinny_wgrad(rows, g, c, g2.data_ptr(), _DT[g2.dtype], xb.data_ptr(), c, _DT[xb.dtype],
+                                                     out.data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream()), "skinny_wgrad")
+            return out
+    return _mm_f32(g2.t(), xb) if xb.dtype != torch.float32 else torch.mm(g2.float().t(), xb)
+
+
 class _LinearFn(Function):
     @staticmethod
     def forward(ctx, x, w, b, dt, out_f32):
@@ -323,9 +360,9 @@ class _LinearFn(Function):
             if gx.dtype != ctx.x_dtype:
                 gx = gx.to(ctx.x_dtype)
         if ctx.needs_input_grad[1]:
-            gw = _mm_f32(g2.t(), xb)
+            gw = _weight_grad(g2, xb)
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            gb = g2.sum(0, dtype=torch.float32)
+            gb = _bias_grad(g2)
         return gx, gw, gb, None, None
 
 
@@ -381,9 +418,9 @@ class _QkvFn(Function):
                                             _lib.ptr(rm), _lib.ptr(rv), mom, _lib.ptr(bias), _lib.ptr(tr), ws.data_ptr(),
                                             ws.numel(), _lib.stream()),
                     "bn_act_forward")
-        v = y[:, 2 * c:].to(torch.float32, copy=True)                        # dense fp32 copy of the column block
-        if bv is not None:
-            v.add_(bv)
+        v = torch.empty((rows, c), dtype=torch.float32, device=dev)          # dense fp32 copy of the v block (+ bias)
+        _lib.check(lib.aopt_copy_cols(rows, c, y.data_ptr() + 2 * c * esz, 3 * c, _DT[dt], _lib.ptr(bv), v.data_ptr(), c, 0,
+                                      _lib.stream()), "copy_cols")
         ctx.save_for_backward(xb, wcat, y, q, k, gq, gk, stats)
         ctx.x_dtype = x.dtype
         ctx.biases = (bq, bk, bv)
@@ -418,7 +455,10 @@ class _QkvFn(Function):
         if gv is None:
             gy[:, 2 * c:].zero_()
         else:
-            gy[:, 2 * c:].copy_(gv)
+            if gv.dtype != torch.float32 or not gv.is_contiguous():
+                gv = gv.float().contiguous()
+            _lib.check(lib.aopt_copy_cols(rows, c, gv.data_ptr(), c, 0, 0, gy.data_ptr() + 2 * c * esz, 3 * c, _DT[dt],
+                                          _lib.stream()), "copy_cols")
         gx = None
         if ctx.needs_input_grad[0]:
             gx = torch.mm(gy, wcat)
@@ -428,7 +468,7 @@ class _QkvFn(Function):
         bq, bk, bv = ctx.biases
         zq = torch.zeros_like(bq) if bq is not None else None          # in front of a training-mode BatchNorm
         zk = torch.zeros_like(bk) if bk is not None else None
-        gbv = gv.sum(0, dtype=torch.float32) if (bv is not None and gv is not None) else (None if bv is None else torch.zeros_like(bv))
+        gbv = _bias_grad(gv) if (bv is not None and gv is not None) else (None if bv is None else torch.zeros_like(bv))
         return (gx, gw[:c], zq, gw[c:2 * c], zk, gw[2 * c:], gbv, ggq, gbq, ggk, gbk) + (None,) * 12
 
 

@@ -737,8 +737,9 @@ def model_step(ctx, name, coord, feat, offset, bucket_cap_mb, steps=10):
     ctx.barrier()
     clocks = sampler.stop() if sampler else None
     ms = ctx.max_over_ranks(e0.elapsed_time(e1)) / steps
-    out = {"what": f"full PTv2m2 ({CONFIGS[name]['model']}) training step: bf16 autocast GEMMs (cuBLAS) + these point ops + "
-                   "cross-entropy + AdamW" + (f"; DistributedDataParallel over {ctx.world} ranks (broadcast_buffers=False, "
+    out = {"what": f"full PTv2m2 ({CONFIGS[name]['model']}) training step: bf16 GEMMs (cuBLAS; q|k|v as one product, cached bf16 "
+                   "weights) + the library's point operators, BatchNorm / ReLU / DropPath / residual kernels (bn_act) and "
+                   "weight-encoding tail (we_tail) + cross-entropy + AdamW (fused=True)" + (f"; DistributedDataParallel over {ctx.world} ranks (broadcast_buffers=False, "
                    f"bucket_cap_mb={bucket_cap_mb}, gradient_as_bucket_view), NCCL all-reduce overlapped with backward"
                    if ctx.world > 1 else ""),
            "ms_per_step": ms, "mpoints_per_s": ctx.world * coord.shape[0] / (ms * 1e-3) / 1e6, "loss": float(loss.item()),

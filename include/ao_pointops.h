@@ -317,6 +317,21 @@ int aopt_we_tail_backward(int64_t rows, int g, const float *rel, const float *up
                           const float *w2, float *grad_u, float *grad_gamma, float *grad_beta, float *grad_b2,
                           float *grad_w2, void *workspace, size_t workspace_bytes, aopt_stream_t stream);
 
+/* Small dense helpers of the Linear layers around the operators above (backward passes).
+ * aopt_col_sum: out (c floats) = column sums of x (rows, c), row stride ldx — a bias gradient; workspace
+ *   aopt_dense_workspace_bytes(2*c).
+ * aopt_copy_cols: dst[r, :] = src[r, :] (+ bias) for a c-wide column block, each side with its own row stride and element
+ *   type (the v block of a fused q|k|v product <-> a dense fp32 tensor).
+ * aopt_skinny_wgrad: out (g, c) fp32 = gradᵀ x, grad (rows, g) dense, x (rows, c) — the weight gradient of a Linear with
+ *   g in {6, 12} outputs over hundreds of thousands of rows; workspace aopt_dense_workspace_bytes(g*c).  Deterministic. */
+int aopt_col_sum(int64_t rows, int c, const void *x, int64_t ldx, int x_dtype, float *out, void *workspace,
+                 size_t workspace_bytes, aopt_stream_t stream);
+int aopt_copy_cols(int64_t rows, int c, const void *src, int64_t ld_src, int src_dtype, const float *bias, void *dst,
+                   int64_t ld_dst, int dst_dtype, aopt_stream_t stream);
+int aopt_skinny_wgrad_supported(int g, int c);
+int aopt_skinny_wgrad(int64_t rows, int g, int c, const void *grad, int grad_dtype, const void *x, int64_t ldx, int x_dtype,
+                      float *out, void *workspace, size_t workspace_bytes, aopt_stream_t stream);
+
 /* ---- PTv1-layout fused ops kept for API parity --------------------------------------------- */
 /* output[n,ch] = sum_s (input[idx[n,s],ch] + position[n,s,ch]) * weight[n,s,ch % w_c]. */
 int aopt_aggregation_forward(int n, int nsample, int c, int w_c, const float *input,

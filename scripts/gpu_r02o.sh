@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, call O: bn_act with the folded Linear bias, fused AdamW: parity tests, model-step A/B, torch profile (GPU + CPU tables)
-TAG=${1:-r02r}
+TAG=${1:-r02u}
 O=gpurun_out/$TAG
 mkdir -p $O
 timeout 900 python -m pytest tests/test_dense_gpu.py -q -x --timeout 600 -p no:cacheprovider > $O/pytest_dense.log 2>&1; echo "dense exit: $?"; tail -15 $O/pytest_dense.log

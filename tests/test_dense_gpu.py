@@ -276,3 +276,35 @@ def test_qkv_one_gemm_equals_three_layers(autocast):
     torch.testing.assert_close(gva.linear_v.weight.grad, ref.linear_v.weight.grad, rtol=5e-2 if autocast else 1e-3,
                                atol=(5e-2 if autocast else 1e-3) * float(ref.linear_v.weight.grad.abs().max()))
     torch.testing.assert_close(gva.linear_v.bias.grad, ref.linear_v.bias.grad, rtol=2e-2, atol=2e-2 * float(ref.linear_v.bias.grad.abs().max()))
+
+
+@pytest.mark.parametrize("g,c,rows", [(6, 48, 320000), (12, 96, 50139), (6, 96, 20000)])
+@pytest.mark.parametrize("gdt,xdt", [(torch.float32, torch.bfloat16), (torch.bfloat16, torch.bfloat16), (torch.float32, torch.float32)])
+def test_skinny_wgrad_col_sum_copy_cols(g, c, rows, gdt, xdt):
+    """The three small helpers of the Linear backward passes against torch in fp64 / exact copies."""
+    from ao_b200 import _lib
+    from ao_b200.pointops import dense
+
+    torch.manual_seed(g * c)
+    grad = torch.randn(rows, g, device=DEV).to(gdt)
+    x = (torch.randn(rows, c, device=DEV) + 0.5).to(xdt)
+    got = dense._weight_grad(grad, x)
+    want = (grad.double().t() @ x.double()).float()
+    torch.testing.assert_close(got, want, rtol=1e-4, atol=1e-4 * float(want.abs().max()))
+    assert torch.equal(got, dense._weight_grad(grad, x))                       # fixed summation order
+    s = dense.col_sum(x)
+    torch.testing.assert_close(s, x.double().sum(0).float(), rtol=1e-4, atol=1e-4 * float(x.double().sum(0).abs().max()))
+    # column block of a (rows, 3c) matrix -> dense fp32 (+ bias) and back
+    wide = torch.randn(rows, 3 * c, device=DEV).to(xdt)
+    bias = torch.randn(c, device=DEV)
+    dst = torch.empty(rows, c, device=DEV)
+    lib = _lib.load()
+    dt = {torch.float32: 0, torch.bfloat16: 1}
+    _lib.check(lib.aopt_copy_cols(rows, c, wide.data_ptr() + 2 * c * wide.element_size(), 3 * c, dt[xdt], bias.data_ptr(),
+                                  dst.data_ptr(), c, 0, _lib.stream()), "copy_cols")
+    torch.testing.assert_close(dst, wide[:, 2 * c:].float() + bias, rtol=0, atol=0)
+    back = torch.zeros_like(wide)
+    _lib.check(lib.aopt_copy_cols(rows, c, dst.data_ptr(), c, 0, 0, back.data_ptr() + 2 * c * back.element_size(), 3 * c, dt[xdt],
+                                  _lib.stream()), "copy_cols")
+    torch.testing.assert_close(back[:, 2 * c:], dst.to(xdt), rtol=0, atol=0)
+    assert float(back[:, :2 * c].abs().max()) == 0.0

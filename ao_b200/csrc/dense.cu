@@ -647,6 +647,66 @@ skinny_wgrad_kernel(long long rows, int c, const GT *__restrict__ g, const XT *_
     }
 }
 
+// Linear with a handful of outputs, forward and input gradient (the key / query projections by weight_encoding[0] in the
+// relation-free schedule: (320 000, 48) x (48, 6)).  cuBLAS serves both shapes — N = 6 and K = 6 — with a 32x32 WMMA
+// kernel at ~170 us; they are 40 MB of traffic.
+//   out[r, i] = Σ_j x[r, j] · w[i, j]         thread = row, the G x c weights in shared memory (broadcast reads)
+//   gx[r, j]  = Σ_i g[r, i] · w[i, j]         thread = (row, 4-channel chunk), its G x 4 weights in registers
+template <typename XT, int G>
+__global__ void __launch_bounds__(kDenseBlock)
+skinny_linear_kernel(long long rows, int c, const XT *__restrict__ x, long long ldx, const float *__restrict__ w,
+                     float *__restrict__ out) {
+    extern __shared__ float4 s_w[];   // [c / 4][G] : chunk-major so that a thread walks it linearly
+    const int cols = c >> 2;
+    for (int t = threadIdx.x; t < cols * G; t += kDenseBlock) {
+        const int i = t % G, ch = t / G;
+        s_w[t] = *reinterpret_cast<const float4 *>(w + (size_t)i * c + 4 * ch);
+    }
+    __syncthreads();
+    for (long long row = (long long)blockIdx.x * kDenseBlock + threadIdx.x; row < rows; row += (long long)gridDim.x * kDenseBlock) {
+        float acc[G];
+#pragma unroll
+        for (int i = 0; i < G; ++i) acc[i] = 0.f;
+        const XT *px = x + row * ldx;
+        for (int ch = 0; ch < cols; ++ch) {
+            const float4 v = ld4(px + 4 * ch);
+#pragma unroll
+            for (int i = 0; i < G; ++i) {
+                const float4 ww = s_w[ch * G + i];
+                acc[i] = fmaf(v.x, ww.x, fmaf(v.y, ww.y, fmaf(v.z, ww.z, fmaf(v.w, ww.w, acc[i]))));
+            }
+        }
+        float2 *o = reinterpret_cast<float2 *>(out + row * G);
+#pragma unroll
+        for (int i = 0; i < G; i += 2) o[i / 2] = make_float2(acc[i], acc[i + 1]);
+    }
+}
+
+template <typename XT, int G>
+__global__ void __launch_bounds__(kDenseBlock)
+skinny_dgrad_kernel(long long rows, int c, const float *__restrict__ g, const float *__restrict__ w,
+                    XT *__restrict__ gx, long long ldgx) {
+    const int cols = c >> 2;
+    const ColWalk cw = col_walk(cols, kDenseBlock);
+    float4 ww[G];
+#pragma unroll
+    for (int i = 0; i < G; ++i) ww[i] = *reinterpret_cast<const float4 *>(w + (size_t)i * c + 4 * cw.col);
+    XT *po = gx + 4 * cw.col;
+    for (long long row = cw.row; row < rows; row += cw.row_step) {
+        const float2 *gp = reinterpret_cast<const float2 *>(g + row * G);
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < G / 2; ++i) {
+            const float2 t = __ldg(gp + i);
+            a.x = fmaf(t.x, ww[2 * i].x, a.x); a.y = fmaf(t.x, ww[2 * i].y, a.y);
+            a.z = fmaf(t.x, ww[2 * i].z, a.z); a.w = fmaf(t.x, ww[2 * i].w, a.w);
+            a.x = fmaf(t.y, ww[2 * i + 1].x, a.x); a.y = fmaf(t.y, ww[2 * i + 1].y, a.y);
+            a.z = fmaf(t.y, ww[2 * i + 1].z, a.z); a.w = fmaf(t.y, ww[2 * i + 1].w, a.w);
+        }
+        st4(po + row * ldgx, a);
+    }
+}
+
 // ---- host side ----------------------------------------------------------------------------------------------------
 static size_t a256(size_t x) { return (x + 255) & ~(size_t)255; }
 
@@ -890,4 +950,39 @@ extern "C" int aopt_skinny_wgrad(int64_t rows, int g, int c, const void *grad, i
     launch_chain(pdl, partials_reduce_kernel, div_up(g * c, 32), 32 * kReduceSlices, 0, st, grid, g * c, g * c,
                  (const float *)partials, (double *)nullptr, out);
     return check_launch(2);
+}
+
+// out (rows, g) fp32 = x (rows, c) · wᵀ, w (g, c) fp32; g in {6, 12} (aopt_skinny_wgrad_supported).
+extern "C" int aopt_skinny_linear(int64_t rows, int g, int c, const void *x, int64_t ldx, int x_dtype, const float *w,
+                                  float *out, aopt_stream_t stream) {
+    if (rows <= 0 || !x || !w || !out || (x_dtype & ~1) || ldx < c || (ldx & 3)) return AOPT_ERR_INVALID_ARGUMENT;
+    if (!aopt_skinny_wgrad_supported(g, c)) return AOPT_ERR_UNSUPPORTED;
+    cudaStream_t st = as_stream(stream);
+    const int grid = row_grid(rows);
+    const size_t smem = (size_t)g * c * sizeof(float);
+    if (g == 6) {
+        if (x_dtype == AOPT_F32) skinny_linear_kernel<float, 6><<<grid, kDenseBlock, smem, st>>>(rows, c, static_cast<const float *>(x), ldx, w, out);
+        else skinny_linear_kernel<__nv_bfloat16, 6><<<grid, kDenseBlock, smem, st>>>(rows, c, static_cast<const __nv_bfloat16 *>(x), ldx, w, out);
+    } else {
+        if (x_dtype == AOPT_F32) skinny_linear_kernel<float, 12><<<grid, kDenseBlock, smem, st>>>(rows, c, static_cast<const float *>(x), ldx, w, out);
+        else skinny_linear_kernel<__nv_bfloat16, 12><<<grid, kDenseBlock, smem, st>>>(rows, c, static_cast<const __nv_bfloat16 *>(x), ldx, w, out);
+    }
+    return check_launch(1);
+}
+
+// grad_x (rows, c) [row stride ldgx, fp32 or bf16] = grad (rows, g) fp32 · w (g, c).
+extern "C" int aopt_skinny_dgrad(int64_t rows, int g, int c, const float *grad, const float *w, void *grad_x, int64_t ldgx,
+                                 int x_dtype, aopt_stream_t stream) {
+    if (rows <= 0 || !grad || !w || !grad_x || (x_dtype & ~1) || ldgx < c || (ldgx & 3)) return AOPT_ERR_INVALID_ARGUMENT;
+    if (!aopt_skinny_wgrad_supported(g, c)) return AOPT_ERR_UNSUPPORTED;
+    cudaStream_t st = as_stream(stream);
+    const int grid = bn_grid(rows, c);
+    if (g == 6) {
+        if (x_dtype == AOPT_F32) skinny_dgrad_kernel<float, 6><<<grid, kDenseBlock, 0, st>>>(rows, c, grad, w, static_cast<float *>(grad_x), ldgx);
+        else skinny_dgrad_kernel<__nv_bfloat16, 6><<<grid, kDenseBlock, 0, st>>>(rows, c, grad, w, static_cast<__nv_bfloat16 *>(grad_x), ldgx);
+    } else {
+        if (x_dtype == AOPT_F32) skinny_dgrad_kernel<float, 12><<<grid, kDenseBlock, 0, st>>>(rows, c, grad, w, static_cast<float *>(grad_x), ldgx);
+        else skinny_dgrad_kernel<__nv_bfloat16, 12><<<grid, kDenseBlock, 0, st>>>(rows, c, grad, w, static_cast<__nv_bfloat16 *>(grad_x), ldgx);
+    }
+    return check_launch(1);
 }

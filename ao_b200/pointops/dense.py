@@ -318,16 +318,54 @@ def _weight_grad(g2: torch.Tensor, xb: torch.Tensor) -> torch.Tensor:
     rows, g = g2.shape
     c = xb.shape[1]
     if g <= 16 and rows >= 16384 and g2.dtype in _DT and xb.dtype in _DT and g2.is_contiguous() and xb.is_contiguous():
-        ok = _SKINNY_OK.get((g, c))
-        if ok is None:
-            ok = _SKINNY_OK[(g, c)] = bool(_lib.load().aopt_skinny_wgrad_supported(g, c))
-        if ok:
+        if _skinny_ok(g, c):
             out = torch.empty((g, c), dtype=torch.float32, device=xb.device)
             ws = _dense_ws(g * c, xb.device)
             _lib.check(_lib.load().aopt_skinny_wgrad(rows, g, c, g2.data_ptr(), _DT[g2.dtype], xb.data_ptr(), c, _DT[xb.dtype],
                                                      out.data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream()), "skinny_wgrad")
             return out
     return _mm_f32(g2.t(), xb) if xb.dtype != torch.float32 else torch.mm(g2.float().t(), xb)
+
+
+def _skinny_ok(g: int, c: int) -> bool:
+    ok = _SKINNY_OK.get((g, c))
+    if ok is None:
+        ok = _SKINNY_OK[(g, c)] = bool(_lib.load().aopt_skinny_wgrad_supported(g, c))
+    return ok
+
+
+class _SkinnyLinearFn(Function):
+    """x (rows, c) -> x wᵀ (rows, g) fp32, w (g, c) fp32 with g in {6, 12}: all three products in own kernels."""
+
+    @staticmethod
+    def forward(ctx, x, w):
+        rows, c = x.shape
+        g = w.shape[0]
+        out = torch.empty((rows, g), dtype=torch.float32, device=x.device)
+        _lib.check(_lib.load().aopt_skinny_linear(rows, g, c, x.data_ptr(), c, _DT[x.dtype], w.data_ptr(), out.data_ptr(),
+                                                  _lib.stream()), "skinny_linear")
+        ctx.save_for_backward(x, w)
+        return out
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w = ctx.saved_tensors
+        rows, c = x.shape
+        g = w.shape[0]
+        if gy.dtype != torch.float32 or not gy.is_contiguous():
+            gy = gy.float().contiguous()
+        gx = gw = None
+        lib = _lib.load()
+        if ctx.needs_input_grad[0]:
+            gx = torch.empty_like(x)
+            _lib.check(lib.aopt_skinny_dgrad(rows, g, c, gy.data_ptr(), w.data_ptr(), gx.data_ptr(), c, _DT[x.dtype],
+                                             _lib.stream()), "skinny_dgrad")
+        if ctx.needs_input_grad[1]:
+            gw = torch.empty((g, c), dtype=torch.float32, device=x.device)
+            ws = _dense_ws(g * c, x.device)
+            _lib.check(lib.aopt_skinny_wgrad(rows, g, c, gy.data_ptr(), 0, x.data_ptr(), c, _DT[x.dtype], gw.data_ptr(),
+                                             ws.data_ptr(), ws.numel(), _lib.stream()), "skinny_wgrad")
+        return gx, gw
 
 
 class _LinearFn(Function):
@@ -370,6 +408,10 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor = None, out
     """torch.nn.functional.linear; under CUDA autocast the low-precision copy of the fp32 parameters is cached across
     calls (see above).  Same arithmetic as the autocast Linear it replaces.  out_f32: return fp32 (under autocast the
     GEMM writes its fp32 accumulator instead of a rounded copy that the caller would cast back)."""
+    if (out_f32 and bias is None and x.is_cuda and x.dim() == 2 and weight.shape[0] <= 16 and x.shape[0] >= 16384
+            and fused_dense_enabled() and x.dtype in _DT and weight.dtype == torch.float32 and x.is_contiguous()
+            and weight.is_contiguous() and _skinny_ok(weight.shape[0], weight.shape[1])):
+        return _SkinnyLinearFn.apply(x, weight)          # a handful of outputs over many rows: own kernels, any mode
     if (x.is_cuda and torch.is_autocast_enabled() and fused_dense_enabled() and weight.dtype == torch.float32
             and x.dtype in (torch.float32, torch.bfloat16, torch.float16) and x.numel() > 0):
         return _LinearFn.apply(x, weight, bias, torch.get_autocast_dtype("cuda"), bool(out_f32))

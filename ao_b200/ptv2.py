@@ -50,6 +50,17 @@ def fused_pe_enabled() -> bool:
     return torch.is_autocast_enabled()
 
 
+def relation_free_all_widths() -> bool:
+    """AOPT_RELFREE_ALL=1 runs the relation-free schedule also at the widths the fused positional-MLP kernel does not
+    cover (C = 192, 384: hidden activation through cuBLAS + bn_act).  Off by default: measured on a B200
+    (profiles/r02v_model_step_relfree*.txt) the S3DIS-cfg training step takes 38.3 ms with it and 36.6 ms without — those
+    levels hold 12.5k / 2.9k points, their kernels are launch-bound and the step is host-bound, so trading one (N,k,C) pass
+    for two more operators per block loses."""
+    import os
+
+    return os.environ.get("AOPT_RELFREE_ALL", "0") == "1"
+
+
 class DropPath(nn.Module):
     """Stochastic depth per row (timm.models.layers.DropPath semantics for a (N,C) input)."""
 
@@ -86,11 +97,12 @@ def _autocast_dtype():
     return torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled() else None
 
 
-def run_seq(seq, x, out_dtype=None):
+def run_seq(seq, x, out_dtype=None, start=0, stop=None):
     """nn.Sequential forward with every [PointBatchNorm, ReLU] pair (or lone PointBatchNorm) routed through
     pointops.bn_act — the Linear -> PointBatchNorm -> ReLU triples of the reference (…v2m2_base.py:86-93,240-242,
-    288-295,363-364,566-571).  out_dtype: element type wanted from a trailing BatchNorm stage (saves a cast kernel)."""
-    mods = list(seq)
+    288-295,363-364,566-571).  out_dtype: element type wanted from a trailing BatchNorm stage (saves a cast kernel);
+    start / stop: run the sub-sequence seq[start:stop]."""
+    mods = list(seq)[start:stop]
     i = 0
     pre_bias = None
     while i < len(mods):
@@ -146,9 +158,11 @@ class GroupedVectorAttention(nn.Module):
         self.attn_drop = nn.Dropout(attn_drop_rate)
 
     def forward(self, feat, coord, reference_index, pos=None, pos_moments=None):
+        # relation-free schedule (_forward_fused): every width under autocast; the positional MLP itself runs in the
+        # tcgen05 kernel where it is supported (C in {48, 96}, G <= 16) and through cuBLAS + bn_act elsewhere
         fused = (self.pe_bias and not self.pe_multiplier and fused_pe_enabled()
-                 and pointops.pe_mlp_supported(self.embed_channels) and self.groups <= 16
-                 and not (self.attn_drop_rate > 0.0 and self.training))
+                 and not (self.attn_drop_rate > 0.0 and self.training)
+                 and ((pointops.pe_mlp_supported(self.embed_channels) and self.groups <= 16) or relation_free_all_widths()))
         # the point operators compute in fp32: q / k feed a GEMM in the relation-free schedule (any dtype) and
         # gva_relation otherwise (fp32); value always feeds gva_aggregate
         qk_dtype = None if fused else torch.float32
@@ -205,7 +219,16 @@ class GroupedVectorAttention(nn.Module):
         with torch.autocast("cuda", enabled=False):
             we = lin_e.weight.float()                                         # (G, C)
             wf = we @ lin2.weight.float()                                     # (G, C) acting on h
-            peb, upe = pointops.pe_bias_mlp(pos, self.linear_p_bias, pos_moments, aux_weight=wf)
+        if pointops.pe_mlp_supported(self.embed_channels) and self.groups <= 16:
+            with torch.autocast("cuda", enabled=False):
+                peb, upe = pointops.pe_bias_mlp(pos, self.linear_p_bias, pos_moments, aux_weight=wf)
+        else:
+            # widths without the fused kernel (C = 192, 384): hidden activation h = ReLU(BN(Linear(3,C)(pos))) through
+            # cuBLAS + bn_act, then the two products that read it
+            h = run_seq(self.linear_p_bias, pos, stop=3)                      # (N, k, C)
+            peb = pointops.linear(h, lin2.weight, lin2.bias, out_f32=True)    # (N, k, C)
+            upe = pointops.linear(h, wf, out_f32=True)                        # (N, k, G)
+        with torch.autocast("cuda", enabled=False):
             const = lin_e.bias.float() if lin_e.bias is not None else None
             if lin2.bias is not None:
                 cb = F.linear(lin2.bias.float(), we)
@@ -218,7 +241,7 @@ class GroupedVectorAttention(nn.Module):
             u = rel + upe
             if const is not None:
                 u = u + const
-        weight = self.weight_encoding[1:](u)                                  # BN(G), ReLU, Linear(G,G)
+        weight = run_seq(self.weight_encoding, u, torch.float32, start=1)     # BN(G), ReLU, Linear(G,G)
         return pointops.gva_aggregate(value, peb, weight, reference_index, self.groups)   # :110,:119-128
 
 

@@ -317,18 +317,24 @@ int aopt_we_tail_backward(int64_t rows, int g, const float *rel, const float *up
                           const float *w2, float *grad_u, float *grad_gamma, float *grad_beta, float *grad_b2,
                           float *grad_w2, void *workspace, size_t workspace_bytes, aopt_stream_t stream);
 
-/* Small dense helpers of the Linear layers around the operators above (backward passes).
+/* Small dense helpers of the Linear layers around the operators above.
  * aopt_col_sum: out (c floats) = column sums of x (rows, c), row stride ldx — a bias gradient; workspace
  *   aopt_dense_workspace_bytes(2*c).
  * aopt_copy_cols: dst[r, :] = src[r, :] (+ bias) for a c-wide column block, each side with its own row stride and element
  *   type (the v block of a fused q|k|v product <-> a dense fp32 tensor).
- * aopt_skinny_wgrad: out (g, c) fp32 = gradᵀ x, grad (rows, g) dense, x (rows, c) — the weight gradient of a Linear with
- *   g in {6, 12} outputs over hundreds of thousands of rows; workspace aopt_dense_workspace_bytes(g*c).  Deterministic. */
+ * aopt_skinny_linear / aopt_skinny_dgrad / aopt_skinny_wgrad: a Linear with g in {6, 12} outputs (weight_encoding[0] applied
+ *   to key / query in the relation-free schedule) over hundreds of thousands of rows, w (g, c) fp32:
+ *   out (rows, g) fp32 = x wᵀ;  grad_x (rows, c) = grad (rows, g) w;  grad_w (g, c) fp32 = gradᵀ x (workspace
+ *   aopt_dense_workspace_bytes(g*c); deterministic). */
 int aopt_col_sum(int64_t rows, int c, const void *x, int64_t ldx, int x_dtype, float *out, void *workspace,
                  size_t workspace_bytes, aopt_stream_t stream);
 int aopt_copy_cols(int64_t rows, int c, const void *src, int64_t ld_src, int src_dtype, const float *bias, void *dst,
                    int64_t ld_dst, int dst_dtype, aopt_stream_t stream);
 int aopt_skinny_wgrad_supported(int g, int c);
+int aopt_skinny_linear(int64_t rows, int g, int c, const void *x, int64_t ldx, int x_dtype, const float *w, float *out,
+                       aopt_stream_t stream);
+int aopt_skinny_dgrad(int64_t rows, int g, int c, const float *grad, const float *w, void *grad_x, int64_t ldgx, int x_dtype,
+                      aopt_stream_t stream);
 int aopt_skinny_wgrad(int64_t rows, int g, int c, const void *grad, int grad_dtype, const void *x, int64_t ldx, int x_dtype,
                       float *out, void *workspace, size_t workspace_bytes, aopt_stream_t stream);
 

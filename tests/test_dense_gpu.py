@@ -308,3 +308,26 @@ def test_skinny_wgrad_col_sum_copy_cols(g, c, rows, gdt, xdt):
                                   _lib.stream()), "copy_cols")
     torch.testing.assert_close(back[:, 2 * c:], dst.to(xdt), rtol=0, atol=0)
     assert float(back[:, :2 * c].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("g,c,rows", [(6, 48, 320000), (12, 96, 50139)])
+@pytest.mark.parametrize("xdt", [torch.bfloat16, torch.float32])
+def test_skinny_linear_forward_backward(g, c, rows, xdt):
+    """pointops.linear(x, w, out_f32=True) with 6 / 12 outputs over many rows (own forward / dgrad / wgrad kernels)
+    against torch in fp64."""
+    from ao_b200 import pointops
+
+    torch.manual_seed(g + c)
+    x = torch.randn(rows, c, device=DEV).to(xdt).requires_grad_(True)
+    w = (torch.randn(g, c, device=DEV) * 0.2).requires_grad_(True)
+    y = pointops.linear(x, w, out_f32=True)
+    assert y.dtype == torch.float32 and y.shape == (rows, g)
+    want = x.detach().double() @ w.detach().double().t()
+    torch.testing.assert_close(y.double(), want, rtol=1e-5, atol=1e-5)
+    gy = torch.randn(rows, g, device=DEV)
+    y.backward(gy)
+    wx = gy.double() @ w.detach().double()
+    tol = dict(rtol=1e-5, atol=1e-5) if xdt == torch.float32 else dict(rtol=2 ** -7, atol=2 ** -7)
+    torch.testing.assert_close(x.grad.double(), wx, **tol)
+    ww = gy.double().t() @ x.detach().double()
+    torch.testing.assert_close(w.grad.double(), ww, rtol=1e-4, atol=1e-4 * float(ww.abs().max()))

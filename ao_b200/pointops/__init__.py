@@ -30,5 +30,5 @@ from .utils import (
     offset2batch,
 )
 from .pe_mlp import pe_bias_mlp, pe_mlp_supported, pos_moments
-from .dense import linear, col_sum, qkv_bn, qkv_usable, bn_act, bn_act_supported, bn_act_usable, bn_fusable, we_tail, we_tail_supported, we_tail_usable, fused_dense_enabled
+from .dense import linear, linear_bn_act, col_sum, qkv_bn, qkv_usable, bn_act, bn_act_supported, bn_act_usable, bn_fusable, we_tail, we_tail_supported, we_tail_usable, fused_dense_enabled
 from ._csr import get_csr, build_csr, prefetch_csr

@@ -547,3 +547,101 @@ def qkv_bn(x: torch.Tensor, seq_q, seq_k, lin_v, qk_dtype: torch.dtype = None):
                         bnk.bias, bnq.running_mean if trackq else None, bnq.running_var if trackq else None,
                         bnk.running_mean if trackk else None, bnk.running_var if trackk else None, momq, momk,
                         float(bnq.eps), float(bnk.eps), trq, trk, dt, qk_dtype)
+
+
+# ---- Linear -> BatchNorm [-> ReLU] as ONE autograd node ----------------------------------------------------------------
+# The step is host-bound: every autograd Function costs ~20 us of Python / engine time per direction.  A Linear whose
+# output goes straight into a training-mode BatchNorm (fc1 + norm1, fc3 + norm3 + residual, GridPool.fc + norm, the
+# Linear -> PointBatchNorm -> ReLU triples) is one node here: the cuBLAS product, then the bn_act kernels on its result;
+# backward = bn_act backward into the GEMM-output gradient, then the two products.
+class _LinearBnFn(Function):
+    @staticmethod
+    def forward(ctx, x, w, lin_bias, gamma, beta, residual, row_scale, rm, rv, mom, eps, relu, out_dtype, tracked, dt):
+        lib = _lib.load()
+        dev = x.device
+        shape = x.shape
+        x2 = x.reshape(-1, shape[-1])
+        xb = x2 if x2.dtype == dt else x2.to(dt)
+        wb = w if dt == torch.float32 else _shadow(w, dt)
+        y = torch.mm(xb, wb.t())
+        rows, c = y.shape
+        out = torch.empty((rows, c), dtype=out_dtype, device=dev)
+        stats = torch.empty(2 * c, dtype=torch.float32, device=dev)
+        with _lib.on_device(dev):
+            ws = _dense_ws(2 * c, dev)
+            _lib.check(
+                lib.aopt_bn_act_forward(rows, c, y.data_ptr(), c, _DT[dt], gamma.data_ptr(), beta.data_ptr(), eps,
+                                        _lib.ptr(residual), _lib.ptr(row_scale), int(relu), out.data_ptr(), _DT[out_dtype],
+                                        stats.data_ptr(), _lib.ptr(rm), _lib.ptr(rv), mom, _lib.ptr(lin_bias), _lib.ptr(tracked),
+                                        ws.data_ptr(), ws.numel(), _lib.stream()),
+                "bn_act_forward")
+        ctx.save_for_backward(xb, wb, y, out if relu else None, gamma, stats, row_scale)
+        ctx.relu = bool(relu)
+        ctx.has_res = residual is not None
+        ctx.lin_bias = lin_bias
+        ctx.x_meta = (x.dtype, shape)
+        return out.view(shape[:-1] + (c,))
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        lib = _lib.load()
+        xb, wb, y, out, gamma, stats, row_scale = ctx.saved_tensors
+        dev = xb.device
+        rows, c = y.shape
+        odt = out.dtype if out is not None else grad_out.dtype
+        grad_out = grad_out.reshape(rows, c)
+        if grad_out.dtype != odt or not grad_out.is_contiguous():
+            grad_out = grad_out.to(odt).contiguous()
+        gy = torch.empty_like(y)
+        want_res = ctx.has_res and ctx.needs_input_grad[5]
+        gres = torch.empty_like(grad_out) if (want_res and ctx.relu) else None
+        gg = torch.empty(c, dtype=torch.float32, device=dev)
+        gb = torch.empty(c, dtype=torch.float32, device=dev)
+        with _lib.on_device(dev):
+            ws = _dense_ws(2 * c, dev)
+            _lib.check(
+                lib.aopt_bn_act_backward(rows, c, grad_out.data_ptr(), _lib.ptr(out), _DT[odt], y.data_ptr(), c, _DT[y.dtype],
+                                         stats.data_ptr(), gamma.data_ptr(), _lib.ptr(row_scale), gy.data_ptr(), c,
+                                         _lib.ptr(gres), gg.data_ptr(), gb.data_ptr(), ws.data_ptr(), ws.numel(),
+                                         _lib.stream()),
+                "bn_act_backward")
+        if want_res and not ctx.relu:
+            gres = grad_out
+        x_dtype, shape = ctx.x_meta
+        gx = gw = None
+        if ctx.needs_input_grad[0]:
+            gx = torch.mm(gy, wb)
+            if gx.dtype != x_dtype:
+                gx = gx.to(x_dtype)
+            gx = gx.view(shape)
+        if ctx.needs_input_grad[1]:
+            gw = _weight_grad(gy, xb) if y.dtype != torch.float32 else torch.mm(gy.t(), xb)
+        gbias = torch.zeros_like(ctx.lin_bias) if (ctx.lin_bias is not None and ctx.needs_input_grad[2]) else None
+        if gres is not None and ctx.has_res:
+            gres = gres.view(shape[:-1] + (c,))
+        return (gx, gw, gbias, gg, gb, gres) + (None,) * 9
+
+
+def linear_bn_act(x: torch.Tensor, lin: torch.nn.Linear, bn: torch.nn.Module, relu: bool = False,
+                  residual: torch.Tensor = None, row_scale: torch.Tensor = None, out_dtype: torch.dtype = None) -> torch.Tensor:
+    """[relu]([residual +] [row_scale *] bn(lin(x))) as one autograd node when bn runs on batch statistics (see above);
+    otherwise bn_act(linear(x))."""
+    bn = getattr(bn, "norm", bn)
+    c = lin.out_features
+    rows = x.numel() // max(x.shape[-1], 1)
+    dt = torch.get_autocast_dtype("cuda") if (x.is_cuda and torch.is_autocast_enabled()) else x.dtype
+    if not (bn_fusable(bn, c, rows, x.is_cuda, dt, out_dtype) and lin.weight.dtype == torch.float32 and dt in _DT):
+        return bn_act(linear(x, lin.weight, lin.bias), bn, relu=relu, residual=residual, row_scale=row_scale, out_dtype=out_dtype)
+    if out_dtype is None:
+        out_dtype = dt if residual is None else torch.promote_types(dt, residual.dtype)
+    if residual is not None:
+        residual = residual.reshape(rows, c)
+        if residual.dtype != out_dtype or not residual.is_contiguous():
+            residual = residual.to(out_dtype).contiguous()
+    if row_scale is not None:
+        row_scale = row_scale.reshape(rows).float().contiguous()
+    track = bn.training and bn.track_running_stats
+    momentum, tracked = _momentum(bn, track)
+    return _LinearBnFn.apply(x, lin.weight, lin.bias, bn.weight, bn.bias, residual, row_scale,
+                             bn.running_mean if track else None, bn.running_var if track else None, momentum, float(bn.eps),
+                             bool(relu), out_dtype, tracked, dt)

@@ -113,14 +113,13 @@ def run_seq(seq, x, out_dtype=None, start=0, stop=None):
             x = pointops.bn_act(x, m.norm, relu=relu, out_dtype=out_dtype if last else None, pre_bias=pre_bias)
             pre_bias = None
             i += 2 if relu else 1
-        elif (isinstance(m, nn.Linear) and m.bias is not None and i + 1 < len(mods) and isinstance(mods[i + 1], PointBatchNorm)
-              and pointops.bn_fusable(mods[i + 1].norm, m.out_features, x.numel() // max(x.shape[-1], 1), x.is_cuda,
-                                      _autocast_dtype() or x.dtype)):
-            # the bias of a Linear in front of a training-mode BatchNorm cancels in the output: the GEMM runs without it
-            # (no bias-gradient reduction over the rows in the backward pass); bn_act adds it to the running mean
-            x = pointops.linear(x, m.weight)
-            pre_bias = m.bias
-            i += 1
+        elif isinstance(m, nn.Linear) and i + 1 < len(mods) and isinstance(mods[i + 1], PointBatchNorm):
+            # Linear -> PointBatchNorm [-> ReLU]: one autograd node; the Linear's bias cancels under batch statistics and
+            # is left out of the GEMM (no bias-gradient reduction over the rows; the running mean still sees it)
+            relu = i + 2 < len(mods) and isinstance(mods[i + 2], nn.ReLU)
+            last = i + (3 if relu else 2) >= len(mods)
+            x = pointops.linear_bn_act(x, m, mods[i + 1].norm, relu=relu, out_dtype=out_dtype if last else None)
+            i += 3 if relu else 2
         elif isinstance(m, nn.Linear):
             x = pointops.linear(x, m.weight, m.bias, out_f32=(out_dtype == torch.float32 and i + 1 == len(mods)))
             i += 1
@@ -264,7 +263,7 @@ class Block(nn.Module):
     def forward(self, points, reference_index, pos=None, pos_moments=None):
         coord, feat, offset = points
         identity = feat
-        feat = pointops.bn_act(pointops.linear(feat, self.fc1.weight, self.fc1.bias), self.norm1.norm, relu=True)
+        feat = pointops.linear_bn_act(feat, self.fc1, self.norm1.norm, relu=True)
         if self.enable_checkpoint:
             from torch.utils.checkpoint import checkpoint
 
@@ -273,12 +272,11 @@ class Block(nn.Module):
             feat = self.attn(feat, coord, reference_index, pos, pos_moments)
         # norm2 + ReLU written in the dtype fc3 consumes; norm3 + DropPath + residual + ReLU in one pass (:194-197)
         feat = pointops.bn_act(feat, self.norm2.norm, relu=True, out_dtype=_autocast_dtype())
-        feat = pointops.linear(feat, self.fc3.weight, self.fc3.bias)
         row_scale = None
         if isinstance(self.drop_path, DropPath) and self.drop_path.drop_prob > 0.0 and self.training:
             keep = 1.0 - self.drop_path.drop_prob
             row_scale = torch.empty(feat.shape[0], dtype=torch.float32, device=feat.device).bernoulli_(keep).div_(keep)
-        feat = pointops.bn_act(feat, self.norm3.norm, relu=True, residual=identity, row_scale=row_scale)
+        feat = pointops.linear_bn_act(feat, self.fc3, self.norm3.norm, relu=True, residual=identity, row_scale=row_scale)
         return [coord, feat, offset]
 
 
@@ -367,7 +365,7 @@ class GridPool(nn.Module):
 
     def forward(self, points, start=None):
         coord, feat, offset = points
-        feat = pointops.bn_act(pointops.linear(feat, self.fc.weight, self.fc.bias), self.norm.norm, relu=True, out_dtype=torch.float32)
+        feat = pointops.linear_bn_act(feat, self.fc, self.norm.norm, relu=True, out_dtype=torch.float32)
         (coord, feat, offset), cluster, part = pointops.grid_pool(coord, feat.float().contiguous(), offset,
                                                                   self.grid_size, start, return_partition=True)
         cluster._aopt_c32 = part.cluster32      # lets UnpoolWithSkip("map") reuse the partition as its CSR

@@ -151,55 +151,139 @@ __device__ __forceinline__ ChanStat stat_from_sums(double s, double q, double in
 }
 
 // ---- BatchNorm (+ ReLU, + residual, + per-row scale) on (rows, C), C % 4 == 0 ----------------------------------
-template <typename XT>
-__global__ void __launch_bounds__(kDenseBlock)
-bn_partial_kernel(long long rows, int c, const XT *__restrict__ x, long long ldx, float *__restrict__ partials) {
-    const int cols = c >> 2;
-    const ColWalk w = col_walk(cols, kDenseBlock);
-    pdl_trigger();
-    float4 s[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
-    float4 q[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
-    const XT *p = x + 4 * w.col;
-    long long row = w.row;
-    for (; row + 3 * w.row_step < rows; row += 4 * w.row_step) {
-        float4 v[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) v[u] = ld4(p + (row + u * w.row_step) * ldx);
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            float4 &S = s[u & 1], &Q = q[u & 1];
-            S.x += v[u].x; S.y += v[u].y; S.z += v[u].z; S.w += v[u].w;
-            Q.x = fmaf(v[u].x, v[u].x, Q.x); Q.y = fmaf(v[u].y, v[u].y, Q.y);
-            Q.z = fmaf(v[u].z, v[u].z, Q.z); Q.w = fmaf(v[u].w, v[u].w, Q.w);
-        }
+// A thread owns V = 8 (C % 8 == 0) or 4 consecutive channels and walks the rows.  These kernels move 30-250 MB per call:
+// what they need is bytes in flight, not occupancy.  The first version (one 8-byte load per thread and iteration) ran at
+// 17-35 % of the DRAM peak at level 0 (profiles/r02t_ops_L0_ncu_summary.md rows 0-6); here every thread issues the raw
+// 16-byte loads of kRowUnroll rows — of all the tensors it reads — before it unpacks the first one.
+constexpr int kRowUnroll = 4;
+
+template <typename T, int V>
+struct Raw;
+template <>
+struct Raw<float, 4> {
+    float4 a;
+    __device__ __forceinline__ void load(const float *p) { a = __ldg(reinterpret_cast<const float4 *>(p)); }
+    __device__ __forceinline__ void unpack(float (&v)[4]) const { v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; }
+};
+template <>
+struct Raw<float, 8> {
+    float4 a, b;
+    __device__ __forceinline__ void load(const float *p) {
+        a = __ldg(reinterpret_cast<const float4 *>(p));
+        b = __ldg(reinterpret_cast<const float4 *>(p) + 1);
     }
-    for (; row < rows; row += w.row_step) {
-        const float4 v = ld4(p + row * ldx);
-        s[0].x += v.x; s[0].y += v.y; s[0].z += v.z; s[0].w += v.w;
-        q[0].x = fmaf(v.x, v.x, q[0].x); q[0].y = fmaf(v.y, v.y, q[0].y);
-        q[0].z = fmaf(v.z, v.z, q[0].z); q[0].w = fmaf(v.w, v.w, q[0].w);
+    __device__ __forceinline__ void unpack(float (&v)[8]) const {
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
     }
-    s[0].x += s[1].x; s[0].y += s[1].y; s[0].z += s[1].z; s[0].w += s[1].w;
-    q[0].x += q[1].x; q[0].y += q[1].y; q[0].z += q[1].z; q[0].w += q[1].w;
-    column_reduce_store(s[0], q[0], cols, c, w.col, partials + (size_t)blockIdx.x * 2 * c);
+};
+template <>
+struct Raw<__nv_bfloat16, 4> {
+    uint2 r;
+    __device__ __forceinline__ void load(const __nv_bfloat16 *p) { r = __ldg(reinterpret_cast<const uint2 *>(p)); }
+    __device__ __forceinline__ void unpack(float (&v)[4]) const {
+        const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&r.x));
+        const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&r.y));
+        v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+    }
+};
+template <>
+struct Raw<__nv_bfloat16, 8> {
+    uint4 r;
+    __device__ __forceinline__ void load(const __nv_bfloat16 *p) { r = __ldg(reinterpret_cast<const uint4 *>(p)); }
+    __device__ __forceinline__ void unpack(float (&v)[8]) const {
+        const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&r.x));
+        const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&r.y));
+        const float2 c = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&r.z));
+        const float2 d = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&r.w));
+        v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+    }
+};
+template <int V>
+__device__ __forceinline__ void store_vec(float *p, const float (&v)[V]) {
+#pragma unroll
+    for (int j = 0; j < V; j += 4) *reinterpret_cast<float4 *>(p + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+}
+template <int V>
+__device__ __forceinline__ void store_vec(__nv_bfloat16 *p, const float (&v)[V]) {
+    unsigned w[V / 2];
+#pragma unroll
+    for (int j = 0; j < V / 2; ++j) {
+        const __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+        w[j] = *reinterpret_cast<const unsigned *>(&t);
+    }
+    if constexpr (V == 8) *reinterpret_cast<uint4 *>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+    else *reinterpret_cast<uint2 *>(p) = make_uint2(w[0], w[1]);
 }
 
-template <typename XT, typename OT>
+// Threads of a CTA that own the same column chunk (t, t + cols, ...) are summed in that order by the first `cols`
+// threads; partial row = [ A (c floats) | B (c floats) ].
+template <int V>
+__device__ __forceinline__ void column_reduce_store_v(const float (&a)[V], const float (&b)[V], int cols, int c, int col,
+                                                      float *__restrict__ partial_row) {
+    __shared__ float sh[2 * V][kDenseBlock];
+    const int t = threadIdx.x;
+#pragma unroll
+    for (int j = 0; j < V; ++j) { sh[j][t] = a[j]; sh[V + j][t] = b[j]; }
+    __syncthreads();
+    if (t < cols) {
+        float A[V], B[V];
+#pragma unroll
+        for (int j = 0; j < V; ++j) { A[j] = sh[j][t]; B[j] = sh[V + j][t]; }
+        for (int u = t + cols; u < kDenseBlock; u += cols) {
+#pragma unroll
+            for (int j = 0; j < V; ++j) { A[j] += sh[j][u]; B[j] += sh[V + j][u]; }
+        }
+        store_vec<V>(partial_row + V * col, A);
+        store_vec<V>(partial_row + c + V * col, B);
+    }
+}
+
+template <typename XT, int V>
+__global__ void __launch_bounds__(kDenseBlock)
+bn_partial_kernel(long long rows, int c, const XT *__restrict__ x, long long ldx, float *__restrict__ partials) {
+    const int cols = c / V;
+    const ColWalk w = col_walk(cols, kDenseBlock);
+    pdl_trigger();
+    float s[V], q[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) { s[j] = 0.f; q[j] = 0.f; }
+    const XT *p = x + V * w.col;
+    for (long long row = w.row; row < rows; row += kRowUnroll * w.row_step) {
+        Raw<XT, V> r[kRowUnroll];
+#pragma unroll
+        for (int u = 0; u < kRowUnroll; ++u) {
+            const long long ru = row + u * w.row_step;
+            r[u].load(p + (ru < rows ? ru : row) * ldx);
+        }
+#pragma unroll
+        for (int u = 0; u < kRowUnroll; ++u) {
+            if (row + u * w.row_step < rows) {
+                float v[V];
+                r[u].unpack(v);
+#pragma unroll
+                for (int j = 0; j < V; ++j) { s[j] += v[j]; q[j] = fmaf(v[j], v[j], q[j]); }
+            }
+        }
+    }
+    column_reduce_store_v<V>(s, q, cols, c, w.col, partials + (size_t)blockIdx.x * 2 * c);
+}
+
+template <typename XT, typename OT, int V>
 __global__ void __launch_bounds__(kDenseBlock)
 bn_apply_kernel(long long rows, int c, const XT *__restrict__ x, long long ldx, const double *__restrict__ sums, double inv_rows,
                 float eps, const float *__restrict__ gamma, const float *__restrict__ beta,
                 const OT *__restrict__ residual, const float *__restrict__ row_scale, int relu, OT *__restrict__ out,
                 float *__restrict__ stats_out, float *__restrict__ running_mean, float *__restrict__ running_var,
                 float momentum, float unbias, const float *__restrict__ mean_shift, long long *__restrict__ batches_tracked) {
-    const int cols = c >> 2;
+    const int cols = c / V;
     const ColWalk w = col_walk(cols, kDenseBlock);
     pdl_wait();
-    float mean[4], sc[4], sh[4];
+    float mean[V], sc[V], sh[V];
     const bool writer = (long long)blockIdx.x * kDenseBlock + threadIdx.x < cols;   // one thread per column chunk
     if (batches_tracked && blockIdx.x == 0 && threadIdx.x == 0) *batches_tracked += 1;   // nn.BatchNorm1d.num_batches_tracked
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int ch = 4 * w.col + j;
+    for (int j = 0; j < V; ++j) {
+        const int ch = V * w.col + j;
         float var;
         const ChanStat st = stat_from_sums(sums[ch], sums[c + ch], inv_rows, eps, &var);
         mean[j] = st.mean;
@@ -215,81 +299,118 @@ bn_apply_kernel(long long rows, int c, const XT *__restrict__ x, long long ldx, 
             if (running_var) running_var[ch] = (1.f - momentum) * running_var[ch] + momentum * var * unbias;
         }
     }
-    const XT *px = x + 4 * w.col;
-    const OT *pr = residual ? residual + 4 * w.col : nullptr;
-    OT *po = out + 4 * w.col;
-    for (long long row = w.row; row < rows; row += w.row_step) {
-        const float4 v = ld4(px + row * ldx);
-        float4 y;
-        y.x = fmaf(v.x - mean[0], sc[0], sh[0]);
-        y.y = fmaf(v.y - mean[1], sc[1], sh[1]);
-        y.z = fmaf(v.z - mean[2], sc[2], sh[2]);
-        y.w = fmaf(v.w - mean[3], sc[3], sh[3]);
-        if (row_scale) {
-            const float r = __ldg(row_scale + row);
-            y.x *= r; y.y *= r; y.z *= r; y.w *= r;
+    const XT *px = x + V * w.col;
+    const OT *pr = residual ? residual + V * w.col : nullptr;
+    OT *po = out + V * w.col;
+    for (long long row = w.row; row < rows; row += kRowUnroll * w.row_step) {
+        Raw<XT, V> rx[kRowUnroll];
+        Raw<OT, V> rr[kRowUnroll];
+        float rs[kRowUnroll];
+#pragma unroll
+        for (int u = 0; u < kRowUnroll; ++u) {
+            const long long ru = row + u * w.row_step;
+            const long long rc = ru < rows ? ru : row;
+            rx[u].load(px + rc * ldx);
+            if (pr) rr[u].load(pr + rc * c);
+            rs[u] = row_scale ? __ldg(row_scale + rc) : 1.f;
         }
-        if (pr) {
-            const float4 e = ld4(pr + row * c);
-            y.x += e.x; y.y += e.y; y.z += e.z; y.w += e.w;
+#pragma unroll
+        for (int u = 0; u < kRowUnroll; ++u) {
+            const long long ru = row + u * w.row_step;
+            if (ru < rows) {
+                float v[V], y[V];
+                rx[u].unpack(v);
+#pragma unroll
+                for (int j = 0; j < V; ++j) y[j] = fmaf(v[j] - mean[j], sc[j], sh[j]) * rs[u];
+                if (pr) {
+                    float e[V];
+                    rr[u].unpack(e);
+#pragma unroll
+                    for (int j = 0; j < V; ++j) y[j] += e[j];
+                }
+                if (relu) {
+#pragma unroll
+                    for (int j = 0; j < V; ++j) y[j] = fmaxf(y[j], 0.f);
+                }
+                store_vec<V>(po + ru * c, y);
+            }
         }
-        if (relu) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
-        st4(po + row * c, y);
     }
 }
 
 // dy = grad_out ⊙ [out > 0] (· row_scale);  partial row = [ Σ dy | Σ dy·x̂ ]
-template <typename XT, typename OT>
+template <typename XT, typename OT, int V>
 __global__ void __launch_bounds__(kDenseBlock)
 bn_bwd_partial_kernel(long long rows, int c, const OT *__restrict__ grad_out, const OT *__restrict__ out,
                       const XT *__restrict__ x, long long ldx, const float *__restrict__ stats,
                       const float *__restrict__ row_scale, float *__restrict__ partials) {
-    const int cols = c >> 2;
+    const int cols = c / V;
     const ColWalk w = col_walk(cols, kDenseBlock);
     pdl_trigger();
-    const float4 mean = *reinterpret_cast<const float4 *>(stats + 4 * w.col);
-    const float4 rstd = *reinterpret_cast<const float4 *>(stats + c + 4 * w.col);
-    float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = make_float4(0.f, 0.f, 0.f, 0.f);
-    const XT *px = x + 4 * w.col;
-    const OT *pg = grad_out + 4 * w.col;
-    const OT *po = out ? out + 4 * w.col : nullptr;
-    for (long long row = w.row; row < rows; row += w.row_step) {
-        float4 g = ld4(pg + row * c);
-        const float4 v = ld4(px + row * ldx);
-        if (po) {
-            const float4 o = ld4(po + row * c);
-            g.x = o.x > 0.f ? g.x : 0.f; g.y = o.y > 0.f ? g.y : 0.f;
-            g.z = o.z > 0.f ? g.z : 0.f; g.w = o.w > 0.f ? g.w : 0.f;
-        }
-        if (row_scale) {
-            const float r = __ldg(row_scale + row);
-            g.x *= r; g.y *= r; g.z *= r; g.w *= r;
-        }
-        s1.x += g.x; s1.y += g.y; s1.z += g.z; s1.w += g.w;
-        s2.x = fmaf(g.x, (v.x - mean.x) * rstd.x, s2.x);
-        s2.y = fmaf(g.y, (v.y - mean.y) * rstd.y, s2.y);
-        s2.z = fmaf(g.z, (v.z - mean.z) * rstd.z, s2.z);
-        s2.w = fmaf(g.w, (v.w - mean.w) * rstd.w, s2.w);
+    float mean[V], rstd[V], s1[V], s2[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+        mean[j] = stats[V * w.col + j];
+        rstd[j] = stats[c + V * w.col + j];
+        s1[j] = 0.f;
+        s2[j] = 0.f;
     }
-    column_reduce_store(s1, s2, cols, c, w.col, partials + (size_t)blockIdx.x * 2 * c);
+    const XT *px = x + V * w.col;
+    const OT *pg = grad_out + V * w.col;
+    const OT *po = out ? out + V * w.col : nullptr;
+    for (long long row = w.row; row < rows; row += kRowUnroll * w.row_step) {
+        Raw<XT, V> rx[kRowUnroll];
+        Raw<OT, V> rg[kRowUnroll], ro[kRowUnroll];
+        float rs[kRowUnroll];
+#pragma unroll
+        for (int u = 0; u < kRowUnroll; ++u) {
+            const long long ru = row + u * w.row_step;
+            const long long rc = ru < rows ? ru : row;
+            rg[u].load(pg + rc * c);
+            rx[u].load(px + rc * ldx);
+            if (po) ro[u].load(po + rc * c);
+            rs[u] = row_scale ? __ldg(row_scale + rc) : 1.f;
+        }
+#pragma unroll
+        for (int u = 0; u < kRowUnroll; ++u) {
+            if (row + u * w.row_step < rows) {
+                float g[V], v[V];
+                rg[u].unpack(g);
+                rx[u].unpack(v);
+                if (po) {
+                    float o[V];
+                    ro[u].unpack(o);
+#pragma unroll
+                    for (int j = 0; j < V; ++j) g[j] = o[j] > 0.f ? g[j] : 0.f;
+                }
+#pragma unroll
+                for (int j = 0; j < V; ++j) {
+                    const float d = g[j] * rs[u];
+                    s1[j] += d;
+                    s2[j] = fmaf(d, (v[j] - mean[j]) * rstd[j], s2[j]);
+                }
+            }
+        }
+    }
+    column_reduce_store_v<V>(s1, s2, cols, c, w.col, partials + (size_t)blockIdx.x * 2 * c);
 }
 
 // dx = γ·rstd·(dy − mean(dy) − x̂·mean(dy·x̂));  grad_residual = grad_out ⊙ [out > 0];  dγ = Σ dy·x̂, dβ = Σ dy
-template <typename XT, typename OT>
+template <typename XT, typename OT, int V>
 __global__ void __launch_bounds__(kDenseBlock)
 bn_bwd_apply_kernel(long long rows, int c, const OT *__restrict__ grad_out, const OT *__restrict__ out,
                     const XT *__restrict__ x, long long ldx, const float *__restrict__ stats, const float *__restrict__ gamma,
                     const float *__restrict__ row_scale, const double *__restrict__ sums, double inv_rows,
                     XT *__restrict__ grad_x, long long ldgx, OT *__restrict__ grad_residual, float *__restrict__ grad_gamma,
                     float *__restrict__ grad_beta) {
-    const int cols = c >> 2;
+    const int cols = c / V;
     const ColWalk w = col_walk(cols, kDenseBlock);
     pdl_wait();
     const bool writer = (long long)blockIdx.x * kDenseBlock + threadIdx.x < cols;
-    float mean[4], rstd[4], a[4], m1[4], m2[4];
+    float mean[V], rstd[V], a[V], m1[V], m2[V];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int ch = 4 * w.col + j;
+    for (int j = 0; j < V; ++j) {
+        const int ch = V * w.col + j;
         mean[j] = stats[ch];
         rstd[j] = stats[c + ch];
         a[j] = __ldg(gamma + ch) * rstd[j];
@@ -301,30 +422,43 @@ bn_bwd_apply_kernel(long long rows, int c, const OT *__restrict__ grad_out, cons
             grad_gamma[ch] = (float)S2;
         }
     }
-    const XT *px = x + 4 * w.col;
-    const OT *pg = grad_out + 4 * w.col;
-    const OT *po = out ? out + 4 * w.col : nullptr;
-    XT *pdx = grad_x + 4 * w.col;
-    OT *pdr = grad_residual ? grad_residual + 4 * w.col : nullptr;
-    for (long long row = w.row; row < rows; row += w.row_step) {
-        float4 g = ld4(pg + row * c);
-        const float4 v = ld4(px + row * ldx);
-        if (po) {
-            const float4 o = ld4(po + row * c);
-            g.x = o.x > 0.f ? g.x : 0.f; g.y = o.y > 0.f ? g.y : 0.f;
-            g.z = o.z > 0.f ? g.z : 0.f; g.w = o.w > 0.f ? g.w : 0.f;
+    const XT *px = x + V * w.col;
+    const OT *pg = grad_out + V * w.col;
+    const OT *po = out ? out + V * w.col : nullptr;
+    XT *pdx = grad_x + V * w.col;
+    OT *pdr = grad_residual ? grad_residual + V * w.col : nullptr;
+    for (long long row = w.row; row < rows; row += kRowUnroll * w.row_step) {
+        Raw<XT, V> rx[kRowUnroll];
+        Raw<OT, V> rg[kRowUnroll], ro[kRowUnroll];
+        float rs[kRowUnroll];
+#pragma unroll
+        for (int u = 0; u < kRowUnroll; ++u) {
+            const long long ru = row + u * w.row_step;
+            const long long rc = ru < rows ? ru : row;
+            rg[u].load(pg + rc * c);
+            rx[u].load(px + rc * ldx);
+            if (po) ro[u].load(po + rc * c);
+            rs[u] = row_scale ? __ldg(row_scale + rc) : 1.f;
         }
-        if (pdr) st4(pdr + row * c, g);
-        if (row_scale) {
-            const float r = __ldg(row_scale + row);
-            g.x *= r; g.y *= r; g.z *= r; g.w *= r;
+#pragma unroll
+        for (int u = 0; u < kRowUnroll; ++u) {
+            const long long ru = row + u * w.row_step;
+            if (ru < rows) {
+                float g[V], v[V], d[V];
+                rg[u].unpack(g);
+                rx[u].unpack(v);
+                if (po) {
+                    float o[V];
+                    ro[u].unpack(o);
+#pragma unroll
+                    for (int j = 0; j < V; ++j) g[j] = o[j] > 0.f ? g[j] : 0.f;
+                }
+                if (pdr) store_vec<V>(pdr + ru * c, g);
+#pragma unroll
+                for (int j = 0; j < V; ++j) d[j] = a[j] * (g[j] * rs[u] - m1[j] - (v[j] - mean[j]) * rstd[j] * m2[j]);
+                store_vec<V>(pdx + ru * ldgx, d);
+            }
         }
-        float4 d;
-        d.x = a[0] * (g.x - m1[0] - (v.x - mean[0]) * rstd[0] * m2[0]);
-        d.y = a[1] * (g.y - m1[1] - (v.y - mean[1]) * rstd[1] * m2[1]);
-        d.z = a[2] * (g.z - m1[2] - (v.z - mean[2]) * rstd[2] * m2[2]);
-        d.w = a[3] * (g.w - m1[3] - (v.w - mean[3]) * rstd[3] * m2[3]);
-        st4(pdx + row * ldgx, d);
     }
 }
 
@@ -711,6 +845,13 @@ skinny_dgrad_kernel(long long rows, int c, const float *__restrict__ g, const fl
 static size_t a256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 static int bn_grid(long long rows, int c) { return col_grid(rows, c >> 2, kDenseBlock, kDenseCtasPerSm); }
+// the row-unrolled BatchNorm kernels: V channels per thread, kRowUnroll rows per iteration; grids sized to what is
+// resident at once (no tail wave): 4 CTAs per SM for the 58-register statistics kernel, 2 for the 92-128-register ones
+static int bn_vec(int c) { return (c & 7) == 0 ? 8 : 4; }
+static int bn_grid_v(long long rows, int c, int ctas_per_sm = 2) {
+    const int cols = c / bn_vec(c);
+    return col_grid((rows + kRowUnroll - 1) / kRowUnroll, cols, kDenseBlock, ctas_per_sm);
+}
 static int row_grid(long long rows) { return stride_grid(rows, kDenseBlock, kDenseCtasPerSm); }
 static bool bn_width_ok(int c) { return c >= 4 && (c & 3) == 0 && c <= 4 * kDenseBlock; }
 
@@ -719,15 +860,24 @@ static int bn_forward_t(long long rows, int c, const void *x, long long ldx, con
                         const void *residual, const float *row_scale, int relu, void *out, float *stats_out,
                         float *running_mean, float *running_var, float momentum, const float *mean_shift,
                         long long *batches_tracked, float *partials, double *sums, cudaStream_t st) {
-    const int grid = bn_grid(rows, c);
+    const int grid_p = bn_grid_v(rows, c, 4), grid = bn_grid_v(rows, c, 2);
     const bool pdl = tuning(kTunePdl) != 2;
-    bn_partial_kernel<XT><<<grid, kDenseBlock, 0, st>>>(rows, c, static_cast<const XT *>(x), ldx, partials);
-    launch_chain(pdl, partials_reduce_kernel, div_up(2 * c, 32), 32 * kReduceSlices, 0, st, grid, 2 * c, 2 * c, (const float *)partials, sums,
+    const bool v8 = bn_vec(c) == 8;
+    if (v8) bn_partial_kernel<XT, 8><<<grid_p, kDenseBlock, 0, st>>>(rows, c, static_cast<const XT *>(x), ldx, partials);
+    else bn_partial_kernel<XT, 4><<<grid_p, kDenseBlock, 0, st>>>(rows, c, static_cast<const XT *>(x), ldx, partials);
+    launch_chain(pdl, partials_reduce_kernel, div_up(2 * c, 32), 32 * kReduceSlices, 0, st, grid_p, 2 * c, 2 * c, (const float *)partials, sums,
                  (float *)nullptr);
     const float unbias = rows > 1 ? (float)((double)rows / (double)(rows - 1)) : 1.f;
-    launch_chain(pdl, bn_apply_kernel<XT, OT>, grid, kDenseBlock, 0, st, rows, c, static_cast<const XT *>(x), ldx,
-                 (const double *)sums, 1.0 / (double)rows, eps, gamma, beta, static_cast<const OT *>(residual), row_scale,
-                 relu, static_cast<OT *>(out), stats_out, running_mean, running_var, momentum, unbias, mean_shift, batches_tracked);
+    if (v8)
+        launch_chain(pdl, bn_apply_kernel<XT, OT, 8>, grid, kDenseBlock, 0, st, rows, c, static_cast<const XT *>(x), ldx,
+                     (const double *)sums, 1.0 / (double)rows, eps, gamma, beta, static_cast<const OT *>(residual), row_scale,
+                     relu, static_cast<OT *>(out), stats_out, running_mean, running_var, momentum, unbias, mean_shift,
+                     batches_tracked);
+    else
+        launch_chain(pdl, bn_apply_kernel<XT, OT, 4>, grid, kDenseBlock, 0, st, rows, c, static_cast<const XT *>(x), ldx,
+                     (const double *)sums, 1.0 / (double)rows, eps, gamma, beta, static_cast<const OT *>(residual), row_scale,
+                     relu, static_cast<OT *>(out), stats_out, running_mean, running_var, momentum, unbias, mean_shift,
+                     batches_tracked);
     return check_launch(3);
 }
 
@@ -736,16 +886,27 @@ static int bn_backward_t(long long rows, int c, const void *grad_out, const void
                          const float *stats, const float *gamma, const float *row_scale, void *grad_x, long long ldgx,
                          void *grad_residual,
                          float *grad_gamma, float *grad_beta, float *partials, double *sums, cudaStream_t st) {
-    const int grid = bn_grid(rows, c);
+    const int grid = bn_grid_v(rows, c);
     const bool pdl = tuning(kTunePdl) != 2;
-    bn_bwd_partial_kernel<XT, OT><<<grid, kDenseBlock, 0, st>>>(rows, c, static_cast<const OT *>(grad_out),
-                                                                static_cast<const OT *>(out), static_cast<const XT *>(x),
-                                                                ldx, stats, row_scale, partials);
+    const bool v8 = bn_vec(c) == 8;
+    if (v8)
+        bn_bwd_partial_kernel<XT, OT, 8><<<grid, kDenseBlock, 0, st>>>(rows, c, static_cast<const OT *>(grad_out),
+                                                                       static_cast<const OT *>(out),
+                                                                       static_cast<const XT *>(x), ldx, stats, row_scale, partials);
+    else
+        bn_bwd_partial_kernel<XT, OT, 4><<<grid, kDenseBlock, 0, st>>>(rows, c, static_cast<const OT *>(grad_out),
+                                                                       static_cast<const OT *>(out),
+                                                                       static_cast<const XT *>(x), ldx, stats, row_scale, partials);
     launch_chain(pdl, partials_reduce_kernel, div_up(2 * c, 32), 32 * kReduceSlices, 0, st, grid, 2 * c, 2 * c, (const float *)partials, sums,
                  (float *)nullptr);
-    launch_chain(pdl, bn_bwd_apply_kernel<XT, OT>, grid, kDenseBlock, 0, st, rows, c, static_cast<const OT *>(grad_out),
-                 static_cast<const OT *>(out), static_cast<const XT *>(x), ldx, stats, gamma, row_scale, (const double *)sums,
-                 1.0 / (double)rows, static_cast<XT *>(grad_x), ldgx, static_cast<OT *>(grad_residual), grad_gamma, grad_beta);
+    if (v8)
+        launch_chain(pdl, bn_bwd_apply_kernel<XT, OT, 8>, grid, kDenseBlock, 0, st, rows, c, static_cast<const OT *>(grad_out),
+                     static_cast<const OT *>(out), static_cast<const XT *>(x), ldx, stats, gamma, row_scale, (const double *)sums,
+                     1.0 / (double)rows, static_cast<XT *>(grad_x), ldgx, static_cast<OT *>(grad_residual), grad_gamma, grad_beta);
+    else
+        launch_chain(pdl, bn_bwd_apply_kernel<XT, OT, 4>, grid, kDenseBlock, 0, st, rows, c, static_cast<const OT *>(grad_out),
+                     static_cast<const OT *>(out), static_cast<const XT *>(x), ldx, stats, gamma, row_scale, (const double *)sums,
+                     1.0 / (double)rows, static_cast<XT *>(grad_x), ldgx, static_cast<OT *>(grad_residual), grad_gamma, grad_beta);
     return check_launch(3);
 }
 
@@ -892,10 +1053,16 @@ extern "C" int aopt_col_sum(int64_t rows, int c, const void *x, int64_t ldx, int
     double *sums;
     if (!carve_dense(workspace, workspace_bytes, 2 * c, &partials, &sums)) return AOPT_ERR_WORKSPACE;
     cudaStream_t st = as_stream(stream);
-    const int grid = bn_grid(rows, c);
+    const int grid = bn_grid_v(rows, c, 4);
     const bool pdl = tuning(kTunePdl) != 2;
-    if (x_dtype == AOPT_F32) bn_partial_kernel<float><<<grid, kDenseBlock, 0, st>>>(rows, c, static_cast<const float *>(x), ldx, partials);
-    else bn_partial_kernel<__nv_bfloat16><<<grid, kDenseBlock, 0, st>>>(rows, c, static_cast<const __nv_bfloat16 *>(x), ldx, partials);
+    const bool v8 = bn_vec(c) == 8;
+    if (x_dtype == AOPT_F32) {
+        if (v8) bn_partial_kernel<float, 8><<<grid, kDenseBlock, 0, st>>>(rows, c, static_cast<const float *>(x), ldx, partials);
+        else bn_partial_kernel<float, 4><<<grid, kDenseBlock, 0, st>>>(rows, c, static_cast<const float *>(x), ldx, partials);
+    } else {
+        if (v8) bn_partial_kernel<__nv_bfloat16, 8><<<grid, kDenseBlock, 0, st>>>(rows, c, static_cast<const __nv_bfloat16 *>(x), ldx, partials);
+        else bn_partial_kernel<__nv_bfloat16, 4><<<grid, kDenseBlock, 0, st>>>(rows, c, static_cast<const __nv_bfloat16 *>(x), ldx, partials);
+    }
     launch_chain(pdl, partials_reduce_kernel, div_up(c, 32), 32 * kReduceSlices, 0, st, grid, c, 2 * c, (const float *)partials,
                  (double *)nullptr, out);
     return check_launch(2);

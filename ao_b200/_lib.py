@@ -81,7 +81,7 @@ SIGNATURES = {
     "aopt_col_sum": (c_int, [c_int64, c_int, P, c_int64, c_int, P, P, c_size_t, P]),
     "aopt_copy_cols": (c_int, [c_int64, c_int, P, c_int64, c_int, P, P, c_int64, c_int, P]),
     "aopt_skinny_wgrad_supported": (c_int, [c_int, c_int]),
-    "aopt_skinny_linear": (c_int, [c_int64, c_int, c_int, P, c_int64, c_int, P, P, P]),
+    "aopt_skinny_linear": (c_int, [c_int64, c_int, c_int, P, c_int64, c_int, P, P, P, P]),
     "aopt_skinny_dgrad": (c_int, [c_int64, c_int, c_int, P, P, P, c_int64, c_int, P]),
     "aopt_skinny_wgrad": (c_int, [c_int64, c_int, c_int, P, c_int, P, c_int64, c_int, P, P, c_size_t, P]),
     "aopt_aggregation_forward": (c_int, [c_int, c_int, c_int, c_int, P, P, P, P, P, P]),

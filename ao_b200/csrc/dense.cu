@@ -718,6 +718,38 @@ copy_cols_kernel(long long rows, int c, const ST *__restrict__ src, long long ld
     }
 }
 
+// One row of G values (fp32 or bf16, dense rows of G elements) into registers; 8-byte loads when rows stay aligned.
+template <typename GT, int G>
+__device__ __forceinline__ void load_small_row(const GT *__restrict__ g, long long row, float (&gr)[G]) {
+    if constexpr (sizeof(GT) == 4) {
+        if constexpr ((G & 1) == 0) {
+            const float2 *gp = reinterpret_cast<const float2 *>(g + row * G);
+#pragma unroll
+            for (int i = 0; i < G / 2; ++i) {
+                const float2 t = __ldg(gp + i);
+                gr[2 * i] = t.x;
+                gr[2 * i + 1] = t.y;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < G; ++i) gr[i] = __ldg(g + row * G + i);
+        }
+    } else {
+        if constexpr ((G & 1) == 0) {
+            const __nv_bfloat162 *gp = reinterpret_cast<const __nv_bfloat162 *>(g + row * G);
+#pragma unroll
+            for (int i = 0; i < G / 2; ++i) {
+                const float2 t = __bfloat1622float2(gp[i]);
+                gr[2 * i] = t.x;
+                gr[2 * i + 1] = t.y;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < G; ++i) gr[i] = __bfloat162float(g[row * G + i]);
+        }
+    }
+}
+
 // Weight gradient of a Linear with a handful of outputs: out[i, :] = Σ_r g[r, i] · x[r, :], g (rows, G), x (rows, c).
 // cuBLAS runs this (G, rows) x (rows, c) product — rows = 320 000, G = 6 — at 170 us (profiles/r02r: a single column of
 // CTAs walks the whole K dimension); here a thread keeps a 4-channel column chunk of x, walks the rows and accumulates
@@ -736,23 +768,7 @@ skinny_wgrad_kernel(long long rows, int c, const GT *__restrict__ g, const XT *_
     for (long long row = w.row; row < rows; row += w.row_step) {
         const float4 v = ld4(px + row * ldx);
         float gr[G];
-        if constexpr (sizeof(GT) == 4) {
-            const float2 *gp = reinterpret_cast<const float2 *>(g + row * G);
-#pragma unroll
-            for (int i = 0; i < G / 2; ++i) {
-                const float2 t = __ldg(gp + i);
-                gr[2 * i] = t.x;
-                gr[2 * i + 1] = t.y;
-            }
-        } else {
-            const __nv_bfloat162 *gp = reinterpret_cast<const __nv_bfloat162 *>(g + row * G);
-#pragma unroll
-            for (int i = 0; i < G / 2; ++i) {
-                const float2 t = __bfloat1622float2(gp[i]);
-                gr[2 * i] = t.x;
-                gr[2 * i + 1] = t.y;
-            }
-        }
+        load_small_row<GT, G>(g, row, gr);
 #pragma unroll
         for (int i = 0; i < G; ++i) {
             acc[i].x = fmaf(gr[i], v.x, acc[i].x);
@@ -789,7 +805,7 @@ skinny_wgrad_kernel(long long rows, int c, const GT *__restrict__ g, const XT *_
 template <typename XT, int G>
 __global__ void __launch_bounds__(kDenseBlock)
 skinny_linear_kernel(long long rows, int c, const XT *__restrict__ x, long long ldx, const float *__restrict__ w,
-                     float *__restrict__ out) {
+                     const float *__restrict__ bias, float *__restrict__ out) {
     extern __shared__ float4 s_w[];   // [c / 4][G] : chunk-major so that a thread walks it linearly
     const int cols = c >> 2;
     for (int t = threadIdx.x; t < cols * G; t += kDenseBlock) {
@@ -800,7 +816,7 @@ skinny_linear_kernel(long long rows, int c, const XT *__restrict__ x, long long 
     for (long long row = (long long)blockIdx.x * kDenseBlock + threadIdx.x; row < rows; row += (long long)gridDim.x * kDenseBlock) {
         float acc[G];
 #pragma unroll
-        for (int i = 0; i < G; ++i) acc[i] = 0.f;
+        for (int i = 0; i < G; ++i) acc[i] = bias ? __ldg(bias + i) : 0.f;
         const XT *px = x + row * ldx;
         for (int ch = 0; ch < cols; ++ch) {
             const float4 v = ld4(px + 4 * ch);
@@ -810,9 +826,14 @@ skinny_linear_kernel(long long rows, int c, const XT *__restrict__ x, long long 
                 acc[i] = fmaf(v.x, ww.x, fmaf(v.y, ww.y, fmaf(v.z, ww.z, fmaf(v.w, ww.w, acc[i]))));
             }
         }
-        float2 *o = reinterpret_cast<float2 *>(out + row * G);
+        if constexpr ((G & 1) == 0) {
+            float2 *o = reinterpret_cast<float2 *>(out + row * G);
 #pragma unroll
-        for (int i = 0; i < G; i += 2) o[i / 2] = make_float2(acc[i], acc[i + 1]);
+            for (int i = 0; i < G; i += 2) o[i / 2] = make_float2(acc[i], acc[i + 1]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < G; ++i) out[row * G + i] = acc[i];
+        }
     }
 }
 
@@ -827,15 +848,13 @@ skinny_dgrad_kernel(long long rows, int c, const float *__restrict__ g, const fl
     for (int i = 0; i < G; ++i) ww[i] = *reinterpret_cast<const float4 *>(w + (size_t)i * c + 4 * cw.col);
     XT *po = gx + 4 * cw.col;
     for (long long row = cw.row; row < rows; row += cw.row_step) {
-        const float2 *gp = reinterpret_cast<const float2 *>(g + row * G);
+        float gr[G];
+        load_small_row<float, G>(g, row, gr);
         float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int i = 0; i < G / 2; ++i) {
-            const float2 t = __ldg(gp + i);
-            a.x = fmaf(t.x, ww[2 * i].x, a.x); a.y = fmaf(t.x, ww[2 * i].y, a.y);
-            a.z = fmaf(t.x, ww[2 * i].z, a.z); a.w = fmaf(t.x, ww[2 * i].w, a.w);
-            a.x = fmaf(t.y, ww[2 * i + 1].x, a.x); a.y = fmaf(t.y, ww[2 * i + 1].y, a.y);
-            a.z = fmaf(t.y, ww[2 * i + 1].z, a.z); a.w = fmaf(t.y, ww[2 * i + 1].w, a.w);
+        for (int i = 0; i < G; ++i) {
+            a.x = fmaf(gr[i], ww[i].x, a.x); a.y = fmaf(gr[i], ww[i].y, a.y);
+            a.z = fmaf(gr[i], ww[i].z, a.z); a.w = fmaf(gr[i], ww[i].w, a.w);
         }
         st4(po + row * ldgx, a);
     }
@@ -1086,7 +1105,16 @@ extern "C" int aopt_copy_cols(int64_t rows, int c, const void *src, int64_t ld_s
     return check_launch(1);
 }
 
-extern "C" int aopt_skinny_wgrad_supported(int g, int c) { return ((g == 6 || g == 12) && bn_width_ok(c)) ? 1 : 0; }
+// widths served: the in_channels / num_classes / groups of the configs BASELINE.json names (S3DIS 6 / 13, ScanNet 9 / 20,
+// SemanticKITTI 4 / 19; weight_encoding groups 6 / 12)
+#define AOPT_SKINNY_WIDTHS(X) X(4) X(6) X(9) X(12) X(13) X(19) X(20)
+extern "C" int aopt_skinny_wgrad_supported(int g, int c) {
+    if (!bn_width_ok(c)) return 0;
+#define AOPT_CASE(GG) if (g == GG) return 1;
+    AOPT_SKINNY_WIDTHS(AOPT_CASE)
+#undef AOPT_CASE
+    return 0;
+}
 
 // out (g, c) fp32 = gradᵀ · x;  grad (rows, g) dense, x (rows, c) with row stride ldx.  workspace: aopt_dense_workspace_bytes(g * c).
 extern "C" int aopt_skinny_wgrad(int64_t rows, int g, int c, const void *grad, int grad_dtype, const void *x, int64_t ldx,
@@ -1102,38 +1130,39 @@ extern "C" int aopt_skinny_wgrad(int64_t rows, int g, int c, const void *grad, i
 #define AOPT_SW(GT, XT, GG)                                                                                         \
     skinny_wgrad_kernel<GT, XT, GG><<<grid, kDenseBlock, 0, st>>>(rows, c, static_cast<const GT *>(grad),        \
                                                                   static_cast<const XT *>(x), ldx, partials)
-    if (g == 6) {
-        if (grad_dtype == AOPT_F32 && x_dtype == AOPT_F32) AOPT_SW(float, float, 6);
-        else if (grad_dtype == AOPT_F32) AOPT_SW(float, __nv_bfloat16, 6);
-        else if (x_dtype == AOPT_F32) AOPT_SW(__nv_bfloat16, float, 6);
-        else AOPT_SW(__nv_bfloat16, __nv_bfloat16, 6);
-    } else {
-        if (grad_dtype == AOPT_F32 && x_dtype == AOPT_F32) AOPT_SW(float, float, 12);
-        else if (grad_dtype == AOPT_F32) AOPT_SW(float, __nv_bfloat16, 12);
-        else if (x_dtype == AOPT_F32) AOPT_SW(__nv_bfloat16, float, 12);
-        else AOPT_SW(__nv_bfloat16, __nv_bfloat16, 12);
+#define AOPT_CASE(GG)                                                                   \
+    if (g == GG) {                                                                      \
+        if (grad_dtype == AOPT_F32 && x_dtype == AOPT_F32) AOPT_SW(float, float, GG);   \
+        else if (grad_dtype == AOPT_F32) AOPT_SW(float, __nv_bfloat16, GG);             \
+        else if (x_dtype == AOPT_F32) AOPT_SW(__nv_bfloat16, float, GG);                \
+        else AOPT_SW(__nv_bfloat16, __nv_bfloat16, GG);                                 \
     }
+    AOPT_SKINNY_WIDTHS(AOPT_CASE)
+#undef AOPT_CASE
 #undef AOPT_SW
     launch_chain(pdl, partials_reduce_kernel, div_up(g * c, 32), 32 * kReduceSlices, 0, st, grid, g * c, g * c,
                  (const float *)partials, (double *)nullptr, out);
     return check_launch(2);
 }
 
-// out (rows, g) fp32 = x (rows, c) · wᵀ, w (g, c) fp32; g in {6, 12} (aopt_skinny_wgrad_supported).
+// out (rows, g) fp32 = x (rows, c) · wᵀ (+ bias), w (g, c) fp32 (aopt_skinny_wgrad_supported).
 extern "C" int aopt_skinny_linear(int64_t rows, int g, int c, const void *x, int64_t ldx, int x_dtype, const float *w,
-                                  float *out, aopt_stream_t stream) {
+                                  const float *bias, float *out, aopt_stream_t stream) {
     if (rows <= 0 || !x || !w || !out || (x_dtype & ~1) || ldx < c || (ldx & 3)) return AOPT_ERR_INVALID_ARGUMENT;
     if (!aopt_skinny_wgrad_supported(g, c)) return AOPT_ERR_UNSUPPORTED;
     cudaStream_t st = as_stream(stream);
     const int grid = row_grid(rows);
     const size_t smem = (size_t)g * c * sizeof(float);
-    if (g == 6) {
-        if (x_dtype == AOPT_F32) skinny_linear_kernel<float, 6><<<grid, kDenseBlock, smem, st>>>(rows, c, static_cast<const float *>(x), ldx, w, out);
-        else skinny_linear_kernel<__nv_bfloat16, 6><<<grid, kDenseBlock, smem, st>>>(rows, c, static_cast<const __nv_bfloat16 *>(x), ldx, w, out);
-    } else {
-        if (x_dtype == AOPT_F32) skinny_linear_kernel<float, 12><<<grid, kDenseBlock, smem, st>>>(rows, c, static_cast<const float *>(x), ldx, w, out);
-        else skinny_linear_kernel<__nv_bfloat16, 12><<<grid, kDenseBlock, smem, st>>>(rows, c, static_cast<const __nv_bfloat16 *>(x), ldx, w, out);
+    if (smem > 48 * 1024) return AOPT_ERR_UNSUPPORTED;
+#define AOPT_CASE(GG)                                                                                                            \
+    if (g == GG) {                                                                                                               \
+        if (x_dtype == AOPT_F32)                                                                                                 \
+            skinny_linear_kernel<float, GG><<<grid, kDenseBlock, smem, st>>>(rows, c, static_cast<const float *>(x), ldx, w, bias, out); \
+        else                                                                                                                     \
+            skinny_linear_kernel<__nv_bfloat16, GG><<<grid, kDenseBlock, smem, st>>>(rows, c, static_cast<const __nv_bfloat16 *>(x), ldx, w, bias, out); \
     }
+    AOPT_SKINNY_WIDTHS(AOPT_CASE)
+#undef AOPT_CASE
     return check_launch(1);
 }
 
@@ -1144,12 +1173,12 @@ extern "C" int aopt_skinny_dgrad(int64_t rows, int g, int c, const float *grad, 
     if (!aopt_skinny_wgrad_supported(g, c)) return AOPT_ERR_UNSUPPORTED;
     cudaStream_t st = as_stream(stream);
     const int grid = bn_grid(rows, c);
-    if (g == 6) {
-        if (x_dtype == AOPT_F32) skinny_dgrad_kernel<float, 6><<<grid, kDenseBlock, 0, st>>>(rows, c, grad, w, static_cast<float *>(grad_x), ldgx);
-        else skinny_dgrad_kernel<__nv_bfloat16, 6><<<grid, kDenseBlock, 0, st>>>(rows, c, grad, w, static_cast<__nv_bfloat16 *>(grad_x), ldgx);
-    } else {
-        if (x_dtype == AOPT_F32) skinny_dgrad_kernel<float, 12><<<grid, kDenseBlock, 0, st>>>(rows, c, grad, w, static_cast<float *>(grad_x), ldgx);
-        else skinny_dgrad_kernel<__nv_bfloat16, 12><<<grid, kDenseBlock, 0, st>>>(rows, c, grad, w, static_cast<__nv_bfloat16 *>(grad_x), ldgx);
+#define AOPT_CASE(GG)                                                                                                                  \
+    if (g == GG) {                                                                                                                     \
+        if (x_dtype == AOPT_F32) skinny_dgrad_kernel<float, GG><<<grid, kDenseBlock, 0, st>>>(rows, c, grad, w, static_cast<float *>(grad_x), ldgx); \
+        else skinny_dgrad_kernel<__nv_bfloat16, GG><<<grid, kDenseBlock, 0, st>>>(rows, c, grad, w, static_cast<__nv_bfloat16 *>(grad_x), ldgx);      \
     }
+    AOPT_SKINNY_WIDTHS(AOPT_CASE)
+#undef AOPT_CASE
     return check_launch(1);
 }

@@ -335,16 +335,17 @@ def _skinny_ok(g: int, c: int) -> bool:
 
 
 class _SkinnyLinearFn(Function):
-    """x (rows, c) -> x wᵀ (rows, g) fp32, w (g, c) fp32 with g in {6, 12}: all three products in own kernels."""
+    """x (rows, c) -> x wᵀ (+ b) (rows, g) fp32, w (g, c) fp32 with a handful of outputs: all three products in own kernels."""
 
     @staticmethod
-    def forward(ctx, x, w):
+    def forward(ctx, x, w, b):
         rows, c = x.shape
         g = w.shape[0]
         out = torch.empty((rows, g), dtype=torch.float32, device=x.device)
-        _lib.check(_lib.load().aopt_skinny_linear(rows, g, c, x.data_ptr(), c, _DT[x.dtype], w.data_ptr(), out.data_ptr(),
-                                                  _lib.stream()), "skinny_linear")
+        _lib.check(_lib.load().aopt_skinny_linear(rows, g, c, x.data_ptr(), c, _DT[x.dtype], w.data_ptr(), _lib.ptr(b),
+                                                  out.data_ptr(), _lib.stream()), "skinny_linear")
         ctx.save_for_backward(x, w)
+        ctx.has_bias = b is not None
         return out
 
     @staticmethod
@@ -354,7 +355,7 @@ class _SkinnyLinearFn(Function):
         g = w.shape[0]
         if gy.dtype != torch.float32 or not gy.is_contiguous():
             gy = gy.float().contiguous()
-        gx = gw = None
+        gx = gw = gb = None
         lib = _lib.load()
         if ctx.needs_input_grad[0]:
             gx = torch.empty_like(x)
@@ -365,7 +366,37 @@ class _SkinnyLinearFn(Function):
             ws = _dense_ws(g * c, x.device)
             _lib.check(lib.aopt_skinny_wgrad(rows, g, c, gy.data_ptr(), 0, x.data_ptr(), c, _DT[x.dtype], gw.data_ptr(),
                                              ws.data_ptr(), ws.numel(), _lib.stream()), "skinny_wgrad")
-        return gx, gw
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = gy.sum(0)
+        return gx, gw, gb
+
+
+def _small_k_usable(x2: torch.Tensor, w: torch.Tensor) -> bool:
+    """A Linear with a handful of INPUT channels over many rows (the patch-embedding projection, 6 -> 48)."""
+    return (x2.dtype == torch.float32 and x2.is_contiguous() and x2.shape[0] >= 16384 and w.shape[1] <= 20
+            and w.dtype == torch.float32 and _skinny_ok(w.shape[1], w.shape[0]))
+
+
+def _small_k_forward(x2: torch.Tensor, w: torch.Tensor, dt: torch.dtype) -> torch.Tensor:
+    """y (rows, out) in dt = x2 (rows, k) fp32 · wᵀ through aopt_skinny_dgrad (its "gradient" operand is x2)."""
+    rows, k = x2.shape
+    cout = w.shape[0]
+    y = torch.empty((rows, cout), dtype=dt, device=x2.device)
+    wt = w.detach().t().contiguous()
+    _lib.check(_lib.load().aopt_skinny_dgrad(rows, k, cout, x2.data_ptr(), wt.data_ptr(), y.data_ptr(), cout, _DT[dt],
+                                             _lib.stream()), "skinny_dgrad")
+    return y
+
+
+def _small_k_wgrad(gy: torch.Tensor, x2: torch.Tensor) -> torch.Tensor:
+    """(out, k) fp32 = gyᵀ · x2 through aopt_skinny_wgrad with the operands exchanged."""
+    rows, k = x2.shape
+    cout = gy.shape[1]
+    gwt = torch.empty((k, cout), dtype=torch.float32, device=x2.device)
+    ws = _dense_ws(k * cout, x2.device)
+    _lib.check(_lib.load().aopt_skinny_wgrad(rows, k, cout, x2.data_ptr(), 0, gy.data_ptr(), cout, _DT[gy.dtype], gwt.data_ptr(),
+                                             ws.data_ptr(), ws.numel(), _lib.stream()), "skinny_wgrad")
+    return gwt.t().contiguous()
 
 
 class _LinearFn(Function):
@@ -408,10 +439,11 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor = None, out
     """torch.nn.functional.linear; under CUDA autocast the low-precision copy of the fp32 parameters is cached across
     calls (see above).  Same arithmetic as the autocast Linear it replaces.  out_f32: return fp32 (under autocast the
     GEMM writes its fp32 accumulator instead of a rounded copy that the caller would cast back)."""
-    if (out_f32 and bias is None and x.is_cuda and x.dim() == 2 and weight.shape[0] <= 16 and x.shape[0] >= 16384
+    if (out_f32 and x.is_cuda and x.dim() == 2 and weight.shape[0] <= 20 and x.shape[0] >= 16384
             and fused_dense_enabled() and x.dtype in _DT and weight.dtype == torch.float32 and x.is_contiguous()
-            and weight.is_contiguous() and _skinny_ok(weight.shape[0], weight.shape[1])):
-        return _SkinnyLinearFn.apply(x, weight)          # a handful of outputs over many rows: own kernels, any mode
+            and weight.is_contiguous() and (bias is None or bias.dtype == torch.float32)
+            and _skinny_ok(weight.shape[0], weight.shape[1])):
+        return _SkinnyLinearFn.apply(x, weight, bias)    # a handful of outputs over many rows: own kernels, any mode
     if (x.is_cuda and torch.is_autocast_enabled() and fused_dense_enabled() and weight.dtype == torch.float32
             and x.dtype in (torch.float32, torch.bfloat16, torch.float16) and x.numel() > 0):
         return _LinearFn.apply(x, weight, bias, torch.get_autocast_dtype("cuda"), bool(out_f32))
@@ -561,9 +593,15 @@ class _LinearBnFn(Function):
         dev = x.device
         shape = x.shape
         x2 = x.reshape(-1, shape[-1])
-        xb = x2 if x2.dtype == dt else x2.to(dt)
-        wb = w if dt == torch.float32 else _shadow(w, dt)
-        y = torch.mm(xb, wb.t())
+        small_k = _small_k_usable(x2, w) and not ctx.needs_input_grad[0]
+        if small_k:
+            xb, wb = x2, w                                                   # fp32 rows of <= 20 inputs: own kernels
+            y = _small_k_forward(x2, w, dt)
+        else:
+            xb = x2 if x2.dtype == dt else x2.to(dt)
+            wb = w if dt == torch.float32 else _shadow(w, dt)
+            y = torch.mm(xb, wb.t())
+        ctx.small_k = small_k
         rows, c = y.shape
         out = torch.empty((rows, c), dtype=out_dtype, device=dev)
         stats = torch.empty(2 * c, dtype=torch.float32, device=dev)
@@ -615,7 +653,10 @@ class _LinearBnFn(Function):
                 gx = gx.to(x_dtype)
             gx = gx.view(shape)
         if ctx.needs_input_grad[1]:
-            gw = _weight_grad(gy, xb) if y.dtype != torch.float32 else torch.mm(gy.t(), xb)
+            if ctx.small_k:
+                gw = _small_k_wgrad(gy, xb)
+            else:
+                gw = _weight_grad(gy, xb) if y.dtype != torch.float32 else torch.mm(gy.t(), xb)
         gbias = torch.zeros_like(ctx.lin_bias) if (ctx.lin_bias is not None and ctx.needs_input_grad[2]) else None
         if gres is not None and ctx.has_res:
             gres = gres.view(shape[:-1] + (c,))

@@ -50,15 +50,18 @@ def fused_pe_enabled() -> bool:
     return torch.is_autocast_enabled()
 
 
-def relation_free_all_widths() -> bool:
-    """AOPT_RELFREE_ALL=1 runs the relation-free schedule also at the widths the fused positional-MLP kernel does not
-    cover (C = 192, 384: hidden activation through cuBLAS + bn_act).  Off by default: measured on a B200
-    (profiles/r02v_model_step_relfree*.txt) the S3DIS-cfg training step takes 38.3 ms with it and 36.6 ms without — those
-    levels hold 12.5k / 2.9k points, their kernels are launch-bound and the step is host-bound, so trading one (N,k,C) pass
-    for two more operators per block loses."""
+def relation_free_min_elems() -> float:
+    """Smallest N·k·C for which the relation-free schedule is also used at the widths the fused positional-MLP kernel
+    does not cover (C = 192, 384: hidden activation through cuBLAS + bn_act, one more GEMM for `upe`).  It trades the
+    (N,k,C) relation tensor and its passes for two more operators per block, which pays once the level is large enough
+    for the step to be device-bound there: S3DIS cfg, 4 rooms (level 2: 38 M elements): 38.3 ms with it at every level vs
+    36.6 ms without; 8 rooms (77 M): 49.6 vs 51.3 ms (profiles/r02v_*, r02y_*).  AOPT_RELFREE_MIN_ELEMS overrides
+    (0 = always, AOPT_RELFREE_ALL=1 is the same)."""
     import os
 
-    return os.environ.get("AOPT_RELFREE_ALL", "0") == "1"
+    if os.environ.get("AOPT_RELFREE_ALL", "") == "1":
+        return 0.0
+    return float(os.environ.get("AOPT_RELFREE_MIN_ELEMS", 64e6))
 
 
 class DropPath(nn.Module):
@@ -161,7 +164,8 @@ class GroupedVectorAttention(nn.Module):
         # tcgen05 kernel where it is supported (C in {48, 96}, G <= 16) and through cuBLAS + bn_act elsewhere
         fused = (self.pe_bias and not self.pe_multiplier and fused_pe_enabled()
                  and not (self.attn_drop_rate > 0.0 and self.training)
-                 and ((pointops.pe_mlp_supported(self.embed_channels) and self.groups <= 16) or relation_free_all_widths()))
+                 and ((pointops.pe_mlp_supported(self.embed_channels) and self.groups <= 16)
+                      or reference_index.numel() * self.embed_channels >= relation_free_min_elems()))
         # the point operators compute in fp32: q / k feed a GEMM in the relation-free schedule (any dtype) and
         # gva_relation otherwise (fp32); value always feeds gva_aggregate
         qk_dtype = None if fused else torch.float32
@@ -540,7 +544,8 @@ class PointTransformerV2(nn.Module):
                 skip_points, cluster = skips.pop(-1)
                 points = self.dec_stages[i](points, skip_points, cluster)
             coord, feat, offset = points
-            return run_seq(self.seg_head, feat) if isinstance(self.seg_head, nn.Sequential) else self.seg_head(feat)
+            # logits in fp32: the loss upcasts them anyway, and the 13- / 19- / 20-output Linear has its own kernels
+            return run_seq(self.seg_head, feat, torch.float32) if isinstance(self.seg_head, nn.Sequential) else self.seg_head(feat)
         finally:
             self._knn_cache.clear()   # the idx tensors stay alive through autograd; do not pin them here
 

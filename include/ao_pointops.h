@@ -322,17 +322,19 @@ int aopt_we_tail_backward(int64_t rows, int g, const float *rel, const float *up
  *   aopt_dense_workspace_bytes(2*c).
  * aopt_copy_cols: dst[r, :] = src[r, :] (+ bias) for a c-wide column block, each side with its own row stride and element
  *   type (the v block of a fused q|k|v product <-> a dense fp32 tensor).
- * aopt_skinny_linear / aopt_skinny_dgrad / aopt_skinny_wgrad: a Linear with g in {6, 12} outputs (weight_encoding[0] applied
- *   to key / query in the relation-free schedule) over hundreds of thousands of rows, w (g, c) fp32:
- *   out (rows, g) fp32 = x wᵀ;  grad_x (rows, c) = grad (rows, g) w;  grad_w (g, c) fp32 = gradᵀ x (workspace
+ * aopt_skinny_linear / aopt_skinny_dgrad / aopt_skinny_wgrad: a Linear with a handful (g) of outputs over hundreds of
+ *   thousands of rows — weight_encoding[0] applied to key / query (g = groups), the segmentation head (g = num_classes) — and,
+ *   with the roles of input and output exchanged, the patch-embedding projection (g = in_channels); w (g, c) fp32,
+ *   g in {4, 6, 9, 12, 13, 19, 20} (aopt_skinny_wgrad_supported):
+ *   out (rows, g) fp32 = x wᵀ (+ bias);  grad_x (rows, c) = grad (rows, g) w;  grad_w (g, c) fp32 = gradᵀ x (workspace
  *   aopt_dense_workspace_bytes(g*c); deterministic). */
 int aopt_col_sum(int64_t rows, int c, const void *x, int64_t ldx, int x_dtype, float *out, void *workspace,
                  size_t workspace_bytes, aopt_stream_t stream);
 int aopt_copy_cols(int64_t rows, int c, const void *src, int64_t ld_src, int src_dtype, const float *bias, void *dst,
                    int64_t ld_dst, int dst_dtype, aopt_stream_t stream);
 int aopt_skinny_wgrad_supported(int g, int c);
-int aopt_skinny_linear(int64_t rows, int g, int c, const void *x, int64_t ldx, int x_dtype, const float *w, float *out,
-                       aopt_stream_t stream);
+int aopt_skinny_linear(int64_t rows, int g, int c, const void *x, int64_t ldx, int x_dtype, const float *w,
+                       const float *bias, float *out, aopt_stream_t stream);
 int aopt_skinny_dgrad(int64_t rows, int g, int c, const float *grad, const float *w, void *grad_x, int64_t ldgx, int x_dtype,
                       aopt_stream_t stream);
 int aopt_skinny_wgrad(int64_t rows, int g, int c, const void *grad, int grad_dtype, const void *x, int64_t ldx, int x_dtype,

@@ -11,7 +11,7 @@ import torch
 from ao_b200 import ptv2, scenes
 
 dev = torch.device("cuda", 0)
-coord_np, feat_np, off_np = scenes.s3dis_batch(4, 80000)
+coord_np, feat_np, off_np = scenes.s3dis_batch(int(os.environ.get('ROOMS', 4)), 80000)
 coord, feat, offset = (torch.from_numpy(a).to(dev) for a in (coord_np, feat_np, off_np))
 torch.manual_seed(0)
 model = ptv2.PointTransformerV2(**ptv2.S3DIS_CFG).to(dev).train()

@@ -310,7 +310,7 @@ def test_skinny_wgrad_col_sum_copy_cols(g, c, rows, gdt, xdt):
     assert float(back[:, :2 * c].abs().max()) == 0.0
 
 
-@pytest.mark.parametrize("g,c,rows", [(6, 48, 320000), (12, 96, 50139)])
+@pytest.mark.parametrize("g,c,rows", [(6, 48, 320000), (12, 96, 50139), (13, 48, 100000), (20, 48, 30000)])
 @pytest.mark.parametrize("xdt", [torch.bfloat16, torch.float32])
 def test_skinny_linear_forward_backward(g, c, rows, xdt):
     """pointops.linear(x, w, out_f32=True) with 6 / 12 outputs over many rows (own forward / dgrad / wgrad kernels)
@@ -320,9 +320,12 @@ def test_skinny_linear_forward_backward(g, c, rows, xdt):
     torch.manual_seed(g + c)
     x = torch.randn(rows, c, device=DEV).to(xdt).requires_grad_(True)
     w = (torch.randn(g, c, device=DEV) * 0.2).requires_grad_(True)
-    y = pointops.linear(x, w, out_f32=True)
+    b = torch.randn(g, device=DEV, requires_grad=True) if g in (13, 20) else None      # the segmentation head has a bias
+    y = pointops.linear(x, w, b, out_f32=True)
     assert y.dtype == torch.float32 and y.shape == (rows, g)
     want = x.detach().double() @ w.detach().double().t()
+    if b is not None:
+        want = want + b.detach().double()
     torch.testing.assert_close(y.double(), want, rtol=1e-5, atol=1e-5)
     gy = torch.randn(rows, g, device=DEV)
     y.backward(gy)
@@ -331,3 +334,30 @@ def test_skinny_linear_forward_backward(g, c, rows, xdt):
     torch.testing.assert_close(x.grad.double(), wx, **tol)
     ww = gy.double().t() @ x.detach().double()
     torch.testing.assert_close(w.grad.double(), ww, rtol=1e-4, atol=1e-4 * float(ww.abs().max()))
+    if b is not None:
+        torch.testing.assert_close(b.grad.double(), gy.double().sum(0), rtol=1e-4, atol=1e-3)
+
+
+@pytest.mark.parametrize("cin", [6, 9, 4])
+@pytest.mark.parametrize("autocast", [False, True])
+def test_patch_projection_small_input_width(cin, autocast):
+    """Linear(in_channels, 48, bias=False) -> PointBatchNorm -> ReLU on 10^5 rows of raw features (GVAPatchEmbed.proj,
+    …v2m2_base.py:363-364): the product runs in the small-K kernels; against the torch modules."""
+    from ao_b200 import ptv2
+
+    torch.manual_seed(cin)
+    seq = nn.Sequential(nn.Linear(cin, 48, bias=False), ptv2.PointBatchNorm(48), nn.ReLU(inplace=True)).to(DEV).train()
+    ref = nn.Sequential(nn.Linear(cin, 48, bias=False), ptv2.PointBatchNorm(48), nn.ReLU(inplace=True)).to(DEV).train()
+    ref.load_state_dict(seq.state_dict())
+    x = torch.randn(100000, cin, device=DEV)
+    with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+        out = ptv2.run_seq(seq, x)
+        want = ref(x)
+    tol = dict(rtol=3e-2, atol=3e-2) if autocast else dict(rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(out.float(), want.float(), **tol)
+    wts = torch.randn_like(want, dtype=torch.float32)
+    (out.float() * wts).sum().backward()
+    (want.float() * wts).sum().backward()
+    ga, gb = seq[0].weight.grad, ref[0].weight.grad
+    # under autocast the torch reference returns this gradient rounded to bf16 (3 significant digits)
+    assert float((ga - gb).norm() / gb.norm()) < (6e-2 if autocast else 1e-3)

@@ -1105,9 +1105,9 @@ extern "C" int aopt_copy_cols(int64_t rows, int c, const void *src, int64_t ld_s
     return check_launch(1);
 }
 
-// widths served: the in_channels / num_classes / groups of the configs BASELINE.json names (S3DIS 6 / 13, ScanNet 9 / 20,
-// SemanticKITTI 4 / 19; weight_encoding groups 6 / 12)
-#define AOPT_SKINNY_WIDTHS(X) X(4) X(6) X(9) X(12) X(13) X(19) X(20)
+// widths served: 3 (relative coordinates into linear_p_bias[0]), the in_channels / num_classes / groups of the configs
+// BASELINE.json names (S3DIS 6 / 13, ScanNet 9 / 20, SemanticKITTI 4 / 19; weight_encoding groups 6 / 12)
+#define AOPT_SKINNY_WIDTHS(X) X(3) X(4) X(6) X(9) X(12) X(13) X(19) X(20)
 extern "C" int aopt_skinny_wgrad_supported(int g, int c) {
     if (!bn_width_ok(c)) return 0;
 #define AOPT_CASE(GG) if (g == GG) return 1;

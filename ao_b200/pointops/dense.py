@@ -324,7 +324,7 @@ def _weight_grad(g2: torch.Tensor, xb: torch.Tensor) -> torch.Tensor:
             _lib.check(_lib.load().aopt_skinny_wgrad(rows, g, c, g2.data_ptr(), _DT[g2.dtype], xb.data_ptr(), c, _DT[xb.dtype],
                                                      out.data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream()), "skinny_wgrad")
             return out
-    return _mm_f32(g2.t(), xb) if xb.dtype != torch.float32 else torch.mm(g2.float().t(), xb)
+    return _wgrad_mm(g2.t(), xb) if xb.dtype != torch.float32 else torch.mm(g2.float().t(), xb)
 
 
 def _skinny_ok(g: int, c: int) -> bool:
@@ -332,6 +332,11 @@ def _skinny_ok(g: int, c: int) -> bool:
     if ok is None:
         ok = _SKINNY_OK[(g, c)] = bool(_lib.load().aopt_skinny_wgrad_supported(g, c))
     return ok
+
+
+def _wgrad_mm(gt: torch.Tensor, xb: torch.Tensor) -> torch.Tensor:
+    """gt (out, rows) @ xb (rows, in) with an fp32 result (cuBLAS writes the accumulator; the output is tiny)."""
+    return _mm_f32(gt, xb)
 
 
 class _SkinnyLinearFn(Function):
@@ -538,7 +543,7 @@ class _QkvFn(Function):
             gx = torch.mm(gy, wcat)
             if gx.dtype != ctx.x_dtype:
                 gx = gx.to(ctx.x_dtype)
-        gw = _mm_f32(gy.t(), xb) if dt != torch.float32 else torch.mm(gy.t(), xb)
+        gw = _wgrad_mm(gy.t(), xb) if dt != torch.float32 else torch.mm(gy.t(), xb)
         bq, bk, bv = ctx.biases
         zq = torch.zeros_like(bq) if bq is not None else None          # in front of a training-mode BatchNorm
         zk = torch.zeros_like(bk) if bk is not None else None

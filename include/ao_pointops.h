@@ -325,7 +325,7 @@ int aopt_we_tail_backward(int64_t rows, int g, const float *rel, const float *up
  * aopt_skinny_linear / aopt_skinny_dgrad / aopt_skinny_wgrad: a Linear with a handful (g) of outputs over hundreds of
  *   thousands of rows — weight_encoding[0] applied to key / query (g = groups), the segmentation head (g = num_classes) — and,
  *   with the roles of input and output exchanged, the patch-embedding projection (g = in_channels); w (g, c) fp32,
- *   g in {4, 6, 9, 12, 13, 19, 20} (aopt_skinny_wgrad_supported):
+ *   the first layer of linear_p_bias (g = 3 coordinates); g in {3, 4, 6, 9, 12, 13, 19, 20} (aopt_skinny_wgrad_supported):
  *   out (rows, g) fp32 = x wᵀ (+ bias);  grad_x (rows, c) = grad (rows, g) w;  grad_w (g, c) fp32 = gradᵀ x (workspace
  *   aopt_dense_workspace_bytes(g*c); deterministic). */
 int aopt_col_sum(int64_t rows, int c, const void *x, int64_t ldx, int x_dtype, float *out, void *workspace,

@@ -338,7 +338,7 @@ def test_skinny_linear_forward_backward(g, c, rows, xdt):
         torch.testing.assert_close(b.grad.double(), gy.double().sum(0), rtol=1e-4, atol=1e-3)
 
 
-@pytest.mark.parametrize("cin", [6, 9, 4])
+@pytest.mark.parametrize("cin", [6, 9, 4, 3])
 @pytest.mark.parametrize("autocast", [False, True])
 def test_patch_projection_small_input_width(cin, autocast):
     """Linear(in_channels, 48, bias=False) -> PointBatchNorm -> ReLU on 10^5 rows of raw features (GVAPatchEmbed.proj,

@@ -76,8 +76,9 @@ SIGNATURES = {
                                     c_size_t, P]),
     "aopt_bn_act_backward": (c_int, [c_int64, c_int, P, P, c_int, P, c_int64, c_int, P, P, P, P, c_int64, P, P, P, P, c_size_t, P]),
     "aopt_we_tail_supported": (c_int, [c_int]),
-    "aopt_we_tail_forward": (c_int, [c_int64, c_int, P, P, P, P, P, c_float, P, P, P, P, P, P, c_float, P, P, c_size_t, P]),
-    "aopt_we_tail_backward": (c_int, [c_int64, c_int, P, P, P, P, P, P, P, P, P, P, P, P, P, P, c_size_t, P]),
+    "aopt_we_tail_forward": (c_int, [c_int64, c_int, P, P, P, P, c_int, P, P, P, P, c_float, P, P, P, P, P, P, c_float, P, P,
+                                     c_size_t, P]),
+    "aopt_we_tail_backward": (c_int, [c_int64, c_int, P, P, P, P, c_int, P, P, P, P, P, P, P, P, P, P, P, P, P, c_size_t, P]),
     "aopt_col_sum": (c_int, [c_int64, c_int, P, c_int64, c_int, P, P, c_size_t, P]),
     "aopt_copy_cols": (c_int, [c_int64, c_int, P, c_int64, c_int, P, P, c_int64, c_int, P]),
     "aopt_skinny_wgrad_supported": (c_int, [c_int, c_int]),

@@ -463,17 +463,37 @@ bn_bwd_apply_kernel(long long rows, int c, const OT *__restrict__ grad_out, cons
 }
 
 // ---- weight-encoding tail on (rows, G): u = rel + upe + cst;  logits = W2 · ReLU(BN(u)) + b2 --------------------------
+// First addend of u: either a materialised (rows, G) tensor `rel`, or — gather mode — key / query projections
+// kp, qp (N, G) and the neighbour list: rel[row] = kp[idx[row]] - qp[row / k] (key row = 0 where idx < 0), the G-wide
+// gva_relation formed while loading, so that the (N, k, G) tensor is neither written nor read twice.
+struct TailSrc {
+    const float *rel, *kp, *qp;
+    const int *idx;
+    int k;
+};
+
 template <int G>
 struct TailRow {
     float u[G];
-    __device__ __forceinline__ void load(const float *__restrict__ rel, const float *__restrict__ upe, const float *cst,
-                                         long long row) {
-        const float2 *a = reinterpret_cast<const float2 *>(rel + row * G);
+    __device__ __forceinline__ void load(const TailSrc &src, const float *__restrict__ upe, const float *cst, long long row) {
+        if (src.rel) {
+            const float2 *a = reinterpret_cast<const float2 *>(src.rel + row * G);
 #pragma unroll
-        for (int j = 0; j < G / 2; ++j) {
-            const float2 v = __ldg(a + j);
-            u[2 * j] = v.x;
-            u[2 * j + 1] = v.y;
+            for (int j = 0; j < G / 2; ++j) {
+                const float2 v = __ldg(a + j);
+                u[2 * j] = v.x;
+                u[2 * j + 1] = v.y;
+            }
+        } else {
+            const int jn = __ldg(src.idx + row);
+            const float2 *q = reinterpret_cast<const float2 *>(src.qp + (row / src.k) * G);
+            const float2 *kk = reinterpret_cast<const float2 *>(src.kp + (size_t)max(jn, 0) * G);
+#pragma unroll
+            for (int j = 0; j < G / 2; ++j) {
+                const float2 a = __ldg(kk + j), b = __ldg(q + j);
+                u[2 * j] = (jn >= 0 ? a.x : 0.f) - b.x;
+                u[2 * j + 1] = (jn >= 0 ? a.y : 0.f) - b.y;
+            }
         }
         if (upe) {
             const float2 *b = reinterpret_cast<const float2 *>(upe + row * G);
@@ -493,7 +513,7 @@ struct TailRow {
 
 template <int G>
 __global__ void __launch_bounds__(kDenseBlock)
-we_partial_kernel(long long rows, const float *__restrict__ rel, const float *__restrict__ upe,
+we_partial_kernel(long long rows, TailSrc src, const float *__restrict__ upe,
                   const float *__restrict__ cst, float *__restrict__ partials) {
     __shared__ float s_c[G];
     pdl_trigger();
@@ -505,7 +525,7 @@ we_partial_kernel(long long rows, const float *__restrict__ rel, const float *__
     for (long long row = (long long)blockIdx.x * kDenseBlock + threadIdx.x; row < rows;
          row += (long long)gridDim.x * kDenseBlock) {
         TailRow<G> r;
-        r.load(rel, upe, cst ? s_c : nullptr, row);
+        r.load(src, upe, cst ? s_c : nullptr, row);
 #pragma unroll
         for (int j = 0; j < G; ++j) {
             acc[j] += r.u[j];
@@ -522,7 +542,7 @@ struct TailParams {   // shared-memory copy of the per-channel maps and the G x 
 
 template <int G>
 __global__ void __launch_bounds__(kDenseBlock)
-we_apply_kernel(long long rows, const float *__restrict__ rel, const float *__restrict__ upe,
+we_apply_kernel(long long rows, TailSrc src, const float *__restrict__ upe,
                 const float *__restrict__ cst, const double *__restrict__ sums, double inv_rows, float eps,
                 const float *__restrict__ gamma, const float *__restrict__ beta, const float *__restrict__ w2,
                 const float *__restrict__ b2, float *__restrict__ logits, float *__restrict__ stats_out,
@@ -551,7 +571,7 @@ we_apply_kernel(long long rows, const float *__restrict__ rel, const float *__re
     __syncthreads();
     for (long long row = (long long)blockIdx.x * kDenseBlock + t; row < rows; row += (long long)gridDim.x * kDenseBlock) {
         TailRow<G> r;
-        r.load(rel, upe, cst ? P.cst : nullptr, row);
+        r.load(src, upe, cst ? P.cst : nullptr, row);
         float h[G];
 #pragma unroll
         for (int j = 0; j < G; ++j) h[j] = fmaxf(fmaf(r.u[j] - P.mean[j], P.sc[j], P.beta[j]), 0.f);
@@ -574,7 +594,7 @@ we_apply_kernel(long long rows, const float *__restrict__ rel, const float *__re
 // block keep the per-thread accumulators in registers; slice 0 also owns the three G-wide sums.
 template <int G, int IB>
 __global__ void __launch_bounds__(kDenseBlock)
-we_bwd_partial_kernel(long long rows, const float *__restrict__ rel, const float *__restrict__ upe,
+we_bwd_partial_kernel(long long rows, TailSrc src, const float *__restrict__ upe,
                       const float *__restrict__ cst, const float *__restrict__ grad_logits,
                       const float *__restrict__ stats, const float *__restrict__ gamma, const float *__restrict__ beta,
                       const float *__restrict__ w2, float *__restrict__ partials) {
@@ -599,7 +619,7 @@ we_bwd_partial_kernel(long long rows, const float *__restrict__ rel, const float
     for (int j = 0; j < IB * G; ++j) wacc[j] = 0.f;
     for (long long row = (long long)blockIdx.x * kDenseBlock + t; row < rows; row += (long long)gridDim.x * kDenseBlock) {
         TailRow<G> r;
-        r.load(rel, upe, cst ? P.cst : nullptr, row);
+        r.load(src, upe, cst ? P.cst : nullptr, row);
         float dl[G], h[G];
         const float2 *gp = reinterpret_cast<const float2 *>(grad_logits + row * G);
 #pragma unroll
@@ -641,7 +661,7 @@ we_bwd_partial_kernel(long long rows, const float *__restrict__ rel, const float
 // Backward, pass 2: du = γ·rstd·(dh − mean(dh) − x̂·mean(dh·x̂)); parameter gradients from the reduced sums.
 template <int G>
 __global__ void __launch_bounds__(kDenseBlock)
-we_bwd_apply_kernel(long long rows, const float *__restrict__ rel, const float *__restrict__ upe,
+we_bwd_apply_kernel(long long rows, TailSrc src, const float *__restrict__ upe,
                     const float *__restrict__ cst, const float *__restrict__ grad_logits,
                     const float *__restrict__ stats, const float *__restrict__ gamma, const float *__restrict__ beta,
                     const float *__restrict__ w2, const double *__restrict__ sums, double inv_rows,
@@ -672,7 +692,7 @@ we_bwd_apply_kernel(long long rows, const float *__restrict__ rel, const float *
     __syncthreads();
     for (long long row = (long long)blockIdx.x * kDenseBlock + t; row < rows; row += (long long)gridDim.x * kDenseBlock) {
         TailRow<G> r;
-        r.load(rel, upe, cst ? P.cst : nullptr, row);
+        r.load(src, upe, cst ? P.cst : nullptr, row);
         float dl[G];
         const float2 *gp = reinterpret_cast<const float2 *>(grad_logits + row * G);
 #pragma unroll
@@ -930,7 +950,7 @@ static int bn_backward_t(long long rows, int c, const void *grad_out, const void
 }
 
 template <int G, int IB>
-static int we_forward_t(long long rows, const float *rel, const float *upe, const float *cst, const float *gamma,
+static int we_forward_t(long long rows, TailSrc rel, const float *upe, const float *cst, const float *gamma,
                         const float *beta, float eps, const float *w2, const float *b2, float *logits, float *stats_out,
                         float *running_mean, float *running_var, float momentum, long long *batches_tracked, float *partials,
                         double *sums, cudaStream_t st) {
@@ -947,7 +967,7 @@ static int we_forward_t(long long rows, const float *rel, const float *upe, cons
 }
 
 template <int G, int IB>
-static int we_backward_t(long long rows, const float *rel, const float *upe, const float *cst, const float *grad_logits,
+static int we_backward_t(long long rows, TailSrc rel, const float *upe, const float *cst, const float *grad_logits,
                          const float *stats, const float *gamma, const float *beta, const float *w2, float *grad_u,
                          float *grad_gamma, float *grad_beta, float *grad_b2, float *grad_w2, float *partials, double *sums,
                          cudaStream_t st) {
@@ -1027,13 +1047,20 @@ extern "C" int aopt_bn_act_backward(int64_t rows, int c, const void *grad_out, c
 #undef AOPT_BN_BWD
 }
 
-extern "C" int aopt_we_tail_forward(int64_t rows, int g, const float *rel, const float *upe, const float *cst,
+static bool tail_src_ok(int64_t rows, const float *rel, const float *kp, const float *qp, const int *idx, int nsample) {
+    return rel || (kp && qp && idx && nsample > 0 && rows % nsample == 0);
+}
+
+extern "C" int aopt_we_tail_forward(int64_t rows, int g, const float *rel_in, const float *kp, const float *qp, const int *idx,
+                                    int nsample, const float *upe, const float *cst,
                                     const float *gamma, const float *beta, float eps, const float *w2, const float *b2,
                                     float *logits, float *stats_out, float *running_mean, float *running_var,
                                     float momentum, long long *batches_tracked, void *workspace, size_t workspace_bytes,
                                     aopt_stream_t stream) {
-    if (rows <= 0 || !rel || !gamma || !beta || !w2 || !logits || !stats_out) return AOPT_ERR_INVALID_ARGUMENT;
+    if (rows <= 0 || !tail_src_ok(rows, rel_in, kp, qp, idx, nsample) || !gamma || !beta || !w2 || !logits || !stats_out)
+        return AOPT_ERR_INVALID_ARGUMENT;
     if (!aopt_we_tail_supported(g)) return AOPT_ERR_UNSUPPORTED;
+    const TailSrc rel = {rel_in, kp, qp, idx, nsample};
     float *partials;
     double *sums;
     if (!carve_dense(workspace, workspace_bytes, 3 * g + g * g, &partials, &sums)) return AOPT_ERR_WORKSPACE;
@@ -1045,14 +1072,16 @@ extern "C" int aopt_we_tail_forward(int64_t rows, int g, const float *rel, const
                                momentum, batches_tracked, partials, sums, st);
 }
 
-extern "C" int aopt_we_tail_backward(int64_t rows, int g, const float *rel, const float *upe, const float *cst,
+extern "C" int aopt_we_tail_backward(int64_t rows, int g, const float *rel_in, const float *kp, const float *qp, const int *idx,
+                                     int nsample, const float *upe, const float *cst,
                                      const float *grad_logits, const float *stats, const float *gamma, const float *beta,
                                      const float *w2, float *grad_u, float *grad_gamma, float *grad_beta, float *grad_b2,
                                      float *grad_w2, void *workspace, size_t workspace_bytes, aopt_stream_t stream) {
-    if (rows <= 0 || !rel || !grad_logits || !stats || !gamma || !beta || !w2 || !grad_u || !grad_gamma || !grad_beta ||
-        !grad_b2 || !grad_w2)
+    if (rows <= 0 || !tail_src_ok(rows, rel_in, kp, qp, idx, nsample) || !grad_logits || !stats || !gamma || !beta || !w2 ||
+        !grad_u || !grad_gamma || !grad_beta || !grad_b2 || !grad_w2)
         return AOPT_ERR_INVALID_ARGUMENT;
     if (!aopt_we_tail_supported(g)) return AOPT_ERR_UNSUPPORTED;
+    const TailSrc rel = {rel_in, kp, qp, idx, nsample};
     float *partials;
     double *sums;
     if (!carve_dense(workspace, workspace_bytes, 3 * g + g * g, &partials, &sums)) return AOPT_ERR_WORKSPACE;

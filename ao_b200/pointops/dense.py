@@ -186,69 +186,112 @@ def bn_act(x: torch.Tensor, bn: torch.nn.Module, relu: bool = False, residual: t
 
 
 class _WeTailFn(Function):
+    """rel is either the materialised (N, k, G) tensor (kp = qp = idx = None) or None (gather mode: rel = kp[idx] - qp)."""
+
     @staticmethod
-    def forward(ctx, rel, upe, cst, gamma, beta, w2, b2, running_mean, running_var, momentum, eps, tracked):
+    def forward(ctx, rel, kp, qp, idx, upe, cst, gamma, beta, w2, b2, running_mean, running_var, momentum, eps, tracked):
         lib = _lib.load()
-        dev = rel.device
-        g = rel.shape[-1]
-        rows = rel.numel() // g
-        logits = torch.empty_like(rel)
+        src = rel if rel is not None else kp
+        dev = src.device
+        g = src.shape[-1]
+        shape = tuple(rel.shape) if rel is not None else (idx.shape[0], idx.shape[1], g)
+        nsample = shape[-2] if len(shape) >= 2 else 1
+        rows = 1
+        for d in shape[:-1]:
+            rows *= d
+        logits = torch.empty(shape, dtype=torch.float32, device=dev)
         stats = torch.empty(2 * g, dtype=torch.float32, device=dev)
         with _lib.on_device(dev):
             ws = _dense_ws(3 * g + g * g, dev)
             _lib.check(
-                lib.aopt_we_tail_forward(rows, g, rel.data_ptr(), _lib.ptr(upe), _lib.ptr(cst), gamma.data_ptr(),
-                                         beta.data_ptr(), eps, w2.data_ptr(), _lib.ptr(b2), logits.data_ptr(),
-                                         stats.data_ptr(), _lib.ptr(running_mean), _lib.ptr(running_var), momentum,
-                                         _lib.ptr(tracked), ws.data_ptr(), ws.numel(), _lib.stream()),
+                lib.aopt_we_tail_forward(rows, g, _lib.ptr(rel), _lib.ptr(kp), _lib.ptr(qp), _lib.ptr(idx), nsample, _lib.ptr(upe),
+                                         _lib.ptr(cst), gamma.data_ptr(), beta.data_ptr(), eps, w2.data_ptr(), _lib.ptr(b2),
+                                         logits.data_ptr(), stats.data_ptr(), _lib.ptr(running_mean), _lib.ptr(running_var),
+                                         momentum, _lib.ptr(tracked), ws.data_ptr(), ws.numel(), _lib.stream()),
                 "we_tail_forward")
-        ctx.save_for_backward(rel, upe, cst, gamma, beta, w2, stats)
+        ctx.save_for_backward(rel, kp, qp, upe, cst, gamma, beta, w2, stats)
+        ctx.idx = idx
+        ctx.meta = (rows, g, nsample, shape)
         ctx.has_b2 = b2 is not None
         return logits
 
     @staticmethod
     def backward(ctx, grad_logits):
         lib = _lib.load()
-        rel, upe, cst, gamma, beta, w2, stats = ctx.saved_tensors
-        dev = rel.device
-        g = rel.shape[-1]
-        rows = rel.numel() // g
+        rel, kp, qp, upe, cst, gamma, beta, w2, stats = ctx.saved_tensors
+        idx = ctx.idx
+        rows, g, nsample, shape = ctx.meta
+        dev = grad_logits.device
         grad_logits = grad_logits.float().contiguous()
-        gu = torch.empty_like(rel)
+        gu = torch.empty(shape, dtype=torch.float32, device=dev)
         gg, gb, gb2 = (torch.empty(g, dtype=torch.float32, device=dev) for _ in range(3))
         gw2 = torch.empty((g, g), dtype=torch.float32, device=dev)
+        gkp = gqp = None
         with _lib.on_device(dev):
             ws = _dense_ws(3 * g + g * g, dev)
             _lib.check(
-                lib.aopt_we_tail_backward(rows, g, rel.data_ptr(), _lib.ptr(upe), _lib.ptr(cst), grad_logits.data_ptr(),
-                                          stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), w2.data_ptr(), gu.data_ptr(),
-                                          gg.data_ptr(), gb.data_ptr(), gb2.data_ptr(), gw2.data_ptr(), ws.data_ptr(),
-                                          ws.numel(), _lib.stream()),
+                lib.aopt_we_tail_backward(rows, g, _lib.ptr(rel), _lib.ptr(kp), _lib.ptr(qp), _lib.ptr(idx), nsample, _lib.ptr(upe),
+                                          _lib.ptr(cst), grad_logits.data_ptr(), stats.data_ptr(), gamma.data_ptr(),
+                                          beta.data_ptr(), w2.data_ptr(), gu.data_ptr(), gg.data_ptr(), gb.data_ptr(),
+                                          gb2.data_ptr(), gw2.data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream()),
                 "we_tail_backward")
+            if rel is None and (ctx.needs_input_grad[1] or ctx.needs_input_grad[2]):
+                # gather mode: grad_u scattered back to the key projection (CSR walk) and summed over k for the query
+                # projection in one pass (aopt_relation_backward, the G-wide backward of gva_relation)
+                from ._csr import get_csr
+
+                n = kp.shape[0]
+                csr = get_csr(idx, n, 0)
+                gkp = torch.empty((n, g), dtype=torch.float32, device=dev)
+                gqp = torch.empty((n, g), dtype=torch.float32, device=dev)
+                _lib.check(lib.aopt_relation_backward(n, nsample, g, gu.data_ptr(), csr.rowptr.data_ptr(), csr.perm.data_ptr(),
+                                                      gkp.data_ptr(), gqp.data_ptr(), _lib.stream()), "relation_backward")
         # cst sits in front of a training-mode BatchNorm: its gradient (the column sums of grad_u) is identically zero
-        gcst = torch.zeros_like(cst) if (cst is not None and ctx.needs_input_grad[2]) else None
-        return (gu, gu if upe is not None else None, gcst, gg, gb, gw2, gb2 if ctx.has_b2 else None,
-                None, None, None, None, None)
+        gcst = torch.zeros_like(cst) if (cst is not None and ctx.needs_input_grad[5]) else None
+        return (gu if rel is not None else None, gkp, gqp, None, gu if upe is not None else None, gcst, gg, gb, gw2,
+                gb2 if ctx.has_b2 else None, None, None, None, None, None)
 
 
-def we_tail_usable(rel: torch.Tensor, bn: torch.nn.Module) -> bool:
+def we_tail_usable(rel: torch.Tensor, bn: torch.nn.Module, rows: int = None) -> bool:
+    """rel: the (…, G) first addend — or, for gather mode, the (N, G) key projection with rows = N·k."""
     bn = getattr(bn, "norm", bn)
+    if rows is None:
+        rows = rel.numel() // rel.shape[-1]
     return (fused_dense_enabled() and rel.is_cuda and rel.dtype == torch.float32 and (bn.training or not bn.track_running_stats)
-            and bn.weight is not None and rel.numel() // rel.shape[-1] >= 2 and we_tail_supported(rel.shape[-1]))
+            and bn.weight is not None and rows >= 2 and we_tail_supported(rel.shape[-1]))
 
 
-def we_tail(rel: torch.Tensor, upe: torch.Tensor, cst: torch.Tensor, bn: torch.nn.Module, lin: torch.nn.Linear) -> torch.Tensor:
+def we_tail(rel: torch.Tensor, upe: torch.Tensor, cst: torch.Tensor, bn: torch.nn.Module, lin: torch.nn.Linear,
+            gather=None) -> torch.Tensor:
     """logits = lin(ReLU(bn(rel + upe + cst))) with `bn` / `lin` = weight_encoding[1] / weight_encoding[3]; rel, upe
-    (..., G) fp32, cst (G) or None.  Training-mode statistics only (check with we_tail_usable); G in {6, 12}."""
+    (..., G) fp32, cst (G) or None.  Training-mode statistics only (check with we_tail_usable); G in {6, 12}.
+    gather = (kp, qp, idx) with rel = None: rel = kp[idx] - qp[:, None] ((N, G) key / query projections, idx (N, k), the
+    G-wide gva_relation) is formed inside the kernels and never stored; gradients flow to kp and qp."""
     bn = getattr(bn, "norm", bn)
-    _lib.require_cuda(rel, lin.weight)
-    if not we_tail_usable(rel, bn):
+    kp = qp = idx = None
+    if gather is not None:
+        if rel is not None:
+            raise ValueError("we_tail: pass either rel or gather=(kp, qp, idx)")
+        kp, qp, idx = gather
+        _lib.require_cuda(kp, qp, idx, lin.weight)
+        if idx.dtype != torch.int32 or not idx.is_contiguous():
+            idx = idx.int().contiguous()
+        kp, qp = kp.float().contiguous(), qp.float().contiguous()
+        if kp.shape != qp.shape or idx.shape[0] != qp.shape[0] or idx.dim() != 2:
+            raise ValueError("we_tail: gather mode needs kp, qp (N, G) and idx (N, k) of one point set")
+        first, rows = kp, idx.numel()
+        shape = (idx.shape[0], idx.shape[1], kp.shape[1])
+    else:
+        _lib.require_cuda(rel, lin.weight)
+        rel = rel.contiguous()
+        first, rows = rel, None
+        shape = rel.shape
+    if not we_tail_usable(first, bn, rows):
         raise ValueError("we_tail: unsupported input (see we_tail_usable)")
-    g = rel.shape[-1]
-    rel = rel.contiguous()
+    g = first.shape[-1]
     if upe is not None:
         upe = upe.float().contiguous()
-        if upe.shape != rel.shape:
+        if tuple(upe.shape) != tuple(shape):
             raise ValueError("we_tail: upe must have rel's shape")
     if cst is not None:
         cst = cst.float().contiguous()
@@ -257,9 +300,9 @@ def we_tail(rel: torch.Tensor, upe: torch.Tensor, cst: torch.Tensor, bn: torch.n
     track = bn.training and bn.track_running_stats
     momentum, tracked = _momentum(bn, track)
     f = lambda t: t if t.dtype == torch.float32 and t.is_contiguous() else t.float().contiguous()
-    return _WeTailFn.apply(rel, upe, cst, f(bn.weight), f(bn.bias), f(lin.weight), None if lin.bias is None else f(lin.bias),
-                           bn.running_mean if track else None, bn.running_var if track else None, momentum,
-                           float(bn.eps), tracked)
+    return _WeTailFn.apply(rel, kp, qp, idx, upe, cst, f(bn.weight), f(bn.bias), f(lin.weight),
+                           None if lin.bias is None else f(lin.bias), bn.running_mean if track else None,
+                           bn.running_var if track else None, momentum, float(bn.eps), tracked)
 
 
 # ---- autocast Linear with cached low-precision weights ------------------------------------------------------------------

@@ -50,6 +50,16 @@ def fused_pe_enabled() -> bool:
     return torch.is_autocast_enabled()
 
 
+def we_gather_enabled() -> bool:
+    """AOPT_WE_GATHER=1: pointops.we_tail forms rel = kp[idx] - qp inside its kernels (gather mode) instead of reading the
+    (N,k,G) tensor gva_relation stored.  Off: the four passes of the tail (two forward, two backward) each repeat the
+    24-byte row gathers and a division per row, which costs more than the one store it saves — we_tail backward 172 ->
+    305 us at level 0, training step 32.6 -> 33.5 ms (profiles/r03h_model_step.txt)."""
+    import os
+
+    return os.environ.get("AOPT_WE_GATHER", "0") == "1"
+
+
 def relation_free_min_elems() -> float:
     """Smallest N·k·C for which the relation-free schedule is also used at the widths the fused positional-MLP kernel
     does not cover (C = 192, 384: hidden activation through cuBLAS + bn_act, one more GEMM for `upe`).  It trades the
@@ -236,6 +246,12 @@ class GroupedVectorAttention(nn.Module):
             if lin2.bias is not None:
                 cb = F.linear(lin2.bias.float(), we)
                 const = cb if const is None else const + cb
+            if (we_gather_enabled() and kp.shape[0] == reference_index.shape[0]
+                    and pointops.we_tail_usable(kp, self.weight_encoding[1], reference_index.numel())):
+                # opt-in: the G-wide relation gathered inside the tail kernels instead of stored once (measured slower)
+                weight = pointops.we_tail(None, upe, const, self.weight_encoding[1], self.weight_encoding[3],
+                                          gather=(kp, qp, reference_index))
+                return pointops.gva_aggregate(value, peb, weight, reference_index, self.groups)
             rel = pointops.gva_relation(kp, qp, reference_index)              # (N, k, G)
             if pointops.we_tail_usable(rel, self.weight_encoding[1]):
                 # u = rel + upe + const = weight_encoding[0](relation_qk); BN(G), ReLU, Linear(G,G) in one operator

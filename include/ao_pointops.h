@@ -304,16 +304,19 @@ int aopt_bn_act_backward(int64_t rows, int c, const void *grad_out, const void *
                          size_t workspace_bytes, aopt_stream_t stream);
 /* Tail of GroupedVectorAttention.weight_encoding (point_transformer_v2m2_base.py:94-99,120) on the (rows = N*nsample, g)
  * tensors:  u = rel + upe + cst  (upe (rows, g) and cst (g) optional),  logits = W2 * ReLU(BatchNorm_train(u)) + b2.
- * g in {6, 12} (aopt_we_tail_supported); w2 (g, g) row-major [out][in]; b2 optional; stats_out (2g) = mean | rstd. */
+ * g in {6, 12} (aopt_we_tail_supported); w2 (g, g) row-major [out][in]; b2 optional; stats_out (2g) = mean | rstd.
+ * rel == NULL selects gather mode: rel[row] = kp[idx[row]] - qp[row / nsample] (kp, qp (N, g); idx (N, nsample), key row = 0
+ * where idx < 0; rows = N * nsample) is formed while loading — the g-wide aopt_gather_sub_forward folded in. */
 int aopt_we_tail_supported(int g);
-int aopt_we_tail_forward(int64_t rows, int g, const float *rel, const float *upe, const float *cst, const float *gamma,
+int aopt_we_tail_forward(int64_t rows, int g, const float *rel, const float *kp, const float *qp, const int *idx,
+                         int nsample, const float *upe, const float *cst, const float *gamma,
                          const float *beta, float eps, const float *w2, const float *b2, float *logits, float *stats_out,
                          float *running_mean, float *running_var, float momentum, long long *batches_tracked,
                          void *workspace, size_t workspace_bytes, aopt_stream_t stream);
 /* grad_u (rows, g) is the gradient of rel and of upe alike (the gradient of cst is identically zero: it sits in
  * front of a training-mode BatchNorm).  grad_w2 (g, g), grad_b2 / grad_gamma / grad_beta (g).  Deterministic. */
-int aopt_we_tail_backward(int64_t rows, int g, const float *rel, const float *upe, const float *cst,
-                          const float *grad_logits, const float *stats, const float *gamma, const float *beta,
+int aopt_we_tail_backward(int64_t rows, int g, const float *rel, const float *kp, const float *qp, const int *idx,
+                          int nsample, const float *upe, const float *cst, const float *grad_logits, const float *stats, const float *gamma, const float *beta,
                           const float *w2, float *grad_u, float *grad_gamma, float *grad_beta, float *grad_b2,
                           float *grad_w2, void *workspace, size_t workspace_bytes, aopt_stream_t stream);
 

@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, call 3B: split-K (bf16-result) weight gradients for the huge-K products: tests, model step at 4 / 8 rooms, profile
-TAG=${1:-r03g}
+TAG=${1:-r03h}
 O=gpurun_out/$TAG
 mkdir -p $O
 timeout 900 python -m pytest tests/test_dense_gpu.py tests/test_modules_gpu.py -q -x --timeout 600 -p no:cacheprovider > $O/pytest.log 2>&1; echo "tests exit: $?"; tail -2 $O/pytest.log

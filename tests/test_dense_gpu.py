@@ -361,3 +361,32 @@ def test_patch_projection_small_input_width(cin, autocast):
     ga, gb = seq[0].weight.grad, ref[0].weight.grad
     # under autocast the torch reference returns this gradient rounded to bf16 (3 significant digits)
     assert float((ga - gb).norm() / gb.norm()) < (6e-2 if autocast else 1e-3)
+
+
+@pytest.mark.parametrize("g", [6, 12])
+def test_we_tail_gather_mode_equals_materialised_relation(g):
+    """we_tail(gather=(kp, qp, idx)) forms rel = kp[idx] - qp inside the kernels: same bits as gva_relation followed by
+    we_tail on the stored tensor, forward and backward, -1 padding included."""
+    from ao_b200 import pointops, scenes
+
+    coord_np, _, off_np = scenes.small_batch(seed=g, sizes=(4000, 9, 3000))       # a scene with 9 < k points: -1 padding
+    coord, offset = torch.from_numpy(coord_np).to(DEV), torch.from_numpy(off_np).to(DEV).int()
+    idx, _ = pointops.knn_query(16, coord, offset)
+    assert int((idx < 0).sum()) > 0
+    n = coord.shape[0]
+    torch.manual_seed(g)
+    bn_a, lin_a = nn.BatchNorm1d(g).to(DEV), nn.Linear(g, g).to(DEV)
+    bn_b, lin_b = nn.BatchNorm1d(g).to(DEV), nn.Linear(g, g).to(DEV)
+    bn_b.load_state_dict(bn_a.state_dict()); lin_b.load_state_dict(lin_a.state_dict())
+    kp, qp = torch.randn(n, g, device=DEV, requires_grad=True), torch.randn(n, g, device=DEV, requires_grad=True)
+    upe = torch.randn(n, 16, g, device=DEV, requires_grad=True)
+    cst = torch.randn(g, device=DEV)
+    kp2, qp2, upe2 = (t.detach().clone().requires_grad_(True) for t in (kp, qp, upe))
+    a = pointops.we_tail(None, upe, cst, bn_a, lin_a, gather=(kp, qp, idx))
+    b = pointops.we_tail(pointops.gva_relation(kp2, qp2, idx), upe2, cst, bn_b, lin_b)
+    assert torch.equal(a, b)
+    gl = torch.randn_like(a)
+    a.backward(gl); b.backward(gl)
+    assert torch.equal(kp.grad, kp2.grad) and torch.equal(qp.grad, qp2.grad) and torch.equal(upe.grad, upe2.grad)
+    assert torch.equal(lin_a.weight.grad, lin_b.weight.grad) and torch.equal(bn_a.weight.grad, bn_b.weight.grad)
+    assert torch.equal(bn_a.running_var, bn_b.running_var)

@@ -57,27 +57,6 @@ __device__ __forceinline__ void st4<__nv_bfloat16>(__nv_bfloat16 *p, const float
 }
 
 // ---- reductions ---------------------------------------------------------------------------------------------------
-// Threads of a CTA that own the same column chunk (t, t + cols, t + 2 cols, ...) are summed in that order by the
-// first `cols` threads; partial row = [ A (c floats) | B (c floats) ].
-__device__ __forceinline__ void column_reduce_store(const float4 &a, const float4 &b, int cols, int c, int col,
-                                                    float *__restrict__ partial_row) {
-    __shared__ float4 sh[2][kDenseBlock];
-    const int t = threadIdx.x;
-    sh[0][t] = a;
-    sh[1][t] = b;
-    __syncthreads();
-    if (t < cols) {
-        float4 A = sh[0][t], B = sh[1][t];
-        for (int u = t + cols; u < kDenseBlock; u += cols) {
-            const float4 x = sh[0][u], y = sh[1][u];
-            A.x += x.x; A.y += x.y; A.z += x.z; A.w += x.w;
-            B.x += y.x; B.y += y.y; B.z += y.z; B.w += y.w;
-        }
-        *reinterpret_cast<float4 *>(partial_row + 4 * col) = A;
-        *reinterpret_cast<float4 *>(partial_row + c + 4 * col) = B;
-    }
-}
-
 // NV per-thread values -> one row of NV floats per CTA (warp shuffles, then the warps in order).
 template <int NV>
 __device__ __forceinline__ void block_reduce_store(float (&v)[NV], float *__restrict__ partial_row) {

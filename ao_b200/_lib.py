@@ -60,6 +60,7 @@ SIGNATURES = {
     "aopt_interp_weights": (c_int, [c_int, c_int, P, P, P]),
     "aopt_interpolation_forward": (c_int, [c_int, c_int, c_int, c_int, P, P, P, P, P]),
     "aopt_interpolation_backward": (c_int, [c_int, c_int, c_int, P, P, P, P, P, P]),
+    "aopt_vote_accumulate": (c_int, [c_int, c_int, c_longlong, P, P, P, P, P]),
     "aopt_pe_mlp_supported": (c_int, [c_int]),
     "aopt_pos_moments_workspace_bytes": (c_size_t, []),
     "aopt_pos_moments": (c_int, [c_int64, P, P, P, c_size_t, P]),

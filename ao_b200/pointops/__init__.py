@@ -6,7 +6,7 @@ Names outside the hot path (ball_query, random_ball_query, farthest_point_sampli
 attention_*_step, ball_query_and_group) exist but raise NotImplementedError.
 New fused operators for the PTv2 caller: group_xyz, gva_relation, gva_aggregate, grid_pool,
 voxel_partition, unpool_map, interpolation_weights, knn_query_raw, pe_bias_mlp (fused positional-bias MLP),
-pos_moments, bn_act (training-mode BatchNorm + ReLU / DropPath / residual on (rows, C)), we_tail (weight-encoding tail).
+pos_moments, vote_accumulate (the tester's softmax + fragment vote), bn_act (training-mode BatchNorm + ReLU / DropPath / residual on (rows, C)), we_tail (weight-encoding tail).
 """
 from .query import knn_query, knn_query_raw, knn_query_sets, prefetch_knn, ball_query, random_ball_query
 from .sampling import farthest_point_sampling
@@ -32,3 +32,4 @@ from .utils import (
 from .pe_mlp import pe_bias_mlp, pe_mlp_supported, pos_moments
 from .dense import linear, linear_bn_act, col_sum, qkv_bn, qkv_usable, bn_act, bn_act_supported, bn_act_usable, bn_fusable, we_tail, we_tail_supported, we_tail_usable, fused_dense_enabled
 from ._csr import get_csr, build_csr, prefetch_csr
+from .vote import vote_accumulate

@@ -30,6 +30,7 @@
  *   aopt_interp_weights                   libs/pointops/functions/interpolation.py:15-17
  *   aopt_grid_sample_keys, aopt_voxel_pick, aopt_sphere_dist2, aopt_select_rows
  *                                         pointcept/datasets/transform.py:792-896,968-979 (GridSample, SphereCrop)
+ *   aopt_vote_accumulate                  pointcept/engines/test.py:106-113 (tester: softmax + fragment vote)
  *   aopt_csr_build                        (new) transpose of the neighbour graph → atomic-free backward
  */
 #ifndef AO_POINTOPS_H_
@@ -228,6 +229,15 @@ int aopt_pool_forward(int n_vox, int c, const float *feat, const float *coord, c
 /* grad_feat[i,ch] = grad_out[cluster[i],ch] if argmax[cluster[i],ch] == i else 0. */
 int aopt_pool_backward(int n, int c, const float *grad_out, const int *argmax, const int *cluster,
                        float *grad_feat, aopt_stream_t stream);
+
+/* ---- tester fragment vote ------------------------------------------------------------------ */
+/* pred[index[r], :] += softmax(logits[r, :]) for r in [0, rows): the per-fragment accumulation of
+ * pointcept/engines/test.py:106-113 (F.softmax, then `pred[idx_part[bs:be], :] += pred_part[bs:be]`) in one
+ * kernel.  logits (rows, c) fp32, index (rows) int64 with DISTINCT values inside one call (one fragment; negative
+ * values wrap like a python index), pred (n_pred, c) fp32 updated in place.  *bad_flag (optional, device int) is
+ * set to 1 if an index falls outside [-n_pred, n_pred); such rows are skipped. */
+int aopt_vote_accumulate(int rows, int c, long long n_pred, const float *logits, const long long *index,
+                         float *pred, int *bad_flag, aopt_stream_t stream);
 
 /* ---- three-NN inverse-distance interpolation ---------------------------------------------- */
 /* weight[n,i] = r_i / sum_j r_j,  r = 1/(sqrt(dist2)+1e-8)  (interpolation.py:15-17). */

@@ -15,6 +15,7 @@ Each function cites the reference lines it follows (paths relative to /root/refe
                        NOT vendored and NOT pinned by the reference (no requirements file) →
                        "parity unpinned" for those two; restated from their published semantics
                        and anchored on the call sites above.
+  vote_accumulate      pointcept/engines/test.py:106-113 (tester: softmax + per-fragment indexed add)
   aggregation (PTv1)   libs/pointops/src/aggregation/aggregation_cuda_kernel.cu:5-39
   subtraction          libs/pointops/src/subtraction/subtraction_cuda_kernel.cu:5-30
 
@@ -221,6 +222,21 @@ def interpolation2_apply(inp, idx, weight):
     for i in range(idx.shape[1]):
         out = out + inp[idx[:, i].long(), :] * weight[:, i].unsqueeze(-1)
     return out
+
+
+# ----------------------------------------------------------------------------------------------
+# tester fragment vote: pointcept/engines/test.py:106-113
+# ----------------------------------------------------------------------------------------------
+def vote_accumulate(pred, logits, index, offset):
+    """The tester's loop, verbatim in structure: softmax over the classes, then one indexed `+=` per fragment."""
+    import torch.nn.functional as F
+
+    pred_part = F.softmax(logits, -1)                        # :107
+    bs = 0
+    for be in offset:                                        # :110-113
+        pred[index[bs:be], :] += pred_part[bs:be]
+        bs = be
+    return pred
 
 
 # ----------------------------------------------------------------------------------------------

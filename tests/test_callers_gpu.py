@@ -2,6 +2,7 @@
 site uses the package, on CUDA tensors, and checked against the oracle.
 
   evaluator        pointcept/engines/hooks/evaluator.py:125-131     k = 1 cross-set kNN, pred[idx]
+  tester vote      pointcept/engines/test.py:106-113                softmax + per-fragment `pred[index] += prob`
   MSC matching     pointcept/models/masked_scene_contrast/masked_scene_contrast_v1m1_base.py:144-153
   PTv1 layer       pointcept/models/point_transformer/point_transformer_seg.py:47-60   knn_query_and_group x2
   PTv1 down        …/point_transformer_seg.py:94-111    farthest_point_sampling + knn_query_and_group
@@ -131,3 +132,54 @@ def test_cac_feature_backbone_num_classes_zero():
     assert out.shape == (coord.shape[0], cfg["dec_channels"][0])
     out.square().mean().backward()
     assert all(p.grad is None or torch.isfinite(p.grad).all() for p in model.parameters())
+
+
+@pytest.mark.parametrize("classes", [13, 20, 19, 1, 40])
+def test_tester_fragment_vote(oracle, classes):
+    """engines/test.py:106-113: pred_part = softmax(logits); for every fragment of the batch
+    pred[idx_part[bs:be], :] += pred_part[bs:be].  Fragments come from the test-mode GridSample
+    (transform.py:834-837): fragment i takes point (i mod count) of every voxel, so indices are distinct inside a
+    fragment and the same point is voted for by several fragments.  Tolerance: fp32, rtol 1e-6 / atol 1e-7 against
+    the torch ops on the same GPU (same expf, the class sum in a different order)."""
+    from ao_b200 import pointops
+
+    rng = np.random.default_rng(100 + classes)
+    n_pred, n_vox, n_frag = 5000, 1200, 5
+    voxel_of = rng.integers(0, n_vox, n_pred)
+    order = np.argsort(voxel_of, kind="stable")
+    count = np.bincount(voxel_of, minlength=n_vox)
+    keep = count > 0
+    starts = np.cumsum(np.insert(count, 0, 0)[:-1])
+    frags = [order[(starts + i % np.maximum(count, 1))[keep]] for i in range(n_frag)]
+    index = np.concatenate(frags).astype(np.int64)
+    offset = np.cumsum([len(f) for f in frags])
+    for f in frags:
+        assert len(np.unique(f)) == len(f)
+    logits = (rng.normal(0, 4, (len(index), classes))).astype(np.float32)
+    lg, ix = to_cuda(logits, index)
+    pred = torch.zeros(n_pred, classes, device="cuda")
+    ref = torch.zeros(n_pred, classes, device="cuda")
+    for _ in range(2):                                   # two batches into the same accumulator (:102-113)
+        out = pointops.vote_accumulate(pred, lg, ix, torch.from_numpy(offset))
+        oracle.vote_accumulate(ref, lg, ix, offset.tolist())
+    assert out is pred
+    assert torch.allclose(pred, ref, rtol=1e-6, atol=1e-7)
+    votes = np.bincount(index, minlength=n_pred) * 2
+    assert torch.allclose(pred.sum(1).cpu(), torch.from_numpy(votes).float(), atol=1e-4)   # every vote sums to 1
+    assert torch.equal(pred.argmax(1)[votes > 0], ref.argmax(1)[votes > 0])
+    # one fragment (offset=None), int32 index, bf16 logits (upcast like .float()), negative (wrapping) index
+    one = torch.zeros(n_pred, classes, device="cuda")
+    pointops.vote_accumulate(one, lg[: offset[0]].bfloat16(), ix[: offset[0]].int())
+    ref1 = torch.zeros(n_pred, classes, device="cuda")
+    oracle.vote_accumulate(ref1, lg[: offset[0]].bfloat16().float(), ix[: offset[0]], [int(offset[0])])
+    assert torch.allclose(one, ref1, rtol=1e-6, atol=1e-7)
+    neg = torch.zeros(4, classes, device="cuda")
+    pointops.vote_accumulate(neg, lg[:1], torch.tensor([-1], device="cuda"))
+    assert float(neg[3].sum()) == pytest.approx(1.0, abs=1e-6) and float(neg[:3].abs().sum()) == 0.0
+    with pytest.raises(IndexError):
+        pointops.vote_accumulate(neg, lg[:1], torch.tensor([4], device="cuda"), check_index=True)
+    assert float(neg[:3].abs().sum()) == 0.0
+    # empty fragment list / empty batch
+    pointops.vote_accumulate(neg, lg[:0], ix[:0])
+    with pytest.raises(ValueError):
+        pointops.vote_accumulate(neg, lg[:2], ix[:1])

@@ -25,6 +25,7 @@ enum Tuning { kTuneCsrImpl = 0,   // AOPT_CSR_IMPL:   1 = radix sort, 2 = count 
               kTuneKnnPend = 4,   // AOPT_KNN_PEND:   1 = per-lane pending list in the GRID query kernel (K >= 8), 0 / 2 = insert in place (default)
               kTuneKnnSample = 5, // AOPT_KNN_SAMPLE: 1 = cell edge from the bounding box (no density sample), 0 / 2 = sampled r_k (default)
               kTunePdl = 6,       // AOPT_PDL:        1 = programmatic dependent launch inside the small-kernel chains, 2 = off
+              kTuneL2Prefetch = 7, // AOPT_L2PF:     0 / 1 = the GVA kernels request the next work item's (k,C) peb block into L2 with a bulk prefetch (default), 2 = off
               kTuneCount = 8 };
 int tuning(int which);
 
@@ -54,6 +55,13 @@ inline void launch_chain(bool pdl, void (*kernel)(KArgs...), int grid, int block
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// Bulk L2 prefetch (SASS UBLKPF.L2): `bytes` (a multiple of 16) from a 16-byte aligned global address are requested into L2
+// by the copy engine — no LSU traffic, no destination, no completion to wait for.  The address is warp-uniform in hardware:
+// ptxas wraps a per-lane address in a loop over the active lanes, so call it from a few lanes per warp only.
+__device__ __forceinline__ void l2_prefetch_bulk(const void *p, unsigned bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 
 inline cudaStream_t as_stream(aopt_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }

@@ -156,7 +156,7 @@ template <int GL, int NS, bool HAS_PEB>
 __global__ void __launch_bounds__(ns_block<NS>())
 gva_forward_ns_kernel(long long n, int c, int g, const float *__restrict__ value,
                       const float *__restrict__ peb, const float *__restrict__ logits,
-                      const int *__restrict__ idx, float *__restrict__ out, float *__restrict__ prob) {
+                      const int *__restrict__ idx, float *__restrict__ out, float *__restrict__ prob, int pf) {
     constexpr int BLK = ns_block<NS>();
     extern __shared__ float4 stage[];  // [2*NS][BLK]: value pieces, then peb pieces
     float4 *sv = stage + threadIdx.x;
@@ -188,7 +188,14 @@ gva_forward_ns_kernel(long long n, int c, int g, const float *__restrict__ value
         float e[NS];
 #pragma unroll
         for (int s = 0; s < NS; ++s) e[s] = __ldg(lg + (size_t)s * g);
-        if (t + step < total) load_idx_row16(idx + (size_t)((t + step) / chunks) * NS, jn, NS / 4);
+        if (t + step < total) {
+            const long long ptn = (t + step) / chunks;
+            load_idx_row16(idx + (size_t)ptn * NS, jn, NS / 4);
+            // tuning "l2pf": the NEXT item's peb block (NS·c floats, contiguous per point) is requested into L2 now, by the lane
+            // that owns the point's first chunk; its cp.async copies one iteration later are L2 hits.  Neutral here (the
+            // forward is at 93 % of the HBM peak either way), kept for symmetry with the fused backward, where it pays.
+            if (HAS_PEB && pf && t + step == ptn * chunks) l2_prefetch_bulk(peb + (size_t)ptn * NS * c, (unsigned)(NS * c * 4));
+        }
         float mx = -INFINITY;
 #pragma unroll
         for (int s = 0; s < NS; ++s) mx = fmaxf(mx, e[s]);
@@ -381,7 +388,7 @@ gva_backward_fused_ns_kernel(long long n, int c, int g, const float *__restrict_
                              const float *__restrict__ prob, const int *__restrict__ idx,
                              const int *__restrict__ rowptr, const int *__restrict__ perm,
                              float *__restrict__ grad_peb, float *__restrict__ grad_logits,
-                             float *__restrict__ grad_value) {
+                             float *__restrict__ grad_value, int pf) {
     constexpr int BLK = ns_block<NS>();
     extern __shared__ float4 stage[];
     constexpr int B = kFusedBatch;
@@ -434,7 +441,18 @@ gva_backward_fused_ns_kernel(long long n, int c, int g, const float *__restrict_
 #pragma unroll
         for (int s = 0; s < NS; ++s) p[s] = __ldg(pr + (size_t)s * g);
         const bool more = base + step < total;
-        if (more) load_idx_row16(idx + (size_t)(min(base + step + lane, total - 1) / chunks) * NS, jn, NS / 4);
+        if (more) {
+            const long long tn = min(base + step + lane, total - 1);
+            const long long ptn = tn / chunks;
+            load_idx_row16(idx + (size_t)ptn * NS, jn, NS / 4);
+            // tuning "l2pf" (default on): the NEXT item's peb block goes from DRAM to L2 while this item's walk runs.  A warp
+            // spends most of an item in the walk's dependent L2 round trips with nothing of its own in flight towards DRAM
+            // (12 warps per SM: ~27 KB in flight per SM on average, below what the HBM pipe needs); the bulk prefetch (copy
+            // engine, no LSU slot, no register, no shared memory) keeps the DRAM stream going: 480 -> 461 us at level 0,
+            // 149 -> 139 us at level 1, 80 -> 74 us at level 2 (profiles/r04b_kernel_bench_l2pf.txt).
+            if (HAS_PEB && pf && tn == ptn * chunks && base + step + lane < total)
+                l2_prefetch_bulk(peb + (size_t)ptn * NS * c, (unsigned)(NS * c * 4));
+        }
         // rowptr of the item after next (two rows ahead, like csr_walk_kernel)
         int nne = 0, nne_end = 0;
         if (base + 2 * step < total) {
@@ -821,15 +839,16 @@ extern "C" int aopt_gva_forward(int n, int nsample, int c, int g, const float *v
         const long long items = (long long)n * (c / 4);
         const int grid = stride_grid(items, kGvaBlock, 8);
         const bool ns_ok = aligned16(idx);  // the specialised kernels read the idx row as int4
+        const int pf = tuning(kTuneL2Prefetch) != 2;
         if (ns_ok && nsample == 16) {
             GVA_DISPATCH_NS(gl, 16, peb != nullptr, gva_forward_ns_kernel, items, as_stream(stream), (long long)n, c, g, value, peb,
-                            logits, idx, out, prob);
+                            logits, idx, out, prob, pf);
         } else if (ns_ok && nsample == 8) {
             GVA_DISPATCH_NS(gl, 8, peb != nullptr, gva_forward_ns_kernel, items, as_stream(stream), (long long)n, c, g, value, peb,
-                            logits, idx, out, prob);
+                            logits, idx, out, prob, pf);
         } else if (ns_ok && nsample == 32) {
             GVA_DISPATCH_NS(gl, 32, peb != nullptr, gva_forward_ns_kernel, items, as_stream(stream), (long long)n, c, g, value, peb,
-                            logits, idx, out, prob);
+                            logits, idx, out, prob, pf);
         } else {
             GVA_DISPATCH(gl, gva_forward_kernel, grid, as_stream(stream), (long long)n, nsample, c, g, value, peb,
                          logits, idx, out, prob);
@@ -939,15 +958,16 @@ extern "C" int aopt_gva_backward(int n, int nsample, int c, int g, const float *
         return aopt_gva_backward_value(n, nsample, c, g, grad_out, prob, rowptr, perm, grad_value, stream);
     }
     const long long items = (long long)n * (c / 4);
+    const int pf = tuning(kTuneL2Prefetch) != 2;
     if (nsample == 16) {
         GVA_DISPATCH_NS(gl, 16, peb != nullptr, gva_backward_fused_ns_kernel, items, as_stream(stream), (long long)n, c, g,
-                        grad_out, value, peb, prob, idx, rowptr, perm, grad_peb, grad_logits, grad_value);
+                        grad_out, value, peb, prob, idx, rowptr, perm, grad_peb, grad_logits, grad_value, pf);
     } else if (nsample == 8) {
         GVA_DISPATCH_NS(gl, 8, peb != nullptr, gva_backward_fused_ns_kernel, items, as_stream(stream), (long long)n, c, g,
-                        grad_out, value, peb, prob, idx, rowptr, perm, grad_peb, grad_logits, grad_value);
+                        grad_out, value, peb, prob, idx, rowptr, perm, grad_peb, grad_logits, grad_value, pf);
     } else {
         GVA_DISPATCH_NS(gl, 32, peb != nullptr, gva_backward_fused_ns_kernel, items, as_stream(stream), (long long)n, c, g,
-                        grad_out, value, peb, prob, idx, rowptr, perm, grad_peb, grad_logits, grad_value);
+                        grad_out, value, peb, prob, idx, rowptr, perm, grad_peb, grad_logits, grad_value, pf);
     }
     return check_launch();
 }

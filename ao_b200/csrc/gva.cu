@@ -133,8 +133,13 @@ template <int NS> __host__ __device__ constexpr int ns_block() { return NS >= 32
 
 // Gathered value rows.  Measured at level 0 on one box (A/B in the same process): forward 232 us with L2-only
 // copies (.cg) vs 244 us with L1-allocating ones (.ca); backward_query 399 us (.cg) vs 368 us (.ca).  Defaults
-// follow that; AOPT_GVA_GATHER=<fwd><bwd> with letters g / a overrides (e.g. "gg", "aa").
-__constant__ int g_gva_gather_ca = 2;   // bit 0: forward uses .ca, bit 1: backward_query uses .ca
+// follow that; AOPT_GVA_GATHER=<fwd><bwd>[<fused bwd>] with letters g / a overrides (e.g. "gg", "aa", "gaa").
+// The FUSED backward takes .cg: its L1 (~60 KB beside the staging slots) is what the CSR walk lives on — sector re-use of
+// the perm / probability / idx loads and the grad_out rows of neighbouring queries — and the value rows only evict that:
+// 457 -> 440 us at level 0 (profiles/r04d_kernel_bench_l1.txt).  The same run showed how much the walk depends on L1:
+// CTA shapes that push the shared-memory carve-out from 196 to 228 KB (L1 60 -> 28 KB) cost 27-76 %, and
+// L1::no_allocate on the "streamed" scalar loads 39 % (a 128-byte line serves 5 consecutive slots of a probability column).
+__constant__ int g_gva_gather_ca = 2;   // bit 0: forward uses .ca, bit 1: backward_query uses .ca, bit 2: fused backward uses .ca
 template <int WHICH>
 __device__ __forceinline__ void cp_async16_row(float4 *dst, const float *src) {
     if (g_gva_gather_ca & WHICH) cp_async16_gather(dst, src);
@@ -428,7 +433,7 @@ gva_backward_fused_ns_kernel(long long n, int c, int g, const float *__restrict_
         for (int s = 0; s < NS; ++s) j[s] = jn[s];
         const float *vbase = value + ch * 4;
 #pragma unroll
-        for (int s = 0; s < NS; ++s) cp_async16_row<2>(sv + s * BLK, vbase + (size_t)max(j[s], 0) * c);
+        for (int s = 0; s < NS; ++s) cp_async16_row<4>(sv + s * BLK, vbase + (size_t)max(j[s], 0) * c);
         if (HAS_PEB) {
             const float *pe = peb + (size_t)pt * NS * c + ch * 4;
 #pragma unroll
@@ -780,7 +785,7 @@ static void gva_gather_mode_init() {
     static const bool once = [] {
         const char *e = getenv("AOPT_GVA_GATHER");
         if (e && e[0] && e[1]) {
-            const int ca = (e[0] == 'a' ? 1 : 0) | (e[1] == 'a' ? 2 : 0);
+            const int ca = (e[0] == 'a' ? 1 : 0) | (e[1] == 'a' ? 2 : 0) | (e[2] == 'a' ? 4 : 0);
             cudaMemcpyToSymbol(g_gva_gather_ca, &ca, sizeof(int));
         }
         return true;

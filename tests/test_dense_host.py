@@ -74,3 +74,19 @@ def test_fused_dense_switch_and_thresholds(monkeypatch):
     monkeypatch.setenv("AOPT_RELFREE_MIN_ELEMS", "1e6")
     assert ptv2.relation_free_min_elems() == 1e6
     assert not ptv2.we_gather_enabled()
+
+
+def test_vote_accumulate_rejects_what_the_kernel_cannot_take():
+    """pointops.vote_accumulate (tester fragment vote, pointcept/engines/test.py:106-113) has no CPU path: host tensors and
+    malformed arguments are refused before anything is launched."""
+    from ao_b200.pointops import vote_accumulate
+
+    pred, logits, index = torch.zeros(10, 13), torch.randn(4, 13), torch.arange(4)
+    with pytest.raises(ValueError, match="CUDA"):
+        vote_accumulate(pred, logits, index)
+    with pytest.raises(ValueError, match="classes"):
+        vote_accumulate(pred, torch.randn(4, 12), index)
+    with pytest.raises(ValueError, match="one entry per logits row"):
+        vote_accumulate(pred, logits, torch.arange(3))
+    with pytest.raises(ValueError):
+        vote_accumulate(pred.double(), logits, index)

@@ -268,3 +268,19 @@ def test_grid_pool_restatement_on_hand_computed_fixture(oracle):
     assert np.array_equal(nc.numpy(), mean)            # the sums are exact in fp32, one IEEE division
     assert nf.tolist() == fx["feat_max"]
     assert arg.tolist() == fx["argmax"]
+
+
+# ------------------------------------------------------------------ tester fragment vote
+def test_vote_oracle_hand_example(oracle):
+    """pointcept/engines/test.py:106-113 on a case small enough to write out: two fragments of one batch, point 2 receives
+    a vote from both, point 3 from none; logits [0, ln 3] -> probabilities [0.25, 0.75]."""
+    ln3 = float(np.log(3.0))
+    logits = torch.tensor([[0.0, ln3], [ln3, 0.0], [0.0, 0.0],      # fragment 0 votes for points 0, 2, 1
+                           [0.0, ln3], [5.0, 5.0]])                  # fragment 1 votes for points 2, 4
+    index = torch.tensor([0, 2, 1, 2, 4])
+    pred = oracle.vote_accumulate(torch.zeros(5, 2), logits, index, [3, 5])
+    want = torch.tensor([[0.25, 0.75], [0.5, 0.5], [0.75 + 0.25, 0.25 + 0.75], [0.0, 0.0], [0.5, 0.5]])
+    assert torch.allclose(pred, want, atol=1e-7)
+    # a second batch accumulates on top (the accumulator lives across batches, :102-113)
+    pred = oracle.vote_accumulate(pred, logits[:1], index[:1], [1])
+    assert torch.allclose(pred[0], torch.tensor([0.5, 1.5]), atol=1e-7)

@@ -48,3 +48,30 @@ def test_b200_arm_has_no_cpu_fallback():
     out = _run(["--steps", "1", "--warmup", "0"])
     assert out.returncode != 0 and out.stdout.strip() == ""
     assert "no CUDA device" in out.stderr
+
+
+@pytest.mark.parametrize("cfg,points", [("s3dis4", 320000), ("s3dis8", 640000), ("scannet150k", 450000), ("kitti120k", None)])
+def test_committed_bench_lines_keep_the_contract_and_add_up(cfg, points):
+    """The end-of-round lines under profiles/ (written on a B200 by scripts/gpu_r04f.sh) carry every key of the contract and
+    their numbers are consistent with each other: value = points / time, roofline.frac = achieved / peak with the
+    algorithmic bytes of the dominant launch, e2e measured with real host copies, launches counted."""
+    path = os.path.join(ROOT, "profiles", f"r04f_bench_{cfg}.json")
+    d = json.loads([l for l in open(path).read().splitlines() if l.strip()][-1])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
+        assert key in d, key
+    assert d["metric"] == "ptv2_pointops_fwd_bwd_throughput" and d["unit"] == "Mpoints/s" and d["dtype"] == "f32"
+    assert d["n_gpus"] == 1 and d["warmup"] >= 3 and d["vs_baseline"] is None and d["data"] == "synthetic"
+    n0 = d["level_sizes"][0]
+    if points is not None:
+        assert n0 == points
+    assert d["value"] == pytest.approx(n0 / (d["ms_per_step"] * 1e-3) / 1e6, rel=1e-6)
+    r = d["roofline"]
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and r["frac"] == pytest.approx(r["achieved"] / r["peak"], abs=2e-4)
+    assert r["achieved"] == pytest.approx(r["alg_bytes_per_launch"] / (r["us_per_launch"] * 1e-6) / 1e9, rel=2e-3)
+    e = d["e2e"]
+    assert e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and 0 < e["value"] <= d["value"] * 1.02
+    assert d["gpu_launches"] >= 100 * d["steps"]          # ~170-190 library kernels per schedule step
+    assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and 0 < cb["value"] < 1.0

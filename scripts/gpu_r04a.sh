@@ -1,6 +1,8 @@
 #!/bin/bash
 # round 2, call 4A: bulk L2 prefetch of the next work item (tuning "l2pf") in gva_forward / gva_backward (fused) /
 # relation_backward — parity with the switch on, then A/B per operator and per step; tester vote kernel test
+# NOTE: at the time of this call AOPT_L2PF=1 also switched the next-item prefetch on in relation_backward; that part was
+# measured slower and removed — today the switch covers the GVA kernels only (default on, AOPT_L2PF=0 = off)
 TAG=${1:-r04a}
 O=gpurun_out/$TAG
 mkdir -p $O

@@ -1,6 +1,8 @@
 #!/bin/bash
 # round 2, call 4B: A/B of (a) the peb-direct fused GVA backward (AOPT_GVA_PD=1: NS smem slots per thread, 4 CTAs per SM),
 # (b) relation_backward with the item's own rows bulk-prefetched into L2 (AOPT_RELBWD_PF=1); default = l2pf on for the GVA kernels
+# NOTE: AOPT_GVA_PD and AOPT_RELBWD_PF selected experiment kernels that were measured slower and removed again
+# (results: profiles/r04b_kernel_bench_l2pf.txt); the script is kept as the record of what was run
 TAG=${1:-r04b}
 O=gpurun_out/$TAG
 mkdir -p $O

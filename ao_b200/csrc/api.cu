@@ -22,7 +22,7 @@ int check_launch(int kernels) {
 
 static std::atomic<int> g_tuning[kTuneCount];
 static std::atomic<bool> g_tuning_init{false};
-static const char *const kTuneNames[kTuneCount] = {"csr_impl", "gva_bwd", "voxel_sort", "knn_topk", "knn_pend", "knn_sample", "pdl", "l2pf"};
+static const char *const kTuneNames[kTuneCount] = {"csr_impl", "gva_bwd", "voxel_sort", "knn_topk", "knn_pend", "knn_sample", "pdl", "l2pf", "knn_site"};
 
 static void tuning_init() {
     if (g_tuning_init.exchange(true)) return;
@@ -39,6 +39,7 @@ static void tuning_init() {
     g_tuning[kTuneKnnSample] = env("AOPT_KNN_SAMPLE", "bbox", "sampled");
     g_tuning[kTunePdl] = env("AOPT_PDL", "1", "0");
     g_tuning[kTuneL2Prefetch] = env("AOPT_L2PF", "1", "0");
+    g_tuning[kTuneKnnSite] = env("AOPT_KNN_SITE", "1", "0");
 }
 
 int tuning(int which) {

@@ -26,7 +26,8 @@ enum Tuning { kTuneCsrImpl = 0,   // AOPT_CSR_IMPL:   1 = radix sort, 2 = count 
               kTuneKnnSample = 5, // AOPT_KNN_SAMPLE: 1 = cell edge from the bounding box (no density sample), 0 / 2 = sampled r_k (default)
               kTunePdl = 6,       // AOPT_PDL:        1 = programmatic dependent launch inside the small-kernel chains, 2 = off
               kTuneL2Prefetch = 7, // AOPT_L2PF:     0 / 1 = the GVA kernels request the next work item's (k,C) peb block into L2 with a bulk prefetch (default), 2 = off
-              kTuneCount = 8 };
+              kTuneKnnSite = 8,    // AOPT_KNN_SITE:  1 = GRID query kernel with a single insert site (knn_grid1_kernel), 0 / 2 = knn_grid_kernel (default)
+              kTuneCount = 9 };
 int tuning(int which);
 
 // ---- programmatic dependent launch (PDL) for chains of small dependent kernels -----------------------------------

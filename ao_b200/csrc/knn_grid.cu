@@ -529,6 +529,113 @@ knn_grid_kernel(int m, int b, int nsample, const float *__restrict__ new_xyz,
     top.store(idx_out + (size_t)row * nsample, dist2_out + (size_t)row * nsample, nsample, root);
 }
 
+// ---- the same search with ONE insert site (tuning "knn_site" = 1, AOPT_KNN_SITE=1; experiment) --------------------------
+// ptxas outlines the list insert of knn_grid_kernel — 20 inlined offer() sites: four per batch plus the tail loop, at four scan
+// sites — into a subroutine (SASS: 16 CALL.REL.NOINC, one RET, and the STL / LDL pairs that `ptxas -v` reports as a 32-byte
+// spill frame whatever the register limit).  Here the traversal produces at most two candidate runs per grid row and ONE loop
+// consumes them: batches of four with the tail masked to +inf instead of a tail loop, the accepted batch offered by a
+// four-trip loop that is not unrolled, and the exhaustive scan of a sparse neighbourhood folded in as one more "ring" whose
+// single run is the whole scene.  Same candidates, same LEX ranking: identical results.
+template <int K, bool SELF>
+__global__ void __launch_bounds__(kQueryBlock)
+knn_grid1_kernel(int m, int b, int nsample, const float *__restrict__ new_xyz,
+                 const int *__restrict__ new_offset, const GridDesc *__restrict__ desc,
+                 const int *__restrict__ cells, const float4 *__restrict__ sorted,
+                 int *__restrict__ idx_out, float *__restrict__ dist2_out, bool root) {
+    pdl_wait();
+    const int t = blockIdx.x * kQueryBlock + threadIdx.x;
+    if (t >= m) return;
+    const int sc = find_segment(t, new_offset, b);
+    float qx = 0.f, qy = 0.f, qz = 0.f;
+    int row = t;
+    if (SELF) {
+        if (sc < b) {
+            const float4 me = __ldg(sorted + t);
+            qx = me.x; qy = me.y; qz = me.z;
+            row = __float_as_int(me.w);
+        }
+    } else {
+        qx = __ldg(new_xyz + (size_t)t * 3); qy = __ldg(new_xyz + (size_t)t * 3 + 1);
+        qz = __ldg(new_xyz + (size_t)t * 3 + 2);
+    }
+    TopK<K, true> top;
+    top.init();
+    if (sc < b) {
+        const GridDesc g = desc[sc];
+        if (g.end > g.start) {
+            const int cx = cell_coord(qx, g.ox, g.inv_h, g.nx);
+            const int cy = cell_coord(qy, g.oy, g.inv_h, g.ny);
+            const int cz = cell_coord(qz, g.oz, g.inv_h, g.nz);
+            const int *cs = cells + g.cell_base;
+            bool done = false;
+            for (int r = 1; r <= kMaxRing + 1 && !done; ++r) {
+                const bool all = r > kMaxRing;   // no stop within kMaxRing shells: start over and scan the whole scene
+                if (all) top.init();
+                const int side = all ? 0 : 2 * r;
+                for (int iz = 0; iz <= side; ++iz) {
+                    const int dz = (iz & 1) ? -((iz + 1) >> 1) : (iz >> 1);
+                    const int z = cz + dz;
+                    if (!all && (z < 0 || z >= g.nz)) continue;
+                    for (int iy = 0; iy <= side; ++iy) {
+                        const int dy = (iy & 1) ? -((iy + 1) >> 1) : (iy >> 1);
+                        const int y = cy + dy;
+                        if (!all && (y < 0 || y >= g.ny)) continue;
+                        int a0 = 0, e0 = 0, a1 = 0, e1 = 0;
+                        if (all) {
+                            a0 = g.start; e0 = g.end;
+                        } else {
+                            const int rowbase = (z * g.ny + y) * g.nx;
+                            const bool full = (r == 1) || max(abs(dz), abs(dy)) == r;
+                            if (full) {
+                                const int x0 = max(cx - r, 0), x1 = min(cx + r, g.nx - 1);
+                                a0 = __ldg(cs + rowbase + x0); e0 = __ldg(cs + rowbase + x1 + 1);
+                            } else {
+                                if (cx - r >= 0) { a0 = __ldg(cs + rowbase + cx - r); e0 = __ldg(cs + rowbase + cx - r + 1); }
+                                if (cx + r <= g.nx - 1) { a1 = __ldg(cs + rowbase + cx + r); e1 = __ldg(cs + rowbase + cx + r + 1); }
+                            }
+                        }
+#pragma unroll 1
+                        for (int rep = 0; rep < 2; ++rep) {
+                            const int a = rep ? a1 : a0, e = rep ? e1 : e0;
+                            for (int i = a; i < e; i += 4) {
+                                const float4 c0 = __ldg(sorted + i), c1 = __ldg(sorted + min(i + 1, e - 1)),
+                                             c2 = __ldg(sorted + min(i + 2, e - 1)), c3 = __ldg(sorted + min(i + 3, e - 1));
+                                const float d0 = dist2_ref(qx, qy, qz, c0.x, c0.y, c0.z);
+                                const float d1 = i + 1 < e ? dist2_ref(qx, qy, qz, c1.x, c1.y, c1.z) : 3.0e38f;
+                                const float d2 = i + 2 < e ? dist2_ref(qx, qy, qz, c2.x, c2.y, c2.z) : 3.0e38f;
+                                const float d3 = i + 3 < e ? dist2_ref(qx, qy, qz, c3.x, c3.y, c3.z) : 3.0e38f;
+                                if (fminf(fminf(d0, d1), fminf(d2, d3)) <= top.worst()) {
+#pragma unroll 1
+                                    for (int u = 0; u < 4; ++u) {
+                                        const float du = u == 0 ? d0 : u == 1 ? d1 : u == 2 ? d2 : d3;
+                                        const float wu = u == 0 ? c0.w : u == 1 ? c1.w : u == 2 ? c2.w : c3.w;
+                                        top.offer(du, __float_as_int(wu));   // masked slots carry 3e38: never accepted
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+                if (all) break;
+                float bound = 3.0e38f;
+                if (cx - r > 0) bound = fminf(bound, qx - (g.ox + (float)(cx - r) * g.h));
+                if (cx + r < g.nx - 1) bound = fminf(bound, (g.ox + (float)(cx + r + 1) * g.h) - qx);
+                if (cy - r > 0) bound = fminf(bound, qy - (g.oy + (float)(cy - r) * g.h));
+                if (cy + r < g.ny - 1) bound = fminf(bound, (g.oy + (float)(cy + r + 1) * g.h) - qy);
+                if (cz - r > 0) bound = fminf(bound, qz - (g.oz + (float)(cz - r) * g.h));
+                if (cz + r < g.nz - 1) bound = fminf(bound, (g.oz + (float)(cz + r + 1) * g.h) - qz);
+                if (bound > 1.0e38f) {
+                    done = true;
+                } else {
+                    const float bs = bound - g.margin;
+                    if (bs > 0.f && top.worst() < bs * bs) done = true;
+                }
+            }
+        }
+    }
+    top.store(idx_out + (size_t)row * nsample, dist2_out + (size_t)row * nsample, nsample, root);
+}
+
 // ---- host side -------------------------------------------------------------------------------------
 static size_t a256(size_t x) { return (x + 255) & ~(size_t)255; }
 
@@ -594,6 +701,17 @@ static void launch_query_t(bool self, int m, int b, int nsample, const float *ne
 template <int K>
 static void launch_query(bool self, int m, int b, int nsample, const float *new_xyz, const int *new_offset,
                          const GridWs &w, int *idx, float *dist2, bool root, cudaStream_t st) {
+    if (tuning(kTuneKnnSite) == 1 && tuning(kTuneKnnTopk) != 1 && tuning(kTuneKnnPend) != 1) {
+        const int grid = div_up(m, kQueryBlock);
+        const bool pdl = tuning(kTunePdl) != 2;
+        if (self)
+            launch_chain(pdl, knn_grid1_kernel<K, true>, grid, kQueryBlock, 0, st, m, b, nsample, new_xyz, new_offset,
+                         (const GridDesc *)w.desc, (const int *)w.cells, (const float4 *)w.sorted, idx, dist2, root);
+        else
+            launch_chain(pdl, knn_grid1_kernel<K, false>, grid, kQueryBlock, 0, st, m, b, nsample, new_xyz, new_offset,
+                         (const GridDesc *)w.desc, (const int *)w.cells, (const float4 *)w.sorted, idx, dist2, root);
+        return;
+    }
     if constexpr (K >= 8) {
         const bool pend = tuning(kTuneKnnPend) == 1;
         if (tuning(kTuneKnnTopk) == 1) {

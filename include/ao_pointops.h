@@ -74,8 +74,9 @@ unsigned long long aopt_kernel_launches(void);
  * 2 = sampled, "pdl" 1 = programmatic dependent launch inside the small-kernel chains / 2 = off, "knn_topk" 1 = top-k of the
  * GRID query kernel as a shared-memory heap / 2 = as a sorted list in registers, "knn_pend" 1 = accepted candidates
  * go through a per-lane pending list drained every eight candidates / 2 = inserted in place, "l2pf" 1 = the GVA kernels
- * request the next work item's peb block into L2 with a bulk prefetch (the default) / 2 = off; 0 = library default.
- * Initial values come from AOPT_CSR_IMPL / AOPT_GVA_BWD / AOPT_VOXEL_SORT / AOPT_KNN_SAMPLE / AOPT_PDL / AOPT_L2PF / AOPT_KNN_TOPK /
+ * request the next work item's peb block into L2 with a bulk prefetch (the default) / 2 = off, "knn_site" 1 = GRID query kernel with a
+ * single scan / insert site (knn_grid1_kernel) / 2 = the default kernel; 0 = library default.
+ * Initial values come from AOPT_CSR_IMPL / AOPT_GVA_BWD / AOPT_VOXEL_SORT / AOPT_KNN_SAMPLE / AOPT_PDL / AOPT_L2PF / AOPT_KNN_SITE / AOPT_KNN_TOPK /
  * AOPT_KNN_PEND. */
 int aopt_set_tuning(const char *name, int value);
 

@@ -63,6 +63,32 @@ def test_heap_container_equals_register_list(oracle, k):
     assert np.array_equal(hi, ri) and np.array_equal(hd, rd)
 
 
+@pytest.mark.parametrize("k", [1, 3, 8, 16, 32])
+def test_single_site_query_kernel_equals_the_default(oracle, k):
+    """Tuning "knn_site" = 1 selects knn_grid1_kernel (one scan and one insert site, tail masked instead of a tail loop,
+    the exhaustive fallback folded into the ring loop): same bits as the default kernel and the oracle, self and cross
+    searches, duplicates, scenes shorter than k."""
+    from ao_b200 import _lib, scenes
+
+    coord, _, offset = scenes.small_batch(seed=70 + k, sizes=(3000, 5, 4100, 257))
+    coord[100:140] = coord[60:100]
+    rng = np.random.default_rng(k)
+    query = (coord[rng.integers(0, coord.shape[0], 900)] + rng.normal(0, 0.05, (900, 3))).astype(np.float32)
+    q_off = np.array([300, 300, 650, 900], np.int32)             # scene 1 has no queries
+    try:
+        _lib.set_tuning("knn_site", 1)
+        si, sd = run("grid", k, coord, offset)
+        sci, scd = run("grid", k, coord, offset, query, q_off)
+    finally:
+        _lib.set_tuning("knn_site", 0)
+    di, dd = run("grid", k, coord, offset)
+    dci, dcd = run("grid", k, coord, offset, query, q_off)
+    assert np.array_equal(si, di) and np.array_equal(sd, dd)
+    assert np.array_equal(sci, dci) and np.array_equal(scd, dcd)
+    ri, rd = oracle.knn_query(k, coord, offset, rule="lex")
+    assert np.array_equal(si, ri) and np.array_equal(sd, rd)
+
+
 @pytest.mark.parametrize("method", ["tile", "grid", "auto"])
 def test_no_candidates_gives_padding(method):
     """Queries against an EMPTY candidate set (n = 0): every row is padding (idx -1, dist2 1e10), whichever method is
